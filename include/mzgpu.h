@@ -1,0 +1,395 @@
+/*
+ * mzgpu.h — C ABI of the B200-native differential-dataflow operator core.
+ *
+ * This is the drop-in boundary for Materialize's compute-layer hot path
+ * (SURVEY.md §8b).  Every entry point replaces one piece of the Rust trait
+ * surface that `mz_compute::render` programs against; the reference interface
+ * each one stands in for is cited as file:line under /root/reference.
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD rows, pointers + sizes, int32 status codes.
+ *     No exceptions or aborts cross this boundary.
+ *   - rows are fixed-width little-endian PODs (R16/R32/R40/RA/ROUT below).
+ *   - times are totally ordered u64 (mz_repr::Timestamp, src/repr/src/timestamp.rs:41-45).
+ *     A frontier (Antichain<u64>) is one u64; MZGPU_FRONTIER_EMPTY is the empty
+ *     antichain ("no more times").
+ *   - diffs are i64 with wrapping arithmetic (mz_ore::Overflowing<i64> in
+ *     release mode, src/ore/src/overflowing.rs:24-35).
+ *   - a `mzgpu_ctx` and everything created from it is confined to the thread
+ *     that created it (one ctx per timely worker; the reference's operators
+ *     are single-threaded Rc<RefCell<..>>, src/compute/src/typedefs.rs:46).
+ *   - row pointers carry a memory-space tag (MZGPU_MEM_HOST / MZGPU_MEM_DEVICE).
+ *   - variable-size results are written to a library-owned device buffer
+ *     (`mzgpu_buf`) that the caller downloads or feeds to the next operator.
+ */
+#ifndef MZGPU_H
+#define MZGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status */
+#define MZGPU_OK 0
+#define MZGPU_E_INVALID (-1)     /* bad argument / protocol violation            */
+#define MZGPU_E_CUDA (-2)        /* sticky CUDA failure: caller panics the worker */
+#define MZGPU_E_CAPACITY (-3)    /* caller buffer too small; *n_out = required    */
+#define MZGPU_E_UNSUPPORTED (-4) /* plan shape outside the fixed-width subset     */
+#define MZGPU_E_NCCL (-5)        /* sticky NCCL failure                           */
+#define MZGPU_E_FRONTIER (-6)    /* batch/spine frontier contract violated        */
+
+#define MZGPU_MEM_HOST 0
+#define MZGPU_MEM_DEVICE 1
+
+#define MZGPU_FRONTIER_EMPTY UINT64_MAX
+
+/* ------------------------------------------------------------------ rows */
+/* (u64 key, i64 diff): BASELINE config 1, `consolidate` on Vec<(u64,i64)>
+ * (src/ore/src/iter.rs:260-268). */
+typedef struct mzgpu_r16 {
+  uint64_t key;
+  int64_t diff;
+} mzgpu_r16;
+
+/* ((key, val), time, diff): the update triple of every arrangement
+ * (KeyValBatcher input, src/compute/src/typedefs.rs:121-126). */
+typedef struct mzgpu_r32 {
+  uint64_t key;
+  uint64_t val;
+  uint64_t time;
+  int64_t diff;
+} mzgpu_r32;
+
+/* join_core result with the identity closure: (key, val1, val2), time, diff
+ * (L: FnMut(Key, Val1, Val2), src/compute/src/render/join/mz_join_core.rs:66). */
+typedef struct mzgpu_r40 {
+  uint64_t key;
+  uint64_t val1;
+  uint64_t val2;
+  uint64_t time;
+  int64_t diff;
+} mzgpu_r40;
+
+/* Accumulable-reduce update: key -> ((), time, (Vec<Accum>, Diff)) with one
+ * accumulated column (src/compute/src/render/reduce.rs:1313-1334,1861-1903).
+ *   total     = Diff component of the pair
+ *   non_nulls = Accum::*.non_nulls
+ *   acc       = Accum::*.accum as i128 (lo/hi), wrapping
+ *   pos_infs / neg_infs / nans = Accum::Float counters (0 for integer SUM) */
+typedef struct mzgpu_racc {
+  uint64_t key;
+  uint64_t time;
+  int64_t total;
+  int64_t non_nulls;
+  uint64_t acc_lo;
+  int64_t acc_hi;
+  int64_t pos_infs;
+  int64_t neg_infs;
+  int64_t nans;
+  int64_t _pad; /* keeps the row 16-byte aligned (80 B) */
+} mzgpu_racc;
+
+/* Reduce output update: (key, finalized aggregates), time, diff (+1/-1)
+ * (finalize_accum, src/compute/src/render/reduce.rs:1671-1835).
+ *   count  = COUNT(col)            = Int64(non_nulls)
+ *   sum_lo/sum_hi = SUM(int64)     = i128 (numeric from i128);
+ *                   SUM(f64)       = f64 bits in sum_lo, sum_hi = 0
+ *   flags  bit0: SUM is NULL (total>0 && accum.is_zero())
+ *          bit1: error row "net-zero records with non-zero accumulation"
+ *                (reduce.rs:1418-1429) */
+typedef struct mzgpu_rout {
+  uint64_t key;
+  int64_t count;
+  uint64_t sum_lo;
+  int64_t sum_hi;
+  uint64_t flags;
+  uint64_t time;
+  int64_t diff;
+  int64_t _pad;
+} mzgpu_rout;
+
+/* ---------------------------------------------------------- descriptors */
+/* Batch description: Description{lower, upper, since}
+ * (differential_dataflow::trace::Description; A3 in SURVEY.md). */
+typedef struct mzgpu_desc {
+  uint64_t lower;
+  uint64_t upper;
+  uint64_t since;
+} mzgpu_desc;
+
+/* Closure descriptor: the fixed-width stand-in for JoinClosure
+ * (src/compute-types/src/plan/join.rs:50-82) and for the key/val plans of
+ * render_reduce (src/compute-types/src/plan/reduce.rs:517-522).  Columns are
+ * bit-fields of the three 64-bit source words (key, stream val, lookup val).
+ *   out.key = OR over key_fields of  field(src) << dst_shift
+ *   out.val = OR over val_fields of  field(src) << dst_shift
+ *             or, if expr_kind == MZGPU_EXPR_MUL_CONST_MINUS,
+ *             field(expr_a) * (expr_c - field(expr_b))     (wrapping i64)
+ *   the row is dropped unless every filter holds.
+ * Anything richer is MZGPU_E_UNSUPPORTED at plan time (the host keeps its own
+ * path for such dataflows; there is no CPU fallback inside the core). */
+#define MZGPU_SRC_KEY 0
+#define MZGPU_SRC_VAL1 1 /* stream row value   */
+#define MZGPU_SRC_VAL2 2 /* lookup row value   */
+
+typedef struct mzgpu_field {
+  uint8_t src;       /* MZGPU_SRC_*                 */
+  uint8_t shift;     /* right shift of source word  */
+  uint8_t bits;      /* field width 1..64           */
+  uint8_t dst_shift; /* left shift in the out word  */
+} mzgpu_field;
+
+#define MZGPU_CMP_EQ 0
+#define MZGPU_CMP_NE 1
+#define MZGPU_CMP_LT 2
+#define MZGPU_CMP_LE 3
+#define MZGPU_CMP_GT 4
+#define MZGPU_CMP_GE 5
+
+typedef struct mzgpu_filter {
+  mzgpu_field field; /* dst_shift unused */
+  uint32_t op;       /* MZGPU_CMP_*, unsigned compare */
+  uint64_t rhs;
+} mzgpu_filter;
+
+#define MZGPU_EXPR_NONE 0
+#define MZGPU_EXPR_MUL_CONST_MINUS 1 /* a * (c - b) */
+
+#define MZGPU_MAX_FIELDS 6
+#define MZGPU_MAX_FILTERS 4
+
+typedef struct mzgpu_closure {
+  uint32_t n_key_fields;
+  uint32_t n_val_fields;
+  uint32_t n_filters;
+  uint32_t expr_kind;
+  mzgpu_field key_fields[MZGPU_MAX_FIELDS];
+  mzgpu_field val_fields[MZGPU_MAX_FIELDS];
+  mzgpu_filter filters[MZGPU_MAX_FILTERS];
+  mzgpu_field expr_a;
+  mzgpu_field expr_b;
+  uint64_t expr_c;
+} mzgpu_closure;
+
+/* half_join time comparison: `le` if source relation < lookup relation else
+ * `lt` (src/compute/src/render/join/delta_join.rs:204-224). */
+#define MZGPU_HALFJOIN_LE 0
+#define MZGPU_HALFJOIN_LT 1
+
+/* Aggregate descriptor for the accumulable reduce (AccumulablePlan,
+ * src/compute-types/src/plan/reduce.rs:146-158).  One accumulated column. */
+#define MZGPU_AGG_COUNT_SUM_I64 0 /* COUNT(val), SUM(val) with val: int64   */
+#define MZGPU_AGG_COUNT_SUM_F64 1 /* COUNT(val), SUM(val) with val: float64 */
+
+/* ---------------------------------------------------------------- handles */
+typedef struct mzgpu_ctx mzgpu_ctx;         /* one per timely worker / GPU            */
+typedef struct mzgpu_buf mzgpu_buf;         /* library-owned growable device row buffer */
+typedef struct mzgpu_batcher mzgpu_batcher; /* MergeBatcher analogue                  */
+typedef struct mzgpu_batch mzgpu_batch;     /* Rc<OrdValBatch> analogue (refcounted)  */
+typedef struct mzgpu_spine mzgpu_spine;     /* Spine / TraceAgent analogue            */
+typedef struct mzgpu_join mzgpu_join;       /* mz_join_core operator state            */
+typedef struct mzgpu_reduce mzgpu_reduce;   /* accumulable reduce operator state      */
+
+/* ---------------------------------------------------------------- context */
+/* One context per timely worker thread: device ordinal, worker index, peers
+ * (TimelyConfig, src/cluster-client/src/client.rs:19-41). */
+int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_t peers, mzgpu_ctx** out);
+void mzgpu_ctx_destroy(mzgpu_ctx* ctx);
+/* Thread-local message for the last failing call on this ctx (never NULL). */
+const char* mzgpu_last_error(mzgpu_ctx* ctx);
+/* Block until all queued device work of this ctx is complete. */
+int32_t mzgpu_ctx_sync(mzgpu_ctx* ctx);
+/* Counters for the metrics the reference exports per arrangement
+ * (src/compute/src/extensions/arrange.rs:210-308) plus kernel launch count. */
+typedef struct mzgpu_stats {
+  uint64_t kernel_launches;
+  uint64_t device_bytes_in_use;
+  uint64_t device_bytes_peak;
+  uint64_t rows_in;
+  uint64_t rows_out;
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} mzgpu_stats;
+int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out);
+/* The CUDA stream all of this ctx's work is issued on (a cudaStream_t), so a
+ * host harness can bracket it with its own events. */
+void* mzgpu_ctx_stream(mzgpu_ctx* ctx);
+
+/* ------------------------------------------------------------ row buffers */
+#define MZGPU_ROW_R16 16
+#define MZGPU_ROW_R32 32
+#define MZGPU_ROW_R40 40
+#define MZGPU_ROW_RACC 80
+#define MZGPU_ROW_ROUT 64
+
+int32_t mzgpu_buf_new(mzgpu_ctx* ctx, uint32_t row_bytes, mzgpu_buf** out);
+void mzgpu_buf_free(mzgpu_buf* buf);
+uint64_t mzgpu_buf_len(const mzgpu_buf* buf);
+uint32_t mzgpu_buf_row_bytes(const mzgpu_buf* buf);
+/* Device pointer to the rows (valid until the next call that writes `buf`). */
+void* mzgpu_buf_device_ptr(mzgpu_buf* buf);
+/* Replace the contents with `n` rows from host or device memory. */
+int32_t mzgpu_buf_upload(mzgpu_buf* buf, const void* rows, uint64_t n, int32_t mem);
+/* Append `n` rows. */
+int32_t mzgpu_buf_append(mzgpu_buf* buf, const void* rows, uint64_t n, int32_t mem);
+/* Copy rows out; MZGPU_E_CAPACITY (with *n_out = len) if cap is too small. */
+int32_t mzgpu_buf_download(mzgpu_buf* buf, void* rows, uint64_t cap, int32_t mem, uint64_t* n_out);
+int32_t mzgpu_buf_clear(mzgpu_buf* buf);
+
+/* ---------------------------------------------------- a1: consolidation */
+/* differential_dataflow::consolidation::consolidate on Vec<(u64,i64)>:
+ * sort by key, sum diffs of equal keys, drop zeros (callers e.g.
+ * src/compute/src/render/join/delta_join.rs:649; pinned by
+ * src/ore/src/iter.rs:260-268).  In place; *n_out = surviving rows. */
+int32_t mzgpu_consolidate_r16(mzgpu_ctx* ctx, mzgpu_r16* rows, uint64_t n, int32_t mem,
+                              uint64_t* n_out);
+/* consolidate_updates on Vec<((K,V),T,R)>: sort by (key,val,time), sum, drop
+ * zeros (src/compute/src/render/join/mz_join_core.rs:563; reference model
+ * src/timely-util/src/columnar/batcher.rs:1116-1130). */
+int32_t mzgpu_consolidate_r32(mzgpu_ctx* ctx, mzgpu_r32* rows, uint64_t n, int32_t mem,
+                              uint64_t* n_out);
+/* Same on a device buffer (R16 / R32 / R40 / RACC by row_bytes), in place. */
+int32_t mzgpu_buf_consolidate(mzgpu_buf* buf);
+
+/* ------------------------------------------ a2-a5: batcher and batches */
+/* Batcher::new (src/timely-util/src/operator.rs:572-575).  row_bytes selects
+ * R32 (KeyValBatcher) or RACC (the accumulable arrangement's batcher). */
+int32_t mzgpu_batcher_new(mzgpu_ctx* ctx, uint32_t row_bytes, mzgpu_batcher** out);
+void mzgpu_batcher_free(mzgpu_batcher* b);
+/* Batcher::push_container: sort + consolidate the container into a chain and
+ * keep chains geometric (Chunker::push_into,
+ * src/timely-util/src/columnar/batcher.rs:65-122; Merger::merge :635-753). */
+int32_t mzgpu_batcher_push(mzgpu_batcher* b, const void* rows, uint64_t n, int32_t mem);
+/* Batcher::seal::<Builder>(upper): merge all chains, ship updates with
+ * !upper.less_equal(time), keep the rest (InternalMerge::extract,
+ * src/timely-util/src/columnation.rs:636-655), build the batch with
+ * Description{lower = previous upper, upper, since = 0}.  *new_lower is the
+ * batcher frontier afterwards (min kept time or MZGPU_FRONTIER_EMPTY). */
+int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_batch** batch_out,
+                           uint64_t* new_lower);
+/* Batcher::frontier (operator.rs:618-631). */
+uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b);
+/* Updates currently buffered. */
+uint64_t mzgpu_batcher_len(const mzgpu_batcher* b);
+
+/* Build a batch directly from unsorted updates with an explicit description
+ * (Builder::seal, operator.rs:647-677): sort + consolidate + index. */
+int32_t mzgpu_batch_build(mzgpu_ctx* ctx, uint32_t row_bytes, const void* rows, uint64_t n,
+                          int32_t mem, mzgpu_desc desc, mzgpu_batch** out);
+uint64_t mzgpu_batch_len(const mzgpu_batch* b);  /* Batch::len = #updates */
+uint64_t mzgpu_batch_keys(const mzgpu_batch* b); /* distinct keys         */
+mzgpu_desc mzgpu_batch_desc(const mzgpu_batch* b);
+void mzgpu_batch_retain(mzgpu_batch* b);  /* Rc::clone */
+void mzgpu_batch_release(mzgpu_batch* b); /* drop      */
+/* Cursor walk of the whole batch in (key,val,time) order into caller memory. */
+int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, int32_t mem,
+                           uint64_t* n_out);
+/* Batch::Merger::{begin_merge,work,done} in one call (a7): merge two adjacent
+ * batches (b1.upper == b2.lower), advance times by `since`, consolidate. */
+int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t since, mzgpu_batch** out);
+
+/* --------------------------------------------- a6, a8, a14: the spine */
+/* Spine::new with the fuel multiplier `effort` (spine_fueled; in-tree fork
+ * src/persist-client/src/internal/trace.rs:1668-1691). */
+int32_t mzgpu_spine_new(mzgpu_ctx* ctx, uint32_t row_bytes, uint32_t effort, mzgpu_spine** out);
+void mzgpu_spine_free(mzgpu_spine* s);
+/* Trace::insert (trace.rs:1737-1770). Takes a reference on `batch`. */
+int32_t mzgpu_spine_insert(mzgpu_spine* s, mzgpu_batch* batch);
+/* Trace::exert (trace.rs:1698-1727); *did_work mirrors its bool result. */
+int32_t mzgpu_spine_exert(mzgpu_spine* s, uint64_t effort, int32_t* did_work);
+/* Materialize's ExertionLogic (src/cluster/src/client.rs:227-254): returns the
+ * effort to exert now (1000) or 0. */
+uint64_t mzgpu_spine_exert_logic(const mzgpu_spine* s, uint32_t proportionality);
+/* TraceReader::{set,get}_{logical,physical}_compaction
+ * (src/compute/src/arrangement/manager.rs:174-219). */
+int32_t mzgpu_spine_set_logical_compaction(mzgpu_spine* s, uint64_t frontier);
+int32_t mzgpu_spine_set_physical_compaction(mzgpu_spine* s, uint64_t frontier);
+uint64_t mzgpu_spine_get_logical_compaction(const mzgpu_spine* s);
+uint64_t mzgpu_spine_get_physical_compaction(const mzgpu_spine* s);
+/* TraceReader::read_upper (mz_join_core.rs:337). */
+uint64_t mzgpu_spine_read_upper(const mzgpu_spine* s);
+/* cursor_through(upper): the batches whose upper <= `upper`, oldest first
+ * (mz_join_core.rs:243-246).  Borrowed pointers, valid until the next call
+ * that mutates the spine.  MZGPU_E_CAPACITY if cap is too small. */
+int32_t mzgpu_spine_batches_through(mzgpu_spine* s, uint64_t upper, mzgpu_batch** batches,
+                                    uint32_t cap, uint32_t* n_out);
+/* Layer structure for tests against the reference's datadriven traces
+ * (src/persist-client/tests/trace/compaction): for each layer, largest first,
+ * writes {n_batches, len(b0), len(b1), merge_remaining_work}. */
+int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint32_t cap_layers,
+                           uint32_t* n_layers);
+/* as_collection / walk_cursor (src/compute/src/render/context.rs:1299-1355):
+ * the consolidated contents of the whole trace, times advanced to `since`. */
+int32_t mzgpu_spine_export(mzgpu_spine* s, mzgpu_buf* out);
+
+/* ------------------------------------------------------ a9: join_core */
+/* mz_join_core over two arrangements (mz_join_core.rs:56-455).  `closure`
+ * NULL = identity: results are R40 (key,val1,val2); otherwise R32. */
+int32_t mzgpu_join_new(mzgpu_ctx* ctx, mzgpu_spine* trace1, mzgpu_spine* trace2,
+                       const mzgpu_closure* closure, mzgpu_join** out);
+void mzgpu_join_free(mzgpu_join* j);
+/* A new batch arrived on input `side` (0 or 1) with capability time `cap`:
+ * enqueue (batch x cursor_through(other, ack_other)) and advance ack_side
+ * (mz_join_core.rs:218-327). */
+int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch* batch, uint64_t cap);
+/* Work::process (mz_join_core.rs:534-582): run deferred work until `fuel_rows`
+ * results were produced; results (consolidated per work item) are appended to
+ * `out`; *done = 1 when the queue is empty. */
+int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out, int32_t* done);
+
+/* --------------------------------------------------- a10: half_join */
+/* dogs3 half_join_internal_unsafe as called at delta_join.rs:401-431: for each
+ * stream update ((key, val1), time, d1) and each (key, val2, t, d2) in `trace`
+ * with cmp(t, time): emit ((closure(key,val1,val2)), time, d1*d2).  The caller
+ * must have advanced the trace's upper beyond every stream time (the operator
+ * waits for the arrangement frontier in the reference).  Results are appended
+ * to `out` (R32 rows, not consolidated unless consolidate_output != 0). */
+int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int32_t mem,
+                        mzgpu_spine* trace, int32_t cmp_mode, const mzgpu_closure* closure,
+                        int32_t consolidate_output, mzgpu_buf* out);
+/* build_update_stream (delta_join.rs:600-707): a batch's updates as a stream,
+ * `initial_closure` applied (val2 unused), updates at `skip_time` dropped when
+ * skip_time != MZGPU_FRONTIER_EMPTY (the as_of rule for source_relation != 0). */
+int32_t mzgpu_update_stream(mzgpu_ctx* ctx, mzgpu_batch* batch, const mzgpu_closure* initial_closure,
+                            uint64_t skip_time, mzgpu_buf* out);
+/* Apply a closure to a stream of R32 rows (DeltaJoinFinalization / key-val
+ * extraction of render_reduce, reduce.rs:106-157). */
+int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_t n, int32_t mem,
+                       const mzgpu_closure* closure, mzgpu_buf* out);
+
+/* ------------------------------------------- a11-a12: accumulable reduce */
+/* build_accumulable (reduce.rs:1261-1471): state = the "ArrangeAccumulable"
+ * arrangement (a spine of RACC batches). */
+int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_reduce** out);
+void mzgpu_reduce_free(mzgpu_reduce* r);
+/* One operator activation: `rows` are the (group key, value, time, diff)
+ * updates with times in [previous upper, upper).  explode_one -> arrange ->
+ * reduce_abelian: appends the output corrections (ROUT rows: -old, +new per
+ * changed key and time) to `out`, consolidated. */
+int32_t mzgpu_reduce_accumulable(mzgpu_reduce* r, const mzgpu_r32* rows, uint64_t n, int32_t mem,
+                                 uint64_t upper, mzgpu_buf* out);
+/* The input arrangement (for sharing / inspection). Borrowed. */
+mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r);
+
+/* ------------------------------------------------------- a13: exchange */
+/* Bytes of the NCCL unique id passed to mzgpu_comm_init. */
+#define MZGPU_COMM_ID_BYTES 128
+/* Rank 0 creates the id; the host distributes it (timely's own bootstrap,
+ * src/cluster/src/communication.rs:288, stays on the host). */
+int32_t mzgpu_comm_unique_id(uint8_t id[MZGPU_COMM_ID_BYTES]);
+int32_t mzgpu_comm_init(mzgpu_ctx* ctx, const uint8_t id[MZGPU_COMM_ID_BYTES]);
+/* Exchange pact by key hash (src/compute/src/extensions/arrange.rs:116,
+ * src/timely-util/src/columnar.rs:227-237): route each row to
+ * hash(key) % peers; collective over all peers' contexts (all must call in the
+ * same order).  `in` and `out` are R32 or RACC buffers; `out` is replaced. */
+int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out);
+/* The routing function itself (for tests and host-side pre-partitioning). */
+uint32_t mzgpu_route(uint64_t key, uint32_t peers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MZGPU_H */
