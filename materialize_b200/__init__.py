@@ -1,0 +1,36 @@
+"""materialize_b200 — a B200-native differential-dataflow operator core.
+
+The hot path of Materialize's compute layer (update consolidation, arrangement
+build/merge, delta/linear join, accumulable reduce) as hand-written sm_100a CUDA
+behind the C ABI of include/mzgpu.h.  See DESIGN.md and INTEGRATION.md.
+
+Importing this package loads libmzgpu.so and raises if it is missing: there is
+no CPU fallback.
+"""
+from . import _ffi  # noqa: F401  (loads the CUDA library; raises if absent)
+from .api import (  # noqa: F401
+    AGG_COUNT_SUM_F64,
+    AGG_COUNT_SUM_I64,
+    FRONTIER_EMPTY,
+    HALFJOIN_LE,
+    HALFJOIN_LT,
+    R16,
+    R32,
+    R40,
+    RACC,
+    ROUT,
+    Batch,
+    Batcher,
+    Closure,
+    Context,
+    DeviceRows,
+    JoinCore,
+    MzGpuError,
+    ReduceAccumulable,
+    Spine,
+    half_join,
+    make_closure,
+    map_rows,
+    route,
+    update_stream,
+)

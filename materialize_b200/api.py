@@ -1,0 +1,381 @@
+"""Host-side mirror of the differential-dataflow operator surface, over the C ABI.
+
+Names follow the reference's traits so the parity tests read like its own:
+
+  consolidate / consolidate_updates   differential_dataflow::consolidation
+  Batcher.push_container / seal       Batcher (src/timely-util/src/operator.rs:572-633)
+  Batch                               Rc<OrdValBatch> (len / description / cursor export)
+  Spine (Trace)                       spine_fueled::Spine behind TraceAgent
+                                      (insert / exert / set_*_compaction / cursor_through)
+  JoinCore                            mz_join_core (src/compute/src/render/join/mz_join_core.rs)
+  half_join                           dogs3 half_join (delta_join.rs:401-431)
+  ReduceAccumulable                   build_accumulable (src/compute/src/render/reduce.rs:1261)
+
+Everything executes on the GPU through libmzgpu.so; rows cross the boundary as
+numpy structured arrays (host memory) or stay in `DeviceRows` (device memory).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi as F
+from ._ffi import (  # noqa: F401  (re-exported)
+    AGG_COUNT_SUM_F64,
+    AGG_COUNT_SUM_I64,
+    FRONTIER_EMPTY,
+    HALFJOIN_LE,
+    HALFJOIN_LT,
+    R16,
+    R32,
+    R40,
+    RACC,
+    ROUT,
+    Closure,
+    MzGpuError,
+)
+
+SRC_KEY, SRC_VAL1, SRC_VAL2 = 0, 1, 2
+_CMP = {"eq": 0, "ne": 1, "lt": 2, "le": 3, "gt": 4, "ge": 5}
+
+
+def make_closure(key_fields=(), val_fields=(), filters=(), expr=None):
+    """Build a closure descriptor.  key_fields / val_fields: (src, shift, bits, dst_shift);
+    filters: (src, shift, bits, op, rhs); expr: ((src, shift, bits), (src, shift, bits), c) = a * (c - b)."""
+    c = F.Closure()
+    c.n_key_fields, c.n_val_fields, c.n_filters = len(key_fields), len(val_fields), len(filters)
+    for i, f in enumerate(key_fields):
+        c.key_fields[i] = F.Field(*f)
+    for i, f in enumerate(val_fields):
+        c.val_fields[i] = F.Field(*f)
+    for i, (src, shift, bits, op, rhs) in enumerate(filters):
+        c.filters[i] = F.Filter(F.Field(src, shift, bits, 0), _CMP[op], rhs)
+    if expr is not None:
+        a, b, k = expr
+        c.expr_kind = 1
+        c.expr_a = F.Field(a[0], a[1], a[2], 0)
+        c.expr_b = F.Field(b[0], b[1], b[2], 0)
+        c.expr_c = k
+    return c
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _clp(closure):
+    return C.byref(closure) if closure is not None else None
+
+
+class Context:
+    """One per timely worker / GPU (mzgpu_ctx)."""
+
+    def __init__(self, device=0, worker_index=0, peers=1):
+        h = C.c_void_p()
+        st = F.lib.mzgpu_ctx_create(device, worker_index, peers, C.byref(h))
+        self.h = h
+        if st != F.OK:
+            msg = F.lib.mzgpu_last_error(h).decode() if h else "context allocation failed"
+            raise MzGpuError(st, msg)
+        self.device, self.worker_index, self.peers = device, worker_index, peers
+
+    def check(self, st):
+        if st != F.OK:
+            raise MzGpuError(st, F.lib.mzgpu_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(F.lib.mzgpu_ctx_sync(self.h))
+
+    def stats(self):
+        s = F.Stats()
+        self.check(F.lib.mzgpu_ctx_stats(self.h, C.byref(s)))
+        return {name: int(getattr(s, name)) for name, _ in F.Stats._fields_}
+
+    def stream(self):
+        return F.lib.mzgpu_ctx_stream(self.h)
+
+    def close(self):
+        if self.h:
+            F.lib.mzgpu_ctx_destroy(self.h)
+            self.h = None
+
+    # -- a1
+    def consolidate(self, rows):
+        """consolidate / consolidate_updates on a host array (R16 or R32); returns the survivors."""
+        rows = np.ascontiguousarray(rows).copy()
+        n_out = C.c_uint64(0)
+        if rows.dtype.itemsize == 16:
+            st = F.lib.mzgpu_consolidate_r16(self.h, _ptr(rows), len(rows), F.MEM_HOST, C.byref(n_out))
+        elif rows.dtype.itemsize == 32:
+            st = F.lib.mzgpu_consolidate_r32(self.h, _ptr(rows), len(rows), F.MEM_HOST, C.byref(n_out))
+        else:
+            buf = DeviceRows(self, rows.dtype.itemsize)
+            buf.upload(rows)
+            buf.consolidate()
+            return buf.download()
+        self.check(st)
+        return rows[: n_out.value].copy()
+
+
+class DeviceRows:
+    """Library-owned device row buffer (mzgpu_buf)."""
+
+    def __init__(self, ctx, row_bytes):
+        self.ctx, self.row_bytes = ctx, row_bytes
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_buf_new(ctx.h, row_bytes, C.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return F.lib.mzgpu_buf_len(self.h)
+
+    def upload(self, rows):
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype.itemsize == self.row_bytes
+        self.ctx.check(F.lib.mzgpu_buf_upload(self.h, _ptr(rows), len(rows), F.MEM_HOST))
+        return self
+
+    def append(self, rows):
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype.itemsize == self.row_bytes
+        self.ctx.check(F.lib.mzgpu_buf_append(self.h, _ptr(rows), len(rows), F.MEM_HOST))
+        return self
+
+    def download(self):
+        n = len(self)
+        out = np.zeros(n, dtype=F.DTYPES[self.row_bytes])
+        got = C.c_uint64(0)
+        self.ctx.check(F.lib.mzgpu_buf_download(self.h, _ptr(out), n, F.MEM_HOST, C.byref(got)))
+        return out
+
+    def device_ptr(self):
+        return F.lib.mzgpu_buf_device_ptr(self.h)
+
+    def clear(self):
+        self.ctx.check(F.lib.mzgpu_buf_clear(self.h))
+
+    def consolidate(self):
+        self.ctx.check(F.lib.mzgpu_buf_consolidate(self.h))
+        return self
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_buf_free(self.h)
+            self.h = None
+
+
+class Batch:
+    def __init__(self, ctx, h, row_bytes):
+        self.ctx, self.h, self.row_bytes = ctx, h, row_bytes
+
+    @staticmethod
+    def build(ctx, rows, lower, upper, since=0):
+        """Builder::seal on unsorted updates with an explicit description."""
+        rows = np.ascontiguousarray(rows)
+        h = C.c_void_p()
+        ctx.check(
+            F.lib.mzgpu_batch_build(
+                ctx.h, rows.dtype.itemsize, _ptr(rows), len(rows), F.MEM_HOST, F.Desc(lower, upper, since), C.byref(h)
+            )
+        )
+        return Batch(ctx, h, rows.dtype.itemsize)
+
+    def __len__(self):
+        return F.lib.mzgpu_batch_len(self.h)
+
+    def keys(self):
+        return F.lib.mzgpu_batch_keys(self.h)
+
+    def desc(self):
+        d = F.lib.mzgpu_batch_desc(self.h)
+        return (d.lower, d.upper, d.since)
+
+    def rows(self):
+        n = len(self)
+        out = np.zeros(n, dtype=F.DTYPES[self.row_bytes])
+        got = C.c_uint64(0)
+        self.ctx.check(F.lib.mzgpu_batch_export(self.h, _ptr(out), n, F.MEM_HOST, C.byref(got)))
+        return out
+
+    def merge(self, other, since):
+        h = C.c_void_p()
+        self.ctx.check(F.lib.mzgpu_batch_merge(self.h, other.h, since, C.byref(h)))
+        return Batch(self.ctx, h, self.row_bytes)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_batch_release(self.h)
+            self.h = None
+
+
+class Batcher:
+    def __init__(self, ctx, row_bytes=32):
+        self.ctx, self.row_bytes = ctx, row_bytes
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_batcher_new(ctx.h, row_bytes, C.byref(h)))
+        self.h = h
+
+    def push_container(self, rows):
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype.itemsize == self.row_bytes
+        self.ctx.check(F.lib.mzgpu_batcher_push(self.h, _ptr(rows), len(rows), F.MEM_HOST))
+
+    def push_device(self, dev_rows):
+        self.ctx.check(F.lib.mzgpu_batcher_push(self.h, dev_rows.device_ptr(), len(dev_rows), F.MEM_DEVICE))
+
+    def seal(self, upper):
+        h = C.c_void_p()
+        lower = C.c_uint64(0)
+        self.ctx.check(F.lib.mzgpu_batcher_seal(self.h, upper, C.byref(h), C.byref(lower)))
+        return Batch(self.ctx, h, self.row_bytes)
+
+    def frontier(self):
+        return F.lib.mzgpu_batcher_frontier(self.h)
+
+    def __len__(self):
+        return F.lib.mzgpu_batcher_len(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_batcher_free(self.h)
+            self.h = None
+
+
+class Spine:
+    """The trace behind an arrangement."""
+
+    def __init__(self, ctx, row_bytes=32, effort=1, _borrowed=None):
+        self.ctx, self.row_bytes = ctx, row_bytes
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            ctx.check(F.lib.mzgpu_spine_new(ctx.h, row_bytes, effort, C.byref(h)))
+            self.h = h
+        else:
+            self.h = _borrowed
+
+    def insert(self, batch):
+        self.ctx.check(F.lib.mzgpu_spine_insert(self.h, batch.h))
+
+    def exert(self, effort):
+        did = C.c_int32(0)
+        self.ctx.check(F.lib.mzgpu_spine_exert(self.h, effort, C.byref(did)))
+        return bool(did.value)
+
+    def exert_logic(self, proportionality=16):
+        return F.lib.mzgpu_spine_exert_logic(self.h, proportionality)
+
+    def set_logical_compaction(self, frontier):
+        self.ctx.check(F.lib.mzgpu_spine_set_logical_compaction(self.h, frontier))
+
+    def set_physical_compaction(self, frontier):
+        self.ctx.check(F.lib.mzgpu_spine_set_physical_compaction(self.h, frontier))
+
+    def get_logical_compaction(self):
+        return F.lib.mzgpu_spine_get_logical_compaction(self.h)
+
+    def get_physical_compaction(self):
+        return F.lib.mzgpu_spine_get_physical_compaction(self.h)
+
+    def read_upper(self):
+        return F.lib.mzgpu_spine_read_upper(self.h)
+
+    def num_batches_through(self, upper):
+        arr = (C.c_void_p * 128)()
+        n = C.c_uint32(0)
+        self.ctx.check(F.lib.mzgpu_spine_batches_through(self.h, upper, arr, 128, C.byref(n)))
+        return n.value
+
+    def layers(self):
+        out = (C.c_uint64 * (4 * 64))()
+        n = C.c_uint32(0)
+        self.ctx.check(F.lib.mzgpu_spine_layers(self.h, out, 64, C.byref(n)))
+        return [tuple(int(out[4 * i + j]) for j in range(4)) for i in range(n.value)]
+
+    def export(self):
+        """as_collection: consolidated contents, times advanced to `since`."""
+        buf = DeviceRows(self.ctx, self.row_bytes)
+        self.ctx.check(F.lib.mzgpu_spine_export(self.h, buf.h))
+        return buf.download()
+
+    def __del__(self):
+        if getattr(self, "h", None) and self._owned and self.ctx.h:
+            F.lib.mzgpu_spine_free(self.h)
+            self.h = None
+
+
+class JoinCore:
+    """mz_join_core over two arrangements."""
+
+    def __init__(self, ctx, trace1, trace2, closure=None):
+        self.ctx, self.closure = ctx, closure
+        self._keep = (trace1, trace2)
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_join_new(ctx.h, trace1.h, trace2.h, _clp(closure), C.byref(h)))
+        self.h = h
+        self.out = DeviceRows(ctx, 32 if closure is not None else 40)
+
+    def push(self, side, batch, cap):
+        self.ctx.check(F.lib.mzgpu_join_core_push(self.h, side, batch.h, cap))
+
+    def work(self, fuel_rows=1 << 62):
+        done = C.c_int32(0)
+        self.ctx.check(F.lib.mzgpu_join_core_work(self.h, fuel_rows, self.out.h, C.byref(done)))
+        return bool(done.value)
+
+    def results(self):
+        return self.out.download()
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_join_free(self.h)
+            self.h = None
+
+
+def half_join(ctx, stream, trace, cmp_mode, closure=None, consolidate_output=True):
+    stream = np.ascontiguousarray(stream)
+    out = DeviceRows(ctx, 32)
+    ctx.check(
+        F.lib.mzgpu_half_join(
+            ctx.h, _ptr(stream), len(stream), F.MEM_HOST, trace.h, cmp_mode, _clp(closure), 1 if consolidate_output else 0, out.h
+        )
+    )
+    return out.download()
+
+
+def update_stream(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY):
+    out = DeviceRows(ctx, 32)
+    ctx.check(F.lib.mzgpu_update_stream(ctx.h, batch.h, _clp(closure), skip_time, out.h))
+    return out.download()
+
+
+def map_rows(ctx, rows, closure):
+    rows = np.ascontiguousarray(rows)
+    out = DeviceRows(ctx, 32)
+    ctx.check(F.lib.mzgpu_map_rows(ctx.h, _ptr(rows), len(rows), F.MEM_HOST, _clp(closure), out.h))
+    return out.download()
+
+
+class ReduceAccumulable:
+    def __init__(self, ctx, agg_kind=F.AGG_COUNT_SUM_I64):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_reduce_new(ctx.h, agg_kind, C.byref(h)))
+        self.h = h
+
+    def step(self, rows, upper):
+        rows = np.ascontiguousarray(rows)
+        out = DeviceRows(self.ctx, 64)
+        self.ctx.check(F.lib.mzgpu_reduce_accumulable(self.h, _ptr(rows), len(rows), F.MEM_HOST, upper, out.h))
+        return out.download()
+
+    def input_trace(self):
+        return Spine(self.ctx, 80, _borrowed=F.lib.mzgpu_reduce_input_trace(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_reduce_free(self.h)
+            self.h = None
+
+
+def route(key, peers):
+    return F.lib.mzgpu_route(key, peers)

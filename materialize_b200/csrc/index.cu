@@ -1,0 +1,84 @@
+// index.cu — per-batch open-addressing hash index over distinct keys
+// (SURVEY.md a5/a8).
+//
+// The reference's OrdValBatch keeps a sorted `keys[]` array and its cursor
+// finds a key with exponential + binary search (`seek_key`; usage
+// src/compute/src/render/join/mz_join_core.rs:606-621).  On the GPU a probe is
+// one 128-bit load of a 16-byte slot {key, first row + 1} (linear probing, load
+// factor <= 0.5), after which the key's updates are a contiguous run of the
+// batch's sorted rows.
+#include "common.cuh"
+
+namespace {
+
+template <int NW>
+__global__ void __launch_bounds__(512) k_count_keys(const u64* __restrict__ rows, u64 n,
+                                                    unsigned long long* __restrict__ count) {
+  u64 i = (u64)blockIdx.x * 512 + threadIdx.x;
+  bool head = false;
+  if (i < n) head = (i == 0) || rows[i * NW] != rows[(i - 1) * NW];
+  u32 m = __ballot_sync(0xffffffffu, head);
+  if (lane_id() == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+template <int NW>
+__global__ void __launch_bounds__(512) k_build_index(const u64* __restrict__ rows, u64 n,
+                                                     HashSlot* __restrict__ table, u64 mask) {
+  u64 i = (u64)blockIdx.x * 512 + threadIdx.x;
+  if (i >= n) return;
+  u64 key = rows[i * NW];
+  if (i != 0 && rows[(i - 1) * NW] == key) return;
+  u64 h = mix64(key) & mask;
+  while (true) {
+    // distinct keys only: claim the first empty slot
+    unsigned long long prev =
+        atomicCAS((unsigned long long*)&table[h].meta, 0ull, (unsigned long long)(i + 1));
+    if (prev == 0ull) {
+      table[h].key = key;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+}  // namespace
+
+int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys) {
+  *n_keys = 0;
+  if (n == 0) return MZGPU_OK;
+  u64* d_count = ctx->d_scratch + 24;
+  MZ_CUDA(ctx, cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+  unsigned grid = (unsigned)((n + 511) / 512);
+  const u64* r = (const u64*)d_rows;
+  switch (row_bytes) {
+    case 32: MZ_LAUNCH(ctx, k_count_keys<4>, grid, 512, 0, r, n, (unsigned long long*)d_count); break;
+    case 80: MZ_LAUNCH(ctx, k_count_keys<10>, grid, 512, 0, r, n, (unsigned long long*)d_count); break;
+    case 64: MZ_LAUNCH(ctx, k_count_keys<8>, grid, 512, 0, r, n, (unsigned long long*)d_count); break;
+    default: MZ_SET_ERR(ctx, "index: unsupported row width %d", row_bytes); return MZGPU_E_UNSUPPORTED;
+  }
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 24, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 8;
+  *n_keys = ctx->h_scratch[24];
+  return MZGPU_OK;
+}
+
+int32_t mz_build_index(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64 n_keys,
+                       DevMem* table, u64* table_slots) {
+  u64 slots = 2;
+  while (slots < 2 * n_keys) slots <<= 1;
+  *table_slots = slots;
+  MZ_TRY(table->alloc(ctx, slots * sizeof(HashSlot)));
+  MZ_CUDA(ctx, cudaMemsetAsync(table->p, 0, slots * sizeof(HashSlot), ctx->stream));
+  if (n == 0) return MZGPU_OK;
+  unsigned grid = (unsigned)((n + 511) / 512);
+  const u64* r = (const u64*)d_rows;
+  HashSlot* t = table->as<HashSlot>();
+  switch (row_bytes) {
+    case 32: MZ_LAUNCH(ctx, k_build_index<4>, grid, 512, 0, r, n, t, slots - 1); break;
+    case 80: MZ_LAUNCH(ctx, k_build_index<10>, grid, 512, 0, r, n, t, slots - 1); break;
+    case 64: MZ_LAUNCH(ctx, k_build_index<8>, grid, 512, 0, r, n, t, slots - 1); break;
+    default: MZ_SET_ERR(ctx, "index: unsupported row width %d", row_bytes); return MZGPU_E_UNSUPPORTED;
+  }
+  return MZGPU_OK;
+}

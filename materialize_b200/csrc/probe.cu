@@ -1,0 +1,206 @@
+// probe.cu — arrangement probes for the joins.
+//
+// Reference:
+//   half_join   differential-dogs3 0.23.0 half_join2::half_join_internal_unsafe
+//               (external) as configured by build_halfjoin2,
+//               src/compute/src/render/join/delta_join.rs:379-484; tie-break
+//               comparison `le`/`lt` :204-224; semantics SURVEY.md A8
+//   join_core   Work::start_work key merge + Joiner::join_key_simple,
+//               src/compute/src/render/join/mz_join_core.rs:591-623,714-726
+//               (the pairwise form; the linear time scan :729-793 yields the
+//               same consolidated output)
+//
+// The CPU operators sort the probe side and walk a merged cursor with
+// `seek_key`.  Here every probe row is one thread: a 128-bit load of the hash
+// slot per batch of the trace, then a contiguous run of 32-byte lookup rows.
+// Two passes (count -> scan -> write) give each probe row a private, bounded
+// output range, so the expansion needs no atomics and no output sort.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT = 256;
+
+// visit every (val2, time2, diff2) of `key` in the trace that passes the time
+// filter; F(v2, t2, d2)
+template <class F>
+__device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64 t1, int mode, F f) {
+  const u64 h0 = mix64(key);
+  for (u32 b = 0; b < tv.n_batches; ++b) {
+    const BatchView& bv = tv.b[b];
+    u64 h = h0 & bv.mask;
+    while (true) {
+      const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      if (slot.y == 0) break;
+      if (slot.x == key) {
+        for (u64 j = slot.y - 1; j < bv.n; ++j) {
+          const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4);
+          if (kv.x != key) break;
+          const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4 + 2);
+          bool ok = mode == MZ_PROBE_HALF_LE ? td.x <= t1 : (mode == MZ_PROBE_HALF_LT ? td.x < t1 : true);
+          if (ok) f(kv.y, td.x, (i64)td.y);
+        }
+        break;
+      }
+      h = (h + 1) & bv.mask;
+    }
+  }
+}
+
+template <int OUT_NW, bool WRITE>
+__global__ void __launch_bounds__(PT) k_probe(const u64* __restrict__ stream, u64 n,
+                                              const __grid_constant__ TraceView tv,
+                                              const __grid_constant__ ProbeParams pp,
+                                              u32* __restrict__ tile_counts,
+                                              const u32* __restrict__ tile_base,
+                                              u64* __restrict__ out) {
+  __shared__ u32 sm[34];
+  const u64 i = (u64)blockIdx.x * PT + threadIdx.x;
+  u64 key = 0, v1 = 0, t1 = 0;
+  i64 d1 = 0;
+  u32 cnt = 0;
+  if (i < n) {
+    const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
+    const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
+    key = kv.x;
+    v1 = kv.y;
+    t1 = td.x;
+    d1 = (i64)td.y;
+    for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+      if (pp.has_closure) {
+        u64 k, v;
+        if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
+      } else {
+        cnt++;
+      }
+    });
+  }
+  u32 total;
+  u32 ex = block_exclusive_scan(cnt, sm, &total);
+  if (!WRITE) {
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+    return;
+  }
+  if (i < n && cnt > 0) {
+    u64 pos = (u64)tile_base[blockIdx.x] + ex;
+    for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+      u64 t = t1;
+      if (pp.mode == MZ_PROBE_JOIN) {
+        t = t1 > t2 ? t1 : t2;
+        t = t > pp.meet ? t : pp.meet;
+      }
+      u64 d = (u64)d1 * (u64)d2;
+      u64 a = pp.swap_vals ? v2 : v1, b = pp.swap_vals ? v1 : v2;
+      if (OUT_NW == 4) {
+        u64 k, v;
+        if (closure_eval(pp.closure, key, a, b, &k, &v)) {
+          u64 r[4] = {k, v, t, d};
+          store_row<4>(out, pos, r);
+          pos++;
+        }
+      } else {
+        u64* o = out + pos * 5;
+        o[0] = key;
+        o[1] = a;
+        o[2] = b;
+        o[3] = t;
+        o[4] = d;
+        pos++;
+      }
+    });
+  }
+}
+
+// closure over R32 rows (val2 = 0), optional skip of one time
+template <bool WRITE>
+__global__ void __launch_bounds__(PT) k_map_rows(const u64* __restrict__ rows, u64 n,
+                                                 const __grid_constant__ mzgpu_closure cl, int has_closure,
+                                                 u64 skip_time, u32* __restrict__ tile_counts,
+                                                 const u32* __restrict__ tile_base,
+                                                 u64* __restrict__ out) {
+  __shared__ u32 sm[34];
+  const u64 i = (u64)blockIdx.x * PT + threadIdx.x;
+  u32 keep = 0;
+  u64 r[4] = {0, 0, 0, 0};
+  if (i < n) {
+    load_row<4>(rows, i, r);
+    keep = 1;
+    if (skip_time != MZGPU_FRONTIER_EMPTY && r[2] == skip_time) keep = 0;
+    if (keep && has_closure) {
+      u64 k, v;
+      if (closure_eval(cl, r[0], r[1], 0, &k, &v)) {
+        r[0] = k;
+        r[1] = v;
+      } else {
+        keep = 0;
+      }
+    }
+  }
+  u32 total;
+  u32 ex = block_exclusive_scan(keep, sm, &total);
+  if (!WRITE) {
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+    return;
+  }
+  if (keep) store_row<4>(out, (u64)tile_base[blockIdx.x] + ex, r);
+}
+
+}  // namespace
+
+int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& trace,
+                 const ProbeParams& pp, DevMem* out, u64* n_out) {
+  *n_out = 0;
+  const int out_rb = pp.has_closure ? 32 : 40;
+  if (n == 0 || trace.n_batches == 0) return out->alloc(ctx, 16);
+  const u64 n_tiles = (n + PT - 1) / PT;
+  DevMem tiles;
+  MZ_TRY(tiles.alloc(ctx, n_tiles * 4));
+  u64* d_total = ctx->d_scratch + 28;
+  if (pp.has_closure) {
+    MZ_LAUNCH(ctx, (k_probe<4, false>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, tiles.as<u32>(),
+              (const u32*)nullptr, (u64*)nullptr);
+  } else {
+    MZ_LAUNCH(ctx, (k_probe<5, false>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, tiles.as<u32>(),
+              (const u32*)nullptr, (u64*)nullptr);
+  }
+  MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 28, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 8;
+  const u64 total = ctx->h_scratch[28];
+  MZ_TRY(out->alloc(ctx, total * out_rb));
+  *n_out = total;
+  if (total == 0) return MZGPU_OK;
+  if (pp.has_closure) {
+    MZ_LAUNCH(ctx, (k_probe<4, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
+              tiles.as<u32>(), out->as<u64>());
+  } else {
+    MZ_LAUNCH(ctx, (k_probe<5, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
+              tiles.as<u32>(), out->as<u64>());
+  }
+  return MZGPU_OK;
+}
+
+int32_t mz_map_rows_dev(mzgpu_ctx* ctx, const u64* d_rows, u64 n, const mzgpu_closure* closure,
+                        u64 skip_time, DevMem* out, u64* n_out) {
+  *n_out = 0;
+  MZ_TRY(out->alloc(ctx, n * 32));
+  if (n == 0) return MZGPU_OK;
+  const u64 n_tiles = (n + PT - 1) / PT;
+  DevMem tiles;
+  MZ_TRY(tiles.alloc(ctx, n_tiles * 4));
+  u64* d_total = ctx->d_scratch + 29;
+  mzgpu_closure cl;
+  memset(&cl, 0, sizeof(cl));
+  if (closure) cl = *closure;
+  MZ_LAUNCH(ctx, (k_map_rows<false>), (unsigned)n_tiles, PT, 0, d_rows, n, cl, closure ? 1 : 0, skip_time,
+            tiles.as<u32>(), (const u32*)nullptr, (u64*)nullptr);
+  MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
+  MZ_LAUNCH(ctx, (k_map_rows<true>), (unsigned)n_tiles, PT, 0, d_rows, n, cl, closure ? 1 : 0, skip_time,
+            (u32*)nullptr, tiles.as<u32>(), out->as<u64>());
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 29, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 8;
+  *n_out = ctx->h_scratch[29];
+  return MZGPU_OK;
+}

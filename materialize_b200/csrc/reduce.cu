@@ -1,0 +1,296 @@
+// reduce.cu — accumulable reduce: COUNT / SUM moved into the diff.
+//
+// Reference (src/compute/src/render/reduce.rs):
+//   explode_one + datum_to_accumulator   :1313-1334, 1530-1669
+//   Multiply<Diff> for Accum             :2043-2104
+//   Semigroup for Accum (i128 wrapping)  :1940-2041
+//   reduce_abelian closure + finalize    :1388-1409, 1671-1835
+//   AccumulableErrorCheck                :1410-1466
+//   FLOAT_SCALE = 2^24                   :1528
+// and the reduce operator contract src/compute/src/extensions/reduce.rs:52-107.
+//
+// GPU shape: values become 80-byte accumulator rows (k_explode), the generic
+// sort + segmented sum arranges them by (key, time), and k_corrections walks
+// each changed key once: it sums the key's history from the prior batches of
+// the arrangement (one hash probe per batch), then replays the new batch's
+// times in order, emitting (-old, +new) output rows whenever the finalized
+// aggregate changes.  All arithmetic is integer (i64 / i128 with carries), so
+// results do not depend on summation order and match the reference bit for bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RT = 256;
+
+// (x * 2^24) as i128 with Rust's saturating float->int cast semantics.
+__device__ __forceinline__ void f64_to_i128_sat(double x, u64* lo, u64* hi) {
+  if (isnan(x)) {
+    *lo = 0;
+    *hi = 0;
+    return;
+  }
+  const bool neg = x < 0.0;
+  const double ax = fabs(x);
+  if (ax < 9223372036854775808.0) {  // < 2^63: exact through i64 (truncation toward zero)
+    long long v = (long long)x;
+    *lo = (u64)v;
+    *hi = v < 0 ? ~0ull : 0ull;
+    return;
+  }
+  if (ax >= 170141183460469231731687303715884105728.0) {  // >= 2^127 (or inf): saturate
+    if (neg) {
+      *lo = 0;
+      *hi = 0x8000000000000000ull;
+    } else {
+      *lo = ~0ull;
+      *hi = 0x7fffffffffffffffull;
+    }
+    return;
+  }
+  const u64 bits = (u64)__double_as_longlong(ax);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1023;  // 63..126
+  const u64 mant = (bits & 0xfffffffffffffull) | (1ull << 52);
+  const int sh = e - 52;  // 11..74
+  u64 l, h;
+  if (sh >= 64) {
+    l = 0;
+    h = mant << (sh - 64);
+  } else {
+    l = mant << sh;
+    h = mant >> (64 - sh);
+  }
+  if (neg) {  // two's complement negate
+    l = ~l + 1;
+    h = ~h + (l == 0 ? 1 : 0);
+  }
+  *lo = l;
+  *hi = h;
+}
+
+// (i128 as f64): round to nearest, ties to even.
+__device__ __forceinline__ double i128_to_f64(u64 lo, u64 hi) {
+  const bool neg = (i64)hi < 0;
+  if (neg) {
+    lo = ~lo + 1;
+    hi = ~hi + (lo == 0 ? 1 : 0);
+  }
+  double r;
+  if (hi == 0) {
+    r = __ull2double_rn(lo);
+  } else {
+    const int lz = __clzll((long long)hi);
+    // top 64 bits of the 128-bit magnitude, sticky bit folded into bit 0
+    const int shift = 64 - lz;  // bits shifted out of `lo`
+    u64 top = lz == 0 ? hi : ((hi << lz) | (lo >> shift));
+    u64 lost = lz == 0 ? lo : (lo << lz);
+    if (lost) top |= 1;
+    r = ldexp(__ull2double_rn(top), shift);
+  }
+  return neg ? -r : r;
+}
+
+// wrapping i128 * i64
+__device__ __forceinline__ void mul_i128_i64(u64 lo, u64 hi, i64 d, u64* rlo, u64* rhi) {
+  const u64 dl = (u64)d;
+  const u64 dh = d < 0 ? ~0ull : 0ull;
+  *rlo = lo * dl;
+  *rhi = __umul64hi(lo, dl) + hi * dl + lo * dh;
+}
+
+__global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, u64 n, int agg_kind,
+                                                u64* __restrict__ out) {
+  u64 i = (u64)blockIdx.x * RT + threadIdx.x;
+  if (i >= n) return;
+  u64 r[4];
+  load_row<4>(rows, i, r);
+  const i64 diff = (i64)r[3];
+  u64 o[10];
+  o[0] = r[0];       // key
+  o[1] = r[2];       // time
+  o[2] = (u64)diff;  // total
+  o[3] = (u64)diff;  // non_nulls
+  u64 alo, ahi;
+  u64 pinf = 0, ninf = 0, nan = 0;
+  if (agg_kind == MZGPU_AGG_COUNT_SUM_F64) {
+    const double v = __longlong_as_double((long long)r[1]);
+    const bool is_nan = isnan(v);
+    const bool is_pinf = isinf(v) && v > 0;
+    const bool is_ninf = isinf(v) && v < 0;
+    nan = is_nan ? (u64)diff : 0;
+    pinf = is_pinf ? (u64)diff : 0;
+    ninf = is_ninf ? (u64)diff : 0;
+    if (is_nan || is_pinf || is_ninf) {
+      alo = 0;
+      ahi = 0;
+    } else {
+      f64_to_i128_sat(v * 16777216.0, &alo, &ahi);
+    }
+  } else {
+    alo = r[1];
+    ahi = (i64)r[1] < 0 ? ~0ull : 0ull;
+  }
+  mul_i128_i64(alo, ahi, diff, &o[4], &o[5]);
+  o[6] = pinf;
+  o[7] = ninf;
+  o[8] = nan;
+  o[9] = 0;
+  store_row<10>(out, i, o);
+}
+
+// finalize_accum + error-check flag for one accumulated diff S (words 2..8 of a RACC row)
+__device__ __forceinline__ void finalize(const u64* S, int agg_kind, u64* o /* count, sum_lo, sum_hi, flags */) {
+  const i64 total = (i64)S[0];
+  const bool accum_zero = (S[1] | S[2] | S[3] | S[4] | S[5] | S[6]) == 0;
+  u64 flags = 0;
+  if (total > 0 && accum_zero) flags |= 1;
+  if (total == 0 && !accum_zero) flags |= 2;
+  o[0] = S[1];
+  if (agg_kind == MZGPU_AGG_COUNT_SUM_F64) {
+    const i64 pinf = (i64)S[4], ninf = (i64)S[5], nan = (i64)S[6];
+    u64 bits;
+    if (nan > 0 || (pinf > 0 && ninf > 0))
+      bits = 0x7ff8000000000000ull;
+    else if (pinf > 0)
+      bits = 0x7ff0000000000000ull;
+    else if (ninf > 0)
+      bits = 0xfff0000000000000ull;
+    else
+      bits = (u64)__double_as_longlong(i128_to_f64(S[2], S[3]) / 16777216.0);
+    o[1] = bits;
+    o[2] = 0;
+  } else {
+    o[1] = S[2];
+    o[2] = S[3];
+  }
+  if (flags & 1) {
+    o[1] = 0;
+    o[2] = 0;
+  }
+  o[3] = flags;
+}
+
+// sum of all prior updates of `key` (times before the new batch)
+__device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) {
+  const u64 h0 = mix64(key);
+  for (u32 b = 0; b < tv.n_batches; ++b) {
+    const BatchView& bv = tv.b[b];
+    u64 h = h0 & bv.mask;
+    while (true) {
+      const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      if (slot.y == 0) break;
+      if (slot.x == key) {
+        for (u64 j = slot.y - 1; j < bv.n; ++j) {
+          const u64* row = bv.rows + j * 10;
+          if (row[0] != key) break;
+          u64 d[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
+          diff_add<8>(S, d);
+        }
+        break;
+      }
+      h = (h + 1) & bv.mask;
+    }
+  }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(RT) k_corrections(const u64* __restrict__ rows, u64 n,
+                                                    const __grid_constant__ TraceView prior, int agg_kind,
+                                                    u32* __restrict__ tile_counts,
+                                                    const u32* __restrict__ tile_base,
+                                                    u64* __restrict__ out) {
+  __shared__ u32 sm[34];
+  const u64 i = (u64)blockIdx.x * RT + threadIdx.x;
+  u32 cnt = 0;
+  const bool head = i < n && (i == 0 || rows[(i - 1) * 10] != rows[i * 10]);
+  u64 key = 0;
+  u64 S0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (head) {
+    key = rows[i * 10];
+    prior_sum(prior, key, S0);
+  }
+  // pass over the key's new times: count (and optionally write) corrections
+  auto walk = [&](bool do_write, u64 pos) -> u32 {
+    u64 S[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) S[w] = S0[w];
+    bool had = !diff_is_zero<8>(S);
+    u64 oldv[4] = {0, 0, 0, 0};
+    if (had) finalize(S, agg_kind, oldv);
+    u32 c = 0;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 10;
+      if (row[0] != key) break;
+      u64 d[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
+      diff_add<8>(S, d);
+      const u64 t = row[1];
+      const bool has = !diff_is_zero<8>(S);
+      u64 newv[4] = {0, 0, 0, 0};
+      if (has) finalize(S, agg_kind, newv);
+      const bool same = had && has && oldv[0] == newv[0] && oldv[1] == newv[1] && oldv[2] == newv[2] &&
+                        oldv[3] == newv[3];
+      if (!same) {
+        if (had) {
+          if (do_write) {
+            u64 r[8] = {key, oldv[0], oldv[1], oldv[2], oldv[3], t, ~0ull, 0};
+            store_row<8>(out, pos + c, r);
+          }
+          ++c;
+        }
+        if (has) {
+          if (do_write) {
+            u64 r[8] = {key, newv[0], newv[1], newv[2], newv[3], t, 1, 0};
+            store_row<8>(out, pos + c, r);
+          }
+          ++c;
+        }
+      }
+      had = has;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) oldv[w] = newv[w];
+    }
+    return c;
+  };
+  if (head) cnt = walk(false, 0);
+  u32 total;
+  u32 ex = block_exclusive_scan(cnt, sm, &total);
+  if (!WRITE) {
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+  } else {
+    if (head && cnt > 0) walk(true, (u64)tile_base[blockIdx.x] + ex);
+  }
+}
+
+}  // namespace
+
+int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, u64 n, int agg_kind, u64* d_racc) {
+  if (n == 0) return MZGPU_OK;
+  MZ_LAUNCH(ctx, k_explode, (unsigned)((n + RT - 1) / RT), RT, 0, d_r32, n, agg_kind, d_racc);
+  return MZGPU_OK;
+}
+
+int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, const TraceView& prior,
+                              int agg_kind, DevMem* out, u64* n_out) {
+  *n_out = 0;
+  if (n == 0) return out->alloc(ctx, 16);
+  const u64 n_tiles = (n + RT - 1) / RT;
+  DevMem tiles;
+  MZ_TRY(tiles.alloc(ctx, n_tiles * 4));
+  u64* d_total = ctx->d_scratch + 30;
+  MZ_LAUNCH(ctx, (k_corrections<false>), (unsigned)n_tiles, RT, 0, d_batch_rows, n, prior, agg_kind,
+            tiles.as<u32>(), (const u32*)nullptr, (u64*)nullptr);
+  MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 30, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.d2h_bytes += 8;
+  const u64 total = ctx->h_scratch[30];
+  MZ_TRY(out->alloc(ctx, total * 64));
+  *n_out = total;
+  if (total == 0) return MZGPU_OK;
+  MZ_LAUNCH(ctx, (k_corrections<true>), (unsigned)n_tiles, RT, 0, d_batch_rows, n, prior, agg_kind,
+            (u32*)nullptr, tiles.as<u32>(), out->as<u64>());
+  return MZGPU_OK;
+}

@@ -397,3 +397,82 @@ def finalize(acc, agg_kind=0):
     out = np.zeros(len(acc), dtype=ROUT)
     lib().mzo_finalize(_ptr(acc), len(acc), agg_kind, _ptr(out))
     return out
+
+
+# ------------------------------------------------------------------ Q3 dataflow
+def _q3_sigs():
+    L = lib()
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_double
+    if getattr(L, "_q3_ready", False):
+        return L
+    L.mzo_q3_new.restype, L.mzo_q3_new.argtypes = vp, [u64, u64, u64, u64, u32, u64]
+    L.mzo_q3_free.restype, L.mzo_q3_free.argtypes = None, [vp]
+    L.mzo_q3_hydrate.restype, L.mzo_q3_hydrate.argtypes = dbl, [vp, C.POINTER(u64)]
+    L.mzo_q3_step.restype, L.mzo_q3_step.argtypes = dbl, [vp, u64, C.POINTER(u64)]
+    L.mzo_q3_drain.restype, L.mzo_q3_drain.argtypes = None, [vp, vp]
+    L.mzo_q3_input.restype, L.mzo_q3_input.argtypes = u64, [vp, i32, vp, u64]
+    L.mzo_gen_cfg1.restype, L.mzo_gen_cfg1.argtypes = None, [u64, u64, u32, vp]
+    L.mzo_gen_cfg2.restype, L.mzo_gen_cfg2.argtypes = None, [u64, u64, u64, vp]
+    L.mzo_zipf_cdf.restype, L.mzo_zipf_cdf.argtypes = None, [dbl, u64, vp]
+    L.mzo_gen_cfg4.restype, L.mzo_gen_cfg4.argtypes = None, [u64, u64, u64, vp, u64, i32, vp]
+    L._q3_ready = True
+    return L
+
+
+class Q3:
+    """The CPU Q3 delta-join + reduce dataflow (W worker threads)."""
+
+    def __init__(self, seed, n_customer, n_orders, n_part, workers=1, per_batch=100):
+        self.L = _q3_sigs()
+        self.h = self.L.mzo_q3_new(seed, n_customer, n_orders, n_part, workers, per_batch)
+
+    def hydrate(self):
+        rows = C.c_uint64(0)
+        secs = self.L.mzo_q3_hydrate(self.h, C.byref(rows))
+        return secs, rows.value
+
+    def step(self, b):
+        rows = C.c_uint64(0)
+        secs = self.L.mzo_q3_step(self.h, b, C.byref(rows))
+        return secs, rows.value
+
+    def drain(self):
+        v = Vec(64)
+        self.L.mzo_q3_drain(self.h, v.h)
+        return v.array()
+
+    def inputs(self, a):
+        n = self.L.mzo_q3_input(self.h, a, None, 0)
+        out = np.zeros(n, dtype=R32)
+        if n:
+            self.L.mzo_q3_input(self.h, a, _ptr(out), n)
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            self.L.mzo_q3_free(self.h)
+            self.h = None
+
+
+def gen_cfg1(seed, n, key_bits):
+    out = np.zeros(n, dtype=R16)
+    _q3_sigs().mzo_gen_cfg1(seed, n, key_bits, _ptr(out))
+    return out
+
+
+def gen_cfg2(seed, n, n_keys):
+    out = np.zeros(n, dtype=R32)
+    _q3_sigs().mzo_gen_cfg2(seed, n, n_keys, _ptr(out))
+    return out
+
+
+def zipf_cdf(theta, n):
+    cdf = np.zeros(n, dtype=np.float64)
+    _q3_sigs().mzo_zipf_cdf(theta, n, _ptr(cdf))
+    return cdf
+
+
+def gen_cfg4(seed, first, n, cdf, as_f64=False):
+    out = np.zeros(n, dtype=R32)
+    _q3_sigs().mzo_gen_cfg4(seed, first, n, _ptr(cdf), len(cdf), 1 if as_f64 else 0, _ptr(out))
+    return out

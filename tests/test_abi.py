@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports
+every symbol include/mzgpu.h declares, the ctypes table covers them all, and
+without a CUDA device the product path fails loudly (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "mzgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mzgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    from materialize_b200 import _ffi
+
+    names = declared_functions()
+    assert len(names) >= 55
+    for name in names:
+        assert hasattr(_ffi.lib, name), f"libmzgpu.so does not export {name}"
+    assert set(names) == set(_ffi.SIGNATURES), set(names) ^ set(_ffi.SIGNATURES)
+
+
+def test_row_layouts_match_header():
+    from materialize_b200 import _ffi
+
+    assert _ffi.R16.itemsize == 16 and _ffi.R32.itemsize == 32 and _ffi.R40.itemsize == 40
+    assert _ffi.RACC.itemsize == 80 and _ffi.ROUT.itemsize == 64
+    import ctypes as C
+
+    assert C.sizeof(_ffi.Closure) == 144
+    assert C.sizeof(_ffi.Desc) == 24 and C.sizeof(_ffi.Stats) == 56
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import materialize_b200 as mz
+
+    with pytest.raises(mz.MzGpuError) as e:
+        mz.Context(0)
+    assert e.value.status == -2  # MZGPU_E_CUDA
+
+
+def test_route_matches_oracle(oracle):
+    import materialize_b200 as mz
+
+    for peers in (1, 2, 3, 8):
+        for key in (0, 1, 2, 12345678901234567, 2**64 - 1):
+            assert mz.route(key, peers) == oracle.lib().mzo_route(key, peers)
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under materialize_b200/ may import, link or load oracle/."""
+    pkg = os.path.join(ROOT, "materialize_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "libmzoracle" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert not re.search(r'#include\s+"[^"]*oracle/', text), f

@@ -1,0 +1,189 @@
+"""The oracle's join / half_join / reduce restatements have no unit-level golden
+vectors in the reference ("parity unpinned"); they are validated
+by algebraic identities and by agreement between independent formulations."""
+import numpy as np
+import pytest
+
+
+def rand_r32(B, rng, n, key_hi, val_hi, time_lo, time_hi):
+    a = np.zeros(n, dtype=B.R32)
+    a["key"] = rng.integers(0, key_hi, size=n, dtype=np.uint64)
+    a["val"] = rng.integers(0, val_hi, size=n, dtype=np.uint64)
+    a["time"] = rng.integers(time_lo, time_hi, size=n, dtype=np.uint64)
+    a["diff"] = rng.integers(-2, 3, size=n, dtype=np.int64)
+    return a
+
+
+def brute_join(a, b):
+    by_key = {}
+    for r in b.tolist():
+        by_key.setdefault(r[0], []).append(r)
+    out = []
+    for k, v1, t1, d1 in a.tolist():
+        for _, v2, t2, d2 in by_key.get(k, ()):
+            out.append((k, v1, v2, max(t1, t2), d1 * d2))
+    return out
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2])
+def test_join_core_equals_bruteforce(oracle, strategy):
+    """A7: every pair of updates is joined exactly once, whatever the batch arrival
+    order, and both join_key strategies give the same consolidated output."""
+    B = oracle
+    rng = np.random.default_rng(strategy)
+    s1, s2 = B.Spine(32, 1, True), B.Spine(32, 1, True)
+    j = B.Join(s1, s2, None, strategy)
+    A, Bb = [], []
+    for t in range(0, 12, 2):
+        order = [0, 1] if (t // 2) % 2 == 0 else [1, 0]
+        for side in order:
+            # few keys, many times per key so the linear time scan path (>= 10 edits) runs
+            a = rand_r32(B, rng, int(rng.integers(0, 400)), 6, 3, t, t + 2)
+            (A if side == 0 else Bb).append(a)
+            batch = B.Batch.build(a, t, t + 2)
+            (s1 if side == 0 else s2).insert(batch)
+            j.push(side, batch, t)
+        j.work()
+    got = B.consolidate(j.results())
+    want = B.consolidate(B.rows(B.R40, brute_join(np.concatenate(A), np.concatenate(Bb))))
+    assert got.tobytes() == want.tobytes()
+
+
+def test_half_join_tiebreak_counts_each_pair_once(oracle):
+    """A8: with `le` on one path and `lt` on the other, the two delta paths together
+    produce exactly the change of the full join (no pair counted twice or missed)."""
+    B = oracle
+    rng = np.random.default_rng(7)
+    sa, sb = B.Spine(32, 1, True), B.Spine(32, 1, True)
+    total = []
+    accA, accB = [], []
+    for t in range(5):
+        a = rand_r32(B, rng, 300, 40, 5, t, t + 1)
+        b = rand_r32(B, rng, 300, 40, 5, t, t + 1)
+        ba, bb = B.Batch.build(a, t, t + 1), B.Batch.build(b, t, t + 1)
+        sa.insert(ba)
+        sb.insert(bb)
+        # path A (relation 0): lookups into B use `le`; path B (relation 1): lookups into A use `lt`
+        cl_a = B.make_closure(key_fields=[(0, 0, 64, 0)], val_fields=[(1, 0, 8, 0), (2, 0, 8, 8)])
+        cl_b = B.make_closure(key_fields=[(0, 0, 64, 0)], val_fields=[(2, 0, 8, 0), (1, 0, 8, 8)])
+        total.append(B.half_join(B.update_stream(ba), sb, 0, cl_a))
+        total.append(B.half_join(B.update_stream(bb), sa, 1, cl_b))
+        accA.append(a)
+        accB.append(b)
+    got = B.consolidate(np.concatenate(total))
+    full = brute_join(B.consolidate(np.concatenate(accA)), B.consolidate(np.concatenate(accB)))
+    want = B.consolidate(B.rows(B.R32, [(k, v1 | (v2 << 8), t, d) for k, v1, v2, t, d in full]))
+    assert got.tobytes() == want.tobytes()
+
+
+def test_reduce_accumulates_to_group_by(oracle):
+    """A9: the accumulated output collection equals GROUP BY over the accumulated input, at every time."""
+    B = oracle
+    rng = np.random.default_rng(9)
+    r = B.Reduce(0)
+    outputs, inputs = [], []
+    for t in range(6):
+        a = np.zeros(500, dtype=B.R32)
+        a["key"] = rng.integers(0, 30, size=500, dtype=np.uint64)
+        a["val"] = rng.integers(-50, 50, size=500, dtype=np.int64).astype(np.uint64)
+        a["time"] = t
+        a["diff"] = rng.integers(-1, 3, size=500, dtype=np.int64)
+        inputs.append(a)
+        outputs.append(r.step(a, t + 1))
+        acc_in = np.concatenate(inputs)
+        want = {}
+        for k, v, _, d in acc_in.tolist():
+            c, s = want.get(k, (0, 0))
+            v = v - 2**64 if v >= 2**63 else v
+            want[k] = (c + d, s + v * d)
+        want = {k: cs for k, cs in want.items() if cs != (0, 0)}
+        acc_out = np.concatenate(outputs).copy()
+        acc_out["time"] = 0
+        acc_out = B.consolidate(acc_out)
+        got = {}
+        for k, c, lo, hi, flags, _, d, _ in acc_out.tolist():
+            assert d == 1
+            got[k] = (c, (hi << 64) + lo if hi >= 0 else (hi << 64) + lo)
+        assert got == {k: (c, s) for k, (c, s) in want.items()}
+
+
+def q3_bruteforce(tables):
+    """Direct evaluation of Q3 on the accumulated base tables (multisets)."""
+    cust = {}
+    for k, v, _, d in tables[0]:
+        cust[(k, v)] = cust.get((k, v), 0) + d
+    orders = {}
+    for k, v, _, d in tables[1]:
+        orders[(k, v)] = orders.get((k, v), 0) + d
+    li = {}
+    for k, v, _, d in tables[3]:
+        li.setdefault(k, {})
+        li[k][v] = li[k].get(v, 0) + d
+    building = {}
+    for (ck, seg), d in cust.items():
+        if seg == 1 and d:
+            building[ck] = building.get(ck, 0) + d
+    out = {}
+    for (ok, v), d in orders.items():
+        if d == 0:
+            continue
+        custkey, odate, prio = v & 0xFFFFFF, (v >> 24) & 0xFFF, (v >> 36) & 1
+        if odate >= 1169 or custkey not in building:
+            continue
+        for lv, ld in li.get(ok, {}).items():
+            ext, disc, ship = (lv >> 3) & 0x1FFFF, (lv >> 20) & 0xF, (lv >> 24) & 0xFFF
+            if ship <= 1169 or ld == 0:
+                continue
+            g = ok | (odate << 32) | (prio << 44)
+            mult = d * ld * building[custkey]
+            c, s = out.get(g, (0, 0))
+            out[g] = (c + mult, s + mult * ext * (100 - disc))
+    return {g: cs for g, cs in out.items() if cs != (0, 0)}
+
+
+@pytest.mark.parametrize("workers", [1, 3])
+def test_q3_dataflow_equals_direct_query(oracle, workers):
+    """Sum over the three delta paths == change of the full join; reduce on top of it
+    accumulates to the GROUP BY of the direct query — checked after hydration and
+    after every update batch, for 1 and for several key-sharded workers."""
+    B = oracle
+    q = B.Q3(seed=7, n_customer=300, n_orders=3000, n_part=400, workers=workers, per_batch=50)
+    tables = {0: [], 1: [], 3: []}
+    outs = []
+
+    def check():
+        acc = np.concatenate(outs).copy()
+        acc["time"] = 0
+        acc = B.consolidate(acc)
+        got = {}
+        for k, c, lo, hi, flags, _, d, _ in acc.tolist():
+            assert d == 1 and flags == 0
+            got[k] = (c, (hi << 64) + lo)
+        assert got == q3_bruteforce(tables)
+
+    q.hydrate()
+    for a in (0, 1, 3):
+        tables[a] += q.inputs(a).tolist()
+    outs.append(q.drain())
+    assert len(outs[0]) > 0
+    check()
+    for b in range(4):
+        q.step(b)
+        for a in (1, 3):
+            tables[a] += q.inputs(a).tolist()
+        outs.append(q.drain())
+        check()
+
+
+def test_q3_workers_agree(oracle):
+    B = oracle
+    res = []
+    for w in (1, 2, 4):
+        q = B.Q3(seed=3, n_customer=200, n_orders=2000, n_part=300, workers=w, per_batch=40)
+        q.hydrate()
+        outs = [q.drain()]
+        for b in range(3):
+            q.step(b)
+            outs.append(q.drain())
+        res.append(np.concatenate(outs).tobytes())
+    assert res[0] == res[1] == res[2]
