@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — update-rows/sec through the TPC-H-Q3-shaped delta join + reduce.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line.  A step is one pass of the hot path over one update batch
+(~100K update rows per GPU at one new timestamp: arrange x4, three delta paths x
+two half_joins, accumulable reduce, compaction).
+
+  value   whole-job update-rows/s with the batch already resident in HBM
+  e2e     the same through the public C-ABI harness with HOST (pinned) buffers:
+          H2D of the batch and D2H of the output corrections inside the timed region
+  roofline  dominant kernel of the step, timed live with CUDA events on the
+          launching stream (mzgpu_profile_*), against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (C++ restatement of the reference algorithms; the
+          Rust reference cannot be built here) on the box's host cores
+
+`--impl reference` times that CPU implementation alone on the same config.
+Multi-GPU (torchrun, one rank per GPU): key-sharded arrangements, NCCL
+all-to-all per exchange point, weak scaling (SF and batch grow with N).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 7
+ORDERS_PER_BATCH_PER_GPU = 10_000  # ~100K update rows (2 order rows + ~8 lineitem rows per replaced order)
+
+
+def scale(sf):
+    return dict(n_customer=150_000 * sf, n_orders=1_500_000 * sf, n_part=200_000 * sf)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------- the CPU reference
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path: the C++ oracle dataflow with
+    all host threads, on the same config / metric / unit."""
+    if rank != 0:
+        return
+    from oracle import binding as B
+
+    cores = os.cpu_count() or 1
+    sf = args.sf
+    q = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU, **scale(sf))
+    t0 = time.time()
+    q.hydrate()
+    hyd = time.time() - t0
+    q.drain()
+    for b in range(args.warmup):
+        q.step(b)
+    rows, secs = 0, 0.0
+    for b in range(args.warmup, args.warmup + args.steps):
+        s, r = q.step(b)
+        secs += s
+        rows += r
+    q.drain()
+    value = rows / secs
+    sample = f"SF={sf} hydrated in {hyd:.1f}s (untimed), {args.steps} batches of ~{rows // max(1, args.steps)} update rows"
+    line = {
+        "impl": "reference",
+        "metric": "update_rows_per_sec",
+        "value": value,
+        "unit": "rows/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1000.0 * secs / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int64",
+        "data": "synthetic",
+        "config": workload_config(sf, 1),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(sf_per_gpu, n):
+    return {
+        "workload": f"TPC-H-Q3-shaped 3-way delta join + accumulable reduce, synthetic SF={sf_per_gpu * n}"
+        f" ({sf_per_gpu}/GPU), ~100K-row update batches per GPU (BASELINE.json configs[2]; configs[4] shape at N>1)",
+        "sf_total": sf_per_gpu * n,
+        "orders_replaced_per_batch": ORDERS_PER_BATCH_PER_GPU * n,
+        "parallelism": f"key-hash sharded x{n}, NCCL all-to-all per exchange point" if n > 1 else "1 GPU",
+        "l2": "inputs_larger_than_l2 (arrangements >= 5 GB/GPU vs 126 MB L2)",
+        "plan": "customer>>orders[custkey]>>lineitem[orderkey]; orders>>customer>>lineitem; lineitem>>orders[orderkey]>>customer",
+    }
+
+
+# ------------------------------------------------------------------- ours
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    import materialize_b200 as mz
+    from materialize_b200 import harness
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    ctx = mz.Context(local_rank, rank, world)
+    if world > 1:
+        # the worker mesh bootstrap stays on the host (timely does its own): rank 0
+        # creates the NCCL id, the others receive it
+        import ctypes as C
+
+        from materialize_b200 import _ffi as F
+
+        idbuf = (C.c_uint8 * F.COMM_ID_BYTES)()
+        if rank == 0:
+            ctx.check(F.lib.mzgpu_comm_unique_id(idbuf))
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = (C.c_uint8 * F.COMM_ID_BYTES)(*t.cpu().tolist())
+        ctx.check(F.lib.mzgpu_comm_init(ctx.h, idbuf))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sf = args.sf * world
+    per_batch = ORDERS_PER_BATCH_PER_GPU * world
+    q = harness.Q3Dataflow(ctx, SEED, per_batch=per_batch, worker=rank, peers=world, **scale(sf))
+    t0 = time.time()
+    hyd_rows = q.hydrate()
+    ctx.sync()
+    hyd_s = time.time() - t0
+    q.clear_out()
+
+    n_warm, n_timed, n_e2e, n_prof = args.warmup, args.steps, args.steps, max(3, min(args.steps, 10))
+    total_batches = n_warm + n_timed + n_warm + n_e2e + n_prof
+    # stage every batch up front (generation is not part of a step)
+    staged, staged_rows = [], []
+    t_first = q.time()
+    for b in range(total_batches):
+        rows = q.stage_batch(b, t_first + b)
+        staged.append([q.staged_copy(a) for a in (1, 2, 3)])
+        staged_rows.append(rows)
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    def run_device_step(b):
+        for a, d in zip((1, 2, 3), staged[b]):
+            q.stage_device(a, d)
+        q.step()
+        q.clear_out()
+
+    # ---- device-resident timing
+    b = 0
+    for _ in range(n_warm):
+        run_device_step(b)
+        b += 1
+    launches0 = ctx.stats()["kernel_launches"]
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    rows_timed = 0
+    for _ in range(n_timed):
+        run_device_step(b)
+        rows_timed += staged_rows[b]
+        b += 1
+    e1.record(ext)
+    barrier()
+    clk = clocks.stop()
+    ms = allmax(e0.elapsed_time(e1))
+    launches = ctx.stats()["kernel_launches"] - launches0
+    total_rows = allsum(rows_timed)
+    value = total_rows / (ms / 1000.0)
+
+    # ---- end to end: pinned host inputs, H2D + D2H inside the timed region
+    host_batches = []
+    for bb in range(b, b + n_warm + n_e2e):
+        hb = []
+        for d in staged[bb]:
+            arr = d.download()
+            pin = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+            view = pin.numpy().view(mz.R32)
+            view[:] = arr
+            hb.append((pin, view))
+        host_batches.append(hb)
+    out_pin = torch.empty(64 * 4_000_000, dtype=torch.uint8).pin_memory()
+    out_view = out_pin.numpy().view(mz.ROUT)
+
+    def run_host_step(hb):
+        for a, (_, view) in zip((1, 2, 3), hb):
+            q.stage_host(a, view)
+        q.step()
+        res = q.out_rows(into=out_view)
+        q.clear_out()
+        return len(res)
+
+    for i in range(n_warm):
+        run_host_step(host_batches[i])
+        b += 1
+    barrier()
+    s0 = ctx.stats()
+    e0.record(ext)
+    rows_e2e, out_rows = 0, 0
+    for i in range(n_warm, n_warm + n_e2e):
+        out_rows += run_host_step(host_batches[i])
+        rows_e2e += staged_rows[b]
+        b += 1
+    e1.record(ext)
+    barrier()
+    ms_e2e = allmax(e0.elapsed_time(e1))
+    s1 = ctx.stats()
+    e2e_value = allsum(rows_e2e) / (ms_e2e / 1000.0)
+    h2d = (s1["h2d_bytes"] - s0["h2d_bytes"]) / n_e2e
+    d2h = (s1["d2h_bytes"] - s0["d2h_bytes"]) / n_e2e
+
+    # ---- live per-kernel timing (CUDA events around every launch) for the roofline
+    ctx.profile(True)
+    ctx.profile_report()
+    for _ in range(n_prof):
+        run_device_step(b)
+        b += 1
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    ranked = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    top_name, top = ranked[0]
+    with_bytes = [kv for kv in ranked if kv[1]["bytes"] > 0]
+    dom_name, dom = with_bytes[0] if with_bytes else ranked[0]
+    peak, peak_kind = measured_peak()
+    achieved = dom["bytes"] / (dom["ms"] / 1000.0) / 1e9 if dom["ms"] > 0 else 0.0
+    roofline = {
+        "bound": "hbm",
+        "kernel": dom_name,
+        "achieved": achieved,
+        "peak": peak,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "launches_per_step": dom["launches"] / n_prof,
+        "avg_launch_us": 1000.0 * dom["ms"] / max(1, dom["launches"]),
+        "algorithmic_bytes_per_launch": dom["bytes"] / max(1, dom["launches"]),
+        "share_of_kernel_time": dom["ms"] / tot_ms,
+        "kernel_time_per_step_ms": tot_ms / n_prof,
+        "top_kernels": [
+            {"kernel": k, "share": round(v["ms"] / tot_ms, 4), "launches_per_step": v["launches"] / n_prof,
+             "gbps": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+            for k, v in ranked[:8]
+        ],
+    }
+
+    line = {
+        "metric": "update_rows_per_sec",
+        "value": value,
+        "unit": "rows/s",
+        "n_gpus": world,
+        "steps": n_timed,
+        "warmup": n_warm,
+        "ms_per_step": ms / n_timed,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int64",
+        "data": "synthetic",
+        "config": workload_config(args.sf, world),
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / n_e2e, "out_rows_per_step": out_rows / n_e2e},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "hydration": {"rows": allsum(hyd_rows), "seconds": allmax(hyd_s)},
+        "device_bytes_peak": ctx.stats()["device_bytes_peak"],
+    }
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as B
+
+        cores = os.cpu_count() or 1
+        t0 = time.time()
+        o = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU, **scale(args.sf))
+        o.hydrate()
+        o.drain()
+        hyd_cpu = time.time() - t0
+        nb = args.cpu_batches
+        o.step(0)
+        rows_c, secs_c = 0, 0.0
+        for bb in range(1, 1 + nb):
+            s, r = o.step(bb)
+            secs_c += s
+            rows_c += r
+        line["cpu_baseline"] = {
+            "value": rows_c / secs_c,
+            "unit": "rows/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"same workload: SF={args.sf} hydrated ({hyd_cpu:.1f}s, untimed), {nb} update batches of ~{rows_c // nb} rows,"
+            f" {cores} worker threads; C++ restatement of the reference CPU algorithms (Rust toolchain unavailable)",
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sf", type=int, default=10, help="TPC-H scale factor per GPU")
+    ap.add_argument("--cpu-batches", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
+        sys.exit(2)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,13 @@ typedef struct mzgpu_stats {
   uint64_t d2h_bytes;
 } mzgpu_stats;
 int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out);
+/* Per-kernel device timing (CUDA events on the ctx stream around every launch).
+ * Off by default; the measurement harness switches it on for a profiling pass
+ * (it adds two event records per launch).  mzgpu_profile_report writes one line
+ * per kernel: "name launches total_ms algorithmic_bytes\n", NUL terminated;
+ * returns MZGPU_E_CAPACITY if `cap` is too small.  Reading the report resets it. */
+int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on);
+int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap);
 /* The CUDA stream all of this ctx's work is issued on (a cudaStream_t), so a
  * host harness can bracket it with its own events. */
 void* mzgpu_ctx_stream(mzgpu_ctx* ctx);

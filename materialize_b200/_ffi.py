@@ -111,6 +111,8 @@ SIGNATURES = {
     "mzgpu_ctx_sync": (i32, [vp]),
     "mzgpu_ctx_stats": (i32, [vp, C.POINTER(Stats)]),
     "mzgpu_ctx_stream": (vp, [vp]),
+    "mzgpu_profile_enable": (i32, [vp, i32]),
+    "mzgpu_profile_report": (i32, [vp, C.c_char_p, u64]),
     "mzgpu_buf_new": (i32, [vp, u32, PV]),
     "mzgpu_buf_free": (None, [vp]),
     "mzgpu_buf_len": (u64, [vp]),

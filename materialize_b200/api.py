@@ -93,6 +93,20 @@ class Context:
     def stream(self):
         return F.lib.mzgpu_ctx_stream(self.h)
 
+    def profile(self, on=True):
+        """Bracket every kernel launch with CUDA events on the ctx stream."""
+        self.check(F.lib.mzgpu_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel: {launches, ms, bytes}} since the last report."""
+        buf = C.create_string_buffer(1 << 20)
+        self.check(F.lib.mzgpu_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, launches, ms, nbytes = line.rsplit(" ", 3)
+            out[name] = {"launches": int(launches), "ms": float(ms), "bytes": int(nbytes)}
+        return out
+
     def close(self):
         if self.h:
             F.lib.mzgpu_ctx_destroy(self.h)

@@ -32,6 +32,16 @@ struct mzgpu_ctx {
   // pinned bounce buffers for host<->device row copies
   void* h_bounce = nullptr;
   size_t h_bounce_bytes = 0;
+  // per-kernel profiling (mzgpu_profile_enable)
+  struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+    u64 bytes;
+  };
+  bool profile = false;
+  u64 next_bytes = 0;  // algorithmic bytes of the next launch (MZ_BYTES)
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
   // NCCL (resolved with dlopen at mzgpu_comm_init)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -67,11 +77,43 @@ struct mzgpu_ctx {
     if ((ctx)->sticky) return MZGPU_E_CUDA;     \
   } while (0)
 
+// Brackets one launch with CUDA events on the launching stream when profiling.
+struct ProfScope {
+  mzgpu_ctx* ctx;
+  mzgpu_ctx::ProfRec rec;
+  bool on;
+  ProfScope(mzgpu_ctx* c, const char* name) : ctx(c), on(c->profile) {
+    if (!on) return;
+    rec.name = name;
+    rec.bytes = c->next_bytes;
+    for (cudaEvent_t* e : {&rec.e0, &rec.e1}) {
+      if (!c->ev_pool.empty()) {
+        *e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+      } else {
+        cudaEventCreate(e);
+      }
+    }
+    cudaEventRecord(rec.e0, c->stream);
+  }
+  ~ProfScope() {
+    ctx->next_bytes = 0;
+    if (!on) return;
+    cudaEventRecord(rec.e1, ctx->stream);
+    ctx->prof.push_back(rec);
+  }
+};
+// algorithmic bytes the next launch moves (documented per kernel in DESIGN.md)
+#define MZ_BYTES(ctx, n) ((ctx)->next_bytes = (u64)(n))
+
 // Kernel launch helper: counts launches (mzgpu_stats.kernel_launches) and
 // surfaces launch-configuration errors immediately.
 #define MZ_LAUNCH(ctx, kernel, grid, block, smem, ...)                              \
   do {                                                                              \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+    {                                                                               \
+      ProfScope _prof(ctx, #kernel);                                                \
+      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);              \
+    }                                                                               \
     (ctx)->stats.kernel_launches++;                                                 \
     MZ_CUDA(ctx, cudaGetLastError());                                               \
   } while (0)

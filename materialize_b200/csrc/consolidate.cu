@@ -155,8 +155,10 @@ int32_t consolidate_sorted_t(mzgpu_ctx* ctx, const u64* rows, u64 n, u64* out, u
   u64* d_nseg = ctx->d_scratch + 16;
   u64* d_nout = ctx->d_scratch + 17;
   MZ_CUDA(ctx, cudaMemsetAsync(seg_sums.p, 0, n * 8 * ND, ctx->stream));
+  MZ_BYTES(ctx, n * NK * 8);
   MZ_LAUNCH(ctx, (k_heads<NW, NK>), (unsigned)n_tiles, CT, 0, rows, n, tiles.as<u32>());
   MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_nseg);
+  MZ_BYTES(ctx, n * (NW * 8 + 4));
   MZ_LAUNCH(ctx, (k_segsum<NW, NK, ND>), (unsigned)n_tiles, CT, 0, rows, n, tiles.as<u32>(),
             seg_sums.as<u64>(), seg_first.as<u32>());
   MZ_LAUNCH(ctx, (k_nz<ND>), (unsigned)n_tiles, CT, 0, seg_sums.as<u64>(), d_nseg, tiles.as<u32>());
@@ -174,6 +176,7 @@ template <int RB>
 int32_t gather_t(mzgpu_ctx* ctx, const u64* rows, const u32* perm, u64 n, u64* out) {
   constexpr int NW = RowT<RB>::NW;
   if (n == 0) return MZGPU_OK;
+  MZ_BYTES(ctx, n * (4 + 2 * NW * 8));
   MZ_LAUNCH(ctx, (k_gather<NW>), (unsigned)((n + 255) / 256), 256, 0, rows, perm, n, out);
   return MZGPU_OK;
 }

@@ -1,0 +1,402 @@
+// harness.cu — a minimal "timely worker" over the C ABI (libmzgpu_harness.so).
+//
+// No Rust toolchain exists in this image, so this C++ harness stands in for the
+// timely worker + mz_compute::render: it owns frontiers (plain u64 times), seals
+// arrangements when the input frontier advances, and wires the rendered shape of
+// the TPC-H-Q3 delta join + accumulable reduce together EXACTLY as
+// render_delta_join (src/compute/src/render/join/delta_join.rs:50-311) and
+// build_accumulable (src/compute/src/render/reduce.rs:1261-1471) do — using
+// nothing but the public entry points of include/mzgpu.h with device pointers.
+// The only CUDA code here is the seeded synthetic-input generation (gen.h), so
+// that benchmark inputs are born in HBM.
+//
+// Per timestamp t (one update batch), on every worker/GPU:
+//   inputs --Exchange(key)--> Batcher::push_container -> seal(t+1) -> Trace::insert   (x4 arrangements)
+//   for each delta path: build_update_stream -> [Exchange -> half_join] x2 -> concat
+//   --Exchange(group key)--> explode / arrange / reduce_abelian -> output corrections
+//   logical compaction to t, physical compaction to t+1, idle merge effort
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <utility>
+#include <vector>
+
+#include "../../include/mzgpu.h"
+#include "gen.h"
+#include "q3_plan.h"
+
+namespace {
+
+struct DevArr {
+  void* p = nullptr;
+  ~DevArr() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess ? 0 : -1;
+  }
+};
+
+__global__ void k_gen_customers(uint64_t seed, uint64_t first, uint64_t n, mzgpu_r32* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mzg_q3_customer(seed, first + i);
+}
+
+// orders [first, first + n) at `version` with multiplicity `diff` and time `t`;
+// lineitems are appended through an atomic cursor (order is irrelevant: the
+// batcher sorts).
+__global__ void k_gen_orders(uint64_t seed, mzg_q3_scale sc, uint64_t first, uint64_t n, int tick,
+                             uint64_t version, uint64_t t, int64_t diff, uint64_t out_base,
+                             mzgpu_r32* o_ok, mzgpu_r32* o_ck, mzgpu_r32* li,
+                             unsigned long long* li_cursor) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t j = tick ? mzg_q3_tick_order(first + i, sc) : first + i;
+  mzg_q3_order o;
+  mzg_q3_order_row(seed, sc, j, version, &o);
+  mzgpu_r32 r;
+  r.time = t;
+  r.diff = diff;
+  r.key = o.orderkey;
+  r.val = mzg_q3_orders_by_orderkey_val(&o);
+  o_ok[out_base + i] = r;
+  r.key = o.custkey;
+  r.val = mzg_q3_orders_by_custkey_val(&o);
+  o_ck[out_base + i] = r;
+  unsigned long long at = atomicAdd(li_cursor, (unsigned long long)o.n_lineitems);
+  for (uint32_t l = 0; l < o.n_lineitems; ++l) {
+    r.key = o.orderkey;
+    r.val = o.lineitem_val[l];
+    li[at + l] = r;
+  }
+}
+
+__global__ void k_gen_cfg1(uint64_t seed, uint64_t first, uint64_t n, uint32_t key_bits, mzgpu_r16* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mzg_cfg1_row(seed, first + i, key_bits);
+}
+__global__ void k_gen_cfg2(uint64_t seed, uint64_t first, uint64_t n, uint64_t n_keys, mzgpu_r32* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = mzg_cfg2_row(seed, first + i, n_keys);
+}
+__global__ void k_gen_cfg4(uint64_t seed, uint64_t first, uint64_t n, const double* cdf, uint64_t n_keys,
+                           int as_f64, uint64_t t, int64_t diff, mzgpu_r32* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    mzgpu_r32 r = mzg_cfg4_row(seed, first + i, cdf, n_keys, as_f64);
+    r.time = t;
+    r.diff = diff;
+    out[i] = r;
+  }
+}
+
+}  // namespace
+
+#define H_TRY(expr)                 \
+  do {                              \
+    int32_t _s = (expr);            \
+    if (_s != MZGPU_OK) return _s;  \
+  } while (0)
+#define H_CUDA(expr)                                   \
+  do {                                                 \
+    if ((expr) != cudaSuccess) return MZGPU_E_CUDA;    \
+  } while (0)
+
+struct mzh_q3 {
+  mzgpu_ctx* ctx;
+  cudaStream_t stream;
+  uint64_t seed;
+  mzg_q3_scale sc;
+  uint64_t per_batch;
+  uint32_t worker, peers;
+  mzg_q3_plan plan;
+  mzgpu_batcher* batcher[4];
+  mzgpu_spine* spine[4];
+  mzgpu_reduce* reduce;
+  mzgpu_buf* input[4];  // staged inputs of the next step (device resident)
+  mzgpu_buf *stream_buf, *next_buf, *results, *xchg, *out;
+  DevArr gen_ok, gen_ck, gen_li, gen_cursor;
+  uint64_t gen_cap_orders = 0;
+  uint64_t next_time = 0;
+  uint64_t last_rows_in = 0;
+};
+
+static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, int n_versions, uint64_t t,
+                             uint64_t* n_li) {
+  // capacity for n orders x n_versions
+  uint64_t need = n * n_versions;
+  if (need > q->gen_cap_orders || q->gen_cursor.p == nullptr) {
+    if (q->gen_ok.alloc(need * 32) || q->gen_ck.alloc(need * 32) || q->gen_li.alloc(need * 7 * 32) ||
+        q->gen_cursor.alloc(8))
+      return MZGPU_E_CUDA;
+    q->gen_cap_orders = need;
+  }
+  H_CUDA(cudaMemsetAsync(q->gen_cursor.p, 0, 8, q->stream));
+  if (n) {
+    unsigned grid = (unsigned)((n + 255) / 256);
+    for (int ver = 0; ver < n_versions; ++ver) {
+      int64_t diff = (n_versions == 2 && ver == 0) ? -1 : 1;
+      k_gen_orders<<<grid, 256, 0, q->stream>>>(q->seed, q->sc, first, n, tick, (uint64_t)ver, t, diff,
+                                                (uint64_t)ver * n, (mzgpu_r32*)q->gen_ok.p,
+                                                (mzgpu_r32*)q->gen_ck.p, (mzgpu_r32*)q->gen_li.p,
+                                                (unsigned long long*)q->gen_cursor.p);
+    }
+    H_CUDA(cudaGetLastError());
+  }
+  unsigned long long h = 0;
+  H_CUDA(cudaMemcpyAsync(&h, q->gen_cursor.p, 8, cudaMemcpyDeviceToHost, q->stream));
+  H_CUDA(cudaStreamSynchronize(q->stream));
+  *n_li = h;
+  return MZGPU_OK;
+}
+
+// Exchange(key) then Batcher::push_container for arrangement `a`
+static int32_t q3_arrange_push(mzh_q3* q, int a, mzgpu_buf* rows) {
+  mzgpu_buf* src = rows;
+  if (q->peers > 1) {
+    H_TRY(mzgpu_exchange(q->ctx, rows, q->xchg));
+    src = q->xchg;
+  }
+  return mzgpu_batcher_push(q->batcher[a], mzgpu_buf_device_ptr(src), mzgpu_buf_len(src), MZGPU_MEM_DEVICE);
+}
+
+// everything after the inputs were pushed: seal, paths, reduce, compaction
+static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
+  const uint64_t upper = t + 1;
+  mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
+  int32_t st = MZGPU_OK;
+  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
+    st = mzgpu_batcher_seal(q->batcher[a], upper, &batch[a], nullptr);
+    if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
+    if (st == MZGPU_OK) st = mzgpu_spine_set_physical_compaction(q->spine[a], upper);
+  }
+  if (st == MZGPU_OK) st = mzgpu_buf_clear(q->results);
+  for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
+    st = mzgpu_buf_clear(q->stream_buf);
+    // as_of rule: only the first relation's path sees the updates at as_of (= 0)
+    if (st == MZGPU_OK)
+      st = mzgpu_update_stream(q->ctx, batch[q->plan.source[path]], &q->plan.initial[path],
+                               path == 0 ? MZGPU_FRONTIER_EMPTY : 0, q->stream_buf);
+    for (int s = 0; s < 2 && st == MZGPU_OK; ++s) {
+      if (q->peers > 1) {  // half_join exchanges its stream by key
+        st = mzgpu_exchange(q->ctx, q->stream_buf, q->xchg);
+        std::swap(q->stream_buf, q->xchg);
+        if (st != MZGPU_OK) break;
+      }
+      st = mzgpu_buf_clear(q->next_buf);
+      if (st == MZGPU_OK)
+        st = mzgpu_half_join(q->ctx, (const mzgpu_r32*)mzgpu_buf_device_ptr(q->stream_buf),
+                             mzgpu_buf_len(q->stream_buf), MZGPU_MEM_DEVICE,
+                             q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
+                             &q->plan.stage[path][s], 0, q->next_buf);
+      std::swap(q->stream_buf, q->next_buf);
+    }
+    if (st == MZGPU_OK)
+      st = mzgpu_buf_append(q->results, mzgpu_buf_device_ptr(q->stream_buf), mzgpu_buf_len(q->stream_buf),
+                            MZGPU_MEM_DEVICE);
+  }
+  if (st == MZGPU_OK && q->peers > 1) {
+    st = mzgpu_exchange(q->ctx, q->results, q->xchg);
+    std::swap(q->results, q->xchg);
+  }
+  if (st == MZGPU_OK)
+    st = mzgpu_reduce_accumulable(q->reduce, (const mzgpu_r32*)mzgpu_buf_device_ptr(q->results),
+                                  mzgpu_buf_len(q->results), MZGPU_MEM_DEVICE, upper, q->out);
+  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
+    st = mzgpu_spine_set_logical_compaction(q->spine[a], t);
+    uint64_t e = mzgpu_spine_exert_logic(q->spine[a], 16);
+    if (st == MZGPU_OK && e) st = mzgpu_spine_exert(q->spine[a], e, nullptr);
+  }
+  if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(mzgpu_reduce_input_trace(q->reduce), t);
+  for (int a = 0; a < 4; ++a)
+    if (batch[a]) mzgpu_batch_release(batch[a]);
+  return st;
+}
+
+extern "C" {
+
+int32_t mzh_q3_new(mzgpu_ctx* ctx, uint64_t seed, uint64_t n_customer, uint64_t n_orders, uint64_t n_part,
+                   uint64_t per_batch, uint32_t worker, uint32_t peers, mzh_q3** out) {
+  if (ctx == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  mzh_q3* q = new mzh_q3();
+  q->ctx = ctx;
+  q->stream = (cudaStream_t)mzgpu_ctx_stream(ctx);
+  q->seed = seed;
+  q->sc.n_customer = n_customer;
+  q->sc.n_orders = n_orders;
+  q->sc.n_part = n_part;
+  q->per_batch = per_batch;
+  q->worker = worker;
+  q->peers = peers;
+  mzg_q3_plan_init(&q->plan);
+  *out = q;
+  for (int a = 0; a < 4; ++a) {
+    H_TRY(mzgpu_batcher_new(ctx, MZGPU_ROW_R32, &q->batcher[a]));
+    H_TRY(mzgpu_spine_new(ctx, MZGPU_ROW_R32, 1, &q->spine[a]));
+    H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->input[a]));
+  }
+  H_TRY(mzgpu_reduce_new(ctx, MZGPU_AGG_COUNT_SUM_I64, &q->reduce));
+  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->stream_buf));
+  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->next_buf));
+  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->results));
+  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->xchg));
+  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_ROUT, &q->out));
+  return MZGPU_OK;
+}
+
+void mzh_q3_free(mzh_q3* q) {
+  if (q == nullptr) return;
+  for (int a = 0; a < 4; ++a) {
+    mzgpu_batcher_free(q->batcher[a]);
+    mzgpu_spine_free(q->spine[a]);
+    mzgpu_buf_free(q->input[a]);
+  }
+  mzgpu_reduce_free(q->reduce);
+  mzgpu_buf_free(q->stream_buf);
+  mzgpu_buf_free(q->next_buf);
+  mzgpu_buf_free(q->results);
+  mzgpu_buf_free(q->xchg);
+  mzgpu_buf_free(q->out);
+  delete q;
+}
+
+// Hydration: every base table arrives at time 0.  Each worker generates its
+// slice of the source rows (chunked), exchanges them and pushes them into the
+// batchers; then the timestamp runs.  *rows_in = rows this worker generated.
+int32_t mzh_q3_hydrate(mzh_q3* q, uint64_t* rows_in) {
+  if (q == nullptr) return MZGPU_E_INVALID;
+  uint64_t total = 0;
+  mzgpu_buf* tmp = q->input[0];
+  {  // customers
+    uint64_t lo = q->sc.n_customer * q->worker / q->peers, hi = q->sc.n_customer * (q->worker + 1) / q->peers;
+    DevArr c;
+    if (c.alloc((hi - lo) * 32)) return MZGPU_E_CUDA;
+    if (hi > lo) {
+      k_gen_customers<<<(unsigned)((hi - lo + 255) / 256), 256, 0, q->stream>>>(q->seed, lo, hi - lo,
+                                                                              (mzgpu_r32*)c.p);
+      H_CUDA(cudaGetLastError());
+    }
+    H_TRY(mzgpu_buf_upload(tmp, c.p, hi - lo, MZGPU_MEM_DEVICE));
+    H_TRY(q3_arrange_push(q, 0, tmp));
+    H_CUDA(cudaStreamSynchronize(q->stream));
+    total += hi - lo;
+  }
+  const uint64_t lo = q->sc.n_orders * q->worker / q->peers, hi = q->sc.n_orders * (q->worker + 1) / q->peers;
+  const uint64_t CHUNK = 4u << 20;
+  // all peers must make the same number of exchange calls
+  const uint64_t max_slice = (q->sc.n_orders + q->peers - 1) / q->peers + 1;
+  const uint64_t n_chunks = (max_slice + CHUNK - 1) / CHUNK;
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    uint64_t first = lo + c * CHUNK;
+    uint64_t n = first < hi ? (hi - first < CHUNK ? hi - first : CHUNK) : 0;
+    uint64_t n_li = 0;
+    H_TRY(q3_gen_orders(q, first, n, 0, 1, 0, &n_li));
+    H_TRY(mzgpu_buf_upload(tmp, q->gen_ok.p, n, MZGPU_MEM_DEVICE));
+    H_TRY(q3_arrange_push(q, 1, tmp));
+    H_TRY(mzgpu_buf_upload(tmp, q->gen_ck.p, n, MZGPU_MEM_DEVICE));
+    H_TRY(q3_arrange_push(q, 2, tmp));
+    H_TRY(mzgpu_buf_upload(tmp, q->gen_li.p, n_li, MZGPU_MEM_DEVICE));
+    H_TRY(q3_arrange_push(q, 3, tmp));
+    total += n + n_li;
+  }
+  H_TRY(mzgpu_buf_clear(tmp));
+  if (rows_in) *rows_in = total;
+  H_TRY(q3_run_timestamp(q, 0));
+  q->next_time = 1;
+  return MZGPU_OK;
+}
+
+// Stage update batch `b` (this worker's share of the tick's order replacements)
+// in device memory: not part of the timed step.  *rows_in = staged update rows
+// (orders counted once, as in the oracle).
+int32_t mzh_q3_stage_batch(mzh_q3* q, uint64_t b, uint64_t t, uint64_t* rows_in) {
+  if (q == nullptr) return MZGPU_E_INVALID;
+  const uint64_t x0 = b * q->per_batch;
+  const uint64_t lo = x0 + q->per_batch * q->worker / q->peers, hi = x0 + q->per_batch * (q->worker + 1) / q->peers;
+  uint64_t n_li = 0;
+  H_TRY(q3_gen_orders(q, lo, hi - lo, 1, 2, t, &n_li));
+  H_TRY(mzgpu_buf_clear(q->input[0]));
+  H_TRY(mzgpu_buf_upload(q->input[1], q->gen_ok.p, 2 * (hi - lo), MZGPU_MEM_DEVICE));
+  H_TRY(mzgpu_buf_upload(q->input[2], q->gen_ck.p, 2 * (hi - lo), MZGPU_MEM_DEVICE));
+  H_TRY(mzgpu_buf_upload(q->input[3], q->gen_li.p, n_li, MZGPU_MEM_DEVICE));
+  q->last_rows_in = 2 * (hi - lo) + n_li;
+  if (rows_in) *rows_in = q->last_rows_in;
+  return mzgpu_ctx_sync(q->ctx);
+}
+
+// Stage host rows for arrangement `a` (the end-to-end path: the H2D copy is
+// issued here, on the ctx stream, inside the caller's timed region).
+int32_t mzh_q3_stage_host(mzh_q3* q, int32_t a, const mzgpu_r32* rows, uint64_t n) {
+  if (q == nullptr || a < 0 || a > 3) return MZGPU_E_INVALID;
+  return mzgpu_buf_upload(q->input[a], rows, n, MZGPU_MEM_HOST);
+}
+
+// Stage rows that already live in device memory (a D2D copy on the ctx stream).
+int32_t mzh_q3_stage_device(mzh_q3* q, int32_t a, const mzgpu_r32* d_rows, uint64_t n) {
+  if (q == nullptr || a < 0 || a > 3) return MZGPU_E_INVALID;
+  return mzgpu_buf_upload(q->input[a], d_rows, n, MZGPU_MEM_DEVICE);
+}
+mzgpu_buf* mzh_q3_input(mzh_q3* q, int32_t a) { return (q && a >= 0 && a < 4) ? q->input[a] : nullptr; }
+
+// Copy the staged device inputs of arrangement `a` to the host (to build the
+// host-resident copies for the end-to-end measurement and for parity tests).
+int32_t mzh_q3_staged(mzh_q3* q, int32_t a, mzgpu_r32* rows, uint64_t cap, uint64_t* n) {
+  if (q == nullptr || a < 0 || a > 3) return MZGPU_E_INVALID;
+  return mzgpu_buf_download(q->input[a], rows, cap, MZGPU_MEM_HOST, n);
+}
+
+// One timestamp over the staged inputs (inputs already resident in HBM).
+int32_t mzh_q3_step(mzh_q3* q) {
+  if (q == nullptr) return MZGPU_E_INVALID;
+  const uint64_t t = q->next_time;
+  for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
+  H_TRY(q3_run_timestamp(q, t));
+  q->next_time = t + 1;
+  return MZGPU_OK;
+}
+
+// Output corrections (ROUT rows) accumulated since the last clear.
+mzgpu_buf* mzh_q3_out(mzh_q3* q) { return q ? q->out : nullptr; }
+int32_t mzh_q3_clear_out(mzh_q3* q) { return q ? mzgpu_buf_clear(q->out) : MZGPU_E_INVALID; }
+uint64_t mzh_q3_time(mzh_q3* q) { return q ? q->next_time : 0; }
+mzgpu_spine* mzh_q3_spine(mzh_q3* q, int32_t a) { return (q && a >= 0 && a < 4) ? q->spine[a] : nullptr; }
+
+// ---- device-side generators for the other BASELINE configs
+int32_t mzh_gen_cfg1(mzgpu_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, uint32_t key_bits,
+                     mzgpu_buf* out) {
+  DevArr d;
+  if (d.alloc(n * 16)) return MZGPU_E_CUDA;
+  cudaStream_t s = (cudaStream_t)mzgpu_ctx_stream(ctx);
+  if (n) k_gen_cfg1<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seed, first, n, key_bits, (mzgpu_r16*)d.p);
+  H_CUDA(cudaGetLastError());
+  H_TRY(mzgpu_buf_upload(out, d.p, n, MZGPU_MEM_DEVICE));
+  return mzgpu_ctx_sync(ctx);
+}
+int32_t mzh_gen_cfg2(mzgpu_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, uint64_t n_keys,
+                     mzgpu_buf* out) {
+  DevArr d;
+  if (d.alloc(n * 32)) return MZGPU_E_CUDA;
+  cudaStream_t s = (cudaStream_t)mzgpu_ctx_stream(ctx);
+  if (n) k_gen_cfg2<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seed, first, n, n_keys, (mzgpu_r32*)d.p);
+  H_CUDA(cudaGetLastError());
+  H_TRY(mzgpu_buf_upload(out, d.p, n, MZGPU_MEM_DEVICE));
+  return mzgpu_ctx_sync(ctx);
+}
+// `cdf` is the host-built zipf inverse-CDF table (n_keys doubles)
+int32_t mzh_gen_cfg4(mzgpu_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, const double* cdf,
+                     uint64_t n_keys, int32_t as_f64, uint64_t t, int64_t diff, mzgpu_buf* out) {
+  DevArr d, dc;
+  if (d.alloc(n * 32) || dc.alloc(n_keys * 8)) return MZGPU_E_CUDA;
+  cudaStream_t s = (cudaStream_t)mzgpu_ctx_stream(ctx);
+  H_CUDA(cudaMemcpyAsync(dc.p, cdf, n_keys * 8, cudaMemcpyHostToDevice, s));
+  if (n)
+    k_gen_cfg4<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seed, first, n, (const double*)dc.p, n_keys,
+                                                           as_f64, t, diff, (mzgpu_r32*)d.p);
+  H_CUDA(cudaGetLastError());
+  H_TRY(mzgpu_buf_upload(out, d.p, n, MZGPU_MEM_DEVICE));
+  return mzgpu_ctx_sync(ctx);
+}
+
+}  // extern "C"

@@ -51,6 +51,11 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev) cudaEventDestroy(ctx->ev);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -68,6 +73,55 @@ extern "C" int32_t mzgpu_ctx_sync(mzgpu_ctx* ctx) {
 extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   if (ctx == nullptr || out == nullptr) return MZGPU_E_INVALID;
   *out = ctx->stats;
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on) {
+  MZ_CHECK_CTX(ctx);
+  ctx->profile = on != 0;
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap) {
+  MZ_CHECK_CTX(ctx);
+  if (buf == nullptr || cap == 0) return MZGPU_E_INVALID;
+  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  struct Agg {
+    std::string name;
+    u64 launches = 0, bytes = 0;
+    double ms = 0;
+  };
+  std::vector<Agg> aggs;
+  for (auto& r : ctx->prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg* a = nullptr;
+    for (auto& x : aggs)
+      if (x.name == r.name) a = &x;
+    if (a == nullptr) {
+      aggs.push_back(Agg());
+      a = &aggs.back();
+      a->name = r.name;
+    }
+    a->launches++;
+    a->bytes += r.bytes;
+    a->ms += ms;
+    ctx->ev_pool.push_back(r.e0);
+    ctx->ev_pool.push_back(r.e1);
+  }
+  ctx->prof.clear();
+  std::string out;
+  for (auto& a : aggs) {
+    char line[384];
+    std::string nm = a.name;
+    for (auto& ch : nm)
+      if (ch == ' ') ch = '_';
+    snprintf(line, sizeof(line), "%s %llu %.6f %llu\n", nm.c_str(), (unsigned long long)a.launches, a.ms,
+             (unsigned long long)a.bytes);
+    out += line;
+  }
+  if (out.size() + 1 > cap) return MZGPU_E_CAPACITY;
+  memcpy(buf, out.c_str(), out.size() + 1);
   return MZGPU_OK;
 }
 

@@ -149,6 +149,7 @@ int32_t merge_t(mzgpu_ctx* ctx, const u64* A, u64 na, const u64* B, u64 nb, u64 
   MZ_TRY(merged.alloc(ctx, n * RB));
   MZ_LAUNCH(ctx, (k_merge_partition<RB>), (unsigned)((n_tiles + 1 + 255) / 256), 256, 0, A, na, B, nb,
             since, n_tiles, split.as<u64>());
+  MZ_BYTES(ctx, n * 2 * RB);
   MZ_LAUNCH(ctx, (k_merge_tiles<RB>), (unsigned)n_tiles, MT, 0, A, na, B, nb, since, split.as<u64>(),
             merged.as<u64>());
   MZ_TRY(mz_consolidate_sorted(ctx, RB, merged.p, n, out->p, n_out));

@@ -171,10 +171,13 @@ int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& tr
   MZ_TRY(out->alloc(ctx, total * out_rb));
   *n_out = total;
   if (total == 0) return MZGPU_OK;
+  // probe row 32 B + one 16 B slot per batch + 32 B per matched row + output row
+  MZ_BYTES(ctx, n * (32 + 16 * trace.n_batches) + total * (32 + out_rb));
   if (pp.has_closure) {
     MZ_LAUNCH(ctx, (k_probe<4, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
               tiles.as<u32>(), out->as<u64>());
   } else {
+    MZ_BYTES(ctx, n * (32 + 16 * trace.n_batches) + total * (32 + out_rb));
     MZ_LAUNCH(ctx, (k_probe<5, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
               tiles.as<u32>(), out->as<u64>());
   }

@@ -272,6 +272,7 @@ int32_t radix_sort_pairs(mzgpu_ctx* ctx, u64* ka, u32* va, u64* kb, u32* vb, u64
     u64 blocks = (n + 256 * 16 - 1) / (256 * 16);
     u64 maxb = (u64)ctx->num_sms * 8;
     if (blocks > maxb) blocks = maxb;
+    MZ_BYTES(ctx, n * 8);
     MZ_LAUNCH(ctx, k_rs_hist, (unsigned)blocks, 256, 0, ka, n, npass, hist.as<u32>());
     MZ_LAUNCH(ctx, k_rs_scan_hist, 1, 256, 0, hist.as<u32>(), npass);
   }
@@ -284,6 +285,7 @@ int32_t radix_sort_pairs(mzgpu_ctx* ctx, u64* ka, u32* va, u64* kb, u32* vb, u64
   u64 *kin = ka, *kout = kb;
   u32 *vin = va, *vout = vb;
   for (int p = 0; p < npass; ++p) {
+    MZ_BYTES(ctx, n * 24);  // read key+idx (12 B), write key+idx (12 B)
     MZ_LAUNCH(ctx, k_rs_onesweep, (unsigned)n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
               n, 8 * p, hist.as<u32>() + p * 256, state.as<u32>() + (size_t)p * n_tiles * 256,
               counters.as<u32>() + p);
@@ -310,6 +312,7 @@ int32_t sort_perm_t(mzgpu_ctx* ctx, const u64* d_rows, u64 n, DevMem* perm_out) 
     u64 blocks = (n + 255) / 256;
     u64 maxb = (u64)ctx->num_sms * 8;
     if (blocks > maxb) blocks = maxb;
+    MZ_BYTES(ctx, n * NK * 8);
     MZ_LAUNCH(ctx, (k_analyze<NW, NK>), (unsigned)blocks, 256, 0, d_rows, n, ctx->d_scratch);
   }
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * NK * 8, cudaMemcpyDeviceToHost,
@@ -372,6 +375,7 @@ int32_t sort_perm_t(mzgpu_ctx* ctx, const u64* d_rows, u64 n, DevMem* perm_out) 
       std::swap(kdst, kalt);
       std::swap(vdst, valt);
     }
+    MZ_BYTES(ctx, n * (chunks[c].nwords * 8 + 12 + (perm ? 4 : 0)));
     MZ_LAUNCH(ctx, (k_pack<NW>), (unsigned)((n + 255) / 256), 256, 0, d_rows, perm, n, chunks[c], kdst,
               vdst);
     u64* k_res;

@@ -366,3 +366,38 @@ def test_reduce_large_i128_sums(mz, ctx, oracle):
     a["diff"] = -3
     a["time"] = 1
     same(gr.step(a, 2), orr.step(a, 2))
+
+
+# -------------------------------------------------- the whole Q3 dataflow
+def test_q3_dataflow_matches_oracle(mz, ctx, oracle):
+    """Hydration + update batches through the C++ harness (delta join, 3 paths x 2
+    half_joins, reduce) vs the CPU oracle dataflow on the same seeded inputs."""
+    from materialize_b200 import harness
+
+    args = dict(seed=7, n_customer=3000, n_orders=30000, n_part=4000, per_batch=500)
+    g = harness.Q3Dataflow(ctx, **args)
+    o = oracle.Q3(workers=2, **args)
+    g.hydrate()
+    o.hydrate()
+    same(oracle.consolidate(g.out_rows()), o.drain())
+    g.clear_out()
+    for b in range(6):
+        rows = g.stage_batch(b, g.time())
+        _, orows = o.step(b)
+        assert rows == orows
+        # the device generator and the host generator produce the same multiset
+        same(oracle.consolidate(g.staged(3)), oracle.consolidate(o.inputs(3)))
+        g.step()
+        same(oracle.consolidate(g.out_rows()), o.drain())
+        g.clear_out()
+
+
+def test_device_generators_match_host(mz, ctx, oracle):
+    from materialize_b200 import harness
+
+    same(harness.gen_cfg1(ctx, 1, 5000, 20).download(), oracle.gen_cfg1(1, 5000, 20))
+    same(harness.gen_cfg1(ctx, 1, 5000, 64).download(), oracle.gen_cfg1(1, 5000, 64))
+    same(harness.gen_cfg2(ctx, 2, 5000, 10**7).download(), oracle.gen_cfg2(2, 5000, 10**7))
+    cdf = oracle.zipf_cdf(0.9, 10000)
+    same(harness.gen_cfg4(ctx, 3, 5000, cdf).download(), oracle.gen_cfg4(3, 0, 5000, cdf))
+    same(harness.gen_cfg4(ctx, 3, 5000, cdf, as_f64=True).download(), oracle.gen_cfg4(3, 0, 5000, cdf, True))
