@@ -32,6 +32,7 @@ struct mzgpu_ctx {
   // pinned bounce buffers for host<->device row copies
   void* h_bounce = nullptr;
   size_t h_bounce_bytes = 0;
+  void* h_fused = nullptr;  // pinned image of the fused kernel's control block (16 KiB)
   // per-kernel profiling (mzgpu_profile_enable)
   struct ProfRec {
     const char* name;
@@ -382,6 +383,21 @@ int32_t mz_consolidate_sorted(mzgpu_ctx* ctx, int row_bytes, const void* d_sorte
 // sort + gather + consolidate; output array is allocated (capacity n rows).
 int32_t mz_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, DevMem* out,
                             u64* n_out);
+
+// fused.cu: the same pipeline (sort + gather + consolidate, optionally + hash
+// index) as ONE cooperative kernel, for small / medium inputs.  If the composite
+// key needs more than 64 bits `fallback` is set and nothing else is valid.
+struct FusedResult {
+  DevMem rows;   // consolidated output (capacity n rows)
+  DevMem table;  // hash index (if requested)
+  u64 n_out = 0, n_keys = 0, slots = 0;
+  u64 min_time = 0, max_time = 0;  // range of the time word over the INPUT rows
+  bool fallback = false;
+};
+int32_t mz_fused_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, bool want_index,
+                                  FusedResult* res);
+// inputs up to this many rows take the fused path
+#define MZ_FUSED_MAX_ROWS (2u << 20)
 
 // merge.cu: merge two sorted consolidated arrays; times are advanced to
 // max(time, since) on the way; result is consolidated.

@@ -212,6 +212,15 @@ int32_t mz_consolidate_sorted(mzgpu_ctx* ctx, int row_bytes, const void* d_sorte
 int32_t mz_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, DevMem* out,
                             u64* n_out) {
   *n_out = 0;
+  if (n > 0 && n <= MZ_FUSED_MAX_ROWS) {
+    FusedResult fr;
+    MZ_TRY(mz_fused_sort_consolidate(ctx, row_bytes, d_rows, n, false, &fr));
+    if (!fr.fallback) {
+      *out = std::move(fr.rows);
+      *n_out = fr.n_out;
+      return MZGPU_OK;
+    }
+  }
   MZ_TRY(out->alloc(ctx, n * (u64)row_bytes));
   if (n == 0) return MZGPU_OK;
   DevMem perm, sorted;

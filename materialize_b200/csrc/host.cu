@@ -32,6 +32,7 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 128 * 8));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 128 * 8));
+  MZ_CUDA(ctx, cudaMallocHost(&ctx->h_fused, 16384));
   // keep freed blocks cached in the stream-ordered pool
   cudaMemPool_t pool;
   MZ_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -49,6 +50,7 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
     if (f) f(ctx->nccl_comm);
   }
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  if (ctx->h_fused) cudaFreeHost(ctx->h_fused);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev) cudaEventDestroy(ctx->ev);
   for (auto& r : ctx->prof) {
@@ -302,6 +304,37 @@ static int32_t make_batch(mzgpu_ctx* ctx, uint32_t rb, DevMem&& rows, u64 len, m
   *out = b.release();
   return MZGPU_OK;
 }
+// rows + index already built (fused path)
+static int32_t make_batch_indexed(mzgpu_ctx* ctx, uint32_t rb, DevMem&& rows, u64 len, DevMem&& table,
+                                  u64 slots, u64 n_keys, mzgpu_desc desc, mzgpu_batch** out) {
+  mzgpu_batch* b = new mzgpu_batch();
+  b->ctx = ctx;
+  b->rb = rb;
+  b->rows = std::move(rows);
+  b->len = len;
+  b->table = std::move(table);
+  b->slots = slots;
+  b->n_keys = n_keys;
+  b->desc = desc;
+  *out = b;
+  return MZGPU_OK;
+}
+// unsorted device rows -> batch: the fused kernel for small inputs, else the
+// multi-kernel path
+static int32_t build_batch_from_unsorted(mzgpu_ctx* ctx, uint32_t rb, const void* d_in, u64 n,
+                                         mzgpu_desc desc, mzgpu_batch** out) {
+  if (n > 0 && n <= MZ_FUSED_MAX_ROWS) {
+    FusedResult fr;
+    MZ_TRY(mz_fused_sort_consolidate(ctx, rb, d_in, n, true, &fr));
+    if (!fr.fallback)
+      return make_batch_indexed(ctx, rb, std::move(fr.rows), fr.n_out, std::move(fr.table), fr.slots,
+                                fr.n_keys, desc, out);
+  }
+  DevMem cons;
+  u64 n_out = 0;
+  MZ_TRY(mz_sort_consolidate(ctx, rb, d_in, n, &cons, &n_out));
+  return make_batch(ctx, rb, std::move(cons), n_out, desc, out);
+}
 static int32_t make_empty_batch(mzgpu_ctx* ctx, uint32_t rb, mzgpu_desc desc, mzgpu_batch** out) {
   DevMem rows;
   MZ_TRY(rows.alloc(ctx, 16));
@@ -319,10 +352,8 @@ extern "C" int32_t mzgpu_batch_build(mzgpu_ctx* ctx, uint32_t row_bytes, const v
     MZ_TRY(copy_in(ctx, in.p, rows, n * row_bytes, mem));
     d_in = in.p;
   }
-  u64 n_out = 0;
-  MZ_TRY(mz_sort_consolidate(ctx, row_bytes, d_in, n, &cons, &n_out));
   ctx->stats.rows_in += n;
-  return make_batch(ctx, row_bytes, std::move(cons), n_out, desc, out);
+  return build_batch_from_unsorted(ctx, row_bytes, d_in, n, desc, out);
 }
 extern "C" uint64_t mzgpu_batch_len(const mzgpu_batch* b) { return b ? b->len : 0; }
 extern "C" uint64_t mzgpu_batch_keys(const mzgpu_batch* b) { return b ? b->n_keys : 0; }
@@ -370,6 +401,13 @@ extern "C" int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t 
 struct Chain {
   DevMem rows;
   u64 len = 0;
+  // known only when the chain came out of the fused kernel (or merges of such)
+  bool time_known = false;
+  u64 max_time = 0;
+  // hash index built by the fused kernel (valid while the chain is unmerged)
+  bool has_index = false;
+  DevMem table;
+  u64 slots = 0, n_keys = 0;
 };
 struct mzgpu_batcher {
   mzgpu_ctx* ctx;
@@ -387,6 +425,8 @@ static int32_t batcher_merge_top(mzgpu_batcher* b) {
   Chain m;
   MZ_TRY(mz_merge_consolidate(b->ctx, b->rb, older.rows.p, older.len, newer.rows.p, newer.len, 0,
                               &m.rows, &m.len));
+  m.time_known = older.time_known && newer.time_known;
+  m.max_time = std::max(older.max_time, newer.max_time);
   b->chains.push_back(std::move(m));
   return MZGPU_OK;
 }
@@ -402,7 +442,23 @@ static int32_t batcher_insert_chain(mzgpu_batcher* b, Chain&& c) {
 static int32_t batcher_push_dev(mzgpu_batcher* b, const void* d_rows, u64 n) {
   if (n == 0) return MZGPU_OK;
   Chain c;
-  MZ_TRY(mz_sort_consolidate(b->ctx, b->rb, d_rows, n, &c.rows, &c.len));
+  bool done = false;
+  if (n <= MZ_FUSED_MAX_ROWS) {
+    FusedResult fr;
+    MZ_TRY(mz_fused_sort_consolidate(b->ctx, b->rb, d_rows, n, true, &fr));
+    if (!fr.fallback) {
+      c.rows = std::move(fr.rows);
+      c.len = fr.n_out;
+      c.time_known = true;
+      c.max_time = fr.max_time;
+      c.has_index = true;
+      c.table = std::move(fr.table);
+      c.slots = fr.slots;
+      c.n_keys = fr.n_keys;
+      done = true;
+    }
+  }
+  if (!done) MZ_TRY(mz_sort_consolidate(b->ctx, b->rb, d_rows, n, &c.rows, &c.len));
   return batcher_insert_chain(b, std::move(c));
 }
 static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
@@ -422,8 +478,8 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
   b->frontier = MZGPU_FRONTIER_EMPTY;
   if (merged.len == 0) {
     MZ_TRY(ship.rows.alloc(ctx, 16));
-  } else if (upper == MZGPU_FRONTIER_EMPTY) {
-    ship = std::move(merged);  // empty antichain: everything ships
+  } else if (upper == MZGPU_FRONTIER_EMPTY || (merged.time_known && merged.max_time < upper)) {
+    ship = std::move(merged);  // empty antichain, or every buffered time is < upper: everything ships
   } else {
     u64 min_keep = MZGPU_FRONTIER_EMPTY;
     MZ_TRY(mz_extract(ctx, b->rb, merged.rows.p, merged.len, upper, &ship.rows, &ship.len, &keep.rows,
@@ -432,7 +488,11 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
   }
   if (keep.len) b->chains.push_back(std::move(keep));
   mzgpu_desc d = {b->lower, upper, 0};
-  MZ_TRY(make_batch(ctx, b->rb, std::move(ship.rows), ship.len, d, batch_out));
+  if (ship.has_index)
+    MZ_TRY(make_batch_indexed(ctx, b->rb, std::move(ship.rows), ship.len, std::move(ship.table), ship.slots,
+                              ship.n_keys, d, batch_out));
+  else
+    MZ_TRY(make_batch(ctx, b->rb, std::move(ship.rows), ship.len, d, batch_out));
   b->lower = upper;
   if (new_lower) *new_lower = b->frontier;
   return MZGPU_OK;

@@ -1,0 +1,126 @@
+// radix.cuh — one tile of one 8-bit LSD radix pass ("onesweep" with decoupled
+// look-back), shared by the stand-alone pass kernel (sort.cu) and the fused
+// cooperative small-input kernel (fused.cu).
+#pragma once
+#include "common.cuh"
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr u32 RS_FLAG_PARTIAL = 1u << 30;
+constexpr u32 RS_FLAG_INCLUSIVE = 2u << 30;
+constexpr u32 RS_VALUE_MASK = (1u << 30) - 1;
+
+template <int ITEMS>
+struct RsSmemT {
+  u64 keys[RS_THREADS * ITEMS];
+  u32 vals[RS_THREADS * ITEMS];
+  u32 whist[RS_WARPS][256];
+  u32 digit_start[256];
+  u32 gofs[256];
+  u32 scan[34];
+  u32 tile;
+};
+
+// Sort tile `tile` (RS_THREADS*ITEMS consecutive (key, val) pairs) by digit
+// (key >> shift) & 255 into (kout, vout).  Stable.  Requirements: blockDim.x ==
+// RS_THREADS; tiles are processed so that every tile < `tile` is already done or
+// is being processed by a co-resident CTA (look-back progress); tile_state is
+// zero before the pass.  No __restrict__ here: inside the fused kernel the
+// input of one pass was written by other CTAs in the previous phase.  Ends with a __syncthreads(): `s` can be reused.
+template <int ITEMS>
+__device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS>& s, u32 tile, const u64* kin,
+                                             const u32* vin, u64* kout,
+                                             u32* vout, u64 n, int shift,
+                                             const u32* gbase, u32* tile_state) {
+  constexpr u32 TILE = RS_THREADS * ITEMS;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.whist[0][0])[i] = 0;
+  __syncthreads();
+  const u64 base = (u64)tile * TILE;
+  const u32 n_valid = (u32)((n - base) < (u64)TILE ? (n - base) : (u64)TILE);
+
+  // warp-striped load: element index inside the tile = warp*(ITEMS*32) + j*32 + lane
+  u64 key[ITEMS];
+  u32 val[ITEMS];
+  u32 rank[ITEMS];
+  const u32 wb = warp * (ITEMS * 32);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    u32 idx = wb + j * 32 + lane;
+    bool ok = idx < n_valid;
+    key[j] = ok ? kin[base + idx] : ~0ull;
+    val[j] = ok ? vin[base + idx] : 0u;
+  }
+  // stable in-warp ranking with match_any / popc (warp-shuffle histograms)
+  const u32 lt_mask = (1u << lane) - 1;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    u32 d = (u32)((key[j] >> shift) & 255);
+    u32 m = __match_any_sync(0xffffffffu, d);
+    u32 leader = __ffs(m) - 1;
+    u32 old = 0;
+    if (lane == leader) {
+      old = s.whist[warp][d];
+      s.whist[warp][d] = old + __popc(m);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[j] = old + __popc(m & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d owns digit d: exclusive scan across warps, then the look-back
+  {
+    const u32 d = tid;
+    u32 tot = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      u32 c = s.whist[w][d];
+      s.whist[w][d] = tot;
+      tot += c;
+    }
+    const u32 n_invalid = TILE - n_valid;  // padding keys all carry digit 255
+    u32 tot_valid = (d == 255) ? tot - n_invalid : tot;
+    u32 excl = 0;
+    volatile u32* st = tile_state;
+    if (tile == 0) {
+      st[d] = RS_FLAG_INCLUSIVE | tot_valid;
+    } else {
+      st[(u64)tile * 256 + d] = RS_FLAG_PARTIAL | tot_valid;
+      long long t = (long long)tile - 1;
+      while (true) {
+        u32 v = st[(u64)t * 256 + d];
+        u32 flag = v >> 30;
+        if (flag == 0) continue;  // predecessor not published yet
+        excl += v & RS_VALUE_MASK;
+        if (flag == 2) break;
+        --t;
+      }
+      st[(u64)tile * 256 + d] = RS_FLAG_INCLUSIVE | ((excl + tot_valid) & RS_VALUE_MASK);
+    }
+    u32 total;
+    u32 ds = block_exclusive_scan(tot, s.scan, &total);
+    s.digit_start[d] = ds;
+    s.gofs[d] = gbase[d] + excl - ds;  // global position = gofs[d] + local position
+  }
+  __syncthreads();
+
+  // stage the tile in shared memory in digit order
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    u32 d = (u32)((key[j] >> shift) & 255);
+    u32 pos = s.digit_start[d] + s.whist[warp][d] + rank[j];
+    s.keys[pos] = key[j];
+    s.vals[pos] = val[j];
+  }
+  __syncthreads();
+  // coalesced runs per digit
+  for (u32 i = tid; i < n_valid; i += RS_THREADS) {
+    u64 k = s.keys[i];
+    u32 d = (u32)((k >> shift) & 255);
+    u32 g = s.gofs[d] + i;
+    kout[g] = k;
+    vout[g] = s.vals[i];
+  }
+  __syncthreads();
+}

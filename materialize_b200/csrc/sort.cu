@@ -20,16 +20,12 @@
 //      memory in digit order and write out coalesced runs;
 //   5. rows are gathered once, by the final permutation (consolidate.cu).
 #include "common.cuh"
+#include "radix.cuh"
 
 namespace {
 
-constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;
-constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
-constexpr u32 RS_FLAG_PARTIAL = 1u << 30;
-constexpr u32 RS_FLAG_INCLUSIVE = 2u << 30;
-constexpr u32 RS_VALUE_MASK = (1u << 30) - 1;
 
 struct ChunkPlan {
   int nwords;
@@ -130,15 +126,7 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(u32* __restrict__ ghist, i
 }
 
 // ------------------------------------------------------------ onesweep pass
-struct RsSmem {
-  u64 keys[RS_TILE];
-  u32 vals[RS_TILE];
-  u32 whist[RS_WARPS][256];
-  u32 digit_start[256];
-  u32 gofs[256];
-  u32 scan[34];
-  u32 tile;
-};
+typedef RsSmemT<RS_ITEMS> RsSmem;
 
 __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(
     const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
@@ -146,101 +134,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(
     u32* __restrict__ tile_state, u32* __restrict__ tile_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RsSmem& s = *reinterpret_cast<RsSmem*>(smem_raw);
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
   // dynamic tile assignment: tile t only starts after tiles < t have started,
-  // which is what makes the look-back below deadlock-free
-  if (tid == 0) s.tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.whist[0][0])[i] = 0;
+  // which is what makes the look-back deadlock-free
+  if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
-  const u32 tile = s.tile;
-  const u64 base = (u64)tile * RS_TILE;
-  const u32 n_valid = (u32)((n - base) < (u64)RS_TILE ? (n - base) : (u64)RS_TILE);
-
-  // warp-striped load: element index inside the tile = warp*512 + j*32 + lane
-  u64 key[RS_ITEMS];
-  u32 val[RS_ITEMS];
-  u32 rank[RS_ITEMS];
-  const u32 wb = warp * (RS_ITEMS * 32);
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    u32 idx = wb + j * 32 + lane;
-    bool ok = idx < n_valid;
-    key[j] = ok ? kin[base + idx] : ~0ull;
-    val[j] = ok ? vin[base + idx] : 0u;
-  }
-  // stable in-warp ranking with match_any / popc (warp-shuffle histograms)
-  const u32 lt_mask = (1u << lane) - 1;
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    u32 d = (u32)((key[j] >> shift) & 255);
-    u32 m = __match_any_sync(0xffffffffu, d);
-    u32 leader = __ffs(m) - 1;
-    u32 old = 0;
-    if (lane == leader) {
-      old = s.whist[warp][d];
-      s.whist[warp][d] = old + __popc(m);
-    }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[j] = old + __popc(m & lt_mask);
-    __syncwarp();
-  }
-  __syncthreads();
-
-  // thread d owns digit d: exclusive scan across warps
-  {
-    const u32 d = tid;
-    u32 tot = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      u32 c = s.whist[w][d];
-      s.whist[w][d] = tot;
-      tot += c;
-    }
-    const u32 n_invalid = RS_TILE - n_valid;  // padding keys all carry digit 255
-    u32 tot_valid = (d == 255) ? tot - n_invalid : tot;
-    // decoupled look-back over earlier tiles' digit counts
-    u32 excl = 0;
-    volatile u32* st = tile_state;
-    if (tile == 0) {
-      st[d] = RS_FLAG_INCLUSIVE | tot_valid;
-    } else {
-      st[(u64)tile * 256 + d] = RS_FLAG_PARTIAL | tot_valid;
-      long long t = (long long)tile - 1;
-      while (true) {
-        u32 v = st[(u64)t * 256 + d];
-        u32 flag = v >> 30;
-        if (flag == 0) continue;  // predecessor not published yet
-        excl += v & RS_VALUE_MASK;
-        if (flag == 2) break;
-        --t;
-      }
-      st[(u64)tile * 256 + d] = RS_FLAG_INCLUSIVE | ((excl + tot_valid) & RS_VALUE_MASK);
-    }
-    u32 total;
-    u32 ds = block_exclusive_scan(tot, s.scan, &total);
-    s.digit_start[d] = ds;
-    s.gofs[d] = gbase[d] + excl - ds;  // global position = gofs[d] + local position
-  }
-  __syncthreads();
-
-  // stage the tile in shared memory in digit order
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    u32 d = (u32)((key[j] >> shift) & 255);
-    u32 pos = s.digit_start[d] + s.whist[warp][d] + rank[j];
-    s.keys[pos] = key[j];
-    s.vals[pos] = val[j];
-  }
-  __syncthreads();
-  // coalesced runs per digit
-  for (u32 i = tid; i < n_valid; i += RS_THREADS) {
-    u64 k = s.keys[i];
-    u32 d = (u32)((k >> shift) & 255);
-    u32 g = s.gofs[d] + i;
-    kout[g] = k;
-    vout[g] = s.vals[i];
-  }
+  rs_tile_pass<RS_ITEMS>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
 }
 
 static int bit_width_u64(u64 x) {
