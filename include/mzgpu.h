@@ -21,6 +21,15 @@
  *   - row pointers carry a memory-space tag (MZGPU_MEM_HOST / MZGPU_MEM_DEVICE).
  *   - variable-size results are written to a library-owned device buffer
  *     (`mzgpu_buf`) that the caller downloads or feeds to the next operator.
+ *   - calls are asynchronous on the ctx stream.  Data-dependent row counts
+ *     (survivors of a consolidation, matches of a probe) stay in device memory
+ *     and flow to the next operator there; the `*_buf` entry points chain
+ *     operators without a host round trip.  Anything that returns an exact
+ *     count to the caller (mzgpu_buf_len, mzgpu_batch_len, a download, ...)
+ *     waits for the device once and resolves every outstanding count.  This is
+ *     the cooperative-scheduling contract of the reference in GPU form: an
+ *     operator returns promptly (yield budgets, src/compute/src/render/join/
+ *     linear_join.rs:145-151) and the worker decides when to look at results.
  */
 #ifndef MZGPU_H
 #define MZGPU_H
@@ -212,6 +221,7 @@ typedef struct mzgpu_stats {
   uint64_t rows_out;
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
+  uint64_t host_syncs; /* times the host waited for the device */
 } mzgpu_stats;
 int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out);
 /* Per-kernel device timing (CUDA events on the ctx stream around every launch).
@@ -245,6 +255,8 @@ int32_t mzgpu_buf_append(mzgpu_buf* buf, const void* rows, uint64_t n, int32_t m
 /* Copy rows out; MZGPU_E_CAPACITY (with *n_out = len) if cap is too small. */
 int32_t mzgpu_buf_download(mzgpu_buf* buf, void* rows, uint64_t cap, int32_t mem, uint64_t* n_out);
 int32_t mzgpu_buf_clear(mzgpu_buf* buf);
+/* Append the rows of `src` (same row width) without reading its length back. */
+int32_t mzgpu_buf_append_buf(mzgpu_buf* dst, mzgpu_buf* src);
 
 /* ---------------------------------------------------- a1: consolidation */
 /* differential_dataflow::consolidation::consolidate on Vec<(u64,i64)>:
@@ -270,6 +282,8 @@ void mzgpu_batcher_free(mzgpu_batcher* b);
  * keep chains geometric (Chunker::push_into,
  * src/timely-util/src/columnar/batcher.rs:65-122; Merger::merge :635-753). */
 int32_t mzgpu_batcher_push(mzgpu_batcher* b, const void* rows, uint64_t n, int32_t mem);
+/* push_container for rows that already sit in a device buffer (no length read-back). */
+int32_t mzgpu_batcher_push_buf(mzgpu_batcher* b, mzgpu_buf* rows);
 /* Batcher::seal::<Builder>(upper): merge all chains, ship updates with
  * !upper.less_equal(time), keep the rest (InternalMerge::extract,
  * src/timely-util/src/columnation.rs:636-655), build the batch with
@@ -357,6 +371,9 @@ int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out, 
 int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int32_t mem,
                         mzgpu_spine* trace, int32_t cmp_mode, const mzgpu_closure* closure,
                         int32_t consolidate_output, mzgpu_buf* out);
+/* The same with the stream in a device buffer: nothing returns to the host. */
+int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
+                            const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out);
 /* build_update_stream (delta_join.rs:600-707): a batch's updates as a stream,
  * `initial_closure` applied (val2 unused), updates at `skip_time` dropped when
  * skip_time != MZGPU_FRONTIER_EMPTY (the as_of rule for source_relation != 0). */
@@ -378,6 +395,7 @@ void mzgpu_reduce_free(mzgpu_reduce* r);
  * changed key and time) to `out`, consolidated. */
 int32_t mzgpu_reduce_accumulable(mzgpu_reduce* r, const mzgpu_r32* rows, uint64_t n, int32_t mem,
                                  uint64_t upper, mzgpu_buf* out);
+int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows, uint64_t upper, mzgpu_buf* out);
 /* The input arrangement (for sharing / inspection). Borrowed. */
 mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r);
 

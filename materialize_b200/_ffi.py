@@ -97,6 +97,7 @@ class Stats(C.Structure):
         ("rows_out", C.c_uint64),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("host_syncs", C.c_uint64),
     ]
 
 
@@ -120,6 +121,10 @@ SIGNATURES = {
     "mzgpu_buf_device_ptr": (vp, [vp]),
     "mzgpu_buf_upload": (i32, [vp, vp, u64, i32]),
     "mzgpu_buf_append": (i32, [vp, vp, u64, i32]),
+    "mzgpu_buf_append_buf": (i32, [vp, vp]),
+    "mzgpu_batcher_push_buf": (i32, [vp, vp]),
+    "mzgpu_half_join_buf": (i32, [vp, vp, vp, i32, C.POINTER(Closure), i32, vp]),
+    "mzgpu_reduce_accumulable_buf": (i32, [vp, vp, u64, vp]),
     "mzgpu_buf_download": (i32, [vp, vp, u64, i32, PU64]),
     "mzgpu_buf_clear": (i32, [vp]),
     "mzgpu_consolidate_r16": (i32, [vp, vp, u64, i32, PU64]),

@@ -32,7 +32,22 @@ struct mzgpu_ctx {
   // pinned bounce buffers for host<->device row copies
   void* h_bounce = nullptr;
   size_t h_bounce_bytes = 0;
-  void* h_fused = nullptr;  // pinned image of the fused kernel's control block (16 KiB)
+  // ---- device-resident counters (lazy read-back; see Lazy4 below)
+  u64* d_cnt = nullptr;        // MZ_CNT_BLOCKS x 4 words
+  u64* h_cnt = nullptr;        // pinned mirror, refreshed by mz_resolve_counters()
+  std::vector<int> cnt_free;   // free block indices
+  int cnt_high = 0;            // blocks [0, cnt_high) have been handed out at least once
+  u64 op_seq = 1;              // bumped whenever a kernel that writes counters is enqueued
+  u64 resolved_seq = 0;        // op_seq covered by the last read-back
+  u64 n_resolves = 0;          // host syncs spent on read-backs
+  // ---- single-pass expansion kernels: look-back state, tile tickets
+  u64* d_lb = nullptr;         // MZ_LB_TILES tagged state words (never written by anything else)
+  u32 lb_epoch = 0;            // tag of the next launch (20 bits)
+  u32* d_tickets = nullptr;    // MZ_TICKETS zeroed tile counters, handed out round-robin
+  u32 ticket_next = 0;
+  u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (bug guard), [1] = rows required
+  void* d_fused_ctl[2] = {nullptr, nullptr};  // control blocks of the fused kernel (each launch clears the other)
+  int fused_flip = 0;
   // per-kernel profiling (mzgpu_profile_enable)
   struct ProfRec {
     const char* name;
@@ -66,11 +81,22 @@ struct mzgpu_ctx {
     }                                                                                    \
   } while (0)
 
+// a host wait on the ctx stream (counted: mzgpu_stats.host_syncs)
+#define MZ_SYNC(ctx)                                            \
+  do {                                                          \
+    MZ_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));         \
+    (ctx)->stats.host_syncs++;                                  \
+  } while (0)
+
 #define MZ_TRY(expr)                 \
   do {                               \
     int32_t _s = (expr);             \
     if (_s != MZGPU_OK) return _s;   \
   } while (0)
+
+#define MZ_CNT_BLOCKS 8192
+#define MZ_LB_TILES (1u << 20)
+#define MZ_TICKETS 4096
 
 #define MZ_CHECK_CTX(ctx)                       \
   do {                                          \
@@ -174,6 +200,121 @@ struct DevMem {
   }
 };
 
+// ------------------------------------------------ device-resident row counts
+// Data-dependent sizes (rows surviving a consolidation, matches of a probe, ...)
+// are produced by kernels.  Reading each one back costs a host sync, and a
+// 100K-row update batch is a chain of ~20 such operators whose kernels run for
+// microseconds: the syncs, not the kernels, would set the pace.  So a count
+// lives in a 4-word block of a small device arena; consumer kernels read it
+// from there (DLen), the host works with upper bounds, and the arena is read
+// back in one copy the first time the host needs any exact value — which
+// resolves every count produced before that point.
+int32_t mz_resolve_counters(mzgpu_ctx* ctx);  // host.cu: one D2H of the arena + sync
+int mz_cnt_alloc(mzgpu_ctx* ctx);             // -1 if the arena is exhausted
+void mz_cnt_free(mzgpu_ctx* ctx, int blk);
+
+struct Lazy4 {
+  mzgpu_ctx* ctx = nullptr;
+  int blk = -1;
+  u64 seq = 0;        // ctx->op_seq when the producing kernel was enqueued
+  bool known = true;  // host copy `v` is valid
+  u64 v[4] = {0, 0, 0, 0};
+  Lazy4() {}
+  Lazy4(const Lazy4&) = delete;
+  Lazy4& operator=(const Lazy4&) = delete;
+  Lazy4(Lazy4&& o) noexcept { *this = std::move(o); }
+  Lazy4& operator=(Lazy4&& o) noexcept {
+    if (this != &o) {
+      drop();
+      ctx = o.ctx;
+      blk = o.blk;
+      seq = o.seq;
+      known = o.known;
+      for (int i = 0; i < 4; ++i) v[i] = o.v[i];
+      o.blk = -1;
+      o.known = true;
+    }
+    return *this;
+  }
+  ~Lazy4() { drop(); }
+  void drop() {
+    if (blk >= 0) mz_cnt_free(ctx, blk);
+    blk = -1;
+  }
+  void set(mzgpu_ctx* c, u64 a, u64 b = 0, u64 cc = 0, u64 d = 0) {
+    drop();
+    ctx = c;
+    known = true;
+    v[0] = a;
+    v[1] = b;
+    v[2] = cc;
+    v[3] = d;
+  }
+  // reserve a device block that a kernel enqueued next will fill
+  int32_t make_pending(mzgpu_ctx* c) {
+    drop();
+    ctx = c;
+    blk = mz_cnt_alloc(c);
+    if (blk < 0) {
+      MZ_SET_ERR(c, "device counter arena exhausted (%d blocks unresolved)", MZ_CNT_BLOCKS);
+      return MZGPU_E_CAPACITY;
+    }
+    known = false;
+    return MZGPU_OK;
+  }
+  u64* dptr() const { return ctx->d_cnt + 4 * (size_t)blk; }
+  // call right after enqueuing the kernel that writes the block
+  void mark_written() { seq = ++ctx->op_seq; }
+  // true if the value is known afterwards; never waits for the device
+  bool try_resolve() {
+    if (known) return true;
+    if (seq > ctx->resolved_seq) return false;
+    for (int i = 0; i < 4; ++i) v[i] = ctx->h_cnt[4 * (size_t)blk + i];
+    known = true;
+    drop();
+    return true;
+  }
+  int32_t resolve() {
+    if (known) return MZGPU_OK;
+    if (seq > ctx->resolved_seq) MZ_TRY(mz_resolve_counters(ctx));
+    for (int i = 0; i < 4; ++i) v[i] = ctx->h_cnt[4 * (size_t)blk + i];
+    known = true;
+    drop();
+    return MZGPU_OK;
+  }
+};
+
+// A row count as a kernel argument: device word if `p`, else the immediate.
+struct DLen {
+  const u64* p;
+  u64 imm;
+};
+static inline DLen dlen_of(const Lazy4& l, int word) {
+  DLen d;
+  if (l.known) {
+    d.p = nullptr;
+    d.imm = l.v[word];
+  } else {
+    d.p = l.dptr() + word;
+    d.imm = 0;
+  }
+  return d;
+}
+static inline DLen dlen_imm(u64 n) {
+  DLen d;
+  d.p = nullptr;
+  d.imm = n;
+  return d;
+}
+
+// Per-launch handle for the single-pass ("chained scan") expansion kernels.
+struct LookBack {
+  u64* state;   // ctx->d_lb
+  u32* ticket;  // one zeroed counter
+  u32 epoch;    // tag of this launch
+};
+int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb);  // host.cu
+
 // ---------------------------------------------------------------- row traits
 // A row is NW 64-bit words: NK sort-key words first (compared as unsigned, in
 // order), then the diff words.  TW = index of the time word (or -1).
@@ -261,6 +402,67 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* smem, u32* total
   *total = smem[32];
   __syncthreads();
   return res;
+}
+
+__device__ __forceinline__ u64 dlen_get(const DLen& l) { return l.p != nullptr ? *l.p : l.imm; }
+
+// ---- chained scan across tiles (decoupled look-back), 64-bit totals.
+// State word: [epoch:20][status:2][value:42].  A stale word (older epoch) reads
+// as "not published", so the state array never needs clearing between launches.
+constexpr u64 LB_VALUE_MASK = (1ull << 42) - 1;
+constexpr u64 LB_PARTIAL = 1, LB_INCLUSIVE = 2;
+__device__ __forceinline__ u64 lb_pack(u32 epoch, u64 status, u64 value) {
+  return ((u64)epoch << 44) | (status << 42) | (value & LB_VALUE_MASK);
+}
+// Next tile for this CTA (tiles are handed out in order, so every predecessor
+// of a tile has started: the look-back cannot deadlock).  All threads call it.
+__device__ __forceinline__ u32 lb_next_tile(const LookBack& lb, u32* s_tile) {
+  __syncthreads();
+  if (threadIdx.x == 0) *s_tile = atomicAdd(lb.ticket, 1u);
+  __syncthreads();
+  return *s_tile;
+}
+// Exclusive prefix of `total` over all tiles before `tile`; publishes this
+// tile's inclusive prefix.  Called by every thread of the CTA (warp 0 works);
+// `s_bcast` is one shared u64.
+__device__ __forceinline__ u64 lb_exclusive_prefix(const LookBack& lb, u32 tile, u64 total, u64* s_bcast) {
+  if (threadIdx.x < 32) {
+    const u32 lane = threadIdx.x;
+    volatile u64* st = lb.state;
+    u64 excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st[0] = lb_pack(lb.epoch, LB_INCLUSIVE, total);
+    } else {
+      if (lane == 0) st[tile] = lb_pack(lb.epoch, LB_PARTIAL, total);
+      long long hi = (long long)tile - 1;  // nearest unread predecessor
+      while (true) {
+        const long long idx = hi - (long long)lane;
+        u64 w = 0;
+        u64 status = LB_INCLUSIVE;  // lanes before tile 0 behave as an inclusive zero
+        if (idx >= 0) {
+          do {
+            w = st[idx];
+            status = ((u32)(w >> 44) == lb.epoch) ? ((w >> 42) & 3) : 0;
+          } while (status == 0);
+        }
+        const u32 incl_mask = __ballot_sync(0xffffffffu, status == LB_INCLUSIVE);
+        const u32 first = __ffs(incl_mask) - 1;  // incl_mask != 0 whenever the window reaches past tile 0
+        u64 contrib = (incl_mask == 0 || lane <= first) ? (w & LB_VALUE_MASK) : 0;
+        if (idx < 0) contrib = 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
+        excl += contrib;
+        if (incl_mask != 0) break;
+        hi -= 32;
+      }
+      if (lane == 0) st[tile] = lb_pack(lb.epoch, LB_INCLUSIVE, excl + total);
+    }
+    if (lane == 0) *s_bcast = excl;
+  }
+  __syncthreads();
+  const u64 r = *s_bcast;
+  __syncthreads();
+  return r;
 }
 
 // Single-block exclusive scan of per-tile counts, in place; the grand total is
@@ -384,19 +586,29 @@ int32_t mz_consolidate_sorted(mzgpu_ctx* ctx, int row_bytes, const void* d_sorte
 int32_t mz_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, DevMem* out,
                             u64* n_out);
 
-// fused.cu: the same pipeline (sort + gather + consolidate, optionally + hash
-// index) as ONE cooperative kernel, for small / medium inputs.  If the composite
-// key needs more than 64 bits `fallback` is set and nothing else is valid.
-struct FusedResult {
-  DevMem rows;   // consolidated output (capacity n rows)
-  DevMem table;  // hash index (if requested)
-  u64 n_out = 0, n_keys = 0, slots = 0;
-  u64 min_time = 0, max_time = 0;  // range of the time word over the INPUT rows
-  bool fallback = false;
+// fused.cu: consolidate(A ++ B with times advanced to `since`), split by `upper`,
+// hash index — ONE cooperative kernel, no host read-back.  Inputs larger than
+// MZ_FUSED_MAX_ROWS take the multi-kernel path (sort.cu, consolidate.cu, ...).
+struct FusedJob {
+  int rb = 0;
+  const void* a = nullptr;  // first input (for a merge: the older batch)
+  const void* b = nullptr;  // optional second input
+  DLen na = {nullptr, 0}, nb = {nullptr, 0};
+  u64 cap = 0;                          // host upper bound on na + nb (sizes every buffer)
+  u64 since = 0;                        // advance_by(since)
+  u64 upper = MZGPU_FRONTIER_EMPTY;     // rows with time < upper go to `rows`, the rest to `keep`
+  bool want_index = false;
 };
-int32_t mz_fused_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, bool want_index,
-                                  FusedResult* res);
-// inputs up to this many rows take the fused path
+struct FusedOut {
+  DevMem rows;  // consolidated (shipped) rows, capacity rows_cap
+  u64 rows_cap = 0;
+  DevMem table;  // hash index, if requested
+  DevMem keep;   // rows with time >= upper (allocated only when upper is a real frontier)
+  Lazy4 st;      // [0] rows out, [1] table mask, [2] distinct keys, [3] longest key run (saturates at 1024)
+  Lazy4 kst;     // [0] rows kept, [1] min kept time (~0 if none), [2] max input time
+};
+int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
+size_t mz_fused_ctl_bytes();
 #define MZ_FUSED_MAX_ROWS (2u << 20)
 
 // merge.cu: merge two sorted consolidated arrays; times are advanced to
@@ -412,7 +624,7 @@ struct HashSlot {
   u64 key;
   u64 meta;  // 0 = empty, else (first row index + 1)
 };
-int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys);
+int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys, u64* max_run);
 int32_t mz_build_index(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64 n_keys,
                        DevMem* table, u64* table_slots);
 
@@ -421,8 +633,14 @@ struct BatchView {  // device-visible description of one batch of a trace
   const u64* rows;
   const HashSlot* table;
   u64 n;
-  u64 mask;  // table_slots - 1
+  u64 mask;        // table_slots - 1
+  const u64* hdr;  // if set, n = hdr[0] and mask = hdr[1] live in device memory (batch built
+                   // by a kernel still in flight; see Lazy4)
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 bv_n(const BatchView& b) { return b.hdr != nullptr ? b.hdr[0] : b.n; }
+__device__ __forceinline__ u64 bv_mask(const BatchView& b) { return b.hdr != nullptr ? b.hdr[1] : b.mask; }
+#endif
 #define MZ_MAX_TRACE_BATCHES 64
 struct TraceView {
   BatchView b[MZ_MAX_TRACE_BATCHES];
@@ -442,12 +660,23 @@ struct ProbeParams {
 // (allocated here) and returns the count.  One sync (to size the output).
 int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& trace,
                  const ProbeParams& pp, DevMem* out, u64* n_out);
+// Single-pass form: `n` is read on the device, results are written at
+// d_out[out_base ...] (capacity out_cap rows: the caller guarantees it with a
+// bound, ctx->d_status records a violation) and the new length is left in
+// *d_out_len.  No host round trip.
+int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, const TraceView& trace,
+                       const ProbeParams& pp, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len);
+int32_t mz_map_rows_async(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, const mzgpu_closure* closure,
+                          u64 skip_time, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len);
 // Apply a closure to R32 rows (val2 = 0); optional skip of rows at `skip_time`.
 int32_t mz_map_rows_dev(mzgpu_ctx* ctx, const u64* d_rows, u64 n, const mzgpu_closure* closure,
                         u64 skip_time, DevMem* out, u64* n_out);
 
 // reduce.cu
-int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, u64 n, int agg_kind, u64* d_racc);
+int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_kind, u64* d_racc);
+int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
+                                    const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
+                                    u64* d_out_len);
 int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, const TraceView& prior,
                               int agg_kind, DevMem* out, u64* n_out);
 

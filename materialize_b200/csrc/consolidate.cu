@@ -166,7 +166,7 @@ int32_t consolidate_sorted_t(mzgpu_ctx* ctx, const u64* rows, u64 n, u64* out, u
   MZ_LAUNCH(ctx, (k_emit<NW, NK, ND>), (unsigned)n_tiles, CT, 0, rows, seg_sums.as<u64>(),
             seg_first.as<u32>(), d_nseg, tiles.as<u32>(), out);
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 16, d_nseg, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 16;
   *n_out = ctx->h_scratch[17];
   return MZGPU_OK;
@@ -212,15 +212,6 @@ int32_t mz_consolidate_sorted(mzgpu_ctx* ctx, int row_bytes, const void* d_sorte
 int32_t mz_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, DevMem* out,
                             u64* n_out) {
   *n_out = 0;
-  if (n > 0 && n <= MZ_FUSED_MAX_ROWS) {
-    FusedResult fr;
-    MZ_TRY(mz_fused_sort_consolidate(ctx, row_bytes, d_rows, n, false, &fr));
-    if (!fr.fallback) {
-      *out = std::move(fr.rows);
-      *n_out = fr.n_out;
-      return MZGPU_OK;
-    }
-  }
   MZ_TRY(out->alloc(ctx, n * (u64)row_bytes));
   if (n == 0) return MZGPU_OK;
   DevMem perm, sorted;

@@ -87,7 +87,7 @@ int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u
   }
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 32, counts.p, peers * 8, cudaMemcpyDeviceToHost,
                                ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += peers * 8;
   u64 off = 0;
   u64 offsets[MAX_PEERS];
@@ -103,6 +103,6 @@ int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u
     default: return MZGPU_E_UNSUPPORTED;
   }
   // `offsets` is a stack array: make sure the H2D copy has consumed it
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   return MZGPU_OK;
 }

@@ -1,25 +1,34 @@
-// fused.cu — the whole "sort + consolidate (+ index)" pipeline as ONE cooperative
-// kernel for small and medium inputs (update batches).
+// fused.cu — "consolidate" as ONE cooperative kernel with every size read on the
+// device: sort + diff-sum + zero-drop, optionally over the union of two sorted
+// inputs with times advanced (batch merge), optionally split by a frontier
+// (batcher seal), optionally followed by the hash index of the result.
 //
-// Why: a 100K-row update batch (BASELINE config 3) moves ~3 MB; every kernel on
-// it finishes in microseconds, so a chain of ~25 dependent launches plus two
-// host round trips per sort is pure latency.  Here a persistent grid (<= the
-// co-resident capacity, launched cooperatively) runs every phase back to back
-// with a device-side grid barrier between phases:
+// Reference semantics (same as sort.cu / consolidate.cu / merge.cu / index.cu):
+//   consolidate_updates               differential-dataflow 0.23 (ext), model at
+//                                     src/timely-util/src/columnar/batcher.rs:1116-1130
+//   Chunker::push_into + seal/extract src/timely-util/src/columnar/batcher.rs:65-122,
+//                                     src/timely-util/src/columnation.rs:636-655
+//   Batch::Merger (advance_by(since)) SURVEY.md A4
 //
-//   analyze (min/max per key word)            -> plan computed ON DEVICE by every CTA
-//   pack composite keys + all-digit histogram
-//   exclusive scan of the histograms
-//   P x 8-bit radix passes (rs_tile_pass, decoupled look-back, 1024-key tiles)
-//   gather rows by the permutation + head flags (from the sorted composites)
-//   warp-segmented diff sums (atomics per (warp, segment))
-//   non-zero flags -> compaction -> output rows
-//   [optional] hash index over the distinct keys of the output
+// Why one kernel: a 100K-row update batch (BASELINE config 3) moves ~3 MB; each
+// of the ~25 kernels of the unfused path runs for microseconds and three of them
+// end in a host read-back.  Here a persistent grid runs every phase back to back
+// with a device-side grid barrier between phases; the input row count is read
+// from device memory (DLen) and every result count (rows out, keys, longest key
+// run, rows kept, min kept time) is left in a device counter block (Lazy4), so
+// the host enqueues the launch and moves on.  CTAs beyond what the actual row
+// count needs leave at once, so a loose upper bound costs nothing.
 //
-// One launch and one host read-back (counts, time range, fallback flag) replace
-// the ~25 launches + 2 syncs of the unfused path (sort.cu + consolidate.cu +
-// index.cu), which remains the path for large inputs and for composites wider
-// than 64 bits (`fallback`).  Same reference semantics as those files.
+//   phase 0  zero scratch, min/max of every key word (times advanced by `since`)
+//   plan     (every CTA, identical) radix rounds of <= 64 composite bits, least
+//            significant key words first
+//   round r  pack composites (+ all-digit histogram) | scan | 8-bit passes with
+//            decoupled look-back (radix.cuh)
+//   gather   rows by the final permutation, head flags
+//   segsum   warp-segmented diff sums, one atomic per (warp, segment)
+//   count    surviving segments per tile, split into ship (time < upper) / keep
+//   emit     ship rows -> out, kept rows -> keep
+//   index    open-addressing hash index over the distinct keys of `out`
 #include "common.cuh"
 #include "radix.cuh"
 
@@ -28,35 +37,43 @@ namespace {
 constexpr int FT = RS_THREADS;  // 256 threads per CTA
 constexpr int FI = 4;           // radix items per thread: 1024-key tiles
 constexpr int FTILE = FT * FI;
+constexpr int MAX_ROUNDS = 6;
+constexpr u32 MAX_RUN_SAT = 1024;  // key runs longer than this report as 1024
 
 struct FusedCtl {
   u32 barrier;
-  u32 fallback;
-  u32 pad[2];
-  u64 minmax[12];  // [2k] = min (init ~0), [2k+1] = max (init 0)
+  u32 pad[3];
+  u64 minmax[12];  // [2k] = max of ~word (so zero is the identity), [2k+1] = max of word
   u64 n_seg;
   u64 n_out;
-  u64 n_keys;
-  u32 hist[8 * 256];
+  u32 hist[MAX_ROUNDS * 8 * 256];
 };
+constexpr size_t CTL_HEADER = offsetof(FusedCtl, hist);
 
 struct FusedArgs {
-  const u64* rows;
-  u64 n;
+  const u64* a;
+  const u64* b;
+  DLen na, nb;
+  u64 since, upper;
   FusedCtl* ctl;
+  FusedCtl* ctl_next;  // header zeroed here for the next launch
   u64* k0;
   u64* k1;
   u32* v0;
   u32* v1;
-  u32* tile_state;  // [8][T][256], zeroed in phase 0
-  u64 T;            // radix tiles
-  u64* sorted;      // n rows
-  u32* tile_cnt;    // [U] per-256-row-tile counts (heads, then non-zero segments)
-  u64* seg_sums;    // [n][ND]
-  u32* seg_first;   // [n]
-  u64* out;         // n rows capacity
-  HashSlot* table;  // optional
-  u64 mask;
+  u32* state0;  // [Tcap][256]
+  u32* state1;
+  u64* sorted;     // cap rows
+  u32* tile_cnt;   // [Ucap]
+  u32* tile_cnt2;  // [Ucap]
+  u64* seg_sums;   // [cap][ND]
+  u32* seg_first;  // [cap]
+  u64* out;        // cap rows
+  u64* keep;       // cap rows or null
+  HashSlot* table;  // table_cap slots or null
+  u64 table_cap;
+  u64* res;   // n_out, mask, n_keys, max_run
+  u64* kres;  // n_keep, min kept time, max input time, -
 };
 
 __device__ __forceinline__ void grid_barrier(u32* counter, u32 G, u32& epoch) {
@@ -75,7 +92,7 @@ __device__ __forceinline__ void grid_barrier(u32* counter, u32 G, u32& epoch) {
 
 __device__ __forceinline__ int bit_width_dev(u64 x) { return x == 0 ? 0 : 64 - __clzll((long long)x); }
 
-// sum of a u32 array prefix [0, m) by the whole CTA (m is small: n / 256 tiles)
+// sum of a u32 array prefix [0, m) by the whole CTA
 __device__ __forceinline__ u32 block_sum_prefix(const u32* a, u64 m, u32* sm) {
   u32 v = 0;
   for (u64 i = threadIdx.x; i < m; i += FT) v += *(volatile const u32*)(a + i);
@@ -95,37 +112,82 @@ union FusedSmem {
 };
 
 template <int RB>
-__global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a) {
-  constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND;
+__global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
+  constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
-  __shared__ int s_nwords, s_word[6], s_shift[6], s_npass;
+  __shared__ int s_nwords, s_nrounds, s_word[6], s_shift[6], s_round[6], s_rbits[MAX_ROUNDS];
   __shared__ u64 s_minv[6];
-  const u32 G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+  const u32 c = blockIdx.x, tid = threadIdx.x;
+  const u64 na = dlen_get(a.na), nb = dlen_get(a.nb);
+  const u64 n = na + nb;
+  const u64 T = (n + FTILE - 1) / FTILE;
+  // CTAs the actual input needs; the rest leave (they hold no barrier slot)
+  u32 G = gridDim.x;
+  {
+    u64 want = T > 0 ? T : 1;
+    if (want < (u64)G) G = (u32)want;
+  }
+  if (c >= G) return;
   const u64 gtid = (u64)c * FT + tid, gstride = (u64)G * FT;
-  const u64 n = a.n;
   FusedCtl* ctl = a.ctl;
   u32 epoch = 0;
+  const u64 since = a.since;
 
-  // ---- phase 0: zero scratch; phase 1: min/max of every key word
+  // logical input row i of A ++ B, time advanced to max(time, since)
+  auto load_in = [&](u64 i, u64* r) {
+    if (i < na)
+      load_row<NW>(a.a, i, r);
+    else
+      load_row<NW>(a.b, i - na, r);
+    if (TW >= 0) {
+      u64& t = r[TW >= 0 ? TW : 0];
+      t = t < since ? since : t;
+    }
+  };
+
+  // table size from the actual input count
+  u64 mask = 0;
+  if (a.table != nullptr) {
+    u64 slots = 2;
+    while (slots < 2 * n) slots <<= 1;
+    if (slots > a.table_cap) slots = a.table_cap;  // cannot happen: cap >= n
+    mask = slots - 1;
+  }
+
+  // ---- phase 0: zero scratch, results, next launch's header; min/max of every key word
   {
-    const u64 n_state = 8ull * a.T * 256;
-    for (u64 i = gtid; i < n_state; i += gstride) a.tile_state[i] = 0;
+    if (c == 0) {
+      for (u32 i = tid; i < CTL_HEADER / 4; i += FT) ((u32*)a.ctl_next)[i] = 0;
+      if (tid == 0) {
+        a.res[0] = 0;
+        a.res[1] = mask;
+        a.res[2] = 0;
+        a.res[3] = 0;
+        a.kres[0] = 0;
+        a.kres[1] = ~0ull;
+        a.kres[2] = 0;
+        a.kres[3] = 0;
+      }
+    }
+    for (u64 i = gtid; i < (u64)MAX_ROUNDS * 8 * 256; i += gstride) ctl->hist[i] = 0;
+    for (u64 i = gtid; i < T * 256; i += gstride) a.state0[i] = 0;
     for (u64 i = gtid; i < n * ND; i += gstride) a.seg_sums[i] = 0;
     if (a.table != nullptr)
-      for (u64 i = gtid; i < (a.mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
+      for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
     u64 mn[NK], mx[NK];
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      mn[k] = ~0ull;
+      mn[k] = 0;
       mx[k] = 0;
     }
     for (u64 i = gtid; i < n; i += gstride) {
-      const u64* p = a.rows + i * NW;
+      u64 r[NW];
+      load_in(i, r);
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        u64 v = p[k];
-        mn[k] = v < mn[k] ? v : mn[k];
+        u64 v = r[k];
+        mn[k] = ~v > mn[k] ? ~v : mn[k];
         mx[k] = v > mx[k] ? v : mx[k];
       }
     }
@@ -135,11 +197,11 @@ __global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a
       for (int off = 16; off > 0; off >>= 1) {
         u64 x = __shfl_xor_sync(0xffffffffu, mn[k], off);
         u64 y = __shfl_xor_sync(0xffffffffu, mx[k], off);
-        mn[k] = x < mn[k] ? x : mn[k];
+        mn[k] = x > mn[k] ? x : mn[k];
         mx[k] = y > mx[k] ? y : mx[k];
       }
-      if (lane_id() == 0) {
-        atomicMin((unsigned long long*)&ctl->minmax[2 * k], (unsigned long long)mn[k]);
+      if (lane_id() == 0 && n > 0) {
+        atomicMax((unsigned long long*)&ctl->minmax[2 * k], (unsigned long long)mn[k]);
         atomicMax((unsigned long long*)&ctl->minmax[2 * k + 1], (unsigned long long)mx[k]);
       }
     }
@@ -148,102 +210,141 @@ __global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a
 
   // ---- plan (every CTA computes the same plan from the global min/max)
   if (tid == 0) {
-    int used = 0, nwords = 0;
-    bool fb = false;
+    int used = 0, nwords = 0, round = 0;
+    for (int r = 0; r < MAX_ROUNDS; ++r) s_rbits[r] = 0;
     for (int k = NK - 1; k >= 0; --k) {
-      u64 lo = *(volatile u64*)&ctl->minmax[2 * k], hi = *(volatile u64*)&ctl->minmax[2 * k + 1];
-      int bits = bit_width_dev(hi - lo);
+      u64 lo = ~*(volatile u64*)&ctl->minmax[2 * k], hi = *(volatile u64*)&ctl->minmax[2 * k + 1];
+      int bits = n > 0 ? bit_width_dev(hi - lo) : 0;
       if (bits == 0) continue;
       if (used + bits > 64) {
-        fb = true;
-        break;
+        round++;
+        used = 0;
       }
       s_word[nwords] = k;
       s_shift[nwords] = used;
       s_minv[nwords] = lo;
+      s_round[nwords] = round;
       nwords++;
       used += bits;
+      s_rbits[round] = used;
     }
     s_nwords = nwords;
-    s_npass = fb ? -1 : (used + 7) / 8;
-    if (fb && c == 0) ctl->fallback = 1;
+    s_nrounds = nwords == 0 ? 0 : round + 1;
+    if (c == 0 && TW >= 0) a.kres[2] = n > 0 ? *(volatile u64*)&ctl->minmax[2 * (TW >= 0 ? TW : 0) + 1] : 0;
   }
   __syncthreads();
-  const int npass = s_npass;
-  if (npass < 0) return;  // composite wider than 64 bits: the host takes the unfused path
+  const int nrounds = s_nrounds;
 
-  // ---- phase 2: pack composites + histogram of every digit place
-  for (int i = tid; i < 8 * 256; i += FT) sm.hist[i] = 0;
-  __syncthreads();
-  for (u64 i = gtid; i < n; i += gstride) {
-    const u64* p = a.rows + i * NW;
-    u64 comp = 0;
-    for (int j = 0; j < s_nwords; ++j) comp |= (p[s_word[j]] - s_minv[j]) << s_shift[j];
-    a.k0[i] = comp;
-    a.v0[i] = (u32)i;
-    for (int ps = 0; ps < npass; ++ps) atomicAdd(&sm.hist[ps * 256 + (u32)((comp >> (8 * ps)) & 255)], 1u);
-  }
-  __syncthreads();
-  for (int i = tid; i < npass * 256; i += FT) {
-    u32 v = sm.hist[i];
-    if (v) atomicAdd(&ctl->hist[i], v);
-  }
-  grid_barrier(&ctl->barrier, G, epoch);
-
-  // ---- phase 3: exclusive scan of each pass's histogram (one CTA per pass)
-  for (int ps = c; ps < npass; ps += G) {
-    u32 v = *(volatile u32*)&ctl->hist[ps * 256 + tid];
-    u32 total;
-    u32 ex = block_exclusive_scan(v, sm_scan, &total);
-    ctl->hist[ps * 256 + tid] = ex;
-  }
-  grid_barrier(&ctl->barrier, G, epoch);
-
-  // ---- phase 4: radix passes.  CTA c takes tiles c, c+G, ...: every predecessor
-  // of a tile is finished or in flight on a co-resident CTA (look-back progress).
-  u64* kin = a.k0;
-  u64* kout = a.k1;
-  u32* vin = a.v0;
-  u32* vout = a.v1;
-  for (int ps = 0; ps < npass; ++ps) {
-    for (u64 t = c; t < a.T; t += G)
-      rs_tile_pass<FI>(sm.rs, (u32)t, kin, vin, kout, vout, n, 8 * ps, ctl->hist + ps * 256,
-                       a.tile_state + (u64)ps * a.T * 256);
+  // ---- radix rounds.  (kin, vin) holds the current order; round r packs into the
+  // other pair (reading the order of round r-1) and sorts that.
+  u64* kcur = a.k0;
+  u32* vcur = a.v0;
+  u64* kalt = a.k1;
+  u32* valt = a.v1;
+  u32 gpass = 0;  // passes done so far (selects the look-back state buffer)
+  if (nrounds == 0) {
+    for (u64 i = gtid; i < n; i += gstride) {
+      kcur[i] = 0;
+      vcur[i] = (u32)i;
+    }
     grid_barrier(&ctl->barrier, G, epoch);
-    u64* tk = kin;
-    kin = kout;
-    kout = tk;
-    u32* tv = vin;
-    vin = vout;
-    vout = tv;
   }
-  const u64* keys = kin;  // sorted composites
-  const u32* perm = vin;  // sorted row indices (identity order if npass == 0)
+  for (int r = 0; r < nrounds; ++r) {
+    const int npass = (s_rbits[r] + 7) / 8;
+    u32* hist = ctl->hist + r * 8 * 256;
+    // pack + histogram of every digit place of this round
+    for (int i = tid; i < 8 * 256; i += FT) sm.hist[i] = 0;
+    __syncthreads();
+    u64* kdst = r == 0 ? kcur : kalt;
+    u32* vdst = r == 0 ? vcur : valt;
+    for (u64 i = gtid; i < n; i += gstride) {
+      const u32 src = r == 0 ? (u32)i : vcur[i];
+      u64 row[NW];
+      load_in(src, row);
+      u64 comp = 0;
+      for (int j = 0; j < s_nwords; ++j)
+        if (s_round[j] == r) comp |= (row[s_word[j]] - s_minv[j]) << s_shift[j];
+      kdst[i] = comp;
+      vdst[i] = src;
+      for (int ps = 0; ps < npass; ++ps) atomicAdd(&sm.hist[ps * 256 + (u32)((comp >> (8 * ps)) & 255)], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < npass * 256; i += FT) {
+      u32 v = sm.hist[i];
+      if (v) atomicAdd(&hist[i], v);
+    }
+    if (r > 0) {
+      u64* tk = kcur;
+      kcur = kalt;
+      kalt = tk;
+      u32* tv = vcur;
+      vcur = valt;
+      valt = tv;
+    }
+    grid_barrier(&ctl->barrier, G, epoch);
+    // exclusive scan of each pass's histogram (one CTA per pass)
+    for (int ps = c; ps < npass; ps += G) {
+      u32 v = *(volatile u32*)&hist[ps * 256 + tid];
+      u32 total;
+      u32 ex = block_exclusive_scan(v, sm_scan, &total);
+      hist[ps * 256 + tid] = ex;
+    }
+    grid_barrier(&ctl->barrier, G, epoch);
+    // passes.  CTA c takes tiles c, c+G, ...: every predecessor of a tile is done
+    // or in flight on a co-resident CTA.  The other state buffer is cleared for
+    // the next pass meanwhile.
+    for (int ps = 0; ps < npass; ++ps, ++gpass) {
+      u32* st = (gpass & 1) ? a.state1 : a.state0;
+      u32* st_next = (gpass & 1) ? a.state0 : a.state1;
+      for (u64 t = c; t < T; t += G) {
+        for (int i = tid; i < 256; i += FT) st_next[t * 256 + i] = 0;
+        rs_tile_pass<FI>(sm.rs, (u32)t, kcur, vcur, kalt, valt, n, 8 * ps, hist + ps * 256, st);
+      }
+      grid_barrier(&ctl->barrier, G, epoch);
+      u64* tk = kcur;
+      kcur = kalt;
+      kalt = tk;
+      u32* tv = vcur;
+      vcur = valt;
+      valt = tv;
+    }
+  }
+  const u32* perm = vcur;  // final order
 
-  // ---- phase 5: gather rows, head flags, per-tile head counts
+  // ---- gather rows, head flags, per-tile head counts
   const u64 U = (n + FT - 1) / FT;
+  auto is_head = [&](u64 i) -> u32 {
+    if (i == 0) return 1u;
+    const u64* p = a.sorted + i * NW;
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      if (p[k] != p[k - NW]) return 1u;
+    return 0u;
+  };
   for (u64 u = c; u < U; u += G) {
     const u64 i = u * FT + tid;
-    u32 flag = 0;
     if (i < n) {
       u64 r[NW];
-      load_row<NW>(a.rows, perm[i], r);
+      load_in(perm[i], r);
       store_row<NW>(a.sorted, i, r);
-      flag = (i == 0) ? 1u : (keys[i] != keys[i - 1] ? 1u : 0u);
     }
+  }
+  grid_barrier(&ctl->barrier, G, epoch);
+  for (u64 u = c; u < U; u += G) {
+    const u64 i = u * FT + tid;
+    u32 flag = i < n ? is_head(i) : 0u;
     u32 total;
     block_exclusive_scan(flag, sm_scan, &total);
     if (tid == 0) a.tile_cnt[u] = total;
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
-  // ---- phase 6: segmented sums
+  // ---- segmented sums
   for (u64 u = c; u < U; u += G) {
     const u32 base = block_sum_prefix(a.tile_cnt, u, sm_scan);
     const u64 i = u * FT + tid;
     const bool valid = i < n;
-    u32 flag = 0;
-    if (valid) flag = (i == 0) ? 1u : (keys[i] != keys[i - 1] ? 1u : 0u);
+    u32 flag = valid ? is_head(i) : 0u;
     u32 total;
     u32 ex = block_exclusive_scan(flag, sm_scan, &total);
     u32 seg = valid ? base + ex + flag - 1 : 0xffffffffu;
@@ -280,51 +381,64 @@ __global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
-  // ---- phase 7: non-zero segments per tile
-  const u64 S = *(volatile u64*)&ctl->n_seg;
+  // ---- surviving segments per tile: ship (time < upper) and keep
+  const u64 S = U == 0 ? 0 : *(volatile u64*)&ctl->n_seg;
   const u64 V = (S + FT - 1) / FT;
+  const u64 upper = a.upper;
+  auto seg_class = [&](u64 s, u64* d) -> u32 {  // 0 dropped, 1 ship, 2 keep
+#pragma unroll
+    for (int w = 0; w < ND; ++w) d[w] = *(volatile u64*)&a.seg_sums[s * ND + w];
+    if (diff_is_zero<ND>(d)) return 0u;
+    if (TW < 0 || upper == MZGPU_FRONTIER_EMPTY) return 1u;
+    const u64 t = a.sorted[(u64)a.seg_first[s] * NW + (TW >= 0 ? TW : 0)];
+    return t < upper ? 1u : 2u;
+  };
   for (u64 v = c; v < V; v += G) {
     const u64 s = v * FT + tid;
-    u32 flag = 0;
-    if (s < S) {
-      u64 d[ND];
-#pragma unroll
-      for (int w = 0; w < ND; ++w) d[w] = *(volatile u64*)&a.seg_sums[s * ND + w];
-      flag = diff_is_zero<ND>(d) ? 0u : 1u;
-    }
+    u64 d[ND];
+    u32 cls = s < S ? seg_class(s, d) : 0u;
     u32 total;
-    block_exclusive_scan(flag, sm_scan, &total);
+    block_exclusive_scan(cls == 1u ? 1u : 0u, sm_scan, &total);
     if (tid == 0) a.tile_cnt[v] = total;
+    block_exclusive_scan(cls == 2u ? 1u : 0u, sm_scan, &total);
+    if (tid == 0) a.tile_cnt2[v] = total;
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
-  // ---- phase 8: emit surviving rows
+  // ---- emit
   for (u64 v = c; v < V; v += G) {
     const u32 base = block_sum_prefix(a.tile_cnt, v, sm_scan);
+    const u32 base2 = a.keep != nullptr ? block_sum_prefix(a.tile_cnt2, v, sm_scan) : 0u;
     const u64 s = v * FT + tid;
-    u32 flag = 0;
     u64 d[ND];
-    if (s < S) {
-#pragma unroll
-      for (int w = 0; w < ND; ++w) d[w] = *(volatile u64*)&a.seg_sums[s * ND + w];
-      flag = diff_is_zero<ND>(d) ? 0u : 1u;
-    }
-    u32 total;
-    u32 ex = block_exclusive_scan(flag, sm_scan, &total);
-    if (flag) {
+    u32 cls = s < S ? seg_class(s, d) : 0u;
+    u32 total, total2;
+    u32 ex = block_exclusive_scan(cls == 1u ? 1u : 0u, sm_scan, &total);
+    u32 ex2 = block_exclusive_scan(cls == 2u ? 1u : 0u, sm_scan, &total2);
+    if (cls != 0u) {
       u64 r[NW];
       load_row<NW>(a.sorted, a.seg_first[s], r);
 #pragma unroll
       for (int w = 0; w < ND; ++w) r[NK + w] = d[w];
-      store_row<NW>(a.out, (u64)base + ex, r);
+      if (cls == 1u) {
+        store_row<NW>(a.out, (u64)base + ex, r);
+      } else if (a.keep != nullptr) {
+        store_row<NW>(a.keep, (u64)base2 + ex2, r);
+        if (TW >= 0) atomicMin((unsigned long long*)&a.kres[1], (unsigned long long)r[TW >= 0 ? TW : 0]);
+      }
     }
-    if (v == V - 1 && tid == 0) ctl->n_out = (u64)base + total;
+    if (v == V - 1 && tid == 0) {
+      ctl->n_out = (u64)base + total;
+      a.res[0] = (u64)base + total;
+      a.kres[0] = (u64)base2 + total2;
+    }
   }
   if (a.table == nullptr) return;
   grid_barrier(&ctl->barrier, G, epoch);
 
-  // ---- phase 9: hash index over the distinct keys of the output
+  // ---- hash index over the distinct keys of the output; longest key run
   const u64 n_out = V == 0 ? 0 : *(volatile u64*)&ctl->n_out;
+  u32 my_run = 0;
   for (u64 i = gtid; i < ((n_out + 31) / 32) * 32; i += gstride) {
     bool head = false;
     u64 key = 0;
@@ -333,9 +447,9 @@ __global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a
       head = (i == 0) || a.out[(i - 1) * NW] != key;
     }
     u32 m = __ballot_sync(0xffffffffu, head);
-    if (lane_id() == 0 && m) atomicAdd((unsigned long long*)&ctl->n_keys, (unsigned long long)__popc(m));
+    if (lane_id() == 0 && m) atomicAdd((unsigned long long*)&a.res[2], (unsigned long long)__popc(m));
     if (head) {
-      u64 h = mix64(key) & a.mask;
+      u64 h = mix64(key) & mask;
       while (true) {
         unsigned long long prev =
             atomicCAS((unsigned long long*)&a.table[h].meta, 0ull, (unsigned long long)(i + 1));
@@ -343,72 +457,99 @@ __global__ void __launch_bounds__(FT) k_fused_sort_consolidate(const FusedArgs a
           a.table[h].key = key;
           break;
         }
-        h = (h + 1) & a.mask;
+        h = (h + 1) & mask;
       }
+      u32 run = 1;
+      while (run < MAX_RUN_SAT && i + run < n_out && a.out[(i + run) * NW] == key) ++run;
+      my_run = run > my_run ? run : my_run;
     }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    u32 o = __shfl_xor_sync(0xffffffffu, my_run, off);
+    my_run = o > my_run ? o : my_run;
+  }
+  if (lane_id() == 0 && my_run) atomicMax((unsigned long long*)&a.res[3], (unsigned long long)my_run);
 }
 
 template <int RB>
-int32_t fused_t(mzgpu_ctx* ctx, const u64* rows, u64 n, bool want_index, FusedResult* res) {
-  constexpr int ND = RowT<RB>::ND, NK = RowT<RB>::NK, TW = RowT<RB>::TW;
+int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
+  constexpr int ND = RowT<RB>::ND;
   static int max_ctas = 0;
   if (max_ctas == 0) {
     int per_sm = 0;
-    MZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_sort_consolidate<RB>, FT, 0));
+    MZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_consolidate<RB>, FT, 0));
     max_ctas = per_sm * ctx->num_sms;
     if (max_ctas <= 0) {
       MZ_SET_ERR(ctx, "fused kernel cannot be made resident");
       return MZGPU_E_CUDA;
     }
   }
+  const u64 cap = job.cap > 0 ? job.cap : 1;
+  if (cap > MZ_FUSED_MAX_ROWS) {
+    MZ_SET_ERR(ctx, "fused consolidate: %llu rows exceed the fused limit", (unsigned long long)cap);
+    return MZGPU_E_INVALID;
+  }
   FusedArgs a;
   memset(&a, 0, sizeof(a));
-  a.rows = rows;
-  a.n = n;
-  a.T = (n + FTILE - 1) / FTILE;
+  a.a = (const u64*)job.a;
+  a.b = (const u64*)job.b;
+  a.na = job.na;
+  a.nb = job.nb;
+  a.since = job.since;
+  a.upper = job.upper;
+  const u64 Tcap = (cap + FTILE - 1) / FTILE;
+  const u64 Ucap = (cap + FT - 1) / FT;
   u64 slots = 0;
-  if (want_index) {
+  if (job.want_index) {
     slots = 2;
-    while (slots < 2 * n) slots <<= 1;
+    while (slots < 2 * cap) slots <<= 1;
   }
-  DevMem ctl, kv, state, sorted, tiles, sums, first;
-  MZ_TRY(ctl.alloc(ctx, sizeof(FusedCtl)));
-  MZ_TRY(kv.alloc(ctx, n * 24));
-  MZ_TRY(state.alloc(ctx, 8ull * a.T * 256 * 4));
-  MZ_TRY(sorted.alloc(ctx, n * RB));
-  MZ_TRY(tiles.alloc(ctx, ((n + FT - 1) / FT) * 4));
-  MZ_TRY(sums.alloc(ctx, n * ND * 8));
-  MZ_TRY(first.alloc(ctx, n * 4));
-  MZ_TRY(res->rows.alloc(ctx, n * RB));
-  if (want_index) MZ_TRY(res->table.alloc(ctx, slots * sizeof(HashSlot)));
-  // control block: zero, then the min/max identities
-  FusedCtl* h = (FusedCtl*)ctx->h_fused;
-  memset(h, 0, sizeof(FusedCtl));
-  for (int k = 0; k < 6; ++k) h->minmax[2 * k] = ~0ull;
-  MZ_CUDA(ctx, cudaMemcpyAsync(ctl.p, h, sizeof(FusedCtl), cudaMemcpyHostToDevice, ctx->stream));
-  a.ctl = ctl.as<FusedCtl>();
-  a.k0 = kv.as<u64>();
-  a.k1 = a.k0 + n;
-  a.v0 = (u32*)(a.k1 + n);
-  a.v1 = a.v0 + n;
-  a.tile_state = state.as<u32>();
-  a.sorted = sorted.as<u64>();
-  a.tile_cnt = tiles.as<u32>();
-  a.seg_sums = sums.as<u64>();
-  a.seg_first = first.as<u32>();
+  // one scratch allocation, carved up (every region 16-byte aligned)
+  auto al = [](u64 x) { return (x + 15) & ~(u64)15; };
+  const u64 o_k0 = 0, o_k1 = o_k0 + al(cap * 8), o_v0 = o_k1 + al(cap * 8), o_v1 = o_v0 + al(cap * 4);
+  const u64 o_s0 = o_v1 + al(cap * 4), o_s1 = o_s0 + al(Tcap * 1024), o_sorted = o_s1 + al(Tcap * 1024);
+  const u64 o_t1 = o_sorted + al(cap * RB), o_t2 = o_t1 + al(Ucap * 4), o_sums = o_t2 + al(Ucap * 4);
+  const u64 o_first = o_sums + al(cap * ND * 8), o_end = o_first + al(cap * 4);
+  DevMem scratch;
+  MZ_TRY(scratch.alloc(ctx, o_end));
+  MZ_TRY(res->rows.alloc(ctx, cap * RB));
+  res->rows_cap = cap;
+  const bool want_keep = job.upper != MZGPU_FRONTIER_EMPTY && RowT<RB>::TW >= 0;
+  if (want_keep) MZ_TRY(res->keep.alloc(ctx, cap * RB));
+  if (job.want_index) MZ_TRY(res->table.alloc(ctx, slots * sizeof(HashSlot)));
+  MZ_TRY(res->st.make_pending(ctx));
+  MZ_TRY(res->kst.make_pending(ctx));
+  char* sp = (char*)scratch.p;
+  a.ctl = (FusedCtl*)ctx->d_fused_ctl[ctx->fused_flip];
+  a.ctl_next = (FusedCtl*)ctx->d_fused_ctl[ctx->fused_flip ^ 1];
+  ctx->fused_flip ^= 1;
+  a.k0 = (u64*)(sp + o_k0);
+  a.k1 = (u64*)(sp + o_k1);
+  a.v0 = (u32*)(sp + o_v0);
+  a.v1 = (u32*)(sp + o_v1);
+  a.state0 = (u32*)(sp + o_s0);
+  a.state1 = (u32*)(sp + o_s1);
+  a.sorted = (u64*)(sp + o_sorted);
+  a.tile_cnt = (u32*)(sp + o_t1);
+  a.tile_cnt2 = (u32*)(sp + o_t2);
+  a.seg_sums = (u64*)(sp + o_sums);
+  a.seg_first = (u32*)(sp + o_first);
   a.out = res->rows.template as<u64>();
-  a.table = want_index ? res->table.template as<HashSlot>() : nullptr;
-  a.mask = want_index ? slots - 1 : 0;
-  u64 want = a.T > ((n + FT - 1) / FT + 3) / 4 ? a.T : ((n + FT - 1) / FT + 3) / 4;
+  a.keep = want_keep ? res->keep.template as<u64>() : nullptr;
+  a.table = job.want_index ? res->table.template as<HashSlot>() : nullptr;
+  a.table_cap = slots;
+  a.res = res->st.dptr();
+  a.kres = res->kst.dptr();
+  u64 want = Tcap;
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);
   if (grid == 0) grid = 1;
   void* kargs[] = {(void*)&a};
   {
-    MZ_BYTES(ctx, n * RB * 4);  // rows read (analyze, pack, gather) + sorted + out written; see DESIGN.md
-    ProfScope prof(ctx, "k_fused_sort_consolidate");
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_fused_sort_consolidate<RB>, dim3(grid), dim3(FT), kargs,
-                                                0, ctx->stream);
+    MZ_BYTES(ctx, cap * RB * 4);  // rows read (analyze, pack, gather) + sorted + out written; see DESIGN.md
+    ProfScope prof(ctx, "k_fused_consolidate");
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_fused_consolidate<RB>, dim3(grid), dim3(FT), kargs, 0,
+                                                ctx->stream);
     if (e != cudaSuccess) {
       MZ_SET_ERR(ctx, "cooperative launch failed: %s", cudaGetErrorString(e));
       ctx->sticky = true;
@@ -416,32 +557,24 @@ int32_t fused_t(mzgpu_ctx* ctx, const u64* rows, u64 n, bool want_index, FusedRe
     }
   }
   ctx->stats.kernel_launches++;
-  MZ_CUDA(ctx, cudaMemcpyAsync(h, ctl.p, offsetof(FusedCtl, hist), cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->stats.d2h_bytes += offsetof(FusedCtl, hist);
-  res->fallback = h->fallback != 0;
-  res->n_out = h->n_out;
-  res->n_keys = h->n_keys;
-  res->slots = slots;
-  res->min_time = TW >= 0 ? h->minmax[2 * (TW >= 0 ? TW : 0)] : 0;
-  res->max_time = TW >= 0 ? h->minmax[2 * (TW >= 0 ? TW : 0) + 1] : 0;
-  (void)NK;
+  res->st.mark_written();
+  res->kst.mark_written();
   return MZGPU_OK;
 }
 
 }  // namespace
 
-int32_t mz_fused_sort_consolidate(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, bool want_index,
-                                  FusedResult* res) {
-  const u64* r = (const u64*)d_rows;
-  switch (row_bytes) {
-    case 16: return fused_t<16>(ctx, r, n, want_index, res);
-    case 32: return fused_t<32>(ctx, r, n, want_index, res);
-    case 40: return fused_t<40>(ctx, r, n, want_index, res);
-    case 80: return fused_t<80>(ctx, r, n, want_index, res);
-    case 64: return fused_t<64>(ctx, r, n, want_index, res);
+size_t mz_fused_ctl_bytes() { return sizeof(FusedCtl); }
+
+int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
+  switch (job.rb) {
+    case 16: return fused_t<16>(ctx, job, res);
+    case 32: return fused_t<32>(ctx, job, res);
+    case 40: return fused_t<40>(ctx, job, res);
+    case 80: return fused_t<80>(ctx, job, res);
+    case 64: return fused_t<64>(ctx, job, res);
     default:
-      MZ_SET_ERR(ctx, "fused: unsupported row width %d", row_bytes);
+      MZ_SET_ERR(ctx, "fused: unsupported row width %d", job.rb);
       return MZGPU_E_UNSUPPORTED;
   }
 }

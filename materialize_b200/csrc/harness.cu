@@ -121,6 +121,7 @@ struct mzh_q3 {
   uint64_t gen_cap_orders = 0;
   uint64_t next_time = 0;
   uint64_t last_rows_in = 0;
+  uint64_t maintain_upper = 0;  // timestamp whose maintenance is still due
 };
 
 static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, int n_versions, uint64_t t,
@@ -159,10 +160,15 @@ static int32_t q3_arrange_push(mzh_q3* q, int a, mzgpu_buf* rows) {
     H_TRY(mzgpu_exchange(q->ctx, rows, q->xchg));
     src = q->xchg;
   }
-  return mzgpu_batcher_push(q->batcher[a], mzgpu_buf_device_ptr(src), mzgpu_buf_len(src), MZGPU_MEM_DEVICE);
+  return mzgpu_batcher_push_buf(q->batcher[a], src);
 }
 
-// everything after the inputs were pushed: seal, paths, reduce, compaction
+// everything after the inputs were pushed: seal, paths, reduce; then the
+// maintenance the reference's worker loop does between operator activations
+// (TraceManager::maintenance, src/compute/src/arrangement/manager.rs:55-73):
+// physical compaction to the new upper, logical compaction, idle merge effort.
+// Nothing in the operator part reads a row count back: counts flow between the
+// operators in device memory (see include/mzgpu.h).
 static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   const uint64_t upper = t + 1;
   mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -170,7 +176,6 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
     st = mzgpu_batcher_seal(q->batcher[a], upper, &batch[a], nullptr);
     if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
-    if (st == MZGPU_OK) st = mzgpu_spine_set_physical_compaction(q->spine[a], upper);
   }
   if (st == MZGPU_OK) st = mzgpu_buf_clear(q->results);
   for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
@@ -187,31 +192,36 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       }
       st = mzgpu_buf_clear(q->next_buf);
       if (st == MZGPU_OK)
-        st = mzgpu_half_join(q->ctx, (const mzgpu_r32*)mzgpu_buf_device_ptr(q->stream_buf),
-                             mzgpu_buf_len(q->stream_buf), MZGPU_MEM_DEVICE,
-                             q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                             &q->plan.stage[path][s], 0, q->next_buf);
+        st = mzgpu_half_join_buf(q->ctx, q->stream_buf, q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
+                                 &q->plan.stage[path][s], 0, q->next_buf);
       std::swap(q->stream_buf, q->next_buf);
     }
-    if (st == MZGPU_OK)
-      st = mzgpu_buf_append(q->results, mzgpu_buf_device_ptr(q->stream_buf), mzgpu_buf_len(q->stream_buf),
-                            MZGPU_MEM_DEVICE);
+    if (st == MZGPU_OK) st = mzgpu_buf_append_buf(q->results, q->stream_buf);
   }
   if (st == MZGPU_OK && q->peers > 1) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);
     std::swap(q->results, q->xchg);
   }
-  if (st == MZGPU_OK)
-    st = mzgpu_reduce_accumulable(q->reduce, (const mzgpu_r32*)mzgpu_buf_device_ptr(q->results),
-                                  mzgpu_buf_len(q->results), MZGPU_MEM_DEVICE, upper, q->out);
+  if (st == MZGPU_OK) st = mzgpu_reduce_accumulable_buf(q->reduce, q->results, upper, q->out);
+  for (int a = 0; a < 4; ++a)
+    if (batch[a]) mzgpu_batch_release(batch[a]);
+  q->maintain_upper = upper;
+  return st;
+}
+
+// Between-activations maintenance for the timestamp that just ran.
+static int32_t q3_maintenance(mzh_q3* q) {
+  if (q->maintain_upper == 0) return MZGPU_OK;
+  const uint64_t upper = q->maintain_upper, t = upper - 1;
+  q->maintain_upper = 0;
+  int32_t st = MZGPU_OK;
   for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
-    st = mzgpu_spine_set_logical_compaction(q->spine[a], t);
+    st = mzgpu_spine_set_physical_compaction(q->spine[a], upper);
+    if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(q->spine[a], t);
     uint64_t e = mzgpu_spine_exert_logic(q->spine[a], 16);
     if (st == MZGPU_OK && e) st = mzgpu_spine_exert(q->spine[a], e, nullptr);
   }
   if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(mzgpu_reduce_input_trace(q->reduce), t);
-  for (int a = 0; a < 4; ++a)
-    if (batch[a]) mzgpu_batch_release(batch[a]);
   return st;
 }
 
@@ -304,6 +314,7 @@ int32_t mzh_q3_hydrate(mzh_q3* q, uint64_t* rows_in) {
   H_TRY(mzgpu_buf_clear(tmp));
   if (rows_in) *rows_in = total;
   H_TRY(q3_run_timestamp(q, 0));
+  H_TRY(q3_maintenance(q));
   q->next_time = 1;
   return MZGPU_OK;
 }
@@ -347,15 +358,20 @@ int32_t mzh_q3_staged(mzh_q3* q, int32_t a, mzgpu_r32* rows, uint64_t cap, uint6
   return mzgpu_buf_download(q->input[a], rows, cap, MZGPU_MEM_HOST, n);
 }
 
-// One timestamp over the staged inputs (inputs already resident in HBM).
+// One timestamp over the staged inputs (inputs already resident in HBM).  The
+// device work is enqueued and the call returns; the previous timestamp's
+// maintenance runs first (its counts have reached the host by now).
 int32_t mzh_q3_step(mzh_q3* q) {
   if (q == nullptr) return MZGPU_E_INVALID;
+  H_TRY(q3_maintenance(q));
   const uint64_t t = q->next_time;
   for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
   H_TRY(q3_run_timestamp(q, t));
   q->next_time = t + 1;
   return MZGPU_OK;
 }
+// Run the maintenance that is due (tests call this before inspecting the spines).
+int32_t mzh_q3_maintain(mzh_q3* q) { return q ? q3_maintenance(q) : MZGPU_E_INVALID; }
 
 // Output corrections (ROUT rows) accumulated since the last clear.
 mzgpu_buf* mzh_q3_out(mzh_q3* q) { return q ? q->out : nullptr; }

@@ -32,7 +32,19 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 128 * 8));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 128 * 8));
-  MZ_CUDA(ctx, cudaMallocHost(&ctx->h_fused, 16384));
+  // device-resident counters, look-back state, tile tickets, fused control blocks
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_cnt, (size_t)MZ_CNT_BLOCKS * 32));
+  MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_cnt, (size_t)MZ_CNT_BLOCKS * 32));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_lb, (size_t)MZ_LB_TILES * 8));
+  MZ_CUDA(ctx, cudaMemset(ctx->d_lb, 0, (size_t)MZ_LB_TILES * 8));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_tickets, (size_t)MZ_TICKETS * 4));
+  MZ_CUDA(ctx, cudaMemset(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_status, 16));
+  MZ_CUDA(ctx, cudaMemset(ctx->d_status, 0, 16));
+  for (int i = 0; i < 2; ++i) {
+    MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl[i], mz_fused_ctl_bytes()));
+    MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
+  }
   // keep freed blocks cached in the stream-ordered pool
   cudaMemPool_t pool;
   MZ_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -50,7 +62,13 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
     if (f) f(ctx->nccl_comm);
   }
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
-  if (ctx->h_fused) cudaFreeHost(ctx->h_fused);
+  if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+  if (ctx->d_cnt) cudaFree(ctx->d_cnt);
+  if (ctx->d_lb) cudaFree(ctx->d_lb);
+  if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+  if (ctx->d_status) cudaFree(ctx->d_status);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev) cudaEventDestroy(ctx->ev);
   for (auto& r : ctx->prof) {
@@ -66,10 +84,61 @@ extern "C" const char* mzgpu_last_error(mzgpu_ctx* ctx) {
   return ctx ? ctx->last_error.c_str() : "null context";
 }
 
+// ------------------------------------------------ device-resident counters
+int mz_cnt_alloc(mzgpu_ctx* ctx) {
+  if (!ctx->cnt_free.empty()) {
+    int b = ctx->cnt_free.back();
+    ctx->cnt_free.pop_back();
+    return b;
+  }
+  if (ctx->cnt_high < MZ_CNT_BLOCKS) return ctx->cnt_high++;
+  return -1;
+}
+void mz_cnt_free(mzgpu_ctx* ctx, int blk) {
+  if (ctx != nullptr && blk >= 0) ctx->cnt_free.push_back(blk);
+}
+// One copy of the whole arena (a few KB) + one wait: every count produced by a
+// kernel enqueued before this call becomes readable on the host.
+int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
+  MZ_CHECK_CTX(ctx);
+  const size_t bytes = (size_t)ctx->cnt_high * 32;
+  if (bytes) MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 40, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_SYNC(ctx);
+  ctx->stats.d2h_bytes += bytes + 16;
+  ctx->resolved_seq = ctx->op_seq;
+  ctx->n_resolves++;
+  if (ctx->h_scratch[40] != 0) {
+    MZ_SET_ERR(ctx, "internal: a bounded operator output overflowed its capacity (%llu rows required)",
+               (unsigned long long)ctx->h_scratch[40]);
+    ctx->sticky = true;
+    return MZGPU_E_CAPACITY;
+  }
+  return MZGPU_OK;
+}
+int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb) {
+  if (max_tiles > MZ_LB_TILES) {
+    MZ_SET_ERR(ctx, "single-pass kernel: %llu tiles exceed the look-back state", (unsigned long long)max_tiles);
+    return MZGPU_E_UNSUPPORTED;
+  }
+  ctx->lb_epoch = (ctx->lb_epoch + 1) & 0xfffffu;
+  if (ctx->lb_epoch == 0) {  // tag space wrapped: clear the state once
+    MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_lb, 0, (size_t)MZ_LB_TILES * 8, ctx->stream));
+    ctx->lb_epoch = 1;
+  }
+  if (ctx->ticket_next == MZ_TICKETS) {
+    MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4, ctx->stream));
+    ctx->ticket_next = 0;
+  }
+  lb->state = ctx->d_lb;
+  lb->ticket = ctx->d_tickets + ctx->ticket_next++;
+  lb->epoch = ctx->lb_epoch;
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_ctx_sync(mzgpu_ctx* ctx) {
   MZ_CHECK_CTX(ctx);
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MZGPU_OK;
+  return mz_resolve_counters(ctx);
 }
 
 extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
@@ -87,7 +156,7 @@ extern "C" int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on) {
 extern "C" int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap) {
   MZ_CHECK_CTX(ctx);
   if (buf == nullptr || cap == 0) return MZGPU_E_INVALID;
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   struct Agg {
     std::string name;
     u64 launches = 0, bytes = 0;
@@ -144,7 +213,7 @@ static int32_t copy_out(mzgpu_ctx* ctx, void* dst, const void* d_src, size_t byt
   if (bytes == 0) return MZGPU_OK;
   if (mem == MZGPU_MEM_HOST) {
     MZ_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MZ_SYNC(ctx);
     ctx->stats.d2h_bytes += bytes;
   } else {
     MZ_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -154,21 +223,95 @@ static int32_t copy_out(mzgpu_ctx* ctx, void* dst, const void* d_src, size_t byt
 
 static bool valid_row_bytes(uint32_t rb) { return rb == 16 || rb == 32 || rb == 40 || rb == 80 || rb == 64; }
 
+// ------------------------------------------------------ device-side append
+// dst[base ...] = src[0 .. n), new length left in *out_len; every size may live
+// in device memory.
+namespace {
+__global__ void __launch_bounds__(256) k_append_rows(const u64* __restrict__ src, const DLen dn, int nw,
+                                                     u64* __restrict__ dst, const DLen dbase, u64 cap_rows,
+                                                     u64* __restrict__ out_len, u64* __restrict__ status) {
+  const u64 n = dlen_get(dn), base = dlen_get(dbase);
+  const u64 gtid = (u64)blockIdx.x * 256 + threadIdx.x, stride = (u64)gridDim.x * 256;
+  u64 m = n;
+  if (base + n > cap_rows) {
+    if (gtid == 0) atomicMax((unsigned long long*)status, (unsigned long long)(base + n));
+    m = cap_rows > base ? cap_rows - base : 0;
+  }
+  const u64 words = m * (u64)nw;
+  u64* d = dst + base * (u64)nw;
+  for (u64 i = gtid; i < words; i += stride) d[i] = src[i];
+  if (gtid == 0) *out_len = base + n;
+}
+}  // namespace
+
+static int32_t append_dev(mzgpu_ctx* ctx, const void* src, DLen n, u64 n_ub, int rb, void* dst, DLen base,
+                          u64 cap_rows, u64* out_len) {
+  u64 grid = (n_ub * (u64)(rb / 8) + 1023) / 1024;
+  const u64 maxg = (u64)ctx->num_sms * 8;
+  if (grid > maxg) grid = maxg;
+  if (grid == 0) grid = 1;
+  MZ_BYTES(ctx, n_ub * rb * 2);
+  MZ_LAUNCH(ctx, k_append_rows, (unsigned)grid, 256, 0, (const u64*)src, n, rb / 8, (u64*)dst, base, cap_rows,
+            out_len, ctx->d_status);
+  return MZGPU_OK;
+}
+
 // ====================================================================== buf
 struct mzgpu_buf {
   mzgpu_ctx* ctx;
   uint32_t rb;
   DevMem mem;
-  u64 len = 0;
   u64 cap = 0;
+  Lazy4 len;     // the row count is word `word` of the block while it is pending
+  int word = 0;
+  u64 ub = 0;    // host upper bound on the row count (exact when len.known)
 };
+
+static DLen buf_dlen(const mzgpu_buf* b) { return dlen_of(b->len, b->word); }
+static void buf_set_len(mzgpu_buf* b, u64 n) {
+  b->len.set(b->ctx, n);
+  b->word = 0;
+  b->ub = n;
+}
+static int32_t buf_resolve(mzgpu_buf* b) {
+  if (b->len.known) return MZGPU_OK;
+  MZ_TRY(b->len.resolve());
+  buf_set_len(b, b->len.v[b->word]);
+  return MZGPU_OK;
+}
+// An operator is about to append a device-counted number of rows: where it
+// reads the current length and where it leaves the new one (never the same word).
+struct Append {
+  DLen base;
+  u64* out_len;
+  int new_word;
+};
+static int32_t buf_begin_append(mzgpu_buf* b, Append* a) {
+  if (b->len.known) {
+    a->base = dlen_imm(b->len.v[b->word]);
+    MZ_TRY(b->len.make_pending(b->ctx));
+    a->out_len = b->len.dptr();
+    a->new_word = 0;
+  } else {
+    a->base.p = b->len.dptr() + b->word;
+    a->base.imm = 0;
+    a->out_len = b->len.dptr() + (b->word ^ 1);
+    a->new_word = b->word ^ 1;
+  }
+  return MZGPU_OK;
+}
+static void buf_end_append(mzgpu_buf* b, const Append& a, u64 added_ub) {
+  b->word = a.new_word;
+  b->len.mark_written();
+  b->ub += added_ub;
+}
 
 static int32_t buf_reserve(mzgpu_buf* b, u64 n, bool keep) {
   if (n <= b->cap) return MZGPU_OK;
   u64 ncap = std::max<u64>(n, b->cap * 2);
   DevMem m;
   MZ_TRY(m.alloc(b->ctx, ncap * b->rb));
-  if (keep && b->len) MZ_TRY(copy_in(b->ctx, m.p, b->mem.p, b->len * b->rb, MZGPU_MEM_DEVICE));
+  if (keep && b->ub) MZ_TRY(copy_in(b->ctx, m.p, b->mem.p, b->ub * b->rb, MZGPU_MEM_DEVICE));
   b->mem = std::move(m);
   b->cap = ncap;
   return MZGPU_OK;
@@ -177,13 +320,21 @@ static int32_t buf_reserve(mzgpu_buf* b, u64 n, bool keep) {
 static void buf_adopt(mzgpu_buf* b, DevMem&& m, u64 len) {
   b->cap = m.bytes / b->rb;
   b->mem = std::move(m);
-  b->len = len;
+  buf_set_len(b, len);
 }
-static int32_t buf_append_dev(mzgpu_buf* b, const void* d_rows, u64 n) {
-  if (n == 0) return MZGPU_OK;
-  MZ_TRY(buf_reserve(b, b->len + n, true));
-  MZ_TRY(copy_in(b->ctx, (char*)b->mem.p + b->len * b->rb, d_rows, n * b->rb, MZGPU_MEM_DEVICE));
-  b->len += n;
+// append n device rows; n may be device resident
+static int32_t buf_append_dev(mzgpu_buf* b, const void* d_rows, DLen n, u64 n_ub) {
+  if (n_ub == 0) return MZGPU_OK;
+  MZ_TRY(buf_reserve(b, b->ub + n_ub, true));
+  if (b->len.known && n.p == nullptr) {
+    MZ_TRY(copy_in(b->ctx, (char*)b->mem.p + b->ub * b->rb, d_rows, n.imm * b->rb, MZGPU_MEM_DEVICE));
+    buf_set_len(b, b->ub + n.imm);
+    return MZGPU_OK;
+  }
+  Append a;
+  MZ_TRY(buf_begin_append(b, &a));
+  MZ_TRY(append_dev(b->ctx, d_rows, n, n_ub, b->rb, b->mem.p, a.base, b->cap, a.out_len));
+  buf_end_append(b, a, n_ub);
   return MZGPU_OK;
 }
 
@@ -193,53 +344,97 @@ extern "C" int32_t mzgpu_buf_new(mzgpu_ctx* ctx, uint32_t row_bytes, mzgpu_buf**
   mzgpu_buf* b = new mzgpu_buf();
   b->ctx = ctx;
   b->rb = row_bytes;
+  b->len.set(ctx, 0);
   *out = b;
   return MZGPU_OK;
 }
 extern "C" void mzgpu_buf_free(mzgpu_buf* b) { delete b; }
-extern "C" uint64_t mzgpu_buf_len(const mzgpu_buf* b) { return b ? b->len : 0; }
+extern "C" uint64_t mzgpu_buf_len(const mzgpu_buf* b) {
+  if (b == nullptr) return 0;
+  if (buf_resolve(const_cast<mzgpu_buf*>(b)) != MZGPU_OK) return 0;
+  return b->ub;
+}
 extern "C" uint32_t mzgpu_buf_row_bytes(const mzgpu_buf* b) { return b ? b->rb : 0; }
 extern "C" void* mzgpu_buf_device_ptr(mzgpu_buf* b) { return b ? b->mem.p : nullptr; }
 extern "C" int32_t mzgpu_buf_clear(mzgpu_buf* b) {
   if (b == nullptr) return MZGPU_E_INVALID;
-  b->len = 0;
+  buf_set_len(b, 0);
   return MZGPU_OK;
 }
 extern "C" int32_t mzgpu_buf_upload(mzgpu_buf* b, const void* rows, uint64_t n, int32_t mem) {
   if (b == nullptr || (rows == nullptr && n)) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
-  b->len = 0;
+  buf_set_len(b, 0);
   MZ_TRY(buf_reserve(b, n, false));
   MZ_TRY(copy_in(b->ctx, b->mem.p, rows, n * b->rb, mem));
-  b->len = n;
+  buf_set_len(b, n);
   b->ctx->stats.rows_in += n;
   return MZGPU_OK;
 }
 extern "C" int32_t mzgpu_buf_append(mzgpu_buf* b, const void* rows, uint64_t n, int32_t mem) {
   if (b == nullptr || (rows == nullptr && n)) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
-  MZ_TRY(buf_reserve(b, b->len + n, true));
-  MZ_TRY(copy_in(b->ctx, (char*)b->mem.p + b->len * b->rb, rows, n * b->rb, mem));
-  b->len += n;
   b->ctx->stats.rows_in += n;
+  if (n == 0) return MZGPU_OK;
+  if (mem == MZGPU_MEM_DEVICE) return buf_append_dev(b, rows, dlen_imm(n), n);
+  MZ_TRY(buf_resolve(b));  // host rows land at an offset the host must know
+  MZ_TRY(buf_reserve(b, b->ub + n, true));
+  MZ_TRY(copy_in(b->ctx, (char*)b->mem.p + b->ub * b->rb, rows, n * b->rb, mem));
+  buf_set_len(b, b->ub + n);
   return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_buf_append_buf(mzgpu_buf* dst, mzgpu_buf* src) {
+  if (dst == nullptr || src == nullptr || dst == src || dst->rb != src->rb) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(dst->ctx);
+  return buf_append_dev(dst, src->mem.p, buf_dlen(src), src->ub);
 }
 extern "C" int32_t mzgpu_buf_download(mzgpu_buf* b, void* rows, uint64_t cap, int32_t mem,
                                       uint64_t* n_out) {
   if (b == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
-  if (n_out) *n_out = b->len;
-  if (cap < b->len) {
+  MZ_TRY(buf_resolve(b));
+  if (n_out) *n_out = b->ub;
+  if (cap < b->ub) {
     MZ_SET_ERR(b->ctx, "buf_download: capacity %llu < %llu rows", (unsigned long long)cap,
-               (unsigned long long)b->len);
+               (unsigned long long)b->ub);
     return MZGPU_E_CAPACITY;
   }
-  MZ_TRY(copy_out(b->ctx, rows, b->mem.p, b->len * b->rb, mem));
-  b->ctx->stats.rows_out += b->len;
+  MZ_TRY(copy_out(b->ctx, rows, b->mem.p, b->ub * b->rb, mem));
+  b->ctx->stats.rows_out += b->ub;
   return MZGPU_OK;
 }
 
 // ============================================================ consolidation
+// rows (device, count possibly device resident) -> consolidated rows; the fused
+// kernel for small / medium inputs, the multi-kernel path beyond.
+static int32_t consolidate_dev(mzgpu_ctx* ctx, int rb, const void* d_in, DLen n, u64 n_ub, DevMem* out,
+                               u64* out_cap, Lazy4* out_len) {
+  if (n_ub <= MZ_FUSED_MAX_ROWS) {
+    FusedJob job;
+    job.rb = rb;
+    job.a = d_in;
+    job.na = n;
+    job.cap = n_ub;
+    FusedOut fo;
+    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
+    *out = std::move(fo.rows);
+    *out_cap = fo.rows_cap;
+    *out_len = std::move(fo.st);
+    return MZGPU_OK;
+  }
+  u64 nn = n.imm;
+  if (n.p != nullptr) {
+    MZ_TRY(mz_resolve_counters(ctx));
+    // the block the caller's DLen points into is part of the arena mirror
+    nn = ctx->h_cnt[n.p - ctx->d_cnt];
+  }
+  u64 n_out = 0;
+  MZ_TRY(mz_sort_consolidate(ctx, rb, d_in, nn, out, &n_out));
+  *out_cap = nn;
+  out_len->set(ctx, n_out);
+  return MZGPU_OK;
+}
+
 static int32_t consolidate_ptr(mzgpu_ctx* ctx, int rb, void* rows, u64 n, int32_t mem, u64* n_out) {
   MZ_CHECK_CTX(ctx);
   if ((rows == nullptr && n) || n_out == nullptr) return MZGPU_E_INVALID;
@@ -253,7 +448,11 @@ static int32_t consolidate_ptr(mzgpu_ctx* ctx, int rb, void* rows, u64 n, int32_
     MZ_TRY(copy_in(ctx, in.p, rows, n * rb, mem));
     d_in = in.p;
   }
-  MZ_TRY(mz_sort_consolidate(ctx, rb, d_in, n, &out, n_out));
+  u64 cap = 0;
+  Lazy4 len;
+  MZ_TRY(consolidate_dev(ctx, rb, d_in, dlen_imm(n), n, &out, &cap, &len));
+  MZ_TRY(len.resolve());
+  *n_out = len.v[0];
   MZ_TRY(copy_out(ctx, rows, out.p, *n_out * rb, mem));
   ctx->stats.rows_out += *n_out;
   return MZGPU_OK;
@@ -269,11 +468,16 @@ extern "C" int32_t mzgpu_consolidate_r32(mzgpu_ctx* ctx, mzgpu_r32* rows, uint64
 extern "C" int32_t mzgpu_buf_consolidate(mzgpu_buf* b) {
   if (b == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
-  if (b->len == 0) return MZGPU_OK;
+  if (b->ub == 0) return MZGPU_OK;
   DevMem out;
-  u64 n_out = 0;
-  MZ_TRY(mz_sort_consolidate(b->ctx, b->rb, b->mem.p, b->len, &out, &n_out));
-  buf_adopt(b, std::move(out), n_out);
+  u64 cap = 0;
+  Lazy4 len;
+  MZ_TRY(consolidate_dev(b->ctx, b->rb, b->mem.p, buf_dlen(b), b->ub, &out, &cap, &len));
+  b->mem = std::move(out);
+  b->cap = cap;
+  b->ub = len.known ? len.v[0] : b->ub;
+  b->len = std::move(len);
+  b->word = 0;
   return MZGPU_OK;
 }
 
@@ -282,70 +486,120 @@ struct mzgpu_batch {
   mzgpu_ctx* ctx;
   uint32_t rb;
   DevMem rows;
-  u64 len = 0;
-  u64 n_keys = 0;
+  u64 rows_cap = 0;
   DevMem table;
-  u64 slots = 0;
+  Lazy4 st;        // [0] len, [1] table mask, [2] distinct keys, [3] longest key run (saturating at 1024)
+  u64 len_ub = 0;  // host upper bound on len
   mzgpu_desc desc;
   int refs = 1;
 };
 
-// sorted + consolidated device rows -> indexed immutable batch
+static int32_t batch_resolve(mzgpu_batch* b) {
+  if (b->st.known) return MZGPU_OK;
+  MZ_TRY(b->st.resolve());
+  b->len_ub = b->st.v[0];
+  return MZGPU_OK;
+}
+// exact length (waits for the device if the batch is still in flight)
+static u64 blen(mzgpu_batch* b) {
+  if (batch_resolve(b) != MZGPU_OK) return 0;
+  return b->st.v[0];
+}
+static DLen batch_dlen(const mzgpu_batch* b) { return dlen_of(b->st, 0); }
+
+// sorted + consolidated device rows of known length -> indexed immutable batch
 static int32_t make_batch(mzgpu_ctx* ctx, uint32_t rb, DevMem&& rows, u64 len, mzgpu_desc desc,
                           mzgpu_batch** out) {
   std::unique_ptr<mzgpu_batch> b(new mzgpu_batch());
   b->ctx = ctx;
   b->rb = rb;
+  b->rows_cap = rows.bytes / rb;
   b->rows = std::move(rows);
-  b->len = len;
+  b->len_ub = len;
   b->desc = desc;
-  MZ_TRY(mz_count_keys(ctx, rb, b->rows.p, len, &b->n_keys));
-  MZ_TRY(mz_build_index(ctx, rb, b->rows.p, len, b->n_keys, &b->table, &b->slots));
+  u64 n_keys = 0, max_run = 0, slots = 0;
+  MZ_TRY(mz_count_keys(ctx, rb, b->rows.p, len, &n_keys, &max_run));
+  MZ_TRY(mz_build_index(ctx, rb, b->rows.p, len, n_keys, &b->table, &slots));
+  b->st.set(ctx, len, slots - 1, n_keys, max_run);
   *out = b.release();
   return MZGPU_OK;
 }
-// rows + index already built (fused path)
-static int32_t make_batch_indexed(mzgpu_ctx* ctx, uint32_t rb, DevMem&& rows, u64 len, DevMem&& table,
-                                  u64 slots, u64 n_keys, mzgpu_desc desc, mzgpu_batch** out) {
+static int32_t batch_from_fused(mzgpu_ctx* ctx, uint32_t rb, FusedOut&& fo, u64 len_ub, mzgpu_desc desc,
+                                mzgpu_batch** out) {
   mzgpu_batch* b = new mzgpu_batch();
   b->ctx = ctx;
   b->rb = rb;
-  b->rows = std::move(rows);
-  b->len = len;
-  b->table = std::move(table);
-  b->slots = slots;
-  b->n_keys = n_keys;
+  b->rows = std::move(fo.rows);
+  b->rows_cap = fo.rows_cap;
+  b->table = std::move(fo.table);
+  b->st = std::move(fo.st);
+  b->len_ub = len_ub;
   b->desc = desc;
   *out = b;
   return MZGPU_OK;
 }
-// unsorted device rows -> batch: the fused kernel for small inputs, else the
-// multi-kernel path
-static int32_t build_batch_from_unsorted(mzgpu_ctx* ctx, uint32_t rb, const void* d_in, u64 n,
+// Release the slack of a batch built with a loose capacity (its length is known now).
+static int32_t batch_shrink(mzgpu_batch* b) {
+  if (!b->st.known) return MZGPU_OK;
+  mzgpu_ctx* ctx = b->ctx;
+  const u64 len = b->st.v[0];
+  if (b->rows_cap > len + len / 2 + 4096) {
+    DevMem m;
+    MZ_TRY(m.alloc(ctx, std::max<u64>(len, 1) * b->rb));
+    MZ_TRY(copy_in(ctx, m.p, b->rows.p, len * b->rb, MZGPU_MEM_DEVICE));
+    b->rows = std::move(m);
+    b->rows_cap = std::max<u64>(len, 1);
+  }
+  const u64 slots = b->st.v[1] + 1;
+  if (b->table.p != nullptr && b->table.bytes > 2 * slots * sizeof(HashSlot) + 65536) {
+    DevMem t;
+    MZ_TRY(t.alloc(ctx, slots * sizeof(HashSlot)));
+    MZ_TRY(copy_in(ctx, t.p, b->table.p, slots * sizeof(HashSlot), MZGPU_MEM_DEVICE));
+    b->table = std::move(t);
+  }
+  return MZGPU_OK;
+}
+// unsorted device rows -> batch
+static int32_t build_batch_from_unsorted(mzgpu_ctx* ctx, uint32_t rb, const void* d_in, DLen n, u64 n_ub,
                                          mzgpu_desc desc, mzgpu_batch** out) {
-  if (n > 0 && n <= MZ_FUSED_MAX_ROWS) {
-    FusedResult fr;
-    MZ_TRY(mz_fused_sort_consolidate(ctx, rb, d_in, n, true, &fr));
-    if (!fr.fallback)
-      return make_batch_indexed(ctx, rb, std::move(fr.rows), fr.n_out, std::move(fr.table), fr.slots,
-                                fr.n_keys, desc, out);
+  if (n_ub <= MZ_FUSED_MAX_ROWS) {
+    FusedJob job;
+    job.rb = rb;
+    job.a = d_in;
+    job.na = n;
+    job.cap = n_ub;
+    job.want_index = true;
+    FusedOut fo;
+    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
+    return batch_from_fused(ctx, rb, std::move(fo), n_ub, desc, out);
   }
   DevMem cons;
-  u64 n_out = 0;
-  MZ_TRY(mz_sort_consolidate(ctx, rb, d_in, n, &cons, &n_out));
-  return make_batch(ctx, rb, std::move(cons), n_out, desc, out);
+  u64 cap = 0;
+  Lazy4 len;
+  MZ_TRY(consolidate_dev(ctx, rb, d_in, n, n_ub, &cons, &cap, &len));
+  MZ_TRY(len.resolve());
+  return make_batch(ctx, rb, std::move(cons), len.v[0], desc, out);
 }
 static int32_t make_empty_batch(mzgpu_ctx* ctx, uint32_t rb, mzgpu_desc desc, mzgpu_batch** out) {
-  DevMem rows;
-  MZ_TRY(rows.alloc(ctx, 16));
-  return make_batch(ctx, rb, std::move(rows), 0, desc, out);
+  mzgpu_batch* b = new mzgpu_batch();
+  b->ctx = ctx;
+  b->rb = rb;
+  b->desc = desc;
+  b->st.set(ctx, 0, 1, 0, 0);
+  *out = b;
+  MZ_TRY(b->rows.alloc(ctx, 16));
+  b->rows_cap = 0;
+  MZ_TRY(b->table.alloc(ctx, 2 * sizeof(HashSlot)));
+  MZ_CUDA(ctx, cudaMemsetAsync(b->table.p, 0, 2 * sizeof(HashSlot), ctx->stream));
+  return MZGPU_OK;
 }
 
 extern "C" int32_t mzgpu_batch_build(mzgpu_ctx* ctx, uint32_t row_bytes, const void* rows, uint64_t n,
                                      int32_t mem, mzgpu_desc desc, mzgpu_batch** out) {
   MZ_CHECK_CTX(ctx);
   if (out == nullptr || (rows == nullptr && n) || (row_bytes != 32 && row_bytes != 80)) return MZGPU_E_INVALID;
-  DevMem in, cons;
+  if (n == 0) return make_empty_batch(ctx, row_bytes, desc, out);
+  DevMem in;
   const void* d_in = rows;
   if (mem == MZGPU_MEM_HOST && n) {
     MZ_TRY(in.alloc(ctx, n * row_bytes));
@@ -353,10 +607,13 @@ extern "C" int32_t mzgpu_batch_build(mzgpu_ctx* ctx, uint32_t row_bytes, const v
     d_in = in.p;
   }
   ctx->stats.rows_in += n;
-  return build_batch_from_unsorted(ctx, row_bytes, d_in, n, desc, out);
+  return build_batch_from_unsorted(ctx, row_bytes, d_in, dlen_imm(n), n, desc, out);
 }
-extern "C" uint64_t mzgpu_batch_len(const mzgpu_batch* b) { return b ? b->len : 0; }
-extern "C" uint64_t mzgpu_batch_keys(const mzgpu_batch* b) { return b ? b->n_keys : 0; }
+extern "C" uint64_t mzgpu_batch_len(const mzgpu_batch* b) { return b ? blen(const_cast<mzgpu_batch*>(b)) : 0; }
+extern "C" uint64_t mzgpu_batch_keys(const mzgpu_batch* b) {
+  if (b == nullptr || batch_resolve(const_cast<mzgpu_batch*>(b)) != MZGPU_OK) return 0;
+  return b->st.v[2];
+}
 extern "C" mzgpu_desc mzgpu_batch_desc(const mzgpu_batch* b) {
   mzgpu_desc d = {0, 0, 0};
   return b ? b->desc : d;
@@ -371,18 +628,37 @@ extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, 
                                       uint64_t* n_out) {
   if (b == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
-  if (n_out) *n_out = b->len;
-  if (cap < b->len) return MZGPU_E_CAPACITY;
-  MZ_TRY(copy_out(b->ctx, rows, b->rows.p, b->len * b->rb, mem));
+  MZ_TRY(batch_resolve(b));
+  const u64 len = b->st.v[0];
+  if (n_out) *n_out = len;
+  if (cap < len) return MZGPU_E_CAPACITY;
+  MZ_TRY(copy_out(b->ctx, rows, b->rows.p, len * b->rb, mem));
   return MZGPU_OK;
 }
+// Batch::Merger in one step: union, advance_by(since), consolidate, index.
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
+  mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
+  if (b1->len_ub + b2->len_ub <= MZ_FUSED_MAX_ROWS) {
+    FusedJob job;
+    job.rb = b1->rb;
+    job.a = b1->rows.p;
+    job.na = batch_dlen(b1);
+    job.b = b2->rows.p;
+    job.nb = batch_dlen(b2);
+    job.cap = b1->len_ub + b2->len_ub;
+    job.since = since;
+    job.want_index = true;
+    FusedOut fo;
+    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
+    return batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out);
+  }
+  MZ_TRY(batch_resolve(b1));
+  MZ_TRY(batch_resolve(b2));
   DevMem merged;
   u64 n_out = 0;
-  MZ_TRY(mz_merge_consolidate(ctx, b1->rb, b1->rows.p, b1->len, b2->rows.p, b2->len, since, &merged,
+  MZ_TRY(mz_merge_consolidate(ctx, b1->rb, b1->rows.p, b1->st.v[0], b2->rows.p, b2->st.v[0], since, &merged,
                               &n_out));
-  mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
   return make_batch(ctx, b1->rb, std::move(merged), n_out, d, out);
 }
 extern "C" int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t since,
@@ -398,68 +674,103 @@ extern "C" int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t 
 }
 
 // ================================================================== batcher
-struct Chain {
+// The reference's MergeBatcher sorts every pushed container at once and keeps
+// geometric chains of sorted chunks, merging them at seal time.  On the GPU the
+// cheaper schedule is to stash pushed containers as they are and do all the
+// work at seal: ONE sort + consolidate of everything buffered, split by the
+// seal frontier (ship: time < upper; keep: the rest) and index of the shipped
+// rows — a single fused kernel for update batches.  The sealed batches and the
+// batcher frontier are identical to the reference's; only the moment the
+// sorting happens differs.  The stash is compacted when it grows large.
+struct Seg {
   DevMem rows;
-  u64 len = 0;
-  // known only when the chain came out of the fused kernel (or merges of such)
-  bool time_known = false;
-  u64 max_time = 0;
-  // hash index built by the fused kernel (valid while the chain is unmerged)
-  bool has_index = false;
-  DevMem table;
-  u64 slots = 0, n_keys = 0;
+  Lazy4 len;  // word `word` = rows; for the keep segment of a seal: [0] rows, [1] min kept time
+  int word = 0;
+  u64 ub = 0;
+  bool is_keep = false;
 };
 struct mzgpu_batcher {
   mzgpu_ctx* ctx;
   uint32_t rb;
-  std::vector<Chain> chains;
+  std::vector<Seg> segs;
   u64 lower = 0;
+  bool frontier_known = true;  // else: derived from the keep segment segs[0]
   u64 frontier = MZGPU_FRONTIER_EMPTY;
 };
+#define MZ_STASH_COMPACT_ROWS (64ull << 20)
 
-static int32_t batcher_merge_top(mzgpu_batcher* b) {
-  Chain newer = std::move(b->chains.back());
-  b->chains.pop_back();
-  Chain older = std::move(b->chains.back());
-  b->chains.pop_back();
-  Chain m;
-  MZ_TRY(mz_merge_consolidate(b->ctx, b->rb, older.rows.p, older.len, newer.rows.p, newer.len, 0,
-                              &m.rows, &m.len));
-  m.time_known = older.time_known && newer.time_known;
-  m.max_time = std::max(older.max_time, newer.max_time);
-  b->chains.push_back(std::move(m));
-  return MZGPU_OK;
+static u64 batcher_ub(const mzgpu_batcher* b) {
+  u64 n = 0;
+  for (auto& s : b->segs) n += s.ub;
+  return n;
 }
-// MergeBatcher::insert_chain: keep chain lengths geometric
-static int32_t batcher_insert_chain(mzgpu_batcher* b, Chain&& c) {
-  if (c.len == 0) return MZGPU_OK;
-  b->chains.push_back(std::move(c));
-  while (b->chains.size() > 1 &&
-         b->chains[b->chains.size() - 1].len >= b->chains[b->chains.size() - 2].len / 2)
-    MZ_TRY(batcher_merge_top(b));
-  return MZGPU_OK;
-}
-static int32_t batcher_push_dev(mzgpu_batcher* b, const void* d_rows, u64 n) {
-  if (n == 0) return MZGPU_OK;
-  Chain c;
-  bool done = false;
-  if (n <= MZ_FUSED_MAX_ROWS) {
-    FusedResult fr;
-    MZ_TRY(mz_fused_sort_consolidate(b->ctx, b->rb, d_rows, n, true, &fr));
-    if (!fr.fallback) {
-      c.rows = std::move(fr.rows);
-      c.len = fr.n_out;
-      c.time_known = true;
-      c.max_time = fr.max_time;
-      c.has_index = true;
-      c.table = std::move(fr.table);
-      c.slots = fr.slots;
-      c.n_keys = fr.n_keys;
-      done = true;
-    }
+static int32_t batcher_resolve_frontier(mzgpu_batcher* b) {
+  if (b->frontier_known) return MZGPU_OK;
+  Seg& k = b->segs[0];
+  if (!k.len.known) {
+    MZ_TRY(k.len.resolve());
+    k.ub = k.len.v[0];
   }
-  if (!done) MZ_TRY(mz_sort_consolidate(b->ctx, b->rb, d_rows, n, &c.rows, &c.len));
-  return batcher_insert_chain(b, std::move(c));
+  b->frontier = k.len.v[0] ? k.len.v[1] : MZGPU_FRONTIER_EMPTY;
+  b->frontier_known = true;
+  return MZGPU_OK;
+}
+// all segments into one device array (device-side offsets where lengths are pending)
+static int32_t batcher_concat(mzgpu_batcher* b, DevMem* out, Lazy4* out_len, int* out_word, u64* out_ub) {
+  mzgpu_ctx* ctx = b->ctx;
+  const u64 total = batcher_ub(b);
+  MZ_TRY(out->alloc(ctx, std::max<u64>(total, 1) * b->rb));
+  mzgpu_buf tmp;  // borrow the append logic of a buffer
+  tmp.ctx = ctx;
+  tmp.rb = b->rb;
+  tmp.mem = std::move(*out);
+  tmp.cap = std::max<u64>(total, 1);
+  tmp.len.set(ctx, 0);
+  for (auto& s : b->segs) MZ_TRY(buf_append_dev(&tmp, s.rows.p, dlen_of(s.len, s.word), s.ub));
+  *out = std::move(tmp.mem);
+  *out_len = std::move(tmp.len);
+  *out_word = tmp.word;
+  *out_ub = tmp.ub;
+  return MZGPU_OK;
+}
+static int32_t batcher_push_seg(mzgpu_batcher* b, Seg&& s) {
+  if (s.ub == 0) return MZGPU_OK;
+  b->segs.push_back(std::move(s));
+  if (batcher_ub(b) > MZ_STASH_COMPACT_ROWS && b->segs.size() > 1) {
+    // compact the stash: consolidate everything buffered into one segment
+    MZ_TRY(batcher_resolve_frontier(b));
+    DevMem all, cons;
+    Lazy4 len, clen;
+    int word = 0;
+    u64 ub = 0, cap = 0;
+    MZ_TRY(batcher_concat(b, &all, &len, &word, &ub));
+    MZ_TRY(consolidate_dev(b->ctx, b->rb, all.p, dlen_of(len, word), ub, &cons, &cap, &clen));
+    MZ_TRY(clen.resolve());
+    b->segs.clear();
+    Seg c;
+    c.rows = std::move(cons);
+    c.ub = clen.v[0];
+    c.len.set(b->ctx, clen.v[0]);
+    b->segs.push_back(std::move(c));
+  }
+  return MZGPU_OK;
+}
+// push device rows the batcher may keep a pointer to only by copying
+static int32_t batcher_push_dev(mzgpu_batcher* b, const void* d_rows, DLen n, u64 n_ub) {
+  if (n_ub == 0) return MZGPU_OK;
+  Seg s;
+  MZ_TRY(s.rows.alloc(b->ctx, n_ub * b->rb));
+  if (n.p == nullptr) {
+    MZ_TRY(copy_in(b->ctx, s.rows.p, d_rows, n.imm * b->rb, MZGPU_MEM_DEVICE));
+    s.len.set(b->ctx, n.imm);
+    s.ub = n.imm;
+  } else {
+    MZ_TRY(s.len.make_pending(b->ctx));
+    MZ_TRY(append_dev(b->ctx, d_rows, n, n_ub, b->rb, s.rows.p, dlen_imm(0), n_ub, s.len.dptr()));
+    s.len.mark_written();
+    s.ub = n_ub;
+  }
+  return batcher_push_seg(b, std::move(s));
 }
 static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
   mzgpu_ctx* ctx = b->ctx;
@@ -468,33 +779,105 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
                (unsigned long long)b->lower);
     return MZGPU_E_FRONTIER;
   }
-  while (b->chains.size() > 1) MZ_TRY(batcher_merge_top(b));
-  Chain merged;
-  if (!b->chains.empty()) {
-    merged = std::move(b->chains.back());
-    b->chains.pop_back();
+  // segments known to be empty cost nothing
+  {
+    std::vector<Seg> live;
+    for (auto& s : b->segs) {
+      // a count that has already reached the host (some read-back happened since) costs nothing
+      if (s.len.try_resolve()) s.ub = s.len.v[s.word];
+      if (!(s.len.known && s.len.v[s.word] == 0)) live.push_back(std::move(s));
+    }
+    b->segs = std::move(live);
   }
-  Chain ship, keep;
-  b->frontier = MZGPU_FRONTIER_EMPTY;
-  if (merged.len == 0) {
-    MZ_TRY(ship.rows.alloc(ctx, 16));
-  } else if (upper == MZGPU_FRONTIER_EMPTY || (merged.time_known && merged.max_time < upper)) {
-    ship = std::move(merged);  // empty antichain, or every buffered time is < upper: everything ships
-  } else {
-    u64 min_keep = MZGPU_FRONTIER_EMPTY;
-    MZ_TRY(mz_extract(ctx, b->rb, merged.rows.p, merged.len, upper, &ship.rows, &ship.len, &keep.rows,
-                      &keep.len, &min_keep));
-    b->frontier = keep.len ? min_keep : MZGPU_FRONTIER_EMPTY;
-  }
-  if (keep.len) b->chains.push_back(std::move(keep));
   mzgpu_desc d = {b->lower, upper, 0};
-  if (ship.has_index)
-    MZ_TRY(make_batch_indexed(ctx, b->rb, std::move(ship.rows), ship.len, std::move(ship.table), ship.slots,
-                              ship.n_keys, d, batch_out));
-  else
-    MZ_TRY(make_batch(ctx, b->rb, std::move(ship.rows), ship.len, d, batch_out));
+  const u64 total = batcher_ub(b);
+  if (total == 0) {
+    b->segs.clear();
+    b->frontier = MZGPU_FRONTIER_EMPTY;
+    b->frontier_known = true;
+    MZ_TRY(make_empty_batch(ctx, b->rb, d, batch_out));
+  } else if (total <= MZ_FUSED_MAX_ROWS) {
+    DevMem all;
+    Lazy4 alen;
+    int aword = 0;
+    u64 aub = 0;
+    FusedJob job;
+    job.rb = b->rb;
+    if (b->segs.size() == 1) {
+      job.a = b->segs[0].rows.p;
+      job.na = dlen_of(b->segs[0].len, b->segs[0].word);
+    } else {
+      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
+      job.a = all.p;
+      job.na = dlen_of(alen, aword);
+    }
+    job.cap = total;
+    job.upper = upper;
+    job.want_index = true;
+    FusedOut fo;
+    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
+    b->segs.clear();  // stream ordered: the kernel above still reads them
+    if (upper != MZGPU_FRONTIER_EMPTY) {
+      Seg k;
+      k.rows = std::move(fo.keep);
+      k.len = std::move(fo.kst);
+      k.word = 0;
+      k.ub = total;
+      k.is_keep = true;
+      b->segs.push_back(std::move(k));
+      b->frontier_known = false;
+    } else {
+      b->frontier = MZGPU_FRONTIER_EMPTY;
+      b->frontier_known = true;
+    }
+    MZ_TRY(batch_from_fused(ctx, b->rb, std::move(fo), total, d, batch_out));
+  } else {
+    // bulk path: exact sizes, multi-kernel sort / extract
+    DevMem all, cons;
+    Lazy4 alen, clen;
+    int aword = 0;
+    u64 aub = 0, cap = 0;
+    const void* src = nullptr;
+    DLen sn;
+    if (b->segs.size() == 1) {
+      src = b->segs[0].rows.p;
+      sn = dlen_of(b->segs[0].len, b->segs[0].word);
+      aub = b->segs[0].ub;
+    } else {
+      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
+      src = all.p;
+      sn = dlen_of(alen, aword);
+    }
+    MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
+    MZ_TRY(clen.resolve());
+    b->segs.clear();
+    all.release();
+    const u64 n_cons = clen.v[0];
+    b->frontier = MZGPU_FRONTIER_EMPTY;
+    b->frontier_known = true;
+    if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0) {
+      MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
+    } else {
+      DevMem ship, keep;
+      u64 n_ship = 0, n_keep = 0, min_keep = MZGPU_FRONTIER_EMPTY;
+      MZ_TRY(mz_extract(ctx, b->rb, cons.p, n_cons, upper, &ship, &n_ship, &keep, &n_keep, &min_keep));
+      cons.release();
+      if (n_keep) {
+        Seg k;
+        k.rows = std::move(keep);
+        k.len.set(ctx, n_keep);
+        k.ub = n_keep;
+        b->segs.push_back(std::move(k));
+        b->frontier = min_keep;
+      }
+      MZ_TRY(make_batch(ctx, b->rb, std::move(ship), n_ship, d, batch_out));
+    }
+  }
   b->lower = upper;
-  if (new_lower) *new_lower = b->frontier;
+  if (new_lower) {
+    MZ_TRY(batcher_resolve_frontier(b));
+    *new_lower = b->frontier;
+  }
   return MZGPU_OK;
 }
 
@@ -513,14 +896,21 @@ extern "C" int32_t mzgpu_batcher_push(mzgpu_batcher* b, const void* rows, uint64
   MZ_CHECK_CTX(b->ctx);
   if (n == 0) return MZGPU_OK;
   b->ctx->stats.rows_in += n;
-  DevMem in;
-  const void* d_in = rows;
   if (mem == MZGPU_MEM_HOST) {
-    MZ_TRY(in.alloc(b->ctx, n * b->rb));
-    MZ_TRY(copy_in(b->ctx, in.p, rows, n * b->rb, mem));
-    d_in = in.p;
+    Seg s;
+    MZ_TRY(s.rows.alloc(b->ctx, n * b->rb));
+    MZ_TRY(copy_in(b->ctx, s.rows.p, rows, n * b->rb, mem));
+    s.len.set(b->ctx, n);
+    s.ub = n;
+    return batcher_push_seg(b, std::move(s));
   }
-  return batcher_push_dev(b, d_in, n);
+  return batcher_push_dev(b, rows, dlen_imm(n), n);
+}
+extern "C" int32_t mzgpu_batcher_push_buf(mzgpu_batcher* b, mzgpu_buf* rows) {
+  if (b == nullptr || rows == nullptr || rows->rb != b->rb) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(b->ctx);
+  b->ctx->stats.rows_in += rows->ub;
+  return batcher_push_dev(b, rows->mem.p, buf_dlen(rows), rows->ub);
 }
 extern "C" int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_batch** batch_out,
                                       uint64_t* new_lower) {
@@ -529,20 +919,33 @@ extern "C" int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_ba
   return batcher_seal(b, upper, batch_out, new_lower);
 }
 extern "C" uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b) {
-  return b ? b->frontier : MZGPU_FRONTIER_EMPTY;
+  if (b == nullptr) return MZGPU_FRONTIER_EMPTY;
+  if (batcher_resolve_frontier(const_cast<mzgpu_batcher*>(b)) != MZGPU_OK) return MZGPU_FRONTIER_EMPTY;
+  return b->frontier;
 }
-extern "C" uint64_t mzgpu_batcher_len(const mzgpu_batcher* b) {
+// Updates currently buffered (as pushed: the stash is consolidated at seal).
+extern "C" uint64_t mzgpu_batcher_len(const mzgpu_batcher* cb) {
+  mzgpu_batcher* b = const_cast<mzgpu_batcher*>(cb);
   u64 n = 0;
   if (b)
-    for (auto& c : b->chains) n += c.len;
+    for (auto& s : b->segs) {
+      if (!s.len.known) {
+        if (s.len.resolve() != MZGPU_OK) return 0;
+        s.ub = s.len.v[s.word];
+      }
+      n += s.len.v[s.word];
+    }
   return n;
 }
 
 // ==================================================================== spine
 // Host-side restatement of spine_fueled::Spine's scheduling (in-tree fork
 // src/persist-client/src/internal/trace.rs:1565-2262) over
-// device batches.  Fuel is bookkeeping on the host; a merge runs as one
-// merge-path kernel sequence when the schedule completes it.
+// device batches.  Fuel is bookkeeping on the host; a merge runs as one kernel
+// sequence when the schedule completes it.  Batches whose length is still in
+// flight on the device wait in `pending` (they are visible to readers, as any
+// inserted batch is) and are admitted to the layers — which need exact lengths —
+// when physical compaction allows it.
 struct mzgpu_spine {
   struct Layer {
     std::vector<mzgpu_batch*> batches;  // at most 2 (owned references)
@@ -571,7 +974,7 @@ struct mzgpu_spine {
   }
   u64 layer_len(const Layer& m) const {
     u64 n = 0;
-    for (auto* b : m.batches) n += b->len;
+    for (auto* b : m.batches) n += blen(b);
     return n;
   }
   bool reduced() const {
@@ -587,7 +990,7 @@ struct mzgpu_spine {
     u64 s = 0, work = 0;
     for (auto* b : m.batches) {
       s = std::max(s, b->desc.since);
-      work += b->len;
+      work += blen(b);
     }
     if (with_frontier) s = std::max(s, since);
     m.has_merge = true;
@@ -616,7 +1019,7 @@ struct mzgpu_spine {
     mzgpu_batch *b1 = m.batches[0], *b2 = m.batches[1];
     mzgpu_batch* out = nullptr;
     int32_t st;
-    if (b1->len == 0 && b2->len == 0) {
+    if (blen(b1) == 0 && blen(b2) == 0) {
       mzgpu_desc d = {b1->desc.lower, b2->desc.upper, m.merge_since};
       st = make_empty_batch(ctx, rb, d, &out);
     } else {
@@ -691,7 +1094,7 @@ struct mzgpu_spine {
     tidy_layers();
   }
   void insert_entry(mzgpu_batch* b) {
-    if (b->len == 0) {
+    if (blen(b) == 0) {
       for (size_t pos = 0; pos < merging.size(); ++pos) {
         if (merging[pos].batches.empty()) continue;
         if (merging[pos].batches.size() == 1 && layer_len(merging[pos]) == 0) {
@@ -706,7 +1109,7 @@ struct mzgpu_spine {
         break;
       }
     }
-    introduce_batch(b, level_of(b->len));
+    introduce_batch(b, level_of(blen(b)));
   }
   void consider_merges() {
     while (!pending.empty()) {
@@ -715,6 +1118,10 @@ struct mzgpu_spine {
                 (b->desc.upper != MZGPU_FRONTIER_EMPTY && b->desc.upper <= physical);
       if (!ok) break;
       pending.erase(pending.begin());
+      // admission needs the exact length; release the slack of a loosely sized batch
+      int32_t st = batch_resolve(b);
+      if (st == MZGPU_OK) st = batch_shrink(b);
+      if (st != MZGPU_OK && err == MZGPU_OK) err = st;
       insert_entry(b);
     }
   }
@@ -734,6 +1141,7 @@ struct mzgpu_spine {
 static int32_t spine_take_err(mzgpu_spine* s) {
   int32_t e = s->err;
   s->err = MZGPU_OK;
+  if (e == MZGPU_OK && s->ctx->sticky) e = MZGPU_E_CUDA;
   return e;
 }
 
@@ -843,8 +1251,8 @@ extern "C" int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint
     if (n >= cap_layers) return MZGPU_E_CAPACITY;
     const auto& m = s->merging[i];
     out4[4 * n + 0] = m.batches.size();
-    out4[4 * n + 1] = m.batches.size() > 0 ? m.batches[0]->len : 0;
-    out4[4 * n + 2] = m.batches.size() > 1 ? m.batches[1]->len : 0;
+    out4[4 * n + 1] = m.batches.size() > 0 ? blen(m.batches[0]) : 0;
+    out4[4 * n + 2] = m.batches.size() > 1 ? blen(m.batches[1]) : 0;
     out4[4 * n + 3] = m.has_merge ? m.remaining : 0;
     ++n;
   }
@@ -852,10 +1260,12 @@ extern "C" int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint
   return MZGPU_OK;
 }
 
+// Device-visible view of a set of batches.  Batches still in flight are passed
+// by their device header (length, mask), resolved ones by value.
 static int32_t trace_view(mzgpu_ctx* ctx, const std::vector<mzgpu_batch*>& batches, TraceView* tv) {
   tv->n_batches = 0;
   for (auto* b : batches) {
-    if (b->len == 0) continue;
+    if (b->st.known && b->st.v[0] == 0) continue;
     if (tv->n_batches >= MZ_MAX_TRACE_BATCHES) {
       MZ_SET_ERR(ctx, "trace has more than %d non-empty batches", MZ_MAX_TRACE_BATCHES);
       return MZGPU_E_UNSUPPORTED;
@@ -863,8 +1273,28 @@ static int32_t trace_view(mzgpu_ctx* ctx, const std::vector<mzgpu_batch*>& batch
     BatchView& v = tv->b[tv->n_batches++];
     v.rows = b->rows.as<u64>();
     v.table = b->table.as<HashSlot>();
-    v.n = b->len;
-    v.mask = b->slots - 1;
+    if (b->st.known) {
+      v.n = b->st.v[0];
+      v.mask = b->st.v[1];
+      v.hdr = nullptr;
+    } else {
+      v.n = 0;
+      v.mask = 0;
+      v.hdr = b->st.dptr();
+    }
+  }
+  return MZGPU_OK;
+}
+// Upper bound on the matches of one probe row: the sum over batches of the
+// longest key run.  *exact is false if some run length saturated.
+static int32_t trace_fanout(const std::vector<mzgpu_batch*>& batches, u64* fan, bool* exact) {
+  *fan = 0;
+  *exact = true;
+  for (auto* b : batches) {
+    MZ_TRY(batch_resolve(b));
+    if (b->st.v[0] == 0) continue;
+    if (b->st.v[3] >= 1024) *exact = false;
+    *fan += b->st.v[3];
   }
   return MZGPU_OK;
 }
@@ -881,7 +1311,8 @@ extern "C" int32_t mzgpu_spine_export(mzgpu_spine* s, mzgpu_buf* out) {
   for (auto* b : all) {
     DevMem m;
     u64 n = 0;
-    MZ_TRY(mz_merge_consolidate(s->ctx, s->rb, acc.p, acc_len, b->rows.p, b->len, s->since, &m, &n));
+    MZ_TRY(batch_resolve(b));
+    MZ_TRY(mz_merge_consolidate(s->ctx, s->rb, acc.p, acc_len, b->rows.p, b->st.v[0], s->since, &m, &n));
     acc = std::move(m);
     acc_len = n;
   }
@@ -943,7 +1374,7 @@ extern "C" int32_t mzgpu_join_new(mzgpu_ctx* ctx, mzgpu_spine* trace1, mzgpu_spi
   all.clear();
   trace2->all_batches(all);
   for (auto* b : all) {
-    if (b->len) join_enqueue(j, 1, b, 0);
+    if (blen(b)) join_enqueue(j, 1, b, 0);
     j->ack2 = b->desc.upper;
   }
   *out = j;
@@ -956,7 +1387,7 @@ extern "C" int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch
   MZ_CHECK_CTX(j->ctx);
   u64& ack = side == 0 ? j->ack1 : j->ack2;
   if (ack <= batch->desc.lower) {
-    if (batch->len) join_enqueue(j, side, batch, cap);
+    if (blen(batch)) join_enqueue(j, side, batch, cap);
     ack = batch->desc.upper;
   }
   // physical compaction of both traces follows the acknowledged frontiers
@@ -979,9 +1410,14 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     mzgpu_join::Work w = std::move(j->todo.front());
     j->todo.pop_front();
     TraceView tv;
-    int32_t st = trace_view(j->ctx, w.others, &tv);
+    int32_t st = MZGPU_OK;
+    for (auto* b : w.others)
+      if (st == MZGPU_OK) st = batch_resolve(b);
+    if (st == MZGPU_OK) st = batch_resolve(w.batch);
+    if (st == MZGPU_OK) st = trace_view(j->ctx, w.others, &tv);
     DevMem res, cons;
-    u64 n_res = 0, n_cons = 0;
+    u64 n_res = 0, ccap = 0;
+    Lazy4 clen;
     if (st == MZGPU_OK) {
       ProbeParams pp;
       memset(&pp, 0, sizeof(pp));
@@ -990,11 +1426,14 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
       pp.has_closure = j->has_closure ? 1 : 0;
       pp.swap_vals = w.side == 1 ? 1 : 0;
       pp.closure = j->closure;
-      st = mz_probe(j->ctx, w.batch->rows.as<u64>(), w.batch->len, tv, pp, &res, &n_res);
+      st = mz_probe(j->ctx, w.batch->rows.as<u64>(), w.batch->st.v[0], tv, pp, &res, &n_res);
     }
     // Work::process consolidates each work item's output buffer before sending
-    if (st == MZGPU_OK) st = mz_sort_consolidate(j->ctx, out_rb, res.p, n_res, &cons, &n_cons);
-    if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, n_cons);
+    if (st == MZGPU_OK && n_res)
+      st = consolidate_dev(j->ctx, out_rb, res.p, dlen_imm(n_res), n_res, &cons, &ccap, &clen);
+    if (st == MZGPU_OK && n_res) st = clen.resolve();
+    const u64 n_cons = n_res ? clen.v[0] : 0;
+    if (st == MZGPU_OK && n_cons) st = buf_append_dev(out, cons.p, dlen_imm(n_cons), n_cons);
     j->release_work(w);
     if (st != MZGPU_OK) return st;
     produced += n_cons;
@@ -1005,6 +1444,82 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
 }
 
 // ================================================================ half_join
+// Bounded probes run in one pass with no host round trip: the capacity
+// n_ub x (sum over batches of the longest key run) cannot be exceeded.  Beyond
+// MZ_BOUND_MAX_ROWS (heavy skew) the exact two-pass form (count, read back,
+// write) is used.
+#define MZ_BOUND_MAX_ROWS (48ull << 20)
+
+static int32_t half_join_dev(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, mzgpu_spine* trace,
+                             int32_t cmp_mode, const mzgpu_closure* closure, int32_t consolidate_output,
+                             mzgpu_buf* out) {
+  if (n_ub == 0) return MZGPU_OK;
+  std::vector<mzgpu_batch*> all;
+  trace->all_batches(all);
+  u64 fan = 0;
+  bool exact = true;
+  MZ_TRY(trace_fanout(all, &fan, &exact));
+  TraceView tv;
+  MZ_TRY(trace_view(ctx, all, &tv));
+  if (tv.n_batches == 0) return MZGPU_OK;
+  ProbeParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.mode = cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
+  pp.has_closure = 1;
+  if (closure) {
+    pp.closure = *closure;
+  } else {
+    // identity on (key, val2): the lookup value replaces the stream value
+    pp.closure.n_key_fields = 1;
+    pp.closure.key_fields[0] = mzgpu_field{MZGPU_SRC_KEY, 0, 64, 0};
+    pp.closure.n_val_fields = 1;
+    pp.closure.val_fields[0] = mzgpu_field{MZGPU_SRC_VAL2, 0, 64, 0};
+  }
+  const bool bounded = exact && fan > 0 && n_ub <= MZ_BOUND_MAX_ROWS / fan &&
+                       (n_ub + 255) / 256 <= MZ_LB_TILES;
+  if (bounded) {
+    const u64 bound = n_ub * fan;
+    if (!consolidate_output) {
+      MZ_TRY(buf_reserve(out, out->ub + bound, true));
+      Append a;
+      MZ_TRY(buf_begin_append(out, &a));
+      MZ_TRY(mz_probe_async(ctx, d_stream, n, n_ub, tv, pp, out->mem.as<u64>(), a.base, out->cap, a.out_len));
+      buf_end_append(out, a, bound);
+      return MZGPU_OK;
+    }
+    // probe into a scratch array, consolidate that, append
+    DevMem res, cons;
+    Lazy4 rlen, clen;
+    u64 ccap = 0;
+    MZ_TRY(res.alloc(ctx, bound * 32));
+    MZ_TRY(rlen.make_pending(ctx));
+    MZ_TRY(mz_probe_async(ctx, d_stream, n, n_ub, tv, pp, res.as<u64>(), dlen_imm(0), bound, rlen.dptr()));
+    rlen.mark_written();
+    MZ_TRY(consolidate_dev(ctx, 32, res.p, dlen_of(rlen, 0), bound, &cons, &ccap, &clen));
+    return buf_append_dev(out, cons.p, dlen_of(clen, 0), clen.known ? clen.v[0] : bound);
+  }
+  // exact two-pass form
+  u64 nn = n.imm;
+  if (n.p != nullptr) {
+    MZ_TRY(mz_resolve_counters(ctx));
+    nn = ctx->h_cnt[n.p - ctx->d_cnt];
+  }
+  if (nn == 0) return MZGPU_OK;
+  DevMem res;
+  u64 n_res = 0;
+  MZ_TRY(mz_probe(ctx, d_stream, nn, tv, pp, &res, &n_res));
+  if (consolidate_output && n_res) {
+    DevMem cons;
+    Lazy4 clen;
+    u64 ccap = 0;
+    MZ_TRY(consolidate_dev(ctx, 32, res.p, dlen_imm(n_res), n_res, &cons, &ccap, &clen));
+    MZ_TRY(buf_append_dev(out, cons.p, dlen_of(clen, 0), clen.known ? clen.v[0] : n_res));
+  } else if (n_res) {
+    MZ_TRY(buf_append_dev(out, res.p, dlen_imm(n_res), n_res));
+  }
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int32_t mem,
                                    mzgpu_spine* trace, int32_t cmp_mode, const mzgpu_closure* closure,
                                    int32_t consolidate_output, mzgpu_buf* out) {
@@ -1021,36 +1536,40 @@ extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint
     MZ_TRY(copy_in(ctx, in.p, stream, n * 32, mem));
     d_stream = in.as<u64>();
   }
-  std::vector<mzgpu_batch*> all;
-  trace->all_batches(all);
-  TraceView tv;
-  MZ_TRY(trace_view(ctx, all, &tv));
-  ProbeParams pp;
-  memset(&pp, 0, sizeof(pp));
-  pp.mode = cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
-  pp.has_closure = 1;
-  if (closure) {
-    pp.closure = *closure;
-  } else {
-    // identity on (key, val2): the lookup value replaces the stream value
-    pp.closure.n_key_fields = 1;
-    pp.closure.key_fields[0] = mzgpu_field{MZGPU_SRC_KEY, 0, 64, 0};
-    pp.closure.n_val_fields = 1;
-    pp.closure.val_fields[0] = mzgpu_field{MZGPU_SRC_VAL2, 0, 64, 0};
+  return half_join_dev(ctx, d_stream, dlen_imm(n), n, trace, cmp_mode, closure, consolidate_output, out);
+}
+extern "C" int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
+                                       const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out) {
+  MZ_CHECK_CTX(ctx);
+  if (stream == nullptr || trace == nullptr || out == nullptr || stream == out || stream->rb != 32 ||
+      trace->rb != 32 || out->rb != 32 || (cmp_mode != MZGPU_HALFJOIN_LE && cmp_mode != MZGPU_HALFJOIN_LT))
+    return MZGPU_E_INVALID;
+  ctx->stats.rows_in += stream->ub;
+  return half_join_dev(ctx, stream->mem.as<u64>(), buf_dlen(stream), stream->ub, trace, cmp_mode, closure,
+                       consolidate_output, out);
+}
+
+// rows -> closure(rows) appended to `out`; at most one output row per input row
+static int32_t map_rows_into(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, const mzgpu_closure* closure,
+                             u64 skip_time, mzgpu_buf* out) {
+  if (n_ub == 0) return MZGPU_OK;
+  if ((n_ub + 255) / 256 > MZ_LB_TILES) {
+    u64 nn = n.imm;
+    if (n.p != nullptr) {
+      MZ_TRY(mz_resolve_counters(ctx));
+      nn = ctx->h_cnt[n.p - ctx->d_cnt];
+    }
+    DevMem res;
+    u64 n_res = 0;
+    MZ_TRY(mz_map_rows_dev(ctx, d_rows, nn, closure, skip_time, &res, &n_res));
+    return buf_append_dev(out, res.p, dlen_imm(n_res), n_res);
   }
-  DevMem res;
-  u64 n_res = 0;
-  MZ_TRY(mz_probe(ctx, d_stream, n, tv, pp, &res, &n_res));
-  if (consolidate_output && n_res) {
-    DevMem cons;
-    u64 n_cons = 0;
-    MZ_TRY(mz_sort_consolidate(ctx, 32, res.p, n_res, &cons, &n_cons));
-    MZ_TRY(buf_append_dev(out, cons.p, n_cons));
-    ctx->stats.rows_out += n_cons;
-  } else {
-    MZ_TRY(buf_append_dev(out, res.p, n_res));
-    ctx->stats.rows_out += n_res;
-  }
+  MZ_TRY(buf_reserve(out, out->ub + n_ub, true));
+  Append a;
+  MZ_TRY(buf_begin_append(out, &a));
+  MZ_TRY(mz_map_rows_async(ctx, d_rows, n, n_ub, closure, skip_time, out->mem.as<u64>(), a.base, out->cap,
+                           a.out_len));
+  buf_end_append(out, a, n_ub);
   return MZGPU_OK;
 }
 
@@ -1059,11 +1578,8 @@ extern "C" int32_t mzgpu_update_stream(mzgpu_ctx* ctx, mzgpu_batch* batch,
                                        mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);
   if (batch == nullptr || out == nullptr || batch->rb != 32 || out->rb != 32) return MZGPU_E_INVALID;
-  if (batch->len == 0) return MZGPU_OK;
-  DevMem res;
-  u64 n_res = 0;
-  MZ_TRY(mz_map_rows_dev(ctx, batch->rows.as<u64>(), batch->len, initial_closure, skip_time, &res, &n_res));
-  return buf_append_dev(out, res.p, n_res);
+  return map_rows_into(ctx, batch->rows.as<u64>(), batch_dlen(batch), batch->len_ub, initial_closure, skip_time,
+                       out);
 }
 
 extern "C" int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_t n, int32_t mem,
@@ -1078,10 +1594,7 @@ extern "C" int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_
     MZ_TRY(copy_in(ctx, in.p, rows, n * 32, mem));
     d_rows = in.as<u64>();
   }
-  DevMem res;
-  u64 n_res = 0;
-  MZ_TRY(mz_map_rows_dev(ctx, d_rows, n, closure, MZGPU_FRONTIER_EMPTY, &res, &n_res));
-  return buf_append_dev(out, res.p, n_res);
+  return map_rows_into(ctx, d_rows, dlen_imm(n), n, closure, MZGPU_FRONTIER_EMPTY, out);
 }
 
 // =================================================================== reduce
@@ -1109,26 +1622,34 @@ extern "C" int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_redu
   return MZGPU_OK;
 }
 extern "C" void mzgpu_reduce_free(mzgpu_reduce* r) { delete r; }
-extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) { return r ? r->input : nullptr; }
+extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) {
+  if (r == nullptr) return nullptr;
+  // inspection sees the arrangement as the reference would: every sealed batch admitted
+  mzgpu_spine_set_physical_compaction(r->input, r->input->upper);
+  return r->input;
+}
 
-extern "C" int32_t mzgpu_reduce_accumulable(mzgpu_reduce* r, const mzgpu_r32* rows, uint64_t n,
-                                            int32_t mem, uint64_t upper, mzgpu_buf* out) {
-  if (r == nullptr || out == nullptr || (rows == nullptr && n) || out->rb != 64) return MZGPU_E_INVALID;
+static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, u64 upper, mzgpu_buf* out) {
   mzgpu_ctx* ctx = r->ctx;
-  MZ_CHECK_CTX(ctx);
-  ctx->stats.rows_in += n;
-  // explode_one: values move into the diff
-  if (n) {
-    DevMem in, exploded;
-    const u64* d_rows = (const u64*)rows;
-    if (mem == MZGPU_MEM_HOST) {
-      MZ_TRY(in.alloc(ctx, n * 32));
-      MZ_TRY(copy_in(ctx, in.p, rows, n * 32, mem));
-      d_rows = in.as<u64>();
+  // batches sealed by earlier activations are merge-eligible now; their lengths
+  // have reached the host with whatever the caller read since (no extra wait)
+  MZ_TRY(mzgpu_spine_set_physical_compaction(r->input, r->input->upper));
+  // explode_one: values move into the diff; the exploded rows become a stash segment
+  if (n_ub) {
+    Seg s;
+    MZ_TRY(s.rows.alloc(ctx, n_ub * 80));
+    MZ_TRY(mz_explode(ctx, d_rows, n, n_ub, r->agg_kind, s.rows.as<u64>()));
+    if (n.p == nullptr) {
+      s.len.set(ctx, n.imm);
+      s.ub = n.imm;
+    } else {
+      // same count as the input rows: share nothing, copy the word on the device
+      MZ_TRY(s.len.make_pending(ctx));
+      MZ_CUDA(ctx, cudaMemcpyAsync(s.len.dptr(), n.p, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      s.len.mark_written();
+      s.ub = n_ub;
     }
-    MZ_TRY(exploded.alloc(ctx, n * 80));
-    MZ_TRY(mz_explode(ctx, d_rows, n, r->agg_kind, exploded.as<u64>()));
-    MZ_TRY(batcher_push_dev(r->batcher, exploded.p, n));
+    MZ_TRY(batcher_push_seg(r->batcher, std::move(s)));
   }
   // arrange: seal the accumulable arrangement's batch at the new frontier
   mzgpu_batch* batch = nullptr;
@@ -1138,17 +1659,61 @@ extern "C" int32_t mzgpu_reduce_accumulable(mzgpu_reduce* r, const mzgpu_r32* ro
   r->input->all_batches(prior);
   TraceView tv;
   int32_t st = trace_view(ctx, prior, &tv);
-  DevMem corr, cons;
-  u64 n_corr = 0, n_cons = 0;
-  if (st == MZGPU_OK)
-    st = mz_reduce_corrections(ctx, batch->rows.as<u64>(), batch->len, tv, r->agg_kind, &corr, &n_corr);
-  if (st == MZGPU_OK && n_corr) st = mz_sort_consolidate(ctx, 64, corr.p, n_corr, &cons, &n_cons);
-  if (st == MZGPU_OK && n_cons) st = buf_append_dev(out, cons.p, n_cons);
+  const u64 b_ub = batch->len_ub;
+  if (st == MZGPU_OK && b_ub > 0) {
+    if ((b_ub + 255) / 256 <= MZ_LB_TILES && 2 * b_ub <= MZ_BOUND_MAX_ROWS) {
+      DevMem corr, cons;
+      Lazy4 clen, flen;
+      u64 ccap = 0;
+      st = corr.alloc(ctx, 2 * b_ub * 64);
+      if (st == MZGPU_OK) st = clen.make_pending(ctx);
+      if (st == MZGPU_OK) {
+        st = mz_reduce_corrections_async(ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind,
+                                         corr.as<u64>(), 2 * b_ub, clen.dptr());
+        clen.mark_written();
+      }
+      if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), 2 * b_ub, &cons, &ccap, &flen);
+      if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : 2 * b_ub);
+    } else {
+      DevMem corr, cons;
+      u64 n_corr = 0, ccap = 0;
+      Lazy4 flen;
+      st = batch_resolve(batch);
+      if (st == MZGPU_OK)
+        st = mz_reduce_corrections(ctx, batch->rows.as<u64>(), batch->st.v[0], tv, r->agg_kind, &corr, &n_corr);
+      if (st == MZGPU_OK && n_corr)
+        st = consolidate_dev(ctx, 64, corr.p, dlen_imm(n_corr), n_corr, &cons, &ccap, &flen);
+      if (st == MZGPU_OK && n_corr)
+        st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : n_corr);
+    }
+  }
   if (st == MZGPU_OK && batch->desc.lower != batch->desc.upper) st = mzgpu_spine_insert(r->input, batch);
-  if (st == MZGPU_OK) st = mzgpu_spine_set_physical_compaction(r->input, r->input->upper);
   mzgpu_batch_release(batch);
-  ctx->stats.rows_out += n_cons;
   return st;
+}
+
+extern "C" int32_t mzgpu_reduce_accumulable(mzgpu_reduce* r, const mzgpu_r32* rows, uint64_t n,
+                                            int32_t mem, uint64_t upper, mzgpu_buf* out) {
+  if (r == nullptr || out == nullptr || (rows == nullptr && n) || out->rb != 64) return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = r->ctx;
+  MZ_CHECK_CTX(ctx);
+  ctx->stats.rows_in += n;
+  DevMem in;
+  const u64* d_rows = (const u64*)rows;
+  if (mem == MZGPU_MEM_HOST && n) {
+    MZ_TRY(in.alloc(ctx, n * 32));
+    MZ_TRY(copy_in(ctx, in.p, rows, n * 32, mem));
+    d_rows = in.as<u64>();
+  }
+  return reduce_dev(r, d_rows, dlen_imm(n), n, upper, out);
+}
+extern "C" int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows, uint64_t upper,
+                                                mzgpu_buf* out) {
+  if (r == nullptr || rows == nullptr || out == nullptr || rows->rb != 32 || out->rb != 64)
+    return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(r->ctx);
+  r->ctx->stats.rows_in += rows->ub;
+  return reduce_dev(r, rows->mem.as<u64>(), buf_dlen(rows), rows->ub, upper, out);
 }
 
 // ================================================================= exchange
@@ -1203,9 +1768,11 @@ extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out)
   if (in == nullptr || out == nullptr || in->rb != out->rb || in == out) return MZGPU_E_INVALID;
   const u32 P = (u32)ctx->peers;
   if (P == 1) {
-    out->len = 0;
-    return buf_append_dev(out, in->mem.p, in->len);
+    buf_set_len(out, 0);
+    return buf_append_dev(out, in->mem.p, buf_dlen(in), in->ub);
   }
+  MZ_TRY(buf_resolve(in));  // send counts go through the host (NCCL sizes are host arguments)
+  const u64 in_len = in->ub;
   if (ctx->nccl_comm == nullptr) {
     MZ_SET_ERR(ctx, "exchange: mzgpu_comm_init has not been called");
     return MZGPU_E_NCCL;
@@ -1221,9 +1788,9 @@ extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out)
   const int NCCL_INT8 = 0, NCCL_UINT64 = 5;
   // 1. bucket rows by destination
   DevMem parts;
-  MZ_TRY(parts.alloc(ctx, in->len * in->rb));
+  MZ_TRY(parts.alloc(ctx, in_len * in->rb));
   u64 send_counts[64], recv_counts[64];
-  MZ_TRY(mz_partition(ctx, in->rb, in->mem.p, in->len, P, parts.p, send_counts));
+  MZ_TRY(mz_partition(ctx, in->rb, in->mem.p, in_len, P, parts.p, send_counts));
   // 2. counts all-to-all (P x u64)
   DevMem d_send, d_recv;
   MZ_TRY(d_send.alloc(ctx, P * 8));
@@ -1245,11 +1812,11 @@ extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out)
   }
   NCCL_TRY(gend());
   MZ_CUDA(ctx, cudaMemcpyAsync(recv_counts, d_recv.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   // 3. payload all-to-all
   u64 total = 0;
   for (u32 p = 0; p < P; ++p) total += recv_counts[p];
-  out->len = 0;
+  buf_set_len(out, 0);
   MZ_TRY(buf_reserve(out, total, false));
   NCCL_TRY(gstart());
   u64 soff = 0, roff = 0;
@@ -1264,7 +1831,7 @@ extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out)
     roff += recv_counts[p];
   }
   NCCL_TRY(gend());
-  out->len = total;
+  buf_set_len(out, total);
   // `parts` is freed stream-ordered after the sends
   return MZGPU_OK;
 #undef NCCL_TRY

@@ -19,6 +19,19 @@ __global__ void __launch_bounds__(512) k_count_keys(const u64* __restrict__ rows
   if (i < n) head = (i == 0) || rows[i * NW] != rows[(i - 1) * NW];
   u32 m = __ballot_sync(0xffffffffu, head);
   if (lane_id() == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+  // longest run of one key (saturating at 1024): bounds the fan-out of a probe
+  u32 run = 0;
+  if (head) {
+    const u64 key = rows[i * NW];
+    run = 1;
+    while (run < 1024 && i + run < n && rows[(i + run) * NW] == key) ++run;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    u32 o = __shfl_xor_sync(0xffffffffu, run, off);
+    run = o > run ? o : run;
+  }
+  if (lane_id() == 0 && run) atomicMax(count + 1, (unsigned long long)run);
 }
 
 template <int NW>
@@ -43,11 +56,12 @@ __global__ void __launch_bounds__(512) k_build_index(const u64* __restrict__ row
 
 }  // namespace
 
-int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys) {
+int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys, u64* max_run) {
   *n_keys = 0;
+  *max_run = 0;
   if (n == 0) return MZGPU_OK;
   u64* d_count = ctx->d_scratch + 24;
-  MZ_CUDA(ctx, cudaMemsetAsync(d_count, 0, 8, ctx->stream));
+  MZ_CUDA(ctx, cudaMemsetAsync(d_count, 0, 16, ctx->stream));
   unsigned grid = (unsigned)((n + 511) / 512);
   const u64* r = (const u64*)d_rows;
   switch (row_bytes) {
@@ -56,10 +70,11 @@ int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, 
     case 64: MZ_LAUNCH(ctx, k_count_keys<8>, grid, 512, 0, r, n, (unsigned long long*)d_count); break;
     default: MZ_SET_ERR(ctx, "index: unsupported row width %d", row_bytes); return MZGPU_E_UNSUPPORTED;
   }
-  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 24, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->stats.d2h_bytes += 8;
+  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 24, d_count, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_SYNC(ctx);
+  ctx->stats.d2h_bytes += 16;
   *n_keys = ctx->h_scratch[24];
+  *max_run = ctx->h_scratch[25];
   return MZGPU_OK;
 }
 

@@ -227,7 +227,7 @@ int32_t extract_t(mzgpu_ctx* ctx, const u64* rows, u64 n, u64 upper, DevMem* shi
   MZ_LAUNCH(ctx, (k_extract_scatter<RB>), (unsigned)n_tiles, 512, 0, rows, n, upper, tiles.as<u32>(),
             ship->as<u64>(), keep->as<u64>());
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 20, d_total, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 16;
   *n_ship = ctx->h_scratch[20];
   *n_keep = n - *n_ship;

@@ -28,12 +28,14 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
   const u64 h0 = mix64(key);
   for (u32 b = 0; b < tv.n_batches; ++b) {
     const BatchView& bv = tv.b[b];
-    u64 h = h0 & bv.mask;
+    const u64 mask = bv_mask(bv);
+    u64 h = h0 & mask;
     while (true) {
       const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
       if (slot.y == 0) break;
       if (slot.x == key) {
-        for (u64 j = slot.y - 1; j < bv.n; ++j) {
+        const u64 bn = bv_n(bv);
+        for (u64 j = slot.y - 1; j < bn; ++j) {
           const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4);
           if (kv.x != key) break;
           const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4 + 2);
@@ -42,8 +44,138 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
         }
         break;
       }
-      h = (h + 1) & bv.mask;
+      h = (h + 1) & mask;
     }
+  }
+}
+
+// ---- single-pass forms: sizes come from device memory, results are appended at
+// a device-resident offset, the new length is left in device memory.  Tiles are
+// chained with a decoupled look-back, so the output order is exactly the
+// two-pass order (stream order x batch order x row order) and nothing returns
+// to the host.
+template <int OUT_NW>
+__global__ void __launch_bounds__(PT) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+                                                 const __grid_constant__ TraceView tv,
+                                                 const __grid_constant__ ProbeParams pp, const LookBack lb,
+                                                 u64* __restrict__ out, const DLen out_base, u64 out_cap,
+                                                 u64* __restrict__ out_len, u64* __restrict__ status) {
+  __shared__ u32 sm[34];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_b;
+  const u64 n = dlen_get(dn);
+  const u64 n_tiles = (n + PT - 1) / PT;
+  const u64 base0 = dlen_get(out_base);
+  while (true) {
+    const u32 tile = lb_next_tile(lb, &s_tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *out_len = base0;
+      break;
+    }
+    const u64 i = (u64)tile * PT + threadIdx.x;
+    u64 key = 0, v1 = 0, t1 = 0;
+    i64 d1 = 0;
+    u32 cnt = 0;
+    if (i < n) {
+      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
+      const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
+      key = kv.x;
+      v1 = kv.y;
+      t1 = td.x;
+      d1 = (i64)td.y;
+      for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+        if (pp.has_closure) {
+          u64 k, v;
+          if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
+        } else {
+          cnt++;
+        }
+      });
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan(cnt, sm, &total);
+    const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
+    if (i < n && cnt > 0) {
+      u64 pos = base0 + excl + ex;
+      if (pos + cnt > out_cap) {
+        atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+      } else {
+        for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+          u64 t = t1;
+          if (pp.mode == MZ_PROBE_JOIN) {
+            t = t1 > t2 ? t1 : t2;
+            t = t > pp.meet ? t : pp.meet;
+          }
+          u64 d = (u64)d1 * (u64)d2;
+          u64 a = pp.swap_vals ? v2 : v1, b = pp.swap_vals ? v1 : v2;
+          if (OUT_NW == 4) {
+            u64 k, v;
+            if (closure_eval(pp.closure, key, a, b, &k, &v)) {
+              u64 r[4] = {k, v, t, d};
+              store_row<4>(out, pos, r);
+              pos++;
+            }
+          } else {
+            u64* o = out + pos * 5;
+            o[0] = key;
+            o[1] = a;
+            o[2] = b;
+            o[3] = t;
+            o[4] = d;
+            pos++;
+          }
+        });
+      }
+    }
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;
+  }
+}
+
+__global__ void __launch_bounds__(PT) k_map_rows_lb(const u64* __restrict__ rows, const DLen dn,
+                                                    const __grid_constant__ mzgpu_closure cl, int has_closure,
+                                                    u64 skip_time, const LookBack lb, u64* __restrict__ out,
+                                                    const DLen out_base, u64 out_cap, u64* __restrict__ out_len,
+                                                    u64* __restrict__ status) {
+  __shared__ u32 sm[34];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_b;
+  const u64 n = dlen_get(dn);
+  const u64 n_tiles = (n + PT - 1) / PT;
+  const u64 base0 = dlen_get(out_base);
+  while (true) {
+    const u32 tile = lb_next_tile(lb, &s_tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *out_len = base0;
+      break;
+    }
+    const u64 i = (u64)tile * PT + threadIdx.x;
+    u32 keep = 0;
+    u64 r[4] = {0, 0, 0, 0};
+    if (i < n) {
+      load_row<4>(rows, i, r);
+      keep = 1;
+      if (skip_time != MZGPU_FRONTIER_EMPTY && r[2] == skip_time) keep = 0;
+      if (keep && has_closure) {
+        u64 k, v;
+        if (closure_eval(cl, r[0], r[1], 0, &k, &v)) {
+          r[0] = k;
+          r[1] = v;
+        } else {
+          keep = 0;
+        }
+      }
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan(keep, sm, &total);
+    const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
+    if (keep) {
+      const u64 pos = base0 + excl + ex;
+      if (pos >= out_cap)
+        atomicMax((unsigned long long*)status, (unsigned long long)(pos + 1));
+      else
+        store_row<4>(out, pos, r);
+    }
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;
   }
 }
 
@@ -165,7 +297,7 @@ int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& tr
   }
   MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 28, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 8;
   const u64 total = ctx->h_scratch[28];
   MZ_TRY(out->alloc(ctx, total * out_rb));
@@ -202,8 +334,45 @@ int32_t mz_map_rows_dev(mzgpu_ctx* ctx, const u64* d_rows, u64 n, const mzgpu_cl
   MZ_LAUNCH(ctx, (k_map_rows<true>), (unsigned)n_tiles, PT, 0, d_rows, n, cl, closure ? 1 : 0, skip_time,
             (u32*)nullptr, tiles.as<u32>(), out->as<u64>());
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 29, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 8;
   *n_out = ctx->h_scratch[29];
+  return MZGPU_OK;
+}
+
+// ---------------------------------------------------------- single-pass forms
+static unsigned lb_grid(mzgpu_ctx* ctx, u64 n_ub) {
+  u64 tiles = (n_ub + PT - 1) / PT;
+  u64 maxg = (u64)ctx->num_sms * 8;
+  if (tiles > maxg) tiles = maxg;
+  return (unsigned)(tiles ? tiles : 1);
+}
+
+int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, const TraceView& trace,
+                       const ProbeParams& pp, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len) {
+  LookBack lb;
+  MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
+  const int out_rb = pp.has_closure ? 32 : 40;
+  MZ_BYTES(ctx, n_ub * (32 + 16 * trace.n_batches + 32 + out_rb));
+  if (pp.has_closure) {
+    MZ_LAUNCH(ctx, (k_probe_lb<4>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
+              out_cap, d_out_len, ctx->d_status);
+  } else {
+    MZ_LAUNCH(ctx, (k_probe_lb<5>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
+              out_cap, d_out_len, ctx->d_status);
+  }
+  return MZGPU_OK;
+}
+
+int32_t mz_map_rows_async(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, const mzgpu_closure* closure,
+                          u64 skip_time, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len) {
+  LookBack lb;
+  MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
+  mzgpu_closure cl;
+  memset(&cl, 0, sizeof(cl));
+  if (closure) cl = *closure;
+  MZ_BYTES(ctx, n_ub * 64);
+  MZ_LAUNCH(ctx, k_map_rows_lb, lb_grid(ctx, n_ub), PT, 0, d_rows, n, cl, closure ? 1 : 0, skip_time, lb, d_out,
+            out_base, out_cap, d_out_len, ctx->d_status);
   return MZGPU_OK;
 }

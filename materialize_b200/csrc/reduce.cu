@@ -97,10 +97,10 @@ __device__ __forceinline__ void mul_i128_i64(u64 lo, u64 hi, i64 d, u64* rlo, u6
   *rhi = __umul64hi(lo, dl) + hi * dl + lo * dh;
 }
 
-__global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, u64 n, int agg_kind,
+__global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, const DLen dn, int agg_kind,
                                                 u64* __restrict__ out) {
-  u64 i = (u64)blockIdx.x * RT + threadIdx.x;
-  if (i >= n) return;
+  const u64 n = dlen_get(dn);
+  for (u64 i = (u64)blockIdx.x * RT + threadIdx.x; i < n; i += (u64)gridDim.x * RT) {
   u64 r[4];
   load_row<4>(rows, i, r);
   const i64 diff = (i64)r[3];
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, u6
   o[8] = nan;
   o[9] = 0;
   store_row<10>(out, i, o);
+  }
 }
 
 // finalize_accum + error-check flag for one accumulated diff S (words 2..8 of a RACC row)
@@ -174,12 +175,14 @@ __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) 
   const u64 h0 = mix64(key);
   for (u32 b = 0; b < tv.n_batches; ++b) {
     const BatchView& bv = tv.b[b];
-    u64 h = h0 & bv.mask;
+    const u64 mask = bv_mask(bv);
+    u64 h = h0 & mask;
     while (true) {
       const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
       if (slot.y == 0) break;
       if (slot.x == key) {
-        for (u64 j = slot.y - 1; j < bv.n; ++j) {
+        const u64 bn = bv_n(bv);
+        for (u64 j = slot.y - 1; j < bn; ++j) {
           const u64* row = bv.rows + j * 10;
           if (row[0] != key) break;
           u64 d[8];
@@ -189,9 +192,57 @@ __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) 
         }
         break;
       }
-      h = (h + 1) & bv.mask;
+      h = (h + 1) & mask;
     }
   }
+}
+
+// Corrections of one changed key: rows [i, ...) of the new batch with this key,
+// given the key's prior accumulation S0.  Counts (and optionally writes at
+// out[pos...]) the (-old, +new) output rows.
+__device__ __forceinline__ u32 walk_key(const u64* __restrict__ rows, u64 n, u64 i, u64 key, const u64* S0,
+                                        int agg_kind, bool do_write, u64* __restrict__ out, u64 pos) {
+  u64 S[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) S[w] = S0[w];
+  bool had = !diff_is_zero<8>(S);
+  u64 oldv[4] = {0, 0, 0, 0};
+  if (had) finalize(S, agg_kind, oldv);
+  u32 c = 0;
+  for (u64 j = i; j < n; ++j) {
+    const u64* row = rows + j * 10;
+    if (row[0] != key) break;
+    u64 d[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
+    diff_add<8>(S, d);
+    const u64 t = row[1];
+    const bool has = !diff_is_zero<8>(S);
+    u64 newv[4] = {0, 0, 0, 0};
+    if (has) finalize(S, agg_kind, newv);
+    const bool same = had && has && oldv[0] == newv[0] && oldv[1] == newv[1] && oldv[2] == newv[2] &&
+                      oldv[3] == newv[3];
+    if (!same) {
+      if (had) {
+        if (do_write) {
+          u64 r[8] = {key, oldv[0], oldv[1], oldv[2], oldv[3], t, ~0ull, 0};
+          store_row<8>(out, pos + c, r);
+        }
+        ++c;
+      }
+      if (has) {
+        if (do_write) {
+          u64 r[8] = {key, newv[0], newv[1], newv[2], newv[3], t, 1, 0};
+          store_row<8>(out, pos + c, r);
+        }
+        ++c;
+      }
+    }
+    had = has;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) oldv[w] = newv[w];
+  }
+  return c;
 }
 
 template <bool WRITE>
@@ -209,66 +260,65 @@ __global__ void __launch_bounds__(RT) k_corrections(const u64* __restrict__ rows
   if (head) {
     key = rows[i * 10];
     prior_sum(prior, key, S0);
+    cnt = walk_key(rows, n, i, key, S0, agg_kind, false, nullptr, 0);
   }
-  // pass over the key's new times: count (and optionally write) corrections
-  auto walk = [&](bool do_write, u64 pos) -> u32 {
-    u64 S[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) S[w] = S0[w];
-    bool had = !diff_is_zero<8>(S);
-    u64 oldv[4] = {0, 0, 0, 0};
-    if (had) finalize(S, agg_kind, oldv);
-    u32 c = 0;
-    for (u64 j = i; j < n; ++j) {
-      const u64* row = rows + j * 10;
-      if (row[0] != key) break;
-      u64 d[8];
-#pragma unroll
-      for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
-      diff_add<8>(S, d);
-      const u64 t = row[1];
-      const bool has = !diff_is_zero<8>(S);
-      u64 newv[4] = {0, 0, 0, 0};
-      if (has) finalize(S, agg_kind, newv);
-      const bool same = had && has && oldv[0] == newv[0] && oldv[1] == newv[1] && oldv[2] == newv[2] &&
-                        oldv[3] == newv[3];
-      if (!same) {
-        if (had) {
-          if (do_write) {
-            u64 r[8] = {key, oldv[0], oldv[1], oldv[2], oldv[3], t, ~0ull, 0};
-            store_row<8>(out, pos + c, r);
-          }
-          ++c;
-        }
-        if (has) {
-          if (do_write) {
-            u64 r[8] = {key, newv[0], newv[1], newv[2], newv[3], t, 1, 0};
-            store_row<8>(out, pos + c, r);
-          }
-          ++c;
-        }
-      }
-      had = has;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) oldv[w] = newv[w];
-    }
-    return c;
-  };
-  if (head) cnt = walk(false, 0);
   u32 total;
   u32 ex = block_exclusive_scan(cnt, sm, &total);
   if (!WRITE) {
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
   } else {
-    if (head && cnt > 0) walk(true, (u64)tile_base[blockIdx.x] + ex);
+    if (head && cnt > 0) walk_key(rows, n, i, key, S0, agg_kind, true, out, (u64)tile_base[blockIdx.x] + ex);
+  }
+}
+
+// single-pass form (sizes on the device, chained tiles): see probe.cu
+__global__ void __launch_bounds__(RT) k_corrections_lb(const u64* __restrict__ rows, const DLen dn,
+                                                       const __grid_constant__ TraceView prior, int agg_kind,
+                                                       const LookBack lb, u64* __restrict__ out, u64 out_cap,
+                                                       u64* __restrict__ out_len, u64* __restrict__ status) {
+  __shared__ u32 sm[34];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_b;
+  const u64 n = dlen_get(dn);
+  const u64 n_tiles = (n + RT - 1) / RT;
+  while (true) {
+    const u32 tile = lb_next_tile(lb, &s_tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *out_len = 0;
+      break;
+    }
+    const u64 i = (u64)tile * RT + threadIdx.x;
+    u32 cnt = 0;
+    const bool head = i < n && (i == 0 || rows[(i - 1) * 10] != rows[i * 10]);
+    u64 key = 0;
+    u64 S0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (head) {
+      key = rows[i * 10];
+      prior_sum(prior, key, S0);
+      cnt = walk_key(rows, n, i, key, S0, agg_kind, false, nullptr, 0);
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan(cnt, sm, &total);
+    const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
+    if (head && cnt > 0) {
+      const u64 pos = excl + ex;
+      if (pos + cnt > out_cap)
+        atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+      else
+        walk_key(rows, n, i, key, S0, agg_kind, true, out, pos);
+    }
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = excl + total;
   }
 }
 
 }  // namespace
 
-int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, u64 n, int agg_kind, u64* d_racc) {
-  if (n == 0) return MZGPU_OK;
-  MZ_LAUNCH(ctx, k_explode, (unsigned)((n + RT - 1) / RT), RT, 0, d_r32, n, agg_kind, d_racc);
+int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_kind, u64* d_racc) {
+  if (n_ub == 0) return MZGPU_OK;
+  u64 grid = (n_ub + RT - 1) / RT;
+  if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
+  MZ_BYTES(ctx, n_ub * 112);
+  MZ_LAUNCH(ctx, k_explode, (unsigned)grid, RT, 0, d_r32, n, agg_kind, d_racc);
   return MZGPU_OK;
 }
 
@@ -284,7 +334,7 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
             tiles.as<u32>(), (const u32*)nullptr, (u64*)nullptr);
   MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 30, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 8;
   const u64 total = ctx->h_scratch[30];
   MZ_TRY(out->alloc(ctx, total * 64));
@@ -292,5 +342,21 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
   if (total == 0) return MZGPU_OK;
   MZ_LAUNCH(ctx, (k_corrections<true>), (unsigned)n_tiles, RT, 0, d_batch_rows, n, prior, agg_kind,
             (u32*)nullptr, tiles.as<u32>(), out->as<u64>());
+  return MZGPU_OK;
+}
+
+// Single-pass form: batch length read on the device; at most two output rows per
+// new (key, time) row, so capacity 2 * n_ub always suffices.
+int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
+                                    const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
+                                    u64* d_out_len) {
+  LookBack lb;
+  MZ_TRY(mz_lookback_begin(ctx, (n_ub + RT - 1) / RT, &lb));
+  u64 grid = (n_ub + RT - 1) / RT;
+  if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
+  if (grid == 0) grid = 1;
+  MZ_BYTES(ctx, n_ub * (80 + 16 + 80 + 128));
+  MZ_LAUNCH(ctx, k_corrections_lb, (unsigned)grid, RT, 0, d_batch_rows, n, prior, agg_kind, lb, d_out, out_cap,
+            d_out_len, ctx->d_status);
   return MZGPU_OK;
 }

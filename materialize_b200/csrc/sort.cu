@@ -215,7 +215,7 @@ int32_t sort_perm_t(mzgpu_ctx* ctx, const u64* d_rows, u64 n, DevMem* perm_out) 
   }
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 2 * NK * 8, cudaMemcpyDeviceToHost,
                                ctx->stream));
-  MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 2 * NK * 8;
   // 2. plan chunks of <= 64 composite bits, least significant word first
   int wbits[NK];

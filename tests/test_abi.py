@@ -33,7 +33,7 @@ def test_row_layouts_match_header():
     import ctypes as C
 
     assert C.sizeof(_ffi.Closure) == 144
-    assert C.sizeof(_ffi.Desc) == 24 and C.sizeof(_ffi.Stats) == 56
+    assert C.sizeof(_ffi.Desc) == 24 and C.sizeof(_ffi.Stats) == 64
 
 
 def test_no_cpu_fallback_without_device():
