@@ -231,6 +231,10 @@ int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out);
  * returns MZGPU_E_CAPACITY if `cap` is too small.  Reading the report resets it. */
 int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on);
 int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap);
+/* Phase timing of the fused consolidate kernel's launches since profiling was
+ * enabled: 32 words per launch ([0..9] globaltimer ns at the phase boundaries,
+ * [16] rows, [17] radix rounds, [18] bits per round (8 bits each), [19] CTAs). */
+int32_t mzgpu_profile_fused_phases(mzgpu_ctx* ctx, uint64_t* out, uint32_t cap_records, uint32_t* n);
 /* The CUDA stream all of this ctx's work is issued on (a cudaStream_t), so a
  * host harness can bracket it with its own events. */
 void* mzgpu_ctx_stream(mzgpu_ctx* ctx);

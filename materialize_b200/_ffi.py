@@ -114,6 +114,7 @@ SIGNATURES = {
     "mzgpu_ctx_stream": (vp, [vp]),
     "mzgpu_profile_enable": (i32, [vp, i32]),
     "mzgpu_profile_report": (i32, [vp, C.c_char_p, u64]),
+    "mzgpu_profile_fused_phases": (i32, [vp, PU64, u32, PU32]),
     "mzgpu_buf_new": (i32, [vp, u32, PV]),
     "mzgpu_buf_free": (None, [vp]),
     "mzgpu_buf_len": (u64, [vp]),

@@ -46,6 +46,8 @@ struct mzgpu_ctx {
   u32* d_tickets = nullptr;    // MZ_TICKETS zeroed tile counters, handed out round-robin
   u32 ticket_next = 0;
   u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (bug guard), [1] = rows required
+  u64* d_dbg = nullptr;  // per-launch phase stamps of the fused kernel while profiling (32 words each)
+  u32 dbg_next = 0;
   void* d_fused_ctl[2] = {nullptr, nullptr};  // control blocks of the fused kernel (each launch clears the other)
   int fused_flip = 0;
   // per-kernel profiling (mzgpu_profile_enable)
@@ -97,6 +99,7 @@ struct mzgpu_ctx {
 #define MZ_CNT_BLOCKS 8192
 #define MZ_LB_TILES (1u << 20)
 #define MZ_TICKETS 4096
+#define MZ_DBG_RECORDS 4096
 
 #define MZ_CHECK_CTX(ctx)                       \
   do {                                          \
@@ -610,6 +613,14 @@ struct FusedOut {
 int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
 size_t mz_fused_ctl_bytes();
 #define MZ_FUSED_MAX_ROWS (2u << 20)
+// ... judged by the exact row count when the host knows it.  When it only has an
+// upper bound (the count is still on the device), the fused kernel takes
+// capacities up to MZ_FUSED_MAX_CAP: buffers are sized by the bound, work by the
+// actual count, and a loose bound is the common case (probe fan-out bounds).
+#define MZ_FUSED_MAX_CAP (32u << 20)
+static inline bool mz_use_fused(bool exact, u64 ub) {
+  return exact ? ub <= MZ_FUSED_MAX_ROWS : ub <= MZ_FUSED_MAX_CAP;
+}
 
 // merge.cu: merge two sorted consolidated arrays; times are advanced to
 // max(time, since) on the way; result is consolidated.

@@ -39,6 +39,11 @@ constexpr int FI = 4;           // radix items per thread: 1024-key tiles
 constexpr int FTILE = FT * FI;
 constexpr int MAX_ROUNDS = 6;
 constexpr u32 MAX_RUN_SAT = 1024;  // key runs longer than this report as 1024
+// MSD path: rows are partitioned into buckets by the leading bits of their
+// composite key and every bucket is sorted AND consolidated inside one CTA's
+// shared memory (rows with equal keys always share a bucket).
+constexpr u32 MSD_MAX_BUCKETS = 4096;
+constexpr u32 MSD_LOCAL_MAX = 1024;  // largest bucket the in-CTA sort takes
 
 struct FusedCtl {
   u32 barrier;
@@ -47,6 +52,7 @@ struct FusedCtl {
   u64 n_seg;
   u64 n_out;
   u32 hist[MAX_ROUNDS * 8 * 256];
+  u32 bcnt[4096];  // MSD path: rows per bucket
 };
 constexpr size_t CTL_HEADER = offsetof(FusedCtl, hist);
 
@@ -74,7 +80,24 @@ struct FusedArgs {
   u64 table_cap;
   u64* res;   // n_out, mask, n_keys, max_run
   u64* kres;  // n_keep, min kept time, max input time, -
+  u64* dbg;   // optional: CTA 0 leaves a globaltimer stamp per phase (profiling runs only)
+  u64* m_lo;  // MSD path: composites and row indices grouped by bucket (cap each)
+  u64* m_hi;
+  u32* m_idx;
+  u64* lb_ship;  // MSD path: look-back state per bucket ((ship << 21) | keep counts), zeroed in phase 0
+  u64* lb_keep;
+  u32 max_g;     // CTAs that take part at most
 };
+
+__device__ __forceinline__ u64 gtimer() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PHASE_STAMP(i)                                                \
+  do {                                                                \
+    if (a.dbg != nullptr && c == 0 && tid == 0) a.dbg[(i)] = gtimer(); \
+  } while (0)
 
 __device__ __forceinline__ void grid_barrier(u32* counter, u32 G, u32& epoch) {
   __syncthreads();
@@ -83,8 +106,7 @@ __device__ __forceinline__ void grid_barrier(u32* counter, u32 G, u32& epoch) {
     __threadfence();
     atomicAdd(counter, 1u);
     const u32 target = epoch * G;
-    while (*(volatile u32*)counter < target) {
-    }
+    while (*(volatile u32*)counter < target) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
@@ -106,9 +128,20 @@ __device__ __forceinline__ u32 block_sum_prefix(const u32* a, u64 m, u32* sm) {
   return tot;
 }
 
+struct MsdSmem {
+  u64 lo[MSD_LOCAL_MAX];
+  u64 hi[MSD_LOCAL_MAX];
+  u32 idx[MSD_LOCAL_MAX];
+  u64 sum[MSD_LOCAL_MAX];  // one-word diff sums per segment of the bucket
+};
+struct MsdScan {  // phase "scatter": bucket bases
+  u32 base[MSD_MAX_BUCKETS + 1];
+};
 union FusedSmem {
   RsSmemT<FI> rs;
   u32 hist[8 * 256];
+  MsdSmem msd;
+  MsdScan scan;
 };
 
 template <int RB>
@@ -117,16 +150,23 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
   __shared__ int s_nwords, s_nrounds, s_word[6], s_shift[6], s_round[6], s_rbits[MAX_ROUNDS];
+  __shared__ int s_shift128[6], s_w128;
+  __shared__ u32 s_max_bucket;
   __shared__ u64 s_minv[6];
   const u32 c = blockIdx.x, tid = threadIdx.x;
   const u64 na = dlen_get(a.na), nb = dlen_get(a.nb);
   const u64 n = na + nb;
   const u64 T = (n + FTILE - 1) / FTILE;
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
+  // MSD bucket count from the row count alone: ~128..256 rows per populated bucket
+  u32 bb = 0;  // log2(buckets)
+  while (bb < 12 && ((u64)256 << bb) < n) ++bb;
+  const u32 NB = 1u << bb;
   u32 G = gridDim.x;
   {
-    u64 want = T > 0 ? T : 1;
+    u64 want = T > (u64)NB ? T : (u64)NB;
     if (want < (u64)G) G = (u32)want;
+    if (G > a.max_g) G = a.max_g;  // more CTAs only make the grid barriers slower
   }
   if (c >= G) return;
   const u64 gtid = (u64)c * FT + tid, gstride = (u64)G * FT;
@@ -155,6 +195,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     mask = slots - 1;
   }
 
+  PHASE_STAMP(0);
   // ---- phase 0: zero scratch, results, next launch's header; min/max of every key word
   {
     if (c == 0) {
@@ -171,6 +212,11 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       }
     }
     for (u64 i = gtid; i < (u64)MAX_ROUNDS * 8 * 256; i += gstride) ctl->hist[i] = 0;
+    for (u64 i = gtid; i < (u64)NB; i += gstride) {
+      ctl->bcnt[i] = 0;
+      a.lb_ship[i] = 0;
+      a.lb_keep[i] = 0;
+    }
     for (u64 i = gtid; i < T * 256; i += gstride) a.state0[i] = 0;
     for (u64 i = gtid; i < n * ND; i += gstride) a.seg_sums[i] = 0;
     if (a.table != nullptr)
@@ -230,11 +276,279 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     }
     s_nwords = nwords;
     s_nrounds = nwords == 0 ? 0 : round + 1;
+    // 128-bit composite layout for the MSD path (least significant word at bit 0)
+    int w128 = 0;
+    for (int j = 0; j < nwords; ++j) {
+      u64 lo = ~*(volatile u64*)&ctl->minmax[2 * s_word[j]], hi = *(volatile u64*)&ctl->minmax[2 * s_word[j] + 1];
+      s_shift128[j] = w128;
+      w128 += bit_width_dev(hi - lo);
+    }
+    s_w128 = w128;
     if (c == 0 && TW >= 0) a.kres[2] = n > 0 ? *(volatile u64*)&ctl->minmax[2 * (TW >= 0 ? TW : 0) + 1] : 0;
   }
   __syncthreads();
   const int nrounds = s_nrounds;
+  PHASE_STAMP(1);
+  if (a.dbg != nullptr && c == 0 && tid == 0) {
+    a.dbg[16] = n;
+    a.dbg[17] = (u64)nrounds;
+    a.dbg[18] = (u64)(s_rbits[0] | ((u64)s_rbits[1] << 8) | ((u64)s_rbits[2] << 16) | ((u64)s_rbits[3] << 24));
+    a.dbg[19] = G;
+  }
 
+
+  // =================================================================== MSD path
+  bool msd_done = false;
+  if (s_w128 <= 128 && n < (1ull << 21)) {
+    const int W = s_w128;
+    auto composite = [&](const u64* row, u64* clo, u64* chi) {
+      unsigned __int128 comp = 0;
+      for (int j = 0; j < s_nwords; ++j)
+        comp |= (unsigned __int128)(row[s_word[j]] - s_minv[j]) << s_shift128[j];
+      *clo = (u64)comp;
+      *chi = (u64)(comp >> 64);
+    };
+    auto bucket_of = [&](u64 clo, u64 chi) -> u32 {
+      if (bb == 0 || W == 0) return 0u;
+      const u64 top = W <= 64 ? (clo << (64 - W)) : ((chi << (128 - W)) | (W == 128 ? 0ull : (clo >> (W - 64))));
+      return (u32)(top >> (64 - bb));
+    };
+    // ---- pack composites, count rows per bucket (the atomic's return value is
+    // the row's slot inside its bucket; the order inside a bucket is irrelevant)
+    for (u64 i = gtid; i < n; i += gstride) {
+      u64 row[NW];
+      load_in(i, row);
+      u64 clo, chi;
+      composite(row, &clo, &chi);
+      const u32 b = bucket_of(clo, chi);
+      const u32 r = atomicAdd(&ctl->bcnt[b], 1u);
+      a.k0[i] = clo;
+      a.k1[i] = chi;
+      a.v0[i] = r;
+      a.v1[i] = b;
+    }
+    grid_barrier(&ctl->barrier, G, epoch);
+    PHASE_STAMP(10);
+    // ---- bucket bases (every CTA scans the same counts), size check, scatter
+    {
+      const u32 per = (NB + FT - 1) / FT;  // consecutive buckets per thread
+      u32 local[MSD_MAX_BUCKETS / FT];
+      u32 sum = 0, mx = 0;
+#pragma unroll
+      for (u32 j = 0; j < MSD_MAX_BUCKETS / FT; ++j) {
+        const u32 bi = tid * per + j;
+        u32 v = (j < per && bi < NB) ? *(volatile u32*)&ctl->bcnt[bi] : 0u;
+        local[j] = v;
+        sum += v;
+        mx = v > mx ? v : mx;
+      }
+      if (tid == 0) s_max_bucket = 0;
+      __syncthreads();
+      atomicMax(&s_max_bucket, mx);
+      u32 total;
+      u32 ex = block_exclusive_scan(sum, sm_scan, &total);
+#pragma unroll
+      for (u32 j = 0; j < MSD_MAX_BUCKETS / FT; ++j) {
+        const u32 bi = tid * per + j;
+        if (j < per && bi < NB) {
+          sm.scan.base[bi] = ex;
+          ex += local[j];
+        }
+      }
+      if (tid == 0) sm.scan.base[NB] = total;
+      __syncthreads();
+    }
+    if (s_max_bucket <= MSD_LOCAL_MAX) {
+      for (u64 i = gtid; i < n; i += gstride) {
+        const u64 p = (u64)sm.scan.base[a.v1[i]] + a.v0[i];
+        a.m_lo[p] = a.k0[i];
+        a.m_hi[p] = a.k1[i];
+        a.m_idx[p] = (u32)i;
+      }
+      grid_barrier(&ctl->barrier, G, epoch);
+      PHASE_STAMP(11);
+      // ---- per bucket: sort in shared memory, consolidate, emit
+      const u64 upper = a.upper;
+      LookBack lbs;
+      lbs.state = a.lb_ship;
+      lbs.ticket = nullptr;
+      lbs.epoch = 1;
+      __shared__ u64 s_lb;
+      // this CTA's buckets (the bases live in the same shared memory as the sort arrays)
+      u32 my_base[MSD_MAX_BUCKETS / 64 + 1], my_m[MSD_MAX_BUCKETS / 64 + 1];
+      {
+        int q = 0;
+        for (u32 b = c; b < NB && q < (int)(MSD_MAX_BUCKETS / 64 + 1); b += G, ++q) {
+          my_base[q] = sm.scan.base[b];
+          my_m[q] = sm.scan.base[b + 1] - sm.scan.base[b];
+        }
+      }
+      int q = 0;
+      for (u32 b = c; b < NB; b += G, ++q) {
+        const u32 gbase = my_base[q];
+        const u32 m = my_m[q];
+        u32 P = 32;
+        while (P < m) P <<= 1;
+        __syncthreads();
+        for (u32 j = tid; j < P; j += FT) {
+          if (j < m) {
+            sm.msd.lo[j] = a.m_lo[gbase + j];
+            sm.msd.hi[j] = a.m_hi[gbase + j];
+            sm.msd.idx[j] = a.m_idx[gbase + j];
+          } else {
+            sm.msd.lo[j] = ~0ull;
+            sm.msd.hi[j] = ~0ull;
+            sm.msd.idx[j] = 0xffffffffu;
+          }
+          sm.msd.sum[j] = 0;
+        }
+        __syncthreads();
+        // bitonic sort of P elements by (hi, lo, idx); padding (all ones) sorts last
+        for (u32 k = 2; k <= P; k <<= 1) {
+          for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = tid; i < P; i += FT) {
+              const u32 x = i ^ j;
+              if (x > i) {
+                const u64 hi1 = sm.msd.hi[i], lo1 = sm.msd.lo[i], hi2 = sm.msd.hi[x], lo2 = sm.msd.lo[x];
+                const u32 i1 = sm.msd.idx[i], i2 = sm.msd.idx[x];
+                const bool gt = hi1 > hi2 || (hi1 == hi2 && (lo1 > lo2 || (lo1 == lo2 && i1 > i2)));
+                const bool up = (i & k) == 0;
+                if (gt == up) {
+                  sm.msd.hi[i] = hi2;
+                  sm.msd.lo[i] = lo2;
+                  sm.msd.idx[i] = i2;
+                  sm.msd.hi[x] = hi1;
+                  sm.msd.lo[x] = lo1;
+                  sm.msd.idx[x] = i1;
+                }
+              }
+            }
+            __syncthreads();
+          }
+        }
+        // pass 1: segmented diff sums over the sorted bucket.  Segment s of the bucket
+        // accumulates in shared memory (one-word diffs) or in seg_sums[gbase + s].
+        u32 nseg = 0;
+        for (u32 j0 = 0; j0 < m; j0 += FT) {
+          const u32 j = j0 + tid;
+          const bool valid = j < m;
+          u32 flag = 0;
+          if (valid)
+            flag = (j == 0 || sm.msd.lo[j] != sm.msd.lo[j - 1] || sm.msd.hi[j] != sm.msd.hi[j - 1]) ? 1u : 0u;
+          u32 total;
+          const u32 ex = block_exclusive_scan(flag, sm_scan, &total);
+          const u32 seg = valid ? nseg + ex + flag - 1 : 0xffffffffu;
+          u64 d[ND];
+          if (valid) {
+            u64 row[NW];
+            load_in(sm.msd.idx[j], row);
+#pragma unroll
+            for (int w = 0; w < ND; ++w) d[w] = row[NK + w];
+          } else {
+#pragma unroll
+            for (int w = 0; w < ND; ++w) d[w] = 0;
+          }
+          const u32 lane = lane_id();
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            u32 oseg = __shfl_up_sync(0xffffffffu, seg, off);
+            u64 o[ND];
+#pragma unroll
+            for (int w = 0; w < ND; ++w) o[w] = __shfl_up_sync(0xffffffffu, d[w], off);
+            if (lane >= (u32)off && oseg == seg) diff_add<ND>(d, o);
+          }
+          const u32 nxt = __shfl_down_sync(0xffffffffu, seg, 1);
+          if (valid && (lane == 31 || nxt != seg)) {
+            if (ND == 8) {
+              u64* acc = a.seg_sums + ((u64)gbase + seg) * ND;
+              if (d[0]) atomicAdd((unsigned long long*)&acc[0], (unsigned long long)d[0]);
+              if (d[1]) atomicAdd((unsigned long long*)&acc[1], (unsigned long long)d[1]);
+              u64 old = atomicAdd((unsigned long long*)&acc[2], (unsigned long long)d[2]);
+              u64 hi = d[3] + ((old + d[2]) < old ? 1 : 0);
+              if (hi) atomicAdd((unsigned long long*)&acc[3], (unsigned long long)hi);
+              if (d[4]) atomicAdd((unsigned long long*)&acc[4], (unsigned long long)d[4]);
+              if (d[5]) atomicAdd((unsigned long long*)&acc[5], (unsigned long long)d[5]);
+              if (d[6]) atomicAdd((unsigned long long*)&acc[6], (unsigned long long)d[6]);
+            } else {
+              atomicAdd((unsigned long long*)&sm.msd.sum[seg], (unsigned long long)d[0]);
+            }
+          }
+          nseg += total;
+        }
+        if (ND == 8) __threadfence();
+        __syncthreads();
+        // pass 2 (run twice: count, then write after the bucket-ordered look-back):
+        // the head row of every surviving segment goes to `out` (time < upper) or `keep`
+        u64 bases = 0;  // (ship << 21) | keep: exclusive prefix over earlier buckets
+        u32 tot_ship = 0, tot_keep = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+          u32 run_ship = 0, run_keep = 0, seg0 = 0;
+          for (u32 j0 = 0; j0 < m; j0 += FT) {
+            const u32 j = j0 + tid;
+            const bool valid = j < m;
+            u32 flag = 0;
+            if (valid)
+              flag = (j == 0 || sm.msd.lo[j] != sm.msd.lo[j - 1] || sm.msd.hi[j] != sm.msd.hi[j - 1]) ? 1u : 0u;
+            u32 total;
+            const u32 ex = block_exclusive_scan(flag, sm_scan, &total);
+            u32 cls = 0;
+            u64 r[NW];
+            if (valid && flag) {
+              const u32 seg = seg0 + ex;
+              u64 d[ND];
+              if (ND == 8) {
+#pragma unroll
+                for (int w = 0; w < ND; ++w) d[w] = *(volatile u64*)&a.seg_sums[((u64)gbase + seg) * ND + w];
+              } else {
+                d[0] = sm.msd.sum[seg];
+#pragma unroll
+                for (int w = 1; w < ND; ++w) d[w] = 0;
+              }
+              if (!diff_is_zero<ND>(d)) {
+                load_in(sm.msd.idx[j], r);
+#pragma unroll
+                for (int w = 0; w < ND; ++w) r[NK + w] = d[w];
+                cls = (TW < 0 || upper == MZGPU_FRONTIER_EMPTY || r[TW >= 0 ? TW : 0] < upper) ? 1u : 2u;
+              }
+            }
+            u32 t1, t2;
+            const u32 e1 = block_exclusive_scan(cls == 1u ? 1u : 0u, sm_scan, &t1);
+            const u32 e2 = block_exclusive_scan(cls == 2u ? 1u : 0u, sm_scan, &t2);
+            if (pass == 1 && cls != 0u) {
+              if (cls == 1u) {
+                store_row<NW>(a.out, (bases >> 21) + run_ship + e1, r);
+              } else if (a.keep != nullptr) {
+                store_row<NW>(a.keep, (bases & ((1ull << 21) - 1)) + run_keep + e2, r);
+                if (TW >= 0) atomicMin((unsigned long long*)&a.kres[1], (unsigned long long)r[TW >= 0 ? TW : 0]);
+              }
+            }
+            run_ship += t1;
+            run_keep += t2;
+            seg0 += total;
+          }
+          if (pass == 0) {
+            tot_ship = run_ship;
+            tot_keep = run_keep;
+            bases = lb_exclusive_prefix(lbs, b, ((u64)tot_ship << 21) | (u64)tot_keep, &s_lb);
+          }
+        }
+        if (b == NB - 1 && tid == 0) {
+          ctl->n_out = (bases >> 21) + tot_ship;
+          a.res[0] = (bases >> 21) + tot_ship;
+          a.kres[0] = (bases & ((1ull << 21) - 1)) + tot_keep;
+        }
+      }
+      msd_done = true;
+    }
+  }
+  PHASE_STAMP(7);
+  if (msd_done) {
+    if (a.table == nullptr) return;
+    grid_barrier(&ctl->barrier, G, epoch);
+    PHASE_STAMP(8);
+  }
+  u64 n_out = 0;
+  if (!msd_done) {
   // ---- radix rounds.  (kin, vin) holds the current order; round r packs into the
   // other pair (reading the order of round r-1) and sorts that.
   u64* kcur = a.k0;
@@ -310,6 +624,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     }
   }
   const u32* perm = vcur;  // final order
+  PHASE_STAMP(2);
 
   // ---- gather rows, head flags, per-tile head counts
   const u64 U = (n + FT - 1) / FT;
@@ -330,6 +645,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     }
   }
   grid_barrier(&ctl->barrier, G, epoch);
+  PHASE_STAMP(3);
   for (u64 u = c; u < U; u += G) {
     const u64 i = u * FT + tid;
     u32 flag = i < n ? is_head(i) : 0u;
@@ -339,6 +655,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
+  PHASE_STAMP(4);
   // ---- segmented sums
   for (u64 u = c; u < U; u += G) {
     const u32 base = block_sum_prefix(a.tile_cnt, u, sm_scan);
@@ -381,6 +698,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
+  PHASE_STAMP(5);
   // ---- surviving segments per tile: ship (time < upper) and keep
   const u64 S = U == 0 ? 0 : *(volatile u64*)&ctl->n_seg;
   const u64 V = (S + FT - 1) / FT;
@@ -405,6 +723,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   grid_barrier(&ctl->barrier, G, epoch);
 
+  PHASE_STAMP(6);
   // ---- emit
   for (u64 v = c; v < V; v += G) {
     const u32 base = block_sum_prefix(a.tile_cnt, v, sm_scan);
@@ -433,11 +752,16 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       a.kres[0] = (u64)base2 + total2;
     }
   }
+  PHASE_STAMP(7);
   if (a.table == nullptr) return;
   grid_barrier(&ctl->barrier, G, epoch);
+  PHASE_STAMP(8);
+  n_out = V == 0 ? 0 : *(volatile u64*)&ctl->n_out;
+  } else {
+    n_out = *(volatile u64*)&ctl->n_out;
+  }
 
   // ---- hash index over the distinct keys of the output; longest key run
-  const u64 n_out = V == 0 ? 0 : *(volatile u64*)&ctl->n_out;
   u32 my_run = 0;
   for (u64 i = gtid; i < ((n_out + 31) / 32) * 32; i += gstride) {
     bool head = false;
@@ -470,6 +794,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     my_run = o > my_run ? o : my_run;
   }
   if (lane_id() == 0 && my_run) atomicMax((unsigned long long*)&a.res[3], (unsigned long long)my_run);
+  PHASE_STAMP(9);
 }
 
 template <int RB>
@@ -486,7 +811,7 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
     }
   }
   const u64 cap = job.cap > 0 ? job.cap : 1;
-  if (cap > MZ_FUSED_MAX_ROWS) {
+  if (cap > MZ_FUSED_MAX_CAP) {
     MZ_SET_ERR(ctx, "fused consolidate: %llu rows exceed the fused limit", (unsigned long long)cap);
     return MZGPU_E_INVALID;
   }
@@ -510,7 +835,9 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   const u64 o_k0 = 0, o_k1 = o_k0 + al(cap * 8), o_v0 = o_k1 + al(cap * 8), o_v1 = o_v0 + al(cap * 4);
   const u64 o_s0 = o_v1 + al(cap * 4), o_s1 = o_s0 + al(Tcap * 1024), o_sorted = o_s1 + al(Tcap * 1024);
   const u64 o_t1 = o_sorted + al(cap * RB), o_t2 = o_t1 + al(Ucap * 4), o_sums = o_t2 + al(Ucap * 4);
-  const u64 o_first = o_sums + al(cap * ND * 8), o_end = o_first + al(cap * 4);
+  const u64 o_first = o_sums + al(cap * ND * 8), o_mlo = o_first + al(cap * 4);
+  const u64 o_mhi = o_mlo + al(cap * 8), o_midx = o_mhi + al(cap * 8), o_lbs = o_midx + al(cap * 4);
+  const u64 o_lbk = o_lbs + MSD_MAX_BUCKETS * 8, o_end = o_lbk + MSD_MAX_BUCKETS * 8;
   DevMem scratch;
   MZ_TRY(scratch.alloc(ctx, o_end));
   MZ_TRY(res->rows.alloc(ctx, cap * RB));
@@ -535,13 +862,24 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   a.tile_cnt2 = (u32*)(sp + o_t2);
   a.seg_sums = (u64*)(sp + o_sums);
   a.seg_first = (u32*)(sp + o_first);
+  a.m_lo = (u64*)(sp + o_mlo);
+  a.m_hi = (u64*)(sp + o_mhi);
+  a.m_idx = (u32*)(sp + o_midx);
+  a.lb_ship = (u64*)(sp + o_lbs);
+  a.lb_keep = (u64*)(sp + o_lbk);
+  a.max_g = 2u * (u32)ctx->num_sms;
   a.out = res->rows.template as<u64>();
   a.keep = want_keep ? res->keep.template as<u64>() : nullptr;
   a.table = job.want_index ? res->table.template as<HashSlot>() : nullptr;
   a.table_cap = slots;
   a.res = res->st.dptr();
   a.kres = res->kst.dptr();
-  u64 want = Tcap;
+  a.dbg = nullptr;
+  if (ctx->profile && ctx->d_dbg != nullptr && ctx->dbg_next < MZ_DBG_RECORDS) {
+    a.dbg = ctx->d_dbg + 32 * (size_t)ctx->dbg_next++;
+    MZ_CUDA(ctx, cudaMemsetAsync(a.dbg, 0, 32 * 8, ctx->stream));
+  }
+  u64 want = (cap + 127) / 128 + 1;  // one CTA per MSD bucket (128..256 rows each), at least one per radix tile
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);
   if (grid == 0) grid = 1;
   void* kargs[] = {(void*)&a};

@@ -67,6 +67,7 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_lb) cudaFree(ctx->d_lb);
   if (ctx->d_tickets) cudaFree(ctx->d_tickets);
   if (ctx->d_status) cudaFree(ctx->d_status);
+  if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int i = 0; i < 2; ++i)
     if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -150,6 +151,20 @@ extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
 extern "C" int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on) {
   MZ_CHECK_CTX(ctx);
   ctx->profile = on != 0;
+  if (on && ctx->d_dbg == nullptr) MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_dbg, (size_t)MZ_DBG_RECORDS * 32 * 8));
+  if (on) ctx->dbg_next = 0;
+  return MZGPU_OK;
+}
+// Phase stamps of the fused kernel's launches since profiling was enabled:
+// 32 words per launch ([0..9] globaltimer ns at phase boundaries, [16] rows,
+// [17] radix rounds, [18] bits per round, [19] CTAs used).  Returns the count.
+extern "C" int32_t mzgpu_profile_fused_phases(mzgpu_ctx* ctx, uint64_t* out, uint32_t cap_records, uint32_t* n) {
+  MZ_CHECK_CTX(ctx);
+  if (out == nullptr || n == nullptr) return MZGPU_E_INVALID;
+  MZ_SYNC(ctx);
+  uint32_t m = ctx->dbg_next < cap_records ? ctx->dbg_next : cap_records;
+  if (m) MZ_CUDA(ctx, cudaMemcpy(out, ctx->d_dbg, (size_t)m * 32 * 8, cudaMemcpyDeviceToHost));
+  *n = m;
   return MZGPU_OK;
 }
 
@@ -409,7 +424,13 @@ extern "C" int32_t mzgpu_buf_download(mzgpu_buf* b, void* rows, uint64_t cap, in
 // kernel for small / medium inputs, the multi-kernel path beyond.
 static int32_t consolidate_dev(mzgpu_ctx* ctx, int rb, const void* d_in, DLen n, u64 n_ub, DevMem* out,
                                u64* out_cap, Lazy4* out_len) {
-  if (n_ub <= MZ_FUSED_MAX_ROWS) {
+  if (n.p != nullptr && !mz_use_fused(false, n_ub)) {
+    // bound too loose to size buffers by: read the count back
+    MZ_TRY(mz_resolve_counters(ctx));
+    n = dlen_imm(ctx->h_cnt[n.p - ctx->d_cnt]);  // the block is part of the arena mirror
+    n_ub = n.imm;
+  }
+  if (mz_use_fused(n.p == nullptr, n_ub)) {
     FusedJob job;
     job.rb = rb;
     job.a = d_in;
@@ -423,11 +444,6 @@ static int32_t consolidate_dev(mzgpu_ctx* ctx, int rb, const void* d_in, DLen n,
     return MZGPU_OK;
   }
   u64 nn = n.imm;
-  if (n.p != nullptr) {
-    MZ_TRY(mz_resolve_counters(ctx));
-    // the block the caller's DLen points into is part of the arena mirror
-    nn = ctx->h_cnt[n.p - ctx->d_cnt];
-  }
   u64 n_out = 0;
   MZ_TRY(mz_sort_consolidate(ctx, rb, d_in, nn, out, &n_out));
   *out_cap = nn;
@@ -562,7 +578,7 @@ static int32_t batch_shrink(mzgpu_batch* b) {
 // unsorted device rows -> batch
 static int32_t build_batch_from_unsorted(mzgpu_ctx* ctx, uint32_t rb, const void* d_in, DLen n, u64 n_ub,
                                          mzgpu_desc desc, mzgpu_batch** out) {
-  if (n_ub <= MZ_FUSED_MAX_ROWS) {
+  if (mz_use_fused(n.p == nullptr, n_ub)) {
     FusedJob job;
     job.rb = rb;
     job.a = d_in;
@@ -639,7 +655,11 @@ extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, 
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
   mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
-  if (b1->len_ub + b2->len_ub <= MZ_FUSED_MAX_ROWS) {
+  if (!mz_use_fused(false, b1->len_ub + b2->len_ub)) {
+    MZ_TRY(batch_resolve(b1));
+    MZ_TRY(batch_resolve(b2));
+  }
+  if (mz_use_fused(b1->st.known && b2->st.known, b1->len_ub + b2->len_ub)) {
     FusedJob job;
     job.rb = b1->rb;
     job.a = b1->rows.p;
@@ -790,13 +810,22 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     b->segs = std::move(live);
   }
   mzgpu_desc d = {b->lower, upper, 0};
+  bool exact = true;
+  for (auto& s : b->segs) exact = exact && s.len.known;
+  if (!exact && !mz_use_fused(false, batcher_ub(b))) {
+    for (auto& s : b->segs) {
+      MZ_TRY(s.len.resolve());
+      s.ub = s.len.v[s.word];
+    }
+    exact = true;
+  }
   const u64 total = batcher_ub(b);
   if (total == 0) {
     b->segs.clear();
     b->frontier = MZGPU_FRONTIER_EMPTY;
     b->frontier_known = true;
     MZ_TRY(make_empty_batch(ctx, b->rb, d, batch_out));
-  } else if (total <= MZ_FUSED_MAX_ROWS) {
+  } else if (mz_use_fused(exact, total)) {
     DevMem all;
     Lazy4 alen;
     int aword = 0;
