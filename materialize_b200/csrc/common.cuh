@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,7 @@ struct mzgpu_ctx {
   u64 op_seq = 1;              // bumped whenever a kernel that writes counters is enqueued
   u64 resolved_seq = 0;        // op_seq covered by the last read-back
   u64 n_resolves = 0;          // host syncs spent on read-backs
+  u64 ns_alloc = 0, ns_sync = 0, n_alloc = 0, bytes_alloc = 0;  // host-side time in the allocator / waiting (MZGPU_DEBUG)
   // ---- single-pass expansion kernels: look-back state, tile tickets
   u64* d_lb = nullptr;         // MZ_LB_TILES tagged state words (never written by anything else)
   u32 lb_epoch = 0;            // tag of the next launch (20 bits)
@@ -86,7 +88,9 @@ struct mzgpu_ctx {
 // a host wait on the ctx stream (counted: mzgpu_stats.host_syncs)
 #define MZ_SYNC(ctx)                                            \
   do {                                                          \
+    auto _t0 = std::chrono::steady_clock::now();                \
     MZ_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));         \
+    (ctx)->ns_sync += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - _t0).count(); \
     (ctx)->stats.host_syncs++;                                  \
   } while (0)
 
@@ -176,7 +180,11 @@ struct DevMem {
     release();
     ctx = c;
     if (n == 0) n = 16;
+    auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+    c->ns_alloc += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    c->n_alloc++;
+    c->bytes_alloc += n;
     if (e != cudaSuccess) {
       p = nullptr;
       MZ_SET_ERR(c, "cudaMallocAsync(%zu bytes) failed: %s", n, cudaGetErrorString(e));
@@ -601,6 +609,7 @@ struct FusedJob {
   u64 since = 0;                        // advance_by(since)
   u64 upper = MZGPU_FRONTIER_EMPTY;     // rows with time < upper go to `rows`, the rest to `keep`
   bool want_index = false;
+  bool merge = false;  // a and b are each sorted and consolidated (a batch merge): merge path, no sort
 };
 struct FusedOut {
   DevMem rows;  // consolidated (shipped) rows, capacity rows_cap

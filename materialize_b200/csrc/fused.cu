@@ -87,6 +87,7 @@ struct FusedArgs {
   u64* lb_ship;  // MSD path: look-back state per bucket ((ship << 21) | keep counts), zeroed in phase 0
   u64* lb_keep;
   u32 max_g;     // CTAs that take part at most
+  u32 merge;     // both inputs are sorted and consolidated: merge path instead of a sort
 };
 
 __device__ __forceinline__ u64 gtimer() {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       mn[k] = 0;
       mx[k] = 0;
     }
-    for (u64 i = gtid; i < n; i += gstride) {
+    for (u64 i = gtid; i < (a.merge ? 0 : n); i += gstride) {
       u64 r[NW];
       load_in(i, r);
 #pragma unroll
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
 
   // =================================================================== MSD path
   bool msd_done = false;
-  if (s_w128 <= 128 && n < (1ull << 21)) {
+  if (!a.merge && s_w128 <= 128 && n < (1ull << 21)) {
     const int W = s_w128;
     auto composite = [&](const u64* row, u64* clo, u64* chi) {
       unsigned __int128 comp = 0;
@@ -549,6 +550,16 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   u64 n_out = 0;
   if (!msd_done) {
+  const u64 U = (n + FT - 1) / FT;
+  auto is_head = [&](u64 i) -> u32 {
+    if (i == 0) return 1u;
+    const u64* p = a.sorted + i * NW;
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      if (p[k] != p[k - NW]) return 1u;
+    return 0u;
+  };
+  if (!a.merge) {
   // ---- radix rounds.  (kin, vin) holds the current order; round r packs into the
   // other pair (reading the order of round r-1) and sorts that.
   u64* kcur = a.k0;
@@ -625,23 +636,63 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   const u32* perm = vcur;  // final order
   PHASE_STAMP(2);
-
-  // ---- gather rows, head flags, per-tile head counts
-  const u64 U = (n + FT - 1) / FT;
-  auto is_head = [&](u64 i) -> u32 {
-    if (i == 0) return 1u;
-    const u64* p = a.sorted + i * NW;
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-      if (p[k] != p[k - NW]) return 1u;
-    return 0u;
-  };
+  // ---- gather rows by the final permutation
   for (u64 u = c; u < U; u += G) {
     const u64 i = u * FT + tid;
     if (i < n) {
       u64 r[NW];
       load_in(perm[i], r);
       store_row<NW>(a.sorted, i, r);
+    }
+  }
+  } else {
+    // ---- merge path: A and B are sorted (and stay sorted under advance_by(since),
+    // which is monotone); every thread finds its diagonal by binary search and
+    // merges MV consecutive outputs.  Ties take A first (A is the older batch).
+    constexpr int MV = 4;
+    auto less_ba = [&](const u64* x, const u64* y) -> bool {  // x < y on the key words, times advanced
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        u64 p = x[k], q = y[k];
+        if (k == TW) {
+          p = p < since ? since : p;
+          q = q < since ? since : q;
+        }
+        if (p != q) return p < q;
+      }
+      return false;
+    };
+    const u64 n_groups = (n + (u64)FT * MV - 1) / ((u64)FT * MV);
+    for (u64 u = c; u < n_groups; u += G) {
+      const u64 o0 = (u * FT + tid) * MV;
+      if (o0 < n) {
+        u64 lo = o0 > nb ? o0 - nb : 0, hi = o0 < na ? o0 : na;
+        while (lo < hi) {
+          const u64 mid = (lo + hi) >> 1;
+          const u64 bi = o0 - mid;  // >= 1
+          if (!less_ba(a.b + (bi - 1) * NW, a.a + mid * NW))
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        u64 ia = lo, ib = o0 - lo;
+#pragma unroll
+        for (int k = 0; k < MV; ++k) {
+          const u64 o = o0 + k;
+          if (o >= n) break;
+          const bool take_a = ib >= nb || (ia < na && !less_ba(a.b + ib * NW, a.a + ia * NW));
+          u64 r[NW];
+          if (take_a)
+            load_row<NW>(a.a, ia++, r);
+          else
+            load_row<NW>(a.b, ib++, r);
+          if (TW >= 0) {
+            u64& t = r[TW >= 0 ? TW : 0];
+            t = t < since ? since : t;
+          }
+          store_row<NW>(a.sorted, o, r);
+        }
+      }
     }
   }
   grid_barrier(&ctl->barrier, G, epoch);
@@ -868,6 +919,7 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   a.lb_ship = (u64*)(sp + o_lbs);
   a.lb_keep = (u64*)(sp + o_lbk);
   a.max_g = 2u * (u32)ctx->num_sms;
+  a.merge = (job.merge && job.b != nullptr) ? 1u : 0u;
   a.out = res->rows.template as<u64>();
   a.keep = want_keep ? res->keep.template as<u64>() : nullptr;
   a.table = job.want_index ? res->table.template as<HashSlot>() : nullptr;

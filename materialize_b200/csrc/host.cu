@@ -50,6 +50,22 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thresh = UINT64_MAX;
   MZ_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  // Pre-size the pool: operator scratch is sized by upper bounds (hundreds of MB per
+  // update batch, released in stream order right away) and growing the pool on the
+  // hot path costs milliseconds.  One reservation up front; MZGPU_POOL_MB overrides.
+  {
+    size_t free_b = 0, total_b = 0;
+    MZ_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t want = (size_t)24 << 30;
+    if (const char* e = getenv("MZGPU_POOL_MB")) want = (size_t)strtoull(e, nullptr, 10) << 20;
+    if (want > free_b / 2) want = free_b / 2;
+    if (want >= ((size_t)1 << 20)) {
+      void* p = nullptr;
+      MZ_CUDA(ctx, cudaMallocAsync(&p, want, ctx->stream));
+      MZ_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+      MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   return MZGPU_OK;
 }
 
@@ -144,6 +160,11 @@ extern "C" int32_t mzgpu_ctx_sync(mzgpu_ctx* ctx) {
 
 extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   if (ctx == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  if (getenv("MZGPU_DEBUG"))
+    fprintf(stderr, "[mzgpu] allocs %llu (%.1f MB, %.3f ms host)  syncs %llu (%.3f ms waiting)  launches %llu\n",
+            (unsigned long long)ctx->n_alloc, ctx->bytes_alloc / 1e6, ctx->ns_alloc / 1e6,
+            (unsigned long long)ctx->stats.host_syncs, ctx->ns_sync / 1e6,
+            (unsigned long long)ctx->stats.kernel_launches);
   *out = ctx->stats;
   return MZGPU_OK;
 }
@@ -669,6 +690,7 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
     job.cap = b1->len_ub + b2->len_ub;
     job.since = since;
     job.want_index = true;
+    job.merge = true;
     FusedOut fo;
     MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
     return batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out);
