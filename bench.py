@@ -314,6 +314,28 @@ def run_ours(args, rank, world, local_rank):
     dom_name, dom = with_bytes[0] if with_bytes else ranked[0]
     peak, peak_kind = measured_peak()
     achieved = dom["bytes"] / (dom["ms"] / 1000.0) / 1e9 if dom["ms"] > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/, same command line): mean of the captured launches, bytes per launch
+    traffic = None
+    try:
+        import csv
+
+        tag = "fused" if "fused" in dom_name else ("probe" if "probe" in dom_name else None)
+        path = os.path.join(ROOT, "profiles", f"r01_ncu_full_{tag}_raw.csv")
+        if tag and os.path.exists(path):
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            tot = []
+            for r in rows[2:]:
+                b = 0.0
+                for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(col)
+                    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
+                    b += float(r[i].replace(",", "")) * mult
+                tot.append(b)
+            traffic = sum(tot) / len(tot) if tot else None
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm",
         "kernel": dom_name,
@@ -322,7 +344,8 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": "profiles/r01_ncu_full_*_raw.csv (ncu --set full, mean over captured launches)" if traffic else None,
         "launches_per_step": dom["launches"] / n_prof,
         "avg_launch_us": 1000.0 * dom["ms"] / max(1, dom["launches"]),
         "algorithmic_bytes_per_launch": dom["bytes"] / max(1, dom["launches"]),

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
   // MSD bucket count from the row count alone: ~128..256 rows per populated bucket
   u32 bb = 0;  // log2(buckets)
-  while (bb < 12 && ((u64)256 << bb) < n) ++bb;
+  while (bb < 12 && ((u64)128 << bb) < n) ++bb;
   const u32 NB = 1u << bb;
   u32 G = gridDim.x;
   {
@@ -295,12 +295,14 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
     a.dbg[17] = (u64)nrounds;
     a.dbg[18] = (u64)(s_rbits[0] | ((u64)s_rbits[1] << 8) | ((u64)s_rbits[2] << 16) | ((u64)s_rbits[3] << 24));
     a.dbg[19] = G;
+    a.dbg[20] = RB;
   }
 
 
   // =================================================================== MSD path
   bool msd_done = false;
-  if (!a.merge && s_w128 <= 128 && n < (1ull << 21)) {
+  // (beyond ~256K rows the bucket phase stops paying: the look-back radix passes win)
+  if (!a.merge && s_w128 <= 128 && n <= (1ull << 18)) {
     const int W = s_w128;
     auto composite = [&](const u64* row, u64* clo, u64* chi) {
       unsigned __int128 comp = 0;
@@ -936,7 +938,10 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   if (grid == 0) grid = 1;
   void* kargs[] = {(void*)&a};
   {
-    MZ_BYTES(ctx, cap * RB * 4);  // rows read (analyze, pack, gather) + sorted + out written; see DESIGN.md
+    // algorithmic bytes: 4 x rows x row bytes (read for min/max, read to pack, read to gather/emit,
+    // written out).  With a device-resident count only the bound is known here;
+    // mzgpu_profile_report substitutes the actual row count of profiled launches.
+    MZ_BYTES(ctx, (job.na.p == nullptr && job.nb.p == nullptr) ? (job.na.imm + job.nb.imm) * RB * 4 : 0);
     ProfScope prof(ctx, "k_fused_consolidate");
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_fused_consolidate<RB>, dim3(grid), dim3(FT), kargs, 0,
                                                 ctx->stream);

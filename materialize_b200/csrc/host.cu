@@ -217,6 +217,17 @@ extern "C" int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap)
     ctx->ev_pool.push_back(r.e1);
   }
   ctx->prof.clear();
+  // the fused kernel leaves its actual row count in its debug record
+  if (ctx->d_dbg != nullptr && ctx->dbg_next > 0) {
+    std::vector<u64> rec((size_t)ctx->dbg_next * 32);
+    if (cudaMemcpy(rec.data(), ctx->d_dbg, rec.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      u64 bytes = 0;
+      for (u32 i = 0; i < ctx->dbg_next; ++i) bytes += rec[(size_t)i * 32 + 16] * rec[(size_t)i * 32 + 20] * 4;
+      for (auto& x : aggs)
+        if (x.name == "k_fused_consolidate" && x.launches == ctx->dbg_next) x.bytes = bytes;
+    }
+    ctx->dbg_next = 0;
+  }
   std::string out;
   for (auto& a : aggs) {
     char line[384];
@@ -286,7 +297,7 @@ static int32_t append_dev(mzgpu_ctx* ctx, const void* src, DLen n, u64 n_ub, int
   const u64 maxg = (u64)ctx->num_sms * 8;
   if (grid > maxg) grid = maxg;
   if (grid == 0) grid = 1;
-  MZ_BYTES(ctx, n_ub * rb * 2);
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * rb * 2 : 0);
   MZ_LAUNCH(ctx, k_append_rows, (unsigned)grid, 256, 0, (const u64*)src, n, rb / 8, (u64*)dst, base, cap_rows,
             out_len, ctx->d_status);
   return MZGPU_OK;

@@ -353,7 +353,7 @@ int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, co
   LookBack lb;
   MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
   const int out_rb = pp.has_closure ? 32 : 40;
-  MZ_BYTES(ctx, n_ub * (32 + 16 * trace.n_batches + 32 + out_rb));
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 * trace.n_batches + 32 + out_rb) : 0);  // exact counts only
   if (pp.has_closure) {
     MZ_LAUNCH(ctx, (k_probe_lb<4>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
               out_cap, d_out_len, ctx->d_status);
@@ -371,7 +371,7 @@ int32_t mz_map_rows_async(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, c
   mzgpu_closure cl;
   memset(&cl, 0, sizeof(cl));
   if (closure) cl = *closure;
-  MZ_BYTES(ctx, n_ub * 64);
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * 64 : 0);
   MZ_LAUNCH(ctx, k_map_rows_lb, lb_grid(ctx, n_ub), PT, 0, d_rows, n, cl, closure ? 1 : 0, skip_time, lb, d_out,
             out_base, out_cap, d_out_len, ctx->d_status);
   return MZGPU_OK;

@@ -317,7 +317,7 @@ int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_k
   if (n_ub == 0) return MZGPU_OK;
   u64 grid = (n_ub + RT - 1) / RT;
   if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
-  MZ_BYTES(ctx, n_ub * 112);
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * 112 : 0);
   MZ_LAUNCH(ctx, k_explode, (unsigned)grid, RT, 0, d_r32, n, agg_kind, d_racc);
   return MZGPU_OK;
 }
@@ -355,7 +355,7 @@ int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLe
   u64 grid = (n_ub + RT - 1) / RT;
   if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
   if (grid == 0) grid = 1;
-  MZ_BYTES(ctx, n_ub * (80 + 16 + 80 + 128));
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * (80 + 16 + 80 + 128) : 0);
   MZ_LAUNCH(ctx, k_corrections_lb, (unsigned)grid, RT, 0, d_batch_rows, n, prior, agg_kind, lb, d_out, out_cap,
             d_out_len, ctx->d_status);
   return MZGPU_OK;
