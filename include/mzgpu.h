@@ -415,6 +415,10 @@ int32_t mzgpu_comm_init(mzgpu_ctx* ctx, const uint8_t id[MZGPU_COMM_ID_BYTES]);
  * hash(key) % peers; collective over all peers' contexts (all must call in the
  * same order).  `in` and `out` are R32 or RACC buffers; `out` is replaced. */
 int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out);
+/* k independent exchanges in one round (one counts all-to-all, one host wait, one
+ * payload all-to-all): the exchange points of operators that run side by side,
+ * e.g. the arrangement inputs of one timestamp.  k <= 8; all peers pass the same k. */
+int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs);
 /* The routing function itself (for tests and host-side pre-partitioning). */
 uint32_t mzgpu_route(uint64_t key, uint32_t peers);
 

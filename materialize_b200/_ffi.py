@@ -172,6 +172,7 @@ SIGNATURES = {
     "mzgpu_comm_unique_id": (i32, [C.POINTER(C.c_uint8)]),
     "mzgpu_comm_init": (i32, [vp, C.POINTER(C.c_uint8)]),
     "mzgpu_exchange": (i32, [vp, vp, vp]),
+    "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
 }
 

@@ -30,6 +30,7 @@ struct mzgpu_ctx {
   // pinned staging for small device->host reads (counts, min/max)
   u64* h_scratch = nullptr;  // 64 words
   u64* d_scratch = nullptr;  // 64 words
+  u64* h_big = nullptr;      // pinned, 512 words (exchange counts)
   // pinned bounce buffers for host<->device row copies
   void* h_bounce = nullptr;
   size_t h_bounce_bytes = 0;
@@ -701,5 +702,5 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
                               int agg_kind, DevMem* out, u64* n_out);
 
 // exchange.cu
-int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u32 peers, void* d_out,
-                     u64* h_counts /* peers */);
+int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, DLen n, u64 n_ub, u32 peers, void* d_out,
+                     u64* d_counts /* 64 words */, u64* d_cursors /* 64 words */);

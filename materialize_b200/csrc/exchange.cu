@@ -27,8 +27,9 @@ __host__ __device__ __forceinline__ u64 fnv1a64(u64 key) {
 }
 
 template <int NW>
-__global__ void __launch_bounds__(XT) k_part_count(const u64* __restrict__ rows, u64 n, u32 peers,
+__global__ void __launch_bounds__(XT) k_part_count(const u64* __restrict__ rows, const DLen dn, u32 peers,
                                                    unsigned long long* __restrict__ counts) {
+  const u64 n = dlen_get(dn);
   __shared__ u32 sh[MAX_PEERS];
   if (threadIdx.x < MAX_PEERS) sh[threadIdx.x] = 0;
   __syncthreads();
@@ -39,70 +40,73 @@ __global__ void __launch_bounds__(XT) k_part_count(const u64* __restrict__ rows,
 }
 
 template <int NW>
-__global__ void __launch_bounds__(XT) k_part_scatter(const u64* __restrict__ rows, u64 n, u32 peers,
+__global__ void __launch_bounds__(XT) k_part_scatter(const u64* __restrict__ rows, const DLen dn, u32 peers,
                                                      unsigned long long* __restrict__ cursors,
                                                      u64* __restrict__ out) {
+  const u64 n = dlen_get(dn);
   __shared__ u32 sh_count[MAX_PEERS];
   __shared__ u64 sh_base[MAX_PEERS];
-  if (threadIdx.x < MAX_PEERS) sh_count[threadIdx.x] = 0;
-  __syncthreads();
-  const u64 i = (u64)blockIdx.x * XT + threadIdx.x;
-  u32 dest = 0, rank = 0;
-  u64 r[NW];
-  if (i < n) {
-    load_row<NW>(rows, i, r);
-    dest = (u32)(fnv1a64(r[0]) % peers);
-    rank = atomicAdd(&sh_count[dest], 1u);
+  for (u64 i0 = (u64)blockIdx.x * XT; i0 < n; i0 += (u64)gridDim.x * XT) {
+    __syncthreads();
+    if (threadIdx.x < MAX_PEERS) sh_count[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 i = i0 + threadIdx.x;
+    u32 dest = 0, rank = 0;
+    u64 r[NW];
+    if (i < n) {
+      load_row<NW>(rows, i, r);
+      dest = (u32)(fnv1a64(r[0]) % peers);
+      rank = atomicAdd(&sh_count[dest], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < peers && sh_count[threadIdx.x])
+      sh_base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)sh_count[threadIdx.x]);
+    __syncthreads();
+    if (i < n) store_row<NW>(out, sh_base[dest] + rank, r);
   }
-  __syncthreads();
-  if (threadIdx.x < peers && sh_count[threadIdx.x])
-    sh_base[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long)sh_count[threadIdx.x]);
-  __syncthreads();
-  if (i < n) store_row<NW>(out, sh_base[dest] + rank, r);
+}
+
+// counts[0..P) -> cursors[0..P) = exclusive offsets (counts stay for the count exchange)
+__global__ void k_part_offsets(const unsigned long long* __restrict__ counts, u32 peers,
+                               unsigned long long* __restrict__ cursors) {
+  if (threadIdx.x == 0) {
+    unsigned long long off = 0;
+    for (u32 p = 0; p < peers; ++p) {
+      cursors[p] = off;
+      off += counts[p];
+    }
+  }
 }
 
 }  // namespace
 
 uint32_t mzgpu_route(uint64_t key, uint32_t peers) { return (uint32_t)(fnv1a64(key) % peers); }
 
-int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u32 peers, void* d_out,
-                     u64* h_counts) {
-  for (u32 p = 0; p < peers; ++p) h_counts[p] = 0;
+// Bucket rows by destination entirely on the device: d_counts[p] = rows for peer
+// p, d_out = rows grouped by destination in peer order.  No host round trip.
+int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, DLen n, u64 n_ub, u32 peers, void* d_out,
+                     u64* d_counts /* MAX_PEERS words */, u64* d_cursors /* MAX_PEERS words */) {
   if (peers > MAX_PEERS) {
     MZ_SET_ERR(ctx, "exchange: %u peers exceed the supported maximum %d", peers, MAX_PEERS);
     return MZGPU_E_UNSUPPORTED;
   }
-  if (n == 0) return MZGPU_OK;
-  DevMem counts;
-  MZ_TRY(counts.alloc(ctx, MAX_PEERS * 8));
-  MZ_CUDA(ctx, cudaMemsetAsync(counts.p, 0, MAX_PEERS * 8, ctx->stream));
+  MZ_CUDA(ctx, cudaMemsetAsync(d_counts, 0, MAX_PEERS * 8, ctx->stream));
+  if (n_ub == 0) return MZGPU_OK;
   const u64* r = (const u64*)d_rows;
-  unsigned long long* c = counts.as<unsigned long long>();
-  u64 blocks = (n + XT - 1) / XT;
-  unsigned cgrid = (unsigned)(blocks < (u64)ctx->num_sms * 8 ? blocks : (u64)ctx->num_sms * 8);
+  unsigned long long* c = (unsigned long long*)d_counts;
+  unsigned long long* cur = (unsigned long long*)d_cursors;
+  u64 blocks = (n_ub + XT - 1) / XT;
+  unsigned grid = (unsigned)(blocks < (u64)ctx->num_sms * 8 ? blocks : (u64)ctx->num_sms * 8);
   switch (row_bytes) {
-    case 32: MZ_LAUNCH(ctx, k_part_count<4>, cgrid, XT, 0, r, n, peers, c); break;
-    case 80: MZ_LAUNCH(ctx, k_part_count<10>, cgrid, XT, 0, r, n, peers, c); break;
+    case 32: MZ_LAUNCH(ctx, k_part_count<4>, grid, XT, 0, r, n, peers, c); break;
+    case 80: MZ_LAUNCH(ctx, k_part_count<10>, grid, XT, 0, r, n, peers, c); break;
     default: MZ_SET_ERR(ctx, "exchange: unsupported row width %d", row_bytes); return MZGPU_E_UNSUPPORTED;
   }
-  MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 32, counts.p, peers * 8, cudaMemcpyDeviceToHost,
-                               ctx->stream));
-  MZ_SYNC(ctx);
-  ctx->stats.d2h_bytes += peers * 8;
-  u64 off = 0;
-  u64 offsets[MAX_PEERS];
-  for (u32 p = 0; p < peers; ++p) {
-    h_counts[p] = ctx->h_scratch[32 + p];
-    offsets[p] = off;
-    off += h_counts[p];
-  }
-  MZ_CUDA(ctx, cudaMemcpyAsync(counts.p, offsets, peers * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MZ_LAUNCH(ctx, k_part_offsets, 1, 32, 0, c, peers, cur);
   switch (row_bytes) {
-    case 32: MZ_LAUNCH(ctx, k_part_scatter<4>, (unsigned)blocks, XT, 0, r, n, peers, c, (u64*)d_out); break;
-    case 80: MZ_LAUNCH(ctx, k_part_scatter<10>, (unsigned)blocks, XT, 0, r, n, peers, c, (u64*)d_out); break;
+    case 32: MZ_LAUNCH(ctx, k_part_scatter<4>, grid, XT, 0, r, n, peers, cur, (u64*)d_out); break;
+    case 80: MZ_LAUNCH(ctx, k_part_scatter<10>, grid, XT, 0, r, n, peers, cur, (u64*)d_out); break;
     default: return MZGPU_E_UNSUPPORTED;
   }
-  // `offsets` is a stack array: make sure the H2D copy has consumed it
-  MZ_SYNC(ctx);
   return MZGPU_OK;
 }

@@ -116,12 +116,16 @@ struct mzh_q3 {
   mzgpu_spine* spine[4];
   mzgpu_reduce* reduce;
   mzgpu_buf* input[4];  // staged inputs of the next step (device resident)
-  mzgpu_buf *stream_buf, *next_buf, *results, *xchg, *out;
+  mzgpu_buf *results, *xchg, *out;
+  mzgpu_buf *pstream[3], *pnext[3], *pxchg[3];  // per delta path: stream, next stage, exchange landing
+  mzgpu_buf* axchg[4];                           // exchange landing per arrangement input
   DevArr gen_ok, gen_ck, gen_li, gen_cursor;
   uint64_t gen_cap_orders = 0;
   uint64_t next_time = 0;
   uint64_t last_rows_in = 0;
   uint64_t maintain_upper = 0;  // timestamp whose maintenance is still due
+  bool static_rel[4] = {true, false, false, false};  // relations the generator never updates after hydration
+  bool stepping = false;                             // false while hydrating
 };
 
 static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, int n_versions, uint64_t t,
@@ -156,7 +160,9 @@ static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, in
 // Exchange(key) then Batcher::push_container for arrangement `a`
 static int32_t q3_arrange_push(mzh_q3* q, int a, mzgpu_buf* rows) {
   mzgpu_buf* src = rows;
-  if (q->peers > 1) {
+  // a relation that receives no updates on ANY worker (customer, in the tick
+  // pattern) has nothing to exchange; every worker takes this branch together
+  if (q->peers > 1 && !(q->static_rel[a] && q->stepping)) {
     H_TRY(mzgpu_exchange(q->ctx, rows, q->xchg));
     src = q->xchg;
   }
@@ -178,26 +184,43 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
     if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
   }
   if (st == MZGPU_OK) st = mzgpu_buf_clear(q->results);
+  // the three delta paths run side by side, stage by stage, so that the exchange
+  // points of one stage share a round (mzgpu_exchange_many).  A path whose source
+  // relation is static (no updates on any worker) has nothing to do while stepping.
+  bool active[3];
   for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
-    st = mzgpu_buf_clear(q->stream_buf);
+    active[path] = !(q->static_rel[q->plan.source[path]] && q->stepping);
+    st = mzgpu_buf_clear(q->pstream[path]);
     // as_of rule: only the first relation's path sees the updates at as_of (= 0)
-    if (st == MZGPU_OK)
+    if (st == MZGPU_OK && active[path])
       st = mzgpu_update_stream(q->ctx, batch[q->plan.source[path]], &q->plan.initial[path],
-                               path == 0 ? MZGPU_FRONTIER_EMPTY : 0, q->stream_buf);
-    for (int s = 0; s < 2 && st == MZGPU_OK; ++s) {
-      if (q->peers > 1) {  // half_join exchanges its stream by key
-        st = mzgpu_exchange(q->ctx, q->stream_buf, q->xchg);
-        std::swap(q->stream_buf, q->xchg);
-        if (st != MZGPU_OK) break;
-      }
-      st = mzgpu_buf_clear(q->next_buf);
-      if (st == MZGPU_OK)
-        st = mzgpu_half_join_buf(q->ctx, q->stream_buf, q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                                 &q->plan.stage[path][s], 0, q->next_buf);
-      std::swap(q->stream_buf, q->next_buf);
-    }
-    if (st == MZGPU_OK) st = mzgpu_buf_append_buf(q->results, q->stream_buf);
+                               path == 0 ? MZGPU_FRONTIER_EMPTY : 0, q->pstream[path]);
   }
+  for (int s = 0; s < 2 && st == MZGPU_OK; ++s) {
+    if (q->peers > 1) {  // half_join exchanges its stream by key
+      mzgpu_buf *ins[3], *outs[3];
+      uint32_t k = 0;
+      for (int path = 0; path < 3; ++path)
+        if (active[path]) {
+          ins[k] = q->pstream[path];
+          outs[k] = q->pxchg[path];
+          ++k;
+        }
+      st = mzgpu_exchange_many(q->ctx, k, ins, outs);
+      for (int path = 0; path < 3; ++path)
+        if (active[path]) std::swap(q->pstream[path], q->pxchg[path]);
+    }
+    for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
+      if (!active[path]) continue;
+      st = mzgpu_buf_clear(q->pnext[path]);
+      if (st == MZGPU_OK)
+        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
+                                 &q->plan.stage[path][s], 0, q->pnext[path]);
+      std::swap(q->pstream[path], q->pnext[path]);
+    }
+  }
+  for (int path = 0; path < 3 && st == MZGPU_OK; ++path)
+    if (active[path]) st = mzgpu_buf_append_buf(q->results, q->pstream[path]);
   if (st == MZGPU_OK && q->peers > 1) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);
     std::swap(q->results, q->xchg);
@@ -248,8 +271,12 @@ int32_t mzh_q3_new(mzgpu_ctx* ctx, uint64_t seed, uint64_t n_customer, uint64_t 
     H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->input[a]));
   }
   H_TRY(mzgpu_reduce_new(ctx, MZGPU_AGG_COUNT_SUM_I64, &q->reduce));
-  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->stream_buf));
-  H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->next_buf));
+  for (int p = 0; p < 3; ++p) {
+    H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->pstream[p]));
+    H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->pnext[p]));
+    H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->pxchg[p]));
+  }
+  for (int a = 0; a < 4; ++a) H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->axchg[a]));
   H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->results));
   H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_R32, &q->xchg));
   H_TRY(mzgpu_buf_new(ctx, MZGPU_ROW_ROUT, &q->out));
@@ -264,8 +291,12 @@ void mzh_q3_free(mzh_q3* q) {
     mzgpu_buf_free(q->input[a]);
   }
   mzgpu_reduce_free(q->reduce);
-  mzgpu_buf_free(q->stream_buf);
-  mzgpu_buf_free(q->next_buf);
+  for (int p = 0; p < 3; ++p) {
+    mzgpu_buf_free(q->pstream[p]);
+    mzgpu_buf_free(q->pnext[p]);
+    mzgpu_buf_free(q->pxchg[p]);
+  }
+  for (int a = 0; a < 4; ++a) mzgpu_buf_free(q->axchg[a]);
   mzgpu_buf_free(q->results);
   mzgpu_buf_free(q->xchg);
   mzgpu_buf_free(q->out);
@@ -364,8 +395,24 @@ int32_t mzh_q3_staged(mzh_q3* q, int32_t a, mzgpu_r32* rows, uint64_t cap, uint6
 int32_t mzh_q3_step(mzh_q3* q) {
   if (q == nullptr) return MZGPU_E_INVALID;
   H_TRY(q3_maintenance(q));
+  q->stepping = true;
   const uint64_t t = q->next_time;
-  for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
+  if (q->peers > 1) {
+    // the arrangement inputs of one timestamp share one exchange round
+    mzgpu_buf *ins[4], *outs[4];
+    uint32_t k = 0;
+    for (int a = 0; a < 4; ++a)
+      if (!q->static_rel[a]) {
+        ins[k] = q->input[a];
+        outs[k] = q->axchg[a];
+        ++k;
+      }
+    H_TRY(mzgpu_exchange_many(q->ctx, k, ins, outs));
+    for (int a = 0; a < 4; ++a)
+      if (!q->static_rel[a]) H_TRY(mzgpu_batcher_push_buf(q->batcher[a], q->axchg[a]));
+  } else {
+    for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
+  }
   H_TRY(q3_run_timestamp(q, t));
   q->next_time = t + 1;
   return MZGPU_OK;

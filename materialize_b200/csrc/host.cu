@@ -32,6 +32,7 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 128 * 8));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 128 * 8));
+  MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_big, 4096));
   // device-resident counters, look-back state, tile tickets, fused control blocks
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_cnt, (size_t)MZ_CNT_BLOCKS * 32));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_cnt, (size_t)MZ_CNT_BLOCKS * 32));
@@ -78,6 +79,7 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
     if (f) f(ctx->nccl_comm);
   }
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  if (ctx->h_big) cudaFreeHost(ctx->h_big);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   if (ctx->d_cnt) cudaFree(ctx->d_cnt);
   if (ctx->d_lb) cudaFree(ctx->d_lb);
@@ -1825,39 +1827,47 @@ extern "C" int32_t mzgpu_comm_init(mzgpu_ctx* ctx, const uint8_t id[MZGPU_COMM_I
   return MZGPU_OK;
 }
 
-extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out) {
+// k independent exchanges in one round: one partition per buffer, ONE counts
+// all-to-all, ONE host wait (NCCL message sizes are host arguments), ONE payload
+// all-to-all.  All peers must call with the same k (identical dataflows).
+#define MZ_MAX_EXCHANGE 8
+extern "C" int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs) {
   MZ_CHECK_CTX(ctx);
-  if (in == nullptr || out == nullptr || in->rb != out->rb || in == out) return MZGPU_E_INVALID;
+  if (k == 0) return MZGPU_OK;
+  if (ins == nullptr || outs == nullptr || k > MZ_MAX_EXCHANGE) return MZGPU_E_INVALID;
+  for (uint32_t e = 0; e < k; ++e)
+    if (ins[e] == nullptr || outs[e] == nullptr || ins[e]->rb != outs[e]->rb || ins[e] == outs[e])
+      return MZGPU_E_INVALID;
   const u32 P = (u32)ctx->peers;
   if (P == 1) {
-    buf_set_len(out, 0);
-    return buf_append_dev(out, in->mem.p, buf_dlen(in), in->ub);
+    for (uint32_t e = 0; e < k; ++e) {
+      buf_set_len(outs[e], 0);
+      MZ_TRY(buf_append_dev(outs[e], ins[e]->mem.p, buf_dlen(ins[e]), ins[e]->ub));
+    }
+    return MZGPU_OK;
   }
-  MZ_TRY(buf_resolve(in));  // send counts go through the host (NCCL sizes are host arguments)
-  const u64 in_len = in->ub;
   if (ctx->nccl_comm == nullptr) {
     MZ_SET_ERR(ctx, "exchange: mzgpu_comm_init has not been called");
     return MZGPU_E_NCCL;
   }
+  if (P > 16) {
+    MZ_SET_ERR(ctx, "exchange: %u peers exceed the supported maximum 16", P);
+    return MZGPU_E_UNSUPPORTED;
+  }
   typedef int (*grp_t)();
   typedef int (*sr_t)(const void*, size_t, int, int, void*, cudaStream_t);
   typedef int (*rv_t)(void*, size_t, int, int, void*, cudaStream_t);
-  grp_t gstart = (grp_t)dlsym(ctx->nccl_lib, "ncclGroupStart");
-  grp_t gend = (grp_t)dlsym(ctx->nccl_lib, "ncclGroupEnd");
-  sr_t send = (sr_t)dlsym(ctx->nccl_lib, "ncclSend");
-  rv_t recv = (rv_t)dlsym(ctx->nccl_lib, "ncclRecv");
+  static grp_t gstart = nullptr, gend = nullptr;
+  static sr_t send = nullptr;
+  static rv_t recv = nullptr;
+  if (gstart == nullptr) {
+    gstart = (grp_t)dlsym(ctx->nccl_lib, "ncclGroupStart");
+    gend = (grp_t)dlsym(ctx->nccl_lib, "ncclGroupEnd");
+    send = (sr_t)dlsym(ctx->nccl_lib, "ncclSend");
+    recv = (rv_t)dlsym(ctx->nccl_lib, "ncclRecv");
+  }
   if (!gstart || !gend || !send || !recv) return MZGPU_E_NCCL;
   const int NCCL_INT8 = 0, NCCL_UINT64 = 5;
-  // 1. bucket rows by destination
-  DevMem parts;
-  MZ_TRY(parts.alloc(ctx, in_len * in->rb));
-  u64 send_counts[64], recv_counts[64];
-  MZ_TRY(mz_partition(ctx, in->rb, in->mem.p, in_len, P, parts.p, send_counts));
-  // 2. counts all-to-all (P x u64)
-  DevMem d_send, d_recv;
-  MZ_TRY(d_send.alloc(ctx, P * 8));
-  MZ_TRY(d_recv.alloc(ctx, P * 8));
-  MZ_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_counts, P * 8, cudaMemcpyHostToDevice, ctx->stream));
 #define NCCL_TRY(expr)                                        \
   do {                                                        \
     int _rc = (expr);                                         \
@@ -1867,34 +1877,65 @@ extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out)
       return MZGPU_E_NCCL;                                    \
     }                                                         \
   } while (0)
+  // 1. bucket rows by destination: counts and offsets stay on the device.
+  // cnt layout: per exchange e: [e*P, e*P+P) send counts (contiguous over e so one
+  // message per peer carries all k counts after the transpose below), cursors apart.
+  DevMem parts[MZ_MAX_EXCHANGE], cnt;
+  MZ_TRY(cnt.alloc(ctx, (size_t)(4 * MZ_MAX_EXCHANGE * 64) * 8));
+  u64* d_cnt = cnt.as<u64>();                         // [e][64] send counts per exchange
+  u64* d_cur = d_cnt + MZ_MAX_EXCHANGE * 64;          // [e][64] cursors
+  u64* d_sendT = d_cur + MZ_MAX_EXCHANGE * 64;        // [p][k] send counts grouped by peer
+  u64* d_recvT = d_sendT + MZ_MAX_EXCHANGE * 64;      // [p][k] recv counts grouped by peer
+  for (uint32_t e = 0; e < k; ++e) {
+    MZ_TRY(parts[e].alloc(ctx, std::max<u64>(ins[e]->ub, 1) * ins[e]->rb));
+    MZ_TRY(mz_partition(ctx, ins[e]->rb, ins[e]->mem.p, buf_dlen(ins[e]), ins[e]->ub, P, parts[e].p,
+                        d_cnt + e * 64, d_cur + e * 64));
+  }
+  // transpose [e][p] -> [p][e] with k*P tiny copies folded into one 2D copy per exchange
+  for (uint32_t e = 0; e < k; ++e)
+    MZ_CUDA(ctx, cudaMemcpy2DAsync(d_sendT + e, (size_t)k * 8, d_cnt + e * 64, 8, 8, P, cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+  // 2. counts all-to-all: k words per peer
   NCCL_TRY(gstart());
   for (u32 p = 0; p < P; ++p) {
-    NCCL_TRY(send(d_send.as<u64>() + p, 1, NCCL_UINT64, (int)p, ctx->nccl_comm, ctx->stream));
-    NCCL_TRY(recv(d_recv.as<u64>() + p, 1, NCCL_UINT64, (int)p, ctx->nccl_comm, ctx->stream));
+    NCCL_TRY(send(d_sendT + (size_t)p * k, k, NCCL_UINT64, (int)p, ctx->nccl_comm, ctx->stream));
+    NCCL_TRY(recv(d_recvT + (size_t)p * k, k, NCCL_UINT64, (int)p, ctx->nccl_comm, ctx->stream));
   }
   NCCL_TRY(gend());
-  MZ_CUDA(ctx, cudaMemcpyAsync(recv_counts, d_recv.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  u64* h = ctx->h_big;  // pinned, 2 * 16 * MZ_MAX_EXCHANGE words
+  MZ_CUDA(ctx, cudaMemcpyAsync(h, d_sendT, (size_t)P * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MZ_CUDA(ctx, cudaMemcpyAsync(h + 16 * MZ_MAX_EXCHANGE, d_recvT, (size_t)P * k * 8, cudaMemcpyDeviceToHost,
+                               ctx->stream));
   MZ_SYNC(ctx);
+  ctx->stats.d2h_bytes += 2 * (size_t)P * k * 8;
+  const u64* hs = h;
+  const u64* hr = h + 16 * MZ_MAX_EXCHANGE;
   // 3. payload all-to-all
-  u64 total = 0;
-  for (u32 p = 0; p < P; ++p) total += recv_counts[p];
-  buf_set_len(out, 0);
-  MZ_TRY(buf_reserve(out, total, false));
+  u64 totals[MZ_MAX_EXCHANGE];
+  for (uint32_t e = 0; e < k; ++e) {
+    totals[e] = 0;
+    for (u32 p = 0; p < P; ++p) totals[e] += hr[(size_t)p * k + e];
+    buf_set_len(outs[e], 0);
+    MZ_TRY(buf_reserve(outs[e], totals[e], false));
+  }
   NCCL_TRY(gstart());
-  u64 soff = 0, roff = 0;
-  for (u32 p = 0; p < P; ++p) {
-    if (send_counts[p])
-      NCCL_TRY(send((const char*)parts.p + soff * in->rb, send_counts[p] * in->rb, NCCL_INT8, (int)p,
-                    ctx->nccl_comm, ctx->stream));
-    if (recv_counts[p])
-      NCCL_TRY(recv((char*)out->mem.p + roff * in->rb, recv_counts[p] * in->rb, NCCL_INT8, (int)p,
-                    ctx->nccl_comm, ctx->stream));
-    soff += send_counts[p];
-    roff += recv_counts[p];
+  for (uint32_t e = 0; e < k; ++e) {
+    const u64 rb = ins[e]->rb;
+    u64 soff = 0, roff = 0;
+    for (u32 p = 0; p < P; ++p) {
+      const u64 sc = hs[(size_t)p * k + e], rc = hr[(size_t)p * k + e];
+      if (sc) NCCL_TRY(send((const char*)parts[e].p + soff * rb, sc * rb, NCCL_INT8, (int)p, ctx->nccl_comm, ctx->stream));
+      if (rc) NCCL_TRY(recv((char*)outs[e]->mem.p + roff * rb, rc * rb, NCCL_INT8, (int)p, ctx->nccl_comm, ctx->stream));
+      soff += sc;
+      roff += rc;
+    }
   }
   NCCL_TRY(gend());
-  buf_set_len(out, total);
-  // `parts` is freed stream-ordered after the sends
+  for (uint32_t e = 0; e < k; ++e) buf_set_len(outs[e], totals[e]);
+  // `parts` are freed stream-ordered after the sends
   return MZGPU_OK;
 #undef NCCL_TRY
+}
+extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out) {
+  return mzgpu_exchange_many(ctx, 1, &in, &out);
 }
