@@ -29,8 +29,10 @@ from .api import (  # noqa: F401
     ReduceAccumulable,
     Spine,
     half_join,
+    half_join_dev,
     make_closure,
     map_rows,
     route,
     update_stream,
+    update_stream_dev,
 )

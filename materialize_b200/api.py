@@ -161,6 +161,11 @@ class DeviceRows:
         self.ctx.check(F.lib.mzgpu_buf_download(self.h, _ptr(out), n, F.MEM_HOST, C.byref(got)))
         return out
 
+    def append_buf(self, other):
+        """Append another device buffer's rows without reading its length back."""
+        self.ctx.check(F.lib.mzgpu_buf_append_buf(self.h, other.h))
+        return self
+
     def device_ptr(self):
         return F.lib.mzgpu_buf_device_ptr(self.h)
 
@@ -235,6 +240,16 @@ class Batcher:
 
     def push_device(self, dev_rows):
         self.ctx.check(F.lib.mzgpu_batcher_push(self.h, dev_rows.device_ptr(), len(dev_rows), F.MEM_DEVICE))
+
+    def push_buf(self, dev_rows):
+        """push_container for rows in a device buffer; its length is not read back."""
+        self.ctx.check(F.lib.mzgpu_batcher_push_buf(self.h, dev_rows.h))
+
+    def seal_lazy(self, upper):
+        """seal without asking for the new frontier: nothing returns to the host."""
+        h = C.c_void_p()
+        self.ctx.check(F.lib.mzgpu_batcher_seal(self.h, upper, C.byref(h), None))
+        return Batch(self.ctx, h, self.row_bytes)
 
     def seal(self, upper):
         h = C.c_void_p()
@@ -356,6 +371,19 @@ def half_join(ctx, stream, trace, cmp_mode, closure=None, consolidate_output=Tru
     return out.download()
 
 
+def half_join_dev(ctx, dev_stream, trace, cmp_mode, closure=None, consolidate_output=False, out=None):
+    """half_join over a device-resident stream; the result stays on the device (no read-back)."""
+    out = out if out is not None else DeviceRows(ctx, 32)
+    ctx.check(F.lib.mzgpu_half_join_buf(ctx.h, dev_stream.h, trace.h, cmp_mode, _clp(closure), 1 if consolidate_output else 0, out.h))
+    return out
+
+
+def update_stream_dev(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY, out=None):
+    out = out if out is not None else DeviceRows(ctx, 32)
+    ctx.check(F.lib.mzgpu_update_stream(ctx.h, batch.h, _clp(closure), skip_time, out.h))
+    return out
+
+
 def update_stream(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY):
     out = DeviceRows(ctx, 32)
     ctx.check(F.lib.mzgpu_update_stream(ctx.h, batch.h, _clp(closure), skip_time, out.h))
@@ -381,6 +409,12 @@ class ReduceAccumulable:
         out = DeviceRows(self.ctx, 64)
         self.ctx.check(F.lib.mzgpu_reduce_accumulable(self.h, _ptr(rows), len(rows), F.MEM_HOST, upper, out.h))
         return out.download()
+
+    def step_dev(self, dev_rows, upper, out=None):
+        """One activation over device-resident rows; corrections are appended to `out` on the device."""
+        out = out if out is not None else DeviceRows(self.ctx, 64)
+        self.ctx.check(F.lib.mzgpu_reduce_accumulable_buf(self.h, dev_rows.h, upper, out.h))
+        return out
 
     def input_trace(self):
         return Spine(self.ctx, 80, _borrowed=F.lib.mzgpu_reduce_input_trace(self.h))

@@ -134,6 +134,7 @@ struct MsdSmem {
   u64 hi[MSD_LOCAL_MAX];
   u32 idx[MSD_LOCAL_MAX];
   u64 sum[MSD_LOCAL_MAX];  // one-word diff sums per segment of the bucket
+  u64 sum8[256][8];        // accumulable diffs (8 words): buckets of at most 256 rows
 };
 struct MsdScan {  // phase "scatter": bucket bases
   u32 base[MSD_MAX_BUCKETS + 1];
@@ -219,7 +220,6 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       a.lb_keep[i] = 0;
     }
     for (u64 i = gtid; i < T * 256; i += gstride) a.state0[i] = 0;
-    for (u64 i = gtid; i < n * ND; i += gstride) a.seg_sums[i] = 0;
     if (a.table != nullptr)
       for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
     u64 mn[NK], mx[NK];
@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       if (tid == 0) sm.scan.base[NB] = total;
       __syncthreads();
     }
-    if (s_max_bucket <= MSD_LOCAL_MAX) {
+    constexpr u32 LOCAL_MAX = ND == 8 ? 256u : MSD_LOCAL_MAX;
+    if (s_max_bucket <= LOCAL_MAX) {
       for (u64 i = gtid; i < n; i += gstride) {
         const u64 p = (u64)sm.scan.base[a.v1[i]] + a.v0[i];
         a.m_lo[p] = a.k0[i];
@@ -404,6 +405,10 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
             sm.msd.idx[j] = 0xffffffffu;
           }
           sm.msd.sum[j] = 0;
+          if (ND == 8 && j < 256) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sm.msd.sum8[j][w] = 0;
+          }
         }
         __syncthreads();
         // bitonic sort of P elements by (hi, lo, idx); padding (all ones) sorts last
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
           const u32 nxt = __shfl_down_sync(0xffffffffu, seg, 1);
           if (valid && (lane == 31 || nxt != seg)) {
             if (ND == 8) {
-              u64* acc = a.seg_sums + ((u64)gbase + seg) * ND;
+              u64* acc = &sm.msd.sum8[seg][0];
               if (d[0]) atomicAdd((unsigned long long*)&acc[0], (unsigned long long)d[0]);
               if (d[1]) atomicAdd((unsigned long long*)&acc[1], (unsigned long long)d[1]);
               u64 old = atomicAdd((unsigned long long*)&acc[2], (unsigned long long)d[2]);
@@ -478,7 +483,6 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
           }
           nseg += total;
         }
-        if (ND == 8) __threadfence();
         __syncthreads();
         // pass 2 (run twice: count, then write after the bucket-ordered look-back):
         // the head row of every surviving segment goes to `out` (time < upper) or `keep`
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
               u64 d[ND];
               if (ND == 8) {
 #pragma unroll
-                for (int w = 0; w < ND; ++w) d[w] = *(volatile u64*)&a.seg_sums[((u64)gbase + seg) * ND + w];
+                for (int w = 0; w < ND; ++w) d[w] = sm.msd.sum8[seg][w & 7];
               } else {
                 d[0] = sm.msd.sum[seg];
 #pragma unroll
@@ -561,6 +565,9 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       if (p[k] != p[k - NW]) return 1u;
     return 0u;
   };
+  // the sort / merge paths accumulate segment sums in global memory (used several
+  // grid barriers from here)
+  for (u64 i = gtid; i < n * ND; i += gstride) a.seg_sums[i] = 0;
   if (!a.merge) {
   // ---- radix rounds.  (kin, vin) holds the current order; round r packs into the
   // other pair (reading the order of round r-1) and sorts that.

@@ -124,6 +124,17 @@ struct mzh_q3 {
   uint64_t next_time = 0;
   uint64_t last_rows_in = 0;
   uint64_t maintain_upper = 0;  // timestamp whose maintenance is still due
+  uint64_t h2d_bytes = 0;       // host rows staged through mzh_q3_stage_host
+  // end-to-end path: host batches land in double-buffered device staging through a
+  // copy stream, so the H2D copy of the next batch overlaps the current timestamp
+  cudaStream_t copy_stream = nullptr;
+  DevArr stage[2][4];
+  uint64_t stage_cap[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  uint64_t stage_n[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool slot_full[2] = {false, false};
+  bool slot_touched[2][4] = {{false, false, false, false}, {false, false, false, false}};
+  int fill_slot = 0, run_slot = 0;
   bool static_rel[4] = {true, false, false, false};  // relations the generator never updates after hydration
   bool stepping = false;                             // false while hydrating
 };
@@ -285,6 +296,14 @@ int32_t mzh_q3_new(mzgpu_ctx* ctx, uint64_t seed, uint64_t n_customer, uint64_t 
 
 void mzh_q3_free(mzh_q3* q) {
   if (q == nullptr) return;
+  if (q->copy_stream) {
+    cudaStreamSynchronize(q->copy_stream);
+    cudaStreamDestroy(q->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(q->ev_up[i]);
+      cudaEventDestroy(q->ev_free[i]);
+    }
+  }
   for (int a = 0; a < 4; ++a) {
     mzgpu_batcher_free(q->batcher[a]);
     mzgpu_spine_free(q->spine[a]);
@@ -368,12 +387,50 @@ int32_t mzh_q3_stage_batch(mzh_q3* q, uint64_t b, uint64_t t, uint64_t* rows_in)
   return mzgpu_ctx_sync(q->ctx);
 }
 
-// Stage host rows for arrangement `a` (the end-to-end path: the H2D copy is
-// issued here, on the ctx stream, inside the caller's timed region).
+// Stage host rows for arrangement `a` of the NEXT timestamp (the end-to-end path:
+// the H2D copy is issued here, inside the caller's timed region, on a copy stream
+// into the staging slot the next mzh_q3_step consumes; call mzh_q3_stage_commit
+// after the last arrangement of the batch).
 int32_t mzh_q3_stage_host(mzh_q3* q, int32_t a, const mzgpu_r32* rows, uint64_t n) {
   if (q == nullptr || a < 0 || a > 3) return MZGPU_E_INVALID;
-  return mzgpu_buf_upload(q->input[a], rows, n, MZGPU_MEM_HOST);
+  const int s = q->fill_slot;
+  if (q->copy_stream == nullptr) {
+    H_CUDA(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      H_CUDA(cudaEventCreateWithFlags(&q->ev_up[i], cudaEventDisableTiming));
+      H_CUDA(cudaEventCreateWithFlags(&q->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  if (q->slot_full[s]) return MZGPU_E_INVALID;  // both slots staged and not yet stepped
+  bool any = false;
+  for (int i = 0; i < 4; ++i) any = any || q->slot_touched[s][i];
+  if (!any) {
+    // first arrangement of this batch: the slot's previous contents must have been consumed
+    H_CUDA(cudaStreamWaitEvent(q->copy_stream, q->ev_free[s], 0));
+    for (int i = 0; i < 4; ++i) q->stage_n[s][i] = 0;
+  }
+  if (n > q->stage_cap[s][a]) {
+    H_CUDA(cudaStreamSynchronize(q->stream));  // growing: rare, after the first batches never
+    if (q->stage[s][a].alloc(n * 32 * 5 / 4)) return MZGPU_E_CUDA;
+    q->stage_cap[s][a] = n * 5 / 4;
+  }
+  if (n) H_CUDA(cudaMemcpyAsync(q->stage[s][a].p, rows, n * 32, cudaMemcpyHostToDevice, q->copy_stream));
+  q->stage_n[s][a] = n;
+  q->slot_touched[s][a] = true;
+  q->h2d_bytes += n * 32;
+  return MZGPU_OK;
 }
+// The batch staged with mzh_q3_stage_host is complete.
+int32_t mzh_q3_stage_commit(mzh_q3* q) {
+  if (q == nullptr || q->copy_stream == nullptr) return MZGPU_E_INVALID;
+  const int s = q->fill_slot;
+  H_CUDA(cudaEventRecord(q->ev_up[s], q->copy_stream));
+  q->slot_full[s] = true;
+  for (int i = 0; i < 4; ++i) q->slot_touched[s][i] = false;
+  q->fill_slot ^= 1;
+  return MZGPU_OK;
+}
+uint64_t mzh_q3_h2d_bytes(mzh_q3* q) { return q ? q->h2d_bytes : 0; }
 
 // Stage rows that already live in device memory (a D2D copy on the ctx stream).
 int32_t mzh_q3_stage_device(mzh_q3* q, int32_t a, const mzgpu_r32* d_rows, uint64_t n) {
@@ -396,6 +453,17 @@ int32_t mzh_q3_step(mzh_q3* q) {
   if (q == nullptr) return MZGPU_E_INVALID;
   H_TRY(q3_maintenance(q));
   q->stepping = true;
+  if (q->slot_full[q->run_slot]) {
+    // a committed host batch: the ctx stream waits for its H2D copies, takes the
+    // rows over (device copies), and frees the slot for the batch after next
+    const int s = q->run_slot;
+    H_CUDA(cudaStreamWaitEvent(q->stream, q->ev_up[s], 0));
+    for (int a = 0; a < 4; ++a)
+      H_TRY(mzgpu_buf_upload(q->input[a], q->stage[s][a].p, q->stage_n[s][a], MZGPU_MEM_DEVICE));
+    H_CUDA(cudaEventRecord(q->ev_free[s], q->stream));
+    q->slot_full[s] = false;
+    q->run_slot ^= 1;
+  }
   const uint64_t t = q->next_time;
   if (q->peers > 1) {
     // the arrangement inputs of one timestamp share one exchange round

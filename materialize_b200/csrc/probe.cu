@@ -23,28 +23,46 @@ constexpr int PT = 256;
 
 // visit every (val2, time2, diff2) of `key` in the trace that passes the time
 // filter; F(v2, t2, d2)
-template <class F>
+template <int GROUP, class F>
 __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64 t1, int mode, F f) {
   const u64 h0 = mix64(key);
-  for (u32 b = 0; b < tv.n_batches; ++b) {
-    const BatchView& bv = tv.b[b];
-    const u64 mask = bv_mask(bv);
-    u64 h = h0 & mask;
-    while (true) {
-      const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
-      if (slot.y == 0) break;
-      if (slot.x == key) {
-        const u64 bn = bv_n(bv);
-        for (u64 j = slot.y - 1; j < bn; ++j) {
-          const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4);
-          if (kv.x != key) break;
-          const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + j * 4 + 2);
-          bool ok = mode == MZ_PROBE_HALF_LE ? td.x <= t1 : (mode == MZ_PROBE_HALF_LT ? td.x < t1 : true);
-          if (ok) f(kv.y, td.x, (i64)td.y);
-        }
-        break;
+  // The first slot of several batches is fetched before any of them is looked at:
+  // the loads are independent, so a probe against a trace of many batches costs
+  // about one memory latency per group instead of one per batch.
+  for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
+    ulonglong2 slot[GROUP];
+    u64 hh[GROUP], mask[GROUP];
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      if (b0 + j < tv.n_batches) {
+        const BatchView& bv = tv.b[b0 + j];
+        mask[j] = bv_mask(bv);
+        hh[j] = h0 & mask[j];
+        slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
       }
-      h = (h + 1) & mask;
+    }
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      if (b0 + j >= tv.n_batches) break;
+      const BatchView& bv = tv.b[b0 + j];
+      ulonglong2 sl = slot[j];
+      u64 h = hh[j];
+      while (true) {
+        if (sl.y == 0) break;
+        if (sl.x == key) {
+          const u64 bn = bv_n(bv);
+          for (u64 r = sl.y - 1; r < bn; ++r) {
+            const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+            if (kv.x != key) break;
+            const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+            bool ok = mode == MZ_PROBE_HALF_LE ? td.x <= t1 : (mode == MZ_PROBE_HALF_LT ? td.x < t1 : true);
+            if (ok) f(kv.y, td.x, (i64)td.y);
+          }
+          break;
+        }
+        h = (h + 1) & mask[j];
+        sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      }
     }
   }
 }
@@ -55,7 +73,7 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // two-pass order (stream order x batch order x row order) and nothing returns
 // to the host.
 template <int OUT_NW>
-__global__ void __launch_bounds__(PT) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+__global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
@@ -83,7 +101,7 @@ __global__ void __launch_bounds__(PT) k_probe_lb(const u64* __restrict__ stream,
       v1 = kv.y;
       t1 = td.x;
       d1 = (i64)td.y;
-      for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+      for_each_match<4>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
         if (pp.has_closure) {
           u64 k, v;
           if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
@@ -100,7 +118,7 @@ __global__ void __launch_bounds__(PT) k_probe_lb(const u64* __restrict__ stream,
       if (pos + cnt > out_cap) {
         atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
       } else {
-        for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+        for_each_match<4>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
           u64 t = t1;
           if (pp.mode == MZ_PROBE_JOIN) {
             t = t1 > t2 ? t1 : t2;
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(PT) k_probe(const u64* __restrict__ stream, u6
     v1 = kv.y;
     t1 = td.x;
     d1 = (i64)td.y;
-    for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+    for_each_match<1>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
       if (pp.has_closure) {
         u64 k, v;
         if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(PT) k_probe(const u64* __restrict__ stream, u6
   }
   if (i < n && cnt > 0) {
     u64 pos = (u64)tile_base[blockIdx.x] + ex;
-    for_each_match(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
+    for_each_match<1>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
       u64 t = t1;
       if (pp.mode == MZ_PROBE_JOIN) {
         t = t1 > t2 ? t1 : t2;

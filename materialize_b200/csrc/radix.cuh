@@ -10,11 +10,11 @@ constexpr u32 RS_FLAG_PARTIAL = 1u << 30;
 constexpr u32 RS_FLAG_INCLUSIVE = 2u << 30;
 constexpr u32 RS_VALUE_MASK = (1u << 30) - 1;
 
-template <int ITEMS>
+template <int ITEMS, int THREADS = RS_THREADS>
 struct RsSmemT {
-  u64 keys[RS_THREADS * ITEMS];
-  u32 vals[RS_THREADS * ITEMS];
-  u32 whist[RS_WARPS][256];
+  u64 keys[THREADS * ITEMS];
+  u32 vals[THREADS * ITEMS];
+  u32 whist[THREADS / 32][256];
   u32 digit_start[256];
   u32 gofs[256];
   u32 scan[34];
@@ -27,14 +27,15 @@ struct RsSmemT {
 // is being processed by a co-resident CTA (look-back progress); tile_state is
 // zero before the pass.  No __restrict__ here: inside the fused kernel the
 // input of one pass was written by other CTAs in the previous phase.  Ends with a __syncthreads(): `s` can be reused.
-template <int ITEMS>
-__device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS>& s, u32 tile, const u64* kin,
+template <int ITEMS, int THREADS = RS_THREADS>
+__device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 tile, const u64* kin,
                                              const u32* vin, u64* kout,
                                              u32* vout, u64 n, int shift,
                                              const u32* gbase, u32* tile_state) {
-  constexpr u32 TILE = RS_THREADS * ITEMS;
+  constexpr u32 TILE = THREADS * ITEMS;
+  constexpr int WARPS = THREADS / 32;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.whist[0][0])[i] = 0;
+  for (int i = tid; i < WARPS * 256; i += THREADS) (&s.whist[0][0])[i] = 0;
   __syncthreads();
   const u64 base = (u64)tile * TILE;
   const u32 n_valid = (u32)((n - base) < (u64)TILE ? (n - base) : (u64)TILE);
@@ -70,11 +71,11 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS>& s, u32 tile, const 
   __syncthreads();
 
   // thread d owns digit d: exclusive scan across warps, then the look-back
-  {
+  if (THREADS == 256 || tid < 256) {
     const u32 d = tid;
     u32 tot = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
       u32 c = s.whist[w][d];
       s.whist[w][d] = tot;
       tot += c;
@@ -98,10 +99,19 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS>& s, u32 tile, const 
       }
       st[(u64)tile * 256 + d] = RS_FLAG_INCLUSIVE | ((excl + tot_valid) & RS_VALUE_MASK);
     }
+    s.digit_start[d] = tot;              // digit totals; scanned below
+    s.gofs[d] = gbase[d] + excl;          // finished below: minus the digit's tile-local start
+  }
+  __syncthreads();
+  {
+    // exclusive scan of the 256 digit totals (every thread of the CTA takes part in the barriers)
+    u32 v = tid < 256 ? s.digit_start[tid] : 0;
     u32 total;
-    u32 ds = block_exclusive_scan(tot, s.scan, &total);
-    s.digit_start[d] = ds;
-    s.gofs[d] = gbase[d] + excl - ds;  // global position = gofs[d] + local position
+    u32 ds = block_exclusive_scan(v, s.scan, &total);
+    if (tid < 256) {
+      s.digit_start[tid] = ds;
+      s.gofs[tid] -= ds;  // global position = gofs[d] + local position
+    }
   }
   __syncthreads();
 
@@ -115,7 +125,7 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS>& s, u32 tile, const 
   }
   __syncthreads();
   // coalesced runs per digit
-  for (u32 i = tid; i < n_valid; i += RS_THREADS) {
+  for (u32 i = tid; i < n_valid; i += THREADS) {
     u64 k = s.keys[i];
     u32 d = (u32)((k >> shift) & 255);
     u32 g = s.gofs[d] + i;

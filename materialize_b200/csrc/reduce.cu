@@ -170,29 +170,46 @@ __device__ __forceinline__ void finalize(const u64* S, int agg_kind, u64* o /* c
   o[3] = flags;
 }
 
-// sum of all prior updates of `key` (times before the new batch)
+// sum of all prior updates of `key` (times before the new batch).  The first hash
+// slot of GROUP batches is fetched before any is inspected (independent loads).
 __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) {
   const u64 h0 = mix64(key);
-  for (u32 b = 0; b < tv.n_batches; ++b) {
-    const BatchView& bv = tv.b[b];
-    const u64 mask = bv_mask(bv);
-    u64 h = h0 & mask;
-    while (true) {
-      const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
-      if (slot.y == 0) break;
-      if (slot.x == key) {
-        const u64 bn = bv_n(bv);
-        for (u64 j = slot.y - 1; j < bn; ++j) {
-          const u64* row = bv.rows + j * 10;
-          if (row[0] != key) break;
-          u64 d[8];
+  constexpr int GROUP = 4;
+  for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
+    ulonglong2 slot[GROUP];
+    u64 hh[GROUP], mask[GROUP];
 #pragma unroll
-          for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
-          diff_add<8>(S, d);
-        }
-        break;
+    for (int j = 0; j < GROUP; ++j) {
+      if (b0 + j < tv.n_batches) {
+        const BatchView& bv = tv.b[b0 + j];
+        mask[j] = bv_mask(bv);
+        hh[j] = h0 & mask[j];
+        slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
       }
-      h = (h + 1) & mask;
+    }
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      if (b0 + j >= tv.n_batches) break;
+      const BatchView& bv = tv.b[b0 + j];
+      ulonglong2 sl = slot[j];
+      u64 h = hh[j];
+      while (true) {
+        if (sl.y == 0) break;
+        if (sl.x == key) {
+          const u64 bn = bv_n(bv);
+          for (u64 r = sl.y - 1; r < bn; ++r) {
+            const u64* row = bv.rows + r * 10;
+            if (row[0] != key) break;
+            u64 d[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) d[w] = row[2 + w];
+            diff_add<8>(S, d);
+          }
+          break;
+        }
+        h = (h + 1) & mask[j];
+        sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      }
     }
   }
 }

@@ -24,8 +24,11 @@
 
 namespace {
 
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+// tile shape variants of the pass kernel (MZGPU_RS_VARIANT selects; default 0)
+struct RsVariant {
+  int items, threads;
+};
+static const RsVariant RS_VARIANTS[] = {{16, 256}, {16, 512}, {24, 256}, {12, 512}, {20, 384}};
 
 struct ChunkPlan {
   int nwords;
@@ -126,19 +129,41 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(u32* __restrict__ ghist, i
 }
 
 // ------------------------------------------------------------ onesweep pass
-typedef RsSmemT<RS_ITEMS> RsSmem;
-
-__global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(
+template <int ITEMS, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_rs_onesweep(
     const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
     u32* __restrict__ vout, u64 n, int shift, const u32* __restrict__ gbase,
     u32* __restrict__ tile_state, u32* __restrict__ tile_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RsSmem& s = *reinterpret_cast<RsSmem*>(smem_raw);
+  typedef RsSmemT<ITEMS, THREADS> Smem;
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   // dynamic tile assignment: tile t only starts after tiles < t have started,
   // which is what makes the look-back deadlock-free
   if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
-  rs_tile_pass<RS_ITEMS>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
+  rs_tile_pass<ITEMS, THREADS>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
+}
+
+template <int ITEMS, int THREADS>
+static int32_t launch_onesweep(mzgpu_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u64 n,
+                               int shift, const u32* gbase, u32* state, u32* counter) {
+  typedef RsSmemT<ITEMS, THREADS> Smem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MZ_CUDA(ctx, cudaFuncSetAttribute(k_rs_onesweep<ITEMS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(Smem)));
+    attr_set = true;
+  }
+  const u64 n_tiles = (n + (u64)ITEMS * THREADS - 1) / ((u64)ITEMS * THREADS);
+  MZ_BYTES(ctx, n * 24);  // read key+idx (12 B), write key+idx (12 B)
+  {
+    ProfScope _prof(ctx, "k_rs_onesweep");
+    k_rs_onesweep<ITEMS, THREADS><<<(unsigned)n_tiles, THREADS, sizeof(Smem), ctx->stream>>>(
+        kin, vin, kout, vout, n, shift, gbase, state, counter);
+  }
+  ctx->stats.kernel_launches++;
+  MZ_CUDA(ctx, cudaGetLastError());
+  return MZGPU_OK;
 }
 
 static int bit_width_u64(u64 x) {
@@ -158,7 +183,14 @@ int32_t radix_sort_pairs(mzgpu_ctx* ctx, u64* ka, u32* va, u64* kb, u32* vb, u64
   *k_res = ka;
   *v_res = va;
   if (npass == 0 || n <= 1) return MZGPU_OK;
-  const u64 n_tiles = (n + RS_TILE - 1) / RS_TILE;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("MZGPU_RS_VARIANT");
+    variant = e ? atoi(e) : 0;
+    if (variant < 0 || variant >= (int)(sizeof(RS_VARIANTS) / sizeof(RS_VARIANTS[0]))) variant = 0;
+  }
+  const u64 tile = (u64)RS_VARIANTS[variant].items * RS_VARIANTS[variant].threads;
+  const u64 n_tiles = (n + tile - 1) / tile;
   DevMem hist, state, counters;
   MZ_TRY(hist.alloc(ctx, (size_t)npass * 256 * 4));
   MZ_TRY(state.alloc(ctx, (size_t)npass * n_tiles * 256 * 4));
@@ -174,19 +206,19 @@ int32_t radix_sort_pairs(mzgpu_ctx* ctx, u64* ka, u32* va, u64* kb, u32* vb, u64
     MZ_LAUNCH(ctx, k_rs_hist, (unsigned)blocks, 256, 0, ka, n, npass, hist.as<u32>());
     MZ_LAUNCH(ctx, k_rs_scan_hist, 1, 256, 0, hist.as<u32>(), npass);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MZ_CUDA(ctx, cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(RsSmem)));
-    attr_set = true;
-  }
   u64 *kin = ka, *kout = kb;
   u32 *vin = va, *vout = vb;
   for (int p = 0; p < npass; ++p) {
-    MZ_BYTES(ctx, n * 24);  // read key+idx (12 B), write key+idx (12 B)
-    MZ_LAUNCH(ctx, k_rs_onesweep, (unsigned)n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
-              n, 8 * p, hist.as<u32>() + p * 256, state.as<u32>() + (size_t)p * n_tiles * 256,
-              counters.as<u32>() + p);
+    const u32* gb = hist.as<u32>() + p * 256;
+    u32* stp = state.as<u32>() + (size_t)p * n_tiles * 256;
+    u32* cnt = counters.as<u32>() + p;
+    switch (variant) {
+      case 1: MZ_TRY((launch_onesweep<16, 512>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 2: MZ_TRY((launch_onesweep<24, 256>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 3: MZ_TRY((launch_onesweep<12, 512>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 4: MZ_TRY((launch_onesweep<20, 384>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      default: MZ_TRY((launch_onesweep<16, 256>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+    }
     std::swap(kin, kout);
     std::swap(vin, vout);
   }

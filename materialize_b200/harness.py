@@ -18,6 +18,9 @@ _SIG = {
     "mzh_q3_stage_batch": (i32, [vp, u64, u64, C.POINTER(u64)]),
     "mzh_q3_stage_host": (i32, [vp, i32, vp, u64]),
     "mzh_q3_stage_device": (i32, [vp, i32, vp, u64]),
+    "mzh_q3_stage_commit": (i32, [vp]),
+    "mzh_q3_h2d_bytes": (u64, [vp]),
+    "mzh_q3_maintain": (i32, [vp]),
     "mzh_q3_input": (vp, [vp, i32]),
     "mzh_q3_staged": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_step": (i32, [vp]),
@@ -55,6 +58,16 @@ class Q3Dataflow:
 
     def stage_host(self, a, rows):
         self.ctx.check(_lib.mzh_q3_stage_host(self.h, a, rows.ctypes.data_as(vp), len(rows)))
+
+    def stage_commit(self):
+        """The host batch staged with stage_host() is complete (the next step() consumes it)."""
+        self.ctx.check(_lib.mzh_q3_stage_commit(self.h))
+
+    def h2d_bytes(self):
+        return _lib.mzh_q3_h2d_bytes(self.h)
+
+    def maintain(self):
+        self.ctx.check(_lib.mzh_q3_maintain(self.h))
 
     def stage_device(self, a, dev_rows):
         self.ctx.check(_lib.mzh_q3_stage_device(self.h, a, dev_rows.device_ptr(), len(dev_rows)))

@@ -368,6 +368,58 @@ def test_reduce_large_i128_sums(mz, ctx, oracle):
     same(gr.step(a, 2), orr.step(a, 2))
 
 
+# ------------------------------------------ device-resident operator chaining
+def test_chained_operators_no_readback(mz, ctx, oracle):
+    """arrange -> update_stream -> half_join x2 -> reduce with every intermediate in a device
+    buffer (the *_buf entry points): same output as the oracle, and the host waits for the
+    device only a handful of times for the whole chain."""
+    rng = np.random.default_rng(31)
+    n = 6000
+    look1 = rand_r32(rng, 5000, 800, 1 << 16, 1, dtype=oracle.R32)
+    look2 = rand_r32(rng, 7000, 1 << 16, 1 << 10, 1, dtype=oracle.R32)
+    look1["time"] = 0
+    look2["time"] = 0
+    gs1, os1 = mz.Spine(ctx, 32), oracle.Spine(32, 1, True)
+    gs2, os2 = mz.Spine(ctx, 32), oracle.Spine(32, 1, True)
+    for gs, os_, rows in ((gs1, os1, look1), (gs2, os2, look2)):
+        gs.insert(mz.Batch.build(ctx, rows, 0, 1))
+        os_.insert(oracle.Batch.build(rows, 0, 1))
+        gs.set_physical_compaction(1)
+        os_.set_physical_compaction(1)
+    # stage 1 keeps the key, stage 2 re-keys by the low 16 bits of the looked-up value
+    cl1 = dict(key_fields=[(2, 0, 16, 0)], val_fields=[(1, 0, 20, 0)])
+    cl2 = dict(key_fields=[(0, 0, 8, 0)], val_fields=[(2, 0, 10, 0), (1, 0, 20, 10)])
+    g1, o1 = mz.make_closure(**cl1), oracle.make_closure(**cl1)
+    g2, o2 = mz.make_closure(**cl2), oracle.make_closure(**cl2)
+    gb, ob = mz.Batcher(ctx, 32), oracle.Batcher(32)
+    gr, orr = mz.ReduceAccumulable(ctx, 0), oracle.Reduce(0)
+    ctx.sync()
+    for t in (1, 2, 3):
+        upd = rand_r32(rng, n, 800, 1 << 20, 1, dtype=oracle.R32)
+        upd["time"] = t
+        dev = mz.DeviceRows(ctx, 32).upload(upd)
+        s0 = ctx.stats()["host_syncs"]
+        gb.push_buf(dev)
+        batch = gb.seal_lazy(t + 1)
+        stream = mz.update_stream_dev(ctx, batch)
+        j1 = mz.half_join_dev(ctx, stream, gs1, mz.HALFJOIN_LE, g1)
+        j2 = mz.half_join_dev(ctx, j1, gs2, mz.HALFJOIN_LT, g2)
+        out = gr.step_dev(j2, t + 1)
+        enqueue_syncs = ctx.stats()["host_syncs"] - s0
+        got = out.download()
+        # oracle, operator by operator
+        ob.push(upd)
+        obatch = ob.seal(t + 1)
+        ws = oracle.update_stream(obatch, None, mz.FRONTIER_EMPTY)
+        w1 = oracle.half_join(ws, os1, 0, o1)
+        w2 = oracle.half_join(w1, os2, 1, o2)
+        want = orr.step(w2, t + 1)
+        same(got, want)
+        # enqueueing the whole chain waits at most twice (the probes' fan-out bounds need the
+        # lengths of freshly sealed batches; nothing else)
+        assert enqueue_syncs <= 2, enqueue_syncs
+
+
 # -------------------------------------------------- the whole Q3 dataflow
 def test_q3_dataflow_matches_oracle(mz, ctx, oracle):
     """Hydration + update batches through the C++ harness (delta join, 3 paths x 2
