@@ -107,8 +107,9 @@ def run_reference(args, rank):
     from oracle import binding as B
 
     cores = os.cpu_count() or 1
-    sf = args.sf
-    q = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU, **scale(sf))
+    # same workload as our arm at --gpus N (weak scaling: SF and batch grow with N)
+    sf = args.sf * max(1, args.gpus)
+    q = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU * max(1, args.gpus), **scale(sf))
     t0 = time.time()
     q.hydrate()
     hyd = time.time() - t0
@@ -137,7 +138,7 @@ def run_reference(args, rank):
         "vs_baseline": None,
         "dtype": "int64",
         "data": "synthetic",
-        "config": workload_config(sf, 1),
+        "config": workload_config(args.sf, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
