@@ -27,7 +27,35 @@ struct RsSmemT {
 // is being processed by a co-resident CTA (look-back progress); tile_state is
 // zero before the pass.  No __restrict__ here: inside the fused kernel the
 // input of one pass was written by other CTAs in the previous phase.  Ends with a __syncthreads(): `s` can be reused.
-template <int ITEMS, int THREADS = RS_THREADS>
+// tile-state words are read and written with GPU-scope relaxed accesses (a word
+// carries its own flag, so no ordering with other data is needed)
+__device__ __forceinline__ u32 rs_load(const u32* p) {
+  u32 v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void rs_store(u32* p, u32 v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lanes of the warp whose 8-bit digit equals this lane's: eight ballots.  (The
+// hardware MATCH.ANY runs on the address-divergence unit at a small fraction of
+// the ballot rate: with ~30 distinct digits per warp it was the pipe that bound
+// the whole pass, profiles/r01_ncu_full_onesweep_raw.csv: pipe_adu 72 %.)
+template <bool BALLOT>
+__device__ __forceinline__ u32 match_digit(u32 d) {
+  if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+  u32 m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
+template <int ITEMS, int THREADS = RS_THREADS, bool BALLOT = true>
 __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 tile, const u64* kin,
                                              const u32* vin, u64* kout,
                                              u32* vout, u64 n, int shift,
@@ -57,7 +85,7 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     u32 d = (u32)((key[j] >> shift) & 255);
-    u32 m = __match_any_sync(0xffffffffu, d);
+    u32 m = match_digit<BALLOT>(d);
     u32 leader = __ffs(m) - 1;
     u32 old = 0;
     if (lane == leader) {
@@ -70,7 +98,9 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
   }
   __syncthreads();
 
-  // thread d owns digit d: exclusive scan across warps, then the look-back
+  // thread d owns digit d: exclusive scan across warps; the tile's digit counts
+  // are published at once (successors only need this aggregate to move on)
+  u32 my_tot_valid = 0;
   if (THREADS == 256 || tid < 256) {
     const u32 d = tid;
     u32 tot = 0;
@@ -81,26 +111,9 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
       tot += c;
     }
     const u32 n_invalid = TILE - n_valid;  // padding keys all carry digit 255
-    u32 tot_valid = (d == 255) ? tot - n_invalid : tot;
-    u32 excl = 0;
-    volatile u32* st = tile_state;
-    if (tile == 0) {
-      st[d] = RS_FLAG_INCLUSIVE | tot_valid;
-    } else {
-      st[(u64)tile * 256 + d] = RS_FLAG_PARTIAL | tot_valid;
-      long long t = (long long)tile - 1;
-      while (true) {
-        u32 v = st[(u64)t * 256 + d];
-        u32 flag = v >> 30;
-        if (flag == 0) continue;  // predecessor not published yet
-        excl += v & RS_VALUE_MASK;
-        if (flag == 2) break;
-        --t;
-      }
-      st[(u64)tile * 256 + d] = RS_FLAG_INCLUSIVE | ((excl + tot_valid) & RS_VALUE_MASK);
-    }
-    s.digit_start[d] = tot;              // digit totals; scanned below
-    s.gofs[d] = gbase[d] + excl;          // finished below: minus the digit's tile-local start
+    my_tot_valid = (d == 255) ? tot - n_invalid : tot;
+    rs_store(&tile_state[(u64)tile * 256 + d], (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL) | my_tot_valid);
+    s.digit_start[d] = tot;  // digit totals; scanned below
   }
   __syncthreads();
   {
@@ -108,10 +121,7 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
     u32 v = tid < 256 ? s.digit_start[tid] : 0;
     u32 total;
     u32 ds = block_exclusive_scan(v, s.scan, &total);
-    if (tid < 256) {
-      s.digit_start[tid] = ds;
-      s.gofs[tid] -= ds;  // global position = gofs[d] + local position
-    }
+    if (tid < 256) s.digit_start[tid] = ds;
   }
   __syncthreads();
 
@@ -122,6 +132,38 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
     u32 pos = s.digit_start[d] + s.whist[warp][d] + rank[j];
     s.keys[pos] = key[j];
     s.vals[pos] = val[j];
+  }
+  // decoupled look-back, as late as possible (the predecessors have had the whole
+  // staging step to publish) and four predecessors per round trip
+  if (THREADS == 256 || tid < 256) {
+    const u32 d = tid;
+    u32 excl = 0;
+    if (tile != 0) {
+      long long t = (long long)tile - 1;
+      bool done = false;
+      while (!done) {
+        u32 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          v[q] = (t - q >= 0) ? rs_load(&tile_state[(u64)(t - q) * 256 + d]) : RS_FLAG_INCLUSIVE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const u32 flag = v[q] >> 30;
+          if (flag == 0) {  // not published yet: re-read from here
+            t -= q;
+            break;
+          }
+          excl += v[q] & RS_VALUE_MASK;
+          if (flag == 2) {
+            done = true;
+            break;
+          }
+          if (q == 3) t -= 4;
+        }
+      }
+      rs_store(&tile_state[(u64)tile * 256 + d], RS_FLAG_INCLUSIVE | ((excl + my_tot_valid) & RS_VALUE_MASK));
+    }
+    s.gofs[d] = gbase[d] + excl - s.digit_start[d];  // global position = gofs[d] + local position
   }
   __syncthreads();
   // coalesced runs per digit

@@ -28,7 +28,7 @@ namespace {
 struct RsVariant {
   int items, threads;
 };
-static const RsVariant RS_VARIANTS[] = {{16, 256}, {16, 512}, {24, 256}, {12, 512}, {20, 384}};
+static const RsVariant RS_VARIANTS[] = {{16, 256}, {16, 512}, {24, 256}, {12, 512}, {20, 384}, {16, 256}, {24, 256}, {14, 256}, {10, 256}};
 
 struct ChunkPlan {
   int nwords;
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(u32* __restrict__ ghist, i
 }
 
 // ------------------------------------------------------------ onesweep pass
-template <int ITEMS, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_rs_onesweep(
+template <int ITEMS, int THREADS, bool BALLOT, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_rs_onesweep(
     const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
     u32* __restrict__ vout, u64 n, int shift, const u32* __restrict__ gbase,
     u32* __restrict__ tile_state, u32* __restrict__ tile_counter) {
@@ -141,16 +141,16 @@ __global__ void __launch_bounds__(THREADS) k_rs_onesweep(
   // which is what makes the look-back deadlock-free
   if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
-  rs_tile_pass<ITEMS, THREADS>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
+  rs_tile_pass<ITEMS, THREADS, BALLOT>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
 }
 
-template <int ITEMS, int THREADS>
+template <int ITEMS, int THREADS, bool BALLOT = true, int MINB = (THREADS >= 512 ? 1 : (ITEMS > 16 ? 2 : 3))>
 static int32_t launch_onesweep(mzgpu_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u64 n,
                                int shift, const u32* gbase, u32* state, u32* counter) {
   typedef RsSmemT<ITEMS, THREADS> Smem;
   static bool attr_set = false;
   if (!attr_set) {
-    MZ_CUDA(ctx, cudaFuncSetAttribute(k_rs_onesweep<ITEMS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MZ_CUDA(ctx, cudaFuncSetAttribute(k_rs_onesweep<ITEMS, THREADS, BALLOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(Smem)));
     attr_set = true;
   }
@@ -158,7 +158,7 @@ static int32_t launch_onesweep(mzgpu_ctx* ctx, const u64* kin, const u32* vin, u
   MZ_BYTES(ctx, n * 24);  // read key+idx (12 B), write key+idx (12 B)
   {
     ProfScope _prof(ctx, "k_rs_onesweep");
-    k_rs_onesweep<ITEMS, THREADS><<<(unsigned)n_tiles, THREADS, sizeof(Smem), ctx->stream>>>(
+    k_rs_onesweep<ITEMS, THREADS, BALLOT, MINB><<<(unsigned)n_tiles, THREADS, sizeof(Smem), ctx->stream>>>(
         kin, vin, kout, vout, n, shift, gbase, state, counter);
   }
   ctx->stats.kernel_launches++;
@@ -217,6 +217,10 @@ int32_t radix_sort_pairs(mzgpu_ctx* ctx, u64* ka, u32* va, u64* kb, u32* vb, u64
       case 2: MZ_TRY((launch_onesweep<24, 256>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
       case 3: MZ_TRY((launch_onesweep<12, 512>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
       case 4: MZ_TRY((launch_onesweep<20, 384>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 5: MZ_TRY((launch_onesweep<16, 256, false>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;  // MATCH.ANY
+      case 6: MZ_TRY((launch_onesweep<24, 256, false>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 7: MZ_TRY((launch_onesweep<14, 256, true, 4>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
+      case 8: MZ_TRY((launch_onesweep<10, 256, true, 5>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
       default: MZ_TRY((launch_onesweep<16, 256>(ctx, kin, vin, kout, vout, n, 8 * p, gb, stp, cnt))); break;
     }
     std::swap(kin, kout);
