@@ -139,6 +139,219 @@ struct MsdSmem {
 struct MsdScan {  // phase "scatter": bucket bases
   u32 base[MSD_MAX_BUCKETS + 1];
 };
+
+// logical input row i of A ++ B, time advanced to max(time, since)
+template <int RB>
+__device__ __forceinline__ void load_in_row(const FusedArgs& a, u64 na, u64 since, u64 i, u64* r) {
+  constexpr int NW = RowT<RB>::NW, TW = RowT<RB>::TW;
+  if (i < na)
+    load_row<NW>(a.a, i, r);
+  else
+    load_row<NW>(a.b, i - na, r);
+  if (TW >= 0) {
+    u64& t = r[TW >= 0 ? TW : 0];
+    t = t < since ? since : t;
+  }
+}
+
+// ---- MSD bucket phase, one bucket per WARP (buckets of at most 32*R rows): the
+// bucket's composites live in registers, a shuffle bitonic network sorts them,
+// a warp-segmented scan sums the diffs of equal keys, and the surviving rows are
+// emitted at offsets from a look-back over chunks of eight buckets (one chunk per
+// CTA iteration).  No shared-memory sort, no block-wide scans: ~5 us per chunk.
+template <int RB, int R>
+__device__ __forceinline__ void msd_warp_buckets(const FusedArgs& a, FusedCtl* ctl, const u32* base, u32 NB, u32 c,
+                                                 u32 G, u64 na, u64 since, u64* s_cnt /* 8 + 1 words */,
+                                                 u64* s_lb) {
+  constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 upper = a.upper;
+  LookBack lbs;
+  lbs.state = a.lb_ship;
+  lbs.ticket = nullptr;
+  lbs.epoch = 1;
+  const u32 n_chunks = (NB + 7) / 8;
+  for (u32 ch = c; ch < n_chunks; ch += G) {
+    const u32 b = ch * 8 + warp;
+    u32 gbase = 0, m = 0;
+    if (b < NB) {
+      gbase = base[b];
+      m = base[b + 1] - gbase;
+    }
+    u64 hi[R], lo[R];
+    u32 ix[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      if (p < m) {
+        lo[r] = a.m_lo[gbase + p];
+        hi[r] = a.m_hi[gbase + p];
+        ix[r] = a.m_idx[gbase + p];
+      } else {
+        lo[r] = ~0ull;
+        hi[r] = ~0ull;
+        ix[r] = 0xffffffffu;
+      }
+    }
+    // diffs (and time) of the rows as they arrived; they travel with the sort
+    // bitonic network over positions p = r*32 + lane, ordered by (hi, lo, idx)
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int r2 = r ^ (j >> 5);
+            if (r2 > r) {
+              const bool up = (((r * 32 + (int)lane) & k) == 0);
+              const bool gt = hi[r] > hi[r2] || (hi[r] == hi[r2] && (lo[r] > lo[r2] || (lo[r] == lo[r2] && ix[r] > ix[r2])));
+              if (gt == up) {
+                u64 t0 = hi[r];
+                hi[r] = hi[r2];
+                hi[r2] = t0;
+                t0 = lo[r];
+                lo[r] = lo[r2];
+                lo[r2] = t0;
+                u32 t1 = ix[r];
+                ix[r] = ix[r2];
+                ix[r2] = t1;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const u64 ohi = __shfl_xor_sync(0xffffffffu, hi[r], j);
+            const u64 olo = __shfl_xor_sync(0xffffffffu, lo[r], j);
+            const u32 oix = __shfl_xor_sync(0xffffffffu, ix[r], j);
+            const bool up = (((r * 32 + (int)lane) & k) == 0);
+            const bool lower = ((lane & j) == 0);
+            const bool gt = hi[r] > ohi || (hi[r] == ohi && (lo[r] > olo || (lo[r] == olo && ix[r] > oix)));
+            // the lower position keeps the smaller element when ascending
+            const bool take = (lower == up) ? gt : !gt;
+            if (take) {
+              hi[r] = ohi;
+              lo[r] = olo;
+              ix[r] = oix;
+            }
+          }
+        }
+      }
+    }
+    // head flags, diffs
+    bool head[R];
+    u64 d[R][ND];
+    u64 tt[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      u64 phi = __shfl_up_sync(0xffffffffu, hi[r], 1), plo = __shfl_up_sync(0xffffffffu, lo[r], 1);
+      if (r > 0) {
+        const u64 qhi = __shfl_sync(0xffffffffu, hi[r - 1 >= 0 ? r - 1 : 0], 31);
+        const u64 qlo = __shfl_sync(0xffffffffu, lo[r - 1 >= 0 ? r - 1 : 0], 31);
+        if (lane == 0) {
+          phi = qhi;
+          plo = qlo;
+        }
+      }
+      head[r] = p < m && (p == 0 || phi != hi[r] || plo != lo[r]);
+      tt[r] = 0;
+      if (p < m) {
+        u64 row[NW];
+        load_in_row<RB>(a, na, since, ix[r], row);
+#pragma unroll
+        for (int w = 0; w < ND; ++w) d[r][w] = row[NK + w];
+        if (TW >= 0) tt[r] = row[TW >= 0 ? TW : 0];
+      } else {
+#pragma unroll
+        for (int w = 0; w < ND; ++w) d[r][w] = 0;
+      }
+    }
+    // segmented inclusive sums in position order; the carry crosses register rows
+    u64 carry[ND];
+#pragma unroll
+    for (int w = 0; w < ND; ++w) carry[w] = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 hm = __ballot_sync(0xffffffffu, head[r]);
+      const u32 below = hm & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1));
+      const int my_start = below ? 31 - __clz(below) : -1;  // lane of my segment's head in this row (-1: continues)
+      const int start_eff = my_start < 0 ? 0 : my_start;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        u64 o[ND];
+#pragma unroll
+        for (int w = 0; w < ND; ++w) o[w] = __shfl_up_sync(0xffffffffu, d[r][w], off);
+        if ((int)lane - off >= start_eff) diff_add<ND>(d[r], o);
+      }
+      if (my_start < 0) diff_add<ND>(d[r], carry);  // my segment started in an earlier row
+#pragma unroll
+      for (int w = 0; w < ND; ++w) carry[w] = __shfl_sync(0xffffffffu, d[r][w], 31);
+    }
+    // survivors: the LAST row of every segment carries the segment's sum
+    u32 cls[R];
+    u32 cnt_ship = 0, cnt_keep = 0;
+    u32 pos_ship[R], pos_keep[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      bool nhead = __shfl_down_sync(0xffffffffu, head[r], 1);
+      if (r + 1 < R) {
+        const bool q = __shfl_sync(0xffffffffu, head[r + 1 < R ? r + 1 : r], 0);
+        if (lane == 31) nhead = q;
+      } else if (lane == 31) {
+        nhead = true;
+      }
+      const bool tail = p < m && (p == m - 1 || nhead);
+      cls[r] = 0;
+      if (tail && !diff_is_zero<ND>(d[r]))
+        cls[r] = (TW < 0 || upper == MZGPU_FRONTIER_EMPTY || tt[r] < upper) ? 1u : 2u;
+      const u32 ms = __ballot_sync(0xffffffffu, cls[r] == 1u), mk = __ballot_sync(0xffffffffu, cls[r] == 2u);
+      const u32 lt = (1u << lane) - 1;
+      pos_ship[r] = cnt_ship + __popc(ms & lt);
+      pos_keep[r] = cnt_keep + __popc(mk & lt);
+      cnt_ship += __popc(ms);
+      cnt_keep += __popc(mk);
+    }
+    // chunk-level offsets: eight warps, then the look-back over chunks
+    __syncthreads();
+    if (lane == 0) s_cnt[warp] = ((u64)cnt_ship << 21) | (u64)cnt_keep;
+    __syncthreads();
+    u64 mine = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FT / 32; ++w) {
+      const u64 v = s_cnt[w];
+      if ((u32)w < warp) mine += v;
+      total += v;
+    }
+    const u64 chunk_base = lb_exclusive_prefix(lbs, ch, total, s_lb);
+    const u64 bases = chunk_base + mine;
+    const u64 ship_base = bases >> 21, keep_base = bases & ((1ull << 21) - 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (cls[r] != 0u) {
+        u64 row[NW];
+        load_in_row<RB>(a, na, since, ix[r], row);
+#pragma unroll
+        for (int w = 0; w < ND; ++w) row[NK + w] = d[r][w];
+        if (cls[r] == 1u) {
+          store_row<NW>(a.out, ship_base + pos_ship[r], row);
+        } else if (a.keep != nullptr) {
+          store_row<NW>(a.keep, keep_base + pos_keep[r], row);
+          if (TW >= 0) atomicMin((unsigned long long*)&a.kres[1], (unsigned long long)row[TW >= 0 ? TW : 0]);
+        }
+      }
+    }
+    if (ch == n_chunks - 1 && tid == 0) {
+      const u64 all = chunk_base + total;
+      ctl->n_out = all >> 21;
+      a.res[0] = all >> 21;
+      a.kres[0] = all & ((1ull << 21) - 1);
+    }
+  }
+}
+
 union FusedSmem {
   RsSmemT<FI> rs;
   u32 hist[8 * 256];
@@ -147,7 +360,7 @@ union FusedSmem {
 };
 
 template <int RB>
-__global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
+__global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) {
   constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
@@ -160,13 +373,22 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   const u64 n = na + nb;
   const u64 T = (n + FTILE - 1) / FTILE;
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
-  // MSD bucket count from the row count alone: ~128..256 rows per populated bucket
+  // MSD bucket count from the row count alone: at most 48 (12 for the 80-byte
+  // accumulable rows, whose warp capacity is 64 and whose keys arrive in clumps:
+  // one row per lineitem of an order) rows per bucket on average
+  constexpr int WR = ND == 8 ? 2 : 4;       // register rows per lane in the warp-bucket phase
+  constexpr u32 WCAP = 32u * WR;            // largest bucket a warp takes
   u32 bb = 0;  // log2(buckets)
-  while (bb < 12 && ((u64)128 << bb) < n) ++bb;
+  while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n) ++bb;
   const u32 NB = 1u << bb;
   u32 G = gridDim.x;
   {
-    u64 want = T > (u64)NB ? T : (u64)NB;
+    // the bucket phase of the MSD path wants one CTA per bucket; a merge only has its
+    // 1024-row tiles (fewer CTAs = cheaper grid barriers)
+    // (a merge has no buckets: two 256-row tiles of the consolidation tail per CTA)
+    const u64 half_u = (n + 2 * FT - 1) / (2 * FT);
+    u64 want = a.merge ? (half_u > T ? half_u : T) : (T < (u64)((NB + 7) / 8) ? (u64)((NB + 7) / 8) : T);
+    if (want == 0) want = 1;
     if (want < (u64)G) G = (u32)want;
     if (G > a.max_g) G = a.max_g;  // more CTAs only make the grid barriers slower
   }
@@ -220,8 +442,6 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       a.lb_keep[i] = 0;
     }
     for (u64 i = gtid; i < T * 256; i += gstride) a.state0[i] = 0;
-    if (a.table != nullptr)
-      for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
     u64 mn[NK], mx[NK];
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
@@ -362,7 +582,21 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
       __syncthreads();
     }
     constexpr u32 LOCAL_MAX = ND == 8 ? 256u : MSD_LOCAL_MAX;
-    if (s_max_bucket <= LOCAL_MAX) {
+    if (s_max_bucket <= WCAP) {
+      // every bucket fits a warp
+      for (u64 i = gtid; i < n; i += gstride) {
+        const u64 p = (u64)sm.scan.base[a.v1[i]] + a.v0[i];
+        a.m_lo[p] = a.k0[i];
+        a.m_hi[p] = a.k1[i];
+        a.m_idx[p] = (u32)i;
+      }
+      grid_barrier(&ctl->barrier, G, epoch);
+      PHASE_STAMP(11);
+      __shared__ u64 s_wcnt[FT / 32 + 1];
+      __shared__ u64 s_wlb;
+      msd_warp_buckets<RB, WR>(a, ctl, sm.scan.base, NB, c, G, na, since, s_wcnt, &s_wlb);
+      msd_done = true;
+    } else if (s_max_bucket <= LOCAL_MAX) {
       for (u64 i = gtid; i < n; i += gstride) {
         const u64 p = (u64)sm.scan.base[a.v1[i]] + a.v0[i];
         a.m_lo[p] = a.k0[i];
@@ -551,6 +785,9 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   PHASE_STAMP(7);
   if (msd_done) {
     if (a.table == nullptr) return;
+    // the table is cleared here, off the critical path of the earlier phases (CTAs
+    // reach this point at different times; the index is built after the barrier)
+    for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
     grid_barrier(&ctl->barrier, G, epoch);
     PHASE_STAMP(8);
   }
@@ -814,6 +1051,7 @@ __global__ void __launch_bounds__(FT) k_fused_consolidate(const FusedArgs a) {
   }
   PHASE_STAMP(7);
   if (a.table == nullptr) return;
+  for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
   grid_barrier(&ctl->barrier, G, epoch);
   PHASE_STAMP(8);
   n_out = V == 0 ? 0 : *(volatile u64*)&ctl->n_out;

@@ -223,6 +223,13 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
     }
     for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
       if (!active[path]) continue;
+      if (s == 1) {
+        // last stage: the paths' outputs are concatenated (delta_join.rs:302-308), so
+        // each path appends straight to the result collection
+        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
+                                 &q->plan.stage[path][s], 0, q->results);
+        continue;
+      }
       st = mzgpu_buf_clear(q->pnext[path]);
       if (st == MZGPU_OK)
         st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
@@ -230,8 +237,6 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       std::swap(q->pstream[path], q->pnext[path]);
     }
   }
-  for (int path = 0; path < 3 && st == MZGPU_OK; ++path)
-    if (active[path]) st = mzgpu_buf_append_buf(q->results, q->pstream[path]);
   if (st == MZGPU_OK && q->peers > 1) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);
     std::swap(q->results, q->xchg);
