@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
   __shared__ u32 sm_scan[34];
   __shared__ int s_nwords, s_nrounds, s_word[6], s_shift[6], s_round[6], s_rbits[MAX_ROUNDS];
   __shared__ int s_shift128[6], s_w128;
-  __shared__ u32 s_max_bucket;
+  __shared__ u32 s_max_bucket, s_max_unit;
   __shared__ u64 s_minv[6];
   const u32 c = blockIdx.x, tid = threadIdx.x;
   const u64 na = dlen_get(a.na), nb = dlen_get(a.nb);
@@ -578,10 +578,28 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
           ex += local[j];
         }
       }
-      if (tid == 0) sm.scan.base[NB] = total;
+      if (tid == 0) {
+        sm.scan.base[NB] = total;
+        s_max_unit = 0;
+      }
+      __syncthreads();
+      // the CTA-level fallback works on units of eight consecutive buckets
+      u32 mu = 0;
+      for (u32 u = tid; u < (NB + 7) / 8; u += FT) {
+        const u32 hi_b = (u * 8 + 8 < NB) ? u * 8 + 8 : NB;
+        const u32 sz = sm.scan.base[hi_b] - sm.scan.base[u * 8];
+        mu = sz > mu ? sz : mu;
+      }
+      atomicMax(&s_max_unit, mu);
       __syncthreads();
     }
+    const u32 NU = (NB + 7) / 8;
     constexpr u32 LOCAL_MAX = ND == 8 ? 256u : MSD_LOCAL_MAX;
+    if (a.dbg != nullptr && c == 0 && tid == 0) {
+      a.dbg[21] = s_max_bucket <= WCAP ? 1 : (s_max_unit <= LOCAL_MAX ? 2 : 3);
+      a.dbg[22] = s_max_bucket;
+      a.dbg[23] = NB;
+    }
     if (s_max_bucket <= WCAP) {
       // every bucket fits a warp
       for (u64 i = gtid; i < n; i += gstride) {
@@ -596,7 +614,7 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
       __shared__ u64 s_wlb;
       msd_warp_buckets<RB, WR>(a, ctl, sm.scan.base, NB, c, G, na, since, s_wcnt, &s_wlb);
       msd_done = true;
-    } else if (s_max_bucket <= LOCAL_MAX) {
+    } else if (s_max_unit <= LOCAL_MAX) {
       for (u64 i = gtid; i < n; i += gstride) {
         const u64 p = (u64)sm.scan.base[a.v1[i]] + a.v0[i];
         a.m_lo[p] = a.k0[i];
@@ -616,13 +634,14 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
       u32 my_base[MSD_MAX_BUCKETS / 64 + 1], my_m[MSD_MAX_BUCKETS / 64 + 1];
       {
         int q = 0;
-        for (u32 b = c; b < NB && q < (int)(MSD_MAX_BUCKETS / 64 + 1); b += G, ++q) {
-          my_base[q] = sm.scan.base[b];
-          my_m[q] = sm.scan.base[b + 1] - sm.scan.base[b];
+        for (u32 b = c; b < NU && q < (int)(MSD_MAX_BUCKETS / 64 + 1); b += G, ++q) {
+          const u32 hi_b = (b * 8 + 8 < NB) ? b * 8 + 8 : NB;
+          my_base[q] = sm.scan.base[b * 8];
+          my_m[q] = sm.scan.base[hi_b] - sm.scan.base[b * 8];
         }
       }
       int q = 0;
-      for (u32 b = c; b < NB; b += G, ++q) {
+      for (u32 b = c; b < NU; b += G, ++q) {  // b: unit of eight buckets
         const u32 gbase = my_base[q];
         const u32 m = my_m[q];
         u32 P = 32;
@@ -773,7 +792,7 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
             bases = lb_exclusive_prefix(lbs, b, ((u64)tot_ship << 21) | (u64)tot_keep, &s_lb);
           }
         }
-        if (b == NB - 1 && tid == 0) {
+        if (b == NU - 1 && tid == 0) {
           ctl->n_out = (bases >> 21) + tot_ship;
           a.res[0] = (bases >> 21) + tot_ship;
           a.kres[0] = (bases & ((1ull << 21) - 1)) + tot_keep;
