@@ -643,8 +643,11 @@ int32_t mz_extract(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64
 // index.cu: open-addressing hash index over the distinct keys of a sorted array.
 struct HashSlot {
   u64 key;
-  u64 meta;  // 0 = empty, else (first row index + 1)
+  u64 meta;  // 0 = empty; bits [0,44): first row index + 1; bits [44,64): the key's run
+             // length if the builder knows it (else 0: the reader scans until the key changes)
 };
+#define MZ_SLOT_ROW_MASK ((1ull << 44) - 1)
+#define MZ_SLOT_LEN_MAX 0xfffffull
 int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64* n_keys, u64* max_run);
 int32_t mz_build_index(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64 n_keys,
                        DevMem* table, u64* table_slots);

@@ -360,7 +360,7 @@ union FusedSmem {
 };
 
 template <int RB>
-__global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) {
+__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(const FusedArgs a) {
   constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
   // MSD bucket count from the row count alone: at most 48 (12 for the 80-byte
   // accumulable rows, whose warp capacity is 64 and whose keys arrive in clumps:
   // one row per lineitem of an order) rows per bucket on average
-  constexpr int WR = ND == 8 ? 2 : 4;       // register rows per lane in the warp-bucket phase
+  constexpr int WR = 4;                     // register rows per lane in the warp-bucket phase
   constexpr u32 WCAP = 32u * WR;            // largest bucket a warp takes
   u32 bb = 0;  // log2(buckets)
   while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n) ++bb;
@@ -1090,19 +1090,20 @@ __global__ void __launch_bounds__(FT, 2) k_fused_consolidate(const FusedArgs a) 
     u32 m = __ballot_sync(0xffffffffu, head);
     if (lane_id() == 0 && m) atomicAdd((unsigned long long*)&a.res[2], (unsigned long long)__popc(m));
     if (head) {
+      u32 run = 1;
+      while (run < MAX_RUN_SAT && i + run < n_out && a.out[(i + run) * NW] == key) ++run;
+      my_run = run > my_run ? run : my_run;
+      // slot: first row + 1, and the run length when it did not saturate
+      const u64 meta = (i + 1) | ((u64)(run < MAX_RUN_SAT ? run : 0u) << 44);
       u64 h = mix64(key) & mask;
       while (true) {
-        unsigned long long prev =
-            atomicCAS((unsigned long long*)&a.table[h].meta, 0ull, (unsigned long long)(i + 1));
+        unsigned long long prev = atomicCAS((unsigned long long*)&a.table[h].meta, 0ull, (unsigned long long)meta);
         if (prev == 0ull) {
           a.table[h].key = key;
           break;
         }
         h = (h + 1) & mask;
       }
-      u32 run = 1;
-      while (run < MAX_RUN_SAT && i + run < n_out && a.out[(i + run) * NW] == key) ++run;
-      my_run = run > my_run ? run : my_run;
     }
   }
 #pragma unroll
@@ -1185,6 +1186,7 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   a.lb_ship = (u64*)(sp + o_lbs);
   a.lb_keep = (u64*)(sp + o_lbk);
   a.max_g = 2u * (u32)ctx->num_sms;
+  if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
   a.merge = (job.merge && job.b != nullptr) ? 1u : 0u;
   a.out = res->rows.template as<u64>();
   a.keep = want_keep ? res->keep.template as<u64>() : nullptr;

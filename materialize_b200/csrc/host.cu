@@ -163,10 +163,12 @@ extern "C" int32_t mzgpu_ctx_sync(mzgpu_ctx* ctx) {
 extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   if (ctx == nullptr || out == nullptr) return MZGPU_E_INVALID;
   if (getenv("MZGPU_DEBUG"))
-    fprintf(stderr, "[mzgpu] allocs %llu (%.1f MB, %.3f ms host)  syncs %llu (%.3f ms waiting)  launches %llu\n",
+    fprintf(stderr,
+            "[mzgpu] allocs %llu (%.1f MB, %.3f ms host)  syncs %llu (%.3f ms waiting)  launches %llu  counter blocks %d"
+            " in use (high water %d)\n",
             (unsigned long long)ctx->n_alloc, ctx->bytes_alloc / 1e6, ctx->ns_alloc / 1e6,
             (unsigned long long)ctx->stats.host_syncs, ctx->ns_sync / 1e6,
-            (unsigned long long)ctx->stats.kernel_launches);
+            (unsigned long long)ctx->stats.kernel_launches, ctx->cnt_high - (int)ctx->cnt_free.size(), ctx->cnt_high);
   *out = ctx->stats;
   return MZGPU_OK;
 }

@@ -41,11 +41,14 @@ __global__ void __launch_bounds__(512) k_build_index(const u64* __restrict__ row
   if (i >= n) return;
   u64 key = rows[i * NW];
   if (i != 0 && rows[(i - 1) * NW] == key) return;
+  // the key's run length, if it ends within 64 rows (longer runs are left for the reader to scan)
+  u64 run = 1;
+  while (run <= 64 && i + run < n && rows[(i + run) * NW] == key) ++run;
+  const u64 meta = (i + 1) | ((run <= 64 ? run : 0ull) << 44);
   u64 h = mix64(key) & mask;
   while (true) {
     // distinct keys only: claim the first empty slot
-    unsigned long long prev =
-        atomicCAS((unsigned long long*)&table[h].meta, 0ull, (unsigned long long)(i + 1));
+    unsigned long long prev = atomicCAS((unsigned long long*)&table[h].meta, 0ull, (unsigned long long)meta);
     if (prev == 0ull) {
       table[h].key = key;
       return;

@@ -50,13 +50,34 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
       while (true) {
         if (sl.y == 0) break;
         if (sl.x == key) {
-          const u64 bn = bv_n(bv);
-          for (u64 r = sl.y - 1; r < bn; ++r) {
-            const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
-            if (kv.x != key) break;
-            const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
-            bool ok = mode == MZ_PROBE_HALF_LE ? td.x <= t1 : (mode == MZ_PROBE_HALF_LT ? td.x < t1 : true);
-            if (ok) f(kv.y, td.x, (i64)td.y);
+          const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+          const u32 len = (u32)(sl.y >> 44);
+          if (len != 0) {
+            // run length known: the rows' loads do not depend on each other
+            for (u32 r0 = 0; r0 < len; r0 += 4) {
+              ulonglong2 kv[4], td[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (r0 + q < len) {
+                  kv[q] = *reinterpret_cast<const ulonglong2*>(bv.rows + (first + r0 + q) * 4);
+                  td[q] = *reinterpret_cast<const ulonglong2*>(bv.rows + (first + r0 + q) * 4 + 2);
+                }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (r0 + q < len) {
+                  bool ok = mode == MZ_PROBE_HALF_LE ? td[q].x <= t1 : (mode == MZ_PROBE_HALF_LT ? td[q].x < t1 : true);
+                  if (ok) f(kv[q].y, td[q].x, (i64)td[q].y);
+                }
+            }
+          } else {
+            const u64 bn = bv_n(bv);
+            for (u64 r = first; r < bn; ++r) {
+              const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+              if (kv.x != key) break;
+              const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+              bool ok = mode == MZ_PROBE_HALF_LE ? td.x <= t1 : (mode == MZ_PROBE_HALF_LT ? td.x < t1 : true);
+              if (ok) f(kv.y, td.x, (i64)td.y);
+            }
           }
           break;
         }

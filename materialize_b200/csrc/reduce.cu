@@ -196,10 +196,12 @@ __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) 
       while (true) {
         if (sl.y == 0) break;
         if (sl.x == key) {
-          const u64 bn = bv_n(bv);
-          for (u64 r = sl.y - 1; r < bn; ++r) {
+          const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+          const u32 len = (u32)(sl.y >> 44);
+          const u64 bn = len != 0 ? first + len : bv_n(bv);
+          for (u64 r = first; r < bn; ++r) {
             const u64* row = bv.rows + r * 10;
-            if (row[0] != key) break;
+            if (len == 0 && row[0] != key) break;
             u64 d[8];
 #pragma unroll
             for (int w = 0; w < 8; ++w) d[w] = row[2 + w];

@@ -93,6 +93,30 @@ def test_consolidate_r32_matches_oracle(mz, ctx, oracle, n, key_hi, val_hi, time
     same(ctx.consolidate(a), oracle.consolidate(a))
 
 
+@pytest.mark.parametrize("hot_keys,per_key", [(50, 400), (4, 3000), (2000, 7), (1, 20000)])
+def test_consolidate_clumped_keys(mz, ctx, oracle, hot_keys, per_key):
+    """Keys arrive in clumps (many rows share the leading key bits): exercises the warp-bucket, the
+    CTA bucket-unit and the radix fall-back paths of the fused kernel, which must all agree."""
+    rng = np.random.default_rng(hot_keys * 7 + per_key)
+    n = hot_keys * per_key
+    a = np.zeros(n, dtype=oracle.R32)
+    a["key"] = np.repeat(rng.integers(0, 1 << 40, size=hot_keys, dtype=np.uint64), per_key)
+    a["val"] = rng.integers(0, 1 << 20, size=n, dtype=np.uint64)
+    a["time"] = rng.integers(0, 3, size=n, dtype=np.uint64)
+    a["diff"] = rng.integers(-2, 3, size=n, dtype=np.int64)
+    rng.shuffle(a)
+    same(ctx.consolidate(a), oracle.consolidate(a))
+    # and through a seal that keeps part of the rows
+    gb, ob = mz.Batcher(ctx, 32), oracle.Batcher(32)
+    gb.push_container(a)
+    ob.push(a)
+    g, o = gb.seal(2), ob.seal(2)
+    same(g.rows(), o.rows())
+    assert gb.frontier() == ob.frontier()
+    g2, o2 = gb.seal(mz.FRONTIER_EMPTY), ob.seal(mz.FRONTIER_EMPTY)
+    same(g2.rows(), o2.rows())
+
+
 def test_consolidate_wrapping_diffs(mz, ctx, oracle):
     a = oracle.rows(oracle.R16, [(1, 2**63 - 1), (1, 1), (2, -(2**63)), (2, -(2**63)), (3, 5)])
     same(ctx.consolidate(a), oracle.consolidate(a))
