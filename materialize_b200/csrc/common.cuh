@@ -38,6 +38,7 @@ struct mzgpu_ctx {
   u64* d_cnt = nullptr;        // MZ_CNT_BLOCKS x 4 words
   u64* h_cnt = nullptr;        // pinned mirror, refreshed by mz_resolve_counters()
   std::vector<int> cnt_free;   // free block indices
+  std::vector<int> cnt_parked; // freed while side-stream work was outstanding: reusable after the join
   int cnt_high = 0;            // blocks [0, cnt_high) have been handed out at least once
   u64 op_seq = 1;              // bumped whenever a kernel that writes counters is enqueued
   u64 resolved_seq = 0;        // op_seq covered by the last read-back
@@ -51,8 +52,17 @@ struct mzgpu_ctx {
   u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (bug guard), [1] = rows required
   u64* d_dbg = nullptr;  // per-launch phase stamps of the fused kernel while profiling (32 words each)
   u32 dbg_next = 0;
-  void* d_fused_ctl[2] = {nullptr, nullptr};  // control blocks of the fused kernel (each launch clears the other)
-  int fused_flip = 0;
+  // control blocks of the fused kernel, a pair per stream (each launch clears the other of its pair)
+  void* d_fused_ctl[4] = {nullptr, nullptr, nullptr, nullptr};
+  int fused_flip[2] = {0, 0};
+  // ---- side stream: batch merges (spine maintenance) run here, concurrently with the
+  // operators on the main stream; a batch produced here carries side_seq and the main
+  // stream waits for the side stream the first time it touches such a batch
+  cudaStream_t main_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+  bool use_side = false;  // off by default: measured no gain on the Q3 step (MZGPU_SIDE_STREAM=1 enables)
+  u64 side_seq = 0;    // merges issued on the side stream so far
+  u64 joined_seq = 0;  // the main stream has waited for merges <= this
   // per-kernel profiling (mzgpu_profile_enable)
   struct ProfRec {
     const char* name;

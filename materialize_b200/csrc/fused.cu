@@ -1166,9 +1166,12 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   MZ_TRY(res->st.make_pending(ctx));
   MZ_TRY(res->kst.make_pending(ctx));
   char* sp = (char*)scratch.p;
-  a.ctl = (FusedCtl*)ctx->d_fused_ctl[ctx->fused_flip];
-  a.ctl_next = (FusedCtl*)ctx->d_fused_ctl[ctx->fused_flip ^ 1];
-  ctx->fused_flip ^= 1;
+  {
+    const int si = (ctx->side_stream != nullptr && ctx->stream == ctx->side_stream) ? 1 : 0;
+    a.ctl = (FusedCtl*)ctx->d_fused_ctl[2 * si + ctx->fused_flip[si]];
+    a.ctl_next = (FusedCtl*)ctx->d_fused_ctl[2 * si + (ctx->fused_flip[si] ^ 1)];
+    ctx->fused_flip[si] ^= 1;
+  }
   a.k0 = (u64*)(sp + o_k0);
   a.k1 = (u64*)(sp + o_k1);
   a.v0 = (u32*)(sp + o_v0);
@@ -1185,7 +1188,10 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   a.m_idx = (u32*)(sp + o_midx);
   a.lb_ship = (u64*)(sp + o_lbs);
   a.lb_keep = (u64*)(sp + o_lbk);
-  a.max_g = 2u * (u32)ctx->num_sms;
+  // With the side stream in use a launch takes at most one CTA slot per SM, so that a merge on
+  // the side stream and a seal on the main stream can be co-resident (cooperative launches
+  // only start when the whole grid fits).
+  a.max_g = (ctx->use_side ? 1u : 2u) * (u32)ctx->num_sms;
   if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
   a.merge = (job.merge && job.b != nullptr) ? 1u : 0u;
   a.out = res->rows.template as<u64>();
@@ -1199,8 +1205,10 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
     a.dbg = ctx->d_dbg + 32 * (size_t)ctx->dbg_next++;
     MZ_CUDA(ctx, cudaMemsetAsync(a.dbg, 0, 32 * 8, ctx->stream));
   }
+  const unsigned a_max_g_host = (unsigned)std::min<u64>((u64)(ctx->use_side ? 1 : 2) * (u64)ctx->num_sms, (u64)max_ctas);
   u64 want = (cap + 127) / 128 + 1;  // one CTA per MSD bucket (128..256 rows each), at least one per radix tile
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);
+  if (grid > a_max_g_host) grid = a_max_g_host;
   if (grid == 0) grid = 1;
   void* kargs[] = {(void*)&a};
   {

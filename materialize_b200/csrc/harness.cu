@@ -186,6 +186,8 @@ static int32_t q3_arrange_push(mzh_q3* q, int a, mzgpu_buf* rows) {
 // physical compaction to the new upper, logical compaction, idle merge effort.
 // Nothing in the operator part reads a row count back: counts flow between the
 // operators in device memory (see include/mzgpu.h).
+static int32_t q3_maintenance(mzh_q3* q);
+
 static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   const uint64_t upper = t + 1;
   mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -194,6 +196,10 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
     st = mzgpu_batcher_seal(q->batcher[a], upper, &batch[a], nullptr);
     if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
   }
+  // The previous timestamp's maintenance runs here: the seals above are already queued on
+  // the device, so the merges it schedules (side stream) and the few lengths it has to read
+  // back overlap with them instead of delaying them.
+  if (st == MZGPU_OK) st = q3_maintenance(q);
   if (st == MZGPU_OK) st = mzgpu_buf_clear(q->results);
   // the three delta paths run side by side, stage by stage, so that the exchange
   // points of one stage share a round (mzgpu_exchange_many).  A path whose source
@@ -248,7 +254,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   return st;
 }
 
-// Between-activations maintenance for the timestamp that just ran.
+// Between-activations maintenance for the timestamp that ran before.
 static int32_t q3_maintenance(mzh_q3* q) {
   if (q->maintain_upper == 0) return MZGPU_OK;
   const uint64_t upper = q->maintain_upper, t = upper - 1;
@@ -456,7 +462,6 @@ int32_t mzh_q3_staged(mzh_q3* q, int32_t a, mzgpu_r32* rows, uint64_t cap, uint6
 // maintenance runs first (its counts have reached the host by now).
 int32_t mzh_q3_step(mzh_q3* q) {
   if (q == nullptr) return MZGPU_E_INVALID;
-  H_TRY(q3_maintenance(q));
   q->stepping = true;
   if (q->slot_full[q->run_slot]) {
     // a committed host batch: the ctx stream waits for its H2D copies, takes the

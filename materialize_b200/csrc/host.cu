@@ -42,10 +42,15 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaMemset(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_status, 16));
   MZ_CUDA(ctx, cudaMemset(ctx->d_status, 0, 16));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 4; ++i) {
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
   }
+  ctx->main_stream = ctx->stream;
+  MZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+  if (const char* e = getenv("MZGPU_SIDE_STREAM")) ctx->use_side = atoi(e) != 0;
   // keep freed blocks cached in the stream-ordered pool
   cudaMemPool_t pool;
   MZ_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -86,8 +91,15 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_tickets) cudaFree(ctx->d_tickets);
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
     if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+  ctx->stream = ctx->main_stream;
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev) cudaEventDestroy(ctx->ev);
   for (auto& r : ctx->prof) {
@@ -114,12 +126,36 @@ int mz_cnt_alloc(mzgpu_ctx* ctx) {
   return -1;
 }
 void mz_cnt_free(mzgpu_ctx* ctx, int blk) {
-  if (ctx != nullptr && blk >= 0) ctx->cnt_free.push_back(blk);
+  if (ctx == nullptr || blk < 0) return;
+  // A block may still be written by a kernel in flight.  On one stream that is harmless (its
+  // next producer is queued behind that kernel); while side-stream work is outstanding the
+  // next producer could run on the other stream, so the block is parked until the join.
+  if (ctx->stream != ctx->main_stream || ctx->joined_seq != ctx->side_seq)
+    ctx->cnt_parked.push_back(blk);
+  else
+    ctx->cnt_free.push_back(blk);
 }
 // One copy of the whole arena (a few KB) + one wait: every count produced by a
 // kernel enqueued before this call becomes readable on the host.
+// the main stream waits for every merge issued on the side stream so far
+static int32_t mz_join_side(mzgpu_ctx* ctx) {
+  if (ctx->joined_seq == ctx->side_seq) return MZGPU_OK;
+  if (ctx->stream == ctx->main_stream) {
+    MZ_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side, 0));
+    ctx->joined_seq = ctx->side_seq;
+    for (int b : ctx->cnt_parked) ctx->cnt_free.push_back(b);
+    ctx->cnt_parked.clear();
+  }
+  return MZGPU_OK;
+}
 int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   MZ_CHECK_CTX(ctx);
+  // counts may have been written on either stream
+  if (ctx->stream == ctx->main_stream) {
+    MZ_TRY(mz_join_side(ctx));
+  } else {
+    MZ_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  }
   const size_t bytes = (size_t)ctx->cnt_high * 32;
   if (bytes) MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 40, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -544,7 +580,13 @@ struct mzgpu_batch {
   u64 len_ub = 0;  // host upper bound on len
   mzgpu_desc desc;
   int refs = 1;
+  u64 side_seq = 0;  // != 0: produced by merge #side_seq on the side stream
 };
+// before the main stream reads or frees a batch: wait for the merge that produced it
+static int32_t batch_ready(mzgpu_batch* b) {
+  if (b->side_seq > b->ctx->joined_seq) return mz_join_side(b->ctx);
+  return MZGPU_OK;
+}
 
 static int32_t batch_resolve(mzgpu_batch* b) {
   if (b->st.known) return MZGPU_OK;
@@ -593,6 +635,7 @@ static int32_t batch_from_fused(mzgpu_ctx* ctx, uint32_t rb, FusedOut&& fo, u64 
 // Release the slack of a batch built with a loose capacity (its length is known now).
 static int32_t batch_shrink(mzgpu_batch* b) {
   if (!b->st.known) return MZGPU_OK;
+  MZ_TRY(batch_ready(b));
   mzgpu_ctx* ctx = b->ctx;
   const u64 len = b->st.v[0];
   if (b->rows_cap > len + len / 2 + 4096) {
@@ -674,12 +717,16 @@ extern "C" void mzgpu_batch_retain(mzgpu_batch* b) {
   if (b) b->refs++;
 }
 extern "C" void mzgpu_batch_release(mzgpu_batch* b) {
-  if (b && --b->refs == 0) delete b;
+  if (b && --b->refs == 0) {
+    batch_ready(b);  // its memory is freed in stream order on the current stream
+    delete b;
+  }
 }
 extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, int32_t mem,
                                       uint64_t* n_out) {
   if (b == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
+  MZ_TRY(batch_ready(b));
   MZ_TRY(batch_resolve(b));
   const u64 len = b->st.v[0];
   if (n_out) *n_out = len;
@@ -727,6 +774,8 @@ extern "C" int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t 
                (unsigned long long)b2->desc.lower);
     return MZGPU_E_FRONTIER;
   }
+  MZ_TRY(batch_ready(b1));
+  MZ_TRY(batch_ready(b2));
   return merge_batches(b1, b2, since, out);
 }
 
@@ -1088,12 +1137,28 @@ struct mzgpu_spine {
     if (blen(b1) == 0 && blen(b2) == 0) {
       mzgpu_desc d = {b1->desc.lower, b2->desc.upper, m.merge_since};
       st = make_empty_batch(ctx, rb, d, &out);
+    } else if (ctx->use_side && ctx->stream == ctx->main_stream && !ctx->profile &&
+               b1->len_ub + b2->len_ub <= MZ_FUSED_MAX_ROWS) {  // (bulk merges read sizes back: main stream)
+      // Spine maintenance runs on the side stream, concurrently with the operators on the
+      // main stream.  The side stream first catches up with the main stream (the inputs,
+      // and every earlier reader of the batches about to be freed, are ordered before it).
+      cudaEventRecord(ctx->ev_fork, ctx->main_stream);
+      cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
+      ctx->stream = ctx->side_stream;
+      st = merge_batches(b1, b2, m.merge_since, &out);
+      mzgpu_batch_release(b1);  // freed in side-stream order, after the merge has read them
+      mzgpu_batch_release(b2);
+      b1 = b2 = nullptr;
+      cudaEventRecord(ctx->ev_side, ctx->side_stream);
+      ctx->stream = ctx->main_stream;
+      ctx->side_seq++;
+      if (out != nullptr) out->side_seq = ctx->side_seq;
     } else {
       st = merge_batches(b1, b2, m.merge_since, &out);
     }
     if (st != MZGPU_OK && err == MZGPU_OK) err = st;
-    mzgpu_batch_release(b1);
-    mzgpu_batch_release(b2);
+    if (b1) mzgpu_batch_release(b1);
+    if (b2) mzgpu_batch_release(b2);
     return out;
   }
   void apply_fuel(long long fuel_in) {
@@ -1331,6 +1396,7 @@ extern "C" int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint
 static int32_t trace_view(mzgpu_ctx* ctx, const std::vector<mzgpu_batch*>& batches, TraceView* tv) {
   tv->n_batches = 0;
   for (auto* b : batches) {
+    MZ_TRY(batch_ready(b));
     if (b->st.known && b->st.v[0] == 0) continue;
     if (tv->n_batches >= MZ_MAX_TRACE_BATCHES) {
       MZ_SET_ERR(ctx, "trace has more than %d non-empty batches", MZ_MAX_TRACE_BATCHES);
@@ -1377,6 +1443,7 @@ extern "C" int32_t mzgpu_spine_export(mzgpu_spine* s, mzgpu_buf* out) {
   for (auto* b : all) {
     DevMem m;
     u64 n = 0;
+    MZ_TRY(batch_ready(b));
     MZ_TRY(batch_resolve(b));
     MZ_TRY(mz_merge_consolidate(s->ctx, s->rb, acc.p, acc_len, b->rows.p, b->st.v[0], s->since, &m, &n));
     acc = std::move(m);
@@ -1479,6 +1546,7 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     int32_t st = MZGPU_OK;
     for (auto* b : w.others)
       if (st == MZGPU_OK) st = batch_resolve(b);
+    if (st == MZGPU_OK) st = batch_ready(w.batch);
     if (st == MZGPU_OK) st = batch_resolve(w.batch);
     if (st == MZGPU_OK) st = trace_view(j->ctx, w.others, &tv);
     DevMem res, cons;
@@ -1644,6 +1712,7 @@ extern "C" int32_t mzgpu_update_stream(mzgpu_ctx* ctx, mzgpu_batch* batch,
                                        mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);
   if (batch == nullptr || out == nullptr || batch->rb != 32 || out->rb != 32) return MZGPU_E_INVALID;
+  MZ_TRY(batch_ready(batch));
   return map_rows_into(ctx, batch->rows.as<u64>(), batch_dlen(batch), batch->len_ub, initial_closure, skip_time,
                        out);
 }
@@ -1688,12 +1757,7 @@ extern "C" int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_redu
   return MZGPU_OK;
 }
 extern "C" void mzgpu_reduce_free(mzgpu_reduce* r) { delete r; }
-extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) {
-  if (r == nullptr) return nullptr;
-  // inspection sees the arrangement as the reference would: every sealed batch admitted
-  mzgpu_spine_set_physical_compaction(r->input, r->input->upper);
-  return r->input;
-}
+extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) { return r ? r->input : nullptr; }
 
 static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, u64 upper, mzgpu_buf* out) {
   mzgpu_ctx* ctx = r->ctx;
