@@ -1217,8 +1217,21 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
     // mzgpu_profile_report substitutes the actual row count of profiled launches.
     MZ_BYTES(ctx, (job.na.p == nullptr && job.nb.p == nullptr) ? (job.na.imm + job.nb.imm) * RB * 4 : 0);
     ProfScope prof(ctx, "k_fused_consolidate");
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_fused_consolidate<RB>, dim3(grid), dim3(FT), kargs, 0,
-                                                ctx->stream);
+    // A cooperative launch guarantees what the kernel's own grid barrier needs (all CTAs
+    // co-resident).  MZGPU_COOP=0 uses a plain launch instead (same grid, <= the resident
+    // capacity): only for measuring the launch-path difference.
+    static int coop = -1;
+    if (coop < 0) {
+      const char* ev = getenv("MZGPU_COOP");
+      coop = ev ? atoi(ev) : 1;
+    }
+    cudaError_t e;
+    if (coop) {
+      e = cudaLaunchCooperativeKernel((void*)k_fused_consolidate<RB>, dim3(grid), dim3(FT), kargs, 0, ctx->stream);
+    } else {
+      k_fused_consolidate<RB><<<grid, FT, 0, ctx->stream>>>(a);
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) {
       MZ_SET_ERR(ctx, "cooperative launch failed: %s", cudaGetErrorString(e));
       ctx->sticky = true;

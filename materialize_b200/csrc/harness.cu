@@ -261,10 +261,12 @@ static int32_t q3_maintenance(mzh_q3* q) {
   q->maintain_upper = 0;
   int32_t st = MZGPU_OK;
   for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
-    st = mzgpu_spine_set_physical_compaction(q->spine[a], upper);
-    if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(q->spine[a], t);
+    // idle merge effort first: it looks at the layers as the previous tick left them (their
+    // lengths have reached the host since), then the new batches are admitted
     uint64_t e = mzgpu_spine_exert_logic(q->spine[a], 16);
-    if (st == MZGPU_OK && e) st = mzgpu_spine_exert(q->spine[a], e, nullptr);
+    if (e) st = mzgpu_spine_exert(q->spine[a], e, nullptr);
+    if (st == MZGPU_OK) st = mzgpu_spine_set_physical_compaction(q->spine[a], upper);
+    if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(q->spine[a], t);
   }
   if (st == MZGPU_OK) st = mzgpu_spine_set_logical_compaction(mzgpu_reduce_input_trace(q->reduce), t);
   return st;

@@ -1067,7 +1067,34 @@ struct mzgpu_spine {
     bool has_merge = false;
     u64 merge_since = 0;
     u64 remaining = 0;
+    // The work of a merge is the exact length of its inputs.  An input that was itself
+    // just produced by a merge still has its length on the device; rather than wait for
+    // it, the fuel applied meanwhile is remembered and `remaining` is settled later
+    // (remaining = max(0, work - fuel applied), exactly what repeated saturating
+    // subtraction gives), unless the decision "does this fuel complete the merge?"
+    // really depends on the unknown length.
+    bool lazy_work = false;
+    u64 fuel_debt = 0;
   };
+  // settle a lazily accounted merge; returns false if a length is still on the device
+  static bool settle(Layer& m, bool force) {
+    if (!m.lazy_work) return true;
+    for (auto* b : m.batches)
+      if (!b->st.known) {
+        if (b->st.try_resolve())
+          b->len_ub = b->st.v[0];
+        else if (force)
+          blen(b);
+        else
+          return false;
+      }
+    u64 work = 0;
+    for (auto* b : m.batches) work += b->st.v[0];
+    m.remaining = work - std::min(work, m.fuel_debt);
+    m.lazy_work = false;
+    m.fuel_debt = 0;
+    return true;
+  }
   mzgpu_ctx* ctx;
   uint32_t rb;
   u64 effort = 1;
@@ -1102,15 +1129,15 @@ struct mzgpu_spine {
     return true;
   }
   void begin_merge(Layer& m, bool with_frontier) {
-    u64 s = 0, work = 0;
-    for (auto* b : m.batches) {
-      s = std::max(s, b->desc.since);
-      work += blen(b);
-    }
+    u64 s = 0;
+    for (auto* b : m.batches) s = std::max(s, b->desc.since);
     if (with_frontier) s = std::max(s, since);
     m.has_merge = true;
     m.merge_since = s;
-    m.remaining = work;
+    m.lazy_work = true;
+    m.fuel_debt = 0;
+    m.remaining = 0;
+    settle(m, false);
   }
   void insert_at(mzgpu_batch* b, size_t index) {
     while (merging.size() <= index) merging.push_back(Layer());
@@ -1134,7 +1161,7 @@ struct mzgpu_spine {
     mzgpu_batch *b1 = m.batches[0], *b2 = m.batches[1];
     mzgpu_batch* out = nullptr;
     int32_t st;
-    if (blen(b1) == 0 && blen(b2) == 0) {
+    if (b1->st.known && b2->st.known && b1->st.v[0] == 0 && b2->st.v[0] == 0) {
       mzgpu_desc d = {b1->desc.lower, b2->desc.upper, m.merge_since};
       st = make_empty_batch(ctx, rb, d, &out);
     } else if (ctx->use_side && ctx->stream == ctx->main_stream && !ctx->profile &&
@@ -1166,6 +1193,25 @@ struct mzgpu_spine {
       Layer& m = merging[index];
       if (m.has_merge) {
         u64 f = fuel_in < 0 ? 0 : (u64)fuel_in;
+        if (m.lazy_work && !settle(m, false)) {
+          // bounds on the work: unknown lengths lie in [0, len_ub]
+          u64 lo = 0, hi = 0;
+          for (auto* b : m.batches) {
+            lo += b->st.known ? b->st.v[0] : 0;
+            hi += b->st.known ? b->st.v[0] : b->len_ub;
+          }
+          const u64 total = m.fuel_debt + f;
+          if (total >= hi) {
+            m.lazy_work = false;  // completes whatever the exact length is
+            m.remaining = 0;
+            f = 0;
+          } else if (total < lo) {
+            m.fuel_debt = total;  // cannot complete yet: settle later
+            continue;
+          } else {
+            settle(m, true);  // the decision depends on the exact length
+          }
+        }
         m.remaining -= std::min(f, m.remaining);
       }
       if (m.has_merge && m.remaining == 0) {
@@ -1380,7 +1426,8 @@ extern "C" int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint
   uint32_t n = 0;
   for (size_t i = s->merging.size(); i-- > 0;) {
     if (n >= cap_layers) return MZGPU_E_CAPACITY;
-    const auto& m = s->merging[i];
+    auto& m = const_cast<mzgpu_spine*>(s)->merging[i];
+    if (m.has_merge) mzgpu_spine::settle(m, true);
     out4[4 * n + 0] = m.batches.size();
     out4[4 * n + 1] = m.batches.size() > 0 ? blen(m.batches[0]) : 0;
     out4[4 * n + 2] = m.batches.size() > 1 ? blen(m.batches[1]) : 0;
