@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
       }
     }
   }
-  grid_barrier(&ctl->barrier, G, epoch);
+  // (a merge needs nothing of phase 0 before its own first barrier)
+  if (!a.merge) grid_barrier(&ctl->barrier, G, epoch);
 
   // ---- plan (every CTA computes the same plan from the global min/max)
   if (tid == 0) {
@@ -928,8 +929,19 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
       return false;
     };
     const u64 n_groups = (n + (u64)FT * MV - 1) / ((u64)FT * MV);
+    __shared__ u32 s_tc[MV];
+    auto keys_differ = [&](const u64* x, const u64* y) -> bool {
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (x[k] != y[k]) return true;
+      return false;
+    };
     for (u64 u = c; u < n_groups; u += G) {
       const u64 o0 = (u * FT + tid) * MV;
+      __syncthreads();
+      if (tid < MV) s_tc[tid] = 0;
+      __syncthreads();
+      u32 heads = 0;
       if (o0 < n) {
         u64 lo = o0 > nb ? o0 - nb : 0, hi = o0 < na ? o0 : na;
         while (lo < hi) {
@@ -941,6 +953,20 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
             hi = mid;
         }
         u64 ia = lo, ib = o0 - lo;
+        // the output just before mine (ties put the B row later), times advanced
+        u64 prev[NW];
+        bool have_prev = o0 > 0;
+        if (have_prev) {
+          const bool use_b = ib > 0 && (ia == 0 || !less_ba(a.b + (ib - 1) * NW, a.a + (ia - 1) * NW));
+          if (use_b)
+            load_row<NW>(a.b, ib - 1, prev);
+          else
+            load_row<NW>(a.a, ia - 1, prev);
+          if (TW >= 0) {
+            u64& t = prev[TW >= 0 ? TW : 0];
+            t = t < since ? since : t;
+          }
+        }
 #pragma unroll
         for (int k = 0; k < MV; ++k) {
           const u64 o = o0 + k;
@@ -956,20 +982,33 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
             t = t < since ? since : t;
           }
           store_row<NW>(a.sorted, o, r);
+          if (!have_prev || keys_differ(r, prev)) ++heads;
+          have_prev = true;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) prev[w] = r[w];
         }
+      }
+      // head counts of the 256-row tiles of this group (64 threads each)
+      if (heads) atomicAdd(&s_tc[tid / (FT / MV)], heads);
+      __syncthreads();
+      if (tid < MV) {
+        const u64 tile = u * MV + tid;
+        if (tile < U) a.tile_cnt[tile] = s_tc[tid];
       }
     }
   }
   grid_barrier(&ctl->barrier, G, epoch);
   PHASE_STAMP(3);
-  for (u64 u = c; u < U; u += G) {
-    const u64 i = u * FT + tid;
-    u32 flag = i < n ? is_head(i) : 0u;
-    u32 total;
-    block_exclusive_scan(flag, sm_scan, &total);
-    if (tid == 0) a.tile_cnt[u] = total;
+  if (!a.merge) {  // (the merge phase has already counted the heads of every tile)
+    for (u64 u = c; u < U; u += G) {
+      const u64 i = u * FT + tid;
+      u32 flag = i < n ? is_head(i) : 0u;
+      u32 total;
+      block_exclusive_scan(flag, sm_scan, &total);
+      if (tid == 0) a.tile_cnt[u] = total;
+    }
+    grid_barrier(&ctl->barrier, G, epoch);
   }
-  grid_barrier(&ctl->barrier, G, epoch);
 
   PHASE_STAMP(4);
   // ---- segmented sums
