@@ -157,6 +157,21 @@ def workload_config(sf_per_gpu, n):
     }
 
 
+class stdout_to_stderr:
+    """fd-level redirect: NCCL prints its version banner to stdout during communicator
+    creation; the contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ------------------------------------------------------------------- ours
 def run_ours(args, rank, world, local_rank):
     import numpy as np
@@ -169,9 +184,13 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout: one JSON line only
+
         dist = dist_mod
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     ctx = mz.Context(local_rank, rank, world)
     if world > 1:
@@ -184,10 +203,16 @@ def run_ours(args, rank, world, local_rank):
         idbuf = (C.c_uint8 * F.COMM_ID_BYTES)()
         if rank == 0:
             ctx.check(F.lib.mzgpu_comm_unique_id(idbuf))
-        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
+        with stdout_to_stderr():
+            t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
         idbuf = (C.c_uint8 * F.COMM_ID_BYTES)(*t.cpu().tolist())
-        ctx.check(F.lib.mzgpu_comm_init(ctx.h, idbuf))
+        with stdout_to_stderr():
+            ctx.check(F.lib.mzgpu_comm_init(ctx.h, idbuf))
+            # first collectives on both communicators (lazy NCCL initialisation prints here)
+            w = torch.zeros(1, device="cuda")
+            dist.all_reduce(w)
+            torch.cuda.synchronize()
 
     def barrier():
         ctx.sync()

@@ -715,5 +715,9 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
                               int agg_kind, DevMem* out, u64* n_out);
 
 // exchange.cu
+#define MZ_MAX_EXCHANGE 8
+int32_t mz_partition_many(mzgpu_ctx* ctx, u32 k, const int* row_bytes, const void* const* d_rows, const DLen* n,
+                          const u64* n_ub, u32 peers, void* const* d_out, u64* d_counts, u64* d_cursors,
+                          u64* d_send_by_peer /* [peer][k] */);
 int32_t mz_partition(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, DLen n, u64 n_ub, u32 peers, void* d_out,
                      u64* d_counts /* 64 words */, u64* d_cursors /* 64 words */);

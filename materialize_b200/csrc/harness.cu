@@ -137,6 +137,7 @@ struct mzh_q3 {
   int fill_slot = 0, run_slot = 0;
   bool static_rel[4] = {true, false, false, false};  // relations the generator never updates after hydration
   bool stepping = false;                             // false while hydrating
+  bool streams_prepared = false;                     // stage-0 streams already mapped + exchanged
 };
 
 static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, int n_versions, uint64_t t,
@@ -207,6 +208,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   bool active[3];
   for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
     active[path] = !(q->static_rel[q->plan.source[path]] && q->stepping);
+    if (q->streams_prepared) continue;  // mapped and exchanged together with the inputs (mzh_q3_step)
     st = mzgpu_buf_clear(q->pstream[path]);
     // as_of rule: only the first relation's path sees the updates at as_of (= 0)
     if (st == MZGPU_OK && active[path])
@@ -214,7 +216,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
                                path == 0 ? MZGPU_FRONTIER_EMPTY : 0, q->pstream[path]);
   }
   for (int s = 0; s < 2 && st == MZGPU_OK; ++s) {
-    if (q->peers > 1) {  // half_join exchanges its stream by key
+    if (q->peers > 1 && !(s == 0 && q->streams_prepared)) {  // half_join exchanges its stream by key
       mzgpu_buf *ins[3], *outs[3];
       uint32_t k = 0;
       for (int path = 0; path < 3; ++path)
@@ -251,6 +253,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   for (int a = 0; a < 4; ++a)
     if (batch[a]) mzgpu_batch_release(batch[a]);
   q->maintain_upper = upper;
+  q->streams_prepared = false;
   return st;
 }
 
@@ -479,7 +482,7 @@ int32_t mzh_q3_step(mzh_q3* q) {
   const uint64_t t = q->next_time;
   if (q->peers > 1) {
     // the arrangement inputs of one timestamp share one exchange round
-    mzgpu_buf *ins[4], *outs[4];
+    mzgpu_buf *ins[8], *outs[8];
     uint32_t k = 0;
     for (int a = 0; a < 4; ++a)
       if (!q->static_rel[a]) {
@@ -487,9 +490,26 @@ int32_t mzh_q3_step(mzh_q3* q) {
         outs[k] = q->axchg[a];
         ++k;
       }
+    // ... and so do the delta paths' update streams: build_update_stream is a per-row map, so
+    // it can run on the raw input rows before they are exchanged (the multiset of stream rows
+    // is the one the consolidated batch would give) — one exchange round fewer per timestamp
+    uint32_t first_stream = k;
+    for (int path = 0; path < 3; ++path) {
+      const int src = q->plan.source[path];
+      if (q->static_rel[src]) continue;
+      H_TRY(mzgpu_buf_clear(q->pstream[path]));
+      H_TRY(mzgpu_map_rows(q->ctx, (const mzgpu_r32*)mzgpu_buf_device_ptr(q->input[src]), mzgpu_buf_len(q->input[src]),
+                           MZGPU_MEM_DEVICE, &q->plan.initial[path], q->pstream[path]));
+      ins[k] = q->pstream[path];
+      outs[k] = q->pxchg[path];
+      ++k;
+    }
     H_TRY(mzgpu_exchange_many(q->ctx, k, ins, outs));
     for (int a = 0; a < 4; ++a)
       if (!q->static_rel[a]) H_TRY(mzgpu_batcher_push_buf(q->batcher[a], q->axchg[a]));
+    for (int path = 0; path < 3; ++path)
+      if (!q->static_rel[q->plan.source[path]]) std::swap(q->pstream[path], q->pxchg[path]);
+    q->streams_prepared = first_stream < k;
   } else {
     for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
   }

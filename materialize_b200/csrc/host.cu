@@ -1943,7 +1943,6 @@ extern "C" int32_t mzgpu_comm_init(mzgpu_ctx* ctx, const uint8_t id[MZGPU_COMM_I
 // k independent exchanges in one round: one partition per buffer, ONE counts
 // all-to-all, ONE host wait (NCCL message sizes are host arguments), ONE payload
 // all-to-all.  All peers must call with the same k (identical dataflows).
-#define MZ_MAX_EXCHANGE 8
 extern "C" int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs) {
   MZ_CHECK_CTX(ctx);
   if (k == 0) return MZGPU_OK;
@@ -1999,15 +1998,22 @@ extern "C" int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** i
   u64* d_cur = d_cnt + MZ_MAX_EXCHANGE * 64;          // [e][64] cursors
   u64* d_sendT = d_cur + MZ_MAX_EXCHANGE * 64;        // [p][k] send counts grouped by peer
   u64* d_recvT = d_sendT + MZ_MAX_EXCHANGE * 64;      // [p][k] recv counts grouped by peer
-  for (uint32_t e = 0; e < k; ++e) {
-    MZ_TRY(parts[e].alloc(ctx, std::max<u64>(ins[e]->ub, 1) * ins[e]->rb));
-    MZ_TRY(mz_partition(ctx, ins[e]->rb, ins[e]->mem.p, buf_dlen(ins[e]), ins[e]->ub, P, parts[e].p,
-                        d_cnt + e * 64, d_cur + e * 64));
+  {
+    int rbs[MZ_MAX_EXCHANGE];
+    const void* srcs[MZ_MAX_EXCHANGE];
+    void* dsts[MZ_MAX_EXCHANGE];
+    DLen ns[MZ_MAX_EXCHANGE];
+    u64 ubs[MZ_MAX_EXCHANGE];
+    for (uint32_t e = 0; e < k; ++e) {
+      MZ_TRY(parts[e].alloc(ctx, std::max<u64>(ins[e]->ub, 1) * ins[e]->rb));
+      rbs[e] = (int)ins[e]->rb;
+      srcs[e] = ins[e]->mem.p;
+      dsts[e] = parts[e].p;
+      ns[e] = buf_dlen(ins[e]);
+      ubs[e] = ins[e]->ub;
+    }
+    MZ_TRY(mz_partition_many(ctx, k, rbs, srcs, ns, ubs, P, dsts, d_cnt, d_cur, d_sendT));
   }
-  // transpose [e][p] -> [p][e] with k*P tiny copies folded into one 2D copy per exchange
-  for (uint32_t e = 0; e < k; ++e)
-    MZ_CUDA(ctx, cudaMemcpy2DAsync(d_sendT + e, (size_t)k * 8, d_cnt + e * 64, 8, 8, P, cudaMemcpyDeviceToDevice,
-                                   ctx->stream));
   // 2. counts all-to-all: k words per peer
   NCCL_TRY(gstart());
   for (u32 p = 0; p < P; ++p) {
