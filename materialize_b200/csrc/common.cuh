@@ -31,6 +31,8 @@ struct mzgpu_ctx {
   u64* h_scratch = nullptr;  // 64 words
   u64* d_scratch = nullptr;  // 64 words
   u64* h_big = nullptr;      // pinned, 512 words (exchange counts)
+  u64 last_minmax[12] = {0};  // min/max of every key word seen by the last bulk sort (mz_sort_perm)
+  bool last_minmax_valid = false;
   // pinned bounce buffers for host<->device row copies
   void* h_bounce = nullptr;
   size_t h_bounce_bytes = 0;

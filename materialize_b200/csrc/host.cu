@@ -963,6 +963,7 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
       src = all.p;
       sn = dlen_of(alen, aword);
     }
+    ctx->last_minmax_valid = false;
     MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
     MZ_TRY(clen.resolve());
     b->segs.clear();
@@ -970,7 +971,11 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     const u64 n_cons = clen.v[0];
     b->frontier = MZGPU_FRONTIER_EMPTY;
     b->frontier_known = true;
-    if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0) {
+    // the bulk sort has seen the range of the time word: if every buffered time precedes
+    // `upper` everything ships and the extract pass (two more copies of the rows) is skipped
+    const int tw = b->rb == 32 ? 2 : 1;
+    const bool all_ship = ctx->last_minmax_valid && ctx->last_minmax[2 * tw + 1] < upper;
+    if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0 || all_ship) {
       MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
     } else {
       DevMem ship, keep;

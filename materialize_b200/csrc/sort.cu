@@ -253,6 +253,8 @@ int32_t sort_perm_t(mzgpu_ctx* ctx, const u64* d_rows, u64 n, DevMem* perm_out) 
                                ctx->stream));
   MZ_SYNC(ctx);
   ctx->stats.d2h_bytes += 2 * NK * 8;
+  for (int k = 0; k < 2 * NK; ++k) ctx->last_minmax[k] = ctx->h_scratch[k];
+  ctx->last_minmax_valid = true;
   // 2. plan chunks of <= 64 composite bits, least significant word first
   int wbits[NK];
   u64 wmin[NK];

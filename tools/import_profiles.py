@@ -23,10 +23,7 @@ if os.path.exists(os.path.join(G, f"{tag}_launches.csv")):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), os.path.join(G, f"{tag}_launches.csv"), "0"],
                              capture_output=True, text=True).stdout
         if skip is None:
-            total = int(txt.split()[1])
-            per_step = 18
-            skip_n = max(0, total - 15 * per_step - 30)
-            txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), os.path.join(G, f"{tag}_launches.csv"), str(skip_n)],
+            txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), os.path.join(G, f"{tag}_launches.csv"), "after:k_gen_orders"],
                                  capture_output=True, text=True).stdout
         open(os.path.join(P, f"{out_tag}_ncu_launches_{name}_summary.txt"), "w").write(txt)
 for k in ("fused", "probe", "onesweep", "probe_bulk"):

@@ -13,7 +13,17 @@ with open(sys.argv[1]) as f:
 rd = csv.reader(lines)
 hdr = next(rd)
 ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+# second argument: a number of launches to skip, or "after:<kernel>" = everything after the
+# last launch of <kernel> (bench.py stages all batches with k_gen_orders before the timed loops)
+skip_arg = sys.argv[2] if len(sys.argv) > 2 else "0"
+all_rows = [r for r in rd if len(r) > iv and r[im] == "gpu__time_duration.sum"]
+if skip_arg.startswith("after:"):
+    pat = skip_arg[6:]
+    last = max([i for i, r in enumerate(all_rows) if pat in r[ik]] or [-1])
+    skip = last + 1
+else:
+    skip = int(skip_arg)
+rd = iter(all_rows)
 agg = OrderedDict()
 n = 0
 for r in rd:
