@@ -392,6 +392,99 @@ def test_reduce_large_i128_sums(mz, ctx, oracle):
     same(gr.step(a, 2), orr.step(a, 2))
 
 
+# ------------------------------------------------------------ edge cases
+def test_empty_inputs_everywhere(mz, ctx, oracle):
+    """Zero-row inputs through every entry point (empty containers are routine in timely)."""
+    e32 = np.zeros(0, dtype=oracle.R32)
+    e16 = np.zeros(0, dtype=oracle.R16)
+    same(ctx.consolidate(e32), e32)
+    same(ctx.consolidate(e16), e16)
+    gb, ob = mz.Batcher(ctx, 32), oracle.Batcher(32)
+    gb.push_container(e32)
+    ob.push(e32)
+    g, o = gb.seal(3), ob.seal(3)
+    same(g.rows(), o.rows())
+    assert len(g) == 0 and g.desc() == o.desc() and gb.frontier() == ob.frontier() == mz.FRONTIER_EMPTY
+    gs, os_ = mz.Spine(ctx, 32), oracle.Spine(32, 1, True)
+    gs.insert(g)
+    os_.insert(o)
+    gs.set_physical_compaction(3)
+    os_.set_physical_compaction(3)
+    assert gs.layers() == os_.layers()
+    # probes: empty stream against a non-empty trace, non-empty stream against an empty trace
+    rng = np.random.default_rng(41)
+    a = rand_r32(rng, 500, 50, 1 << 10, 1, dtype=oracle.R32)
+    a["time"] = 3
+    same(mz.half_join(ctx, a, gs, 0), oracle.half_join(a, os_, 0))
+    gs.insert(mz.Batch.build(ctx, a, 3, 4))
+    os_.insert(oracle.Batch.build(a, 3, 4))
+    same(mz.half_join(ctx, e32, gs, 1), oracle.half_join(e32, os_, 1))
+    same(mz.update_stream(ctx, g), oracle.update_stream(o))
+    same(mz.map_rows(ctx, e32, None), e32)
+    # reduce: an activation without input, then one whose input cancels completely
+    gr, orr = mz.ReduceAccumulable(ctx, 0), oracle.Reduce(0)
+    same(gr.step(e32, 1), orr.step(e32, 1))
+    b = rand_r32(rng, 300, 20, 1 << 10, 1, dtype=oracle.R32)
+    b["time"] = 1
+    b["diff"] = 1
+    c = b.copy()
+    c["diff"] = -1
+    both = np.concatenate([b, c])
+    same(gr.step(both, 2), orr.step(both, 2))
+    assert len(ctx.consolidate(both)) == 0
+    same(gr.step(b, 3), orr.step(b, 3))
+    # merge of two empty batches, and of an empty with a non-empty one
+    m1 = mz.Batch.build(ctx, e32, 0, 1).merge(mz.Batch.build(ctx, e32, 1, 2), 0)
+    assert len(m1) == 0 and m1.desc() == (0, 2, 0)
+    m2 = mz.Batch.build(ctx, e32, 0, 1).merge(mz.Batch.build(ctx, a, 1, 4), 2)
+    o2 = oracle.Batch.build(e32, 0, 1).merge(oracle.Batch.build(a, 1, 4), 2)
+    same(m2.rows(), o2.rows())
+
+
+def test_extreme_values_and_single_rows(mz, ctx, oracle):
+    """u64 extremes in every key word, i64 extremes and wrapping in the diffs, one-row inputs."""
+    M = 2**64 - 1
+    rows = [(0, 0, 0, 1), (M, M, 7, -1), (M, 0, 7, 2**63 - 1), (M, 0, 7, 2**63 - 1), (0, M, 0, -(2**63)),
+            (0, M, 0, -(2**63)), (1, 1, 1, 5), (1, 1, 1, -5), (M - 1, M - 1, 6, 3)]
+    a = oracle.rows(oracle.R32, rows)
+    same(ctx.consolidate(a), oracle.consolidate(a))
+    one = oracle.rows(oracle.R32, [(M, M, 5, -7)])
+    same(ctx.consolidate(one), one)
+    g, o = mz.Batch.build(ctx, a, 0, 8), oracle.Batch.build(a, 0, 8)
+    same(g.rows(), o.rows())
+    assert g.keys() == o.keys()
+    gs, os_ = mz.Spine(ctx, 32), oracle.Spine(32, 1, True)
+    gs.insert(g)
+    os_.insert(o)
+    stream = oracle.rows(oracle.R32, [(M, 9, 8, 2), (0, 9, 8, -3), (5, 9, 8, 1), (M - 1, 9, 8, 2**62)])
+    for cmp_mode in (0, 1):
+        same(mz.half_join(ctx, stream, gs, cmp_mode), oracle.half_join(stream, os_, cmp_mode))
+    r16 = oracle.rows(oracle.R16, [(M, 1), (0, -1), (M, -1), (0, 2**63 - 1), (0, 2**63 - 1), (7, 0)])
+    same(ctx.consolidate(r16), oracle.consolidate(r16))
+
+
+def test_hash_index_collisions(mz, ctx, oracle):
+    """Many distinct keys packed into few hash slots' neighbourhoods (long linear-probe chains):
+    a batch of dense keys 0..n-1 fills its open-addressing table to the 0.5 load factor; every key
+    and a comparable number of absent keys are probed."""
+    rng = np.random.default_rng(43)
+    n = 70000
+    a = np.zeros(n, dtype=oracle.R32)
+    a["key"] = np.arange(n, dtype=np.uint64) * np.uint64(1 << 20)  # same low bits: the mixer must spread them
+    a["val"] = rng.integers(0, 1 << 30, size=n, dtype=np.uint64)
+    a["diff"] = 1
+    gs, os_ = mz.Spine(ctx, 32), oracle.Spine(32, 1, True)
+    gs.insert(mz.Batch.build(ctx, a, 0, 1))
+    os_.insert(oracle.Batch.build(a, 0, 1))
+    stream = np.zeros(2 * n, dtype=oracle.R32)
+    stream["key"] = np.concatenate([a["key"], a["key"] + np.uint64(1)])
+    stream["val"] = np.arange(2 * n, dtype=np.uint64)
+    stream["time"] = 1
+    stream["diff"] = 1
+    rng.shuffle(stream)
+    same(mz.half_join(ctx, stream, gs, 0), oracle.half_join(stream, os_, 0))
+
+
 # ------------------------------------------ device-resident operator chaining
 def test_chained_operators_no_readback(mz, ctx, oracle):
     """arrange -> update_stream -> half_join x2 -> reduce with every intermediate in a device
