@@ -28,7 +28,8 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
   const u64 h0 = mix64(key);
   // The first slot of several batches is fetched before any of them is looked at:
   // the loads are independent, so a probe against a trace of many batches costs
-  // about one memory latency per group instead of one per batch.
+  // about one memory latency per group instead of one per batch (update-batch probes
+  // take eight batches per group).
   for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
     ulonglong2 slot[GROUP];
     u64 hh[GROUP], mask[GROUP];
@@ -93,12 +94,19 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // chained with a decoupled look-back, so the output order is exactly the
 // two-pass order (stream order x batch order x row order) and nothing returns
 // to the host.
+// One compact walk serves both passes (the kernel used to inline two unrolled copies of the
+// walk and of the closure per batch group: 34K instructions, bound by instruction fetch).
+// Pass 0 counts the matches and keeps the first KC output rows in a per-thread cache; after the
+// scan + look-back the cached rows are written, and only a probe row with more than KC matches
+// walks the trace again (pass 1).
 template <int OUT_NW>
-__global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+__global__ void __launch_bounds__(PT, 2) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
                                                  u64* __restrict__ out_len, u64* __restrict__ status) {
+  constexpr int KC = 8;
+  constexpr int GROUP = 8;
   __shared__ u32 sm[34];
   __shared__ u32 s_tile;
   __shared__ u64 s_b;
@@ -114,7 +122,6 @@ __global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stre
     const u64 i = (u64)tile * PT + threadIdx.x;
     u64 key = 0, v1 = 0, t1 = 0;
     i64 d1 = 0;
-    u32 cnt = 0;
     if (i < n) {
       const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
       const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
@@ -122,48 +129,108 @@ __global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stre
       v1 = kv.y;
       t1 = td.x;
       d1 = (i64)td.y;
-      for_each_match<4>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
-        if (pp.has_closure) {
-          u64 k, v;
-          if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
-        } else {
-          cnt++;
-        }
-      });
     }
-    u32 total;
-    const u32 ex = block_exclusive_scan(cnt, sm, &total);
-    const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
-    if (i < n && cnt > 0) {
-      u64 pos = base0 + excl + ex;
-      if (pos + cnt > out_cap) {
-        atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
-      } else {
-        for_each_match<4>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
-          u64 t = t1;
-          if (pp.mode == MZ_PROBE_JOIN) {
-            t = t1 > t2 ? t1 : t2;
-            t = t > pp.meet ? t : pp.meet;
-          }
-          u64 d = (u64)d1 * (u64)d2;
-          u64 a = pp.swap_vals ? v2 : v1, b = pp.swap_vals ? v1 : v2;
-          if (OUT_NW == 4) {
-            u64 k, v;
-            if (closure_eval(pp.closure, key, a, b, &k, &v)) {
-              u64 r[4] = {k, v, t, d};
-              store_row<4>(out, pos, r);
-              pos++;
+    u64 cache[KC][OUT_NW];
+    u32 cnt = 0;
+    u64 pos = 0;
+    u32 ex = 0, total = 0;
+    u64 excl = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool walk = i < n && (pass == 0 || cnt > (u32)KC);
+      if (walk) {
+        const u64 h0 = mix64(key);
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
+          // independent first-slot loads of a group of batches, then the (rare) matches
+          ulonglong2 slot[GROUP];
+          u64 hh[GROUP], msk[GROUP];
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            if (b0 + j < tv.n_batches) {
+              const BatchView& bv = tv.b[b0 + j];
+              msk[j] = bv_mask(bv);
+              hh[j] = h0 & msk[j];
+              slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
             }
-          } else {
-            u64* o = out + pos * 5;
-            o[0] = key;
-            o[1] = a;
-            o[2] = b;
-            o[3] = t;
-            o[4] = d;
-            pos++;
           }
-        });
+#pragma unroll 1
+          for (int j = 0; j < GROUP; ++j) {
+            if (b0 + j >= tv.n_batches) break;
+            const BatchView& bv = tv.b[b0 + j];
+            ulonglong2 sl = slot[j];
+            u64 h = hh[j];
+            const u64 mask = msk[j];
+            while (sl.y != 0 && sl.x != key) {
+              h = (h + 1) & mask;
+              sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+            }
+            if (sl.y == 0) continue;
+            const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+            const u32 len = (u32)(sl.y >> 44);
+            const u64 end = len != 0 ? first + len : bv_n(bv);
+#pragma unroll 1
+            for (u64 r = first; r < end; ++r) {
+              const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+              if (len == 0 && rkv.x != key) break;
+              const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+              const u64 t2 = rtd.x;
+              const bool ok = pp.mode == MZ_PROBE_HALF_LE ? t2 <= t1 : (pp.mode == MZ_PROBE_HALF_LT ? t2 < t1 : true);
+              if (!ok) continue;
+              u64 t = t1;
+              if (pp.mode == MZ_PROBE_JOIN) {
+                t = t1 > t2 ? t1 : t2;
+                t = t > pp.meet ? t : pp.meet;
+              }
+              const u64 d = (u64)d1 * rtd.y;
+              const u64 va = pp.swap_vals ? rkv.y : v1, vb = pp.swap_vals ? v1 : rkv.y;
+              u64 row[OUT_NW];
+              if (OUT_NW == 4) {
+                u64 k, v;
+                if (!closure_eval(pp.closure, key, va, vb, &k, &v)) continue;
+                row[0] = k;
+                row[1] = v;
+                row[2] = t;
+                row[3] = d;
+              } else {
+                row[0] = key;
+                row[1] = va;
+                row[2] = vb;
+                row[3] = t;
+                row[OUT_NW - 1] = d;
+              }
+              if (pass == 0) {
+                if (cnt < (u32)KC) {
+#pragma unroll
+                  for (int w = 0; w < OUT_NW; ++w) cache[cnt][w] = row[w];
+                }
+                cnt++;
+              } else {
+                u64* o = out + pos * OUT_NW;
+#pragma unroll
+                for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
+                pos++;
+              }
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+        ex = block_exclusive_scan(cnt, sm, &total);
+        excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
+        pos = base0 + excl + ex;
+        if (i < n && cnt > 0) {
+          if (pos + cnt > out_cap) {
+            atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+            cnt = 0;  // nothing is written (the overflow is reported at the next read-back)
+          } else if (cnt <= (u32)KC) {
+            for (u32 c = 0; c < cnt; ++c) {
+              u64* o = out + (pos + c) * OUT_NW;
+#pragma unroll
+              for (int w = 0; w < OUT_NW; ++w) o[w] = cache[c][w];
+            }
+          }
+        }
       }
     }
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;

@@ -174,7 +174,7 @@ __device__ __forceinline__ void finalize(const u64* S, int agg_kind, u64* o /* c
 // slot of GROUP batches is fetched before any is inspected (independent loads).
 __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) {
   const u64 h0 = mix64(key);
-  constexpr int GROUP = 4;
+  constexpr int GROUP = 8;
   for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
     ulonglong2 slot[GROUP];
     u64 hh[GROUP], mask[GROUP];
