@@ -192,6 +192,16 @@ typedef struct mzgpu_closure {
  * src/compute-types/src/plan/reduce.rs:146-158).  One accumulated column. */
 #define MZGPU_AGG_COUNT_SUM_I64 0 /* COUNT(val), SUM(val) with val: int64   */
 #define MZGPU_AGG_COUNT_SUM_F64 1 /* COUNT(val), SUM(val) with val: float64 */
+/* ReducePlan::Distinct (build_distinct, src/compute/src/render/reduce.rs:264-334): the
+ * arrangement key is the whole row (val is ignored); the output holds (key, ()) once while
+ * the key's accumulated multiplicity is non-zero.  ROUT rows: count = 1, sums = 0, flags
+ * bit1 = "Non-positive multiplicity in DistinctBy" (the DistinctByErrorCheck reduce). */
+#define MZGPU_AGG_DISTINCT 2
+/* ThresholdPlan::Basic (threshold_arrangement, src/compute/src/render/threshold.rs:33-77):
+ * rows with a positive accumulated multiplicity are kept WITH that multiplicity.  The key is
+ * the whole row; ROUT rows carry count = sums = flags = 0 and diff = the change of
+ * max(multiplicity, 0). */
+#define MZGPU_AGG_THRESHOLD 3
 
 /* ---------------------------------------------------------------- handles */
 typedef struct mzgpu_ctx mzgpu_ctx;         /* one per timely worker / GPU            */

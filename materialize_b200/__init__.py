@@ -10,6 +10,8 @@ no CPU fallback.
 from . import _ffi  # noqa: F401  (loads the CUDA library; raises if absent)
 from .api import (  # noqa: F401
     AGG_COUNT_SUM_F64,
+    AGG_DISTINCT,
+    AGG_THRESHOLD,
     AGG_COUNT_SUM_I64,
     FRONTIER_EMPTY,
     HALFJOIN_LE,

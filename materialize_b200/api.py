@@ -21,6 +21,8 @@ import numpy as np
 from . import _ffi as F
 from ._ffi import (  # noqa: F401  (re-exported)
     AGG_COUNT_SUM_F64,
+    AGG_DISTINCT,
+    AGG_THRESHOLD,
     AGG_COUNT_SUM_I64,
     FRONTIER_EMPTY,
     HALFJOIN_LE,

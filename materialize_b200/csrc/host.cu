@@ -1798,8 +1798,7 @@ struct mzgpu_reduce {
 
 extern "C" int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_reduce** out) {
   MZ_CHECK_CTX(ctx);
-  if (out == nullptr || (agg_kind != MZGPU_AGG_COUNT_SUM_I64 && agg_kind != MZGPU_AGG_COUNT_SUM_F64))
-    return MZGPU_E_INVALID;
+  if (out == nullptr || agg_kind < MZGPU_AGG_COUNT_SUM_I64 || agg_kind > MZGPU_AGG_THRESHOLD) return MZGPU_E_INVALID;
   std::unique_ptr<mzgpu_reduce> r(new mzgpu_reduce());
   r->ctx = ctx;
   r->agg_kind = agg_kind;

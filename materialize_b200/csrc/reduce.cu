@@ -108,6 +108,13 @@ __global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, co
   o[0] = r[0];       // key
   o[1] = r[2];       // time
   o[2] = (u64)diff;  // total
+  if (agg_kind == MZGPU_AGG_DISTINCT || agg_kind == MZGPU_AGG_THRESHOLD) {
+    // only the multiplicity matters (build_distinct / threshold_arrangement)
+#pragma unroll
+    for (int w = 3; w < 10; ++w) o[w] = 0;
+    store_row<10>(out, i, o);
+    continue;
+  }
   o[3] = (u64)diff;  // non_nulls
   u64 alo, ahi;
   u64 pinf = 0, ninf = 0, nan = 0;
@@ -141,6 +148,13 @@ __global__ void __launch_bounds__(RT) k_explode(const u64* __restrict__ rows, co
 // finalize_accum + error-check flag for one accumulated diff S (words 2..8 of a RACC row)
 __device__ __forceinline__ void finalize(const u64* S, int agg_kind, u64* o /* count, sum_lo, sum_hi, flags */) {
   const i64 total = (i64)S[0];
+  if (agg_kind == MZGPU_AGG_DISTINCT) {  // (key, ()) once; error flag for a negative multiplicity
+    o[0] = 1;
+    o[1] = 0;
+    o[2] = 0;
+    o[3] = total < 0 ? 2 : 0;
+    return;
+  }
   const bool accum_zero = (S[1] | S[2] | S[3] | S[4] | S[5] | S[6]) == 0;
   u64 flags = 0;
   if (total > 0 && accum_zero) flags |= 1;
@@ -224,6 +238,26 @@ __device__ __forceinline__ u32 walk_key(const u64* __restrict__ rows, u64 n, u64
   u64 S[8];
 #pragma unroll
   for (int w = 0; w < 8; ++w) S[w] = S0[w];
+  if (agg_kind == MZGPU_AGG_THRESHOLD) {
+    // output multiplicity = max(accumulated multiplicity, 0); one row per change, diff = the change
+    i64 mult = (i64)S[0] > 0 ? (i64)S[0] : 0;
+    u32 c = 0;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 10;
+      if (row[0] != key) break;
+      S[0] += row[2];
+      const i64 m2 = (i64)S[0] > 0 ? (i64)S[0] : 0;
+      if (m2 != mult) {
+        if (do_write) {
+          u64 r[8] = {key, 0, 0, 0, 0, row[1], (u64)(m2 - mult), 0};
+          store_row<8>(out, pos + c, r);
+        }
+        ++c;
+      }
+      mult = m2;
+    }
+    return c;
+  }
   bool had = !diff_is_zero<8>(S);
   u64 oldv[4] = {0, 0, 0, 0};
   if (had) finalize(S, agg_kind, oldv);

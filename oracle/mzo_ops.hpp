@@ -359,6 +359,7 @@ static inline mzgpu_racc explode_row(const mzgpu_r32& r, int agg_kind) {
   a.key = r.key;
   a.time = r.time;
   a.total = r.diff;
+  if (agg_kind == MZGPU_AGG_DISTINCT || agg_kind == MZGPU_AGG_THRESHOLD) return a;  // only the multiplicity matters
   a.non_nulls = r.diff;
   i128 acc;
   if (agg_kind == MZGPU_AGG_COUNT_SUM_F64) {
@@ -383,6 +384,12 @@ static inline mzgpu_racc explode_row(const mzgpu_r32& r, int agg_kind) {
 static inline void finalize_row(const mzgpu_racc& s, int agg_kind, mzgpu_rout* o) {
   std::memset(o, 0, sizeof(*o));
   o->key = s.key;
+  if (agg_kind == MZGPU_AGG_DISTINCT) {  // build_distinct: (key, ()) once; error row if the count is negative
+    o->count = 1;
+    if (s.total < 0) o->flags |= 2;
+    return;
+  }
+  if (agg_kind == MZGPU_AGG_THRESHOLD) return;  // unit value; the multiplicity travels in the diff
   o->count = s.non_nulls;
   bool accum_zero = s.acc_lo == 0 && s.acc_hi == 0 && s.non_nulls == 0 && s.pos_infs == 0 &&
                     s.neg_infs == 0 && s.nans == 0;
@@ -463,20 +470,23 @@ struct ReduceAccumulable {
           bool had = it != output.end();
           mzgpu_rout fresh;
           bool has = !Tr<mzgpu_racc>::zero(s);
+          // threshold_arrangement keeps (record, count) only while count is positive
+          if (agg_kind == MZGPU_AGG_THRESHOLD) has = s.total > 0;
+          const int64_t mult = agg_kind == MZGPU_AGG_THRESHOLD ? s.total : 1;
           if (has) finalize_row(s, agg_kind, &fresh);
           if (had) {
             mzgpu_rout old = it->second;
             old.time = t;
-            old.diff = -1;
+            old.diff = -old.diff;  // the multiplicity the output held
             local.push_back(old);
           }
           if (has) {
             fresh.time = t;
-            fresh.diff = 1;
+            fresh.diff = mult;
             local.push_back(fresh);
             mzgpu_rout keep = fresh;
             keep.time = 0;
-            keep.diff = 1;
+            keep.diff = mult;
             output[key] = keep;
           } else if (had) {
             output.erase(it);

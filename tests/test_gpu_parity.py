@@ -376,6 +376,24 @@ def test_reduce_accumulable_matches_oracle(mz, ctx, oracle, agg_kind):
     same(gr.input_trace().export(), oracle.consolidate(gr.input_trace().export()))
 
 
+@pytest.mark.parametrize("agg_kind", [2, 3])
+def test_reduce_distinct_and_threshold_match_oracle(mz, ctx, oracle, agg_kind):
+    """ReducePlan::Distinct (reduce.rs:264-334) and ThresholdPlan::Basic (threshold.rs:33-77) as
+    instances of the same reduce operator: multiplicities go negative, return to zero, recover."""
+    rng = np.random.default_rng(50 + agg_kind)
+    gr, orr = mz.ReduceAccumulable(ctx, agg_kind), oracle.Reduce(agg_kind)
+    t = 0
+    for step in range(10):
+        n = int(rng.integers(1, 5000))
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 400, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 1 << 30, size=n, dtype=np.uint64)  # ignored by both plans
+        a["time"] = rng.integers(t, t + 3, size=n, dtype=np.uint64)
+        a["diff"] = rng.integers(-3, 4, size=n, dtype=np.int64)
+        t += 3
+        same(gr.step(a, t), orr.step(a, t))
+
+
 def test_reduce_large_i128_sums(mz, ctx, oracle):
     """i128 accumulation with carries: sums far beyond i64."""
     a = np.zeros(40000, dtype=oracle.R32)

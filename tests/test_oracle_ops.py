@@ -187,3 +187,36 @@ def test_q3_workers_agree(oracle):
             outs.append(q.drain())
         res.append(np.concatenate(outs).tobytes())
     assert res[0] == res[1] == res[2]
+
+
+def test_distinct_and_threshold_accumulate_to_their_definitions():
+    """ReducePlan::Distinct keeps (key, ()) once while the multiplicity is non-zero (error flag when it is
+    negative, reduce.rs:264-334); ThresholdPlan::Basic keeps a row with its multiplicity while that is
+    positive (threshold.rs:33-77).  The oracle's output corrections must accumulate to exactly that at
+    every time."""
+    import numpy as np
+
+    from oracle import binding as oracle
+
+    rng = np.random.default_rng(3)
+    for kind in (2, 3):
+        r = oracle.Reduce(kind)
+        acc, out_acc = {}, {}
+        for step in range(6):
+            n = 2000
+            a = np.zeros(n, dtype=oracle.R32)
+            a["key"] = rng.integers(0, 150, size=n, dtype=np.uint64)
+            a["time"] = step
+            a["diff"] = rng.integers(-2, 3, size=n)
+            out = r.step(a, step + 1)
+            for k, d in zip(a["key"].tolist(), a["diff"].tolist()):
+                acc[k] = acc.get(k, 0) + d
+            for row in out.tolist():
+                key = (row[0], row[1], row[2], row[3], row[4])
+                out_acc[key] = out_acc.get(key, 0) + row[6]
+            out_acc = {k: v for k, v in out_acc.items() if v}
+            if kind == 2:
+                want = {(k, 1, 0, 0, 2 if c < 0 else 0): 1 for k, c in acc.items() if c != 0}
+            else:
+                want = {(k, 0, 0, 0, 0): c for k, c in acc.items() if c > 0}
+            assert out_acc == want, (kind, step)
