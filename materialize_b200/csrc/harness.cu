@@ -117,6 +117,15 @@ struct mzh_q3 {
   mzgpu_reduce* reduce;
   mzgpu_buf* input[4];  // staged inputs of the next step (device resident)
   mzgpu_buf *results, *xchg, *out;
+  // pipelined result read-back (end-to-end path): timestamps alternate between two output
+  // buffers; the previous timestamp's corrections are copied out on the copy stream while the
+  // current one runs
+  mzgpu_buf* out2 = nullptr;
+  bool pipelined_out = false;
+  cudaEvent_t ev_out[2] = {nullptr, nullptr};
+  mzgpu_buf* out_of[2] = {nullptr, nullptr};
+  bool out_pending[2] = {false, false};
+  int out_parity = 0;
   mzgpu_buf *pstream[3], *pnext[3], *pxchg[3];  // per delta path: stream, next stage, exchange landing
   mzgpu_buf* axchg[4];                           // exchange landing per arrangement input
   DevArr gen_ok, gen_ck, gen_li, gen_cursor;
@@ -125,6 +134,7 @@ struct mzh_q3 {
   uint64_t last_rows_in = 0;
   uint64_t maintain_upper = 0;  // timestamp whose maintenance is still due
   uint64_t h2d_bytes = 0;       // host rows staged through mzh_q3_stage_host
+  uint64_t d2h_bytes = 0;       // output rows copied out through mzh_q3_fetch_out
   // end-to-end path: host batches land in double-buffered device staging through a
   // copy stream, so the H2D copy of the next batch overlaps the current timestamp
   cudaStream_t copy_stream = nullptr;
@@ -249,7 +259,20 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);
     std::swap(q->results, q->xchg);
   }
-  if (st == MZGPU_OK) st = mzgpu_reduce_accumulable_buf(q->reduce, q->results, upper, q->out);
+  mzgpu_buf* out_buf = q->out;
+  if (q->pipelined_out) {
+    q->out_parity ^= 1;
+    out_buf = q->out_of[q->out_parity];
+    if (q->out_pending[q->out_parity]) {  // the output two timestamps back was never fetched: dropped
+      st = mzgpu_buf_clear(out_buf);
+      q->out_pending[q->out_parity] = false;
+    }
+  }
+  if (st == MZGPU_OK) st = mzgpu_reduce_accumulable_buf(q->reduce, q->results, upper, out_buf);
+  if (st == MZGPU_OK && q->pipelined_out) {
+    H_CUDA(cudaEventRecord(q->ev_out[q->out_parity], q->stream));
+    q->out_pending[q->out_parity] = true;
+  }
   for (int a = 0; a < 4; ++a)
     if (batch[a]) mzgpu_batch_release(batch[a]);
   q->maintain_upper = upper;
@@ -335,6 +358,9 @@ void mzh_q3_free(mzh_q3* q) {
   mzgpu_buf_free(q->results);
   mzgpu_buf_free(q->xchg);
   mzgpu_buf_free(q->out);
+  if (q->out2) mzgpu_buf_free(q->out2);
+  for (int i = 0; i < 2; ++i)
+    if (q->ev_out[i]) cudaEventDestroy(q->ev_out[i]);
   delete q;
 }
 
@@ -522,6 +548,48 @@ int32_t mzh_q3_maintain(mzh_q3* q) { return q ? q3_maintenance(q) : MZGPU_E_INVA
 
 // Output corrections (ROUT rows) accumulated since the last clear.
 mzgpu_buf* mzh_q3_out(mzh_q3* q) { return q ? q->out : nullptr; }
+
+// Pipelined result read-back: from now on timestamps alternate between two output buffers.
+int32_t mzh_q3_pipeline_out(mzh_q3* q) {
+  if (q == nullptr) return MZGPU_E_INVALID;
+  if (q->pipelined_out) return MZGPU_OK;
+  if (q->copy_stream == nullptr) H_CUDA(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+  if (q->ev_up[0] == nullptr)
+    for (int i = 0; i < 2; ++i) {
+      H_CUDA(cudaEventCreateWithFlags(&q->ev_up[i], cudaEventDisableTiming));
+      H_CUDA(cudaEventCreateWithFlags(&q->ev_free[i], cudaEventDisableTiming));
+    }
+  H_TRY(mzgpu_buf_new(q->ctx, MZGPU_ROW_ROUT, &q->out2));
+  for (int i = 0; i < 2; ++i) H_CUDA(cudaEventCreateWithFlags(&q->ev_out[i], cudaEventDisableTiming));
+  q->out_of[0] = q->out;
+  q->out_of[1] = q->out2;
+  H_TRY(mzgpu_buf_clear(q->out));
+  q->pipelined_out = true;
+  return MZGPU_OK;
+}
+// Copy out the corrections of a finished timestamp: `which` = 0 the one before the timestamp
+// enqueued last (its kernels have long finished; nothing newer is waited for), 1 the latest
+// (drains the stream's tail).  The copy runs on the copy stream behind the event recorded when
+// that timestamp's reduce was enqueued.  *n = rows copied (0 if nothing is pending).
+int32_t mzh_q3_fetch_out(mzh_q3* q, int32_t which, mzgpu_rout* rows, uint64_t cap, uint64_t* n) {
+  if (q == nullptr || !q->pipelined_out || n == nullptr) return MZGPU_E_INVALID;
+  const int p = which == 0 ? (q->out_parity ^ 1) : q->out_parity;
+  *n = 0;
+  if (!q->out_pending[p]) return MZGPU_OK;
+  mzgpu_buf* b = q->out_of[p];
+  // the length travelled to the host with the read-back of the timestamp that followed (or is
+  // read back now, for the latest timestamp)
+  const uint64_t len = mzgpu_buf_len(b);
+  if (len > cap) return MZGPU_E_CAPACITY;
+  H_CUDA(cudaStreamWaitEvent(q->copy_stream, q->ev_out[p], 0));
+  if (len) H_CUDA(cudaMemcpyAsync(rows, mzgpu_buf_device_ptr(b), len * sizeof(mzgpu_rout), cudaMemcpyDeviceToHost, q->copy_stream));
+  H_CUDA(cudaStreamSynchronize(q->copy_stream));
+  q->d2h_bytes += len * sizeof(mzgpu_rout);
+  *n = len;
+  q->out_pending[p] = false;
+  return mzgpu_buf_clear(b);
+}
+uint64_t mzh_q3_d2h_bytes(mzh_q3* q) { return q ? q->d2h_bytes : 0; }
 int32_t mzh_q3_clear_out(mzh_q3* q) { return q ? mzgpu_buf_clear(q->out) : MZGPU_E_INVALID; }
 uint64_t mzh_q3_time(mzh_q3* q) { return q ? q->next_time : 0; }
 mzgpu_spine* mzh_q3_spine(mzh_q3* q, int32_t a) { return (q && a >= 0 && a < 4) ? q->spine[a] : nullptr; }

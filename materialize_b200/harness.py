@@ -20,6 +20,9 @@ _SIG = {
     "mzh_q3_stage_device": (i32, [vp, i32, vp, u64]),
     "mzh_q3_stage_commit": (i32, [vp]),
     "mzh_q3_h2d_bytes": (u64, [vp]),
+    "mzh_q3_d2h_bytes": (u64, [vp]),
+    "mzh_q3_pipeline_out": (i32, [vp]),
+    "mzh_q3_fetch_out": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_maintain": (i32, [vp]),
     "mzh_q3_input": (vp, [vp, i32]),
     "mzh_q3_staged": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
@@ -62,6 +65,20 @@ class Q3Dataflow:
     def stage_commit(self):
         """The host batch staged with stage_host() is complete (the next step() consumes it)."""
         self.ctx.check(_lib.mzh_q3_stage_commit(self.h))
+
+    def pipeline_out(self):
+        """Alternate output buffers per timestamp so that fetch_out(0) can read the previous
+        timestamp's corrections while the current one runs."""
+        self.ctx.check(_lib.mzh_q3_pipeline_out(self.h))
+
+    def fetch_out(self, which, into):
+        """which=0: corrections of the timestamp before the one enqueued last; 1: the latest."""
+        n = u64(0)
+        self.ctx.check(_lib.mzh_q3_fetch_out(self.h, which, into.ctypes.data_as(vp), len(into), C.byref(n)))
+        return into[: n.value]
+
+    def d2h_bytes(self):
+        return _lib.mzh_q3_d2h_bytes(self.h)
 
     def h2d_bytes(self):
         return _lib.mzh_q3_h2d_bytes(self.h)
