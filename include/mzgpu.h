@@ -202,6 +202,16 @@ typedef struct mzgpu_closure {
  * the whole row; ROUT rows carry count = sums = flags = 0 and diff = the change of
  * max(multiplicity, 0). */
 #define MZGPU_AGG_THRESHOLD 3
+/* MIN(val) / MAX(val) per key: the result of the hierarchical reduce
+ * (build_bucketed / build_bucketed_negated_output, src/compute/src/render/reduce.rs:796-1135):
+ * over the accumulated (value, count) pairs of the key with non-zero count, any non-positive
+ * count yields the error row ("Non-positive accumulation in MinsMaxesHierarchical", flags bit1),
+ * otherwise func(values).  Values compare as unsigned 64-bit integers.  ROUT rows: sum_lo = the
+ * aggregate, count = sum_hi = 0.  The reference buckets large groups into a reduction tree; this
+ * operator evaluates a key's values directly and reports MZGPU_E_UNSUPPORTED (at the next
+ * read-back) for a key with more than 32 distinct live values. */
+#define MZGPU_AGG_MIN 4
+#define MZGPU_AGG_MAX 5
 
 /* ---------------------------------------------------------------- handles */
 typedef struct mzgpu_ctx mzgpu_ctx;         /* one per timely worker / GPU            */

@@ -12,6 +12,8 @@ from .api import (  # noqa: F401
     AGG_COUNT_SUM_F64,
     AGG_DISTINCT,
     AGG_THRESHOLD,
+    AGG_MIN,
+    AGG_MAX,
     AGG_COUNT_SUM_I64,
     FRONTIER_EMPTY,
     HALFJOIN_LE,

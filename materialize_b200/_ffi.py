@@ -57,7 +57,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 FRONTIER_EMPTY = 2**64 - 1
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NCCL, E_FRONTIER = 0, -1, -2, -3, -4, -5, -6
 HALFJOIN_LE, HALFJOIN_LT = 0, 1
-AGG_COUNT_SUM_I64, AGG_COUNT_SUM_F64, AGG_DISTINCT, AGG_THRESHOLD = 0, 1, 2, 3
+AGG_COUNT_SUM_I64, AGG_COUNT_SUM_F64, AGG_DISTINCT, AGG_THRESHOLD, AGG_MIN, AGG_MAX = 0, 1, 2, 3, 4, 5
 COMM_ID_BYTES = 128
 
 

@@ -23,6 +23,8 @@ from ._ffi import (  # noqa: F401  (re-exported)
     AGG_COUNT_SUM_F64,
     AGG_DISTINCT,
     AGG_THRESHOLD,
+    AGG_MIN,
+    AGG_MAX,
     AGG_COUNT_SUM_I64,
     FRONTIER_EMPTY,
     HALFJOIN_LE,

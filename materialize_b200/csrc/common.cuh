@@ -24,7 +24,8 @@ struct mzgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
   int num_sms = 148;
-  bool sticky = false;  // a CUDA/NCCL failure happened: every later call fails
+  bool sticky = false;  // a CUDA/NCCL failure (or a deferred device-side report) happened: every later call fails
+  int32_t sticky_code = MZGPU_E_CUDA;  // ... with this status
   std::string last_error;
   mzgpu_stats stats;
   // pinned staging for small device->host reads (counts, min/max)
@@ -51,7 +52,7 @@ struct mzgpu_ctx {
   u32 lb_epoch = 0;            // tag of the next launch (20 bits)
   u32* d_tickets = nullptr;    // MZ_TICKETS zeroed tile counters, handed out round-robin
   u32 ticket_next = 0;
-  u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (bug guard), [1] = rows required
+  u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (rows required), [1] != 0: a MIN/MAX key outgrew its table
   u64* d_dbg = nullptr;  // per-launch phase stamps of the fused kernel while profiling (32 words each)
   u32 dbg_next = 0;
   // control blocks of the fused kernel, a pair per stream (each launch clears the other of its pair)
@@ -121,7 +122,7 @@ struct mzgpu_ctx {
 #define MZ_CHECK_CTX(ctx)                       \
   do {                                          \
     if ((ctx) == nullptr) return MZGPU_E_INVALID; \
-    if ((ctx)->sticky) return MZGPU_E_CUDA;     \
+    if ((ctx)->sticky) return (ctx)->sticky_code; \
   } while (0)
 
 // Brackets one launch with CUDA events on the launching stream when profiling.
@@ -710,6 +711,9 @@ int32_t mz_map_rows_dev(mzgpu_ctx* ctx, const u64* d_rows, u64 n, const mzgpu_cl
 
 // reduce.cu
 int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_kind, u64* d_racc);
+int32_t mz_reduce_minmax_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
+                               const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
+                               u64* d_out_len);
 int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
                                     const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
                                     u64* d_out_len);

@@ -167,7 +167,15 @@ int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
     MZ_SET_ERR(ctx, "internal: a bounded operator output overflowed its capacity (%llu rows required)",
                (unsigned long long)ctx->h_scratch[40]);
     ctx->sticky = true;
+    ctx->sticky_code = MZGPU_E_CAPACITY;
     return MZGPU_E_CAPACITY;
+  }
+  if (ctx->h_scratch[41] != 0) {
+    MZ_SET_ERR(ctx, "MIN/MAX reduce: a key has more than 32 distinct live values (bucketed reduction tree "
+                    "not implemented)");
+    ctx->sticky = true;
+    ctx->sticky_code = MZGPU_E_UNSUPPORTED;
+    return MZGPU_E_UNSUPPORTED;
   }
   return MZGPU_OK;
 }
@@ -1323,7 +1331,7 @@ struct mzgpu_spine {
 static int32_t spine_take_err(mzgpu_spine* s) {
   int32_t e = s->err;
   s->err = MZGPU_OK;
-  if (e == MZGPU_OK && s->ctx->sticky) e = MZGPU_E_CUDA;
+  if (e == MZGPU_OK && s->ctx->sticky) e = s->ctx->sticky_code;
   return e;
 }
 
@@ -1798,12 +1806,14 @@ struct mzgpu_reduce {
 
 extern "C" int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_reduce** out) {
   MZ_CHECK_CTX(ctx);
-  if (out == nullptr || agg_kind < MZGPU_AGG_COUNT_SUM_I64 || agg_kind > MZGPU_AGG_THRESHOLD) return MZGPU_E_INVALID;
+  if (out == nullptr || agg_kind < MZGPU_AGG_COUNT_SUM_I64 || agg_kind > MZGPU_AGG_MAX) return MZGPU_E_INVALID;
   std::unique_ptr<mzgpu_reduce> r(new mzgpu_reduce());
   r->ctx = ctx;
   r->agg_kind = agg_kind;
-  MZ_TRY(mzgpu_batcher_new(ctx, 80, &r->batcher));
-  MZ_TRY(mzgpu_spine_new(ctx, 80, 1, &r->input));
+  // accumulable kinds arrange exploded diffs (RACC); MIN/MAX arranges the (key, value) rows themselves
+  const uint32_t rb = (agg_kind == MZGPU_AGG_MIN || agg_kind == MZGPU_AGG_MAX) ? 32 : 80;
+  MZ_TRY(mzgpu_batcher_new(ctx, rb, &r->batcher));
+  MZ_TRY(mzgpu_spine_new(ctx, rb, 1, &r->input));
   *out = r.release();
   return MZGPU_OK;
 }
@@ -1816,10 +1826,16 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
   // have reached the host with whatever the caller read since (no extra wait)
   MZ_TRY(mzgpu_spine_set_physical_compaction(r->input, r->input->upper));
   // explode_one: values move into the diff; the exploded rows become a stash segment
+  const bool minmax = r->agg_kind == MZGPU_AGG_MIN || r->agg_kind == MZGPU_AGG_MAX;
   if (n_ub) {
     Seg s;
-    MZ_TRY(s.rows.alloc(ctx, n_ub * 80));
-    MZ_TRY(mz_explode(ctx, d_rows, n, n_ub, r->agg_kind, s.rows.as<u64>()));
+    if (minmax) {
+      MZ_TRY(s.rows.alloc(ctx, n_ub * 32));
+      MZ_CUDA(ctx, cudaMemcpyAsync(s.rows.p, d_rows, n_ub * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      MZ_TRY(s.rows.alloc(ctx, n_ub * 80));
+      MZ_TRY(mz_explode(ctx, d_rows, n, n_ub, r->agg_kind, s.rows.as<u64>()));
+    }
     if (n.p == nullptr) {
       s.len.set(ctx, n.imm);
       s.ub = n.imm;
@@ -1849,8 +1865,9 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
       st = corr.alloc(ctx, 2 * b_ub * 64);
       if (st == MZGPU_OK) st = clen.make_pending(ctx);
       if (st == MZGPU_OK) {
-        st = mz_reduce_corrections_async(ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind,
-                                         corr.as<u64>(), 2 * b_ub, clen.dptr());
+        st = (minmax ? mz_reduce_minmax_async : mz_reduce_corrections_async)(
+            ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind, corr.as<u64>(), 2 * b_ub,
+            clen.dptr());
         clen.mark_written();
       }
       if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), 2 * b_ub, &cons, &ccap, &flen);
@@ -1860,6 +1877,11 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
       u64 n_corr = 0, ccap = 0;
       Lazy4 flen;
       st = batch_resolve(batch);
+      if (st == MZGPU_OK && minmax) {
+        MZ_SET_ERR(ctx, "MIN/MAX reduce: batch of %llu rows exceeds the single-pass bound",
+                   (unsigned long long)b_ub);
+        st = MZGPU_E_UNSUPPORTED;
+      }
       if (st == MZGPU_OK)
         st = mz_reduce_corrections(ctx, batch->rows.as<u64>(), batch->st.v[0], tv, r->agg_kind, &corr, &n_corr);
       if (st == MZGPU_OK && n_corr)

@@ -364,7 +364,200 @@ __global__ void __launch_bounds__(RT) k_corrections_lb(const u64* __restrict__ r
   }
 }
 
+// ------------------------------------------------------------------ MIN / MAX
+// Result of the hierarchical reduce (reduce.rs:1050-1135): per key the live
+// (value, count) pairs; a negative count -> the error row, else MIN / MAX of the
+// values.  One thread per changed key keeps the key's pairs in a small local table.
+constexpr int MM_CAP = 32;
+struct MinMaxAcc {
+  u64 vals[MM_CAP];
+  i64 cnts[MM_CAP];
+  int m;
+  bool overflow;
+};
+__device__ __forceinline__ void mm_add(MinMaxAcc& a, u64 val, i64 d) {
+  for (int j = 0; j < a.m; ++j)
+    if (a.vals[j] == val) {
+      a.cnts[j] += d;
+      return;
+    }
+  // reuse a dead entry before growing
+  for (int j = 0; j < a.m; ++j)
+    if (a.cnts[j] == 0) {
+      a.vals[j] = val;
+      a.cnts[j] = d;
+      return;
+    }
+  if (a.m < MM_CAP) {
+    a.vals[a.m] = val;
+    a.cnts[a.m] = d;
+    ++a.m;
+  } else {
+    a.overflow = true;
+  }
+}
+__device__ __forceinline__ bool mm_eval(const MinMaxAcc& a, int agg_kind, u64* o /* count, sum_lo, sum_hi, flags */) {
+  bool any = false, bad = false, have = false;
+  u64 best = 0;
+  for (int j = 0; j < a.m; ++j) {
+    const i64 c = a.cnts[j];
+    if (c == 0) continue;
+    any = true;
+    if (c < 0) {
+      bad = true;
+      continue;
+    }
+    const u64 v = a.vals[j];
+    if (!have || (agg_kind == MZGPU_AGG_MIN ? v < best : v > best)) best = v;
+    have = true;
+  }
+  o[0] = 0;
+  o[1] = bad ? 0 : best;
+  o[2] = 0;
+  o[3] = bad ? 2 : 0;
+  return any;
+}
+__device__ __forceinline__ void mm_prior(const TraceView& tv, u64 key, MinMaxAcc& a) {
+  const u64 h0 = mix64(key);
+  for (u32 b = 0; b < tv.n_batches; ++b) {
+    const BatchView& bv = tv.b[b];
+    const u64 mask = bv_mask(bv);
+    u64 h = h0 & mask;
+    while (true) {
+      const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      if (sl.y == 0) break;
+      if (sl.x == key) {
+        const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+        const u32 len = (u32)(sl.y >> 44);
+        const u64 bn = len != 0 ? first + len : bv_n(bv);
+        for (u64 r = first; r < bn; ++r) {
+          const ulonglong2* row = reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+          const ulonglong2 kv = row[0];
+          if (len == 0 && kv.x != key) break;
+          mm_add(a, kv.y, (i64)row[1].y);
+        }
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+}
+// rows [i, ...) of the new batch share `key` (sorted by (val, time)): replay them in
+// time order on top of the prior pairs and emit (-old, +new) whenever the result changes.
+__device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64 i, u64 key,
+                                        const TraceView& prior, int agg_kind, bool do_write,
+                                        u64* __restrict__ out, u64 pos, u64* __restrict__ status) {
+  MinMaxAcc a;
+  a.m = 0;
+  a.overflow = false;
+  mm_prior(prior, key, a);
+  u64 oldv[4];
+  bool had = mm_eval(a, agg_kind, oldv);
+  u32 c = 0;
+  bool first = true;
+  u64 t_prev = 0;
+  while (true) {
+    // next distinct time of this key
+    bool found = false;
+    u64 t_cur = 0;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 4;
+      if (row[0] != key) break;
+      const u64 t = row[2];
+      if ((first || t > t_prev) && (!found || t < t_cur)) {
+        t_cur = t;
+        found = true;
+      }
+    }
+    if (!found) break;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 4;
+      if (row[0] != key) break;
+      if (row[2] == t_cur) mm_add(a, row[1], (i64)row[3]);
+    }
+    u64 newv[4];
+    const bool has = mm_eval(a, agg_kind, newv);
+    const bool same = (had == has) && (!has || (oldv[1] == newv[1] && oldv[3] == newv[3]));
+    if (!same) {
+      if (had) {
+        if (do_write) {
+          u64 r[8] = {key, oldv[0], oldv[1], oldv[2], oldv[3], t_cur, ~0ull, 0};
+          store_row<8>(out, pos + c, r);
+        }
+        ++c;
+      }
+      if (has) {
+        if (do_write) {
+          u64 r[8] = {key, newv[0], newv[1], newv[2], newv[3], t_cur, 1, 0};
+          store_row<8>(out, pos + c, r);
+        }
+        ++c;
+      }
+    }
+    had = has;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) oldv[w] = newv[w];
+    first = false;
+    t_prev = t_cur;
+  }
+  if (a.overflow) status[1] = 1;
+  return c;
+}
+
+__global__ void __launch_bounds__(RT) k_minmax_lb(const u64* __restrict__ rows, const DLen dn,
+                                                  const __grid_constant__ TraceView prior, int agg_kind,
+                                                  const LookBack lb, u64* __restrict__ out, u64 out_cap,
+                                                  u64* __restrict__ out_len, u64* __restrict__ status) {
+  __shared__ u32 sm[34];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_b;
+  const u64 n = dlen_get(dn);
+  const u64 n_tiles = (n + RT - 1) / RT;
+  while (true) {
+    const u32 tile = lb_next_tile(lb, &s_tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *out_len = 0;
+      break;
+    }
+    const u64 i = (u64)tile * RT + threadIdx.x;
+    u32 cnt = 0;
+    const bool head = i < n && (i == 0 || rows[(i - 1) * 4] != rows[i * 4]);
+    u64 key = 0;
+    if (head) {
+      key = rows[i * 4];
+      cnt = walk_minmax(rows, n, i, key, prior, agg_kind, false, nullptr, 0, status);
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan(cnt, sm, &total);
+    const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
+    if (head && cnt > 0) {
+      const u64 pos = excl + ex;
+      if (pos + cnt > out_cap)
+        atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+      else
+        walk_minmax(rows, n, i, key, prior, agg_kind, true, out, pos, status);
+    }
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = excl + total;
+  }
+}
+
 }  // namespace
+
+// MIN / MAX corrections of a sealed R32 batch against the prior R32 arrangement;
+// at most two output rows per distinct (key, time), so capacity 2 * n_ub suffices.
+int32_t mz_reduce_minmax_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
+                               const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
+                               u64* d_out_len) {
+  LookBack lb;
+  MZ_TRY(mz_lookback_begin(ctx, (n_ub + RT - 1) / RT, &lb));
+  u64 grid = (n_ub + RT - 1) / RT;
+  if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
+  if (grid == 0) grid = 1;
+  MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 + 32 + 128) : 0);
+  MZ_LAUNCH(ctx, k_minmax_lb, (unsigned)grid, RT, 0, d_batch_rows, n, prior, agg_kind, lb, d_out, out_cap,
+            d_out_len, ctx->d_status);
+  return MZGPU_OK;
+}
 
 int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_kind, u64* d_racc) {
   if (n_ub == 0) return MZGPU_OK;

@@ -463,11 +463,30 @@ void mzo_map_rows(const mzgpu_r32* rows, uint64_t n, const mzgpu_closure* closur
 }
 
 // ----------------------------------------------------------------- reduce
-void* mzo_reduce_new(int32_t agg_kind) { return new ReduceAccumulable(agg_kind); }
-void mzo_reduce_free(void* r) { delete (ReduceAccumulable*)r; }
-void mzo_reduce_step(void* r, const mzgpu_r32* rows, uint64_t n, uint64_t upper, void* vec) {
+struct AnyReduce {
+  ReduceAccumulable* acc = nullptr;
+  ReduceMinMax* mm = nullptr;
+  ~AnyReduce() {
+    delete acc;
+    delete mm;
+  }
+};
+void* mzo_reduce_new(int32_t agg_kind) {
+  AnyReduce* r = new AnyReduce();
+  if (agg_kind == MZGPU_AGG_MIN || agg_kind == MZGPU_AGG_MAX)
+    r->mm = new ReduceMinMax(agg_kind);
+  else
+    r->acc = new ReduceAccumulable(agg_kind);
+  return r;
+}
+void mzo_reduce_free(void* r) { delete (AnyReduce*)r; }
+void mzo_reduce_step(void* rv, const mzgpu_r32* rows, uint64_t n, uint64_t upper, void* vec) {
   std::vector<mzgpu_rout> out;
-  ((ReduceAccumulable*)r)->step(rows, n, upper, out);
+  AnyReduce* r = (AnyReduce*)rv;
+  if (r->mm)
+    r->mm->step(rows, n, upper, out);
+  else
+    r->acc->step(rows, n, upper, out);
   vec_append((Vec*)vec, out);
 }
 void mzo_explode(const mzgpu_r32* rows, uint64_t n, int32_t agg_kind, mzgpu_racc* out) {

@@ -501,4 +501,97 @@ struct ReduceAccumulable {
   }
 };
 
+// MIN / MAX per key: the final result of the hierarchical reduce
+// (build_bucketed_negated_output, reduce.rs:1050-1135): source = the key's accumulated
+// (value, count) pairs with non-zero count; a non-positive count -> the error row; otherwise
+// func.eval(values).  Emission protocol as in ReduceAccumulable (reduce_abelian contract,
+// extensions/reduce.rs:52-107).
+struct ReduceMinMax {
+  int agg_kind;
+  Batcher<mzgpu_r32> batcher;
+  ValSpine input;
+  std::map<u64, mzgpu_rout> output;
+
+  explicit ReduceMinMax(int kind) : agg_kind(kind), input(real_ops<mzgpu_r32>(), 1, false) {}
+
+  bool evaluate(u64 key, const std::map<u64, i64>& acc, mzgpu_rout* o) const {
+    bool any = false, bad = false, have = false;
+    u64 best = 0;
+    for (auto& kv : acc) {
+      if (kv.second == 0) continue;
+      any = true;
+      if (kv.second < 0) {
+        bad = true;
+        continue;
+      }
+      if (!have || (agg_kind == MZGPU_AGG_MIN ? kv.first < best : kv.first > best)) best = kv.first;
+      have = true;
+    }
+    if (!any) return false;
+    std::memset(o, 0, sizeof(*o));
+    o->key = key;
+    if (bad)
+      o->flags = 2;
+    else
+      o->sum_lo = best;
+    return true;
+  }
+
+  void step(const mzgpu_r32* rows, size_t n, u64 upper, std::vector<mzgpu_rout>& out) {
+    batcher.push_container(rows, n);
+    ValBatch batch = batcher.seal(upper);
+    std::vector<ValBatch> prior;
+    for (auto& e : input.all_batches()) prior.push_back(e.batch);
+    if (batch->desc.lower != batch->desc.upper) input.insert(batch);
+    input.set_physical_compaction(input.upper);
+    std::vector<mzgpu_rout> local;
+    CursorList<mzgpu_r32> pc(prior);
+    BatchCursor<mzgpu_r32> bc(batch.get());
+    while (bc.key_valid()) {
+      const u64 key = bc.key();
+      std::map<u64, i64> acc;
+      pc.seek_key(key);
+      if (pc.key_valid() && pc.key() == key) {
+        while (pc.val_valid()) {
+          pc.map_times([&](const mzgpu_r32& r) { acc[r.val] += r.diff; });
+          pc.step_val();
+        }
+      }
+      // the batch's updates of this key, by time
+      std::map<u64, std::vector<mzgpu_r32>> by_time;
+      while (bc.val_valid()) {
+        bc.map_times([&](const mzgpu_r32& r) { by_time[r.time].push_back(r); });
+        bc.step_val();
+      }
+      for (auto& tv : by_time) {
+        for (auto& r : tv.second) acc[r.val] += r.diff;
+        const u64 t = tv.first;
+        auto it = output.find(key);
+        const bool had = it != output.end();
+        mzgpu_rout fresh;
+        const bool has = evaluate(key, acc, &fresh);
+        if (had) {
+          mzgpu_rout old = it->second;
+          old.time = t;
+          old.diff = -1;
+          local.push_back(old);
+        }
+        if (has) {
+          fresh.time = t;
+          fresh.diff = 1;
+          local.push_back(fresh);
+          mzgpu_rout keep = fresh;
+          keep.time = 0;
+          output[key] = keep;
+        } else if (had) {
+          output.erase(it);
+        }
+      }
+      bc.step_key();
+    }
+    consolidate(local);
+    out.insert(out.end(), local.begin(), local.end());
+  }
+};
+
 }  // namespace mzo

@@ -394,6 +394,42 @@ def test_reduce_distinct_and_threshold_match_oracle(mz, ctx, oracle, agg_kind):
         same(gr.step(a, t), orr.step(a, t))
 
 
+@pytest.mark.parametrize("agg_kind", [4, 5])
+def test_reduce_min_max_match_oracle(mz, ctx, oracle, agg_kind):
+    """MIN / MAX: the hierarchical reduce's result (reduce.rs:796-1135): values retract, the
+    extremum moves both ways, groups empty out and come back, negative counts give the error row."""
+    rng = np.random.default_rng(70 + agg_kind)
+    gr, orr = mz.ReduceAccumulable(ctx, agg_kind), oracle.Reduce(agg_kind)
+    t = 0
+    saw_err = False
+    for step in range(12):
+        n = int(rng.integers(1, 6000))
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 500, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 14, size=n, dtype=np.uint64) * np.uint64(0x1234567890ABCDEF)
+        a["time"] = rng.integers(t, t + 3, size=n, dtype=np.uint64)
+        a["diff"] = rng.integers(-1, 3, size=n, dtype=np.int64)
+        t += 3
+        got, want = gr.step(a, t), orr.step(a, t)
+        same(got, want)
+        saw_err = saw_err or bool((want["flags"] == 2).any())
+    assert saw_err
+
+
+def test_reduce_min_max_group_too_wide_is_reported(mz, oracle):
+    """A key with more than 32 distinct live values needs the bucketed tree: reported, not wrong.
+    (The report is deferred and poisons the context, hence a private one.)"""
+    ctx = mz.Context(0)
+    a = np.zeros(40, dtype=oracle.R32)
+    a["key"] = 7
+    a["val"] = np.arange(40)
+    a["diff"] = 1
+    gr = mz.ReduceAccumulable(ctx, 4)
+    with pytest.raises(mz.MzGpuError) as e:
+        gr.step(a, 1)
+    assert e.value.status == -4  # MZGPU_E_UNSUPPORTED
+
+
 def test_reduce_large_i128_sums(mz, ctx, oracle):
     """i128 accumulation with carries: sums far beyond i64."""
     a = np.zeros(40000, dtype=oracle.R32)

@@ -220,3 +220,37 @@ def test_distinct_and_threshold_accumulate_to_their_definitions():
             else:
                 want = {(k, 0, 0, 0, 0): c for k, c in acc.items() if c > 0}
             assert out_acc == want, (kind, step)
+
+
+@pytest.mark.parametrize("kind", [4, 5])
+def test_min_max_accumulate_to_their_definitions(oracle, kind):
+    """MIN / MAX (reduce.rs:1050-1135): the accumulated output equals func(values with positive
+    count) per key, or the error row when any count is negative."""
+    rng = np.random.default_rng(5 + kind)
+    r = oracle.Reduce(kind)
+    acc, out_acc = {}, {}
+    for step in range(8):
+        n = 1500
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 120, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 12, size=n, dtype=np.uint64)
+        a["time"] = rng.integers(step * 2, step * 2 + 2, size=n, dtype=np.uint64)
+        a["diff"] = rng.integers(-1, 3, size=n)
+        out = r.step(a, step * 2 + 2)
+        for k, v, d in zip(a["key"].tolist(), a["val"].tolist(), a["diff"].tolist()):
+            acc.setdefault(k, {})
+            acc[k][v] = acc[k].get(v, 0) + d
+        for row in out.tolist():
+            key = (row[0], row[1], row[2], row[3], row[4])
+            out_acc[key] = out_acc.get(key, 0) + row[6]
+        out_acc = {k: v for k, v in out_acc.items() if v}
+        want = {}
+        for k, m in acc.items():
+            nz = {v: c for v, c in m.items() if c != 0}
+            if not nz:
+                continue
+            if any(c < 0 for c in nz.values()):
+                want[(k, 0, 0, 0, 2)] = 1
+            else:
+                want[(k, 0, (min if kind == 4 else max)(nz), 0, 0)] = 1
+        assert out_acc == want
