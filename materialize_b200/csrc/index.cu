@@ -17,8 +17,9 @@ __global__ void __launch_bounds__(512) k_count_keys(const u64* __restrict__ rows
   u64 i = (u64)blockIdx.x * 512 + threadIdx.x;
   bool head = false;
   if (i < n) head = (i == 0) || rows[i * NW] != rows[(i - 1) * NW];
-  u32 m = __ballot_sync(0xffffffffu, head);
-  if (lane_id() == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+  // one atomic pair per CTA: same-address atomics from every warp serialise in L2
+  __shared__ u32 s_heads[16], s_run[16];
+  const u32 m = __ballot_sync(0xffffffffu, head);
   // longest run of one key (saturating at 1024): bounds the fan-out of a probe
   u32 run = 0;
   if (head) {
@@ -31,7 +32,25 @@ __global__ void __launch_bounds__(512) k_count_keys(const u64* __restrict__ rows
     u32 o = __shfl_xor_sync(0xffffffffu, run, off);
     run = o > run ? o : run;
   }
-  if (lane_id() == 0 && run) atomicMax(count + 1, (unsigned long long)run);
+  if (lane_id() == 0) {
+    s_heads[threadIdx.x >> 5] = __popc(m);
+    s_run[threadIdx.x >> 5] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u32 h = threadIdx.x < 16 ? s_heads[threadIdx.x] : 0;
+    u32 r = threadIdx.x < 16 ? s_run[threadIdx.x] : 0;
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      h += __shfl_xor_sync(0xffffffffu, h, off);
+      u32 o = __shfl_xor_sync(0xffffffffu, r, off);
+      r = o > r ? o : r;
+    }
+    if (threadIdx.x == 0 && h) {
+      atomicAdd(count, (unsigned long long)h);
+      atomicMax(count + 1, (unsigned long long)r);
+    }
+  }
 }
 
 template <int NW>

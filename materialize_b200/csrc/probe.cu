@@ -23,8 +23,11 @@ constexpr int PT = 256;
 
 // visit every (val2, time2, diff2) of `key` in the trace that passes the time
 // filter; F(v2, t2, d2)
+// `count_runs` != nullptr: the caller only counts, and every row of a run matches (no time
+// filter, no closure) -- a run whose length is in the slot adds it without touching the rows.
 template <int GROUP, class F>
-__device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64 t1, int mode, F f) {
+__device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64 t1, int mode, F f,
+                                               u32* count_runs = nullptr) {
   const u64 h0 = mix64(key);
   // The first slot of several batches is fetched before any of them is looked at:
   // the loads are independent, so a probe against a trace of many batches costs
@@ -53,7 +56,9 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
         if (sl.x == key) {
           const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
           const u32 len = (u32)(sl.y >> 44);
-          if (len != 0) {
+          if (len != 0 && count_runs != nullptr) {
+            *count_runs += len;
+          } else if (len != 0) {
             // run length known: the rows' loads do not depend on each other
             for (u32 r0 = 0; r0 < len; r0 += 4) {
               ulonglong2 kv[4], td[4];
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(PT) k_probe(const u64* __restrict__ stream, u6
                                               const __grid_constant__ ProbeParams pp,
                                               u32* __restrict__ tile_counts,
                                               const u32* __restrict__ tile_base,
+                                              u32* __restrict__ row_counts,
                                               u64* __restrict__ out) {
   __shared__ u32 sm[34];
   const u64 i = (u64)blockIdx.x * PT + threadIdx.x;
@@ -298,20 +304,36 @@ __global__ void __launch_bounds__(PT) k_probe(const u64* __restrict__ stream, u6
   i64 d1 = 0;
   u32 cnt = 0;
   if (i < n) {
-    const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
-    const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
-    key = kv.x;
-    v1 = kv.y;
-    t1 = td.x;
-    d1 = (i64)td.y;
-    for_each_match<1>(tv, key, t1, pp.mode, [&](u64 v2, u64 t2, i64 d2) {
-      if (pp.has_closure) {
-        u64 k, v;
-        if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
-      } else {
-        cnt++;
-      }
-    });
+    if (!WRITE) {
+      // the count pass needs the key and the time only
+      key = stream[i * 4];
+      t1 = stream[i * 4 + 2];
+      v1 = pp.has_closure ? stream[i * 4 + 1] : 0;
+      u32 runs = 0;
+      const bool whole_runs = pp.mode == MZ_PROBE_JOIN && !pp.has_closure;
+      for_each_match<1>(
+          tv, key, t1, pp.mode,
+          [&](u64 v2, u64 t2, i64 d2) {
+            if (pp.has_closure) {
+              u64 k, v;
+              if (closure_eval(pp.closure, key, pp.swap_vals ? v2 : v1, pp.swap_vals ? v1 : v2, &k, &v)) cnt++;
+            } else {
+              cnt++;
+            }
+          },
+          whole_runs ? &runs : nullptr);
+      cnt += runs;
+      row_counts[i] = cnt;
+    } else {
+      // the write pass takes the row's count from the count pass: one walk per pass
+      cnt = row_counts[i];
+      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
+      const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
+      key = kv.x;
+      v1 = kv.y;
+      t1 = td.x;
+      d1 = (i64)td.y;
+    }
   }
   u32 total;
   u32 ex = block_exclusive_scan(cnt, sm, &total);
@@ -391,15 +413,16 @@ int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& tr
   const int out_rb = pp.has_closure ? 32 : 40;
   if (n == 0 || trace.n_batches == 0) return out->alloc(ctx, 16);
   const u64 n_tiles = (n + PT - 1) / PT;
-  DevMem tiles;
+  DevMem tiles, row_counts;
   MZ_TRY(tiles.alloc(ctx, n_tiles * 4));
+  MZ_TRY(row_counts.alloc(ctx, n * 4));
   u64* d_total = ctx->d_scratch + 28;
   if (pp.has_closure) {
     MZ_LAUNCH(ctx, (k_probe<4, false>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, tiles.as<u32>(),
-              (const u32*)nullptr, (u64*)nullptr);
+              (const u32*)nullptr, row_counts.as<u32>(), (u64*)nullptr);
   } else {
     MZ_LAUNCH(ctx, (k_probe<5, false>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, tiles.as<u32>(),
-              (const u32*)nullptr, (u64*)nullptr);
+              (const u32*)nullptr, row_counts.as<u32>(), (u64*)nullptr);
   }
   MZ_LAUNCH(ctx, k_scan_tiles, 1, 1024, 0, tiles.as<u32>(), n_tiles, d_total);
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 28, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -413,11 +436,10 @@ int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& tr
   MZ_BYTES(ctx, n * (32 + 16 * trace.n_batches) + total * (32 + out_rb));
   if (pp.has_closure) {
     MZ_LAUNCH(ctx, (k_probe<4, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
-              tiles.as<u32>(), out->as<u64>());
+              tiles.as<u32>(), row_counts.as<u32>(), out->as<u64>());
   } else {
-    MZ_BYTES(ctx, n * (32 + 16 * trace.n_batches) + total * (32 + out_rb));
     MZ_LAUNCH(ctx, (k_probe<5, true>), (unsigned)n_tiles, PT, 0, d_stream, n, trace, pp, (u32*)nullptr,
-              tiles.as<u32>(), out->as<u64>());
+              tiles.as<u32>(), row_counts.as<u32>(), out->as<u64>());
   }
   return MZGPU_OK;
 }

@@ -160,6 +160,69 @@ def test_consolidate_large_properties(mz, ctx):
     same(ctx.consolidate(out), out)
 
 
+def test_arrange_join_full_size_properties(mz, ctx):
+    """BASELINE configs[1] at full size (2 x 10 M rows, uniform keys): the oracle cannot run this in
+    seconds, so the join is pinned by size-independent properties -- per-key output counts are the
+    product of the inputs' per-key counts, the value columns' checksums follow by linearity, and the
+    consolidated output is sorted with unit diffs (row-index values make every output row distinct)."""
+    from materialize_b200 import harness
+
+    n = 10_000_000
+    a, b = harness.gen_cfg2(ctx, 1, n, n), harness.gen_cfg2(ctx, 2, n, n)
+    ha, hb = a.download(), b.download()
+    ba, bb = mz.Batcher(ctx, 32), mz.Batcher(ctx, 32)
+    ba.push_device(a)
+    bb.push_device(b)
+    xa, xb = ba.seal(1), bb.seal(1)
+    sa, sb = mz.Spine(ctx, 32), mz.Spine(ctx, 32)
+    j = mz.JoinCore(ctx, sa, sb)
+    sa.insert(xa)
+    j.push(0, xa, 0)
+    sb.insert(xb)
+    j.push(1, xb, 0)
+    j.work()
+    out = j.results()
+    ka, kb = ha["key"].astype(np.int64), hb["key"].astype(np.int64)
+    ca, cb = np.bincount(ka, minlength=n), np.bincount(kb, minlength=n)
+    assert len(out) == int((ca * cb).sum())
+    assert np.array_equal(np.bincount(out["key"].astype(np.int64), minlength=n), ca * cb)
+    va = np.bincount(ka, weights=ha["val"].astype(np.float64), minlength=n).astype(np.int64)
+    vb = np.bincount(kb, weights=hb["val"].astype(np.float64), minlength=n).astype(np.int64)
+    assert int(out["val1"].astype(np.int64).sum()) == int((va * cb).sum())
+    assert int(out["val2"].astype(np.int64).sum()) == int((vb * ca).sum())
+    assert np.all(out["diff"] == 1) and np.all(out["time"] == 0)
+    k, v1, v2 = out["key"], out["val1"], out["val2"]
+    lt = (k[:-1] < k[1:]) | ((k[:-1] == k[1:]) & ((v1[:-1] < v1[1:]) | ((v1[:-1] == v1[1:]) & (v2[:-1] < v2[1:]))))
+    assert np.all(lt)
+
+
+def test_reduce_full_size_properties(mz, ctx):
+    """BASELINE configs[3] at full size (100 M rows, 1 M Zipf(0.9) keys): COUNT and SUM per key
+    against numpy's bincount of the same rows, one output row per live key, sorted by key."""
+    from materialize_b200 import harness
+
+    n, nk = 100_000_000, 1_000_000
+    w = 1.0 / np.power(np.arange(1, nk + 1, dtype=np.float64), 0.9)
+    cdf = np.cumsum(w / w.sum())
+    cdf[-1] = 1.0
+    d = harness.gen_cfg4(ctx, 3, n, cdf)
+    h = d.download()
+    r = mz.ReduceAccumulable(ctx, mz.AGG_COUNT_SUM_I64)
+    out = r.step_dev(d, 1).download()
+    del d
+    keys = h["key"].astype(np.int64)
+    hi = int(keys.max()) + 1
+    cnt = np.bincount(keys, minlength=hi)
+    sums = np.bincount(keys, weights=h["val"].astype(np.int64).astype(np.float64), minlength=hi)
+    assert np.abs(sums).max() < 2.0**53  # float64 accumulation of these integers is exact
+    live = np.nonzero(cnt)[0]
+    assert np.array_equal(out["key"].astype(np.int64), live)
+    assert np.array_equal(out["count"], cnt[live])
+    assert np.array_equal(out["sum_lo"].astype(np.int64), sums[live].astype(np.int64))
+    assert np.all(out["sum_hi"] == np.where(sums[live] < 0, -1, 0))
+    assert np.all(out["diff"] == 1) and np.all(out["flags"] == 0)
+
+
 # ------------------------------------------------------------- a2 - a5
 def test_batcher_seal_matches_oracle(mz, ctx, oracle):
     rng = np.random.default_rng(21)
