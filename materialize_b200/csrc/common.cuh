@@ -459,26 +459,46 @@ __device__ __forceinline__ u64 lb_exclusive_prefix(const LookBack& lb, u32 tile,
       if (lane == 0) st[0] = lb_pack(lb.epoch, LB_INCLUSIVE, total);
     } else {
       if (lane == 0) st[tile] = lb_pack(lb.epoch, LB_PARTIAL, total);
+      // Each lane reads LBW consecutive predecessors per round (independent loads), so one round
+      // covers 32 * LBW tiles: an update batch's few hundred tiles all start together, and the
+      // walk would otherwise pay one memory round trip per 32 of them.
+      constexpr int LBW = 4;
       long long hi = (long long)tile - 1;  // nearest unread predecessor
       while (true) {
-        const long long idx = hi - (long long)lane;
-        u64 w = 0;
-        u64 status = LB_INCLUSIVE;  // lanes before tile 0 behave as an inclusive zero
-        if (idx >= 0) {
-          do {
-            w = st[idx];
-            status = ((u32)(w >> 44) == lb.epoch) ? ((w >> 42) & 3) : 0;
-          } while (status == 0);
+        u64 w[LBW];
+#pragma unroll
+        for (int j = 0; j < LBW; ++j) {
+          const long long idx = hi - (long long)(lane * LBW + j);
+          w[j] = idx >= 0 ? st[idx] : 0;
         }
-        const u32 incl_mask = __ballot_sync(0xffffffffu, status == LB_INCLUSIVE);
-        const u32 first = __ffs(incl_mask) - 1;  // incl_mask != 0 whenever the window reaches past tile 0
-        u64 contrib = (incl_mask == 0 || lane <= first) ? (w & LB_VALUE_MASK) : 0;
-        if (idx < 0) contrib = 0;
+        int fj = LBW;  // this lane's nearest inclusive predecessor
+        u64 contrib = 0;
+#pragma unroll
+        for (int j = 0; j < LBW; ++j) {
+          const long long idx = hi - (long long)(lane * LBW + j);
+          if (fj == LBW) {
+            if (idx < 0) {
+              fj = j;  // before tile 0: an inclusive zero
+            } else {
+              u64 x = w[j];
+              u64 status = ((u32)(x >> 44) == lb.epoch) ? ((x >> 42) & 3) : 0;
+              while (status == 0) {
+                x = st[idx];
+                status = ((u32)(x >> 44) == lb.epoch) ? ((x >> 42) & 3) : 0;
+              }
+              contrib += x & LB_VALUE_MASK;
+              if (status == LB_INCLUSIVE) fj = j;
+            }
+          }
+        }
+        const u32 incl_mask = __ballot_sync(0xffffffffu, fj < LBW);
+        const u32 first = __ffs(incl_mask) - 1;
+        if (incl_mask != 0 && lane > first) contrib = 0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
         excl += contrib;
         if (incl_mask != 0) break;
-        hi -= 32;
+        hi -= 32 * LBW;
       }
       if (lane == 0) st[tile] = lb_pack(lb.epoch, LB_INCLUSIVE, excl + total);
     }

@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
     mask = slots - 1;
   }
 
+  __shared__ u64 s_mm[FT / 32][2 * NK];
   PHASE_STAMP(0);
   // ---- phase 0: zero scratch, results, next launch's header; min/max of every key word
   {
@@ -467,10 +468,18 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
         mn[k] = x > mn[k] ? x : mn[k];
         mx[k] = y > mx[k] ? y : mx[k];
       }
-      if (lane_id() == 0 && n > 0) {
-        atomicMax((unsigned long long*)&ctl->minmax[2 * k], (unsigned long long)mn[k]);
-        atomicMax((unsigned long long*)&ctl->minmax[2 * k + 1], (unsigned long long)mx[k]);
+      if (lane_id() == 0) {
+        s_mm[warp_id()][2 * k] = mn[k];
+        s_mm[warp_id()][2 * k + 1] = mx[k];
       }
+    }
+    // one atomic per CTA and word: same-address atomics from every warp serialise in L2
+    __syncthreads();
+    if (tid < 2 * NK && n > 0 && !a.merge) {
+      u64 v = 0;
+#pragma unroll
+      for (int w = 0; w < FT / 32; ++w) v = s_mm[w][tid] > v ? s_mm[w][tid] : v;
+      atomicMax((unsigned long long*)&ctl->minmax[tid], (unsigned long long)v);
     }
   }
   // (a merge needs nothing of phase 0 before its own first barrier)
@@ -1118,7 +1127,14 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
   }
 
   // ---- hash index over the distinct keys of the output; longest key run
-  u32 my_run = 0;
+  // (key count and longest run are reduced per CTA: one global atomic each)
+  __shared__ u32 s_nheads, s_runmax;
+  if (tid == 0) {
+    s_nheads = 0;
+    s_runmax = 0;
+  }
+  __syncthreads();
+  u32 my_run = 0, my_heads = 0;
   for (u64 i = gtid; i < ((n_out + 31) / 32) * 32; i += gstride) {
     bool head = false;
     u64 key = 0;
@@ -1127,7 +1143,7 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
       head = (i == 0) || a.out[(i - 1) * NW] != key;
     }
     u32 m = __ballot_sync(0xffffffffu, head);
-    if (lane_id() == 0 && m) atomicAdd((unsigned long long*)&a.res[2], (unsigned long long)__popc(m));
+    my_heads += __popc(m);
     if (head) {
       u32 run = 1;
       while (run < MAX_RUN_SAT && i + run < n_out && a.out[(i + run) * NW] == key) ++run;
@@ -1150,7 +1166,15 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
     u32 o = __shfl_xor_sync(0xffffffffu, my_run, off);
     my_run = o > my_run ? o : my_run;
   }
-  if (lane_id() == 0 && my_run) atomicMax((unsigned long long*)&a.res[3], (unsigned long long)my_run);
+  if (lane_id() == 0) {
+    if (my_heads) atomicAdd(&s_nheads, my_heads);
+    if (my_run) atomicMax(&s_runmax, my_run);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_nheads) atomicAdd((unsigned long long*)&a.res[2], (unsigned long long)s_nheads);
+    if (s_runmax) atomicMax((unsigned long long*)&a.res[3], (unsigned long long)s_runmax);
+  }
   PHASE_STAMP(9);
 }
 
