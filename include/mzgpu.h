@@ -212,6 +212,16 @@ typedef struct mzgpu_closure {
  * read-back) for a key with more than 32 distinct live values. */
 #define MZGPU_AGG_MIN 4
 #define MZGPU_AGG_MAX 5
+/* TopK per key (BasicTopKPlan, src/compute/src/render/top_k.rs:215-248 and the reduction logic of
+ * build_topk_negated_stage, :521-673): over the key's live (value, count) pairs -- any non-positive
+ * count yields the error row (flags bit1, diff 1); otherwise the values are ordered (ascending, or
+ * descending), `offset` rows are skipped and at most `limit` rows kept, counting multiplicities.
+ * The operator emits the changes of that window directly (the reference emits its negated complement
+ * and concatenates it with the input: the same collection).  ROUT rows: sum_lo = the value,
+ * diff = the change of the value's multiplicity inside the window, count = sum_hi = 0.  The staged
+ * bucket tree (build_topk, :251-380) bounds per-key work for huge groups; as for MIN/MAX a key with more
+ * than 32 distinct live values is reported MZGPU_E_UNSUPPORTED.  Created by mzgpu_topk_new. */
+#define MZGPU_AGG_TOPK 6
 
 /* ---------------------------------------------------------------- handles */
 typedef struct mzgpu_ctx mzgpu_ctx;         /* one per timely worker / GPU            */
@@ -412,6 +422,11 @@ int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_t n, int32_
 /* build_accumulable (reduce.rs:1261-1471): state = the "ArrangeAccumulable"
  * arrangement (a spine of RACC batches). */
 int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_reduce** out);
+/* A TopK operator (MZGPU_AGG_TOPK) behind the same handle: limit < 0 = no limit (LIMIT NULL),
+ * offset >= 0, descending != 0 orders the values high to low.  Stepped with
+ * mzgpu_reduce_accumulable[_buf] like every other kind. */
+int32_t mzgpu_topk_new(mzgpu_ctx* ctx, int64_t limit, uint64_t offset, int32_t descending,
+                       mzgpu_reduce** out);
 void mzgpu_reduce_free(mzgpu_reduce* r);
 /* One operator activation: `rows` are the (group key, value, time, diff)
  * updates with times in [previous upper, upper).  explode_one -> arrange ->

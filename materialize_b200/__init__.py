@@ -32,6 +32,7 @@ from .api import (  # noqa: F401
     MzGpuError,
     ReduceAccumulable,
     Spine,
+    TopK,
     half_join,
     half_join_dev,
     make_closure,

@@ -57,7 +57,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 FRONTIER_EMPTY = 2**64 - 1
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NCCL, E_FRONTIER = 0, -1, -2, -3, -4, -5, -6
 HALFJOIN_LE, HALFJOIN_LT = 0, 1
-AGG_COUNT_SUM_I64, AGG_COUNT_SUM_F64, AGG_DISTINCT, AGG_THRESHOLD, AGG_MIN, AGG_MAX = 0, 1, 2, 3, 4, 5
+AGG_COUNT_SUM_I64, AGG_COUNT_SUM_F64, AGG_DISTINCT, AGG_THRESHOLD, AGG_MIN, AGG_MAX, AGG_TOPK = 0, 1, 2, 3, 4, 5, 6
 COMM_ID_BYTES = 128
 
 
@@ -166,6 +166,7 @@ SIGNATURES = {
     "mzgpu_update_stream": (i32, [vp, vp, C.POINTER(Closure), u64, vp]),
     "mzgpu_map_rows": (i32, [vp, vp, u64, i32, C.POINTER(Closure), vp]),
     "mzgpu_reduce_new": (i32, [vp, i32, PV]),
+    "mzgpu_topk_new": (i32, [vp, C.c_int64, u64, i32, PV]),
     "mzgpu_reduce_free": (None, [vp]),
     "mzgpu_reduce_accumulable": (i32, [vp, vp, u64, i32, u64, vp]),
     "mzgpu_reduce_input_trace": (vp, [vp]),

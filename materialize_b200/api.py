@@ -423,6 +423,18 @@ class ReduceAccumulable:
     def input_trace(self):
         return Spine(self.ctx, 80, _borrowed=F.lib.mzgpu_reduce_input_trace(self.h))
 
+
+class TopK(ReduceAccumulable):
+    """TopK per key over (key, value) rows (BasicTopKPlan, src/compute/src/render/top_k.rs:215-248,
+    521-673): `limit` < 0 or None = no limit; stepped like every other reduce kind."""
+
+    def __init__(self, ctx, limit, offset=0, descending=False):
+        self.ctx = ctx
+        h = C.c_void_p()
+        lim = -1 if limit is None else int(limit)
+        ctx.check(F.lib.mzgpu_topk_new(ctx.h, lim, int(offset), 1 if descending else 0, C.byref(h)))
+        self.h = h
+
     def __del__(self):
         if getattr(self, "h", None) and self.ctx.h:
             F.lib.mzgpu_reduce_free(self.h)

@@ -731,9 +731,14 @@ int32_t mz_map_rows_dev(mzgpu_ctx* ctx, const u64* d_rows, u64 n, const mzgpu_cl
 
 // reduce.cu
 int32_t mz_explode(mzgpu_ctx* ctx, const u64* d_r32, DLen n, u64 n_ub, int agg_kind, u64* d_racc);
+struct TopKParams {
+  i64 limit;  // < 0: none
+  u64 offset;
+  int descending;
+};
 int32_t mz_reduce_minmax_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
-                               const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
-                               u64* d_out_len);
+                               const TraceView& prior, int agg_kind, const TopKParams& tp, u64* d_out,
+                               u64 out_cap, u64* d_out_len);
 int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
                                     const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
                                     u64* d_out_len);

@@ -1796,6 +1796,7 @@ extern "C" int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_
 struct mzgpu_reduce {
   mzgpu_ctx* ctx;
   int agg_kind;
+  TopKParams topk = {-1, 0, 0};
   mzgpu_batcher* batcher = nullptr;
   mzgpu_spine* input = nullptr;
   ~mzgpu_reduce() {
@@ -1817,6 +1818,21 @@ extern "C" int32_t mzgpu_reduce_new(mzgpu_ctx* ctx, int32_t agg_kind, mzgpu_redu
   *out = r.release();
   return MZGPU_OK;
 }
+extern "C" int32_t mzgpu_topk_new(mzgpu_ctx* ctx, int64_t limit, uint64_t offset, int32_t descending,
+                                  mzgpu_reduce** out) {
+  MZ_CHECK_CTX(ctx);
+  if (out == nullptr) return MZGPU_E_INVALID;
+  std::unique_ptr<mzgpu_reduce> r(new mzgpu_reduce());
+  r->ctx = ctx;
+  r->agg_kind = MZGPU_AGG_TOPK;
+  r->topk.limit = limit < 0 ? -1 : limit;
+  r->topk.offset = offset;
+  r->topk.descending = descending != 0;
+  MZ_TRY(mzgpu_batcher_new(ctx, 32, &r->batcher));
+  MZ_TRY(mzgpu_spine_new(ctx, 32, 1, &r->input));
+  *out = r.release();
+  return MZGPU_OK;
+}
 extern "C" void mzgpu_reduce_free(mzgpu_reduce* r) { delete r; }
 extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) { return r ? r->input : nullptr; }
 
@@ -1826,7 +1842,15 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
   // have reached the host with whatever the caller read since (no extra wait)
   MZ_TRY(mzgpu_spine_set_physical_compaction(r->input, r->input->upper));
   // explode_one: values move into the diff; the exploded rows become a stash segment
-  const bool minmax = r->agg_kind == MZGPU_AGG_MIN || r->agg_kind == MZGPU_AGG_MAX;
+  // MIN / MAX / TopK keep the (key, value) rows themselves
+  const bool minmax =
+      r->agg_kind == MZGPU_AGG_MIN || r->agg_kind == MZGPU_AGG_MAX || r->agg_kind == MZGPU_AGG_TOPK;
+  // output rows per distinct (key, time) of the new batch
+  u64 per_row = 2;
+  if (r->agg_kind == MZGPU_AGG_TOPK) {
+    const u64 w = r->topk.limit >= 0 && r->topk.limit < 32 ? (u64)r->topk.limit : 32;
+    per_row = 2 * w + 2;
+  }
   if (n_ub) {
     Seg s;
     if (minmax) {
@@ -1858,27 +1882,30 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
   int32_t st = trace_view(ctx, prior, &tv);
   const u64 b_ub = batch->len_ub;
   if (st == MZGPU_OK && b_ub > 0) {
-    if ((b_ub + 255) / 256 <= MZ_LB_TILES && 2 * b_ub <= MZ_BOUND_MAX_ROWS) {
+    if ((b_ub + 255) / 256 <= MZ_LB_TILES && per_row * b_ub <= MZ_BOUND_MAX_ROWS) {
       DevMem corr, cons;
       Lazy4 clen, flen;
       u64 ccap = 0;
-      st = corr.alloc(ctx, 2 * b_ub * 64);
+      st = corr.alloc(ctx, per_row * b_ub * 64);
       if (st == MZGPU_OK) st = clen.make_pending(ctx);
       if (st == MZGPU_OK) {
-        st = (minmax ? mz_reduce_minmax_async : mz_reduce_corrections_async)(
-            ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind, corr.as<u64>(), 2 * b_ub,
-            clen.dptr());
+        if (minmax)
+          st = mz_reduce_minmax_async(ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind,
+                                      r->topk, corr.as<u64>(), per_row * b_ub, clen.dptr());
+        else
+          st = mz_reduce_corrections_async(ctx, batch->rows.as<u64>(), batch_dlen(batch), b_ub, tv, r->agg_kind,
+                                           corr.as<u64>(), per_row * b_ub, clen.dptr());
         clen.mark_written();
       }
-      if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), 2 * b_ub, &cons, &ccap, &flen);
-      if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : 2 * b_ub);
+      if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), per_row * b_ub, &cons, &ccap, &flen);
+      if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : per_row * b_ub);
     } else {
       DevMem corr, cons;
       u64 n_corr = 0, ccap = 0;
       Lazy4 flen;
       st = batch_resolve(batch);
       if (st == MZGPU_OK && minmax) {
-        MZ_SET_ERR(ctx, "MIN/MAX reduce: batch of %llu rows exceeds the single-pass bound",
+        MZ_SET_ERR(ctx, "MIN/MAX/TopK reduce: batch of %llu rows exceeds the single-pass bound",
                    (unsigned long long)b_ub);
         st = MZGPU_E_UNSUPPORTED;
       }

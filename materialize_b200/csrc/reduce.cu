@@ -504,15 +504,132 @@ __device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64
   return c;
 }
 
+// ---------------------------------------------------------------------- TopK
+// build_topk_negated_stage (top_k.rs:521-673): order the key's live values, skip `offset`
+// rows, keep at most `limit` (multiplicities counted); a negative count -> the error row.
+struct TopKWin {
+  u64 v[MM_CAP];
+  i64 m[MM_CAP];
+  int n;
+  bool err;
+};
+__device__ __noinline__ void tk_eval(const MinMaxAcc& a, const TopKParams& tp, TopKWin& w) {
+  w.n = 0;
+  w.err = false;
+  for (int j = 0; j < a.m; ++j)
+    if (a.cnts[j] < 0) {
+      w.err = true;
+      return;
+    }
+  u64 skip = tp.offset;
+  i64 left = tp.limit;
+  bool has_last = false;
+  u64 last = 0;
+  while (!(tp.limit >= 0 && left == 0)) {
+    // next value in order (selection over at most MM_CAP live entries)
+    int best = -1;
+    for (int j = 0; j < a.m; ++j) {
+      if (a.cnts[j] <= 0) continue;
+      const u64 v = a.vals[j];
+      const bool after = !has_last || (tp.descending ? v < last : v > last);
+      if (after && (best < 0 || (tp.descending ? v > a.vals[best] : v < a.vals[best]))) best = j;
+    }
+    if (best < 0) break;
+    last = a.vals[best];
+    has_last = true;
+    i64 cnt = a.cnts[best];
+    if (skip > 0) {
+      const u64 s = skip < (u64)cnt ? skip : (u64)cnt;
+      skip -= s;
+      cnt -= (i64)s;
+    }
+    if (tp.limit >= 0) {
+      cnt = cnt < left ? cnt : left;
+      left -= cnt;
+    }
+    if (cnt > 0) {
+      w.v[w.n] = last;
+      w.m[w.n] = cnt;
+      ++w.n;
+    }
+  }
+}
+// changes old -> fresh at time t; returns the number of rows (written at out[pos...] if do_write)
+__device__ __forceinline__ u32 tk_emit(u64 key, const TopKWin& old, const TopKWin& fresh, u64 t, bool do_write,
+                                       u64* __restrict__ out, u64 pos) {
+  u32 c = 0;
+  auto put = [&](u64 val, u64 flags, i64 d) {
+    if (do_write) {
+      u64 r[8] = {key, 0, val, 0, flags, t, (u64)d, 0};
+      store_row<8>(out, pos + c, r);
+    }
+    ++c;
+  };
+  if (old.err != fresh.err) put(0, 2, fresh.err ? 1 : -1);
+  for (int i = 0; i < old.n; ++i) {
+    i64 now = 0;
+    for (int j = 0; j < fresh.n; ++j)
+      if (fresh.v[j] == old.v[i]) now = fresh.m[j];
+    if (now != old.m[i]) put(old.v[i], 0, now - old.m[i]);
+  }
+  for (int j = 0; j < fresh.n; ++j) {
+    bool seen = false;
+    for (int i = 0; i < old.n; ++i) seen = seen || old.v[i] == fresh.v[j];
+    if (!seen) put(fresh.v[j], 0, fresh.m[j]);
+  }
+  return c;
+}
+__device__ __noinline__ u32 walk_topk(const u64* __restrict__ rows, u64 n, u64 i, u64 key,
+                                      const TraceView& prior, const TopKParams& tp, bool do_write,
+                                      u64* __restrict__ out, u64 pos, u64* __restrict__ status) {
+  MinMaxAcc a;
+  a.m = 0;
+  a.overflow = false;
+  mm_prior(prior, key, a);
+  TopKWin old, fresh;
+  tk_eval(a, tp, old);
+  u32 c = 0;
+  bool first = true;
+  u64 t_prev = 0;
+  while (true) {
+    bool found = false;
+    u64 t_cur = 0;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 4;
+      if (row[0] != key) break;
+      const u64 t = row[2];
+      if ((first || t > t_prev) && (!found || t < t_cur)) {
+        t_cur = t;
+        found = true;
+      }
+    }
+    if (!found) break;
+    for (u64 j = i; j < n; ++j) {
+      const u64* row = rows + j * 4;
+      if (row[0] != key) break;
+      if (row[2] == t_cur) mm_add(a, row[1], (i64)row[3]);
+    }
+    tk_eval(a, tp, fresh);
+    c += tk_emit(key, old, fresh, t_cur, do_write, out, pos + c);
+    old = fresh;
+    first = false;
+    t_prev = t_cur;
+  }
+  if (a.overflow) status[1] = 1;
+  return c;
+}
+
 __global__ void __launch_bounds__(RT) k_minmax_lb(const u64* __restrict__ rows, const DLen dn,
                                                   const __grid_constant__ TraceView prior, int agg_kind,
-                                                  const LookBack lb, u64* __restrict__ out, u64 out_cap,
+                                                  const TopKParams tp, const LookBack lb,
+                                                  u64* __restrict__ out, u64 out_cap,
                                                   u64* __restrict__ out_len, u64* __restrict__ status) {
   __shared__ u32 sm[34];
   __shared__ u32 s_tile;
   __shared__ u64 s_b;
   const u64 n = dlen_get(dn);
   const u64 n_tiles = (n + RT - 1) / RT;
+  const bool topk = agg_kind == MZGPU_AGG_TOPK;
   while (true) {
     const u32 tile = lb_next_tile(lb, &s_tile);
     if ((u64)tile >= n_tiles) {
@@ -525,7 +642,8 @@ __global__ void __launch_bounds__(RT) k_minmax_lb(const u64* __restrict__ rows, 
     u64 key = 0;
     if (head) {
       key = rows[i * 4];
-      cnt = walk_minmax(rows, n, i, key, prior, agg_kind, false, nullptr, 0, status);
+      cnt = topk ? walk_topk(rows, n, i, key, prior, tp, false, nullptr, 0, status)
+                 : walk_minmax(rows, n, i, key, prior, agg_kind, false, nullptr, 0, status);
     }
     u32 total;
     const u32 ex = block_exclusive_scan(cnt, sm, &total);
@@ -534,6 +652,8 @@ __global__ void __launch_bounds__(RT) k_minmax_lb(const u64* __restrict__ rows, 
       const u64 pos = excl + ex;
       if (pos + cnt > out_cap)
         atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+      else if (topk)
+        walk_topk(rows, n, i, key, prior, tp, true, out, pos, status);
       else
         walk_minmax(rows, n, i, key, prior, agg_kind, true, out, pos, status);
     }
@@ -543,18 +663,19 @@ __global__ void __launch_bounds__(RT) k_minmax_lb(const u64* __restrict__ rows, 
 
 }  // namespace
 
-// MIN / MAX corrections of a sealed R32 batch against the prior R32 arrangement;
-// at most two output rows per distinct (key, time), so capacity 2 * n_ub suffices.
+// MIN / MAX / TopK corrections of a sealed R32 batch against the prior R32 arrangement.
+// MIN / MAX: at most two output rows per distinct (key, time), capacity 2 * n_ub suffices;
+// TopK: at most 2 * min(limit, 32) + 2 (every window entry may change, plus the error row).
 int32_t mz_reduce_minmax_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLen n, u64 n_ub,
-                               const TraceView& prior, int agg_kind, u64* d_out, u64 out_cap,
-                               u64* d_out_len) {
+                               const TraceView& prior, int agg_kind, const TopKParams& tp, u64* d_out,
+                               u64 out_cap, u64* d_out_len) {
   LookBack lb;
   MZ_TRY(mz_lookback_begin(ctx, (n_ub + RT - 1) / RT, &lb));
   u64 grid = (n_ub + RT - 1) / RT;
   if (grid > (u64)ctx->num_sms * 8) grid = (u64)ctx->num_sms * 8;
   if (grid == 0) grid = 1;
   MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 + 32 + 128) : 0);
-  MZ_LAUNCH(ctx, k_minmax_lb, (unsigned)grid, RT, 0, d_batch_rows, n, prior, agg_kind, lb, d_out, out_cap,
+  MZ_LAUNCH(ctx, k_minmax_lb, (unsigned)grid, RT, 0, d_batch_rows, n, prior, agg_kind, tp, lb, d_out, out_cap,
             d_out_len, ctx->d_status);
   return MZGPU_OK;
 }

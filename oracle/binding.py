@@ -165,6 +165,7 @@ def lib():
             "mzo_update_stream": (None, [vp, vp, u64, vp]),
             "mzo_map_rows": (None, [vp, u64, vp, vp]),
             "mzo_reduce_new": (vp, [i32]),
+            "mzo_topk_new": (vp, [C.c_int64, u64, i32]),
             "mzo_reduce_free": (None, [vp]),
             "mzo_reduce_step": (None, [vp, vp, u64, u64, vp]),
             "mzo_explode": (None, [vp, u64, i32, vp]),
@@ -383,6 +384,13 @@ class Reduce:
         v = Vec(64)
         lib().mzo_reduce_step(self.h, _ptr(a), len(a), upper, v.h)
         return v.array()
+
+
+class TopK(Reduce):
+    """TopK per key (oracle ReduceTopK): limit < 0 = none."""
+
+    def __init__(self, limit, offset=0, descending=False):
+        self.h = lib().mzo_topk_new(limit, offset, 1 if descending else 0)
 
 
 def explode(a, agg_kind=0):

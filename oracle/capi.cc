@@ -466,11 +466,18 @@ void mzo_map_rows(const mzgpu_r32* rows, uint64_t n, const mzgpu_closure* closur
 struct AnyReduce {
   ReduceAccumulable* acc = nullptr;
   ReduceMinMax* mm = nullptr;
+  ReduceTopK* tk = nullptr;
   ~AnyReduce() {
     delete acc;
     delete mm;
+    delete tk;
   }
 };
+void* mzo_topk_new(int64_t limit, uint64_t offset, int32_t descending) {
+  AnyReduce* r = new AnyReduce();
+  r->tk = new ReduceTopK(limit, offset, descending != 0);
+  return r;
+}
 void* mzo_reduce_new(int32_t agg_kind) {
   AnyReduce* r = new AnyReduce();
   if (agg_kind == MZGPU_AGG_MIN || agg_kind == MZGPU_AGG_MAX)
@@ -485,6 +492,8 @@ void mzo_reduce_step(void* rv, const mzgpu_r32* rows, uint64_t n, uint64_t upper
   AnyReduce* r = (AnyReduce*)rv;
   if (r->mm)
     r->mm->step(rows, n, upper, out);
+  else if (r->tk)
+    r->tk->step(rows, n, upper, out);
   else
     r->acc->step(rows, n, upper, out);
   vec_append((Vec*)vec, out);

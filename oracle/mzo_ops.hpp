@@ -594,4 +594,116 @@ struct ReduceMinMax {
   }
 };
 
+// TopK per key (build_topk_negated_stage, top_k.rs:521-673): the live (value, count) pairs of the
+// key, a non-positive count -> the error row; otherwise order the values, skip `offset` rows and keep
+// at most `limit` (multiplicities counted).  The reference's reduce emits the negated complement and
+// the dataflow concatenates it with the input; the window itself is the resulting collection, and its
+// changes are what this operator emits.
+struct ReduceTopK {
+  i64 limit;  // < 0: none
+  u64 offset;
+  bool descending;
+  Batcher<mzgpu_r32> batcher;
+  ValSpine input;
+  struct Window {
+    bool error = false;
+    std::map<u64, i64> rows;  // value -> multiplicity inside the window
+  };
+  std::map<u64, Window> output;
+
+  ReduceTopK(i64 lim, u64 off, bool desc)
+      : limit(lim), offset(off), descending(desc), input(real_ops<mzgpu_r32>(), 1, false) {}
+
+  Window evaluate(const std::map<u64, i64>& acc) const {
+    Window w;
+    for (auto& kv : acc)
+      if (kv.second < 0) {
+        w.error = true;
+        return w;
+      }
+    u64 skip = offset;
+    i64 left = limit;
+    auto take = [&](u64 val, i64 cnt) {
+      if (cnt <= 0) return;
+      if (skip > 0) {
+        const u64 s = std::min<u64>(skip, (u64)cnt);
+        skip -= s;
+        cnt -= (i64)s;
+      }
+      if (limit >= 0) {
+        cnt = std::min(cnt, left);
+        left -= cnt;
+      }
+      if (cnt > 0) w.rows[val] = cnt;
+    };
+    if (descending)
+      for (auto it = acc.rbegin(); it != acc.rend(); ++it) take(it->first, it->second);
+    else
+      for (auto it = acc.begin(); it != acc.end(); ++it) take(it->first, it->second);
+    return w;
+  }
+
+  void step(const mzgpu_r32* rows, size_t n, u64 upper, std::vector<mzgpu_rout>& out) {
+    batcher.push_container(rows, n);
+    ValBatch batch = batcher.seal(upper);
+    std::vector<ValBatch> prior;
+    for (auto& e : input.all_batches()) prior.push_back(e.batch);
+    if (batch->desc.lower != batch->desc.upper) input.insert(batch);
+    input.set_physical_compaction(input.upper);
+    std::vector<mzgpu_rout> local;
+    CursorList<mzgpu_r32> pc(prior);
+    BatchCursor<mzgpu_r32> bc(batch.get());
+    auto emit = [&](u64 key, u64 val, u64 flags, u64 t, i64 d) {
+      mzgpu_rout o;
+      std::memset(&o, 0, sizeof(o));
+      o.key = key;
+      o.sum_lo = val;
+      o.flags = flags;
+      o.time = t;
+      o.diff = d;
+      local.push_back(o);
+    };
+    while (bc.key_valid()) {
+      const u64 key = bc.key();
+      std::map<u64, i64> acc;
+      pc.seek_key(key);
+      if (pc.key_valid() && pc.key() == key) {
+        while (pc.val_valid()) {
+          pc.map_times([&](const mzgpu_r32& r) { acc[r.val] += r.diff; });
+          pc.step_val();
+        }
+      }
+      std::map<u64, std::vector<mzgpu_r32>> by_time;
+      while (bc.val_valid()) {
+        bc.map_times([&](const mzgpu_r32& r) { by_time[r.time].push_back(r); });
+        bc.step_val();
+      }
+      for (auto& tv : by_time) {
+        for (auto& r : tv.second) {
+          acc[r.val] += r.diff;
+          if (acc[r.val] == 0) acc.erase(r.val);
+        }
+        const u64 t = tv.first;
+        Window fresh = evaluate(acc);
+        Window& old = output[key];
+        if (old.error != fresh.error) emit(key, 0, 2, t, fresh.error ? 1 : -1);
+        for (auto& kv : old.rows) {
+          auto it = fresh.rows.find(kv.first);
+          const i64 now = it == fresh.rows.end() ? 0 : it->second;
+          if (now != kv.second) emit(key, kv.first, 0, t, now - kv.second);
+        }
+        for (auto& kv : fresh.rows)
+          if (!old.rows.count(kv.first)) emit(key, kv.first, 0, t, kv.second);
+        if (!fresh.error && fresh.rows.empty())
+          output.erase(key);
+        else
+          old = fresh;
+      }
+      bc.step_key();
+    }
+    consolidate(local);
+    out.insert(out.end(), local.begin(), local.end());
+  }
+};
+
 }  // namespace mzo

@@ -479,6 +479,27 @@ def test_reduce_min_max_match_oracle(mz, ctx, oracle, agg_kind):
     assert saw_err
 
 
+@pytest.mark.parametrize(
+    "limit,offset,desc", [(1, 0, False), (3, 0, True), (2, 1, False), (None, 2, True), (0, 0, False), (40, 0, False)]
+)
+def test_topk_matches_oracle(mz, ctx, oracle, limit, offset, desc):
+    """TopK per key (top_k.rs:215-248, 521-673): windows shift as values arrive and retract, offsets
+    eat multiplicities, limits cut inside a value's copies, negative counts give the error row."""
+    rng = np.random.default_rng(90 + (limit or 0) + offset)
+    gr = mz.TopK(ctx, limit, offset, desc)
+    orr = oracle.TopK(-1 if limit is None else limit, offset, desc)
+    t = 0
+    for step in range(10):
+        n = int(rng.integers(1, 5000))
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 400, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 12, size=n, dtype=np.uint64) * np.uint64(0x0123456789ABCDEF)
+        a["time"] = rng.integers(t, t + 3, size=n, dtype=np.uint64)
+        a["diff"] = rng.integers(-1, 3, size=n, dtype=np.int64)
+        t += 3
+        same(gr.step(a, t), orr.step(a, t))
+
+
 def test_reduce_min_max_group_too_wide_is_reported(mz, oracle):
     """A key with more than 32 distinct live values needs the bucketed tree: reported, not wrong.
     (The report is deferred and poisons the context, hence a private one.)"""

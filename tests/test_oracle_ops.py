@@ -254,3 +254,44 @@ def test_min_max_accumulate_to_their_definitions(oracle, kind):
             else:
                 want[(k, 0, (min if kind == 4 else max)(nz), 0, 0)] = 1
         assert out_acc == want
+
+
+@pytest.mark.parametrize("limit,offset,desc", [(3, 0, False), (2, 1, True), (-1, 2, False), (0, 0, False), (5, 0, True)])
+def test_topk_accumulates_to_its_definition(oracle, limit, offset, desc):
+    """TopK (top_k.rs:521-673): the accumulated output is, per key, the rows [offset, offset+limit) of
+    the live values in order with multiplicities, or the error row when a count is negative."""
+    rng = np.random.default_rng(9)
+    r = oracle.TopK(limit, offset, desc)
+    acc, out_acc = {}, {}
+    for step in range(8):
+        n = 1200
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 100, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 10, size=n, dtype=np.uint64)
+        a["time"] = rng.integers(step * 2, step * 2 + 2, size=n, dtype=np.uint64)
+        a["diff"] = rng.integers(-1, 3, size=n)
+        out = r.step(a, step * 2 + 2)
+        for k, v, d in zip(a["key"].tolist(), a["val"].tolist(), a["diff"].tolist()):
+            acc.setdefault(k, {})
+            acc[k][v] = acc[k].get(v, 0) + d
+        for row in out.tolist():
+            key = (row[0], row[2], row[4])
+            out_acc[key] = out_acc.get(key, 0) + row[6]
+        out_acc = {k: v for k, v in out_acc.items() if v}
+        want = {}
+        for k, m in acc.items():
+            nz = {v: c for v, c in m.items() if c != 0}
+            if not nz:
+                continue
+            if any(c < 0 for c in nz.values()):
+                want[(k, 0, 2)] = 1
+                continue
+            rows = []
+            for v in sorted(nz, reverse=desc):
+                rows += [v] * nz[v]
+            rows = rows[offset:]
+            if limit >= 0:
+                rows = rows[:limit]
+            for v in rows:
+                want[(k, v, 0)] = want.get((k, v, 0), 0) + 1
+        assert out_acc == want
