@@ -45,8 +45,63 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.nvml, self.handle, self.samples, self.thread = None, None, [], None
+        self.stop_flag = threading.Event()
+
+    # -- in-process NVML (a query costs microseconds, so even a 10 ms timed region is sampled);
+    #    nvidia-smi -lms (below) is the fallback when NVML cannot be loaded
+    def _nvml_open(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except TypeError:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+        self.nvml, self.handle = pynvml, handle
+        self.sample_now()  # fails here (-> fallback) rather than in the thread
+
+    def sample_now(self):
+        """One sample of (SM MHz, max SM MHz, event-reason bits); called from the sampling thread and
+        once by the timing loop itself while the GPU still has the timed steps queued."""
+        if self.nvml is None:
+            return
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((float(sm), float(mx), int(bits)))
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.sample_now()
+            except Exception:
+                return
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            self._nvml_open()
+            self.samples = []  # the probe sample was taken before the timed region
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml, self.thread = None, None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -62,7 +117,33 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def _stop_nvml(self):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        n = self.nvml
+        names = [
+            ("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+            ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+            ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+            ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)),
+        ]
+        sm = sorted(x[0] for x in self.samples)
+        reasons = sorted({nm for _, _, bits in self.samples for nm, bit in names if bits & bit})
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(x[1] for x in self.samples) if self.samples else None,
+            "samples": len(sm),
+            "reasons": reasons,
+            "source": "nvml",
+        }
+
     def stop(self):
+        if self.nvml is not None:
+            try:
+                return self._stop_nvml()
+            except Exception as e:  # never let the sampler take the bench line down
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [f"nvml: {e}"]}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -277,6 +358,10 @@ def run_ours(args, rank, world, local_rank):
         rows_timed += staged_rows[b]
         b += 1
     e1.record(ext)
+    try:
+        clocks.sample_now()  # the GPU is still working through the queued steps
+    except Exception:
+        pass
     barrier()
     clk = clocks.stop()
     ms = allmax(e0.elapsed_time(e1))

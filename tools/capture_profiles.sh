@@ -16,7 +16,7 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_pr
   -o $O/${TAG}_probe python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_probe.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_rs_onesweep -s 10 -c 1 \
   -o $O/${TAG}_onesweep python tools/big_kernels.py sort > $O/${TAG}_ncu_onesweep.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:k_probe<" -s 2 -c 2 \
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:^k_probe$" -s 2 -c 2 \
   -o $O/${TAG}_probe_bulk python tools/big_kernels.py join > $O/${TAG}_ncu_probe_bulk.log 2>&1
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/${TAG}_clocks_idle.csv
 ls -la $O | tail -20
