@@ -171,6 +171,18 @@ class ClockSampler:
         }
 
 
+def oracle_workers():
+    """Worker threads of the CPU oracle dataflow: every host core (one timely worker per core, as
+    the reference deploys), unless MZ_ORACLE_WORKERS says otherwise.  At ~100K-row batches the
+    oracle is synchronisation bound well before 128 workers (8 workers on 8 cores already reach
+    ~1.2e7 rows/s at SF=1), so a smaller count can be the stronger baseline on a big host."""
+    try:
+        w = int(os.environ.get("MZ_ORACLE_WORKERS", "0"))
+    except ValueError:
+        w = 0
+    return w if w > 0 else (os.cpu_count() or 1)
+
+
 def measured_peak():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -187,7 +199,7 @@ def run_reference(args, rank):
         return
     from oracle import binding as B
 
-    cores = os.cpu_count() or 1
+    cores = oracle_workers()
     # same workload as our arm at --gpus N (weak scaling: SF and batch grow with N)
     sf = args.sf * max(1, args.gpus)
     q = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU * max(1, args.gpus), **scale(sf))
@@ -510,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import binding as B
 
-        cores = os.cpu_count() or 1
+        cores = oracle_workers()
         t0 = time.time()
         o = B.Q3(seed=SEED, workers=cores, per_batch=ORDERS_PER_BATCH_PER_GPU, **scale(args.sf))
         o.hydrate()
