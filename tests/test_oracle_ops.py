@@ -295,3 +295,40 @@ def test_topk_accumulates_to_its_definition(oracle, limit, offset, desc):
             for v in rows:
                 want[(k, v, 0)] = want.get((k, v, 0), 0) + 1
         assert out_acc == want
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_spine_preserves_contents_under_random_maintenance(oracle, seed):
+    """Whatever the fueled spine does (merges, roll-ups, idle effort, physical/logical compaction —
+    trace.rs:1698-2047), its accumulated contents are the consolidation of everything inserted with
+    times advanced to `since`, and every batch's description tiles [0, upper)."""
+    rng = np.random.default_rng(seed)
+    sp = oracle.Spine(32, 1, True)
+    inserted = []
+    t = 0
+    since = 0
+    for step in range(40):
+        n = int(rng.integers(0, 3000))
+        a = np.zeros(n, dtype=oracle.R32)
+        a["key"] = rng.integers(0, 300, size=n, dtype=np.uint64)
+        a["val"] = rng.integers(0, 5, size=n, dtype=np.uint64)
+        a["time"] = t
+        a["diff"] = rng.integers(-2, 3, size=n)
+        sp.insert(oracle.Batch.build(a, t, t + 1))
+        inserted.append(a)
+        t += 1
+        sp.set_physical_compaction(t)
+        if rng.integers(0, 3) == 0:
+            since = max(since, int(rng.integers(0, t)))
+            sp.set_logical_compaction(since)
+        if rng.integers(0, 4) == 0:
+            e = sp.exert_logic(16)
+            if e:
+                sp.exert(e)
+        assert sp.read_upper() == t
+        got = sp.export()
+        allr = np.concatenate(inserted)
+        allr["time"] = np.maximum(allr["time"], np.uint64(since))
+        # export folds with advance_by(since) applied: compare as consolidated collections
+        want = oracle.consolidate(allr)
+        assert oracle.consolidate(got).tobytes() == want.tobytes()
