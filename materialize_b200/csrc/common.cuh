@@ -58,6 +58,8 @@ struct mzgpu_ctx {
   // control blocks of the fused kernel, a pair per stream (each launch clears the other of its pair)
   void* d_fused_ctl[4] = {nullptr, nullptr, nullptr, nullptr};
   int fused_flip[2] = {0, 0};
+  void* d_fused_ctl_many[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // per job slot
+  int fused_flip_many[4] = {0, 0, 0, 0};
   // ---- side stream: batch merges (spine maintenance) run here, concurrently with the
   // operators on the main stream; a batch produced here carries side_seq and the main
   // stream waits for the side stream the first time it touches such a batch
@@ -654,6 +656,9 @@ struct FusedOut {
   Lazy4 kst;     // [0] rows kept, [1] min kept time (~0 if none), [2] max input time
 };
 int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
+// k independent jobs of one row width in one cooperative launch (k <= MZ_FUSED_MANY_MAX)
+#define MZ_FUSED_MANY_MAX 4
+int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs);
 size_t mz_fused_ctl_bytes();
 #define MZ_FUSED_MAX_ROWS (2u << 20)
 // ... judged by the exact row count when the host knows it.  When it only has an

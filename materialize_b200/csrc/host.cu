@@ -46,6 +46,10 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
   }
+  for (int i = 0; i < 8; ++i) {
+    MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl_many[i], mz_fused_ctl_bytes()));
+    MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl_many[i], 0, mz_fused_ctl_bytes()));
+  }
   ctx->main_stream = ctx->stream;
   MZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -93,6 +97,8 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int i = 0; i < 4; ++i)
     if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
