@@ -325,6 +325,13 @@ int32_t mzgpu_batcher_push_buf(mzgpu_batcher* b, mzgpu_buf* rows);
  * batcher frontier afterwards (min kept time or MZGPU_FRONTIER_EMPTY). */
 int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_batch** batch_out,
                            uint64_t* new_lower);
+/* Seal k distinct batchers of one context at the same frontier: the k arrangements a timely
+ * worker seals when a timestamp closes (one `Batcher::seal` per arrange operator,
+ * src/compute/src/extensions/arrange.rs:86-119, all activated by the same frontier advance).
+ * Results are those of k mzgpu_batcher_seal calls in this order; the update-batch-sized seals
+ * share one cooperative launch, so k seals cost about one. */
+int32_t mzgpu_batcher_seal_many(uint32_t k, mzgpu_batcher* const* batchers, uint64_t upper,
+                                mzgpu_batch** batches_out);
 /* Batcher::frontier (operator.rs:618-631). */
 uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b);
 /* Updates currently buffered. */

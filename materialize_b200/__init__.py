@@ -34,6 +34,7 @@ from .api import (  # noqa: F401
     Spine,
     TopK,
     half_join,
+    seal_many,
     half_join_dev,
     make_closure,
     map_rows,

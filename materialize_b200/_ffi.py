@@ -135,6 +135,7 @@ SIGNATURES = {
     "mzgpu_batcher_free": (None, [vp]),
     "mzgpu_batcher_push": (i32, [vp, vp, u64, i32]),
     "mzgpu_batcher_seal": (i32, [vp, u64, PV, PU64]),
+    "mzgpu_batcher_seal_many": (i32, [u32, vp, u64, vp]),
     "mzgpu_batcher_frontier": (u64, [vp]),
     "mzgpu_batcher_len": (u64, [vp]),
     "mzgpu_batch_build": (i32, [vp, u32, vp, u64, i32, Desc, PV]),

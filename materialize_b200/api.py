@@ -186,6 +186,18 @@ class DeviceRows:
             self.h = None
 
 
+def seal_many(batchers, upper):
+    """Seal several batchers at one frontier (mzgpu_batcher_seal_many): the same batches as
+    [b.seal_lazy(upper) for b in batchers]; update-batch-sized seals share one launch."""
+    k = len(batchers)
+    if k == 0:
+        return []
+    hs = (C.c_void_p * k)(*[b.h for b in batchers])
+    outs = (C.c_void_p * k)()
+    batchers[0].ctx.check(F.lib.mzgpu_batcher_seal_many(k, hs, upper, outs))
+    return [Batch(b.ctx, C.c_void_p(outs[i]), b.row_bytes) for i, b in enumerate(batchers)]
+
+
 class Batch:
     def __init__(self, ctx, h, row_bytes):
         self.ctx, self.h, self.row_bytes = ctx, h, row_bytes

@@ -203,10 +203,9 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   const uint64_t upper = t + 1;
   mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
   int32_t st = MZGPU_OK;
-  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
-    st = mzgpu_batcher_seal(q->batcher[a], upper, &batch[a], nullptr);
-    if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
-  }
+  // the four arrange operators are activated by the same frontier advance: one batched seal
+  st = mzgpu_batcher_seal_many(4, q->batcher, upper, batch);
+  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) st = mzgpu_spine_insert(q->spine[a], batch[a]);
   // The previous timestamp's maintenance runs here: the seals above are already queued on
   // the device, so the merges it schedules (side stream) and the few lengths it has to read
   // back overlap with them instead of delaying them.

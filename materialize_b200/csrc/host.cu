@@ -892,7 +892,22 @@ static int32_t batcher_push_dev(mzgpu_batcher* b, const void* d_rows, DLen n, u6
   }
   return batcher_push_seg(b, std::move(s));
 }
-static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
+// A seal in three steps, so that the fused launches of several batchers sealed at the same
+// frontier can share one cooperative launch (seal_many): plan (what to run) -> run -> finish.
+struct SealPlan {
+  mzgpu_batcher* b = nullptr;
+  u64 upper = 0;
+  mzgpu_desc d = {0, 0, 0};
+  u64 total = 0;
+  bool exact = true;
+  bool fused = false;  // one fused job (`job`) does the whole seal
+  DevMem all;          // concatenated stash (kept alive until the launch is enqueued)
+  Lazy4 alen;
+  FusedJob job;
+  FusedOut fo;
+};
+
+static int32_t seal_plan(mzgpu_batcher* b, u64 upper, SealPlan* p) {
   mzgpu_ctx* ctx = b->ctx;
   if (upper != MZGPU_FRONTIER_EMPTY && upper < b->lower) {
     MZ_SET_ERR(ctx, "batcher_seal: upper %llu precedes lower %llu", (unsigned long long)upper,
@@ -909,7 +924,9 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     }
     b->segs = std::move(live);
   }
-  mzgpu_desc d = {b->lower, upper, 0};
+  p->b = b;
+  p->upper = upper;
+  p->d = mzgpu_desc{b->lower, upper, 0};
   bool exact = true;
   for (auto& s : b->segs) exact = exact && s.len.known;
   if (!exact && !mz_use_fused(false, batcher_ub(b))) {
@@ -919,98 +936,159 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     }
     exact = true;
   }
-  const u64 total = batcher_ub(b);
-  if (total == 0) {
-    b->segs.clear();
-    b->frontier = MZGPU_FRONTIER_EMPTY;
-    b->frontier_known = true;
-    MZ_TRY(make_empty_batch(ctx, b->rb, d, batch_out));
-  } else if (mz_use_fused(exact, total)) {
-    DevMem all;
-    Lazy4 alen;
+  p->exact = exact;
+  p->total = batcher_ub(b);
+  p->fused = p->total > 0 && mz_use_fused(exact, p->total);
+  if (p->fused) {
     int aword = 0;
     u64 aub = 0;
-    FusedJob job;
-    job.rb = b->rb;
+    p->job.rb = b->rb;
     if (b->segs.size() == 1) {
-      job.a = b->segs[0].rows.p;
-      job.na = dlen_of(b->segs[0].len, b->segs[0].word);
+      p->job.a = b->segs[0].rows.p;
+      p->job.na = dlen_of(b->segs[0].len, b->segs[0].word);
     } else {
-      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
-      job.a = all.p;
-      job.na = dlen_of(alen, aword);
+      MZ_TRY(batcher_concat(b, &p->all, &p->alen, &aword, &aub));
+      p->job.a = p->all.p;
+      p->job.na = dlen_of(p->alen, aword);
     }
-    job.cap = total;
-    job.upper = upper;
-    job.want_index = true;
-    FusedOut fo;
-    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
-    b->segs.clear();  // stream ordered: the kernel above still reads them
-    if (upper != MZGPU_FRONTIER_EMPTY) {
-      Seg k;
-      k.rows = std::move(fo.keep);
-      k.len = std::move(fo.kst);
-      k.word = 0;
-      k.ub = total;
-      k.is_keep = true;
-      b->segs.push_back(std::move(k));
-      b->frontier_known = false;
-    } else {
-      b->frontier = MZGPU_FRONTIER_EMPTY;
-      b->frontier_known = true;
-    }
-    MZ_TRY(batch_from_fused(ctx, b->rb, std::move(fo), total, d, batch_out));
+    p->job.cap = p->total;
+    p->job.upper = upper;
+    p->job.want_index = true;
+  }
+  return MZGPU_OK;
+}
+
+// after the fused launch of the plan has been enqueued
+static int32_t seal_finish_fused(SealPlan* p, mzgpu_batch** batch_out) {
+  mzgpu_batcher* b = p->b;
+  mzgpu_ctx* ctx = b->ctx;
+  b->segs.clear();  // stream ordered: the kernel still reads them
+  if (p->upper != MZGPU_FRONTIER_EMPTY) {
+    Seg k;
+    k.rows = std::move(p->fo.keep);
+    k.len = std::move(p->fo.kst);
+    k.word = 0;
+    k.ub = p->total;
+    k.is_keep = true;
+    b->segs.push_back(std::move(k));
+    b->frontier_known = false;
   } else {
-    // bulk path: exact sizes, multi-kernel sort / extract
-    DevMem all, cons;
-    Lazy4 alen, clen;
-    int aword = 0;
-    u64 aub = 0, cap = 0;
-    const void* src = nullptr;
-    DLen sn;
-    if (b->segs.size() == 1) {
-      src = b->segs[0].rows.p;
-      sn = dlen_of(b->segs[0].len, b->segs[0].word);
-      aub = b->segs[0].ub;
-    } else {
-      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
-      src = all.p;
-      sn = dlen_of(alen, aword);
-    }
-    ctx->last_minmax_valid = false;
-    MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
-    MZ_TRY(clen.resolve());
-    b->segs.clear();
-    all.release();
-    const u64 n_cons = clen.v[0];
     b->frontier = MZGPU_FRONTIER_EMPTY;
     b->frontier_known = true;
-    // the bulk sort has seen the range of the time word: if every buffered time precedes
-    // `upper` everything ships and the extract pass (two more copies of the rows) is skipped
-    const int tw = b->rb == 32 ? 2 : 1;
-    const bool all_ship = ctx->last_minmax_valid && ctx->last_minmax[2 * tw + 1] < upper;
-    if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0 || all_ship) {
-      MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
-    } else {
-      DevMem ship, keep;
-      u64 n_ship = 0, n_keep = 0, min_keep = MZGPU_FRONTIER_EMPTY;
-      MZ_TRY(mz_extract(ctx, b->rb, cons.p, n_cons, upper, &ship, &n_ship, &keep, &n_keep, &min_keep));
-      cons.release();
-      if (n_keep) {
-        Seg k;
-        k.rows = std::move(keep);
-        k.len.set(ctx, n_keep);
-        k.ub = n_keep;
-        b->segs.push_back(std::move(k));
-        b->frontier = min_keep;
-      }
-      MZ_TRY(make_batch(ctx, b->rb, std::move(ship), n_ship, d, batch_out));
+  }
+  return batch_from_fused(ctx, b->rb, std::move(p->fo), p->total, p->d, batch_out);
+}
+
+// the seals a fused job cannot take: nothing buffered, or the bulk multi-kernel path
+static int32_t seal_run_unfused(SealPlan* p, mzgpu_batch** batch_out) {
+  mzgpu_batcher* b = p->b;
+  mzgpu_ctx* ctx = b->ctx;
+  const u64 upper = p->upper;
+  const mzgpu_desc d = p->d;
+  if (p->total == 0) {
+    b->segs.clear();
+    b->frontier = MZGPU_FRONTIER_EMPTY;
+    b->frontier_known = true;
+    return make_empty_batch(ctx, b->rb, d, batch_out);
+  }
+  // bulk path: exact sizes, multi-kernel sort / extract
+  DevMem all, cons;
+  Lazy4 alen, clen;
+  int aword = 0;
+  u64 aub = 0, cap = 0;
+  const void* src = nullptr;
+  DLen sn;
+  if (b->segs.size() == 1) {
+    src = b->segs[0].rows.p;
+    sn = dlen_of(b->segs[0].len, b->segs[0].word);
+    aub = b->segs[0].ub;
+  } else {
+    MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
+    src = all.p;
+    sn = dlen_of(alen, aword);
+  }
+  ctx->last_minmax_valid = false;
+  MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
+  MZ_TRY(clen.resolve());
+  b->segs.clear();
+  all.release();
+  const u64 n_cons = clen.v[0];
+  b->frontier = MZGPU_FRONTIER_EMPTY;
+  b->frontier_known = true;
+  // the bulk sort has seen the range of the time word: if every buffered time precedes
+  // `upper` everything ships and the extract pass (two more copies of the rows) is skipped
+  const int tw = b->rb == 32 ? 2 : 1;
+  const bool all_ship = ctx->last_minmax_valid && ctx->last_minmax[2 * tw + 1] < upper;
+  if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0 || all_ship) {
+    MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
+  } else {
+    DevMem ship, keep;
+    u64 n_ship = 0, n_keep = 0, min_keep = MZGPU_FRONTIER_EMPTY;
+    MZ_TRY(mz_extract(ctx, b->rb, cons.p, n_cons, upper, &ship, &n_ship, &keep, &n_keep, &min_keep));
+    cons.release();
+    if (n_keep) {
+      Seg k;
+      k.rows = std::move(keep);
+      k.len.set(ctx, n_keep);
+      k.ub = n_keep;
+      b->segs.push_back(std::move(k));
+      b->frontier = min_keep;
     }
+    MZ_TRY(make_batch(ctx, b->rb, std::move(ship), n_ship, d, batch_out));
+  }
+  return MZGPU_OK;
+}
+
+static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
+  SealPlan p;
+  MZ_TRY(seal_plan(b, upper, &p));
+  if (p.fused) {
+    MZ_TRY(mz_fused_consolidate(b->ctx, p.job, &p.fo));
+    MZ_TRY(seal_finish_fused(&p, batch_out));
+  } else {
+    MZ_TRY(seal_run_unfused(&p, batch_out));
   }
   b->lower = upper;
   if (new_lower) {
     MZ_TRY(batcher_resolve_frontier(b));
     *new_lower = b->frontier;
+  }
+  return MZGPU_OK;
+}
+
+// Seal k batchers at the same frontier; the fused jobs of one row width share ONE cooperative
+// launch (groups of MZ_FUSED_MANY_MAX).  Same results as k batcher_seal calls in this order.
+static int32_t batcher_seal_many(int k, mzgpu_batcher* const* bs, u64 upper, mzgpu_batch** batches_out) {
+  if (k <= 0) return MZGPU_OK;
+  std::vector<SealPlan> plans((size_t)k);
+  for (int i = 0; i < k; ++i) {
+    batches_out[i] = nullptr;
+    MZ_TRY(seal_plan(bs[i], upper, &plans[(size_t)i]));
+  }
+  std::vector<char> done((size_t)k, 0);
+  for (int i = 0; i < k; ++i) {
+    if (done[(size_t)i] || !plans[(size_t)i].fused) continue;
+    // this plan and the later fused plans of the same row width
+    int idx[MZ_FUSED_MANY_MAX];
+    int g = 0;
+    for (int j = i; j < k && g < MZ_FUSED_MANY_MAX; ++j)
+      if (!done[(size_t)j] && plans[(size_t)j].fused && plans[(size_t)j].job.rb == plans[(size_t)i].job.rb) idx[g++] = j;
+    FusedJob jobs[MZ_FUSED_MANY_MAX];
+    FusedOut outs[MZ_FUSED_MANY_MAX];
+    for (int t = 0; t < g; ++t) jobs[t] = plans[(size_t)idx[t]].job;
+    MZ_TRY(mz_fused_consolidate_many(bs[i]->ctx, g, jobs, outs));
+    for (int t = 0; t < g; ++t) {
+      plans[(size_t)idx[t]].fo = std::move(outs[t]);
+      done[(size_t)idx[t]] = 1;
+    }
+  }
+  for (int i = 0; i < k; ++i) {
+    SealPlan& p = plans[(size_t)i];
+    if (p.fused)
+      MZ_TRY(seal_finish_fused(&p, &batches_out[i]));
+    else
+      MZ_TRY(seal_run_unfused(&p, &batches_out[i]));
+    bs[i]->lower = upper;
   }
   return MZGPU_OK;
 }
@@ -1051,6 +1129,18 @@ extern "C" int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_ba
   if (b == nullptr || batch_out == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
   return batcher_seal(b, upper, batch_out, new_lower);
+}
+extern "C" int32_t mzgpu_batcher_seal_many(uint32_t k, mzgpu_batcher* const* batchers, uint64_t upper,
+                                           mzgpu_batch** batches_out) {
+  if (k == 0) return MZGPU_OK;
+  if (batchers == nullptr || batches_out == nullptr) return MZGPU_E_INVALID;
+  for (uint32_t i = 0; i < k; ++i) {
+    if (batchers[i] == nullptr || batchers[i]->ctx != batchers[0]->ctx) return MZGPU_E_INVALID;
+    for (uint32_t j = 0; j < i; ++j)
+      if (batchers[j] == batchers[i]) return MZGPU_E_INVALID;
+  }
+  MZ_CHECK_CTX(batchers[0]->ctx);
+  return batcher_seal_many((int)k, batchers, upper, batches_out);
 }
 extern "C" uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b) {
   if (b == nullptr) return MZGPU_FRONTIER_EMPTY;

@@ -245,6 +245,29 @@ def test_batcher_seal_matches_oracle(mz, ctx, oracle):
             lower = upper
 
 
+def test_seal_many_matches_single_seals(mz, ctx, oracle):
+    """mzgpu_batcher_seal_many: k arrangements sealed by one frontier advance in one launch give the
+    batches, kept rows and frontiers of k separate seals (and of the oracle's batchers)."""
+    rng = np.random.default_rng(31)
+    sizes = [30000, 0, 7000, 90000, 1]
+    gbs = [mz.Batcher(ctx, 32) for _ in sizes]
+    obs = [oracle.Batcher(32) for _ in sizes]
+    t = 0
+    for rnd in range(4):
+        for gb, ob, n in zip(gbs, obs, sizes):
+            a = rand_r32(rng, n, 1 << (8 + 4 * rnd), 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = rng.integers(t, t + 4, size=n, dtype=np.uint64)  # some rows stay behind the frontier
+            gb.push_container(a)
+            ob.push(a)
+        t += 2
+        got = mz.seal_many(gbs, t)
+        for g, gb, ob in zip(got, gbs, obs):
+            o = ob.seal(t)
+            same(g.rows(), o.rows())
+            assert g.desc() == o.desc()
+            assert gb.frontier() == ob.frontier()
+
+
 def test_batch_merge_matches_oracle(mz, ctx, oracle):
     rng = np.random.default_rng(22)
     for since in (0, 2, 4, 100):
