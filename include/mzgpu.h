@@ -415,6 +415,16 @@ int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int
 /* The same with the stream in a device buffer: nothing returns to the host. */
 int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
                             const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out);
+/* k half joins over device-resident streams in one launch: the half-join stages that the delta
+ * paths of one dataflow run side by side at a timestamp (`build_delta_join` renders one path per
+ * input relation, delta_join.rs:71-310; their stages are independent operators).  Request j
+ * probes streams[j] against traces[j] and appends to outs[j] exactly as
+ * mzgpu_half_join_buf(..., consolidate_output = 0, ...) would; requests naming the same output
+ * buffer must be adjacent and append in request order (the concatenation of the paths' outputs,
+ * delta_join.rs:302-308).  closures may be NULL (identity closures for every request). */
+int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* const* streams,
+                             mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                             const mzgpu_closure* const* closures, mzgpu_buf* const* outs);
 /* build_update_stream (delta_join.rs:600-707): a batch's updates as a stream,
  * `initial_closure` applied (val2 unused), updates at `skip_time` dropped when
  * skip_time != MZGPU_FRONTIER_EMPTY (the as_of rule for source_relation != 0). */

@@ -36,6 +36,7 @@ from .api import (  # noqa: F401
     half_join,
     seal_many,
     half_join_dev,
+    half_join_many,
     make_closure,
     map_rows,
     route,

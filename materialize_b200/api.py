@@ -394,6 +394,21 @@ def half_join_dev(ctx, dev_stream, trace, cmp_mode, closure=None, consolidate_ou
     return out
 
 
+def half_join_many(ctx, requests):
+    """Several half joins in one launch (mzgpu_half_join_many).  requests: (dev_stream, trace, cmp_mode,
+    closure or None, out DeviceRows); requests naming the same `out` must be adjacent and append in order."""
+    k = len(requests)
+    if k == 0:
+        return
+    streams = (C.c_void_p * k)(*[r[0].h for r in requests])
+    traces = (C.c_void_p * k)(*[r[1].h for r in requests])
+    cmps = (C.c_int32 * k)(*[r[2] for r in requests])
+    # a NULL entry means the identity closure (key, val2), as in mzgpu_half_join_buf
+    cls = (C.c_void_p * k)(*[C.cast(C.pointer(r[3]), C.c_void_p) if r[3] is not None else None for r in requests])
+    outs = (C.c_void_p * k)(*[r[4].h for r in requests])
+    ctx.check(F.lib.mzgpu_half_join_many(ctx.h, k, streams, traces, cmps, cls, outs))
+
+
 def update_stream_dev(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY, out=None):
     out = out if out is not None else DeviceRows(ctx, 32)
     ctx.check(F.lib.mzgpu_update_stream(ctx.h, batch.h, _clp(closure), skip_time, out.h))

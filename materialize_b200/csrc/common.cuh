@@ -341,6 +341,8 @@ struct LookBack {
   u32 epoch;    // tag of this launch
 };
 int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb);  // host.cu
+// the same over the state words [at, at + max_tiles): concurrent chains of one launch
+int32_t mz_lookback_begin_at(mzgpu_ctx* ctx, u64 at, u64 max_tiles, LookBack* lb);
 
 // ---------------------------------------------------------------- row traits
 // A row is NW 64-bit words: NK sort-key words first (compared as unsigned, in
@@ -718,6 +720,20 @@ struct ProbeParams {
   int swap_vals;    // join_core side 1: probe rows are val2, lookup rows are val1
   mzgpu_closure closure;
 };
+#define MZ_PROBE_MANY_MAX 3
+struct ProbeJobHost {
+  const u64* d_stream;
+  DLen n;
+  u64 n_ub;
+  const TraceView* trace;
+  const ProbeParams* pp;
+  int chain;  // jobs with equal chain ids are consecutive and append to one output
+  u64* d_out;
+  DLen out_base;
+  u64 out_cap;
+  u64* d_out_len;
+};
+int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs);
 // Probe `n` R32 stream rows against the trace; appends results to d_out
 // (allocated here) and returns the count.  One sync (to size the output).
 int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& trace,

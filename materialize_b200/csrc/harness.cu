@@ -238,21 +238,28 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       for (int path = 0; path < 3; ++path)
         if (active[path]) std::swap(q->pstream[path], q->pxchg[path]);
     }
+    // the active paths' stage-s half joins are independent operators: one launch.  Last stage:
+    // the paths' outputs are concatenated (delta_join.rs:302-308), so every path appends
+    // straight to the result collection (one chain, path order)
+    mzgpu_buf *hs[3], *ho[3];
+    mzgpu_spine* ht[3];
+    int32_t hc[3];
+    const mzgpu_closure* hcl[3];
+    uint32_t hk = 0;
     for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
       if (!active[path]) continue;
-      if (s == 1) {
-        // last stage: the paths' outputs are concatenated (delta_join.rs:302-308), so
-        // each path appends straight to the result collection
-        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                                 &q->plan.stage[path][s], 0, q->results);
-        continue;
-      }
-      st = mzgpu_buf_clear(q->pnext[path]);
-      if (st == MZGPU_OK)
-        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                                 &q->plan.stage[path][s], 0, q->pnext[path]);
-      std::swap(q->pstream[path], q->pnext[path]);
+      if (s == 0) st = mzgpu_buf_clear(q->pnext[path]);
+      hs[hk] = q->pstream[path];
+      ht[hk] = q->spine[q->plan.lookup[path][s]];
+      hc[hk] = q->plan.cmp[path][s];
+      hcl[hk] = &q->plan.stage[path][s];
+      ho[hk] = s == 1 ? q->results : q->pnext[path];
+      ++hk;
     }
+    if (st == MZGPU_OK) st = mzgpu_half_join_many(q->ctx, hk, hs, ht, hc, hcl, ho);
+    if (s == 0)
+      for (int path = 0; path < 3; ++path)
+        if (active[path]) std::swap(q->pstream[path], q->pnext[path]);
   }
   if (st == MZGPU_OK && q->peers > 1) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);

@@ -186,8 +186,12 @@ int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   return MZGPU_OK;
 }
 int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb) {
-  if (max_tiles > MZ_LB_TILES) {
-    MZ_SET_ERR(ctx, "single-pass kernel: %llu tiles exceed the look-back state", (unsigned long long)max_tiles);
+  return mz_lookback_begin_at(ctx, 0, max_tiles, lb);
+}
+int32_t mz_lookback_begin_at(mzgpu_ctx* ctx, u64 at, u64 max_tiles, LookBack* lb) {
+  if (at + max_tiles > MZ_LB_TILES) {
+    MZ_SET_ERR(ctx, "single-pass kernel: %llu tiles exceed the look-back state",
+               (unsigned long long)(at + max_tiles));
     return MZGPU_E_UNSUPPORTED;
   }
   ctx->lb_epoch = (ctx->lb_epoch + 1) & 0xfffffu;
@@ -199,7 +203,7 @@ int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb) {
     MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4, ctx->stream));
     ctx->ticket_next = 0;
   }
-  lb->state = ctx->d_lb;
+  lb->state = ctx->d_lb + at;
   lb->ticket = ctx->d_tickets + ctx->ticket_next++;
   lb->epoch = ctx->lb_epoch;
   return MZGPU_OK;
@@ -1828,6 +1832,122 @@ extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint
   }
   return half_join_dev(ctx, d_stream, dlen_imm(n), n, trace, cmp_mode, closure, consolidate_output, out);
 }
+// k half joins in one launch (mz_probe_async_many).  Requests whose output buffers coincide must
+// be adjacent: they form a chain whose results are appended in request order -- the last stage of
+// the delta paths, whose outputs are concatenated (delta_join.rs:302-308).  Anything the single
+// launch cannot take (unbounded fan-out, an empty stream or trace, a buffer named twice apart)
+// runs request by request; the results are the same either way.
+struct HalfJoinReq {
+  mzgpu_buf* stream;
+  mzgpu_spine* trace;
+  int32_t cmp_mode;
+  const mzgpu_closure* closure;
+  mzgpu_buf* out;
+};
+static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs) {
+  auto one_by_one = [&]() -> int32_t {
+    for (int j = 0; j < k; ++j)
+      MZ_TRY(half_join_dev(ctx, reqs[j].stream->mem.as<u64>(), buf_dlen(reqs[j].stream), reqs[j].stream->ub,
+                           reqs[j].trace, reqs[j].cmp_mode, reqs[j].closure, 0, reqs[j].out));
+    return MZGPU_OK;
+  };
+  if (k < 2 || k > MZ_PROBE_MANY_MAX) return one_by_one();
+  static TraceView tvs[MZ_PROBE_MANY_MAX];  // large: kept off the stack (a context is confined to one thread)
+  ProbeParams pps[MZ_PROBE_MANY_MAX];
+  u64 bound[MZ_PROBE_MANY_MAX];
+  u64 tiles = 0;
+  for (int j = 0; j < k; ++j) {
+    const HalfJoinReq& r = reqs[j];
+    for (int i = 0; i + 1 < j; ++i)
+      if (reqs[i].out == r.out && reqs[j - 1].out != r.out) return one_by_one();
+    for (int i = 0; i < k; ++i)
+      if (reqs[i].stream == r.out) return one_by_one();
+    if (r.stream->ub == 0) return one_by_one();
+    std::vector<mzgpu_batch*> all;
+    r.trace->all_batches(all);
+    u64 fan = 0;
+    bool exact = true;
+    MZ_TRY(trace_fanout(all, &fan, &exact));
+    MZ_TRY(trace_view(ctx, all, &tvs[j]));
+    if (tvs[j].n_batches == 0 || !exact || fan == 0 || r.stream->ub > MZ_BOUND_MAX_ROWS / fan) return one_by_one();
+    bound[j] = r.stream->ub * fan;
+    tiles += (r.stream->ub + 255) / 256;
+    memset(&pps[j], 0, sizeof(ProbeParams));
+    pps[j].mode = r.cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
+    pps[j].has_closure = 1;
+    if (r.closure) {
+      pps[j].closure = *r.closure;
+    } else {
+      pps[j].closure.n_key_fields = 1;
+      pps[j].closure.key_fields[0] = mzgpu_field{MZGPU_SRC_KEY, 0, 64, 0};
+      pps[j].closure.n_val_fields = 1;
+      pps[j].closure.val_fields[0] = mzgpu_field{MZGPU_SRC_VAL2, 0, 64, 0};
+    }
+  }
+  if (tiles > MZ_LB_TILES) return one_by_one();
+  // chains: reserve each output for the sum of its requests' bounds, open one append per chain
+  ProbeJobHost jobs[MZ_PROBE_MANY_MAX];
+  Append app[MZ_PROBE_MANY_MAX];
+  u64 chain_bound[MZ_PROBE_MANY_MAX];
+  int chain_first[MZ_PROBE_MANY_MAX];
+  int nc = 0;
+  for (int j = 0; j < k; ++j) {
+    if (j == 0 || reqs[j].out != reqs[j - 1].out) {
+      chain_first[nc] = j;
+      chain_bound[nc] = 0;
+      ++nc;
+    }
+    chain_bound[nc - 1] += bound[j];
+  }
+  for (int c = 0; c < nc; ++c) {
+    mzgpu_buf* out = reqs[chain_first[c]].out;
+    MZ_TRY(buf_reserve(out, out->ub + chain_bound[c], true));
+    MZ_TRY(buf_begin_append(out, &app[c]));
+  }
+  int c = -1;
+  for (int j = 0; j < k; ++j) {
+    if (j == 0 || reqs[j].out != reqs[j - 1].out) ++c;
+    mzgpu_buf* out = reqs[j].out;
+    jobs[j].d_stream = reqs[j].stream->mem.as<u64>();
+    jobs[j].n = buf_dlen(reqs[j].stream);
+    jobs[j].n_ub = reqs[j].stream->ub;
+    jobs[j].trace = &tvs[j];
+    jobs[j].pp = &pps[j];
+    jobs[j].chain = c;
+    jobs[j].d_out = out->mem.as<u64>();
+    jobs[j].out_base = app[c].base;
+    jobs[j].out_cap = out->cap;
+    jobs[j].d_out_len = app[c].out_len;
+  }
+  MZ_TRY(mz_probe_async_many(ctx, k, jobs));
+  for (int cc = 0; cc < nc; ++cc) buf_end_append(reqs[chain_first[cc]].out, app[cc], chain_bound[cc]);
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* const* streams,
+                                        mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                                        const mzgpu_closure* const* closures, mzgpu_buf* const* outs) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (streams == nullptr || traces == nullptr || cmp_modes == nullptr || outs == nullptr || k > 64)
+    return MZGPU_E_INVALID;
+  std::vector<HalfJoinReq> reqs(k);
+  for (uint32_t j = 0; j < k; ++j) {
+    if (streams[j] == nullptr || traces[j] == nullptr || outs[j] == nullptr || streams[j] == outs[j] ||
+        streams[j]->rb != 32 || traces[j]->rb != 32 || outs[j]->rb != 32 ||
+        (cmp_modes[j] != MZGPU_HALFJOIN_LE && cmp_modes[j] != MZGPU_HALFJOIN_LT))
+      return MZGPU_E_INVALID;
+    reqs[j] = HalfJoinReq{streams[j], traces[j], cmp_modes[j], closures ? closures[j] : nullptr, outs[j]};
+    ctx->stats.rows_in += streams[j]->ub;
+  }
+  // groups of at most MZ_PROBE_MANY_MAX, never splitting a chain's adjacency
+  for (uint32_t at = 0; at < k; at += MZ_PROBE_MANY_MAX) {
+    const int g = (int)std::min<uint32_t>(MZ_PROBE_MANY_MAX, k - at);
+    MZ_TRY(half_join_many_dev(ctx, g, reqs.data() + at));
+  }
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
                                        const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);

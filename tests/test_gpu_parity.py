@@ -410,6 +410,40 @@ def test_half_join_matches_oracle(mz, ctx, oracle, cmp_mode):
         same(got, want)
 
 
+def test_half_join_many_matches_single_half_joins(mz, ctx, oracle):
+    """mzgpu_half_join_many: independent half joins of one stage in one launch; requests naming the
+    same output form a chain and append in request order (the concatenated outputs of the delta
+    paths' last stage) -- row for row what the single calls produce."""
+    rng = np.random.default_rng(77)
+    spines = []
+    for sp in range(3):
+        gs = mz.Spine(ctx, 32)
+        for t in range(3 + sp):
+            a = rand_r32(rng, 3000, 400 + 100 * sp, 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = t
+            gs.insert(mz.Batch.build(ctx, a, t, t + 1))
+            gs.set_physical_compaction(t + 1)
+        spines.append(gs)
+    streams = [rand_r32(rng, n, 600, 1 << 20, 8, dtype=oracle.R32) for n in (5000, 1, 777)]
+    cl = mz.make_closure(key_fields=[(2, 0, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 10, 10, 20)], filters=[(2, 0, 20, "lt", 900000)])
+    closures = [None, cl, cl]
+    cmps = [mz.HALFJOIN_LE, mz.HALFJOIN_LT, mz.HALFJOIN_LE]
+    devs = [mz.DeviceRows(ctx, 32).upload(s) for s in streams]
+    # (a) three independent outputs, (b) chain of two + one apart, (c) one chain of three
+    for layout in ([0, 1, 2], [0, 0, 1], [0, 0, 0]):
+        outs = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        want = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        # something already in the buffers: appends must start behind it
+        for o, w in zip(outs, want):
+            o.upload(streams[1])
+            w.upload(streams[1])
+        mz.half_join_many(ctx, [(devs[j], spines[j], cmps[j], closures[j], outs[layout[j]]) for j in range(3)])
+        for j in range(3):
+            mz.half_join_dev(ctx, devs[j], spines[j], cmps[j], closures[j], False, want[layout[j]])
+        for o, w in zip(outs, want):
+            same(o.download(), w.download())
+
+
 def test_update_stream_and_map_rows(mz, ctx, oracle):
     rng = np.random.default_rng(28)
     a = rand_r32(rng, 5000, 100, 1 << 12, 3, dtype=oracle.R32)
