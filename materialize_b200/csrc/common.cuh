@@ -58,8 +58,12 @@ struct mzgpu_ctx {
   // control blocks of the fused kernel, a pair per stream (each launch clears the other of its pair)
   void* d_fused_ctl[4] = {nullptr, nullptr, nullptr, nullptr};
   int fused_flip[2] = {0, 0};
-  void* d_fused_ctl_many[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // per job slot
-  int fused_flip_many[4] = {0, 0, 0, 0};
+  void* d_fused_ctl_many[16] = {};  // per job slot: 0-3 multi-job launches, 4-7 deferred jobs
+  int fused_flip_many[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* fused_deferred = nullptr;       // fused.cu: jobs prepared but not launched yet
+  std::vector<struct mzgpu_batch*> deferred_inputs;  // retained until the flush
+  u64 defer_seq = 0, flushed_seq = 0;   // deferred jobs enqueued / launched
+  bool defer_merges = true;             // spine merges wait for each other (MZGPU_DEFER_MERGES=0: launch at once)
   // ---- side stream: batch merges (spine maintenance) run here, concurrently with the
   // operators on the main stream; a batch produced here carries side_seq and the main
   // stream waits for the side stream the first time it touches such a batch
@@ -661,6 +665,10 @@ int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out)
 // k independent jobs of one row width in one cooperative launch (k <= MZ_FUSED_MANY_MAX)
 #define MZ_FUSED_MANY_MAX 4
 int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs);
+// prepare now, launch with the other deferred jobs at mz_fused_flush (host.cu: mz_flush_deferred)
+int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
+int32_t mz_fused_flush(mzgpu_ctx* ctx);
+void mz_fused_deferred_free(mzgpu_ctx* ctx);
 size_t mz_fused_ctl_bytes();
 #define MZ_FUSED_MAX_ROWS (2u << 20)
 // ... judged by the exact row count when the host knows it.  When it only has an

@@ -1353,10 +1353,10 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   return MZGPU_OK;
 }
 
-// k independent jobs (same row width) in one cooperative launch.  The resident capacity is
+// k prepared jobs (same row width) in one cooperative launch.  The resident capacity is
 // shared out in proportion to what each job alone would take.
 template <int RB>
-int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs) {
+int32_t fused_launch_many(mzgpu_ctx* ctx, int k, const FusedArgs* args, const u64* want_in, u64 bytes) {
   static int max_ctas = 0;
   if (max_ctas == 0) {
     int per_sm = 0;
@@ -1367,19 +1367,17 @@ int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs
       return MZGPU_E_CUDA;
     }
   }
-  FusedMany m;
+  static FusedMany m;  // ~1.5 KB, passed by value
   memset(&m, 0, sizeof(m));
   m.k = (u32)k;
-  DevMem scratch[FUSED_MANY_MAX];
   u64 want[FUSED_MANY_MAX];
-  u64 want_sum = 0, bytes = 0;
+  u64 want_sum = 0;
   const u64 solo_max = std::min<u64>(2ull * (u64)ctx->num_sms, (u64)max_ctas);
   for (int j = 0; j < k; ++j) {
-    MZ_TRY(fused_prepare<RB>(ctx, jobs[j], &outs[j], j, &m.job[j], &want[j], &scratch[j]));
-    if (want[j] > solo_max) want[j] = solo_max;
+    m.job[j] = args[j];
+    want[j] = want_in[j] > solo_max ? solo_max : want_in[j];
     if (want[j] == 0) want[j] = 1;
     want_sum += want[j];
-    if (jobs[j].na.p == nullptr && jobs[j].nb.p == nullptr) bytes += (jobs[j].na.imm + jobs[j].nb.imm) * RB * 4;
   }
   u32 at = 0;
   for (int j = 0; j < k; ++j) {
@@ -1412,6 +1410,24 @@ int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs
     }
   }
   ctx->stats.kernel_launches++;
+  return MZGPU_OK;
+}
+
+static u64 fused_job_bytes(const FusedJob& job) {
+  return (job.na.p == nullptr && job.nb.p == nullptr) ? (job.na.imm + job.nb.imm) * (u64)job.rb * 4 : 0;
+}
+
+template <int RB>
+int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs) {
+  FusedArgs args[FUSED_MANY_MAX];
+  DevMem scratch[FUSED_MANY_MAX];
+  u64 want[FUSED_MANY_MAX];
+  u64 bytes = 0;
+  for (int j = 0; j < k; ++j) {
+    MZ_TRY(fused_prepare<RB>(ctx, jobs[j], &outs[j], j, &args[j], &want[j], &scratch[j]));
+    bytes += fused_job_bytes(jobs[j]);
+  }
+  MZ_TRY(fused_launch_many<RB>(ctx, k, args, want, bytes));
   for (int j = 0; j < k; ++j) {
     outs[j].st.mark_written();
     outs[j].kst.mark_written();
@@ -1419,9 +1435,80 @@ int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs
   return MZGPU_OK;
 }
 
+// Jobs prepared now and launched together later (mz_fused_defer / mz_fused_flush): the merges that
+// the spine inserts of one timestamp trigger.  Their control blocks are the job slots
+// FUSED_MANY_MAX .. 2 * FUSED_MANY_MAX - 1, used in prepare order = launch order.
+struct FusedDeferred {
+  int rb = 0;
+  int k = 0;
+  FusedArgs args[FUSED_MANY_MAX];
+  u64 want[FUSED_MANY_MAX];
+  DevMem scratch[FUSED_MANY_MAX];
+  u64 bytes = 0;
+};
+
+template <int RB>
+int32_t fused_defer_t(mzgpu_ctx* ctx, FusedDeferred* d, const FusedJob& job, FusedOut* out) {
+  const int j = d->k;
+  MZ_TRY(fused_prepare<RB>(ctx, job, out, FUSED_MANY_MAX + j, &d->args[j], &d->want[j], &d->scratch[j]));
+  d->bytes += fused_job_bytes(job);
+  d->rb = RB;
+  d->k = j + 1;
+  return MZGPU_OK;
+}
+
 }  // namespace
 
 size_t mz_fused_ctl_bytes() { return sizeof(FusedCtl); }
+
+int32_t mz_fused_flush(mzgpu_ctx* ctx) {
+  FusedDeferred* d = (FusedDeferred*)ctx->fused_deferred;
+  if (d == nullptr || d->k == 0) return MZGPU_OK;
+  const int k = d->k;
+  d->k = 0;  // whatever happens below, the jobs are not retried
+  int32_t st;
+  switch (d->rb) {
+    case 16: st = fused_launch_many<16>(ctx, k, d->args, d->want, d->bytes); break;
+    case 32: st = fused_launch_many<32>(ctx, k, d->args, d->want, d->bytes); break;
+    case 40: st = fused_launch_many<40>(ctx, k, d->args, d->want, d->bytes); break;
+    case 80: st = fused_launch_many<80>(ctx, k, d->args, d->want, d->bytes); break;
+    case 64: st = fused_launch_many<64>(ctx, k, d->args, d->want, d->bytes); break;
+    default: st = MZGPU_E_UNSUPPORTED; break;
+  }
+  for (int j = 0; j < k; ++j) d->scratch[j].release();  // stream ordered: after the launch
+  d->bytes = 0;
+  if (st != MZGPU_OK) ctx->sticky = true;  // outputs were promised to readers
+  return st;
+}
+
+void mz_fused_deferred_free(mzgpu_ctx* ctx) {
+  delete (FusedDeferred*)ctx->fused_deferred;
+  ctx->fused_deferred = nullptr;
+}
+
+// Prepare `job` (buffers, counters, control block) and leave the launch to mz_fused_flush.  The
+// result counters count as written from now on: mz_resolve_counters flushes before it copies the
+// arena, so a counter can never be read back ahead of its launch.
+int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out) {
+  if (ctx->fused_deferred == nullptr) ctx->fused_deferred = new FusedDeferred();
+  FusedDeferred* d = (FusedDeferred*)ctx->fused_deferred;
+  if (d->k > 0 && (d->rb != job.rb || d->k == FUSED_MANY_MAX)) MZ_TRY(mz_fused_flush(ctx));
+  int32_t st;
+  switch (job.rb) {
+    case 16: st = fused_defer_t<16>(ctx, d, job, out); break;
+    case 32: st = fused_defer_t<32>(ctx, d, job, out); break;
+    case 40: st = fused_defer_t<40>(ctx, d, job, out); break;
+    case 80: st = fused_defer_t<80>(ctx, d, job, out); break;
+    case 64: st = fused_defer_t<64>(ctx, d, job, out); break;
+    default:
+      MZ_SET_ERR(ctx, "fused: unsupported row width %d", job.rb);
+      return MZGPU_E_UNSUPPORTED;
+  }
+  if (st != MZGPU_OK) return st;
+  out->st.mark_written();
+  out->kst.mark_written();
+  return MZGPU_OK;
+}
 
 int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs) {
   if (k <= 0) return MZGPU_OK;

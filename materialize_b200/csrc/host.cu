@@ -46,7 +46,8 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
   }
-  for (int i = 0; i < 8; ++i) {
+  if (const char* e = getenv("MZGPU_DEFER_MERGES")) ctx->defer_merges = atoi(e) != 0;
+  for (int i = 0; i < 16; ++i) {
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl_many[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl_many[i], 0, mz_fused_ctl_bytes()));
   }
@@ -97,8 +98,9 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int i = 0; i < 4; ++i)
     if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 16; ++i)
     if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
+  mz_fused_deferred_free(ctx);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
@@ -154,8 +156,11 @@ static int32_t mz_join_side(mzgpu_ctx* ctx) {
   }
   return MZGPU_OK;
 }
+static int32_t mz_flush_deferred(mzgpu_ctx* ctx);
 int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   MZ_CHECK_CTX(ctx);
+  // counters of deferred jobs count as written: their launch must precede the copy
+  MZ_TRY(mz_flush_deferred(ctx));
   // counts may have been written on either stream
   if (ctx->stream == ctx->main_stream) {
     MZ_TRY(mz_join_side(ctx));
@@ -599,9 +604,22 @@ struct mzgpu_batch {
   mzgpu_desc desc;
   int refs = 1;
   u64 side_seq = 0;  // != 0: produced by merge #side_seq on the side stream
+  u64 deferred_seq = 0;  // != 0: produced by deferred job #deferred_seq (launched at the next flush)
 };
+static void batch_release_internal(mzgpu_batch* b);
+// Launch the deferred merges (one multi-job launch) and let go of their inputs.
+static int32_t mz_flush_deferred(mzgpu_ctx* ctx) {
+  if (ctx->flushed_seq == ctx->defer_seq) return MZGPU_OK;
+  ctx->flushed_seq = ctx->defer_seq;
+  const int32_t st = mz_fused_flush(ctx);
+  std::vector<mzgpu_batch*> ins;
+  ins.swap(ctx->deferred_inputs);
+  for (auto* b : ins) batch_release_internal(b);  // freed in stream order, behind the launch
+  return st;
+}
 // before the main stream reads or frees a batch: wait for the merge that produced it
 static int32_t batch_ready(mzgpu_batch* b) {
+  if (b->deferred_seq > b->ctx->flushed_seq) MZ_TRY(mz_flush_deferred(b->ctx));
   if (b->side_seq > b->ctx->joined_seq) return mz_join_side(b->ctx);
   return MZGPU_OK;
 }
@@ -734,12 +752,13 @@ extern "C" mzgpu_desc mzgpu_batch_desc(const mzgpu_batch* b) {
 extern "C" void mzgpu_batch_retain(mzgpu_batch* b) {
   if (b) b->refs++;
 }
-extern "C" void mzgpu_batch_release(mzgpu_batch* b) {
+static void batch_release_internal(mzgpu_batch* b) {
   if (b && --b->refs == 0) {
     batch_ready(b);  // its memory is freed in stream order on the current stream
     delete b;
   }
 }
+extern "C" void mzgpu_batch_release(mzgpu_batch* b) { batch_release_internal(b); }
 extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, int32_t mem,
                                       uint64_t* n_out) {
   if (b == nullptr) return MZGPU_E_INVALID;
@@ -755,6 +774,10 @@ extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, 
 // Batch::Merger in one step: union, advance_by(since), consolidate, index.
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
+  // an input that is itself the output of a deferred merge must be launched first (jobs of one
+  // multi-job launch run side by side)
+  MZ_TRY(batch_ready(b1));
+  MZ_TRY(batch_ready(b2));
   mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
   if (!mz_use_fused(false, b1->len_ub + b2->len_ub)) {
     MZ_TRY(batch_resolve(b1));
@@ -772,6 +795,20 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
     job.want_index = true;
     job.merge = true;
     FusedOut fo;
+    if (ctx->defer_merges && ctx->stream == ctx->main_stream) {
+      // The merges that the inserts of one timestamp trigger (one per arrangement, all alike)
+      // are independent: they are prepared here and launched together, by the first reader of
+      // any of their outputs (batch_ready) or the next counter read-back.
+      MZ_TRY(mz_fused_defer(ctx, job, &fo));
+      b1->refs++;
+      b2->refs++;
+      ctx->deferred_inputs.push_back(b1);
+      ctx->deferred_inputs.push_back(b2);
+      const u64 seq = ++ctx->defer_seq;
+      MZ_TRY(batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out));
+      (*out)->deferred_seq = seq;
+      return MZGPU_OK;
+    }
     MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
     return batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out);
   }
