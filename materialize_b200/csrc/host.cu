@@ -2150,8 +2150,16 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
                                            corr.as<u64>(), per_row * b_ub, clen.dptr());
         clen.mark_written();
       }
-      if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), per_row * b_ub, &cons, &ccap, &flen);
-      if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : per_row * b_ub);
+      if (st == MZGPU_OK && !minmax) {
+        // the accumulable kinds' corrections leave the kernel consolidated (reduce.cu:
+        // sort_key_corrections): keys ascending, each key's few rows sorted by its thread
+        st = buf_append_dev(out, corr.p, dlen_of(clen, 0), per_row * b_ub);
+      } else {
+        if (st == MZGPU_OK)
+          st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), per_row * b_ub, &cons, &ccap, &flen);
+        if (st == MZGPU_OK)
+          st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : per_row * b_ub);
+      }
     } else {
       DevMem corr, cons;
       u64 n_corr = 0, ccap = 0;
