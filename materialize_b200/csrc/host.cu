@@ -1726,6 +1726,8 @@ extern "C" int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch
   return MZGPU_OK;
 }
 
+// bulk probes (join_core work items): the bounded single-pass form may take this much output memory
+#define MZ_BULK_BOUND_BYTES (12ull << 30)
 extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out,
                                         int32_t* done) {
   if (j == nullptr || out == nullptr) return MZGPU_E_INVALID;
@@ -1757,7 +1759,30 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
       pp.has_closure = j->has_closure ? 1 : 0;
       pp.swap_vals = w.side == 1 ? 1 : 0;
       pp.closure = j->closure;
-      st = mz_probe(j->ctx, w.batch->rows.as<u64>(), w.batch->st.v[0], tv, pp, &res, &n_res);
+      // Bounded fan-out: one pass into a buffer of n x (sum of the longest key runs) rows -- the
+      // probe walks the trace once instead of twice (count, write) and the only read-back is the
+      // result count that the fuel accounting needs anyway.
+      u64 fan = 0;
+      bool exact = true;
+      st = trace_fanout(w.others, &fan, &exact);
+      const u64 n_probe = w.batch->st.v[0];
+      const bool bounded = st == MZGPU_OK && exact && fan > 0 && n_probe > 0 &&
+                           n_probe <= MZ_BULK_BOUND_BYTES / (fan * out_rb) && (n_probe + 255) / 256 <= MZ_LB_TILES;
+      if (st == MZGPU_OK && bounded) {
+        Lazy4 rlen;
+        const u64 bound = n_probe * fan;
+        st = res.alloc(j->ctx, bound * out_rb);
+        if (st == MZGPU_OK) st = rlen.make_pending(j->ctx);
+        if (st == MZGPU_OK) {
+          st = mz_probe_async(j->ctx, w.batch->rows.as<u64>(), dlen_imm(n_probe), n_probe, tv, pp, res.as<u64>(),
+                              dlen_imm(0), bound, rlen.dptr());
+          rlen.mark_written();
+        }
+        if (st == MZGPU_OK) st = rlen.resolve();
+        if (st == MZGPU_OK) n_res = rlen.v[0];
+      } else if (st == MZGPU_OK) {
+        st = mz_probe(j->ctx, w.batch->rows.as<u64>(), n_probe, tv, pp, &res, &n_res);
+      }
     }
     // Work::process consolidates each work item's output buffer before sending
     if (st == MZGPU_OK && n_res)

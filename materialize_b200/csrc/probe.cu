@@ -104,14 +104,16 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // Pass 0 counts the matches and keeps the first KC output rows in a per-thread cache; after the
 // scan + look-back the cached rows are written, and only a probe row with more than KC matches
 // walks the trace again (pass 1).
-template <int OUT_NW>
-__global__ void __launch_bounds__(PT, 2) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+// KC / MINB: update batches cache eight output rows per probe row (lookups with a fan-out of
+// up to eight never walk twice) at two CTAs per SM; bulk probes (millions of rows, fan-out ~1)
+// keep two and trade the cache registers for twice the resident warps -- their limit is the
+// number of DRAM accesses in flight.  GROUP = batches whose first slot is fetched together.
+template <int OUT_NW, int KC, int MINB, int GROUP>
+__global__ void __launch_bounds__(PT, MINB) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
                                                  u64* __restrict__ out_len, u64* __restrict__ status) {
-  constexpr int KC = 8;
-  constexpr int GROUP = 8;
   __shared__ u32 sm[34];
   __shared__ u32 s_tile;
   __shared__ u64 s_b;
@@ -656,12 +658,23 @@ int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, co
   MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
   const int out_rb = pp.has_closure ? 32 : 40;
   MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 * trace.n_batches + 32 + out_rb) : 0);  // exact counts only
+  const bool bulk = n_ub >= (1ull << 20);
   if (pp.has_closure) {
-    MZ_LAUNCH(ctx, (k_probe_lb<4>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
-              out_cap, d_out_len, ctx->d_status);
+    if (bulk) {
+      MZ_LAUNCH(ctx, (k_probe_lb<4, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    } else {
+      MZ_LAUNCH(ctx, (k_probe_lb<4, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    }
   } else {
-    MZ_LAUNCH(ctx, (k_probe_lb<5>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
-              out_cap, d_out_len, ctx->d_status);
+    if (bulk) {
+      MZ_LAUNCH(ctx, (k_probe_lb<5, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    } else {
+      MZ_LAUNCH(ctx, (k_probe_lb<5, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    }
   }
   return MZGPU_OK;
 }
