@@ -1367,7 +1367,7 @@ int32_t fused_launch_many(mzgpu_ctx* ctx, int k, const FusedArgs* args, const u6
       return MZGPU_E_CUDA;
     }
   }
-  static FusedMany m;  // ~1.5 KB, passed by value
+  static thread_local FusedMany m;  // ~1.5 KB, passed by value
   memset(&m, 0, sizeof(m));
   m.k = (u32)k;
   u64 want[FUSED_MANY_MAX];

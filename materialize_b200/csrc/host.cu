@@ -1914,7 +1914,7 @@ static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs
     return MZGPU_OK;
   };
   if (k < 2 || k > MZ_PROBE_MANY_MAX) return one_by_one();
-  static TraceView tvs[MZ_PROBE_MANY_MAX];  // large: kept off the stack (a context is confined to one thread)
+  static thread_local TraceView tvs[MZ_PROBE_MANY_MAX];  // large: kept off the stack
   ProbeParams pps[MZ_PROBE_MANY_MAX];
   u64 bound[MZ_PROBE_MANY_MAX];
   u64 tiles = 0;

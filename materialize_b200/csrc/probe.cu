@@ -687,7 +687,7 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     MZ_SET_ERR(ctx, "probe: %d jobs exceed the maximum %d per launch", k, PROBE_MANY_MAX);
     return MZGPU_E_INVALID;
   }
-  static ProbeMany m;  // large: kept off the stack (a context is confined to one thread)
+  static thread_local ProbeMany m;  // large: kept off the stack
   memset(&m, 0, sizeof(m));
   const bool closure = jobs[0].pp->has_closure != 0;
   u64 lb_at = 0, max_grid = 1, bytes = 0;
