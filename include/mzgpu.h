@@ -425,6 +425,16 @@ int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trac
 int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* const* streams,
                              mzgpu_spine* const* traces, const int32_t* cmp_modes,
                              const mzgpu_closure* const* closures, mzgpu_buf* const* outs);
+/* The first stage of k delta paths in one launch: request j forms the update stream of
+ * batches[j] (build_update_stream, delta_join.rs:312-377: updates at skip_times[j] dropped unless
+ * it is MZGPU_FRONTIER_EMPTY, initial_closures[j] applied) inside the probe kernel and half-joins
+ * it against traces[j] -- the results of mzgpu_update_stream followed by mzgpu_half_join_buf(...,
+ * consolidate_output = 0, ...) without materialising the stream.  Single-worker dataflows only:
+ * with peers > 1 the stream is exchanged by its new key between the two steps. */
+int32_t mzgpu_delta_first_stage_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_batch* const* batches,
+                                     const mzgpu_closure* const* initial_closures, const uint64_t* skip_times,
+                                     mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                                     const mzgpu_closure* const* closures, mzgpu_buf* const* outs);
 /* build_update_stream (delta_join.rs:600-707): a batch's updates as a stream,
  * `initial_closure` applied (val2 unused), updates at `skip_time` dropped when
  * skip_time != MZGPU_FRONTIER_EMPTY (the as_of rule for source_relation != 0). */

@@ -37,6 +37,7 @@ from .api import (  # noqa: F401
     seal_many,
     half_join_dev,
     half_join_many,
+    delta_first_stage_many,
     make_closure,
     map_rows,
     route,

@@ -126,6 +126,7 @@ SIGNATURES = {
     "mzgpu_batcher_push_buf": (i32, [vp, vp]),
     "mzgpu_half_join_buf": (i32, [vp, vp, vp, i32, C.POINTER(Closure), i32, vp]),
     "mzgpu_half_join_many": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+    "mzgpu_delta_first_stage_many": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, vp]),
     "mzgpu_reduce_accumulable_buf": (i32, [vp, vp, u64, vp]),
     "mzgpu_buf_download": (i32, [vp, vp, u64, i32, PU64]),
     "mzgpu_buf_clear": (i32, [vp]),

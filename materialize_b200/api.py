@@ -409,6 +409,27 @@ def half_join_many(ctx, requests):
     ctx.check(F.lib.mzgpu_half_join_many(ctx.h, k, streams, traces, cmps, cls, outs))
 
 
+def delta_first_stage_many(ctx, requests):
+    """build_update_stream + first half join of several delta paths in one launch
+    (mzgpu_delta_first_stage_many).  requests: (batch, initial_closure or None, skip_time, trace, cmp_mode,
+    closure or None, out DeviceRows)."""
+    k = len(requests)
+    if k == 0:
+        return
+
+    def ptrs(cls):
+        return (C.c_void_p * k)(*[C.cast(C.pointer(c), C.c_void_p) if c is not None else None for c in cls])
+
+    batches = (C.c_void_p * k)(*[r[0].h for r in requests])
+    initial = ptrs([r[1] for r in requests])
+    skips = (C.c_uint64 * k)(*[r[2] for r in requests])
+    traces = (C.c_void_p * k)(*[r[3].h for r in requests])
+    cmps = (C.c_int32 * k)(*[r[4] for r in requests])
+    closures = ptrs([r[5] for r in requests])
+    outs = (C.c_void_p * k)(*[r[6].h for r in requests])
+    ctx.check(F.lib.mzgpu_delta_first_stage_many(ctx.h, k, batches, initial, skips, traces, cmps, closures, outs))
+
+
 def update_stream_dev(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY, out=None):
     out = out if out is not None else DeviceRows(ctx, 32)
     ctx.check(F.lib.mzgpu_update_stream(ctx.h, batch.h, _clp(closure), skip_time, out.h))

@@ -736,6 +736,9 @@ struct ProbeJobHost {
   const TraceView* trace;
   const ProbeParams* pp;
   int chain;  // jobs with equal chain ids are consecutive and append to one output
+  bool has_pre = false;                 // map in front of the probe: drop rows at skip_time, apply `pre`
+  const mzgpu_closure* pre = nullptr;   // (nullptr: identity)
+  u64 skip_time = MZGPU_FRONTIER_EMPTY;
   u64* d_out;
   DLen out_base;
   u64 out_cap;

@@ -218,6 +218,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
     active[path] = !(q->static_rel[q->plan.source[path]] && q->stepping);
     if (q->streams_prepared) continue;  // mapped and exchanged together with the inputs (mzh_q3_step)
+    if (q->peers == 1) continue;        // one worker: the update stream is formed inside the first half join
     st = mzgpu_buf_clear(q->pstream[path]);
     // as_of rule: only the first relation's path sees the updates at as_of (= 0)
     if (st == MZGPU_OK && active[path])
@@ -256,7 +257,24 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       ho[hk] = s == 1 ? q->results : q->pnext[path];
       ++hk;
     }
-    if (st == MZGPU_OK) st = mzgpu_half_join_many(q->ctx, hk, hs, ht, hc, hcl, ho);
+    if (st == MZGPU_OK && s == 0 && q->peers == 1 && !q->streams_prepared) {
+      // build_update_stream + the first half join of every active path in one launch
+      mzgpu_batch* hb[3];
+      const mzgpu_closure* hi[3];
+      uint64_t hskip[3];
+      uint32_t j = 0;
+      for (int path = 0; path < 3; ++path) {
+        if (!active[path]) continue;
+        hb[j] = batch[q->plan.source[path]];
+        hi[j] = &q->plan.initial[path];
+        // as_of rule: only the first relation's path sees the updates at as_of (= 0)
+        hskip[j] = path == 0 ? MZGPU_FRONTIER_EMPTY : 0;
+        ++j;
+      }
+      st = mzgpu_delta_first_stage_many(q->ctx, hk, hb, hi, hskip, ht, hc, hcl, ho);
+    } else if (st == MZGPU_OK) {
+      st = mzgpu_half_join_many(q->ctx, hk, hs, ht, hc, hcl, ho);
+    }
     if (s == 0)
       for (int path = 0; path < 3; ++path)
         if (active[path]) std::swap(q->pstream[path], q->pnext[path]);

@@ -1900,20 +1900,45 @@ extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint
 // launch cannot take (unbounded fan-out, an empty stream or trace, a buffer named twice apart)
 // runs request by request; the results are the same either way.
 struct HalfJoinReq {
-  mzgpu_buf* stream;
+  mzgpu_buf* stream;  // the stream to probe with, or ...
   mzgpu_spine* trace;
   int32_t cmp_mode;
   const mzgpu_closure* closure;
   mzgpu_buf* out;
+  // ... a sealed batch whose update stream (build_update_stream: rows at `skip_time` dropped,
+  // `pre` applied) is formed inside the probe kernel
+  mzgpu_batch* src = nullptr;
+  const mzgpu_closure* pre = nullptr;
+  u64 skip_time = MZGPU_FRONTIER_EMPTY;
 };
+static int32_t map_rows_into(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, const mzgpu_closure* closure,
+                             u64 skip_time, mzgpu_buf* out);
+static const u64* req_rows(const HalfJoinReq& r) { return r.src ? r.src->rows.as<u64>() : r.stream->mem.as<u64>(); }
+static DLen req_dlen(const HalfJoinReq& r) { return r.src ? batch_dlen(r.src) : buf_dlen(r.stream); }
+static u64 req_ub(const HalfJoinReq& r) { return r.src ? r.src->len_ub : r.stream->ub; }
 static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs) {
   auto one_by_one = [&]() -> int32_t {
-    for (int j = 0; j < k; ++j)
-      MZ_TRY(half_join_dev(ctx, reqs[j].stream->mem.as<u64>(), buf_dlen(reqs[j].stream), reqs[j].stream->ub,
-                           reqs[j].trace, reqs[j].cmp_mode, reqs[j].closure, 0, reqs[j].out));
+    for (int j = 0; j < k; ++j) {
+      const HalfJoinReq& r = reqs[j];
+      if (r.src != nullptr) {
+        // the separate operators: update stream into a scratch buffer, then the half join
+        mzgpu_buf tmp;
+        tmp.ctx = ctx;
+        tmp.rb = 32;
+        tmp.len.set(ctx, 0);
+        MZ_TRY(map_rows_into(ctx, req_rows(r), req_dlen(r), req_ub(r), r.pre, r.skip_time, &tmp));
+        MZ_TRY(half_join_dev(ctx, tmp.mem.as<u64>(), buf_dlen(&tmp), tmp.ub, r.trace, r.cmp_mode, r.closure, 0, r.out));
+      } else {
+        MZ_TRY(half_join_dev(ctx, req_rows(r), req_dlen(r), req_ub(r), r.trace, r.cmp_mode, r.closure, 0, r.out));
+      }
+    }
     return MZGPU_OK;
   };
-  if (k < 2 || k > MZ_PROBE_MANY_MAX) return one_by_one();
+  for (int j = 0; j < k; ++j)
+    if (reqs[j].src != nullptr) MZ_TRY(batch_ready(reqs[j].src));
+  bool any_src = false;
+  for (int j = 0; j < k; ++j) any_src = any_src || reqs[j].src != nullptr;
+  if ((k < 2 && !any_src) || k > MZ_PROBE_MANY_MAX) return one_by_one();
   static thread_local TraceView tvs[MZ_PROBE_MANY_MAX];  // large: kept off the stack
   ProbeParams pps[MZ_PROBE_MANY_MAX];
   u64 bound[MZ_PROBE_MANY_MAX];
@@ -1923,17 +1948,17 @@ static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs
     for (int i = 0; i + 1 < j; ++i)
       if (reqs[i].out == r.out && reqs[j - 1].out != r.out) return one_by_one();
     for (int i = 0; i < k; ++i)
-      if (reqs[i].stream == r.out) return one_by_one();
-    if (r.stream->ub == 0) return one_by_one();
+      if (reqs[i].stream != nullptr && reqs[i].stream == r.out) return one_by_one();
+    if (req_ub(r) == 0) return one_by_one();
     std::vector<mzgpu_batch*> all;
     r.trace->all_batches(all);
     u64 fan = 0;
     bool exact = true;
     MZ_TRY(trace_fanout(all, &fan, &exact));
     MZ_TRY(trace_view(ctx, all, &tvs[j]));
-    if (tvs[j].n_batches == 0 || !exact || fan == 0 || r.stream->ub > MZ_BOUND_MAX_ROWS / fan) return one_by_one();
-    bound[j] = r.stream->ub * fan;
-    tiles += (r.stream->ub + 255) / 256;
+    if (tvs[j].n_batches == 0 || !exact || fan == 0 || req_ub(r) > MZ_BOUND_MAX_ROWS / fan) return one_by_one();
+    bound[j] = req_ub(r) * fan;
+    tiles += (req_ub(r) + 255) / 256;
     memset(&pps[j], 0, sizeof(ProbeParams));
     pps[j].mode = r.cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
     pps[j].has_closure = 1;
@@ -1970,9 +1995,12 @@ static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs
   for (int j = 0; j < k; ++j) {
     if (j == 0 || reqs[j].out != reqs[j - 1].out) ++c;
     mzgpu_buf* out = reqs[j].out;
-    jobs[j].d_stream = reqs[j].stream->mem.as<u64>();
-    jobs[j].n = buf_dlen(reqs[j].stream);
-    jobs[j].n_ub = reqs[j].stream->ub;
+    jobs[j].d_stream = req_rows(reqs[j]);
+    jobs[j].n = req_dlen(reqs[j]);
+    jobs[j].n_ub = req_ub(reqs[j]);
+    jobs[j].has_pre = reqs[j].src != nullptr;
+    jobs[j].pre = reqs[j].pre;
+    jobs[j].skip_time = reqs[j].skip_time;
     jobs[j].trace = &tvs[j];
     jobs[j].pp = &pps[j];
     jobs[j].chain = c;
@@ -1999,10 +2027,47 @@ extern "C" int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* c
         streams[j]->rb != 32 || traces[j]->rb != 32 || outs[j]->rb != 32 ||
         (cmp_modes[j] != MZGPU_HALFJOIN_LE && cmp_modes[j] != MZGPU_HALFJOIN_LT))
       return MZGPU_E_INVALID;
-    reqs[j] = HalfJoinReq{streams[j], traces[j], cmp_modes[j], closures ? closures[j] : nullptr, outs[j]};
+    reqs[j].stream = streams[j];
+    reqs[j].trace = traces[j];
+    reqs[j].cmp_mode = cmp_modes[j];
+    reqs[j].closure = closures ? closures[j] : nullptr;
+    reqs[j].out = outs[j];
     ctx->stats.rows_in += streams[j]->ub;
   }
   // groups of at most MZ_PROBE_MANY_MAX, never splitting a chain's adjacency
+  for (uint32_t at = 0; at < k; at += MZ_PROBE_MANY_MAX) {
+    const int g = (int)std::min<uint32_t>(MZ_PROBE_MANY_MAX, k - at);
+    MZ_TRY(half_join_many_dev(ctx, g, reqs.data() + at));
+  }
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_delta_first_stage_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_batch* const* batches,
+                                                const mzgpu_closure* const* initial_closures,
+                                                const uint64_t* skip_times, mzgpu_spine* const* traces,
+                                                const int32_t* cmp_modes, const mzgpu_closure* const* closures,
+                                                mzgpu_buf* const* outs) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (batches == nullptr || skip_times == nullptr || traces == nullptr || cmp_modes == nullptr || outs == nullptr ||
+      k > 64)
+    return MZGPU_E_INVALID;
+  std::vector<HalfJoinReq> reqs(k);
+  for (uint32_t j = 0; j < k; ++j) {
+    if (batches[j] == nullptr || traces[j] == nullptr || outs[j] == nullptr || batches[j]->rb != 32 ||
+        traces[j]->rb != 32 || outs[j]->rb != 32 ||
+        (cmp_modes[j] != MZGPU_HALFJOIN_LE && cmp_modes[j] != MZGPU_HALFJOIN_LT))
+      return MZGPU_E_INVALID;
+    reqs[j].stream = nullptr;
+    reqs[j].src = batches[j];
+    reqs[j].pre = initial_closures ? initial_closures[j] : nullptr;
+    reqs[j].skip_time = skip_times[j];
+    reqs[j].trace = traces[j];
+    reqs[j].cmp_mode = cmp_modes[j];
+    reqs[j].closure = closures ? closures[j] : nullptr;
+    reqs[j].out = outs[j];
+    ctx->stats.rows_in += batches[j]->len_ub;
+  }
   for (uint32_t at = 0; at < k; at += MZ_PROBE_MANY_MAX) {
     const int g = (int)std::min<uint32_t>(MZ_PROBE_MANY_MAX, k - at);
     MZ_TRY(half_join_many_dev(ctx, g, reqs.data() + at));

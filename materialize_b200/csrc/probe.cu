@@ -256,6 +256,11 @@ struct ProbeJobDev {
   DLen dn;
   TraceView tv;
   ProbeParams pp;
+  // optional map in front of the probe (build_update_stream fused into the first half join,
+  // delta_join.rs:312-377): rows at `skip_time` are dropped, the closure rewrites (key, val) or drops
+  int has_pre, pre_has_closure;
+  u64 skip_time;
+  mzgpu_closure pre;
 };
 struct ProbeChain {
   u32 first, count;  // jobs [first, first + count)
@@ -311,6 +316,20 @@ __global__ void __launch_bounds__(PT, 2) k_probe_chains(const __grid_constant__ 
       t1 = td.x;
       d1 = (i64)td.y;
     }
+    bool live = i < n;
+    if (live && J.has_pre) {
+      if (J.skip_time != MZGPU_FRONTIER_EMPTY && t1 == J.skip_time) {
+        live = false;
+      } else if (J.pre_has_closure) {
+        u64 k, v;
+        if (closure_eval(J.pre, key, v1, 0, &k, &v)) {
+          key = k;
+          v1 = v;
+        } else {
+          live = false;
+        }
+      }
+    }
     u64 cache[KC][OUT_NW];
     u32 cnt = 0;
     u64 pos = 0;
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(PT, 2) k_probe_chains(const __grid_constant__ 
     u64 excl = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      const bool walk = i < n && (pass == 0 || cnt > (u32)KC);
+      const bool walk = live && (pass == 0 || cnt > (u32)KC);
       if (walk) {
         const u64 h0 = mix64(key);
 #pragma unroll 1
@@ -701,6 +720,10 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     m.job[j].dn = jobs[j].n;
     m.job[j].tv = *jobs[j].trace;
     m.job[j].pp = *jobs[j].pp;
+    m.job[j].has_pre = jobs[j].has_pre ? 1 : 0;
+    m.job[j].pre_has_closure = (jobs[j].has_pre && jobs[j].pre != nullptr) ? 1 : 0;
+    m.job[j].skip_time = jobs[j].skip_time;
+    if (m.job[j].pre_has_closure) m.job[j].pre = *jobs[j].pre;
     if (j == 0 || jobs[j].chain != jobs[j - 1].chain) {
       ProbeChain& c = m.chain[nc++];
       c.first = (u32)j;

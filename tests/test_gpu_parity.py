@@ -444,6 +444,39 @@ def test_half_join_many_matches_single_half_joins(mz, ctx, oracle):
             same(o.download(), w.download())
 
 
+def test_delta_first_stage_many_matches_separate_operators(mz, ctx, oracle):
+    """mzgpu_delta_first_stage_many = update_stream (as_of skip + initial closure) then half_join,
+    for one and for several paths, including paths that share the output collection."""
+    rng = np.random.default_rng(78)
+    spines, batches = [], []
+    for sp in range(3):
+        gs = mz.Spine(ctx, 32)
+        for t in range(2 + sp):
+            a = rand_r32(rng, 3000, 400, 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = t
+            gs.insert(mz.Batch.build(ctx, a, t, t + 1))
+            gs.set_physical_compaction(t + 1)
+        spines.append(gs)
+        b = rand_r32(rng, (4000, 2, 900)[sp], 500, 1 << 20, 3, dtype=oracle.R32)
+        batches.append(mz.Batch.build(ctx, b, 0, 3))
+    init = mz.make_closure(key_fields=[(1, 0, 9, 0)], val_fields=[(0, 0, 20, 0)], filters=[(1, 0, 20, "lt", 800000)])
+    stage = mz.make_closure(key_fields=[(2, 0, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 10, 10, 20)])
+    inits = [init, None, init]
+    skips = [mz.FRONTIER_EMPTY, 0, 1]
+    cmps = [mz.HALFJOIN_LE, mz.HALFJOIN_LT, mz.HALFJOIN_LE]
+    for k, layout in ((1, [0]), (3, [0, 1, 2]), (3, [0, 0, 0]), (2, [0, 0])):
+        outs = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        want = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        mz.delta_first_stage_many(
+            ctx, [(batches[j], inits[j], skips[j], spines[j], cmps[j], stage, outs[layout[j]]) for j in range(k)]
+        )
+        for j in range(k):
+            stream = mz.update_stream_dev(ctx, batches[j], inits[j], skips[j])
+            mz.half_join_dev(ctx, stream, spines[j], cmps[j], stage, False, want[layout[j]])
+        for o, w in zip(outs, want):
+            same(o.download(), w.download())
+
+
 def test_update_stream_and_map_rows(mz, ctx, oracle):
     rng = np.random.default_rng(28)
     a = rand_r32(rng, 5000, 100, 1 << 12, 3, dtype=oracle.R32)
