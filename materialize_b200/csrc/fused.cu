@@ -1395,7 +1395,7 @@ int32_t fused_launch_many(mzgpu_ctx* ctx, int k, const FusedArgs* args, const u6
   void* kargs[] = {(void*)&m};
   {
     MZ_BYTES(ctx, bytes);
-    ProfScope prof(ctx, "k_fused_many");
+    ProfScope prof(ctx, "k_fused_consolidate");  // one profile line for the operator, whatever the launch shape
     cudaError_t e;
     if (fused_coop_mode()) {
       e = cudaLaunchCooperativeKernel((void*)k_fused_many<RB>, dim3(at), dim3(FT), kargs, 0, ctx->stream);

@@ -287,7 +287,8 @@ extern "C" int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap)
       u64 bytes = 0;
       for (u32 i = 0; i < ctx->dbg_next; ++i) bytes += rec[(size_t)i * 32 + 16] * rec[(size_t)i * 32 + 20] * 4;
       for (auto& x : aggs)
-        if (x.name == "k_fused_consolidate" && x.launches == ctx->dbg_next) x.bytes = bytes;
+        // (one record per job: a multi-job launch leaves several)
+        if (x.name == "k_fused_consolidate" && x.launches <= ctx->dbg_next) x.bytes = bytes;
     }
     ctx->dbg_next = 0;
   }
