@@ -164,6 +164,13 @@ def lib():
             "mzo_half_join": (None, [vp, u64, vp, i32, vp, i32, vp]),
             "mzo_update_stream": (None, [vp, vp, u64, vp]),
             "mzo_map_rows": (None, [vp, u64, vp, vp]),
+            "mzo_correction_new": (vp, [C.c_double, u64]),
+            "mzo_correction_free": (None, [vp]),
+            "mzo_correction_insert": (None, [vp, vp, u64, i32]),
+            "mzo_correction_updates_before": (None, [vp, u64, vp]),
+            "mzo_correction_advance_since": (None, [vp, u64]),
+            "mzo_correction_consolidate_at_since": (None, [vp]),
+            "mzo_correction_chains": (u64, [vp, vp, u64, vp]),
             "mzo_reduce_new": (vp, [i32]),
             "mzo_topk_new": (vp, [C.c_int64, u64, i32]),
             "mzo_reduce_free": (None, [vp]),
@@ -384,6 +391,40 @@ class Reduce:
         v = Vec(64)
         lib().mzo_reduce_step(self.h, _ptr(a), len(a), upper, v.h)
         return v.array()
+
+
+class Correction:
+    """MV sink correction buffer (oracle CorrectionV2; src/compute/src/sink/correction_v2.rs)."""
+
+    def __init__(self, chain_proportionality=3.0, chunk_capacity=64):
+        self.h = lib().mzo_correction_new(chain_proportionality, chunk_capacity)
+        self.chunk_capacity = chunk_capacity
+
+    def insert(self, rows, negate=False):
+        rows = np.ascontiguousarray(rows)
+        lib().mzo_correction_insert(self.h, _ptr(rows), len(rows), 1 if negate else 0)
+
+    def updates_before(self, upper):
+        v = Vec(32)
+        lib().mzo_correction_updates_before(self.h, upper, v.h)
+        return v.array()
+
+    def advance_since(self, since):
+        lib().mzo_correction_advance_since(self.h, since)
+
+    def consolidate_at_since(self):
+        lib().mzo_correction_consolidate_at_since(self.h)
+
+    def chains(self):
+        lens = (C.c_uint64 * 256)()
+        staged = C.c_uint64(0)
+        n = lib().mzo_correction_chains(self.h, lens, 256, C.byref(staged))
+        return [int(lens[i]) for i in range(min(n, 256))], int(staged.value)
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.mzo_correction_free(self.h)
+            self.h = None
 
 
 class TopK(Reduce):

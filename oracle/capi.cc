@@ -8,6 +8,7 @@
 #include <sstream>
 #include <string>
 
+#include "mzo_correction.hpp"
 #include "mzo_ops.hpp"
 #include "mzo_vec.hpp"
 
@@ -506,5 +507,29 @@ void mzo_finalize(const mzgpu_racc* acc, uint64_t n, int32_t agg_kind, mzgpu_rou
 }
 
 uint32_t mzo_route(uint64_t key, uint32_t peers) { return route(key, peers); }
+
+// ------------------------------------------------- MV sink correction buffer
+void* mzo_correction_new(double chain_proportionality, uint64_t chunk_capacity) {
+  return new CorrectionV2(chain_proportionality, (size_t)chunk_capacity);
+}
+void mzo_correction_free(void* c) { delete (CorrectionV2*)c; }
+void mzo_correction_insert(void* c, const mzgpu_r32* rows, uint64_t n, int32_t negate) {
+  ((CorrectionV2*)c)->insert(rows, (size_t)n, negate != 0);
+}
+void mzo_correction_updates_before(void* c, uint64_t upper, void* vec) {
+  std::vector<mzgpu_r32> out;
+  ((CorrectionV2*)c)->updates_before(upper, &out);
+  vec_append((Vec*)vec, out);
+}
+void mzo_correction_advance_since(void* c, uint64_t since) { ((CorrectionV2*)c)->advance_since(since); }
+void mzo_correction_consolidate_at_since(void* c) { ((CorrectionV2*)c)->consolidate_at_since(); }
+// chain lengths in updates (n_out entries written, at most cap); returns the number of chains;
+// *staged = updates in the stage
+uint64_t mzo_correction_chains(void* cv, uint64_t* lens, uint64_t cap, uint64_t* staged) {
+  CorrectionV2* c = (CorrectionV2*)cv;
+  for (size_t i = 0; i < c->chains.size() && i < cap; ++i) lens[i] = c->chains[i].size();
+  if (staged) *staged = c->stage.size();
+  return c->chains.size();
+}
 
 }  // extern "C"
