@@ -5,7 +5,22 @@
 set -u
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $O/r2_pytest.log
+# Smallest new pieces first, each under its own short timeout: a hung cooperative kernel must not
+# take the box (and a gpurun strike) with it.  Stop at the first failure.
+step() {
+  echo "== $1"
+  timeout "$2" python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$3" 2>&1 | tail -8 | tee -a $O/r2_pytest.log
+  if [ "${PIPESTATUS[0]}" -ne 0 ]; then echo "FAILED: $1"; exit 1; fi
+}
+: > $O/r2_pytest.log
+step "single-job fused kernel after the body refactor" 120 "consolidate or batcher_seal or batch_merge"
+step "multi-job seal" 90 "seal_many"
+step "deferred merges (spine)" 120 "spine"
+step "chained probes" 90 "half_join_many"
+step "fused first stage" 90 "delta_first_stage"
+step "reduce corrections without the sort launch" 120 "reduce"
+step "joins (bulk single-pass probe)" 180 "join"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee -a $O/r2_pytest.log
 line() {
   python -c "
 import sys, json
