@@ -325,6 +325,13 @@ int32_t mzgpu_batcher_push_buf(mzgpu_batcher* b, mzgpu_buf* rows);
  * batcher frontier afterwards (min kept time or MZGPU_FRONTIER_EMPTY). */
 int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_batch** batch_out,
                            uint64_t* new_lower);
+/* Seal k distinct batchers of one context at the same frontier: the k arrangements a timely
+ * worker seals when a timestamp closes (one `Batcher::seal` per arrange operator,
+ * src/compute/src/extensions/arrange.rs:86-119, all activated by the same frontier advance).
+ * Results are those of k mzgpu_batcher_seal calls in this order; the update-batch-sized seals
+ * share one cooperative launch, so k seals cost about one. */
+int32_t mzgpu_batcher_seal_many(uint32_t k, mzgpu_batcher* const* batchers, uint64_t upper,
+                                mzgpu_batch** batches_out);
 /* Batcher::frontier (operator.rs:618-631). */
 uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b);
 /* Updates currently buffered. */
@@ -408,6 +415,26 @@ int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int
 /* The same with the stream in a device buffer: nothing returns to the host. */
 int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
                             const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out);
+/* k half joins over device-resident streams in one launch: the half-join stages that the delta
+ * paths of one dataflow run side by side at a timestamp (`build_delta_join` renders one path per
+ * input relation, delta_join.rs:71-310; their stages are independent operators).  Request j
+ * probes streams[j] against traces[j] and appends to outs[j] exactly as
+ * mzgpu_half_join_buf(..., consolidate_output = 0, ...) would; requests naming the same output
+ * buffer must be adjacent and append in request order (the concatenation of the paths' outputs,
+ * delta_join.rs:302-308).  closures may be NULL (identity closures for every request). */
+int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* const* streams,
+                             mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                             const mzgpu_closure* const* closures, mzgpu_buf* const* outs);
+/* The first stage of k delta paths in one launch: request j forms the update stream of
+ * batches[j] (build_update_stream, delta_join.rs:312-377: updates at skip_times[j] dropped unless
+ * it is MZGPU_FRONTIER_EMPTY, initial_closures[j] applied) inside the probe kernel and half-joins
+ * it against traces[j] -- the results of mzgpu_update_stream followed by mzgpu_half_join_buf(...,
+ * consolidate_output = 0, ...) without materialising the stream.  Single-worker dataflows only:
+ * with peers > 1 the stream is exchanged by its new key between the two steps. */
+int32_t mzgpu_delta_first_stage_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_batch* const* batches,
+                                     const mzgpu_closure* const* initial_closures, const uint64_t* skip_times,
+                                     mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                                     const mzgpu_closure* const* closures, mzgpu_buf* const* outs);
 /* build_update_stream (delta_join.rs:600-707): a batch's updates as a stream,
  * `initial_closure` applied (val2 unused), updates at `skip_time` dropped when
  * skip_time != MZGPU_FRONTIER_EMPTY (the as_of rule for source_relation != 0). */

@@ -34,7 +34,10 @@ from .api import (  # noqa: F401
     Spine,
     TopK,
     half_join,
+    seal_many,
     half_join_dev,
+    half_join_many,
+    delta_first_stage_many,
     make_closure,
     map_rows,
     route,

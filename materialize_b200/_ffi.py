@@ -125,6 +125,8 @@ SIGNATURES = {
     "mzgpu_buf_append_buf": (i32, [vp, vp]),
     "mzgpu_batcher_push_buf": (i32, [vp, vp]),
     "mzgpu_half_join_buf": (i32, [vp, vp, vp, i32, C.POINTER(Closure), i32, vp]),
+    "mzgpu_half_join_many": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+    "mzgpu_delta_first_stage_many": (i32, [vp, u32, vp, vp, vp, vp, vp, vp, vp]),
     "mzgpu_reduce_accumulable_buf": (i32, [vp, vp, u64, vp]),
     "mzgpu_buf_download": (i32, [vp, vp, u64, i32, PU64]),
     "mzgpu_buf_clear": (i32, [vp]),
@@ -135,6 +137,7 @@ SIGNATURES = {
     "mzgpu_batcher_free": (None, [vp]),
     "mzgpu_batcher_push": (i32, [vp, vp, u64, i32]),
     "mzgpu_batcher_seal": (i32, [vp, u64, PV, PU64]),
+    "mzgpu_batcher_seal_many": (i32, [u32, vp, u64, vp]),
     "mzgpu_batcher_frontier": (u64, [vp]),
     "mzgpu_batcher_len": (u64, [vp]),
     "mzgpu_batch_build": (i32, [vp, u32, vp, u64, i32, Desc, PV]),

@@ -186,6 +186,18 @@ class DeviceRows:
             self.h = None
 
 
+def seal_many(batchers, upper):
+    """Seal several batchers at one frontier (mzgpu_batcher_seal_many): the same batches as
+    [b.seal_lazy(upper) for b in batchers]; update-batch-sized seals share one launch."""
+    k = len(batchers)
+    if k == 0:
+        return []
+    hs = (C.c_void_p * k)(*[b.h for b in batchers])
+    outs = (C.c_void_p * k)()
+    batchers[0].ctx.check(F.lib.mzgpu_batcher_seal_many(k, hs, upper, outs))
+    return [Batch(b.ctx, C.c_void_p(outs[i]), b.row_bytes) for i, b in enumerate(batchers)]
+
+
 class Batch:
     def __init__(self, ctx, h, row_bytes):
         self.ctx, self.h, self.row_bytes = ctx, h, row_bytes
@@ -380,6 +392,42 @@ def half_join_dev(ctx, dev_stream, trace, cmp_mode, closure=None, consolidate_ou
     out = out if out is not None else DeviceRows(ctx, 32)
     ctx.check(F.lib.mzgpu_half_join_buf(ctx.h, dev_stream.h, trace.h, cmp_mode, _clp(closure), 1 if consolidate_output else 0, out.h))
     return out
+
+
+def half_join_many(ctx, requests):
+    """Several half joins in one launch (mzgpu_half_join_many).  requests: (dev_stream, trace, cmp_mode,
+    closure or None, out DeviceRows); requests naming the same `out` must be adjacent and append in order."""
+    k = len(requests)
+    if k == 0:
+        return
+    streams = (C.c_void_p * k)(*[r[0].h for r in requests])
+    traces = (C.c_void_p * k)(*[r[1].h for r in requests])
+    cmps = (C.c_int32 * k)(*[r[2] for r in requests])
+    # a NULL entry means the identity closure (key, val2), as in mzgpu_half_join_buf
+    cls = (C.c_void_p * k)(*[C.cast(C.pointer(r[3]), C.c_void_p) if r[3] is not None else None for r in requests])
+    outs = (C.c_void_p * k)(*[r[4].h for r in requests])
+    ctx.check(F.lib.mzgpu_half_join_many(ctx.h, k, streams, traces, cmps, cls, outs))
+
+
+def delta_first_stage_many(ctx, requests):
+    """build_update_stream + first half join of several delta paths in one launch
+    (mzgpu_delta_first_stage_many).  requests: (batch, initial_closure or None, skip_time, trace, cmp_mode,
+    closure or None, out DeviceRows)."""
+    k = len(requests)
+    if k == 0:
+        return
+
+    def ptrs(cls):
+        return (C.c_void_p * k)(*[C.cast(C.pointer(c), C.c_void_p) if c is not None else None for c in cls])
+
+    batches = (C.c_void_p * k)(*[r[0].h for r in requests])
+    initial = ptrs([r[1] for r in requests])
+    skips = (C.c_uint64 * k)(*[r[2] for r in requests])
+    traces = (C.c_void_p * k)(*[r[3].h for r in requests])
+    cmps = (C.c_int32 * k)(*[r[4] for r in requests])
+    closures = ptrs([r[5] for r in requests])
+    outs = (C.c_void_p * k)(*[r[6].h for r in requests])
+    ctx.check(F.lib.mzgpu_delta_first_stage_many(ctx.h, k, batches, initial, skips, traces, cmps, closures, outs))
 
 
 def update_stream_dev(ctx, batch, closure=None, skip_time=F.FRONTIER_EMPTY, out=None):

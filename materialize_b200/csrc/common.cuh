@@ -58,6 +58,12 @@ struct mzgpu_ctx {
   // control blocks of the fused kernel, a pair per stream (each launch clears the other of its pair)
   void* d_fused_ctl[4] = {nullptr, nullptr, nullptr, nullptr};
   int fused_flip[2] = {0, 0};
+  void* d_fused_ctl_many[16] = {};  // per job slot: 0-3 multi-job launches, 4-7 deferred jobs
+  int fused_flip_many[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* fused_deferred = nullptr;       // fused.cu: jobs prepared but not launched yet
+  std::vector<struct mzgpu_batch*> deferred_inputs;  // retained until the flush
+  u64 defer_seq = 0, flushed_seq = 0;   // deferred jobs enqueued / launched
+  bool defer_merges = true;             // spine merges wait for each other (MZGPU_DEFER_MERGES=0: launch at once)
   // ---- side stream: batch merges (spine maintenance) run here, concurrently with the
   // operators on the main stream; a batch produced here carries side_seq and the main
   // stream waits for the side stream the first time it touches such a batch
@@ -339,6 +345,8 @@ struct LookBack {
   u32 epoch;    // tag of this launch
 };
 int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb);  // host.cu
+// the same over the state words [at, at + max_tiles): concurrent chains of one launch
+int32_t mz_lookback_begin_at(mzgpu_ctx* ctx, u64 at, u64 max_tiles, LookBack* lb);
 
 // ---------------------------------------------------------------- row traits
 // A row is NW 64-bit words: NK sort-key words first (compared as unsigned, in
@@ -654,6 +662,13 @@ struct FusedOut {
   Lazy4 kst;     // [0] rows kept, [1] min kept time (~0 if none), [2] max input time
 };
 int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
+// k independent jobs of one row width in one cooperative launch (k <= MZ_FUSED_MANY_MAX)
+#define MZ_FUSED_MANY_MAX 4
+int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs);
+// prepare now, launch with the other deferred jobs at mz_fused_flush (host.cu: mz_flush_deferred)
+int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
+int32_t mz_fused_flush(mzgpu_ctx* ctx);
+void mz_fused_deferred_free(mzgpu_ctx* ctx);
 size_t mz_fused_ctl_bytes();
 #define MZ_FUSED_MAX_ROWS (2u << 20)
 // ... judged by the exact row count when the host knows it.  When it only has an
@@ -713,6 +728,23 @@ struct ProbeParams {
   int swap_vals;    // join_core side 1: probe rows are val2, lookup rows are val1
   mzgpu_closure closure;
 };
+#define MZ_PROBE_MANY_MAX 3
+struct ProbeJobHost {
+  const u64* d_stream;
+  DLen n;
+  u64 n_ub;
+  const TraceView* trace;
+  const ProbeParams* pp;
+  int chain;  // jobs with equal chain ids are consecutive and append to one output
+  bool has_pre = false;                 // map in front of the probe: drop rows at skip_time, apply `pre`
+  const mzgpu_closure* pre = nullptr;   // (nullptr: identity)
+  u64 skip_time = MZGPU_FRONTIER_EMPTY;
+  u64* d_out;
+  DLen out_base;
+  u64 out_cap;
+  u64* d_out_len;
+};
+int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs);
 // Probe `n` R32 stream rows against the trace; appends results to d_out
 // (allocated here) and returns the count.  One sync (to size the output).
 int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& trace,

@@ -359,8 +359,12 @@ union FusedSmem {
   MsdScan scan;
 };
 
+// The whole operator for one job.  `c` = this CTA's index among the `gdim` CTAs the launch gave
+// the job (a single-job launch: blockIdx.x / gridDim.x; a multi-job launch: the job's slice of
+// the grid).  Every grid-wide step synchronises on the job's own control block, so independent
+// jobs of one launch never wait for each other.
 template <int RB>
-__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(const FusedArgs a) {
+__device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, const u32 gdim) {
   constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
   __shared__ int s_shift128[6], s_w128;
   __shared__ u32 s_max_bucket, s_max_unit;
   __shared__ u64 s_minv[6];
-  const u32 c = blockIdx.x, tid = threadIdx.x;
+  const u32 tid = threadIdx.x;
   const u64 na = dlen_get(a.na), nb = dlen_get(a.nb);
   const u64 n = na + nb;
   const u64 T = (n + FTILE - 1) / FTILE;
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
   u32 bb = 0;  // log2(buckets)
   while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n) ++bb;
   const u32 NB = 1u << bb;
-  u32 G = gridDim.x;
+  u32 G = gdim;
   {
     // the bucket phase of the MSD path wants one CTA per bucket; a merge only has its
     // 1024-row tiles (fewer CTAs = cheaper grid barriers)
@@ -1179,24 +1183,40 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(co
 }
 
 template <int RB>
-int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
+__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(const FusedArgs a) {
+  fused_body<RB>(a, blockIdx.x, gridDim.x);
+}
+
+// Several independent jobs of one row width in ONE cooperative launch (the arrangement seals of
+// one timestamp, the merges their inserts trigger): job j owns CTAs [start[j], start[j+1]).  An
+// update-batch job is a chain of latency-bound phases that leaves most of the machine idle, so
+// jobs side by side cost about as much as the longest of them alone.
+constexpr int FUSED_MANY_MAX = MZ_FUSED_MANY_MAX;
+struct FusedMany {
+  u32 k;
+  u32 start[FUSED_MANY_MAX + 1];
+  FusedArgs job[FUSED_MANY_MAX];
+};
+template <int RB>
+__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_many(const __grid_constant__ FusedMany m) {
+  u32 j = 0;
+  while (j + 1 < m.k && blockIdx.x >= m.start[j + 1]) ++j;
+  fused_body<RB>(m.job[j], blockIdx.x - m.start[j], m.start[j + 1] - m.start[j]);
+}
+
+// Everything of a launch but the launch: buffers, control block, kernel arguments.
+// `slot` < 0: the context's single-job control blocks; otherwise job slot `slot` of a
+// multi-job launch (each slot flips between its own pair of control blocks).
+template <int RB>
+int32_t fused_prepare(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res, int slot, FusedArgs* a_out,
+                      u64* want_out, DevMem* scratch) {
   constexpr int ND = RowT<RB>::ND;
-  static int max_ctas = 0;
-  if (max_ctas == 0) {
-    int per_sm = 0;
-    MZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_consolidate<RB>, FT, 0));
-    max_ctas = per_sm * ctx->num_sms;
-    if (max_ctas <= 0) {
-      MZ_SET_ERR(ctx, "fused kernel cannot be made resident");
-      return MZGPU_E_CUDA;
-    }
-  }
   const u64 cap = job.cap > 0 ? job.cap : 1;
   if (cap > MZ_FUSED_MAX_CAP) {
     MZ_SET_ERR(ctx, "fused consolidate: %llu rows exceed the fused limit", (unsigned long long)cap);
     return MZGPU_E_INVALID;
   }
-  FusedArgs a;
+  FusedArgs& a = *a_out;
   memset(&a, 0, sizeof(a));
   a.a = (const u64*)job.a;
   a.b = (const u64*)job.b;
@@ -1219,8 +1239,7 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   const u64 o_first = o_sums + al(cap * ND * 8), o_mlo = o_first + al(cap * 4);
   const u64 o_mhi = o_mlo + al(cap * 8), o_midx = o_mhi + al(cap * 8), o_lbs = o_midx + al(cap * 4);
   const u64 o_lbk = o_lbs + MSD_MAX_BUCKETS * 8, o_end = o_lbk + MSD_MAX_BUCKETS * 8;
-  DevMem scratch;
-  MZ_TRY(scratch.alloc(ctx, o_end));
+  MZ_TRY(scratch->alloc(ctx, o_end));
   MZ_TRY(res->rows.alloc(ctx, cap * RB));
   res->rows_cap = cap;
   const bool want_keep = job.upper != MZGPU_FRONTIER_EMPTY && RowT<RB>::TW >= 0;
@@ -1228,12 +1247,16 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   if (job.want_index) MZ_TRY(res->table.alloc(ctx, slots * sizeof(HashSlot)));
   MZ_TRY(res->st.make_pending(ctx));
   MZ_TRY(res->kst.make_pending(ctx));
-  char* sp = (char*)scratch.p;
-  {
+  char* sp = (char*)scratch->p;
+  if (slot < 0) {
     const int si = (ctx->side_stream != nullptr && ctx->stream == ctx->side_stream) ? 1 : 0;
     a.ctl = (FusedCtl*)ctx->d_fused_ctl[2 * si + ctx->fused_flip[si]];
     a.ctl_next = (FusedCtl*)ctx->d_fused_ctl[2 * si + (ctx->fused_flip[si] ^ 1)];
     ctx->fused_flip[si] ^= 1;
+  } else {
+    a.ctl = (FusedCtl*)ctx->d_fused_ctl_many[2 * slot + ctx->fused_flip_many[slot]];
+    a.ctl_next = (FusedCtl*)ctx->d_fused_ctl_many[2 * slot + (ctx->fused_flip_many[slot] ^ 1)];
+    ctx->fused_flip_many[slot] ^= 1;
   }
   a.k0 = (u64*)(sp + o_k0);
   a.k1 = (u64*)(sp + o_k1);
@@ -1251,11 +1274,6 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   a.m_idx = (u32*)(sp + o_midx);
   a.lb_ship = (u64*)(sp + o_lbs);
   a.lb_keep = (u64*)(sp + o_lbk);
-  // With the side stream in use a launch takes at most one CTA slot per SM, so that a merge on
-  // the side stream and a seal on the main stream can be co-resident (cooperative launches
-  // only start when the whole grid fits).
-  a.max_g = (ctx->use_side ? 1u : 2u) * (u32)ctx->num_sms;
-  if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
   a.merge = (job.merge && job.b != nullptr) ? 1u : 0u;
   a.out = res->rows.template as<u64>();
   a.keep = want_keep ? res->keep.template as<u64>() : nullptr;
@@ -1268,8 +1286,44 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
     a.dbg = ctx->d_dbg + 32 * (size_t)ctx->dbg_next++;
     MZ_CUDA(ctx, cudaMemsetAsync(a.dbg, 0, 32 * 8, ctx->stream));
   }
-  const unsigned a_max_g_host = (unsigned)std::min<u64>((u64)(ctx->use_side ? 1 : 2) * (u64)ctx->num_sms, (u64)max_ctas);
-  u64 want = (cap + 127) / 128 + 1;  // one CTA per MSD bucket (128..256 rows each), at least one per radix tile
+  *want_out = (cap + 127) / 128 + 1;  // one CTA per MSD bucket (128..256 rows each), at least one per radix tile
+  return MZGPU_OK;
+}
+
+static int fused_coop_mode() {
+  // A cooperative launch guarantees what the kernel's own grid barrier needs (all CTAs
+  // co-resident).  MZGPU_COOP=0 uses a plain launch instead (same grid, <= the resident
+  // capacity): only for measuring the launch-path difference.
+  static int coop = -1;
+  if (coop < 0) {
+    const char* ev = getenv("MZGPU_COOP");
+    coop = ev ? atoi(ev) : 1;
+  }
+  return coop;
+}
+
+template <int RB>
+int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int per_sm = 0;
+    MZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_consolidate<RB>, FT, 0));
+    max_ctas = per_sm * ctx->num_sms;
+    if (max_ctas <= 0) {
+      MZ_SET_ERR(ctx, "fused kernel cannot be made resident");
+      return MZGPU_E_CUDA;
+    }
+  }
+  FusedArgs a;
+  u64 want = 0;
+  DevMem scratch;
+  MZ_TRY(fused_prepare<RB>(ctx, job, res, -1, &a, &want, &scratch));
+  // With the side stream in use a launch takes at most one CTA slot per SM, so that a merge on
+  // the side stream and a seal on the main stream can be co-resident (cooperative launches
+  // only start when the whole grid fits).
+  a.max_g = (ctx->use_side ? 1u : 2u) * (u32)ctx->num_sms;
+  if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
+  const unsigned a_max_g_host = a.max_g;
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);
   if (grid > a_max_g_host) grid = a_max_g_host;
   if (grid == 0) grid = 1;
@@ -1280,16 +1334,8 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
     // mzgpu_profile_report substitutes the actual row count of profiled launches.
     MZ_BYTES(ctx, (job.na.p == nullptr && job.nb.p == nullptr) ? (job.na.imm + job.nb.imm) * RB * 4 : 0);
     ProfScope prof(ctx, "k_fused_consolidate");
-    // A cooperative launch guarantees what the kernel's own grid barrier needs (all CTAs
-    // co-resident).  MZGPU_COOP=0 uses a plain launch instead (same grid, <= the resident
-    // capacity): only for measuring the launch-path difference.
-    static int coop = -1;
-    if (coop < 0) {
-      const char* ev = getenv("MZGPU_COOP");
-      coop = ev ? atoi(ev) : 1;
-    }
     cudaError_t e;
-    if (coop) {
+    if (fused_coop_mode()) {
       e = cudaLaunchCooperativeKernel((void*)k_fused_consolidate<RB>, dim3(grid), dim3(FT), kargs, 0, ctx->stream);
     } else {
       k_fused_consolidate<RB><<<grid, FT, 0, ctx->stream>>>(a);
@@ -1307,9 +1353,186 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   return MZGPU_OK;
 }
 
+// k prepared jobs (same row width) in one cooperative launch.  The resident capacity is
+// shared out in proportion to what each job alone would take.
+template <int RB>
+int32_t fused_launch_many(mzgpu_ctx* ctx, int k, const FusedArgs* args, const u64* want_in, u64 bytes) {
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    int per_sm = 0;
+    MZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_many<RB>, FT, 0));
+    max_ctas = per_sm * ctx->num_sms;
+    if (max_ctas <= 0) {
+      MZ_SET_ERR(ctx, "fused kernel cannot be made resident");
+      return MZGPU_E_CUDA;
+    }
+  }
+  static thread_local FusedMany m;  // ~1.5 KB, passed by value
+  memset(&m, 0, sizeof(m));
+  m.k = (u32)k;
+  u64 want[FUSED_MANY_MAX];
+  u64 want_sum = 0;
+  const u64 solo_max = std::min<u64>(2ull * (u64)ctx->num_sms, (u64)max_ctas);
+  for (int j = 0; j < k; ++j) {
+    m.job[j] = args[j];
+    want[j] = want_in[j] > solo_max ? solo_max : want_in[j];
+    if (want[j] == 0) want[j] = 1;
+    want_sum += want[j];
+  }
+  u32 at = 0;
+  for (int j = 0; j < k; ++j) {
+    u64 g = want_sum <= (u64)max_ctas ? want[j] : want[j] * (u64)max_ctas / want_sum;
+    if (g == 0) g = 1;
+    m.start[j] = at;
+    m.job[j].max_g = (u32)g;
+    at += (u32)g;
+  }
+  m.start[k] = at;
+  if ((int)at > max_ctas) {  // k jobs of one CTA each always fit: k <= FUSED_MANY_MAX << max_ctas
+    MZ_SET_ERR(ctx, "fused multi-job launch: %u CTAs exceed the resident capacity %d", at, max_ctas);
+    return MZGPU_E_INVALID;
+  }
+  void* kargs[] = {(void*)&m};
+  {
+    MZ_BYTES(ctx, bytes);
+    ProfScope prof(ctx, "k_fused_consolidate");  // one profile line for the operator, whatever the launch shape
+    cudaError_t e;
+    if (fused_coop_mode()) {
+      e = cudaLaunchCooperativeKernel((void*)k_fused_many<RB>, dim3(at), dim3(FT), kargs, 0, ctx->stream);
+    } else {
+      k_fused_many<RB><<<at, FT, 0, ctx->stream>>>(m);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+      MZ_SET_ERR(ctx, "cooperative launch failed: %s", cudaGetErrorString(e));
+      ctx->sticky = true;
+      return MZGPU_E_CUDA;
+    }
+  }
+  ctx->stats.kernel_launches++;
+  return MZGPU_OK;
+}
+
+static u64 fused_job_bytes(const FusedJob& job) {
+  return (job.na.p == nullptr && job.nb.p == nullptr) ? (job.na.imm + job.nb.imm) * (u64)job.rb * 4 : 0;
+}
+
+template <int RB>
+int32_t fused_many_t(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs) {
+  FusedArgs args[FUSED_MANY_MAX];
+  DevMem scratch[FUSED_MANY_MAX];
+  u64 want[FUSED_MANY_MAX];
+  u64 bytes = 0;
+  for (int j = 0; j < k; ++j) {
+    MZ_TRY(fused_prepare<RB>(ctx, jobs[j], &outs[j], j, &args[j], &want[j], &scratch[j]));
+    bytes += fused_job_bytes(jobs[j]);
+  }
+  MZ_TRY(fused_launch_many<RB>(ctx, k, args, want, bytes));
+  for (int j = 0; j < k; ++j) {
+    outs[j].st.mark_written();
+    outs[j].kst.mark_written();
+  }
+  return MZGPU_OK;
+}
+
+// Jobs prepared now and launched together later (mz_fused_defer / mz_fused_flush): the merges that
+// the spine inserts of one timestamp trigger.  Their control blocks are the job slots
+// FUSED_MANY_MAX .. 2 * FUSED_MANY_MAX - 1, used in prepare order = launch order.
+struct FusedDeferred {
+  int rb = 0;
+  int k = 0;
+  FusedArgs args[FUSED_MANY_MAX];
+  u64 want[FUSED_MANY_MAX];
+  DevMem scratch[FUSED_MANY_MAX];
+  u64 bytes = 0;
+};
+
+template <int RB>
+int32_t fused_defer_t(mzgpu_ctx* ctx, FusedDeferred* d, const FusedJob& job, FusedOut* out) {
+  const int j = d->k;
+  MZ_TRY(fused_prepare<RB>(ctx, job, out, FUSED_MANY_MAX + j, &d->args[j], &d->want[j], &d->scratch[j]));
+  d->bytes += fused_job_bytes(job);
+  d->rb = RB;
+  d->k = j + 1;
+  return MZGPU_OK;
+}
+
 }  // namespace
 
 size_t mz_fused_ctl_bytes() { return sizeof(FusedCtl); }
+
+int32_t mz_fused_flush(mzgpu_ctx* ctx) {
+  FusedDeferred* d = (FusedDeferred*)ctx->fused_deferred;
+  if (d == nullptr || d->k == 0) return MZGPU_OK;
+  const int k = d->k;
+  d->k = 0;  // whatever happens below, the jobs are not retried
+  int32_t st;
+  switch (d->rb) {
+    case 16: st = fused_launch_many<16>(ctx, k, d->args, d->want, d->bytes); break;
+    case 32: st = fused_launch_many<32>(ctx, k, d->args, d->want, d->bytes); break;
+    case 40: st = fused_launch_many<40>(ctx, k, d->args, d->want, d->bytes); break;
+    case 80: st = fused_launch_many<80>(ctx, k, d->args, d->want, d->bytes); break;
+    case 64: st = fused_launch_many<64>(ctx, k, d->args, d->want, d->bytes); break;
+    default: st = MZGPU_E_UNSUPPORTED; break;
+  }
+  for (int j = 0; j < k; ++j) d->scratch[j].release();  // stream ordered: after the launch
+  d->bytes = 0;
+  if (st != MZGPU_OK) ctx->sticky = true;  // outputs were promised to readers
+  return st;
+}
+
+void mz_fused_deferred_free(mzgpu_ctx* ctx) {
+  delete (FusedDeferred*)ctx->fused_deferred;
+  ctx->fused_deferred = nullptr;
+}
+
+// Prepare `job` (buffers, counters, control block) and leave the launch to mz_fused_flush.  The
+// result counters count as written from now on: mz_resolve_counters flushes before it copies the
+// arena, so a counter can never be read back ahead of its launch.
+int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out) {
+  if (ctx->fused_deferred == nullptr) ctx->fused_deferred = new FusedDeferred();
+  FusedDeferred* d = (FusedDeferred*)ctx->fused_deferred;
+  if (d->k > 0 && (d->rb != job.rb || d->k == FUSED_MANY_MAX)) MZ_TRY(mz_fused_flush(ctx));
+  int32_t st;
+  switch (job.rb) {
+    case 16: st = fused_defer_t<16>(ctx, d, job, out); break;
+    case 32: st = fused_defer_t<32>(ctx, d, job, out); break;
+    case 40: st = fused_defer_t<40>(ctx, d, job, out); break;
+    case 80: st = fused_defer_t<80>(ctx, d, job, out); break;
+    case 64: st = fused_defer_t<64>(ctx, d, job, out); break;
+    default:
+      MZ_SET_ERR(ctx, "fused: unsupported row width %d", job.rb);
+      return MZGPU_E_UNSUPPORTED;
+  }
+  if (st != MZGPU_OK) return st;
+  out->st.mark_written();
+  out->kst.mark_written();
+  return MZGPU_OK;
+}
+
+int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs) {
+  if (k <= 0) return MZGPU_OK;
+  if (k == 1) return mz_fused_consolidate(ctx, jobs[0], &outs[0]);
+  if (k > FUSED_MANY_MAX) {
+    MZ_SET_ERR(ctx, "fused multi-job launch: %d jobs exceed the maximum %d", k, FUSED_MANY_MAX);
+    return MZGPU_E_INVALID;
+  }
+  for (int j = 1; j < k; ++j)
+    if (jobs[j].rb != jobs[0].rb) {
+      MZ_SET_ERR(ctx, "fused multi-job launch: mixed row widths %d / %d", jobs[0].rb, jobs[j].rb);
+      return MZGPU_E_INVALID;
+    }
+  switch (jobs[0].rb) {
+    case 16: return fused_many_t<16>(ctx, k, jobs, outs);
+    case 32: return fused_many_t<32>(ctx, k, jobs, outs);
+    case 40: return fused_many_t<40>(ctx, k, jobs, outs);
+    case 80: return fused_many_t<80>(ctx, k, jobs, outs);
+    case 64: return fused_many_t<64>(ctx, k, jobs, outs);
+    default:
+      MZ_SET_ERR(ctx, "fused: unsupported row width %d", jobs[0].rb);
+      return MZGPU_E_UNSUPPORTED;
+  }
+}
 
 int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   switch (job.rb) {

@@ -203,10 +203,9 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   const uint64_t upper = t + 1;
   mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
   int32_t st = MZGPU_OK;
-  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) {
-    st = mzgpu_batcher_seal(q->batcher[a], upper, &batch[a], nullptr);
-    if (st == MZGPU_OK) st = mzgpu_spine_insert(q->spine[a], batch[a]);
-  }
+  // the four arrange operators are activated by the same frontier advance: one batched seal
+  st = mzgpu_batcher_seal_many(4, q->batcher, upper, batch);
+  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) st = mzgpu_spine_insert(q->spine[a], batch[a]);
   // The previous timestamp's maintenance runs here: the seals above are already queued on
   // the device, so the merges it schedules (side stream) and the few lengths it has to read
   // back overlap with them instead of delaying them.
@@ -219,6 +218,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
     active[path] = !(q->static_rel[q->plan.source[path]] && q->stepping);
     if (q->streams_prepared) continue;  // mapped and exchanged together with the inputs (mzh_q3_step)
+    if (q->peers == 1) continue;        // one worker: the update stream is formed inside the first half join
     st = mzgpu_buf_clear(q->pstream[path]);
     // as_of rule: only the first relation's path sees the updates at as_of (= 0)
     if (st == MZGPU_OK && active[path])
@@ -239,21 +239,45 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       for (int path = 0; path < 3; ++path)
         if (active[path]) std::swap(q->pstream[path], q->pxchg[path]);
     }
+    // the active paths' stage-s half joins are independent operators: one launch.  Last stage:
+    // the paths' outputs are concatenated (delta_join.rs:302-308), so every path appends
+    // straight to the result collection (one chain, path order)
+    mzgpu_buf *hs[3], *ho[3];
+    mzgpu_spine* ht[3];
+    int32_t hc[3];
+    const mzgpu_closure* hcl[3];
+    uint32_t hk = 0;
     for (int path = 0; path < 3 && st == MZGPU_OK; ++path) {
       if (!active[path]) continue;
-      if (s == 1) {
-        // last stage: the paths' outputs are concatenated (delta_join.rs:302-308), so
-        // each path appends straight to the result collection
-        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                                 &q->plan.stage[path][s], 0, q->results);
-        continue;
-      }
-      st = mzgpu_buf_clear(q->pnext[path]);
-      if (st == MZGPU_OK)
-        st = mzgpu_half_join_buf(q->ctx, q->pstream[path], q->spine[q->plan.lookup[path][s]], q->plan.cmp[path][s],
-                                 &q->plan.stage[path][s], 0, q->pnext[path]);
-      std::swap(q->pstream[path], q->pnext[path]);
+      if (s == 0) st = mzgpu_buf_clear(q->pnext[path]);
+      hs[hk] = q->pstream[path];
+      ht[hk] = q->spine[q->plan.lookup[path][s]];
+      hc[hk] = q->plan.cmp[path][s];
+      hcl[hk] = &q->plan.stage[path][s];
+      ho[hk] = s == 1 ? q->results : q->pnext[path];
+      ++hk;
     }
+    if (st == MZGPU_OK && s == 0 && q->peers == 1 && !q->streams_prepared) {
+      // build_update_stream + the first half join of every active path in one launch
+      mzgpu_batch* hb[3];
+      const mzgpu_closure* hi[3];
+      uint64_t hskip[3];
+      uint32_t j = 0;
+      for (int path = 0; path < 3; ++path) {
+        if (!active[path]) continue;
+        hb[j] = batch[q->plan.source[path]];
+        hi[j] = &q->plan.initial[path];
+        // as_of rule: only the first relation's path sees the updates at as_of (= 0)
+        hskip[j] = path == 0 ? MZGPU_FRONTIER_EMPTY : 0;
+        ++j;
+      }
+      st = mzgpu_delta_first_stage_many(q->ctx, hk, hb, hi, hskip, ht, hc, hcl, ho);
+    } else if (st == MZGPU_OK) {
+      st = mzgpu_half_join_many(q->ctx, hk, hs, ht, hc, hcl, ho);
+    }
+    if (s == 0)
+      for (int path = 0; path < 3; ++path)
+        if (active[path]) std::swap(q->pstream[path], q->pnext[path]);
   }
   if (st == MZGPU_OK && q->peers > 1) {
     st = mzgpu_exchange(q->ctx, q->results, q->xchg);

@@ -46,6 +46,11 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
   }
+  if (const char* e = getenv("MZGPU_DEFER_MERGES")) ctx->defer_merges = atoi(e) != 0;
+  for (int i = 0; i < 16; ++i) {
+    MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl_many[i], mz_fused_ctl_bytes()));
+    MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl_many[i], 0, mz_fused_ctl_bytes()));
+  }
   ctx->main_stream = ctx->stream;
   MZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -93,6 +98,9 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int i = 0; i < 4; ++i)
     if (ctx->d_fused_ctl[i]) cudaFree(ctx->d_fused_ctl[i]);
+  for (int i = 0; i < 16; ++i)
+    if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
+  mz_fused_deferred_free(ctx);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
@@ -148,8 +156,11 @@ static int32_t mz_join_side(mzgpu_ctx* ctx) {
   }
   return MZGPU_OK;
 }
+static int32_t mz_flush_deferred(mzgpu_ctx* ctx);
 int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   MZ_CHECK_CTX(ctx);
+  // counters of deferred jobs count as written: their launch must precede the copy
+  MZ_TRY(mz_flush_deferred(ctx));
   // counts may have been written on either stream
   if (ctx->stream == ctx->main_stream) {
     MZ_TRY(mz_join_side(ctx));
@@ -180,8 +191,12 @@ int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   return MZGPU_OK;
 }
 int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb) {
-  if (max_tiles > MZ_LB_TILES) {
-    MZ_SET_ERR(ctx, "single-pass kernel: %llu tiles exceed the look-back state", (unsigned long long)max_tiles);
+  return mz_lookback_begin_at(ctx, 0, max_tiles, lb);
+}
+int32_t mz_lookback_begin_at(mzgpu_ctx* ctx, u64 at, u64 max_tiles, LookBack* lb) {
+  if (at + max_tiles > MZ_LB_TILES) {
+    MZ_SET_ERR(ctx, "single-pass kernel: %llu tiles exceed the look-back state",
+               (unsigned long long)(at + max_tiles));
     return MZGPU_E_UNSUPPORTED;
   }
   ctx->lb_epoch = (ctx->lb_epoch + 1) & 0xfffffu;
@@ -193,7 +208,7 @@ int32_t mz_lookback_begin(mzgpu_ctx* ctx, u64 max_tiles, LookBack* lb) {
     MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4, ctx->stream));
     ctx->ticket_next = 0;
   }
-  lb->state = ctx->d_lb;
+  lb->state = ctx->d_lb + at;
   lb->ticket = ctx->d_tickets + ctx->ticket_next++;
   lb->epoch = ctx->lb_epoch;
   return MZGPU_OK;
@@ -272,7 +287,8 @@ extern "C" int32_t mzgpu_profile_report(mzgpu_ctx* ctx, char* buf, uint64_t cap)
       u64 bytes = 0;
       for (u32 i = 0; i < ctx->dbg_next; ++i) bytes += rec[(size_t)i * 32 + 16] * rec[(size_t)i * 32 + 20] * 4;
       for (auto& x : aggs)
-        if (x.name == "k_fused_consolidate" && x.launches == ctx->dbg_next) x.bytes = bytes;
+        // (one record per job: a multi-job launch leaves several)
+        if (x.name == "k_fused_consolidate" && x.launches <= ctx->dbg_next) x.bytes = bytes;
     }
     ctx->dbg_next = 0;
   }
@@ -589,9 +605,22 @@ struct mzgpu_batch {
   mzgpu_desc desc;
   int refs = 1;
   u64 side_seq = 0;  // != 0: produced by merge #side_seq on the side stream
+  u64 deferred_seq = 0;  // != 0: produced by deferred job #deferred_seq (launched at the next flush)
 };
+static void batch_release_internal(mzgpu_batch* b);
+// Launch the deferred merges (one multi-job launch) and let go of their inputs.
+static int32_t mz_flush_deferred(mzgpu_ctx* ctx) {
+  if (ctx->flushed_seq == ctx->defer_seq) return MZGPU_OK;
+  ctx->flushed_seq = ctx->defer_seq;
+  const int32_t st = mz_fused_flush(ctx);
+  std::vector<mzgpu_batch*> ins;
+  ins.swap(ctx->deferred_inputs);
+  for (auto* b : ins) batch_release_internal(b);  // freed in stream order, behind the launch
+  return st;
+}
 // before the main stream reads or frees a batch: wait for the merge that produced it
 static int32_t batch_ready(mzgpu_batch* b) {
+  if (b->deferred_seq > b->ctx->flushed_seq) MZ_TRY(mz_flush_deferred(b->ctx));
   if (b->side_seq > b->ctx->joined_seq) return mz_join_side(b->ctx);
   return MZGPU_OK;
 }
@@ -724,12 +753,13 @@ extern "C" mzgpu_desc mzgpu_batch_desc(const mzgpu_batch* b) {
 extern "C" void mzgpu_batch_retain(mzgpu_batch* b) {
   if (b) b->refs++;
 }
-extern "C" void mzgpu_batch_release(mzgpu_batch* b) {
+static void batch_release_internal(mzgpu_batch* b) {
   if (b && --b->refs == 0) {
     batch_ready(b);  // its memory is freed in stream order on the current stream
     delete b;
   }
 }
+extern "C" void mzgpu_batch_release(mzgpu_batch* b) { batch_release_internal(b); }
 extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, int32_t mem,
                                       uint64_t* n_out) {
   if (b == nullptr) return MZGPU_E_INVALID;
@@ -745,6 +775,10 @@ extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, 
 // Batch::Merger in one step: union, advance_by(since), consolidate, index.
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
+  // an input that is itself the output of a deferred merge must be launched first (jobs of one
+  // multi-job launch run side by side)
+  MZ_TRY(batch_ready(b1));
+  MZ_TRY(batch_ready(b2));
   mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
   if (!mz_use_fused(false, b1->len_ub + b2->len_ub)) {
     MZ_TRY(batch_resolve(b1));
@@ -762,6 +796,20 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
     job.want_index = true;
     job.merge = true;
     FusedOut fo;
+    if (ctx->defer_merges && ctx->stream == ctx->main_stream) {
+      // The merges that the inserts of one timestamp trigger (one per arrangement, all alike)
+      // are independent: they are prepared here and launched together, by the first reader of
+      // any of their outputs (batch_ready) or the next counter read-back.
+      MZ_TRY(mz_fused_defer(ctx, job, &fo));
+      b1->refs++;
+      b2->refs++;
+      ctx->deferred_inputs.push_back(b1);
+      ctx->deferred_inputs.push_back(b2);
+      const u64 seq = ++ctx->defer_seq;
+      MZ_TRY(batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out));
+      (*out)->deferred_seq = seq;
+      return MZGPU_OK;
+    }
     MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
     return batch_from_fused(ctx, b1->rb, std::move(fo), job.cap, d, out);
   }
@@ -886,7 +934,22 @@ static int32_t batcher_push_dev(mzgpu_batcher* b, const void* d_rows, DLen n, u6
   }
   return batcher_push_seg(b, std::move(s));
 }
-static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
+// A seal in three steps, so that the fused launches of several batchers sealed at the same
+// frontier can share one cooperative launch (seal_many): plan (what to run) -> run -> finish.
+struct SealPlan {
+  mzgpu_batcher* b = nullptr;
+  u64 upper = 0;
+  mzgpu_desc d = {0, 0, 0};
+  u64 total = 0;
+  bool exact = true;
+  bool fused = false;  // one fused job (`job`) does the whole seal
+  DevMem all;          // concatenated stash (kept alive until the launch is enqueued)
+  Lazy4 alen;
+  FusedJob job;
+  FusedOut fo;
+};
+
+static int32_t seal_plan(mzgpu_batcher* b, u64 upper, SealPlan* p) {
   mzgpu_ctx* ctx = b->ctx;
   if (upper != MZGPU_FRONTIER_EMPTY && upper < b->lower) {
     MZ_SET_ERR(ctx, "batcher_seal: upper %llu precedes lower %llu", (unsigned long long)upper,
@@ -903,7 +966,9 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     }
     b->segs = std::move(live);
   }
-  mzgpu_desc d = {b->lower, upper, 0};
+  p->b = b;
+  p->upper = upper;
+  p->d = mzgpu_desc{b->lower, upper, 0};
   bool exact = true;
   for (auto& s : b->segs) exact = exact && s.len.known;
   if (!exact && !mz_use_fused(false, batcher_ub(b))) {
@@ -913,98 +978,159 @@ static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out
     }
     exact = true;
   }
-  const u64 total = batcher_ub(b);
-  if (total == 0) {
-    b->segs.clear();
-    b->frontier = MZGPU_FRONTIER_EMPTY;
-    b->frontier_known = true;
-    MZ_TRY(make_empty_batch(ctx, b->rb, d, batch_out));
-  } else if (mz_use_fused(exact, total)) {
-    DevMem all;
-    Lazy4 alen;
+  p->exact = exact;
+  p->total = batcher_ub(b);
+  p->fused = p->total > 0 && mz_use_fused(exact, p->total);
+  if (p->fused) {
     int aword = 0;
     u64 aub = 0;
-    FusedJob job;
-    job.rb = b->rb;
+    p->job.rb = b->rb;
     if (b->segs.size() == 1) {
-      job.a = b->segs[0].rows.p;
-      job.na = dlen_of(b->segs[0].len, b->segs[0].word);
+      p->job.a = b->segs[0].rows.p;
+      p->job.na = dlen_of(b->segs[0].len, b->segs[0].word);
     } else {
-      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
-      job.a = all.p;
-      job.na = dlen_of(alen, aword);
+      MZ_TRY(batcher_concat(b, &p->all, &p->alen, &aword, &aub));
+      p->job.a = p->all.p;
+      p->job.na = dlen_of(p->alen, aword);
     }
-    job.cap = total;
-    job.upper = upper;
-    job.want_index = true;
-    FusedOut fo;
-    MZ_TRY(mz_fused_consolidate(ctx, job, &fo));
-    b->segs.clear();  // stream ordered: the kernel above still reads them
-    if (upper != MZGPU_FRONTIER_EMPTY) {
-      Seg k;
-      k.rows = std::move(fo.keep);
-      k.len = std::move(fo.kst);
-      k.word = 0;
-      k.ub = total;
-      k.is_keep = true;
-      b->segs.push_back(std::move(k));
-      b->frontier_known = false;
-    } else {
-      b->frontier = MZGPU_FRONTIER_EMPTY;
-      b->frontier_known = true;
-    }
-    MZ_TRY(batch_from_fused(ctx, b->rb, std::move(fo), total, d, batch_out));
+    p->job.cap = p->total;
+    p->job.upper = upper;
+    p->job.want_index = true;
+  }
+  return MZGPU_OK;
+}
+
+// after the fused launch of the plan has been enqueued
+static int32_t seal_finish_fused(SealPlan* p, mzgpu_batch** batch_out) {
+  mzgpu_batcher* b = p->b;
+  mzgpu_ctx* ctx = b->ctx;
+  b->segs.clear();  // stream ordered: the kernel still reads them
+  if (p->upper != MZGPU_FRONTIER_EMPTY) {
+    Seg k;
+    k.rows = std::move(p->fo.keep);
+    k.len = std::move(p->fo.kst);
+    k.word = 0;
+    k.ub = p->total;
+    k.is_keep = true;
+    b->segs.push_back(std::move(k));
+    b->frontier_known = false;
   } else {
-    // bulk path: exact sizes, multi-kernel sort / extract
-    DevMem all, cons;
-    Lazy4 alen, clen;
-    int aword = 0;
-    u64 aub = 0, cap = 0;
-    const void* src = nullptr;
-    DLen sn;
-    if (b->segs.size() == 1) {
-      src = b->segs[0].rows.p;
-      sn = dlen_of(b->segs[0].len, b->segs[0].word);
-      aub = b->segs[0].ub;
-    } else {
-      MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
-      src = all.p;
-      sn = dlen_of(alen, aword);
-    }
-    ctx->last_minmax_valid = false;
-    MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
-    MZ_TRY(clen.resolve());
-    b->segs.clear();
-    all.release();
-    const u64 n_cons = clen.v[0];
     b->frontier = MZGPU_FRONTIER_EMPTY;
     b->frontier_known = true;
-    // the bulk sort has seen the range of the time word: if every buffered time precedes
-    // `upper` everything ships and the extract pass (two more copies of the rows) is skipped
-    const int tw = b->rb == 32 ? 2 : 1;
-    const bool all_ship = ctx->last_minmax_valid && ctx->last_minmax[2 * tw + 1] < upper;
-    if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0 || all_ship) {
-      MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
-    } else {
-      DevMem ship, keep;
-      u64 n_ship = 0, n_keep = 0, min_keep = MZGPU_FRONTIER_EMPTY;
-      MZ_TRY(mz_extract(ctx, b->rb, cons.p, n_cons, upper, &ship, &n_ship, &keep, &n_keep, &min_keep));
-      cons.release();
-      if (n_keep) {
-        Seg k;
-        k.rows = std::move(keep);
-        k.len.set(ctx, n_keep);
-        k.ub = n_keep;
-        b->segs.push_back(std::move(k));
-        b->frontier = min_keep;
-      }
-      MZ_TRY(make_batch(ctx, b->rb, std::move(ship), n_ship, d, batch_out));
+  }
+  return batch_from_fused(ctx, b->rb, std::move(p->fo), p->total, p->d, batch_out);
+}
+
+// the seals a fused job cannot take: nothing buffered, or the bulk multi-kernel path
+static int32_t seal_run_unfused(SealPlan* p, mzgpu_batch** batch_out) {
+  mzgpu_batcher* b = p->b;
+  mzgpu_ctx* ctx = b->ctx;
+  const u64 upper = p->upper;
+  const mzgpu_desc d = p->d;
+  if (p->total == 0) {
+    b->segs.clear();
+    b->frontier = MZGPU_FRONTIER_EMPTY;
+    b->frontier_known = true;
+    return make_empty_batch(ctx, b->rb, d, batch_out);
+  }
+  // bulk path: exact sizes, multi-kernel sort / extract
+  DevMem all, cons;
+  Lazy4 alen, clen;
+  int aword = 0;
+  u64 aub = 0, cap = 0;
+  const void* src = nullptr;
+  DLen sn;
+  if (b->segs.size() == 1) {
+    src = b->segs[0].rows.p;
+    sn = dlen_of(b->segs[0].len, b->segs[0].word);
+    aub = b->segs[0].ub;
+  } else {
+    MZ_TRY(batcher_concat(b, &all, &alen, &aword, &aub));
+    src = all.p;
+    sn = dlen_of(alen, aword);
+  }
+  ctx->last_minmax_valid = false;
+  MZ_TRY(consolidate_dev(ctx, b->rb, src, sn, aub, &cons, &cap, &clen));
+  MZ_TRY(clen.resolve());
+  b->segs.clear();
+  all.release();
+  const u64 n_cons = clen.v[0];
+  b->frontier = MZGPU_FRONTIER_EMPTY;
+  b->frontier_known = true;
+  // the bulk sort has seen the range of the time word: if every buffered time precedes
+  // `upper` everything ships and the extract pass (two more copies of the rows) is skipped
+  const int tw = b->rb == 32 ? 2 : 1;
+  const bool all_ship = ctx->last_minmax_valid && ctx->last_minmax[2 * tw + 1] < upper;
+  if (upper == MZGPU_FRONTIER_EMPTY || n_cons == 0 || all_ship) {
+    MZ_TRY(make_batch(ctx, b->rb, std::move(cons), n_cons, d, batch_out));
+  } else {
+    DevMem ship, keep;
+    u64 n_ship = 0, n_keep = 0, min_keep = MZGPU_FRONTIER_EMPTY;
+    MZ_TRY(mz_extract(ctx, b->rb, cons.p, n_cons, upper, &ship, &n_ship, &keep, &n_keep, &min_keep));
+    cons.release();
+    if (n_keep) {
+      Seg k;
+      k.rows = std::move(keep);
+      k.len.set(ctx, n_keep);
+      k.ub = n_keep;
+      b->segs.push_back(std::move(k));
+      b->frontier = min_keep;
     }
+    MZ_TRY(make_batch(ctx, b->rb, std::move(ship), n_ship, d, batch_out));
+  }
+  return MZGPU_OK;
+}
+
+static int32_t batcher_seal(mzgpu_batcher* b, u64 upper, mzgpu_batch** batch_out, u64* new_lower) {
+  SealPlan p;
+  MZ_TRY(seal_plan(b, upper, &p));
+  if (p.fused) {
+    MZ_TRY(mz_fused_consolidate(b->ctx, p.job, &p.fo));
+    MZ_TRY(seal_finish_fused(&p, batch_out));
+  } else {
+    MZ_TRY(seal_run_unfused(&p, batch_out));
   }
   b->lower = upper;
   if (new_lower) {
     MZ_TRY(batcher_resolve_frontier(b));
     *new_lower = b->frontier;
+  }
+  return MZGPU_OK;
+}
+
+// Seal k batchers at the same frontier; the fused jobs of one row width share ONE cooperative
+// launch (groups of MZ_FUSED_MANY_MAX).  Same results as k batcher_seal calls in this order.
+static int32_t batcher_seal_many(int k, mzgpu_batcher* const* bs, u64 upper, mzgpu_batch** batches_out) {
+  if (k <= 0) return MZGPU_OK;
+  std::vector<SealPlan> plans((size_t)k);
+  for (int i = 0; i < k; ++i) {
+    batches_out[i] = nullptr;
+    MZ_TRY(seal_plan(bs[i], upper, &plans[(size_t)i]));
+  }
+  std::vector<char> done((size_t)k, 0);
+  for (int i = 0; i < k; ++i) {
+    if (done[(size_t)i] || !plans[(size_t)i].fused) continue;
+    // this plan and the later fused plans of the same row width
+    int idx[MZ_FUSED_MANY_MAX];
+    int g = 0;
+    for (int j = i; j < k && g < MZ_FUSED_MANY_MAX; ++j)
+      if (!done[(size_t)j] && plans[(size_t)j].fused && plans[(size_t)j].job.rb == plans[(size_t)i].job.rb) idx[g++] = j;
+    FusedJob jobs[MZ_FUSED_MANY_MAX];
+    FusedOut outs[MZ_FUSED_MANY_MAX];
+    for (int t = 0; t < g; ++t) jobs[t] = plans[(size_t)idx[t]].job;
+    MZ_TRY(mz_fused_consolidate_many(bs[i]->ctx, g, jobs, outs));
+    for (int t = 0; t < g; ++t) {
+      plans[(size_t)idx[t]].fo = std::move(outs[t]);
+      done[(size_t)idx[t]] = 1;
+    }
+  }
+  for (int i = 0; i < k; ++i) {
+    SealPlan& p = plans[(size_t)i];
+    if (p.fused)
+      MZ_TRY(seal_finish_fused(&p, &batches_out[i]));
+    else
+      MZ_TRY(seal_run_unfused(&p, &batches_out[i]));
+    bs[i]->lower = upper;
   }
   return MZGPU_OK;
 }
@@ -1045,6 +1171,18 @@ extern "C" int32_t mzgpu_batcher_seal(mzgpu_batcher* b, uint64_t upper, mzgpu_ba
   if (b == nullptr || batch_out == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(b->ctx);
   return batcher_seal(b, upper, batch_out, new_lower);
+}
+extern "C" int32_t mzgpu_batcher_seal_many(uint32_t k, mzgpu_batcher* const* batchers, uint64_t upper,
+                                           mzgpu_batch** batches_out) {
+  if (k == 0) return MZGPU_OK;
+  if (batchers == nullptr || batches_out == nullptr) return MZGPU_E_INVALID;
+  for (uint32_t i = 0; i < k; ++i) {
+    if (batchers[i] == nullptr || batchers[i]->ctx != batchers[0]->ctx) return MZGPU_E_INVALID;
+    for (uint32_t j = 0; j < i; ++j)
+      if (batchers[j] == batchers[i]) return MZGPU_E_INVALID;
+  }
+  MZ_CHECK_CTX(batchers[0]->ctx);
+  return batcher_seal_many((int)k, batchers, upper, batches_out);
 }
 extern "C" uint64_t mzgpu_batcher_frontier(const mzgpu_batcher* b) {
   if (b == nullptr) return MZGPU_FRONTIER_EMPTY;
@@ -1589,6 +1727,8 @@ extern "C" int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch
   return MZGPU_OK;
 }
 
+// bulk probes (join_core work items): the bounded single-pass form may take this much output memory
+#define MZ_BULK_BOUND_BYTES (12ull << 30)
 extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out,
                                         int32_t* done) {
   if (j == nullptr || out == nullptr) return MZGPU_E_INVALID;
@@ -1620,7 +1760,30 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
       pp.has_closure = j->has_closure ? 1 : 0;
       pp.swap_vals = w.side == 1 ? 1 : 0;
       pp.closure = j->closure;
-      st = mz_probe(j->ctx, w.batch->rows.as<u64>(), w.batch->st.v[0], tv, pp, &res, &n_res);
+      // Bounded fan-out: one pass into a buffer of n x (sum of the longest key runs) rows -- the
+      // probe walks the trace once instead of twice (count, write) and the only read-back is the
+      // result count that the fuel accounting needs anyway.
+      u64 fan = 0;
+      bool exact = true;
+      st = trace_fanout(w.others, &fan, &exact);
+      const u64 n_probe = w.batch->st.v[0];
+      const bool bounded = st == MZGPU_OK && exact && fan > 0 && n_probe > 0 &&
+                           n_probe <= MZ_BULK_BOUND_BYTES / (fan * out_rb) && (n_probe + 255) / 256 <= MZ_LB_TILES;
+      if (st == MZGPU_OK && bounded) {
+        Lazy4 rlen;
+        const u64 bound = n_probe * fan;
+        st = res.alloc(j->ctx, bound * out_rb);
+        if (st == MZGPU_OK) st = rlen.make_pending(j->ctx);
+        if (st == MZGPU_OK) {
+          st = mz_probe_async(j->ctx, w.batch->rows.as<u64>(), dlen_imm(n_probe), n_probe, tv, pp, res.as<u64>(),
+                              dlen_imm(0), bound, rlen.dptr());
+          rlen.mark_written();
+        }
+        if (st == MZGPU_OK) st = rlen.resolve();
+        if (st == MZGPU_OK) n_res = rlen.v[0];
+      } else if (st == MZGPU_OK) {
+        st = mz_probe(j->ctx, w.batch->rows.as<u64>(), n_probe, tv, pp, &res, &n_res);
+      }
     }
     // Work::process consolidates each work item's output buffer before sending
     if (st == MZGPU_OK && n_res)
@@ -1732,6 +1895,187 @@ extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint
   }
   return half_join_dev(ctx, d_stream, dlen_imm(n), n, trace, cmp_mode, closure, consolidate_output, out);
 }
+// k half joins in one launch (mz_probe_async_many).  Requests whose output buffers coincide must
+// be adjacent: they form a chain whose results are appended in request order -- the last stage of
+// the delta paths, whose outputs are concatenated (delta_join.rs:302-308).  Anything the single
+// launch cannot take (unbounded fan-out, an empty stream or trace, a buffer named twice apart)
+// runs request by request; the results are the same either way.
+struct HalfJoinReq {
+  mzgpu_buf* stream;  // the stream to probe with, or ...
+  mzgpu_spine* trace;
+  int32_t cmp_mode;
+  const mzgpu_closure* closure;
+  mzgpu_buf* out;
+  // ... a sealed batch whose update stream (build_update_stream: rows at `skip_time` dropped,
+  // `pre` applied) is formed inside the probe kernel
+  mzgpu_batch* src = nullptr;
+  const mzgpu_closure* pre = nullptr;
+  u64 skip_time = MZGPU_FRONTIER_EMPTY;
+};
+static int32_t map_rows_into(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, const mzgpu_closure* closure,
+                             u64 skip_time, mzgpu_buf* out);
+static const u64* req_rows(const HalfJoinReq& r) { return r.src ? r.src->rows.as<u64>() : r.stream->mem.as<u64>(); }
+static DLen req_dlen(const HalfJoinReq& r) { return r.src ? batch_dlen(r.src) : buf_dlen(r.stream); }
+static u64 req_ub(const HalfJoinReq& r) { return r.src ? r.src->len_ub : r.stream->ub; }
+static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs) {
+  auto one_by_one = [&]() -> int32_t {
+    for (int j = 0; j < k; ++j) {
+      const HalfJoinReq& r = reqs[j];
+      if (r.src != nullptr) {
+        // the separate operators: update stream into a scratch buffer, then the half join
+        mzgpu_buf tmp;
+        tmp.ctx = ctx;
+        tmp.rb = 32;
+        tmp.len.set(ctx, 0);
+        MZ_TRY(map_rows_into(ctx, req_rows(r), req_dlen(r), req_ub(r), r.pre, r.skip_time, &tmp));
+        MZ_TRY(half_join_dev(ctx, tmp.mem.as<u64>(), buf_dlen(&tmp), tmp.ub, r.trace, r.cmp_mode, r.closure, 0, r.out));
+      } else {
+        MZ_TRY(half_join_dev(ctx, req_rows(r), req_dlen(r), req_ub(r), r.trace, r.cmp_mode, r.closure, 0, r.out));
+      }
+    }
+    return MZGPU_OK;
+  };
+  for (int j = 0; j < k; ++j)
+    if (reqs[j].src != nullptr) MZ_TRY(batch_ready(reqs[j].src));
+  bool any_src = false;
+  for (int j = 0; j < k; ++j) any_src = any_src || reqs[j].src != nullptr;
+  if ((k < 2 && !any_src) || k > MZ_PROBE_MANY_MAX) return one_by_one();
+  static thread_local TraceView tvs[MZ_PROBE_MANY_MAX];  // large: kept off the stack
+  ProbeParams pps[MZ_PROBE_MANY_MAX];
+  u64 bound[MZ_PROBE_MANY_MAX];
+  u64 tiles = 0;
+  for (int j = 0; j < k; ++j) {
+    const HalfJoinReq& r = reqs[j];
+    for (int i = 0; i + 1 < j; ++i)
+      if (reqs[i].out == r.out && reqs[j - 1].out != r.out) return one_by_one();
+    for (int i = 0; i < k; ++i)
+      if (reqs[i].stream != nullptr && reqs[i].stream == r.out) return one_by_one();
+    if (req_ub(r) == 0) return one_by_one();
+    std::vector<mzgpu_batch*> all;
+    r.trace->all_batches(all);
+    u64 fan = 0;
+    bool exact = true;
+    MZ_TRY(trace_fanout(all, &fan, &exact));
+    MZ_TRY(trace_view(ctx, all, &tvs[j]));
+    if (tvs[j].n_batches == 0 || !exact || fan == 0 || req_ub(r) > MZ_BOUND_MAX_ROWS / fan) return one_by_one();
+    bound[j] = req_ub(r) * fan;
+    tiles += (req_ub(r) + 255) / 256;
+    memset(&pps[j], 0, sizeof(ProbeParams));
+    pps[j].mode = r.cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
+    pps[j].has_closure = 1;
+    if (r.closure) {
+      pps[j].closure = *r.closure;
+    } else {
+      pps[j].closure.n_key_fields = 1;
+      pps[j].closure.key_fields[0] = mzgpu_field{MZGPU_SRC_KEY, 0, 64, 0};
+      pps[j].closure.n_val_fields = 1;
+      pps[j].closure.val_fields[0] = mzgpu_field{MZGPU_SRC_VAL2, 0, 64, 0};
+    }
+  }
+  if (tiles > MZ_LB_TILES) return one_by_one();
+  // chains: reserve each output for the sum of its requests' bounds, open one append per chain
+  ProbeJobHost jobs[MZ_PROBE_MANY_MAX];
+  Append app[MZ_PROBE_MANY_MAX];
+  u64 chain_bound[MZ_PROBE_MANY_MAX];
+  int chain_first[MZ_PROBE_MANY_MAX];
+  int nc = 0;
+  for (int j = 0; j < k; ++j) {
+    if (j == 0 || reqs[j].out != reqs[j - 1].out) {
+      chain_first[nc] = j;
+      chain_bound[nc] = 0;
+      ++nc;
+    }
+    chain_bound[nc - 1] += bound[j];
+  }
+  for (int c = 0; c < nc; ++c) {
+    mzgpu_buf* out = reqs[chain_first[c]].out;
+    MZ_TRY(buf_reserve(out, out->ub + chain_bound[c], true));
+    MZ_TRY(buf_begin_append(out, &app[c]));
+  }
+  int c = -1;
+  for (int j = 0; j < k; ++j) {
+    if (j == 0 || reqs[j].out != reqs[j - 1].out) ++c;
+    mzgpu_buf* out = reqs[j].out;
+    jobs[j].d_stream = req_rows(reqs[j]);
+    jobs[j].n = req_dlen(reqs[j]);
+    jobs[j].n_ub = req_ub(reqs[j]);
+    jobs[j].has_pre = reqs[j].src != nullptr;
+    jobs[j].pre = reqs[j].pre;
+    jobs[j].skip_time = reqs[j].skip_time;
+    jobs[j].trace = &tvs[j];
+    jobs[j].pp = &pps[j];
+    jobs[j].chain = c;
+    jobs[j].d_out = out->mem.as<u64>();
+    jobs[j].out_base = app[c].base;
+    jobs[j].out_cap = out->cap;
+    jobs[j].d_out_len = app[c].out_len;
+  }
+  MZ_TRY(mz_probe_async_many(ctx, k, jobs));
+  for (int cc = 0; cc < nc; ++cc) buf_end_append(reqs[chain_first[cc]].out, app[cc], chain_bound[cc]);
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* const* streams,
+                                        mzgpu_spine* const* traces, const int32_t* cmp_modes,
+                                        const mzgpu_closure* const* closures, mzgpu_buf* const* outs) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (streams == nullptr || traces == nullptr || cmp_modes == nullptr || outs == nullptr || k > 64)
+    return MZGPU_E_INVALID;
+  std::vector<HalfJoinReq> reqs(k);
+  for (uint32_t j = 0; j < k; ++j) {
+    if (streams[j] == nullptr || traces[j] == nullptr || outs[j] == nullptr || streams[j] == outs[j] ||
+        streams[j]->rb != 32 || traces[j]->rb != 32 || outs[j]->rb != 32 ||
+        (cmp_modes[j] != MZGPU_HALFJOIN_LE && cmp_modes[j] != MZGPU_HALFJOIN_LT))
+      return MZGPU_E_INVALID;
+    reqs[j].stream = streams[j];
+    reqs[j].trace = traces[j];
+    reqs[j].cmp_mode = cmp_modes[j];
+    reqs[j].closure = closures ? closures[j] : nullptr;
+    reqs[j].out = outs[j];
+    ctx->stats.rows_in += streams[j]->ub;
+  }
+  // groups of at most MZ_PROBE_MANY_MAX, never splitting a chain's adjacency
+  for (uint32_t at = 0; at < k; at += MZ_PROBE_MANY_MAX) {
+    const int g = (int)std::min<uint32_t>(MZ_PROBE_MANY_MAX, k - at);
+    MZ_TRY(half_join_many_dev(ctx, g, reqs.data() + at));
+  }
+  return MZGPU_OK;
+}
+
+extern "C" int32_t mzgpu_delta_first_stage_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_batch* const* batches,
+                                                const mzgpu_closure* const* initial_closures,
+                                                const uint64_t* skip_times, mzgpu_spine* const* traces,
+                                                const int32_t* cmp_modes, const mzgpu_closure* const* closures,
+                                                mzgpu_buf* const* outs) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (batches == nullptr || skip_times == nullptr || traces == nullptr || cmp_modes == nullptr || outs == nullptr ||
+      k > 64)
+    return MZGPU_E_INVALID;
+  std::vector<HalfJoinReq> reqs(k);
+  for (uint32_t j = 0; j < k; ++j) {
+    if (batches[j] == nullptr || traces[j] == nullptr || outs[j] == nullptr || batches[j]->rb != 32 ||
+        traces[j]->rb != 32 || outs[j]->rb != 32 ||
+        (cmp_modes[j] != MZGPU_HALFJOIN_LE && cmp_modes[j] != MZGPU_HALFJOIN_LT))
+      return MZGPU_E_INVALID;
+    reqs[j].stream = nullptr;
+    reqs[j].src = batches[j];
+    reqs[j].pre = initial_closures ? initial_closures[j] : nullptr;
+    reqs[j].skip_time = skip_times[j];
+    reqs[j].trace = traces[j];
+    reqs[j].cmp_mode = cmp_modes[j];
+    reqs[j].closure = closures ? closures[j] : nullptr;
+    reqs[j].out = outs[j];
+    ctx->stats.rows_in += batches[j]->len_ub;
+  }
+  for (uint32_t at = 0; at < k; at += MZ_PROBE_MANY_MAX) {
+    const int g = (int)std::min<uint32_t>(MZ_PROBE_MANY_MAX, k - at);
+    MZ_TRY(half_join_many_dev(ctx, g, reqs.data() + at));
+  }
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_spine* trace, int32_t cmp_mode,
                                        const mzgpu_closure* closure, int32_t consolidate_output, mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);
@@ -1897,8 +2241,16 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
                                            corr.as<u64>(), per_row * b_ub, clen.dptr());
         clen.mark_written();
       }
-      if (st == MZGPU_OK) st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), per_row * b_ub, &cons, &ccap, &flen);
-      if (st == MZGPU_OK) st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : per_row * b_ub);
+      if (st == MZGPU_OK && !minmax) {
+        // the accumulable kinds' corrections leave the kernel consolidated (reduce.cu:
+        // sort_key_corrections): keys ascending, each key's few rows sorted by its thread
+        st = buf_append_dev(out, corr.p, dlen_of(clen, 0), per_row * b_ub);
+      } else {
+        if (st == MZGPU_OK)
+          st = consolidate_dev(ctx, 64, corr.p, dlen_of(clen, 0), per_row * b_ub, &cons, &ccap, &flen);
+        if (st == MZGPU_OK)
+          st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : per_row * b_ub);
+      }
     } else {
       DevMem corr, cons;
       u64 n_corr = 0, ccap = 0;

@@ -104,14 +104,16 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // Pass 0 counts the matches and keeps the first KC output rows in a per-thread cache; after the
 // scan + look-back the cached rows are written, and only a probe row with more than KC matches
 // walks the trace again (pass 1).
-template <int OUT_NW>
-__global__ void __launch_bounds__(PT, 2) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+// KC / MINB: update batches cache eight output rows per probe row (lookups with a fan-out of
+// up to eight never walk twice) at two CTAs per SM; bulk probes (millions of rows, fan-out ~1)
+// keep two and trade the cache registers for twice the resident warps -- their limit is the
+// number of DRAM accesses in flight.  GROUP = batches whose first slot is fetched together.
+template <int OUT_NW, int KC, int MINB, int GROUP>
+__global__ void __launch_bounds__(PT, MINB) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
                                                  u64* __restrict__ out_len, u64* __restrict__ status) {
-  constexpr int KC = 8;
-  constexpr int GROUP = 8;
   __shared__ u32 sm[34];
   __shared__ u32 s_tile;
   __shared__ u64 s_b;
@@ -239,6 +241,199 @@ __global__ void __launch_bounds__(PT, 2) k_probe_lb(const u64* __restrict__ stre
       }
     }
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;
+  }
+}
+
+// ---- several probes in one launch.  A *chain* is a sequence of probe jobs whose results are
+// appended, in job order, to ONE output buffer (the last stage of the delta paths: every path
+// appends to the result collection); chains are independent of each other (an earlier stage: one
+// output buffer per path).  A chain numbers the tiles of its jobs consecutively and runs one
+// look-back over all of them, so its output is exactly what its jobs would have appended one
+// after the other; blockIdx.y selects the chain.
+constexpr int PROBE_MANY_MAX = MZ_PROBE_MANY_MAX;
+struct ProbeJobDev {
+  const u64* stream;
+  DLen dn;
+  TraceView tv;
+  ProbeParams pp;
+  // optional map in front of the probe (build_update_stream fused into the first half join,
+  // delta_join.rs:312-377): rows at `skip_time` are dropped, the closure rewrites (key, val) or drops
+  int has_pre, pre_has_closure;
+  u64 skip_time;
+  mzgpu_closure pre;
+};
+struct ProbeChain {
+  u32 first, count;  // jobs [first, first + count)
+  LookBack lb;
+  u64* out;
+  DLen out_base;
+  u64 out_cap;
+  u64* out_len;
+};
+struct ProbeMany {
+  u32 n_chains;
+  ProbeChain chain[PROBE_MANY_MAX];
+  ProbeJobDev job[PROBE_MANY_MAX];
+};
+static_assert(sizeof(ProbeMany) <= 32000, "kernel parameter space");
+
+template <int OUT_NW>
+__global__ void __launch_bounds__(PT, 2) k_probe_chains(const __grid_constant__ ProbeMany m,
+                                                     u64* __restrict__ status) {
+  constexpr int KC = 8;
+  constexpr int GROUP = 8;
+  __shared__ u32 sm[34];
+  __shared__ u32 s_tile;
+  __shared__ u64 s_b;
+  const ProbeChain& ch = m.chain[blockIdx.y];
+  u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
+  tiles_before[0] = 0;
+#pragma unroll
+  for (int q = 0; q < PROBE_MANY_MAX; ++q) {
+    nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
+    tiles_before[q + 1] = tiles_before[q] + (nj[q] + PT - 1) / PT;
+  }
+  const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
+  const u64 base0 = dlen_get(ch.out_base);
+  while (true) {
+    const u32 tile = lb_next_tile(ch.lb, &s_tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
+      break;
+    }
+    u32 q = 0;
+    while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
+    const ProbeJobDev& J = m.job[ch.first + q];
+    const u64 n = nj[q];
+    const u64 i = (u64)(tile - tiles_before[q]) * PT + threadIdx.x;
+    u64 key = 0, v1 = 0, t1 = 0;
+    i64 d1 = 0;
+    if (i < n) {
+      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(J.stream + i * 4);
+      const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(J.stream + i * 4 + 2);
+      key = kv.x;
+      v1 = kv.y;
+      t1 = td.x;
+      d1 = (i64)td.y;
+    }
+    bool live = i < n;
+    if (live && J.has_pre) {
+      if (J.skip_time != MZGPU_FRONTIER_EMPTY && t1 == J.skip_time) {
+        live = false;
+      } else if (J.pre_has_closure) {
+        u64 k, v;
+        if (closure_eval(J.pre, key, v1, 0, &k, &v)) {
+          key = k;
+          v1 = v;
+        } else {
+          live = false;
+        }
+      }
+    }
+    u64 cache[KC][OUT_NW];
+    u32 cnt = 0;
+    u64 pos = 0;
+    u32 ex = 0, total = 0;
+    u64 excl = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool walk = live && (pass == 0 || cnt > (u32)KC);
+      if (walk) {
+        const u64 h0 = mix64(key);
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < J.tv.n_batches; b0 += GROUP) {
+          // independent first-slot loads of a group of batches, then the (rare) matches
+          ulonglong2 slot[GROUP];
+          u64 hh[GROUP], msk[GROUP];
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            if (b0 + j < J.tv.n_batches) {
+              const BatchView& bv = J.tv.b[b0 + j];
+              msk[j] = bv_mask(bv);
+              hh[j] = h0 & msk[j];
+              slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
+            }
+          }
+#pragma unroll 1
+          for (int j = 0; j < GROUP; ++j) {
+            if (b0 + j >= J.tv.n_batches) break;
+            const BatchView& bv = J.tv.b[b0 + j];
+            ulonglong2 sl = slot[j];
+            u64 h = hh[j];
+            const u64 mask = msk[j];
+            while (sl.y != 0 && sl.x != key) {
+              h = (h + 1) & mask;
+              sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+            }
+            if (sl.y == 0) continue;
+            const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+            const u32 len = (u32)(sl.y >> 44);
+            const u64 end = len != 0 ? first + len : bv_n(bv);
+#pragma unroll 1
+            for (u64 r = first; r < end; ++r) {
+              const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+              if (len == 0 && rkv.x != key) break;
+              const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+              const u64 t2 = rtd.x;
+              const bool ok = J.pp.mode == MZ_PROBE_HALF_LE ? t2 <= t1 : (J.pp.mode == MZ_PROBE_HALF_LT ? t2 < t1 : true);
+              if (!ok) continue;
+              u64 t = t1;
+              if (J.pp.mode == MZ_PROBE_JOIN) {
+                t = t1 > t2 ? t1 : t2;
+                t = t > J.pp.meet ? t : J.pp.meet;
+              }
+              const u64 d = (u64)d1 * rtd.y;
+              const u64 va = J.pp.swap_vals ? rkv.y : v1, vb = J.pp.swap_vals ? v1 : rkv.y;
+              u64 row[OUT_NW];
+              if (OUT_NW == 4) {
+                u64 k, v;
+                if (!closure_eval(J.pp.closure, key, va, vb, &k, &v)) continue;
+                row[0] = k;
+                row[1] = v;
+                row[2] = t;
+                row[3] = d;
+              } else {
+                row[0] = key;
+                row[1] = va;
+                row[2] = vb;
+                row[3] = t;
+                row[OUT_NW - 1] = d;
+              }
+              if (pass == 0) {
+                if (cnt < (u32)KC) {
+#pragma unroll
+                  for (int w = 0; w < OUT_NW; ++w) cache[cnt][w] = row[w];
+                }
+                cnt++;
+              } else {
+                u64* o = ch.out + pos * OUT_NW;
+#pragma unroll
+                for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
+                pos++;
+              }
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+        ex = block_exclusive_scan(cnt, sm, &total);
+        excl = lb_exclusive_prefix(ch.lb, tile, (u64)total, &s_b);
+        pos = base0 + excl + ex;
+        if (i < n && cnt > 0) {
+          if (pos + cnt > ch.out_cap) {
+            atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
+            cnt = 0;  // nothing is written (the overflow is reported at the next read-back)
+          } else if (cnt <= (u32)KC) {
+            for (u32 c = 0; c < cnt; ++c) {
+              u64* o = ch.out + (pos + c) * OUT_NW;
+#pragma unroll
+              for (int w = 0; w < OUT_NW; ++w) o[w] = cache[c][w];
+            }
+          }
+        }
+      }
+    }
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
   }
 }
 
@@ -482,12 +677,83 @@ int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, co
   MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
   const int out_rb = pp.has_closure ? 32 : 40;
   MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 * trace.n_batches + 32 + out_rb) : 0);  // exact counts only
+  const bool bulk = n_ub >= (1ull << 20);
   if (pp.has_closure) {
-    MZ_LAUNCH(ctx, (k_probe_lb<4>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
-              out_cap, d_out_len, ctx->d_status);
+    if (bulk) {
+      MZ_LAUNCH(ctx, (k_probe_lb<4, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    } else {
+      MZ_LAUNCH(ctx, (k_probe_lb<4, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    }
   } else {
-    MZ_LAUNCH(ctx, (k_probe_lb<5>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base,
-              out_cap, d_out_len, ctx->d_status);
+    if (bulk) {
+      MZ_LAUNCH(ctx, (k_probe_lb<5, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    } else {
+      MZ_LAUNCH(ctx, (k_probe_lb<5, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
+                out_base, out_cap, d_out_len, ctx->d_status);
+    }
+  }
+  return MZGPU_OK;
+}
+
+// Several single-pass probes in one launch (see k_probe_chains).  jobs[j].chain: jobs of one chain
+// are consecutive and share out / out_base / out_cap / out_len (taken from the chain's first job).
+int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
+  if (k <= 0) return MZGPU_OK;
+  if (k > PROBE_MANY_MAX) {
+    MZ_SET_ERR(ctx, "probe: %d jobs exceed the maximum %d per launch", k, PROBE_MANY_MAX);
+    return MZGPU_E_INVALID;
+  }
+  static thread_local ProbeMany m;  // large: kept off the stack
+  memset(&m, 0, sizeof(m));
+  const bool closure = jobs[0].pp->has_closure != 0;
+  u64 lb_at = 0, max_grid = 1, bytes = 0;
+  int nc = 0;
+  for (int j = 0; j < k; ++j) {
+    if ((jobs[j].pp->has_closure != 0) != closure) {
+      MZ_SET_ERR(ctx, "probe: jobs of one launch must agree on the output row shape");
+      return MZGPU_E_INVALID;
+    }
+    m.job[j].stream = jobs[j].d_stream;
+    m.job[j].dn = jobs[j].n;
+    m.job[j].tv = *jobs[j].trace;
+    m.job[j].pp = *jobs[j].pp;
+    m.job[j].has_pre = jobs[j].has_pre ? 1 : 0;
+    m.job[j].pre_has_closure = (jobs[j].has_pre && jobs[j].pre != nullptr) ? 1 : 0;
+    m.job[j].skip_time = jobs[j].skip_time;
+    if (m.job[j].pre_has_closure) m.job[j].pre = *jobs[j].pre;
+    if (j == 0 || jobs[j].chain != jobs[j - 1].chain) {
+      ProbeChain& c = m.chain[nc++];
+      c.first = (u32)j;
+      c.count = 0;
+      c.out = jobs[j].d_out;
+      c.out_base = jobs[j].out_base;
+      c.out_cap = jobs[j].out_cap;
+      c.out_len = jobs[j].d_out_len;
+    }
+    m.chain[nc - 1].count++;
+  }
+  m.n_chains = (u32)nc;
+  for (int c = 0; c < nc; ++c) {
+    u64 tiles = 0, rows_ub = 0;
+    for (u32 q = 0; q < m.chain[c].count; ++q) {
+      const ProbeJobHost& J = jobs[m.chain[c].first + q];
+      tiles += (J.n_ub + PT - 1) / PT;
+      rows_ub += J.n_ub;
+      if (J.n.p == nullptr) bytes += J.n.imm * (32 + 16 * J.trace->n_batches + 32 + (closure ? 32 : 40));
+    }
+    MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
+    lb_at += tiles;
+    const u64 g = lb_grid(ctx, rows_ub);
+    if (g > max_grid) max_grid = g;
+  }
+  MZ_BYTES(ctx, bytes);
+  if (closure) {
+    MZ_LAUNCH(ctx, (k_probe_chains<4>), dim3((unsigned)max_grid, (unsigned)nc), PT, 0, m, ctx->d_status);
+  } else {
+    MZ_LAUNCH(ctx, (k_probe_chains<5>), dim3((unsigned)max_grid, (unsigned)nc), PT, 0, m, ctx->d_status);
   }
   return MZGPU_OK;
 }

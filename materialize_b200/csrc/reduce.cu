@@ -230,6 +230,35 @@ __device__ __forceinline__ void prior_sum(const TraceView& tv, u64 key, u64* S) 
   }
 }
 
+// The corrections of ONE key, out[pos .. pos + c), put into consolidated order (words 1..5:
+// count, sum_lo, sum_hi, flags, time; the key is the same).  A key's corrections are distinct rows
+// (-old and +new differ in their values, different times differ in the time word), and keys are
+// written in ascending order by construction, so with this the kernel's whole output is already
+// what consolidate() would return: the separate sort launch (40 us for a few hundred rows) is gone.
+__device__ __forceinline__ void sort_key_corrections(u64* __restrict__ out, u64 pos, u32 c) {
+  for (u32 x = 1; x < c; ++x) {
+    u64 r[8];
+    load_row<8>(out, pos + x, r);
+    u32 y = x;
+    while (y > 0) {
+      u64 p[8];
+      load_row<8>(out, pos + y - 1, p);
+      bool less = false;
+#pragma unroll
+      for (int w = 1; w <= 5; ++w) {
+        if (r[w] != p[w]) {
+          less = r[w] < p[w];
+          break;
+        }
+      }
+      if (!less) break;
+      store_row<8>(out, pos + y, p);
+      --y;
+    }
+    if (y != x) store_row<8>(out, pos + y, r);
+  }
+}
+
 // Corrections of one changed key: rows [i, ...) of the new batch with this key,
 // given the key's prior accumulation S0.  Counts (and optionally writes at
 // out[pos...]) the (-old, +new) output rows.
@@ -256,6 +285,7 @@ __device__ __forceinline__ u32 walk_key(const u64* __restrict__ rows, u64 n, u64
       }
       mult = m2;
     }
+    if (do_write && c > 1) sort_key_corrections(out, pos, c);
     return c;
   }
   bool had = !diff_is_zero<8>(S);
@@ -295,6 +325,7 @@ __device__ __forceinline__ u32 walk_key(const u64* __restrict__ rows, u64 n, u64
 #pragma unroll
     for (int w = 0; w < 4; ++w) oldv[w] = newv[w];
   }
+  if (do_write && c > 1) sort_key_corrections(out, pos, c);
   return c;
 }
 

@@ -245,6 +245,29 @@ def test_batcher_seal_matches_oracle(mz, ctx, oracle):
             lower = upper
 
 
+def test_seal_many_matches_single_seals(mz, ctx, oracle):
+    """mzgpu_batcher_seal_many: k arrangements sealed by one frontier advance in one launch give the
+    batches, kept rows and frontiers of k separate seals (and of the oracle's batchers)."""
+    rng = np.random.default_rng(31)
+    sizes = [30000, 0, 7000, 90000, 1]
+    gbs = [mz.Batcher(ctx, 32) for _ in sizes]
+    obs = [oracle.Batcher(32) for _ in sizes]
+    t = 0
+    for rnd in range(4):
+        for gb, ob, n in zip(gbs, obs, sizes):
+            a = rand_r32(rng, n, 1 << (8 + 4 * rnd), 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = rng.integers(t, t + 4, size=n, dtype=np.uint64)  # some rows stay behind the frontier
+            gb.push_container(a)
+            ob.push(a)
+        t += 2
+        got = mz.seal_many(gbs, t)
+        for g, gb, ob in zip(got, gbs, obs):
+            o = ob.seal(t)
+            same(g.rows(), o.rows())
+            assert g.desc() == o.desc()
+            assert gb.frontier() == ob.frontier()
+
+
 def test_batch_merge_matches_oracle(mz, ctx, oracle):
     rng = np.random.default_rng(22)
     for since in (0, 2, 4, 100):
@@ -385,6 +408,73 @@ def test_half_join_matches_oracle(mz, ctx, oracle, cmp_mode):
         got = mz.half_join(ctx, stream, gs, cmp_mode, gcl)
         want = oracle.half_join(stream, os_, cmp_mode, ocl)
         same(got, want)
+
+
+def test_half_join_many_matches_single_half_joins(mz, ctx, oracle):
+    """mzgpu_half_join_many: independent half joins of one stage in one launch; requests naming the
+    same output form a chain and append in request order (the concatenated outputs of the delta
+    paths' last stage) -- row for row what the single calls produce."""
+    rng = np.random.default_rng(77)
+    spines = []
+    for sp in range(3):
+        gs = mz.Spine(ctx, 32)
+        for t in range(3 + sp):
+            a = rand_r32(rng, 3000, 400 + 100 * sp, 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = t
+            gs.insert(mz.Batch.build(ctx, a, t, t + 1))
+            gs.set_physical_compaction(t + 1)
+        spines.append(gs)
+    streams = [rand_r32(rng, n, 600, 1 << 20, 8, dtype=oracle.R32) for n in (5000, 1, 777)]
+    cl = mz.make_closure(key_fields=[(2, 0, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 10, 10, 20)], filters=[(2, 0, 20, "lt", 900000)])
+    closures = [None, cl, cl]
+    cmps = [mz.HALFJOIN_LE, mz.HALFJOIN_LT, mz.HALFJOIN_LE]
+    devs = [mz.DeviceRows(ctx, 32).upload(s) for s in streams]
+    # (a) three independent outputs, (b) chain of two + one apart, (c) one chain of three
+    for layout in ([0, 1, 2], [0, 0, 1], [0, 0, 0]):
+        outs = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        want = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        # something already in the buffers: appends must start behind it
+        for o, w in zip(outs, want):
+            o.upload(streams[1])
+            w.upload(streams[1])
+        mz.half_join_many(ctx, [(devs[j], spines[j], cmps[j], closures[j], outs[layout[j]]) for j in range(3)])
+        for j in range(3):
+            mz.half_join_dev(ctx, devs[j], spines[j], cmps[j], closures[j], False, want[layout[j]])
+        for o, w in zip(outs, want):
+            same(o.download(), w.download())
+
+
+def test_delta_first_stage_many_matches_separate_operators(mz, ctx, oracle):
+    """mzgpu_delta_first_stage_many = update_stream (as_of skip + initial closure) then half_join,
+    for one and for several paths, including paths that share the output collection."""
+    rng = np.random.default_rng(78)
+    spines, batches = [], []
+    for sp in range(3):
+        gs = mz.Spine(ctx, 32)
+        for t in range(2 + sp):
+            a = rand_r32(rng, 3000, 400, 1 << 20, 1, dtype=oracle.R32)
+            a["time"] = t
+            gs.insert(mz.Batch.build(ctx, a, t, t + 1))
+            gs.set_physical_compaction(t + 1)
+        spines.append(gs)
+        b = rand_r32(rng, (4000, 2, 900)[sp], 500, 1 << 20, 3, dtype=oracle.R32)
+        batches.append(mz.Batch.build(ctx, b, 0, 3))
+    init = mz.make_closure(key_fields=[(1, 0, 9, 0)], val_fields=[(0, 0, 20, 0)], filters=[(1, 0, 20, "lt", 800000)])
+    stage = mz.make_closure(key_fields=[(2, 0, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 10, 10, 20)])
+    inits = [init, None, init]
+    skips = [mz.FRONTIER_EMPTY, 0, 1]
+    cmps = [mz.HALFJOIN_LE, mz.HALFJOIN_LT, mz.HALFJOIN_LE]
+    for k, layout in ((1, [0]), (3, [0, 1, 2]), (3, [0, 0, 0]), (2, [0, 0])):
+        outs = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        want = [mz.DeviceRows(ctx, 32) for _ in range(3)]
+        mz.delta_first_stage_many(
+            ctx, [(batches[j], inits[j], skips[j], spines[j], cmps[j], stage, outs[layout[j]]) for j in range(k)]
+        )
+        for j in range(k):
+            stream = mz.update_stream_dev(ctx, batches[j], inits[j], skips[j])
+            mz.half_join_dev(ctx, stream, spines[j], cmps[j], stage, False, want[layout[j]])
+        for o, w in zip(outs, want):
+            same(o.download(), w.download())
 
 
 def test_update_stream_and_map_rows(mz, ctx, oracle):
