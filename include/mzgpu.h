@@ -19,6 +19,11 @@
  *     that created it (one ctx per timely worker; the reference's operators
  *     are single-threaded Rc<RefCell<..>>, src/compute/src/typedefs.rs:46).
  *   - row pointers carry a memory-space tag (MZGPU_MEM_HOST / MZGPU_MEM_DEVICE).
+ *     INPUT row pointers (either space) are read by a copy or kernel enqueued on
+ *     the ctx stream: the caller must leave the rows untouched until the next
+ *     call that waits for the device (mzgpu_ctx_sync, or anything returning an
+ *     exact count).  Pageable host memory is staged by the driver before the
+ *     call returns; PINNED host memory and device memory are read in place.
  *   - variable-size results are written to a library-owned device buffer
  *     (`mzgpu_buf`) that the caller downloads or feeds to the next operator.
  *   - calls are asynchronous on the ctx stream.  Data-dependent row counts
@@ -408,7 +413,12 @@ int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out, 
  * with cmp(t, time): emit ((closure(key,val1,val2)), time, d1*d2).  The caller
  * must have advanced the trace's upper beyond every stream time (the operator
  * waits for the arrangement frontier in the reference).  Results are appended
- * to `out` (R32 rows, not consolidated unless consolidate_output != 0). */
+ * to `out` (R32 rows, not consolidated unless consolidate_output != 0).
+ * A probe sees at most 64 non-empty batches of `trace` (admitted layers plus
+ * batches still waiting for physical compaction): advance the trace's physical
+ * compaction (mzgpu_spine_set_physical_compaction) as the arrangement frontier
+ * moves, as TraceManager::maintenance does, or the call returns
+ * MZGPU_E_UNSUPPORTED once more than 64 batches have piled up. */
 int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint64_t n, int32_t mem,
                         mzgpu_spine* trace, int32_t cmp_mode, const mzgpu_closure* closure,
                         int32_t consolidate_output, mzgpu_buf* out);

@@ -332,6 +332,44 @@ static int32_t copy_out(mzgpu_ctx* ctx, void* dst, const void* d_src, size_t byt
   return MZGPU_OK;
 }
 
+// Closure descriptors come from the caller: everything the device code indexes or shifts by is
+// checked here, once, at plan time (include/mzgpu.h: richer plans are MZGPU_E_UNSUPPORTED, malformed
+// descriptors MZGPU_E_INVALID; nothing undefined reaches a kernel).
+static int32_t validate_field(mzgpu_ctx* ctx, const mzgpu_field& f, bool uses_dst) {
+  if (f.src > MZGPU_SRC_VAL2 || f.shift >= 64 || f.bits < 1 || f.bits > 64 || (uses_dst && f.dst_shift >= 64)) {
+    MZ_SET_ERR(ctx, "closure: bad field {src=%u shift=%u bits=%u dst_shift=%u}", f.src, f.shift, f.bits, f.dst_shift);
+    return MZGPU_E_INVALID;
+  }
+  return MZGPU_OK;
+}
+static int32_t validate_closure(mzgpu_ctx* ctx, const mzgpu_closure* c) {
+  if (c == nullptr) return MZGPU_OK;
+  if (c->n_key_fields > MZGPU_MAX_FIELDS || c->n_val_fields > MZGPU_MAX_FIELDS || c->n_filters > MZGPU_MAX_FILTERS) {
+    MZ_SET_ERR(ctx, "closure: %u key fields / %u value fields / %u filters exceed the descriptor (%d / %d / %d)",
+               c->n_key_fields, c->n_val_fields, c->n_filters, MZGPU_MAX_FIELDS, MZGPU_MAX_FIELDS, MZGPU_MAX_FILTERS);
+    return MZGPU_E_UNSUPPORTED;
+  }
+  if (c->expr_kind != MZGPU_EXPR_NONE && c->expr_kind != MZGPU_EXPR_MUL_CONST_MINUS) {
+    MZ_SET_ERR(ctx, "closure: unknown expression kind %u", c->expr_kind);
+    return MZGPU_E_UNSUPPORTED;
+  }
+  for (uint32_t i = 0; i < c->n_key_fields; ++i) MZ_TRY(validate_field(ctx, c->key_fields[i], true));
+  if (c->expr_kind == MZGPU_EXPR_MUL_CONST_MINUS) {
+    MZ_TRY(validate_field(ctx, c->expr_a, false));
+    MZ_TRY(validate_field(ctx, c->expr_b, false));
+  } else {
+    for (uint32_t i = 0; i < c->n_val_fields; ++i) MZ_TRY(validate_field(ctx, c->val_fields[i], true));
+  }
+  for (uint32_t i = 0; i < c->n_filters; ++i) {
+    MZ_TRY(validate_field(ctx, c->filters[i].field, false));
+    if (c->filters[i].op > MZGPU_CMP_GE) {
+      MZ_SET_ERR(ctx, "closure: unknown comparison %u", c->filters[i].op);
+      return MZGPU_E_UNSUPPORTED;
+    }
+  }
+  return MZGPU_OK;
+}
+
 static bool valid_row_bytes(uint32_t rb) { return rb == 16 || rb == 32 || rb == 40 || rb == 80 || rb == 64; }
 
 // ------------------------------------------------------ device-side append
@@ -780,6 +818,9 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
   MZ_TRY(batch_ready(b1));
   MZ_TRY(batch_ready(b2));
   mzgpu_desc d = {b1->desc.lower, b2->desc.upper, since};
+  // advance_by of an empty antichain leaves every time alone; the kernels compute
+  // max(time, since), for which 0 is the no-op
+  const u64 adv = since == MZGPU_FRONTIER_EMPTY ? 0 : since;
   if (!mz_use_fused(false, b1->len_ub + b2->len_ub)) {
     MZ_TRY(batch_resolve(b1));
     MZ_TRY(batch_resolve(b2));
@@ -792,7 +833,7 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
     job.b = b2->rows.p;
     job.nb = batch_dlen(b2);
     job.cap = b1->len_ub + b2->len_ub;
-    job.since = since;
+    job.since = adv;
     job.want_index = true;
     job.merge = true;
     FusedOut fo;
@@ -817,7 +858,7 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
   MZ_TRY(batch_resolve(b2));
   DevMem merged;
   u64 n_out = 0;
-  MZ_TRY(mz_merge_consolidate(ctx, b1->rb, b1->rows.p, b1->st.v[0], b2->rows.p, b2->st.v[0], since, &merged,
+  MZ_TRY(mz_merge_consolidate(ctx, b1->rb, b1->rows.p, b1->st.v[0], b2->rows.p, b2->st.v[0], adv, &merged,
                               &n_out));
   return make_batch(ctx, b1->rb, std::move(merged), n_out, d, out);
 }
@@ -1257,13 +1298,12 @@ struct mzgpu_spine {
   std::vector<mzgpu_batch*> view;     // scratch for batches_through
   int32_t err = MZGPU_OK;             // first failure inside a scheduling step
 
+  // usize::next_power_of_two().trailing_zeros() (trace.rs:1714); next_power_of_two overflows
+  // beyond 2^63 in the reference (a debug panic / release 0): capped at level 63 here
   static u64 level_of(u64 n) {
-    u64 p = 1, l = 0;
-    while (p < n) {
-      p <<= 1;
-      ++l;
-    }
-    return l;
+    if (n <= 1) return 0;
+    const u64 l = 64 - (u64)__builtin_clzll(n - 1);
+    return l > 63 ? 63 : l;
   }
   u64 layer_len(const Layer& m) const {
     u64 n = 0;
@@ -1509,7 +1549,8 @@ extern "C" int32_t mzgpu_spine_exert(mzgpu_spine* s, uint64_t effort, int32_t* d
   bool any = false;
   for (auto& m : s->merging) any = any || m.has_merge;
   if (any) {
-    s->apply_fuel((long long)effort);
+    // isize::try_from(effort).unwrap_or(isize::MAX) (trace.rs:1706)
+    s->apply_fuel(effort > (uint64_t)INT64_MAX ? (long long)INT64_MAX : (long long)effort);
   } else {
     mzgpu_batch* e = nullptr;
     mzgpu_desc d = {s->upper, s->upper, s->since};
@@ -1690,6 +1731,7 @@ extern "C" int32_t mzgpu_join_new(mzgpu_ctx* ctx, mzgpu_spine* trace1, mzgpu_spi
   MZ_CHECK_CTX(ctx);
   if (trace1 == nullptr || trace2 == nullptr || out == nullptr || trace1->rb != 32 || trace2->rb != 32)
     return MZGPU_E_INVALID;
+  MZ_TRY(validate_closure(ctx, closure));
   mzgpu_join* j = new mzgpu_join();
   j->ctx = ctx;
   j->t1 = trace1;
@@ -1740,8 +1782,9 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
   }
   u64 produced = 0;
   while (!j->todo.empty() && produced < fuel_rows) {
-    mzgpu_join::Work w = std::move(j->todo.front());
-    j->todo.pop_front();
+    // the item leaves the queue only once its output has been appended: a failure below (more
+    // batches than a trace view holds, counter arena, ...) leaves it queued, so no join work is lost
+    mzgpu_join::Work& w = j->todo.front();
     TraceView tv;
     int32_t st = MZGPU_OK;
     for (auto* b : w.others)
@@ -1791,8 +1834,9 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     if (st == MZGPU_OK && n_res) st = clen.resolve();
     const u64 n_cons = n_res ? clen.v[0] : 0;
     if (st == MZGPU_OK && n_cons) st = buf_append_dev(out, cons.p, dlen_imm(n_cons), n_cons);
-    j->release_work(w);
     if (st != MZGPU_OK) return st;
+    j->release_work(w);
+    j->todo.pop_front();
     produced += n_cons;
     j->ctx->stats.rows_out += n_cons;
   }
@@ -1884,6 +1928,7 @@ extern "C" int32_t mzgpu_half_join(mzgpu_ctx* ctx, const mzgpu_r32* stream, uint
   if (trace == nullptr || out == nullptr || (stream == nullptr && n) || trace->rb != 32 || out->rb != 32 ||
       (cmp_mode != MZGPU_HALFJOIN_LE && cmp_mode != MZGPU_HALFJOIN_LT))
     return MZGPU_E_INVALID;
+  MZ_TRY(validate_closure(ctx, closure));
   if (n == 0) return MZGPU_OK;
   ctx->stats.rows_in += n;
   DevMem in;
@@ -2032,6 +2077,7 @@ extern "C" int32_t mzgpu_half_join_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf* c
     reqs[j].trace = traces[j];
     reqs[j].cmp_mode = cmp_modes[j];
     reqs[j].closure = closures ? closures[j] : nullptr;
+    MZ_TRY(validate_closure(ctx, reqs[j].closure));
     reqs[j].out = outs[j];
     ctx->stats.rows_in += streams[j]->ub;
   }
@@ -2066,6 +2112,8 @@ extern "C" int32_t mzgpu_delta_first_stage_many(mzgpu_ctx* ctx, uint32_t k, mzgp
     reqs[j].trace = traces[j];
     reqs[j].cmp_mode = cmp_modes[j];
     reqs[j].closure = closures ? closures[j] : nullptr;
+    MZ_TRY(validate_closure(ctx, reqs[j].pre));
+    MZ_TRY(validate_closure(ctx, reqs[j].closure));
     reqs[j].out = outs[j];
     ctx->stats.rows_in += batches[j]->len_ub;
   }
@@ -2082,6 +2130,7 @@ extern "C" int32_t mzgpu_half_join_buf(mzgpu_ctx* ctx, mzgpu_buf* stream, mzgpu_
   if (stream == nullptr || trace == nullptr || out == nullptr || stream == out || stream->rb != 32 ||
       trace->rb != 32 || out->rb != 32 || (cmp_mode != MZGPU_HALFJOIN_LE && cmp_mode != MZGPU_HALFJOIN_LT))
     return MZGPU_E_INVALID;
+  MZ_TRY(validate_closure(ctx, closure));
   ctx->stats.rows_in += stream->ub;
   return half_join_dev(ctx, stream->mem.as<u64>(), buf_dlen(stream), stream->ub, trace, cmp_mode, closure,
                        consolidate_output, out);
@@ -2116,6 +2165,7 @@ extern "C" int32_t mzgpu_update_stream(mzgpu_ctx* ctx, mzgpu_batch* batch,
                                        mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);
   if (batch == nullptr || out == nullptr || batch->rb != 32 || out->rb != 32) return MZGPU_E_INVALID;
+  MZ_TRY(validate_closure(ctx, initial_closure));
   MZ_TRY(batch_ready(batch));
   return map_rows_into(ctx, batch->rows.as<u64>(), batch_dlen(batch), batch->len_ub, initial_closure, skip_time,
                        out);
@@ -2125,6 +2175,7 @@ extern "C" int32_t mzgpu_map_rows(mzgpu_ctx* ctx, const mzgpu_r32* rows, uint64_
                                   const mzgpu_closure* closure, mzgpu_buf* out) {
   MZ_CHECK_CTX(ctx);
   if (out == nullptr || (rows == nullptr && n) || out->rb != 32) return MZGPU_E_INVALID;
+  MZ_TRY(validate_closure(ctx, closure));
   if (n == 0) return MZGPU_OK;
   DevMem in;
   const u64* d_rows = (const u64*)rows;
@@ -2143,6 +2194,8 @@ struct mzgpu_reduce {
   TopKParams topk = {-1, 0, 0};
   mzgpu_batcher* batcher = nullptr;
   mzgpu_spine* input = nullptr;
+  int32_t failed = MZGPU_OK;  // set when an activation failed after its seal (reduce_dev)
+  std::string failed_msg;
   ~mzgpu_reduce() {
     delete batcher;
     delete input;
@@ -2182,6 +2235,10 @@ extern "C" mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r) { return r ? r
 
 static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, u64 upper, mzgpu_buf* out) {
   mzgpu_ctx* ctx = r->ctx;
+  if (r->failed != MZGPU_OK) {  // an earlier activation lost its corrections: the operator is dead, not the worker
+    ctx->last_error = r->failed_msg;
+    return r->failed;
+  }
   // batches sealed by earlier activations are merge-eligible now; their lengths
   // have reached the host with whatever the caller read since (no extra wait)
   MZ_TRY(mzgpu_spine_set_physical_compaction(r->input, r->input->upper));
@@ -2269,8 +2326,18 @@ static int32_t reduce_dev(mzgpu_reduce* r, const u64* d_rows, DLen n, u64 n_ub, 
         st = buf_append_dev(out, cons.p, dlen_of(flen, 0), flen.known ? flen.v[0] : n_corr);
     }
   }
-  if (st == MZGPU_OK && batch->desc.lower != batch->desc.upper) st = mzgpu_spine_insert(r->input, batch);
+  // The seal above consumed the batcher's rows and advanced its frontier, so the batch joins the
+  // input trace whatever happened since (the arrangement stays consistent with the frontier); a
+  // failure after the seal means this activation's corrections are missing from `out`, which no
+  // later activation can repair: the operator reports that status from now on.
+  int32_t ins = MZGPU_OK;
+  if (batch->desc.lower != batch->desc.upper) ins = mzgpu_spine_insert(r->input, batch);
   mzgpu_batch_release(batch);
+  if (st == MZGPU_OK) st = ins;
+  if (st != MZGPU_OK && !ctx->sticky) {
+    r->failed = st;
+    r->failed_msg = ctx->last_error;
+  }
   return st;
 }
 

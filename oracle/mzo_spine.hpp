@@ -165,12 +165,10 @@ struct Spine {
 
   static size_t level_of(size_t n) {
     // usize::next_power_of_two().trailing_zeros(); next_power_of_two(0) == 1.
-    size_t p = 1, l = 0;
-    while (p < n) {
-      p <<= 1;
-      ++l;
-    }
-    return l;
+    // (next_power_of_two overflows beyond 2^63 in the reference; capped at level 63 here)
+    if (n <= 1) return 0;
+    const size_t l = 64 - (size_t)__builtin_clzll((unsigned long long)(n - 1));
+    return l > 63 ? 63 : l;
   }
 
   void set_logical_compaction(u64 f) {
@@ -219,7 +217,8 @@ struct Spine {
     bool any = false;
     for (auto& m : merging) any = any || m.has_merge;
     if (any) {
-      apply_fuel((long long)eff);
+      // isize::try_from(effort).unwrap_or(isize::MAX) (trace.rs:1706)
+      apply_fuel(eff > (size_t)INT64_MAX ? (long long)INT64_MAX : (long long)eff);
     } else {
       size_t level = level_of(eff);
       size_t a, b;

@@ -489,6 +489,51 @@ def test_update_stream_and_map_rows(mz, ctx, oracle):
     same(mz.map_rows(ctx, a, gcl), oracle.map_rows(a, ocl))
 
 
+def test_malformed_closures_are_rejected_at_plan_time(mz, ctx):
+    """Closure descriptors are caller data: counts beyond the descriptor, shifts >= 64, zero-width
+    fields, unknown sources / operators / expression kinds never reach a kernel (mzgpu.h: E_INVALID
+    for malformed descriptors, E_UNSUPPORTED for plans outside the subset)."""
+    from materialize_b200 import _ffi as F
+
+    a = rand_r32(np.random.default_rng(5), 64, 100, 100, 3, dtype=mz.R32)
+    good = dict(key_fields=[(0, 0, 64, 0)], val_fields=[(1, 0, 64, 0)])
+
+    def bad(mutate):
+        c = mz.make_closure(**good)
+        mutate(c)
+        return c
+
+    cases = [
+        (bad(lambda c: setattr(c, "n_key_fields", 7)), F.E_UNSUPPORTED),
+        (bad(lambda c: setattr(c, "n_val_fields", 100)), F.E_UNSUPPORTED),
+        (bad(lambda c: setattr(c, "n_filters", 5)), F.E_UNSUPPORTED),
+        (bad(lambda c: setattr(c, "expr_kind", 9)), F.E_UNSUPPORTED),
+        (bad(lambda c: setattr(c.key_fields[0], "shift", 64)), F.E_INVALID),
+        (bad(lambda c: setattr(c.key_fields[0], "bits", 0)), F.E_INVALID),
+        (bad(lambda c: setattr(c.key_fields[0], "bits", 65)), F.E_INVALID),
+        (bad(lambda c: setattr(c.val_fields[0], "dst_shift", 64)), F.E_INVALID),
+        (bad(lambda c: setattr(c.val_fields[0], "src", 3)), F.E_INVALID),
+    ]
+    flt = mz.make_closure(filters=[(0, 0, 8, "ge", 1)], **good)
+    flt.filters[0].op = 6
+    cases.append((flt, F.E_UNSUPPORTED))
+    gb = mz.Batch.build(ctx, a, 0, 3)
+    gs = mz.Spine(ctx, 32)
+    gs.insert(gb)
+    for c, code in cases:
+        for call in (
+            lambda: mz.map_rows(ctx, a, c),
+            lambda: mz.update_stream(ctx, gb, c),
+            lambda: mz.half_join(ctx, a, gs, mz.HALFJOIN_LE, c),
+            lambda: mz.JoinCore(ctx, gs, gs, c),
+        ):
+            with pytest.raises(mz.MzGpuError) as e:
+                call()
+            assert e.value.status == code, (e.value.status, code)
+    # the context is still usable (nothing sticky)
+    same(mz.map_rows(ctx, a, mz.make_closure(**good)), mz.map_rows(ctx, a, mz.make_closure(**good)))
+
+
 # ----------------------------------------------------------- a11, a12
 @pytest.mark.parametrize("agg_kind", [0, 1])
 def test_reduce_accumulable_matches_oracle(mz, ctx, oracle, agg_kind):
