@@ -332,3 +332,34 @@ def test_spine_preserves_contents_under_random_maintenance(oracle, seed):
         # export folds with advance_by(since) applied: compare as consolidated collections
         want = oracle.consolidate(allr)
         assert oracle.consolidate(got).tobytes() == want.tobytes()
+
+
+# ------------------------------------------------ reference-held SQL known answers
+def test_oracle_operators_reproduce_sqllogictest_answers(oracle):
+    """Pins the join / distinct / reduce restatements to answers the reference itself holds: the
+    integer-only cases of test/sqllogictest/joins.slt and aggregates.slt (fixture cites the lines)."""
+    import sql_golden as sg
+
+    fx = sg.load()
+    ops = sg.OracleOps(oracle)
+    ran = 0
+    for case in fx["cases"]:
+        if case["shape"] == "sum_of_nulls":
+            continue
+        got = sg.norm(sg.evaluate(ops, case, fx["tables"]))
+        want = sg.norm([tuple(r) for r in case["expect"]])
+        assert got == want, (case["name"], case["cite"], got, want)
+        ran += 1
+    assert ran >= 12
+
+
+def test_oracle_sum_of_nulls_is_null(oracle):
+    """aggregates.slt:156-176: SUM over only-NULL inputs is NULL.  NULL inputs never reach explode (the
+    fixed-width subset has no NULL datum), so this pins finalize_accum alone (reduce.rs:1905-1937): an
+    accumulator that counted two rows and no non-NULL value finalizes to the NULL-sum flag."""
+    acc = np.zeros(1, dtype=oracle.RACC)
+    acc["key"], acc["total"], acc["non_nulls"] = 0, 2, 0
+    out = oracle.finalize(acc, 0)
+    assert int(out["flags"][0]) & 1
+    acc["non_nulls"] = 2
+    assert int(oracle.finalize(acc, 0)["flags"][0]) & 1 == 0
