@@ -63,6 +63,7 @@ struct mzgpu_ctx {
   void* fused_deferred = nullptr;       // fused.cu: jobs prepared but not launched yet
   std::vector<struct mzgpu_batch*> deferred_inputs;  // retained until the flush
   u64 defer_seq = 0, flushed_seq = 0;   // deferred jobs enqueued / launched
+  int deferred_unlaunched = 0;          // jobs prepared by mz_fused_defer and not launched yet
   bool defer_merges = true;             // spine merges wait for each other (MZGPU_DEFER_MERGES=0: launch at once)
   // ---- side stream: batch merges (spine maintenance) run here, concurrently with the
   // operators on the main stream; a batch produced here carries side_seq and the main
@@ -243,6 +244,7 @@ struct DevMem {
 int32_t mz_resolve_counters(mzgpu_ctx* ctx);  // host.cu: one D2H of the arena + sync
 int mz_cnt_alloc(mzgpu_ctx* ctx);             // -1 if the arena is exhausted
 void mz_cnt_free(mzgpu_ctx* ctx, int blk);
+void mz_cnt_unpark(mzgpu_ctx* ctx);
 
 struct Lazy4 {
   mzgpu_ctx* ctx = nullptr;

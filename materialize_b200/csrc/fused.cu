@@ -47,7 +47,8 @@ constexpr u32 MSD_LOCAL_MAX = 1024;  // largest bucket the in-CTA sort takes
 
 struct FusedCtl {
   u32 barrier;
-  u32 pad[3];
+  u32 overflow;  // fast MSD path: a bucket outgrew its fixed-capacity region (the exact path runs instead)
+  u32 pad[2];
   u64 minmax[12];  // [2k] = max of ~word (so zero is the identity), [2k+1] = max of word
   u64 n_seg;
   u64 n_out;
@@ -88,6 +89,7 @@ struct FusedArgs {
   u64* lb_keep;
   u32 max_g;     // CTAs that take part at most
   u32 merge;     // both inputs are sorted and consolidated: merge path instead of a sort
+  u32 fast;      // fast MSD path allowed (MZGPU_FUSED_FAST=0 turns it off: bisecting, A/B timing)
 };
 
 __device__ __forceinline__ u64 gtimer() {
@@ -100,15 +102,20 @@ __device__ __forceinline__ u64 gtimer() {
     if (a.dbg != nullptr && c == 0 && tid == 0) a.dbg[(i)] = gtimer(); \
   } while (0)
 
+// Grid-wide barrier over the job's own counter (monotone: epoch e completes at e * G arrivals).
+// One thread per CTA arrives with a release reduction and spins on an acquire load; the
+// __syncthreads() on either side extend the ordering to the whole CTA (CTA-scope barriers are
+// cumulative), so everything written before the barrier by any CTA is visible after it.
 __device__ __forceinline__ void grid_barrier(u32* counter, u32 G, u32& epoch) {
   __syncthreads();
   epoch++;
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     const u32 target = epoch * G;
-    while (*(volatile u32*)counter < target) __nanosleep(20);
-    __threadfence();
+    u32 v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }
@@ -352,11 +359,270 @@ __device__ __forceinline__ void msd_warp_buckets(const FusedArgs& a, FusedCtl* c
   }
 }
 
+// ---- fast MSD path, bucket phase.  Differences from msd_warp_buckets above:
+//  * a bucket is a FIXED-capacity region (32*R slots at b * 32*R) that the pack phase filled
+//    directly (slot = atomic counter of the bucket), so there is no count -> scan -> scatter;
+//  * only the bits that vary inside a bucket are kept (the composite minus its leading bucket
+//    bits): KW = 1 when they fit one word -- the usual case -- halves the sort's shuffles;
+//  * the hash index of the shipped rows is built right here when a key cannot span buckets
+//    (`inline_index`): the warp knows the final position of every row it ships once the
+//    look-back has given the chunk's base, so no table pass (and no grid barrier) follows.
+template <int RB, int R, int KW>
+__device__ __forceinline__ void msd_warp_buckets2(const FusedArgs& a, FusedCtl* ctl, u32 NB, u32 c, u32 G, u64 na,
+                                                  u64 since, u64 mask, bool inline_index, u64* s_cnt, u64* s_lb,
+                                                  u64* s_keys /* [FT/32][32*R] */, u32* s_stat /* [2] */) {
+  constexpr int NW = RowT<RB>::NW, NK = RowT<RB>::NK, ND = RowT<RB>::ND, TW = RowT<RB>::TW;
+  constexpr u32 CAP = 32u * R;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 upper = a.upper;
+  LookBack lbs;
+  lbs.state = a.lb_ship;
+  lbs.ticket = nullptr;
+  lbs.epoch = 1;
+  u64* wkeys = s_keys + (size_t)warp * CAP;
+  u32 my_heads = 0, my_run = 0;
+  const u32 n_chunks = (NB + 7) / 8;
+  for (u32 ch = c; ch < n_chunks; ch += G) {
+    const u32 b = ch * 8 + warp;
+    u32 m = 0;
+    if (b < NB) {
+      m = *(volatile u32*)&ctl->bcnt[b];
+      m = m < CAP ? m : CAP;  // (an overflow never gets here: the exact path runs instead)
+    }
+    const u64 gbase = (u64)b * CAP;
+    u64 hi[R], lo[R];
+    u32 ix[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      if (p < m) {
+        lo[r] = a.m_lo[gbase + p];
+        hi[r] = KW == 2 ? a.m_hi[gbase + p] : 0ull;
+        ix[r] = a.m_idx[gbase + p];
+      } else {
+        lo[r] = ~0ull;
+        hi[r] = KW == 2 ? ~0ull : 0ull;
+        ix[r] = 0xffffffffu;
+      }
+    }
+    // bitonic network over positions p = r*32 + lane, ordered by (hi, lo, idx): idx makes real
+    // elements distinct (and puts the padding last among equal keys)
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int r2 = r ^ (j >> 5);
+            if (r2 > r) {
+              const bool up = (((r * 32 + (int)lane) & k) == 0);
+              bool gt;
+              if (KW == 2)
+                gt = hi[r] > hi[r2] || (hi[r] == hi[r2] && (lo[r] > lo[r2] || (lo[r] == lo[r2] && ix[r] > ix[r2])));
+              else
+                gt = lo[r] > lo[r2] || (lo[r] == lo[r2] && ix[r] > ix[r2]);
+              if (gt == up) {
+                u64 t0 = lo[r];
+                lo[r] = lo[r2];
+                lo[r2] = t0;
+                if (KW == 2) {
+                  t0 = hi[r];
+                  hi[r] = hi[r2];
+                  hi[r2] = t0;
+                }
+                u32 t1 = ix[r];
+                ix[r] = ix[r2];
+                ix[r2] = t1;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const u64 olo = __shfl_xor_sync(0xffffffffu, lo[r], j);
+            const u64 ohi = KW == 2 ? __shfl_xor_sync(0xffffffffu, hi[r], j) : 0ull;
+            const u32 oix = __shfl_xor_sync(0xffffffffu, ix[r], j);
+            const bool up = (((r * 32 + (int)lane) & k) == 0);
+            const bool lower = ((lane & j) == 0);
+            bool gt;
+            if (KW == 2)
+              gt = hi[r] > ohi || (hi[r] == ohi && (lo[r] > olo || (lo[r] == olo && ix[r] > oix)));
+            else
+              gt = lo[r] > olo || (lo[r] == olo && ix[r] > oix);
+            const bool take = (lower == up) ? gt : !gt;
+            if (take) {
+              lo[r] = olo;
+              if (KW == 2) hi[r] = ohi;
+              ix[r] = oix;
+            }
+          }
+        }
+      }
+    }
+    // head flags, diffs
+    bool head[R];
+    u64 d[R][ND];
+    u64 tt[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      u64 plo = __shfl_up_sync(0xffffffffu, lo[r], 1);
+      u64 phi = KW == 2 ? __shfl_up_sync(0xffffffffu, hi[r], 1) : 0ull;
+      if (r > 0) {
+        const u64 qlo = __shfl_sync(0xffffffffu, lo[r - 1 >= 0 ? r - 1 : 0], 31);
+        const u64 qhi = KW == 2 ? __shfl_sync(0xffffffffu, hi[r - 1 >= 0 ? r - 1 : 0], 31) : 0ull;
+        if (lane == 0) {
+          plo = qlo;
+          phi = qhi;
+        }
+      }
+      head[r] = p < m && (p == 0 || plo != lo[r] || (KW == 2 && phi != hi[r]));
+      tt[r] = 0;
+      if (p < m) {
+        u64 row[NW];
+        load_in_row<RB>(a, na, since, ix[r], row);
+#pragma unroll
+        for (int w = 0; w < ND; ++w) d[r][w] = row[NK + w];
+        if (TW >= 0) tt[r] = row[TW >= 0 ? TW : 0];
+      } else {
+#pragma unroll
+        for (int w = 0; w < ND; ++w) d[r][w] = 0;
+      }
+    }
+    // segmented inclusive sums in position order; the carry crosses register rows
+    u64 carry[ND];
+#pragma unroll
+    for (int w = 0; w < ND; ++w) carry[w] = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 hm = __ballot_sync(0xffffffffu, head[r]);
+      const u32 below = hm & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1));
+      const int my_start = below ? 31 - __clz(below) : -1;
+      const int start_eff = my_start < 0 ? 0 : my_start;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        u64 o[ND];
+#pragma unroll
+        for (int w = 0; w < ND; ++w) o[w] = __shfl_up_sync(0xffffffffu, d[r][w], off);
+        if ((int)lane - off >= start_eff) diff_add<ND>(d[r], o);
+      }
+      if (my_start < 0) diff_add<ND>(d[r], carry);
+#pragma unroll
+      for (int w = 0; w < ND; ++w) carry[w] = __shfl_sync(0xffffffffu, d[r][w], 31);
+    }
+    // survivors: the LAST row of every segment carries the segment's sum
+    u32 cls[R];
+    u32 cnt_ship = 0, cnt_keep = 0;
+    u32 pos_ship[R], pos_keep[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const u32 p = r * 32 + lane;
+      bool nhead = __shfl_down_sync(0xffffffffu, head[r], 1);
+      if (r + 1 < R) {
+        const bool q = __shfl_sync(0xffffffffu, head[r + 1 < R ? r + 1 : r], 0);
+        if (lane == 31) nhead = q;
+      } else if (lane == 31) {
+        nhead = true;
+      }
+      const bool tail = p < m && (p == m - 1 || nhead);
+      cls[r] = 0;
+      if (tail && !diff_is_zero<ND>(d[r]))
+        cls[r] = (TW < 0 || upper == MZGPU_FRONTIER_EMPTY || tt[r] < upper) ? 1u : 2u;
+      const u32 ms = __ballot_sync(0xffffffffu, cls[r] == 1u), mk = __ballot_sync(0xffffffffu, cls[r] == 2u);
+      const u32 lt = (1u << lane) - 1;
+      pos_ship[r] = cnt_ship + __popc(ms & lt);
+      pos_keep[r] = cnt_keep + __popc(mk & lt);
+      cnt_ship += __popc(ms);
+      cnt_keep += __popc(mk);
+    }
+    // chunk-level offsets: eight warps, then the look-back over chunks
+    __syncthreads();
+    if (lane == 0) s_cnt[warp] = ((u64)cnt_ship << 21) | (u64)cnt_keep;
+    __syncthreads();
+    u64 mine = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FT / 32; ++w) {
+      const u64 v = s_cnt[w];
+      if ((u32)w < warp) mine += v;
+      total += v;
+    }
+    const u64 chunk_base = lb_exclusive_prefix(lbs, ch, total, s_lb);
+    const u64 bases = chunk_base + mine;
+    const u64 ship_base = bases >> 21, keep_base = bases & ((1ull << 21) - 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (cls[r] != 0u) {
+        u64 row[NW];
+        load_in_row<RB>(a, na, since, ix[r], row);
+#pragma unroll
+        for (int w = 0; w < ND; ++w) row[NK + w] = d[r][w];
+        if (cls[r] == 1u) {
+          store_row<NW>(a.out, ship_base + pos_ship[r], row);
+          if (inline_index) wkeys[pos_ship[r]] = row[0];
+        } else if (a.keep != nullptr) {
+          store_row<NW>(a.keep, keep_base + pos_keep[r], row);
+          if (TW >= 0) atomicMin((unsigned long long*)&a.kres[1], (unsigned long long)row[TW >= 0 ? TW : 0]);
+        }
+      }
+    }
+    if (inline_index) {
+      // keys of the rows this warp shipped, in output order: heads claim their slots
+      __syncwarp();
+      for (u32 e = lane; e < cnt_ship; e += 32) {
+        const u64 key = wkeys[e];
+        if (e == 0 || wkeys[e - 1] != key) {
+          u32 run = 1;
+          while (e + run < cnt_ship && wkeys[e + run] == key) ++run;
+          ++my_heads;
+          my_run = run > my_run ? run : my_run;
+          const u64 meta = (ship_base + e + 1) | ((u64)(run < MAX_RUN_SAT ? run : 0u) << 44);
+          u64 h = mix64(key) & mask;
+          while (true) {
+            unsigned long long prev = atomicCAS((unsigned long long*)&a.table[h].meta, 0ull, (unsigned long long)meta);
+            if (prev == 0ull) {
+              a.table[h].key = key;
+              break;
+            }
+            h = (h + 1) & mask;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (ch == n_chunks - 1 && tid == 0) {
+      const u64 all = chunk_base + total;
+      ctl->n_out = all >> 21;
+      a.res[0] = all >> 21;
+      a.kres[0] = all & ((1ull << 21) - 1);
+    }
+  }
+  if (inline_index) {
+    // distinct keys and the longest key run: one global atomic each per CTA
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      my_heads += __shfl_xor_sync(0xffffffffu, my_heads, off);
+      const u32 o = __shfl_xor_sync(0xffffffffu, my_run, off);
+      my_run = o > my_run ? o : my_run;
+    }
+    if (lane == 0) {
+      if (my_heads) atomicAdd(&s_stat[0], my_heads);
+      if (my_run) atomicMax(&s_stat[1], my_run);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (s_stat[0]) atomicAdd((unsigned long long*)&a.res[2], (unsigned long long)s_stat[0]);
+      if (s_stat[1]) atomicMax((unsigned long long*)&a.res[3], (unsigned long long)s_stat[1]);
+    }
+  }
+}
+
 union FusedSmem {
   RsSmemT<FI> rs;
   u32 hist[8 * 256];
   MsdSmem msd;
   MsdScan scan;
+  u64 wkeys[FT / 32][128];  // fast MSD path: keys of the rows a warp ships (inline hash index)
 };
 
 // The whole operator for one job.  `c` = this CTA's index among the `gdim` CTAs the launch gave
@@ -369,13 +635,16 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   __shared__ FusedSmem sm;
   __shared__ u32 sm_scan[34];
   __shared__ int s_nwords, s_nrounds, s_word[6], s_shift[6], s_round[6], s_rbits[MAX_ROUNDS];
-  __shared__ int s_shift128[6], s_w128;
+  __shared__ int s_shift128[6], s_w128, s_keybits;
   __shared__ u32 s_max_bucket, s_max_unit;
   __shared__ u64 s_minv[6];
   const u32 tid = threadIdx.x;
   const u64 na = dlen_get(a.na), nb = dlen_get(a.nb);
   const u64 n = na + nb;
   const u64 T = (n + FTILE - 1) / FTILE;
+  // A merge of update-batch size runs as a sort of A ++ B: the fast MSD path below has two grid
+  // barriers, the merge path five; sortedness only pays beyond the bucket phase's reach.
+  const bool merge = a.merge != 0 && !(a.fast != 0 && n <= (1ull << 18));
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
   // MSD bucket count from the row count alone: at most 48 (12 for the 80-byte
   // accumulable rows, whose warp capacity is 64 and whose keys arrive in clumps:
@@ -391,7 +660,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
     // 1024-row tiles (fewer CTAs = cheaper grid barriers)
     // (a merge has no buckets: two 256-row tiles of the consolidation tail per CTA)
     const u64 half_u = (n + 2 * FT - 1) / (2 * FT);
-    u64 want = a.merge ? (half_u > T ? half_u : T) : (T < (u64)((NB + 7) / 8) ? (u64)((NB + 7) / 8) : T);
+    u64 want = merge ? (half_u > T ? half_u : T) : (T < (u64)((NB + 7) / 8) ? (u64)((NB + 7) / 8) : T);
     if (want == 0) want = 1;
     if (want < (u64)G) G = (u32)want;
     if (G > a.max_g) G = a.max_g;  // more CTAs only make the grid barriers slower
@@ -453,7 +722,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
       mn[k] = 0;
       mx[k] = 0;
     }
-    for (u64 i = gtid; i < (a.merge ? 0 : n); i += gstride) {
+    for (u64 i = gtid; i < (merge ? 0 : n); i += gstride) {
       u64 r[NW];
       load_in(i, r);
 #pragma unroll
@@ -479,7 +748,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
     }
     // one atomic per CTA and word: same-address atomics from every warp serialise in L2
     __syncthreads();
-    if (tid < 2 * NK && n > 0 && !a.merge) {
+    if (tid < 2 * NK && n > 0 && !merge) {
       u64 v = 0;
 #pragma unroll
       for (int w = 0; w < FT / 32; ++w) v = s_mm[w][tid] > v ? s_mm[w][tid] : v;
@@ -487,7 +756,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
     }
   }
   // (a merge needs nothing of phase 0 before its own first barrier)
-  if (!a.merge) grid_barrier(&ctl->barrier, G, epoch);
+  if (!merge) grid_barrier(&ctl->barrier, G, epoch);
 
   // ---- plan (every CTA computes the same plan from the global min/max)
   if (tid == 0) {
@@ -519,6 +788,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
       w128 += bit_width_dev(hi - lo);
     }
     s_w128 = w128;
+    // width of the leading key word inside the composite (word 0 comes last in the plan)
+    s_keybits = (nwords > 0 && s_word[nwords - 1] == 0) ? w128 - s_shift128[nwords - 1] : 0;
     if (c == 0 && TW >= 0) a.kres[2] = n > 0 ? *(volatile u64*)&ctl->minmax[2 * (TW >= 0 ? TW : 0) + 1] : 0;
   }
   __syncthreads();
@@ -536,7 +807,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   // =================================================================== MSD path
   bool msd_done = false;
   // (beyond ~256K rows the bucket phase stops paying: the look-back radix passes win)
-  if (!a.merge && s_w128 <= 128 && n <= (1ull << 18)) {
+  if (!merge && s_w128 <= 128 && n <= (1ull << 18)) {
     const int W = s_w128;
     auto composite = [&](const u64* row, u64* clo, u64* chi) {
       unsigned __int128 comp = 0;
@@ -550,6 +821,69 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
       const u64 top = W <= 64 ? (clo << (64 - W)) : ((chi << (128 - W)) | (W == 128 ? 0ull : (clo >> (W - 64))));
       return (u32)(top >> (64 - bb));
     };
+    // ---- fast path: pack composites and scatter them straight into fixed-capacity bucket
+    // regions (slot = the bucket's atomic counter), then one warp per bucket.  Two grid barriers
+    // in all (after min/max, after the scatter); a bucket that outgrows its region (clumped
+    // keys) raises ctl->overflow and the exact count -> scan -> scatter path below runs instead.
+    bool fast_done = false, index_done = false;
+    if (a.fast != 0) {
+      const int Wr = W > (int)bb ? W - (int)bb : 0;  // bits that vary inside a bucket
+      const bool narrow = Wr <= 64;
+      // a key never spans two buckets when the bucket bits are all key bits
+      const bool inline_index = a.table != nullptr && s_keybits >= (int)bb;
+      for (u64 i = gtid; i < n; i += gstride) {
+        u64 row[NW];
+        load_in(i, row);
+        u64 clo, chi;
+        composite(row, &clo, &chi);
+        const u32 b = bucket_of(clo, chi);
+        const u32 r = atomicAdd(&ctl->bcnt[b], 1u);
+        if (r < WCAP) {
+          const u64 p = (u64)b * WCAP + r;
+          if (narrow) {
+            a.m_lo[p] = Wr >= 64 ? clo : (clo & ((1ull << Wr) - 1));
+          } else {
+            a.m_lo[p] = clo;
+            a.m_hi[p] = Wr >= 128 ? chi : (chi & ((1ull << (Wr - 64)) - 1));
+          }
+          a.m_idx[p] = (u32)i;
+        } else {
+          *(volatile u32*)&ctl->overflow = 1u;
+        }
+      }
+      if (inline_index)
+        for (u64 i = gtid; i < (mask + 1) * 2; i += gstride) ((u64*)a.table)[i] = 0;
+      grid_barrier(&ctl->barrier, G, epoch);
+      PHASE_STAMP(10);
+      if (*(volatile u32*)&ctl->overflow == 0u) {
+        __shared__ u64 s_wcnt2[FT / 32 + 1];
+        __shared__ u64 s_wlb2;
+        __shared__ u32 s_stat2[2];
+        if (tid == 0) {
+          s_stat2[0] = 0;
+          s_stat2[1] = 0;
+        }
+        __syncthreads();
+        if (a.dbg != nullptr && c == 0 && tid == 0) {
+          a.dbg[21] = narrow ? 4 : 5;
+          a.dbg[22] = inline_index ? 1 : 0;
+          a.dbg[23] = NB;
+        }
+        if (narrow)
+          msd_warp_buckets2<RB, WR, 1>(a, ctl, NB, c, G, na, since, mask, inline_index, s_wcnt2, &s_wlb2,
+                                       &sm.wkeys[0][0], s_stat2);
+        else
+          msd_warp_buckets2<RB, WR, 2>(a, ctl, NB, c, G, na, since, mask, inline_index, s_wcnt2, &s_wlb2,
+                                       &sm.wkeys[0][0], s_stat2);
+        fast_done = true;
+        msd_done = true;
+        index_done = inline_index;
+      } else {
+        for (u64 i = gtid; i < (u64)NB; i += gstride) ctl->bcnt[i] = 0;
+        grid_barrier(&ctl->barrier, G, epoch);
+      }
+    }
+    if (!fast_done) {
     // ---- pack composites, count rows per bucket (the atomic's return value is
     // the row's slot inside its bucket; the order inside a bucket is irrelevant)
     for (u64 i = gtid; i < n; i += gstride) {
@@ -814,6 +1148,11 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
       }
       msd_done = true;
     }
+    }  // !fast_done
+    if (index_done) {
+      PHASE_STAMP(7);
+      return;
+    }
   }
   PHASE_STAMP(7);
   if (msd_done) {
@@ -838,7 +1177,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   // the sort / merge paths accumulate segment sums in global memory (used several
   // grid barriers from here)
   for (u64 i = gtid; i < n * ND; i += gstride) a.seg_sums[i] = 0;
-  if (!a.merge) {
+  if (!merge) {
   // ---- radix rounds.  (kin, vin) holds the current order; round r packs into the
   // other pair (reading the order of round r-1) and sorts that.
   u64* kcur = a.k0;
@@ -1012,7 +1351,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   }
   grid_barrier(&ctl->barrier, G, epoch);
   PHASE_STAMP(3);
-  if (!a.merge) {  // (the merge phase has already counted the heads of every tile)
+  if (!merge) {  // (the merge phase has already counted the heads of every tile)
     for (u64 u = c; u < U; u += G) {
       const u64 i = u * FT + tid;
       u32 flag = i < n ? is_head(i) : 0u;
@@ -1204,6 +1543,15 @@ __global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_many(const __g
   fused_body<RB>(m.job[j], blockIdx.x - m.start[j], m.start[j + 1] - m.start[j]);
 }
 
+static int fused_fast_mode() {
+  static int fast = -1;
+  if (fast < 0) {
+    const char* ev = getenv("MZGPU_FUSED_FAST");
+    fast = ev ? atoi(ev) : 1;
+  }
+  return fast;
+}
+
 // Everything of a launch but the launch: buffers, control block, kernel arguments.
 // `slot` < 0: the context's single-job control blocks; otherwise job slot `slot` of a
 // multi-job launch (each slot flips between its own pair of control blocks).
@@ -1236,8 +1584,18 @@ int32_t fused_prepare(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res, int sl
   const u64 o_k0 = 0, o_k1 = o_k0 + al(cap * 8), o_v0 = o_k1 + al(cap * 8), o_v1 = o_v0 + al(cap * 4);
   const u64 o_s0 = o_v1 + al(cap * 4), o_s1 = o_s0 + al(Tcap * 1024), o_sorted = o_s1 + al(Tcap * 1024);
   const u64 o_t1 = o_sorted + al(cap * RB), o_t2 = o_t1 + al(Ucap * 4), o_sums = o_t2 + al(Ucap * 4);
+  // the fast MSD path's buckets are fixed-capacity regions (128 slots each): the bucket arrays
+  // hold (buckets for the largest row count this launch can see) x 128 entries
+  u64 mcap = cap;
+  {
+    const u64 n_max = cap < (1ull << 18) ? cap : (1ull << 18);
+    u32 bb = 0;
+    while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n_max) ++bb;
+    const u64 regions = ((u64)1 << bb) * 128;
+    if (regions > mcap) mcap = regions;
+  }
   const u64 o_first = o_sums + al(cap * ND * 8), o_mlo = o_first + al(cap * 4);
-  const u64 o_mhi = o_mlo + al(cap * 8), o_midx = o_mhi + al(cap * 8), o_lbs = o_midx + al(cap * 4);
+  const u64 o_mhi = o_mlo + al(mcap * 8), o_midx = o_mhi + al(mcap * 8), o_lbs = o_midx + al(mcap * 4);
   const u64 o_lbk = o_lbs + MSD_MAX_BUCKETS * 8, o_end = o_lbk + MSD_MAX_BUCKETS * 8;
   MZ_TRY(scratch->alloc(ctx, o_end));
   MZ_TRY(res->rows.alloc(ctx, cap * RB));
@@ -1281,6 +1639,7 @@ int32_t fused_prepare(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res, int sl
   a.table_cap = slots;
   a.res = res->st.dptr();
   a.kres = res->kst.dptr();
+  a.fast = fused_fast_mode() ? 1u : 0u;
   a.dbg = nullptr;
   if (ctx->profile && ctx->d_dbg != nullptr && ctx->dbg_next < MZ_DBG_RECORDS) {
     a.dbg = ctx->d_dbg + 32 * (size_t)ctx->dbg_next++;
@@ -1466,6 +1825,7 @@ int32_t mz_fused_flush(mzgpu_ctx* ctx) {
   if (d == nullptr || d->k == 0) return MZGPU_OK;
   const int k = d->k;
   d->k = 0;  // whatever happens below, the jobs are not retried
+  ctx->deferred_unlaunched = 0;
   int32_t st;
   switch (d->rb) {
     case 16: st = fused_launch_many<16>(ctx, k, d->args, d->want, d->bytes); break;
@@ -1477,6 +1837,7 @@ int32_t mz_fused_flush(mzgpu_ctx* ctx) {
   }
   for (int j = 0; j < k; ++j) d->scratch[j].release();  // stream ordered: after the launch
   d->bytes = 0;
+  mz_cnt_unpark(ctx);  // counter blocks freed while the jobs waited (their inputs' lengths)
   if (st != MZGPU_OK) ctx->sticky = true;  // outputs were promised to readers
   return st;
 }
@@ -1505,6 +1866,7 @@ int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out) {
       return MZGPU_E_UNSUPPORTED;
   }
   if (st != MZGPU_OK) return st;
+  ctx->deferred_unlaunched = d->k;
   out->st.mark_written();
   out->kst.mark_written();
   return MZGPU_OK;

@@ -138,10 +138,19 @@ void mz_cnt_free(mzgpu_ctx* ctx, int blk) {
   // A block may still be written by a kernel in flight.  On one stream that is harmless (its
   // next producer is queued behind that kernel); while side-stream work is outstanding the
   // next producer could run on the other stream, so the block is parked until the join.
-  if (ctx->stream != ctx->main_stream || ctx->joined_seq != ctx->side_seq)
+  // The same holds while prepared-but-unlaunched (deferred) jobs exist: such a job may read
+  // this block (an input length captured as a device pointer), and the block's next producer
+  // would be enqueued AHEAD of the deferred launch -- parked until the flush.
+  if (ctx->stream != ctx->main_stream || ctx->joined_seq != ctx->side_seq || ctx->deferred_unlaunched > 0)
     ctx->cnt_parked.push_back(blk);
   else
     ctx->cnt_free.push_back(blk);
+}
+// parked blocks become reusable once nothing unlaunched or unjoined can touch them
+void mz_cnt_unpark(mzgpu_ctx* ctx) {
+  if (ctx->stream != ctx->main_stream || ctx->joined_seq != ctx->side_seq || ctx->deferred_unlaunched > 0) return;
+  for (int b : ctx->cnt_parked) ctx->cnt_free.push_back(b);
+  ctx->cnt_parked.clear();
 }
 // One copy of the whole arena (a few KB) + one wait: every count produced by a
 // kernel enqueued before this call becomes readable on the host.
@@ -151,8 +160,7 @@ static int32_t mz_join_side(mzgpu_ctx* ctx) {
   if (ctx->stream == ctx->main_stream) {
     MZ_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side, 0));
     ctx->joined_seq = ctx->side_seq;
-    for (int b : ctx->cnt_parked) ctx->cnt_free.push_back(b);
-    ctx->cnt_parked.clear();
+    mz_cnt_unpark(ctx);
   }
   return MZGPU_OK;
 }
@@ -713,7 +721,13 @@ static int32_t batch_shrink(mzgpu_batch* b) {
   MZ_TRY(batch_ready(b));
   mzgpu_ctx* ctx = b->ctx;
   const u64 len = b->st.v[0];
-  if (b->rows_cap > len + len / 2 + 4096) {
+  const u64 slots_now = b->st.v[1] + 1;
+  const bool realloc_rows = b->rows_cap > len + len / 2 + 4096;
+  const bool realloc_table = b->table.p != nullptr && b->table.bytes > 2 * slots_now * sizeof(HashSlot) + 65536;
+  // the old allocations are freed in stream order, i.e. AHEAD of jobs that were prepared but not
+  // launched yet; such a job may read this batch (a deferred merge's input): launch them first
+  if ((realloc_rows || realloc_table) && ctx->deferred_unlaunched > 0) MZ_TRY(mz_flush_deferred(ctx));
+  if (realloc_rows) {
     DevMem m;
     MZ_TRY(m.alloc(ctx, std::max<u64>(len, 1) * b->rb));
     MZ_TRY(copy_in(ctx, m.p, b->rows.p, len * b->rb, MZGPU_MEM_DEVICE));

@@ -28,7 +28,7 @@ def phases(ctx):
         st = sorted((int(x), i) for i, x in enumerate(r[:16]) if int(x))
         d = {"rows": int(r[16]), "rounds": int(r[17]), "bits": [int((int(r[18]) >> (8 * i)) & 255) for i in range(4)],
              "ctas": int(r[19]), "total_us": (st[-1][0] - st[0][0]) / 1e3,
-             "path": {0: "lsd/merge", 1: "msd-warp", 2: "msd-cta", 3: "lsd(overflow)"}.get(int(r[21]), "?"),
+             "path": {0: "lsd/merge", 1: "msd-warp", 2: "msd-cta", 3: "lsd(overflow)", 4: "fast-msd(64-bit)", 5: "fast-msd(128-bit)"}.get(int(r[21]), "?"),
              "max_bucket": int(r[22]), "buckets": int(r[23]), "row_bytes": int(r[20]),
              # stamp ids: 0 start, 1 after minmax+plan, 10 after MSD pack, 11 after MSD scatter, 7 after emit,
              # 8 after the barrier before the index, 9 end; LSD path: 2 radix, 3 gather, 4 heads, 5 segsum, 6 count
