@@ -493,6 +493,16 @@ int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out);
 int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs);
 /* The routing function itself (for tests and host-side pre-partitioning). */
 uint32_t mzgpu_route(uint64_t key, uint32_t peers);
+/* The device half of an exchange round on its own: the k buffers are bucketed by
+ * destination for `peers` workers (any 1 <= peers <= 64, independent of the ctx's
+ * own peer count) with the kernels mzgpu_exchange_many runs; outs[e] receives the
+ * rows of ins[e] grouped by destination in worker order, counts[e * peers + p] the
+ * rows bound for worker p (read back: one host wait).  Row order inside a
+ * destination group is unspecified (the receiving Batcher sorts).  Lets a host
+ * that moves the bytes itself (timely's own network layer) keep the partitioning
+ * on the GPU, and lets one GPU test the routing for any cluster size. */
+int32_t mzgpu_partition_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, uint32_t peers, mzgpu_buf** outs,
+                             uint64_t* counts);
 
 #ifdef __cplusplus
 }

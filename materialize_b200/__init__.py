@@ -40,6 +40,7 @@ from .api import (  # noqa: F401
     delta_first_stage_many,
     make_closure,
     map_rows,
+    partition_many,
     route,
     update_stream,
     update_stream_dev,

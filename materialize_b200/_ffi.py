@@ -178,6 +178,7 @@ SIGNATURES = {
     "mzgpu_exchange": (i32, [vp, vp, vp]),
     "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
+    "mzgpu_partition_many": (i32, [vp, u32, PV, u32, PV, PU64]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

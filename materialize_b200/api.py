@@ -491,3 +491,15 @@ class TopK(ReduceAccumulable):
 
 def route(key, peers):
     return F.lib.mzgpu_route(key, peers)
+
+
+def partition_many(ctx, bufs, peers):
+    """The device half of an exchange round for `peers` workers (mzgpu_partition_many): returns
+    [(rows grouped by destination, counts per destination)] for each DeviceRows in `bufs`."""
+    k = len(bufs)
+    outs = [DeviceRows(ctx, b.row_bytes) for b in bufs]
+    ins_a = (C.c_void_p * k)(*[b.h for b in bufs])
+    outs_a = (C.c_void_p * k)(*[o.h for o in outs])
+    counts = (C.c_uint64 * (k * peers))()
+    ctx.check(F.lib.mzgpu_partition_many(ctx.h, k, ins_a, peers, outs_a, counts))
+    return [(outs[e].download(), [int(counts[e * peers + p]) for p in range(peers)]) for e in range(k)]

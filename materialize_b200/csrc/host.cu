@@ -2541,6 +2541,47 @@ extern "C" int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** i
   return MZGPU_OK;
 #undef NCCL_TRY
 }
+extern "C" int32_t mzgpu_partition_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, uint32_t peers,
+                                        mzgpu_buf** outs, uint64_t* counts) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (ins == nullptr || outs == nullptr || counts == nullptr || k > MZ_MAX_EXCHANGE || peers == 0 || peers > 64)
+    return MZGPU_E_INVALID;
+  for (uint32_t e = 0; e < k; ++e)
+    if (ins[e] == nullptr || outs[e] == nullptr || ins[e]->rb != outs[e]->rb || ins[e] == outs[e])
+      return MZGPU_E_INVALID;
+  DevMem cnt;
+  MZ_TRY(cnt.alloc(ctx, (size_t)(3 * MZ_MAX_EXCHANGE * 64) * 8));
+  u64* d_cnt = cnt.as<u64>();
+  u64* d_cur = d_cnt + MZ_MAX_EXCHANGE * 64;
+  u64* d_sendT = d_cur + MZ_MAX_EXCHANGE * 64;
+  int rbs[MZ_MAX_EXCHANGE];
+  const void* srcs[MZ_MAX_EXCHANGE];
+  void* dsts[MZ_MAX_EXCHANGE];
+  DLen ns[MZ_MAX_EXCHANGE];
+  u64 ubs[MZ_MAX_EXCHANGE];
+  for (uint32_t e = 0; e < k; ++e) {
+    buf_set_len(outs[e], 0);
+    MZ_TRY(buf_reserve(outs[e], std::max<u64>(ins[e]->ub, 1), false));
+    rbs[e] = (int)ins[e]->rb;
+    srcs[e] = ins[e]->mem.p;
+    dsts[e] = outs[e]->mem.p;
+    ns[e] = buf_dlen(ins[e]);
+    ubs[e] = ins[e]->ub;
+  }
+  MZ_TRY(mz_partition_many(ctx, k, rbs, srcs, ns, ubs, peers, dsts, d_cnt, d_cur, d_sendT));
+  std::vector<u64> h((size_t)k * 64);
+  MZ_TRY(copy_out(ctx, h.data(), d_cnt, h.size() * 8, MZGPU_MEM_HOST));
+  for (uint32_t e = 0; e < k; ++e) {
+    u64 tot = 0;
+    for (uint32_t p = 0; p < peers; ++p) {
+      counts[(size_t)e * peers + p] = h[(size_t)e * 64 + p];
+      tot += h[(size_t)e * 64 + p];
+    }
+    buf_set_len(outs[e], tot);
+  }
+  return MZGPU_OK;
+}
 extern "C" int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out) {
   return mzgpu_exchange_many(ctx, 1, &in, &out);
 }
