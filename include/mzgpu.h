@@ -354,6 +354,47 @@ void mzgpu_batch_release(mzgpu_batch* b); /* drop      */
 /* Cursor walk of the whole batch in (key,val,time) order into caller memory. */
 int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, int32_t mem,
                            uint64_t* n_out);
+/* ---- a8: cursors over a batch (BatchReader::cursor; the walk mz_join_core does at
+ * src/compute/src/render/join/mz_join_core.rs:606-621,816-837 and walk_cursor at
+ * src/compute/src/render/context.rs:1299-1355), in batched form: a round trip to the
+ * device per seek_key would waste the machine, so a seek takes N keys and a scan takes
+ * a page of keys.  A host-side Cursor (rust-shim/src/cursor.rs) keeps the returned
+ * runs and rows and answers get_key / step_key / get_val / step_val / map_times from
+ * them: rows of a run are in (val, time) order, so step_val is "next row whose val
+ * differs" and map_times is "the rows that share the val". */
+typedef struct mzgpu_key_run {
+  uint64_t key;   /* Cursor::key after the seek (valid iff len != 0)            */
+  uint64_t first; /* index of the key's first update row in the batch           */
+  uint64_t len;   /* update rows of that key; 0 = key_valid() is false (the end) */
+} mzgpu_key_run;
+/* Cursor::seek_key for n keys at once: runs[i] describes the first key >= keys[i]
+ * (seek_key's position; exact match iff runs[i].key == keys[i]).  keys / runs live
+ * in `mem` space. */
+int32_t mzgpu_batch_seek_keys(mzgpu_batch* b, const uint64_t* keys, uint64_t n, int32_t mem,
+                              mzgpu_key_run* runs);
+/* Cursor::rewind_keys + step_key in pages: the distinct keys with ordinals
+ * [first_ordinal, first_ordinal + max_keys) in key order, with their runs.
+ * *n_out = keys written (fewer than max_keys at the end of the batch). */
+int32_t mzgpu_batch_key_page(mzgpu_batch* b, uint64_t first_ordinal, uint64_t max_keys, int32_t mem,
+                             mzgpu_key_run* runs, uint64_t* n_out);
+/* The update rows [first, first + len) of the batch in cursor order -- get_val /
+ * step_val / map_times over one or several consecutive key runs -- into caller memory
+ * (rows of the batch's row width). */
+int32_t mzgpu_batch_rows(mzgpu_batch* b, uint64_t first, uint64_t len, void* rows, int32_t mem);
+
+/* ---- a5: Builder::{with_capacity, push, done} (src/timely-util/src/operator.rs:634-677;
+ * OrdValBuilder): chunks of updates are pushed in order, `done` seals them into a batch
+ * with the given description.  The builder accepts any chunk order (it sorts and
+ * consolidates at `done`, which is a no-op on the sorted, consolidated chains a Batcher
+ * hands over), so it also serves as "arrange this collection". */
+typedef struct mzgpu_builder mzgpu_builder;
+int32_t mzgpu_builder_new(mzgpu_ctx* ctx, uint32_t row_bytes, uint64_t capacity_rows, mzgpu_builder** out);
+void mzgpu_builder_free(mzgpu_builder* b);
+int32_t mzgpu_builder_push(mzgpu_builder* b, const void* rows, uint64_t n, int32_t mem);
+int32_t mzgpu_builder_push_buf(mzgpu_builder* b, mzgpu_buf* rows);
+/* Consumes the pushed rows; the builder is empty afterwards and can be reused. */
+int32_t mzgpu_builder_done(mzgpu_builder* b, mzgpu_desc desc, mzgpu_batch** out);
+
 /* Batch::Merger::{begin_merge,work,done} in one call (a7): merge two adjacent
  * batches (b1.upper == b2.lower), advance times by `since`, consolidate. */
 int32_t mzgpu_batch_merge(mzgpu_batch* b1, mzgpu_batch* b2, uint64_t since, mzgpu_batch** out);
@@ -388,6 +429,20 @@ int32_t mzgpu_spine_batches_through(mzgpu_spine* s, uint64_t upper, mzgpu_batch*
  * writes {n_batches, len(b0), len(b1), merge_remaining_work}. */
 int32_t mzgpu_spine_layers(const mzgpu_spine* s, uint64_t* out4, uint32_t cap_layers,
                            uint32_t* n_layers);
+/* ArrangementSize (src/compute/src/extensions/arrange.rs:210-308 logs size, capacity and
+ * allocations of every arrangement through its batches' heap_size): the same three
+ * numbers for this spine's batches (admitted and pending).  size = bytes of live update
+ * rows and occupied index slots, capacity = bytes of the device allocations backing
+ * them, allocations = number of device allocations.  Never waits for the device: a
+ * batch whose length is still in flight counts with its upper bound. */
+typedef struct mzgpu_arrangement_size {
+  uint64_t size_bytes;
+  uint64_t capacity_bytes;
+  uint64_t allocations;
+  uint64_t batches;
+  uint64_t updates; /* sum of batch lengths (upper bound while in flight) */
+} mzgpu_arrangement_size;
+int32_t mzgpu_spine_size(const mzgpu_spine* s, mzgpu_arrangement_size* out);
 /* as_collection / walk_cursor (src/compute/src/render/context.rs:1299-1355):
  * the consolidated contents of the whole trace, times advanced to `since`. */
 int32_t mzgpu_spine_export(mzgpu_spine* s, mzgpu_buf* out);
@@ -406,6 +461,15 @@ int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch* batch, ui
  * results were produced; results (consolidated per work item) are appended to
  * `out`; *done = 1 when the queue is empty. */
 int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out, int32_t* done);
+/* The same with the reference's yield function (YieldSpec,
+ * src/compute/src/render/join/linear_join.rs:145-151: stop after `fuel_rows` of work OR
+ * after a time budget): work stops at the first yield point after `deadline_ns`
+ * (CLOCK_MONOTONIC nanoseconds; 0 = none).  Yield points are between work items AND
+ * inside one: a work item's batch is probed in slices of at most 1M rows
+ * (mz_join_core.rs:862-934 yields inside a key group as well), each slice's results
+ * consolidated and appended before the next starts. */
+int32_t mzgpu_join_core_work_until(mzgpu_join* j, uint64_t fuel_rows, uint64_t deadline_ns, mzgpu_buf* out,
+                                   int32_t* done);
 
 /* --------------------------------------------------- a10: half_join */
 /* dogs3 half_join_internal_unsafe as called at delta_join.rs:401-431: for each

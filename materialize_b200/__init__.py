@@ -25,6 +25,7 @@ from .api import (  # noqa: F401
     ROUT,
     Batch,
     Batcher,
+    Builder,
     Closure,
     Context,
     DeviceRows,

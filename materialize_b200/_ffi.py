@@ -179,7 +179,20 @@ SIGNATURES = {
     "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
     "mzgpu_partition_many": (i32, [vp, u32, PV, u32, PV, PU64]),
+    "mzgpu_batch_seek_keys": (i32, [vp, vp, u64, i32, vp]),
+    "mzgpu_batch_key_page": (i32, [vp, u64, u64, i32, vp, PU64]),
+    "mzgpu_batch_rows": (i32, [vp, u64, u64, vp, i32]),
+    "mzgpu_builder_new": (i32, [vp, u32, u64, PV]),
+    "mzgpu_builder_free": (None, [vp]),
+    "mzgpu_builder_push": (i32, [vp, vp, u64, i32]),
+    "mzgpu_builder_push_buf": (i32, [vp, vp]),
+    "mzgpu_builder_done": (i32, [vp, Desc, PV]),
+    "mzgpu_spine_size": (i32, [vp, vp]),
+    "mzgpu_join_core_work_until": (i32, [vp, u64, u64, vp, PI32]),
 }
+
+KEY_RUN = np.dtype([("key", "<u8"), ("first", "<u8"), ("len", "<u8")])
+ARRANGEMENT_SIZE = np.dtype([("size_bytes", "<u8"), ("capacity_bytes", "<u8"), ("allocations", "<u8"), ("batches", "<u8"), ("updates", "<u8")])
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the .so does not export a declared symbol

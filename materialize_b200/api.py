@@ -236,9 +236,59 @@ class Batch:
         self.ctx.check(F.lib.mzgpu_batch_merge(self.h, other.h, since, C.byref(h)))
         return Batch(self.ctx, h, self.row_bytes)
 
+    # -- a8: batched cursor calls
+    def seek_keys(self, keys):
+        """Cursor::seek_key for every key: array of (key found, first row, rows of that key);
+        len == 0 where the cursor ran off the end."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        runs = np.zeros(len(keys), dtype=F.KEY_RUN)
+        self.ctx.check(F.lib.mzgpu_batch_seek_keys(self.h, _ptr(keys), len(keys), F.MEM_HOST, _ptr(runs)))
+        return runs
+
+    def key_page(self, first_ordinal, max_keys):
+        """step_key in pages: the distinct keys [first_ordinal, first_ordinal + max_keys) with their runs."""
+        runs = np.zeros(max_keys, dtype=F.KEY_RUN)
+        n = C.c_uint64(0)
+        self.ctx.check(F.lib.mzgpu_batch_key_page(self.h, first_ordinal, max_keys, F.MEM_HOST, _ptr(runs), C.byref(n)))
+        return runs[: n.value]
+
+    def rows_range(self, first, length):
+        """The update rows [first, first + length) in cursor order (get_val / step_val / map_times)."""
+        out = np.zeros(length, dtype=F.DTYPES[self.row_bytes])
+        self.ctx.check(F.lib.mzgpu_batch_rows(self.h, first, length, _ptr(out), F.MEM_HOST))
+        return out
+
     def __del__(self):
         if getattr(self, "h", None) and self.ctx.h:
             F.lib.mzgpu_batch_release(self.h)
+            self.h = None
+
+
+class Builder:
+    """Builder::{push, done} (OrdValBuilder): chunks in, one batch out."""
+
+    def __init__(self, ctx, row_bytes=32, capacity=0):
+        self.ctx, self.row_bytes = ctx, row_bytes
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_builder_new(ctx.h, row_bytes, capacity, C.byref(h)))
+        self.h = h
+
+    def push(self, rows):
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype.itemsize == self.row_bytes
+        self.ctx.check(F.lib.mzgpu_builder_push(self.h, _ptr(rows), len(rows), F.MEM_HOST))
+
+    def push_buf(self, dev_rows):
+        self.ctx.check(F.lib.mzgpu_builder_push_buf(self.h, dev_rows.h))
+
+    def done(self, lower, upper, since=0):
+        h = C.c_void_p()
+        self.ctx.check(F.lib.mzgpu_builder_done(self.h, F.Desc(lower, upper, since), C.byref(h)))
+        return Batch(self.ctx, h, self.row_bytes)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_builder_free(self.h)
             self.h = None
 
 
@@ -336,6 +386,12 @@ class Spine:
         self.ctx.check(F.lib.mzgpu_spine_layers(self.h, out, 64, C.byref(n)))
         return [tuple(int(out[4 * i + j]) for j in range(4)) for i in range(n.value)]
 
+    def size(self):
+        """ArrangementSize: {size_bytes, capacity_bytes, allocations, batches, updates}."""
+        out = np.zeros(1, dtype=F.ARRANGEMENT_SIZE)
+        self.ctx.check(F.lib.mzgpu_spine_size(self.h, _ptr(out)))
+        return {k: int(out[k][0]) for k in out.dtype.names}
+
     def export(self):
         """as_collection: consolidated contents, times advanced to `since`."""
         buf = DeviceRows(self.ctx, self.row_bytes)
@@ -365,6 +421,13 @@ class JoinCore:
     def work(self, fuel_rows=1 << 62):
         done = C.c_int32(0)
         self.ctx.check(F.lib.mzgpu_join_core_work(self.h, fuel_rows, self.out.h, C.byref(done)))
+        return bool(done.value)
+
+    def work_until(self, fuel_rows, deadline_ns):
+        """Work::process with the reference's yield function: stop after fuel_rows of results or at the
+        first yield point after deadline_ns (time.monotonic_ns() clock; 0 = no deadline)."""
+        done = C.c_int32(0)
+        self.ctx.check(F.lib.mzgpu_join_core_work_until(self.h, fuel_rows, deadline_ns, self.out.h, C.byref(done)))
         return bool(done.value)
 
     def results(self):

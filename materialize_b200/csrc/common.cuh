@@ -702,6 +702,11 @@ int32_t mz_count_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, 
 int32_t mz_build_index(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n, u64 n_keys,
                        DevMem* table, u64* table_slots);
 
+int32_t mz_seek_keys(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, DLen n, const u64* d_probe, u64 n_probe,
+                     u64* d_out);
+int32_t mz_key_page(mzgpu_ctx* ctx, int row_bytes, const void* d_rows, u64 n_rows, u64 first_ordinal, u64 max_keys,
+                    u64* d_out);
+
 // probe.cu
 struct BatchView {  // device-visible description of one batch of a trace
   const u64* rows;

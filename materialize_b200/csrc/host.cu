@@ -824,6 +824,116 @@ extern "C" int32_t mzgpu_batch_export(mzgpu_batch* b, void* rows, uint64_t cap, 
   MZ_TRY(copy_out(b->ctx, rows, b->rows.p, len * b->rb, mem));
   return MZGPU_OK;
 }
+// ---- a8: batched cursor calls
+extern "C" int32_t mzgpu_batch_seek_keys(mzgpu_batch* b, const uint64_t* keys, uint64_t n, int32_t mem,
+                                         mzgpu_key_run* runs) {
+  if (b == nullptr || (n && (keys == nullptr || runs == nullptr))) return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = b->ctx;
+  MZ_CHECK_CTX(ctx);
+  if (n == 0) return MZGPU_OK;
+  MZ_TRY(batch_ready(b));
+  DevMem dk, dr;
+  const u64* d_keys = keys;
+  u64* d_runs = (u64*)runs;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(dk.alloc(ctx, n * 8));
+    MZ_TRY(dr.alloc(ctx, n * sizeof(mzgpu_key_run)));
+    MZ_TRY(copy_in(ctx, dk.p, keys, n * 8, mem));
+    d_keys = dk.as<u64>();
+    d_runs = dr.as<u64>();
+  }
+  MZ_TRY(mz_seek_keys(ctx, (int)b->rb, b->rows.p, batch_dlen(b), d_keys, n, d_runs));
+  if (mem == MZGPU_MEM_HOST) MZ_TRY(copy_out(ctx, runs, d_runs, n * sizeof(mzgpu_key_run), mem));
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_batch_key_page(mzgpu_batch* b, uint64_t first_ordinal, uint64_t max_keys, int32_t mem,
+                                        mzgpu_key_run* runs, uint64_t* n_out) {
+  if (b == nullptr || (max_keys && runs == nullptr)) return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = b->ctx;
+  MZ_CHECK_CTX(ctx);
+  MZ_TRY(batch_ready(b));
+  MZ_TRY(batch_resolve(b));
+  const u64 n_keys = b->st.v[2];
+  u64 avail = first_ordinal < n_keys ? n_keys - first_ordinal : 0;
+  if (avail > max_keys) avail = max_keys;
+  if (n_out) *n_out = avail;
+  if (avail == 0) return MZGPU_OK;
+  DevMem dr;
+  u64* d_runs = (u64*)runs;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(dr.alloc(ctx, avail * sizeof(mzgpu_key_run)));
+    d_runs = dr.as<u64>();
+  }
+  MZ_TRY(mz_key_page(ctx, (int)b->rb, b->rows.p, b->st.v[0], first_ordinal, avail, d_runs));
+  if (mem == MZGPU_MEM_HOST) MZ_TRY(copy_out(ctx, runs, d_runs, avail * sizeof(mzgpu_key_run), mem));
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_batch_rows(mzgpu_batch* b, uint64_t first, uint64_t len, void* rows, int32_t mem) {
+  if (b == nullptr || (len && rows == nullptr)) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(b->ctx);
+  if (len == 0) return MZGPU_OK;
+  MZ_TRY(batch_ready(b));
+  MZ_TRY(batch_resolve(b));
+  if (first > b->st.v[0] || len > b->st.v[0] - first) {
+    MZ_SET_ERR(b->ctx, "batch_rows: [%llu, +%llu) is outside the batch's %llu rows", (unsigned long long)first,
+               (unsigned long long)len, (unsigned long long)b->st.v[0]);
+    return MZGPU_E_INVALID;
+  }
+  return copy_out(b->ctx, rows, (const char*)b->rows.p + first * b->rb, len * b->rb, mem);
+}
+
+// ---- a5: Builder::{push, done}
+struct mzgpu_builder {
+  mzgpu_ctx* ctx;
+  uint32_t rb;
+  mzgpu_buf rows;
+};
+extern "C" int32_t mzgpu_builder_new(mzgpu_ctx* ctx, uint32_t row_bytes, uint64_t capacity_rows,
+                                     mzgpu_builder** out) {
+  MZ_CHECK_CTX(ctx);
+  if (out == nullptr || (row_bytes != 32 && row_bytes != 80)) return MZGPU_E_INVALID;
+  std::unique_ptr<mzgpu_builder> b(new mzgpu_builder());
+  b->ctx = ctx;
+  b->rb = row_bytes;
+  b->rows.ctx = ctx;
+  b->rows.rb = row_bytes;
+  buf_set_len(&b->rows, 0);
+  if (capacity_rows) MZ_TRY(buf_reserve(&b->rows, capacity_rows, false));
+  *out = b.release();
+  return MZGPU_OK;
+}
+extern "C" void mzgpu_builder_free(mzgpu_builder* b) { delete b; }
+extern "C" int32_t mzgpu_builder_push(mzgpu_builder* b, const void* rows, uint64_t n, int32_t mem) {
+  if (b == nullptr || (rows == nullptr && n)) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(b->ctx);
+  if (n == 0) return MZGPU_OK;
+  if (mem == MZGPU_MEM_DEVICE) return buf_append_dev(&b->rows, rows, dlen_imm(n), n);
+  MZ_TRY(buf_resolve(&b->rows));
+  MZ_TRY(buf_reserve(&b->rows, b->rows.ub + n, true));
+  MZ_TRY(copy_in(b->ctx, (char*)b->rows.mem.p + b->rows.ub * b->rb, rows, n * b->rb, mem));
+  buf_set_len(&b->rows, b->rows.ub + n);
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_builder_push_buf(mzgpu_builder* b, mzgpu_buf* rows) {
+  if (b == nullptr || rows == nullptr || rows->rb != b->rb) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(b->ctx);
+  return buf_append_dev(&b->rows, rows->mem.p, buf_dlen(rows), rows->ub);
+}
+extern "C" int32_t mzgpu_builder_done(mzgpu_builder* b, mzgpu_desc desc, mzgpu_batch** out) {
+  if (b == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = b->ctx;
+  MZ_CHECK_CTX(ctx);
+  int32_t st;
+  if (b->rows.ub == 0) {
+    st = make_empty_batch(ctx, b->rb, desc, out);
+  } else {
+    ctx->stats.rows_in += b->rows.ub;
+    st = build_batch_from_unsorted(ctx, b->rb, b->rows.mem.p, buf_dlen(&b->rows), b->rows.ub, desc, out);
+  }
+  buf_set_len(&b->rows, 0);  // (the storage is kept for the next batch; the build read it in stream order)
+  return st;
+}
+
 // Batch::Merger in one step: union, advance_by(since), consolidate, index.
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
@@ -1684,6 +1794,24 @@ static int32_t trace_fanout(const std::vector<mzgpu_batch*>& batches, u64* fan, 
   return MZGPU_OK;
 }
 
+extern "C" int32_t mzgpu_spine_size(const mzgpu_spine* s, mzgpu_arrangement_size* out) {
+  if (s == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  std::vector<mzgpu_batch*> all;
+  s->all_batches(all);
+  for (auto* b : all) {
+    b->st.try_resolve();  // (never waits)
+    const u64 len = b->st.known ? b->st.v[0] : b->len_ub;
+    const u64 keys = b->st.known ? b->st.v[2] : 0;
+    out->batches++;
+    out->updates += len;
+    out->size_bytes += len * b->rb + keys * sizeof(HashSlot);
+    out->capacity_bytes += b->rows.bytes + b->table.bytes;
+    out->allocations += (b->rows.p != nullptr ? 1 : 0) + (b->table.p != nullptr ? 1 : 0);
+  }
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_spine_export(mzgpu_spine* s, mzgpu_buf* out) {
   if (s == nullptr || out == nullptr || out->rb != s->rb) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(s->ctx);
@@ -1718,6 +1846,7 @@ struct mzgpu_join {
     mzgpu_batch* batch;
     std::vector<mzgpu_batch*> others;
     u64 cap;
+    u64 pos = 0;  // rows of `batch` already joined (a work item is probed in slices)
   };
   std::deque<Work> todo;
   void release_work(Work& w) {
@@ -1785,8 +1914,15 @@ extern "C" int32_t mzgpu_join_core_push(mzgpu_join* j, int32_t side, mzgpu_batch
 
 // bulk probes (join_core work items): the bounded single-pass form may take this much output memory
 #define MZ_BULK_BOUND_BYTES (12ull << 30)
-extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out,
-                                        int32_t* done) {
+static u64 mono_ns() {
+  return (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+// rows of a work item's batch probed per slice: the reference's yield budget is 1M rows of work
+// (linear_join.rs:145-151), so a bulk work item (hydration: 10M x 10M rows) yields ~10 times
+#define MZ_JOIN_SLICE_ROWS (1ull << 20)
+extern "C" int32_t mzgpu_join_core_work_until(mzgpu_join* j, uint64_t fuel_rows, uint64_t deadline_ns,
+                                              mzgpu_buf* out, int32_t* done) {
   if (j == nullptr || out == nullptr) return MZGPU_E_INVALID;
   MZ_CHECK_CTX(j->ctx);
   const uint32_t out_rb = j->has_closure ? 32 : 40;
@@ -1795,7 +1931,7 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     return MZGPU_E_INVALID;
   }
   u64 produced = 0;
-  while (!j->todo.empty() && produced < fuel_rows) {
+  while (!j->todo.empty() && produced < fuel_rows && (deadline_ns == 0 || mono_ns() < deadline_ns)) {
     // the item leaves the queue only once its output has been appended: a failure below (more
     // batches than a trace view holds, counter arena, ...) leaves it queued, so no join work is lost
     mzgpu_join::Work& w = j->todo.front();
@@ -1809,7 +1945,11 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     DevMem res, cons;
     u64 n_res = 0, ccap = 0;
     Lazy4 clen;
-    if (st == MZGPU_OK) {
+    // this slice: rows [w.pos, w.pos + n_probe) of the work item's batch
+    const u64 n_total = st == MZGPU_OK ? w.batch->st.v[0] : 0;
+    const u64 n_probe = std::min<u64>(n_total - std::min(n_total, w.pos), MZ_JOIN_SLICE_ROWS);
+    const u64* d_probe = w.batch->rows.as<u64>() + w.pos * 4;
+    if (st == MZGPU_OK && n_probe > 0) {
       ProbeParams pp;
       memset(&pp, 0, sizeof(pp));
       pp.mode = MZ_PROBE_JOIN;
@@ -1823,8 +1963,7 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
       u64 fan = 0;
       bool exact = true;
       st = trace_fanout(w.others, &fan, &exact);
-      const u64 n_probe = w.batch->st.v[0];
-      const bool bounded = st == MZGPU_OK && exact && fan > 0 && n_probe > 0 &&
+      const bool bounded = st == MZGPU_OK && exact && fan > 0 &&
                            n_probe <= MZ_BULK_BOUND_BYTES / (fan * out_rb) && (n_probe + 255) / 256 <= MZ_LB_TILES;
       if (st == MZGPU_OK && bounded) {
         Lazy4 rlen;
@@ -1832,14 +1971,14 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
         st = res.alloc(j->ctx, bound * out_rb);
         if (st == MZGPU_OK) st = rlen.make_pending(j->ctx);
         if (st == MZGPU_OK) {
-          st = mz_probe_async(j->ctx, w.batch->rows.as<u64>(), dlen_imm(n_probe), n_probe, tv, pp, res.as<u64>(),
-                              dlen_imm(0), bound, rlen.dptr());
+          st = mz_probe_async(j->ctx, d_probe, dlen_imm(n_probe), n_probe, tv, pp, res.as<u64>(), dlen_imm(0), bound,
+                              rlen.dptr());
           rlen.mark_written();
         }
         if (st == MZGPU_OK) st = rlen.resolve();
         if (st == MZGPU_OK) n_res = rlen.v[0];
       } else if (st == MZGPU_OK) {
-        st = mz_probe(j->ctx, w.batch->rows.as<u64>(), n_probe, tv, pp, &res, &n_res);
+        st = mz_probe(j->ctx, d_probe, n_probe, tv, pp, &res, &n_res);
       }
     }
     // Work::process consolidates each work item's output buffer before sending
@@ -1849,13 +1988,19 @@ extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu
     const u64 n_cons = n_res ? clen.v[0] : 0;
     if (st == MZGPU_OK && n_cons) st = buf_append_dev(out, cons.p, dlen_imm(n_cons), n_cons);
     if (st != MZGPU_OK) return st;
-    j->release_work(w);
-    j->todo.pop_front();
+    w.pos += n_probe;
+    if (w.pos >= n_total) {
+      j->release_work(w);
+      j->todo.pop_front();
+    }
     produced += n_cons;
     j->ctx->stats.rows_out += n_cons;
   }
   if (done) *done = j->todo.empty() ? 1 : 0;
   return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_join_core_work(mzgpu_join* j, uint64_t fuel_rows, mzgpu_buf* out, int32_t* done) {
+  return mzgpu_join_core_work_until(j, fuel_rows, 0, out, done);
 }
 
 // ================================================================ half_join

@@ -319,6 +319,120 @@ def test_spine_structure_and_contents_match_oracle(mz, ctx, oracle):
     same(gs.export(), os_.export())
 
 
+# ----------------------------------------------------------------- a8 / a5
+def test_batched_cursor_matches_the_oracle_batch(mz, ctx, oracle):
+    """Cursor surface (a8): seek_key for many keys at once, step_key in pages, map_times over runs.
+    A host-side cursor built from these calls walks the batch exactly as the oracle's OrdValBatch
+    cursor does (same keys, same (val, time, diff) sequence per key)."""
+    rng = np.random.default_rng(410)
+    a = rand_r32(rng, 60000, 5000, 40, 6, dtype=oracle.R32)
+    a["key"] *= np.uint64(0x9E3779B97F4A7C15 >> 20)  # spread over the u64 range, gaps between keys
+    gb, ob = mz.Batch.build(ctx, a, 0, 6), oracle.Batch.build(a, 0, 6)
+    rows = ob.rows()
+    same(gb.rows(), rows)
+    keys = np.unique(rows["key"])
+    # seek: present keys, absent keys (gaps), below the first, beyond the last
+    probe = np.concatenate([keys[::7], keys[::11] + np.uint64(1), [0, keys[0], keys[-1], keys[-1] + np.uint64(1), (1 << 64) - 1]]).astype(np.uint64)
+    runs = gb.seek_keys(probe)
+    for k, r in zip(probe.tolist(), runs):
+        lo = int(np.searchsorted(rows["key"], np.uint64(k), side="left"))
+        if lo == len(rows):
+            assert int(r["len"]) == 0
+            continue
+        found = int(rows["key"][lo])
+        hi = int(np.searchsorted(rows["key"], np.uint64(found), side="right"))
+        assert (int(r["key"]), int(r["first"]), int(r["len"])) == (found, lo, hi - lo)
+    assert len(gb.seek_keys(np.zeros(0, dtype=np.uint64))) == 0
+    # step_key paging covers every distinct key once, in order, with its run
+    pages, at = [], 0
+    while True:
+        pg = gb.key_page(at, 777)
+        if len(pg) == 0:
+            break
+        pages.append(pg)
+        at += len(pg)
+    allk = np.concatenate(pages)
+    assert allk["key"].tolist() == keys.tolist() and at == gb.keys()
+    assert int(allk["len"].sum()) == len(rows)
+    assert (allk["first"][1:] == allk["first"][:-1] + allk["len"][:-1]).all()
+    # map_times over runs: the rows of a few key runs (and of several consecutive runs at once)
+    for r in allk[:: max(1, len(allk) // 40)]:
+        same(gb.rows_range(int(r["first"]), int(r["len"])), rows[int(r["first"]) : int(r["first"]) + int(r["len"])])
+    same(gb.rows_range(int(allk["first"][3]), int(allk["len"][3:9].sum())), rows[int(allk["first"][3]) : int(allk["first"][9])])
+    with pytest.raises(mz.MzGpuError):
+        gb.rows_range(len(rows) - 1, 5)
+    # an empty batch: every seek is at the end
+    eb = mz.Batch.build(ctx, a[:0], 6, 7)
+    assert int(eb.seek_keys(np.array([5], dtype=np.uint64))["len"][0]) == 0 and len(eb.key_page(0, 10)) == 0
+
+
+def test_builder_push_done_matches_batch_build(mz, ctx, oracle):
+    """Builder::{push, done} (a5): chunks pushed in any order seal into the batch the oracle builds
+    from the same updates; the builder is reusable; sizes are reported per arrangement."""
+    rng = np.random.default_rng(411)
+    a = rand_r32(rng, 30000, 900, 12, 4, dtype=oracle.R32)
+    bld = mz.Builder(ctx, 32, capacity=1000)
+    for chunk in np.array_split(a, 7):
+        bld.push(chunk)
+    gb = bld.done(0, 4)
+    ob = oracle.Batch.build(a, 0, 4)
+    same(gb.rows(), ob.rows())
+    assert gb.desc() == (0, 4, 0) and gb.keys() == ob.keys()
+    # reuse, device-resident chunk, empty batch
+    b2 = rand_r32(rng, 5000, 100, 3, 1, dtype=oracle.R32)
+    b2["time"] += 4
+    bld.push_buf(mz.DeviceRows(ctx, 32).upload(b2))
+    g2 = bld.done(4, 5)
+    same(g2.rows(), oracle.Batch.build(b2, 4, 5).rows())
+    assert len(bld.done(5, 6)) == 0
+    gs = mz.Spine(ctx, 32)
+    gs.insert(gb)
+    gs.insert(g2)
+    gs.set_physical_compaction(5)
+    sz = gs.size()
+    assert sz["updates"] == len(gb) + len(g2) or sz["batches"] == 1  # (merged or not, nothing lost)
+    assert sz["size_bytes"] >= 32 * sz["updates"] and sz["capacity_bytes"] >= sz["size_bytes"] - 16 * (gb.keys() + g2.keys())
+    assert sz["allocations"] >= 2 * sz["batches"] and sz["batches"] >= 1
+
+
+def test_join_core_yields_inside_a_work_item(mz, ctx, oracle):
+    """mzgpu_join_core_work_until: a deadline in the past stops after ONE slice of one work item
+    (the yield point inside a work item); repeated calls finish the work and the result equals
+    the oracle's."""
+    import time
+
+    rng = np.random.default_rng(412)
+    n = (1 << 20) + 50000  # more than one slice
+    a = np.zeros(n, dtype=oracle.R32)
+    a["key"] = rng.integers(0, 200000, size=n, dtype=np.uint64)
+    a["val"] = rng.integers(0, 3, size=n, dtype=np.uint64)
+    a["diff"] = 1
+    b = a[:70000].copy()
+    b["val"] += 10
+    g1, g2 = mz.Spine(ctx, 32), mz.Spine(ctx, 32)
+    o1, o2 = oracle.Spine(32, 1, True), oracle.Spine(32, 1, True)
+    ga, gbb = mz.Batch.build(ctx, a, 0, 1), mz.Batch.build(ctx, b, 0, 1)
+    oa, obb = oracle.Batch.build(a, 0, 1), oracle.Batch.build(b, 0, 1)
+    g2.insert(gbb)
+    o2.insert(obb)
+    gj, oj = mz.JoinCore(ctx, g1, g2), oracle.Join(o1, o2)
+    g1.insert(ga)
+    o1.insert(oa)
+    gj.push(0, ga, 0)
+    oj.push(0, oa, 0)
+    calls, done = 0, False
+    while not done:
+        done = gj.work_until(1 << 62, 1)  # deadline long past: one slice per call
+        calls += 1
+        assert calls < 10
+    assert calls >= 2  # the single work item took more than one call
+    oj.work()
+    same(oracle.consolidate(gj.results()), oracle.consolidate(oj.results()))
+    # a generous deadline finishes in one call
+    gj2 = mz.JoinCore(ctx, g1, g2)
+    assert gj2.work_until(1 << 62, time.monotonic_ns() + 60_000_000_000)
+
+
 # ----------------------------------------------------------------- a9
 def brute_join(a, b, cap):
     """All pairs per key: (key, v1, v2, max(t1, t2, cap), d1*d2), consolidated by the caller."""
