@@ -1,0 +1,96 @@
+//! FFI declarations for libmzgpu.so (include/mzgpu.h).  UNCOMPILED: see ../README.md.
+#![allow(non_camel_case_types, dead_code)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)] #[derive(Clone, Copy, Debug, Default, PartialEq, Eq, PartialOrd, Ord)]
+pub struct R32 { pub key: u64, pub val: u64, pub time: u64, pub diff: i64 }
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)]
+pub struct Desc { pub lower: u64, pub upper: u64, pub since: u64 }
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)]
+pub struct KeyRun { pub key: u64, pub first: u64, pub len: u64 }
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)]
+pub struct ArrangementSize { pub size_bytes: u64, pub capacity_bytes: u64, pub allocations: u64, pub batches: u64, pub updates: u64 }
+#[repr(C)] pub struct Closure { _b: [u8; 144] }
+
+pub enum Ctx {} pub enum Buf {} pub enum Batcher {} pub enum Builder {} pub enum Batch {}
+pub enum Spine {} pub enum Join {} pub enum Reduce {}
+
+pub const OK: i32 = 0;
+pub const E_INVALID: i32 = -1;
+pub const E_CUDA: i32 = -2;
+pub const E_CAPACITY: i32 = -3;
+pub const E_UNSUPPORTED: i32 = -4;
+pub const E_NCCL: i32 = -5;
+pub const E_FRONTIER: i32 = -6;
+pub const MEM_HOST: i32 = 0;
+pub const MEM_DEVICE: i32 = 1;
+pub const FRONTIER_EMPTY: u64 = u64::MAX;
+pub const ROW_R32: u32 = 32;
+
+#[link(name = "mzgpu")]
+extern "C" {
+    pub fn mzgpu_ctx_create(device: i32, worker_index: i32, peers: i32, out: *mut *mut Ctx) -> i32;
+    pub fn mzgpu_ctx_destroy(ctx: *mut Ctx);
+    pub fn mzgpu_ctx_sync(ctx: *mut Ctx) -> i32;
+    pub fn mzgpu_last_error(ctx: *mut Ctx) -> *const c_char;
+    // a2-a4: batcher
+    pub fn mzgpu_batcher_new(ctx: *mut Ctx, row_bytes: u32, out: *mut *mut Batcher) -> i32;
+    pub fn mzgpu_batcher_free(b: *mut Batcher);
+    pub fn mzgpu_batcher_push(b: *mut Batcher, rows: *const c_void, n: u64, mem: i32) -> i32;
+    pub fn mzgpu_batcher_seal(b: *mut Batcher, upper: u64, batch: *mut *mut Batch, new_lower: *mut u64) -> i32;
+    pub fn mzgpu_batcher_frontier(b: *mut Batcher) -> u64;
+    // a5: builder, batches
+    pub fn mzgpu_builder_new(ctx: *mut Ctx, row_bytes: u32, capacity_rows: u64, out: *mut *mut Builder) -> i32;
+    pub fn mzgpu_builder_free(b: *mut Builder);
+    pub fn mzgpu_builder_push(b: *mut Builder, rows: *const c_void, n: u64, mem: i32) -> i32;
+    pub fn mzgpu_builder_done(b: *mut Builder, desc: Desc, out: *mut *mut Batch) -> i32;
+    pub fn mzgpu_batch_len(b: *const Batch) -> u64;
+    pub fn mzgpu_batch_keys(b: *const Batch) -> u64;
+    pub fn mzgpu_batch_desc(b: *const Batch) -> Desc;
+    pub fn mzgpu_batch_retain(b: *mut Batch);
+    pub fn mzgpu_batch_release(b: *mut Batch);
+    pub fn mzgpu_batch_merge(b1: *mut Batch, b2: *mut Batch, since: u64, out: *mut *mut Batch) -> i32;
+    // a8: cursors (batched)
+    pub fn mzgpu_batch_seek_keys(b: *mut Batch, keys: *const u64, n: u64, mem: i32, runs: *mut KeyRun) -> i32;
+    pub fn mzgpu_batch_key_page(b: *mut Batch, first_ordinal: u64, max_keys: u64, mem: i32, runs: *mut KeyRun, n_out: *mut u64) -> i32;
+    pub fn mzgpu_batch_rows(b: *mut Batch, first: u64, len: u64, rows: *mut c_void, mem: i32) -> i32;
+    // a6, a14: spine
+    pub fn mzgpu_spine_new(ctx: *mut Ctx, row_bytes: u32, effort: u32, out: *mut *mut Spine) -> i32;
+    pub fn mzgpu_spine_free(s: *mut Spine);
+    pub fn mzgpu_spine_insert(s: *mut Spine, batch: *mut Batch) -> i32;
+    pub fn mzgpu_spine_exert(s: *mut Spine, effort: u64, did_work: *mut i32) -> i32;
+    pub fn mzgpu_spine_exert_logic(s: *const Spine, proportionality: u32) -> u64;
+    pub fn mzgpu_spine_set_logical_compaction(s: *mut Spine, frontier: u64) -> i32;
+    pub fn mzgpu_spine_set_physical_compaction(s: *mut Spine, frontier: u64) -> i32;
+    pub fn mzgpu_spine_get_logical_compaction(s: *const Spine) -> u64;
+    pub fn mzgpu_spine_get_physical_compaction(s: *const Spine) -> u64;
+    pub fn mzgpu_spine_read_upper(s: *const Spine) -> u64;
+    pub fn mzgpu_spine_batches_through(s: *mut Spine, upper: u64, batches: *mut *mut Batch, cap: u32, n_out: *mut u32) -> i32;
+    pub fn mzgpu_spine_size(s: *const Spine, out: *mut ArrangementSize) -> i32;
+    // a9, a10: joins
+    pub fn mzgpu_join_new(ctx: *mut Ctx, t1: *mut Spine, t2: *mut Spine, c: *const Closure, out: *mut *mut Join) -> i32;
+    pub fn mzgpu_join_free(j: *mut Join);
+    pub fn mzgpu_join_core_push(j: *mut Join, side: i32, batch: *mut Batch, cap: u64) -> i32;
+    pub fn mzgpu_join_core_work_until(j: *mut Join, fuel_rows: u64, deadline_ns: u64, out: *mut Buf, done: *mut i32) -> i32;
+    pub fn mzgpu_half_join(ctx: *mut Ctx, stream: *const R32, n: u64, mem: i32, trace: *mut Spine, cmp_mode: i32,
+                           closure: *const Closure, consolidate: i32, out: *mut Buf) -> i32;
+    // a11, a12: reduce
+    pub fn mzgpu_reduce_new(ctx: *mut Ctx, agg_kind: i32, out: *mut *mut Reduce) -> i32;
+    pub fn mzgpu_reduce_free(r: *mut Reduce);
+    pub fn mzgpu_reduce_accumulable(r: *mut Reduce, rows: *const R32, n: u64, mem: i32, upper: u64, out: *mut Buf) -> i32;
+    // buffers
+    pub fn mzgpu_buf_new(ctx: *mut Ctx, row_bytes: u32, out: *mut *mut Buf) -> i32;
+    pub fn mzgpu_buf_free(b: *mut Buf);
+    pub fn mzgpu_buf_len(b: *mut Buf) -> u64;
+    pub fn mzgpu_buf_download(b: *mut Buf, rows: *mut c_void, cap: u64, mem: i32, n_out: *mut u64) -> i32;
+    pub fn mzgpu_buf_clear(b: *mut Buf) -> i32;
+}
+
+/// Status -> Result; CUDA / NCCL failures are sticky: the caller panics the worker (compute state
+/// is soft, the replica rehydrates: src/cluster/src/communication.rs:18-27).
+pub unsafe fn check(ctx: *mut Ctx, st: i32) -> Result<(), (i32, String)> {
+    if st == OK { return Ok(()); }
+    let msg = std::ffi::CStr::from_ptr(mzgpu_last_error(ctx)).to_string_lossy().into_owned();
+    if st == E_CUDA || st == E_NCCL { panic!("mzgpu: sticky device failure {st}: {msg}"); }
+    Err((st, msg))
+}
