@@ -752,6 +752,15 @@ struct ProbeJobHost {
   u64* d_out_len;
 };
 int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs);
+// tiles the single-pass probe cuts `n_ub` probe rows into (rows per tile shrink with the trace's
+// batch count so that a tile's hit list fits in shared memory)
+static inline u64 mz_probe_tile_rows(u32 n_batches) {
+  return n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
+}
+static inline u64 mz_probe_tiles(u64 n_ub, u32 n_batches) {
+  const u64 tr = mz_probe_tile_rows(n_batches);
+  return (n_ub + tr - 1) / tr;
+}
 // Probe `n` R32 stream rows against the trace; appends results to d_out
 // (allocated here) and returns the count.  One sync (to size the output).
 int32_t mz_probe(mzgpu_ctx* ctx, const u64* d_stream, u64 n, const TraceView& trace,

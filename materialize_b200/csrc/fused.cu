@@ -1522,7 +1522,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
 }
 
 template <int RB>
-__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_consolidate(const FusedArgs a) {
+__global__ void __launch_bounds__(FT, (RB == 80 ? 2 : 4)) k_fused_consolidate(const FusedArgs a) {
   fused_body<RB>(a, blockIdx.x, gridDim.x);
 }
 
@@ -1537,7 +1537,7 @@ struct FusedMany {
   FusedArgs job[FUSED_MANY_MAX];
 };
 template <int RB>
-__global__ void __launch_bounds__(FT, (RB == 80 ? 1 : 2)) k_fused_many(const __grid_constant__ FusedMany m) {
+__global__ void __launch_bounds__(FT, (RB == 80 ? 2 : 4)) k_fused_many(const __grid_constant__ FusedMany m) {
   u32 j = 0;
   while (j + 1 < m.k && blockIdx.x >= m.start[j + 1]) ++j;
   fused_body<RB>(m.job[j], blockIdx.x - m.start[j], m.start[j + 1] - m.start[j]);
@@ -1680,7 +1680,9 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   // With the side stream in use a launch takes at most one CTA slot per SM, so that a merge on
   // the side stream and a seal on the main stream can be co-resident (cooperative launches
   // only start when the whole grid fits).
-  a.max_g = (ctx->use_side ? 1u : 2u) * (u32)ctx->num_sms;
+  // (64 registers per thread: four CTAs per SM are resident, 592 on a B200; the bucket phase
+  // wants one warp per bucket, and a 160K-row merge has 4096 of them)
+  a.max_g = ctx->use_side ? (u32)ctx->num_sms : (u32)max_ctas;
   if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
   const unsigned a_max_g_host = a.max_g;
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);
@@ -1731,7 +1733,7 @@ int32_t fused_launch_many(mzgpu_ctx* ctx, int k, const FusedArgs* args, const u6
   m.k = (u32)k;
   u64 want[FUSED_MANY_MAX];
   u64 want_sum = 0;
-  const u64 solo_max = std::min<u64>(2ull * (u64)ctx->num_sms, (u64)max_ctas);
+  const u64 solo_max = (u64)max_ctas;
   for (int j = 0; j < k; ++j) {
     m.job[j] = args[j];
     want[j] = want_in[j] > solo_max ? solo_max : want_in[j];

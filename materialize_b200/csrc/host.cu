@@ -1964,7 +1964,7 @@ extern "C" int32_t mzgpu_join_core_work_until(mzgpu_join* j, uint64_t fuel_rows,
       bool exact = true;
       st = trace_fanout(w.others, &fan, &exact);
       const bool bounded = st == MZGPU_OK && exact && fan > 0 &&
-                           n_probe <= MZ_BULK_BOUND_BYTES / (fan * out_rb) && (n_probe + 255) / 256 <= MZ_LB_TILES;
+                           n_probe <= MZ_BULK_BOUND_BYTES / (fan * out_rb) && mz_probe_tiles(n_probe, tv.n_batches) <= MZ_LB_TILES;
       if (st == MZGPU_OK && bounded) {
         Lazy4 rlen;
         const u64 bound = n_probe * fan;
@@ -2036,7 +2036,7 @@ static int32_t half_join_dev(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_
     pp.closure.val_fields[0] = mzgpu_field{MZGPU_SRC_VAL2, 0, 64, 0};
   }
   const bool bounded = exact && fan > 0 && n_ub <= MZ_BOUND_MAX_ROWS / fan &&
-                       (n_ub + 255) / 256 <= MZ_LB_TILES;
+                       mz_probe_tiles(n_ub, tv.n_batches) <= MZ_LB_TILES;
   if (bounded) {
     const u64 bound = n_ub * fan;
     if (!consolidate_output) {
@@ -2163,7 +2163,7 @@ static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs
     MZ_TRY(trace_view(ctx, all, &tvs[j]));
     if (tvs[j].n_batches == 0 || !exact || fan == 0 || req_ub(r) > MZ_BOUND_MAX_ROWS / fan) return one_by_one();
     bound[j] = req_ub(r) * fan;
-    tiles += (req_ub(r) + 255) / 256;
+    tiles += mz_probe_tiles(req_ub(r), tvs[j].n_batches);
     memset(&pps[j], 0, sizeof(ProbeParams));
     pps[j].mode = r.cmp_mode == MZGPU_HALFJOIN_LE ? MZ_PROBE_HALF_LE : MZ_PROBE_HALF_LT;
     pps[j].has_closure = 1;

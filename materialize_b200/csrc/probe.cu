@@ -99,147 +99,278 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // chained with a decoupled look-back, so the output order is exactly the
 // two-pass order (stream order x batch order x row order) and nothing returns
 // to the host.
-// One compact walk serves both passes (the kernel used to inline two unrolled copies of the
-// walk and of the closure per batch group: 34K instructions, bound by instruction fetch).
-// Pass 0 counts the matches and keeps the first KC output rows in a per-thread cache; after the
-// scan + look-back the cached rows are written, and only a probe row with more than KC matches
-// walks the trace again (pass 1).
-// KC / MINB: update batches cache eight output rows per probe row (lookups with a fan-out of
-// up to eight never walk twice) at two CTAs per SM; bulk probes (millions of rows, fan-out ~1)
-// keep two and trade the cache registers for twice the resident warps -- their limit is the
-// number of DRAM accesses in flight.  GROUP = batches whose first slot is fetched together.
-template <int OUT_NW, int KC, int MINB, int GROUP>
-__global__ void __launch_bounds__(PT, MINB) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
+//
+// A tile is expanded by the whole CTA.  The reference's half_join walks a cursor per key; a
+// thread per probe row doing the same serialises on memory latency (a key with rows in three
+// batches = a dozen dependent DRAM round trips, and the rest of the CTA waits at the scan
+// barrier: profiles/r02b: 56 % barrier stall, 60 us per launch for 14K probe rows).  Here:
+//   1. thread per probe row: first slot of every batch (independent loads), hits counted;
+//   2. block scans give every hit its place in the tile's hit list (thread-major, batch order)
+//      and the tile's CANDIDATE list (the rows of every hit run, concatenated);
+//   3. the candidates are split evenly over the warps: each lane loads one lookup row per step
+//      (independent loads, any fan-out, any skew inside the tile), applies the time filter and
+//      the closure, and counts the survivors; look-back; the same walk again writes them
+//      (rows come from L1/L2 the second time) at offsets from warp ballots -- no block barrier
+//      inside either walk.
+// Rows per tile shrink with the number of batches so that the hit list always fits
+// (hits <= rows x batches <= PROBE_HCAP).
+constexpr int PROBE_HCAP = 2048;
+__host__ __device__ __forceinline__ u32 probe_tile_rows(u32 n_batches) {
+  return n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
+}
+struct ProbeSmem {
+  u32 scan[34];
+  u32 tile;
+  u64 bcast;
+  u32 warp_keep[PT / 32];
+  u32 hit_pref[PROBE_HCAP + 1];  // candidates before hit h (exclusive); [n_hits] = all candidates
+  u64 hit_first[PROBE_HCAP];     // first row of the run | batch index << 48
+  uint16_t hit_row[PROBE_HCAP];       // probe row (thread) the hit belongs to
+  u64 key[PT], v1[PT], t1[PT], d1[PT];  // the tile's probe rows (after the optional pre-map)
+};
+
+struct ProbePre {  // optional map in front of the probe (build_update_stream fused in)
+  int has_pre, pre_has_closure;
+  u64 skip_time;
+  const mzgpu_closure* pre;
+};
+
+// first matching slot of `key` in batch `bv`: {first row, run length} or len = 0 when absent
+__device__ __forceinline__ bool probe_slot_resolve(const BatchView& bv, u64 key, ulonglong2 sl, u64 h, u64 mask,
+                                                   u64* first, u32* len) {
+  while (sl.y != 0 && sl.x != key) {
+    h = (h + 1) & mask;
+    sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+  }
+  if (sl.y == 0) return false;
+  const u64 f = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+  u32 l = (u32)(sl.y >> 44);
+  if (l == 0) {
+    // the builder did not record the run length (a long run): rows are sorted by key, so the end
+    // of the run is an upper-bound search
+    u64 lo = f + 1, hi = bv_n(bv);
+    while (lo < hi) {
+      const u64 mid = (lo + hi) >> 1;
+      if (bv.rows[mid * 4] == key)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    const u64 run = lo - f;
+    l = run > 0xffffffffull ? 0xffffffffu : (u32)run;
+  }
+  *first = f;
+  *len = l;
+  return true;
+}
+
+// One tile: probe rows [row0, row0 + TR) of `stream` (n rows) against `tv`.  Returns through
+// *tile_total the rows the tile appended; `excl_out` the look-back prefix it was given.
+template <int OUT_NW>
+__device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__ stream, u64 n, u64 row0, u32 TR,
+                                           const TraceView& tv, const ProbeParams& pp, const ProbePre& pre,
+                                           const LookBack& lb, u32 tile, u64* __restrict__ out, u64 base0,
+                                           u64 out_cap, u64* __restrict__ status, u64* excl_out, u32* total_out) {
+  constexpr int GROUP = 8;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- 1. this thread's probe row
+  const u64 i = row0 + tid;
+  u64 key = 0, v1 = 0, t1 = 0, d1 = 0;
+  bool live = tid < TR && i < n;
+  if (live) {
+    const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
+    const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
+    key = kv.x;
+    v1 = kv.y;
+    t1 = td.x;
+    d1 = td.y;
+    if (pre.has_pre) {
+      if (pre.skip_time != MZGPU_FRONTIER_EMPTY && t1 == pre.skip_time) {
+        live = false;
+      } else if (pre.pre_has_closure) {
+        u64 k, v;
+        if (closure_eval(*pre.pre, key, v1, 0, &k, &v)) {
+          key = k;
+          v1 = v;
+        } else {
+          live = false;
+        }
+      }
+    }
+  }
+  S.key[tid] = key;
+  S.v1[tid] = v1;
+  S.t1[tid] = t1;
+  S.d1[tid] = d1;
+  const u64 h0 = mix64(key);
+  // ---- 2. hits: count, scan, record (the second walk of the slots hits L1)
+  u32 my_hits = 0, my_cand = 0, hit_off = 0, cand_off = 0;
+#pragma unroll 1
+  for (int phase = 0; phase < 2; ++phase) {
+    u32 k_hit = 0, k_cand = 0;
+    if (live) {
+#pragma unroll 1
+      for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
+        ulonglong2 slot[GROUP];
+        u64 hh[GROUP], msk[GROUP];
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          if (b0 + j < tv.n_batches) {
+            const BatchView& bv = tv.b[b0 + j];
+            msk[j] = bv_mask(bv);
+            hh[j] = h0 & msk[j];
+            slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
+          }
+        }
+#pragma unroll 1
+        for (int j = 0; j < GROUP; ++j) {
+          if (b0 + j >= tv.n_batches) break;
+          u64 first;
+          u32 len;
+          if (!probe_slot_resolve(tv.b[b0 + j], key, slot[j], hh[j], msk[j], &first, &len)) continue;
+          if (phase == 1) {
+            const u32 h = hit_off + k_hit;
+            S.hit_first[h] = first | ((u64)(b0 + j) << 48);
+            S.hit_row[h] = (uint16_t)tid;
+            S.hit_pref[h] = cand_off + k_cand;
+          }
+          k_hit++;
+          k_cand += len;
+        }
+      }
+    }
+    if (phase == 0) {
+      my_hits = k_hit;
+      my_cand = k_cand;
+      u32 tot_h, tot_c;
+      hit_off = block_exclusive_scan(my_hits, S.scan, &tot_h);
+      cand_off = block_exclusive_scan(my_cand, S.scan, &tot_c);
+      if (tid == 0) {
+        S.hit_pref[tot_h] = tot_c;
+        S.warp_keep[0] = tot_h;  // (borrowed: read back below, before the walks use it)
+      }
+    }
+  }
+  __syncthreads();
+  const u32 n_hits = S.warp_keep[0];
+  const u32 n_cand = S.hit_pref[n_hits];
+  __syncthreads();
+  // ---- 3. the candidate walks: warp w owns candidates [w * per, (w + 1) * per)
+  const u32 per = (n_cand + PT / 32 - 1) / (PT / 32);
+  const u32 c_lo = warp * per < n_cand ? warp * per : n_cand;
+  const u32 c_hi = c_lo + per < n_cand ? c_lo + per : n_cand;
+  u64 excl = 0;
+  u32 total = 0;
+  u64 wbase = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    u32 run = 0;
+#pragma unroll 1
+    for (u32 c0 = c_lo; c0 < c_hi; c0 += 32) {
+      const u32 c = c0 + lane;
+      bool keep = false;
+      u64 row[OUT_NW];
+      if (c < c_hi) {
+        // the hit this candidate belongs to: last h with hit_pref[h] <= c
+        u32 lo = 0, hi = n_hits;
+        while (hi - lo > 1) {
+          const u32 mid = (lo + hi) >> 1;
+          if (S.hit_pref[mid] <= c)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        const u64 hf = S.hit_first[lo];
+        const BatchView& bv = tv.b[(u32)(hf >> 48)];
+        const u64 r = (hf & MZ_SLOT_ROW_MASK) + (u64)(c - S.hit_pref[lo]);
+        const u32 pr = S.hit_row[lo];
+        const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+        const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+        const u64 pk = S.key[pr], pv = S.v1[pr], pt = S.t1[pr];
+        const u64 t2 = rtd.x;
+        keep = pp.mode == MZ_PROBE_HALF_LE ? t2 <= pt : (pp.mode == MZ_PROBE_HALF_LT ? t2 < pt : true);
+        if (keep) {
+          u64 t = pt;
+          if (pp.mode == MZ_PROBE_JOIN) {
+            t = pt > t2 ? pt : t2;
+            t = t > pp.meet ? t : pp.meet;
+          }
+          const u64 d = S.d1[pr] * rtd.y;
+          const u64 va = pp.swap_vals ? rkv.y : pv, vb = pp.swap_vals ? pv : rkv.y;
+          if (OUT_NW == 4) {
+            u64 k, v;
+            keep = closure_eval(pp.closure, pk, va, vb, &k, &v);
+            row[0] = k;
+            row[1] = v;
+            row[2] = t;
+            row[3] = d;
+          } else {
+            row[0] = pk;
+            row[1] = va;
+            row[2] = vb;
+            row[3] = t;
+            row[OUT_NW - 1] = d;
+          }
+        }
+      }
+      const u32 m = __ballot_sync(0xffffffffu, keep);
+      if (pass == 1 && keep) {
+        const u64 pos = wbase + run + __popc(m & ((1u << lane) - 1));
+        if (pos >= out_cap) {
+          atomicMax((unsigned long long*)status, (unsigned long long)(pos + 1));
+        } else {
+          u64* o = out + pos * OUT_NW;
+#pragma unroll
+          for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
+        }
+      }
+      run += __popc(m);
+    }
+    if (pass == 0) {
+      if (lane == 0) S.warp_keep[warp] = run;
+      __syncthreads();
+      u32 mine = 0;
+      total = 0;
+#pragma unroll
+      for (int w = 0; w < PT / 32; ++w) {
+        const u32 v = S.warp_keep[w];
+        if ((u32)w < warp) mine += v;
+        total += v;
+      }
+      excl = lb_exclusive_prefix(lb, tile, (u64)total, &S.bcast);
+      wbase = base0 + excl + mine;
+    }
+  }
+  *excl_out = excl;
+  *total_out = total;
+}
+
+template <int OUT_NW>
+__global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stream, const DLen dn,
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
                                                  u64* __restrict__ out_len, u64* __restrict__ status) {
-  __shared__ u32 sm[34];
-  __shared__ u32 s_tile;
-  __shared__ u64 s_b;
+  __shared__ ProbeSmem S;
   const u64 n = dlen_get(dn);
-  const u64 n_tiles = (n + PT - 1) / PT;
+  const u32 TR = probe_tile_rows(tv.n_batches);
+  const u64 n_tiles = (n + TR - 1) / TR;
   const u64 base0 = dlen_get(out_base);
+  ProbePre pre;
+  pre.has_pre = 0;
+  pre.pre_has_closure = 0;
+  pre.skip_time = MZGPU_FRONTIER_EMPTY;
+  pre.pre = nullptr;
   while (true) {
-    const u32 tile = lb_next_tile(lb, &s_tile);
+    const u32 tile = lb_next_tile(lb, &S.tile);
     if ((u64)tile >= n_tiles) {
       if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *out_len = base0;
       break;
     }
-    const u64 i = (u64)tile * PT + threadIdx.x;
-    u64 key = 0, v1 = 0, t1 = 0;
-    i64 d1 = 0;
-    if (i < n) {
-      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
-      const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
-      key = kv.x;
-      v1 = kv.y;
-      t1 = td.x;
-      d1 = (i64)td.y;
-    }
-    u64 cache[KC][OUT_NW];
-    u32 cnt = 0;
-    u64 pos = 0;
-    u32 ex = 0, total = 0;
-    u64 excl = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const bool walk = i < n && (pass == 0 || cnt > (u32)KC);
-      if (walk) {
-        const u64 h0 = mix64(key);
-#pragma unroll 1
-        for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
-          // independent first-slot loads of a group of batches, then the (rare) matches
-          ulonglong2 slot[GROUP];
-          u64 hh[GROUP], msk[GROUP];
-#pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
-            if (b0 + j < tv.n_batches) {
-              const BatchView& bv = tv.b[b0 + j];
-              msk[j] = bv_mask(bv);
-              hh[j] = h0 & msk[j];
-              slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
-            }
-          }
-#pragma unroll 1
-          for (int j = 0; j < GROUP; ++j) {
-            if (b0 + j >= tv.n_batches) break;
-            const BatchView& bv = tv.b[b0 + j];
-            ulonglong2 sl = slot[j];
-            u64 h = hh[j];
-            const u64 mask = msk[j];
-            while (sl.y != 0 && sl.x != key) {
-              h = (h + 1) & mask;
-              sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
-            }
-            if (sl.y == 0) continue;
-            const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
-            const u32 len = (u32)(sl.y >> 44);
-            const u64 end = len != 0 ? first + len : bv_n(bv);
-#pragma unroll 1
-            for (u64 r = first; r < end; ++r) {
-              const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
-              if (len == 0 && rkv.x != key) break;
-              const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
-              const u64 t2 = rtd.x;
-              const bool ok = pp.mode == MZ_PROBE_HALF_LE ? t2 <= t1 : (pp.mode == MZ_PROBE_HALF_LT ? t2 < t1 : true);
-              if (!ok) continue;
-              u64 t = t1;
-              if (pp.mode == MZ_PROBE_JOIN) {
-                t = t1 > t2 ? t1 : t2;
-                t = t > pp.meet ? t : pp.meet;
-              }
-              const u64 d = (u64)d1 * rtd.y;
-              const u64 va = pp.swap_vals ? rkv.y : v1, vb = pp.swap_vals ? v1 : rkv.y;
-              u64 row[OUT_NW];
-              if (OUT_NW == 4) {
-                u64 k, v;
-                if (!closure_eval(pp.closure, key, va, vb, &k, &v)) continue;
-                row[0] = k;
-                row[1] = v;
-                row[2] = t;
-                row[3] = d;
-              } else {
-                row[0] = key;
-                row[1] = va;
-                row[2] = vb;
-                row[3] = t;
-                row[OUT_NW - 1] = d;
-              }
-              if (pass == 0) {
-                if (cnt < (u32)KC) {
-#pragma unroll
-                  for (int w = 0; w < OUT_NW; ++w) cache[cnt][w] = row[w];
-                }
-                cnt++;
-              } else {
-                u64* o = out + pos * OUT_NW;
-#pragma unroll
-                for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
-                pos++;
-              }
-            }
-          }
-        }
-      }
-      if (pass == 0) {
-        ex = block_exclusive_scan(cnt, sm, &total);
-        excl = lb_exclusive_prefix(lb, tile, (u64)total, &s_b);
-        pos = base0 + excl + ex;
-        if (i < n && cnt > 0) {
-          if (pos + cnt > out_cap) {
-            atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
-            cnt = 0;  // nothing is written (the overflow is reported at the next read-back)
-          } else if (cnt <= (u32)KC) {
-            for (u32 c = 0; c < cnt; ++c) {
-              u64* o = out + (pos + c) * OUT_NW;
-#pragma unroll
-              for (int w = 0; w < OUT_NW; ++w) o[w] = cache[c][w];
-            }
-          }
-        }
-      }
-    }
+    u64 excl;
+    u32 total;
+    probe_tile<OUT_NW>(S, stream, n, (u64)tile * TR, TR, tv, pp, pre, lb, tile, out, base0, out_cap, status, &excl,
+                       &total);
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;
   }
 }
@@ -278,25 +409,23 @@ struct ProbeMany {
 static_assert(sizeof(ProbeMany) <= 32000, "kernel parameter space");
 
 template <int OUT_NW>
-__global__ void __launch_bounds__(PT, 2) k_probe_chains(const __grid_constant__ ProbeMany m,
+__global__ void __launch_bounds__(PT, 3) k_probe_chains(const __grid_constant__ ProbeMany m,
                                                      u64* __restrict__ status) {
-  constexpr int KC = 8;
-  constexpr int GROUP = 8;
-  __shared__ u32 sm[34];
-  __shared__ u32 s_tile;
-  __shared__ u64 s_b;
+  __shared__ ProbeSmem S;
   const ProbeChain& ch = m.chain[blockIdx.y];
   u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
+  u32 trj[PROBE_MANY_MAX];
   tiles_before[0] = 0;
 #pragma unroll
   for (int q = 0; q < PROBE_MANY_MAX; ++q) {
     nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
-    tiles_before[q + 1] = tiles_before[q] + (nj[q] + PT - 1) / PT;
+    trj[q] = (u32)q < ch.count ? probe_tile_rows(m.job[ch.first + q].tv.n_batches) : 256u;
+    tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
   }
   const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
   const u64 base0 = dlen_get(ch.out_base);
   while (true) {
-    const u32 tile = lb_next_tile(ch.lb, &s_tile);
+    const u32 tile = lb_next_tile(ch.lb, &S.tile);
     if ((u64)tile >= n_tiles) {
       if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
       break;
@@ -304,135 +433,15 @@ __global__ void __launch_bounds__(PT, 2) k_probe_chains(const __grid_constant__ 
     u32 q = 0;
     while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
     const ProbeJobDev& J = m.job[ch.first + q];
-    const u64 n = nj[q];
-    const u64 i = (u64)(tile - tiles_before[q]) * PT + threadIdx.x;
-    u64 key = 0, v1 = 0, t1 = 0;
-    i64 d1 = 0;
-    if (i < n) {
-      const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(J.stream + i * 4);
-      const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(J.stream + i * 4 + 2);
-      key = kv.x;
-      v1 = kv.y;
-      t1 = td.x;
-      d1 = (i64)td.y;
-    }
-    bool live = i < n;
-    if (live && J.has_pre) {
-      if (J.skip_time != MZGPU_FRONTIER_EMPTY && t1 == J.skip_time) {
-        live = false;
-      } else if (J.pre_has_closure) {
-        u64 k, v;
-        if (closure_eval(J.pre, key, v1, 0, &k, &v)) {
-          key = k;
-          v1 = v;
-        } else {
-          live = false;
-        }
-      }
-    }
-    u64 cache[KC][OUT_NW];
-    u32 cnt = 0;
-    u64 pos = 0;
-    u32 ex = 0, total = 0;
-    u64 excl = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const bool walk = live && (pass == 0 || cnt > (u32)KC);
-      if (walk) {
-        const u64 h0 = mix64(key);
-#pragma unroll 1
-        for (u32 b0 = 0; b0 < J.tv.n_batches; b0 += GROUP) {
-          // independent first-slot loads of a group of batches, then the (rare) matches
-          ulonglong2 slot[GROUP];
-          u64 hh[GROUP], msk[GROUP];
-#pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
-            if (b0 + j < J.tv.n_batches) {
-              const BatchView& bv = J.tv.b[b0 + j];
-              msk[j] = bv_mask(bv);
-              hh[j] = h0 & msk[j];
-              slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
-            }
-          }
-#pragma unroll 1
-          for (int j = 0; j < GROUP; ++j) {
-            if (b0 + j >= J.tv.n_batches) break;
-            const BatchView& bv = J.tv.b[b0 + j];
-            ulonglong2 sl = slot[j];
-            u64 h = hh[j];
-            const u64 mask = msk[j];
-            while (sl.y != 0 && sl.x != key) {
-              h = (h + 1) & mask;
-              sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
-            }
-            if (sl.y == 0) continue;
-            const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
-            const u32 len = (u32)(sl.y >> 44);
-            const u64 end = len != 0 ? first + len : bv_n(bv);
-#pragma unroll 1
-            for (u64 r = first; r < end; ++r) {
-              const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
-              if (len == 0 && rkv.x != key) break;
-              const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
-              const u64 t2 = rtd.x;
-              const bool ok = J.pp.mode == MZ_PROBE_HALF_LE ? t2 <= t1 : (J.pp.mode == MZ_PROBE_HALF_LT ? t2 < t1 : true);
-              if (!ok) continue;
-              u64 t = t1;
-              if (J.pp.mode == MZ_PROBE_JOIN) {
-                t = t1 > t2 ? t1 : t2;
-                t = t > J.pp.meet ? t : J.pp.meet;
-              }
-              const u64 d = (u64)d1 * rtd.y;
-              const u64 va = J.pp.swap_vals ? rkv.y : v1, vb = J.pp.swap_vals ? v1 : rkv.y;
-              u64 row[OUT_NW];
-              if (OUT_NW == 4) {
-                u64 k, v;
-                if (!closure_eval(J.pp.closure, key, va, vb, &k, &v)) continue;
-                row[0] = k;
-                row[1] = v;
-                row[2] = t;
-                row[3] = d;
-              } else {
-                row[0] = key;
-                row[1] = va;
-                row[2] = vb;
-                row[3] = t;
-                row[OUT_NW - 1] = d;
-              }
-              if (pass == 0) {
-                if (cnt < (u32)KC) {
-#pragma unroll
-                  for (int w = 0; w < OUT_NW; ++w) cache[cnt][w] = row[w];
-                }
-                cnt++;
-              } else {
-                u64* o = ch.out + pos * OUT_NW;
-#pragma unroll
-                for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
-                pos++;
-              }
-            }
-          }
-        }
-      }
-      if (pass == 0) {
-        ex = block_exclusive_scan(cnt, sm, &total);
-        excl = lb_exclusive_prefix(ch.lb, tile, (u64)total, &s_b);
-        pos = base0 + excl + ex;
-        if (i < n && cnt > 0) {
-          if (pos + cnt > ch.out_cap) {
-            atomicMax((unsigned long long*)status, (unsigned long long)(pos + cnt));
-            cnt = 0;  // nothing is written (the overflow is reported at the next read-back)
-          } else if (cnt <= (u32)KC) {
-            for (u32 c = 0; c < cnt; ++c) {
-              u64* o = ch.out + (pos + c) * OUT_NW;
-#pragma unroll
-              for (int w = 0; w < OUT_NW; ++w) o[w] = cache[c][w];
-            }
-          }
-        }
-      }
-    }
+    ProbePre pre;
+    pre.has_pre = J.has_pre;
+    pre.pre_has_closure = J.pre_has_closure;
+    pre.skip_time = J.skip_time;
+    pre.pre = &J.pre;
+    u64 excl;
+    u32 total;
+    probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q], J.tv, J.pp, pre, ch.lb, tile,
+                       ch.out, base0, ch.out_cap, status, &excl, &total);
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
   }
 }
@@ -670,30 +679,26 @@ static unsigned lb_grid(mzgpu_ctx* ctx, u64 n_ub) {
   if (tiles > maxg) tiles = maxg;
   return (unsigned)(tiles ? tiles : 1);
 }
+// probes: tiles are handed out by ticket, so the grid only has to cover the machine
+static unsigned probe_grid(mzgpu_ctx* ctx, u64 tiles) {
+  u64 maxg = (u64)ctx->num_sms * 3;
+  if (tiles > maxg) tiles = maxg;
+  return (unsigned)(tiles ? tiles : 1);
+}
 
 int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, const TraceView& trace,
                        const ProbeParams& pp, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len) {
   LookBack lb;
-  MZ_TRY(mz_lookback_begin(ctx, (n_ub + PT - 1) / PT, &lb));
+  const u64 tiles = mz_probe_tiles(n_ub, trace.n_batches);
+  MZ_TRY(mz_lookback_begin(ctx, tiles, &lb));
   const int out_rb = pp.has_closure ? 32 : 40;
   MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 * trace.n_batches + 32 + out_rb) : 0);  // exact counts only
-  const bool bulk = n_ub >= (1ull << 20);
   if (pp.has_closure) {
-    if (bulk) {
-      MZ_LAUNCH(ctx, (k_probe_lb<4, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
-                out_base, out_cap, d_out_len, ctx->d_status);
-    } else {
-      MZ_LAUNCH(ctx, (k_probe_lb<4, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
-                out_base, out_cap, d_out_len, ctx->d_status);
-    }
+    MZ_LAUNCH(ctx, (k_probe_lb<4>), probe_grid(ctx, tiles), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base, out_cap,
+              d_out_len, ctx->d_status);
   } else {
-    if (bulk) {
-      MZ_LAUNCH(ctx, (k_probe_lb<5, 2, 4, 2>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
-                out_base, out_cap, d_out_len, ctx->d_status);
-    } else {
-      MZ_LAUNCH(ctx, (k_probe_lb<5, 8, 2, 8>), lb_grid(ctx, n_ub), PT, 0, d_stream, n, trace, pp, lb, d_out,
-                out_base, out_cap, d_out_len, ctx->d_status);
-    }
+    MZ_LAUNCH(ctx, (k_probe_lb<5>), probe_grid(ctx, tiles), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base, out_cap,
+              d_out_len, ctx->d_status);
   }
   return MZGPU_OK;
 }
@@ -740,13 +745,13 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     u64 tiles = 0, rows_ub = 0;
     for (u32 q = 0; q < m.chain[c].count; ++q) {
       const ProbeJobHost& J = jobs[m.chain[c].first + q];
-      tiles += (J.n_ub + PT - 1) / PT;
+      tiles += mz_probe_tiles(J.n_ub, J.trace->n_batches);
       rows_ub += J.n_ub;
       if (J.n.p == nullptr) bytes += J.n.imm * (32 + 16 * J.trace->n_batches + 32 + (closure ? 32 : 40));
     }
     MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
     lb_at += tiles;
-    const u64 g = lb_grid(ctx, rows_ub);
+    const u64 g = probe_grid(ctx, tiles);
     if (g > max_grid) max_grid = g;
   }
   MZ_BYTES(ctx, bytes);
