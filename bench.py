@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 SEED = 7
 ORDERS_PER_BATCH_PER_GPU = 10_000  # ~100K update rows (2 order rows + ~8 lineitem rows per replaced order)
+P2P_LANDING_ROWS = 1 << 19  # capacity of one landing region (rows one worker may send to one peer per buffer and round)
 
 
 def scale(sf):
@@ -295,7 +296,8 @@ def workload_config(sf_per_gpu, n):
         " arrangements hold SF=10 on one GPU and SF=12.5 per GPU beyond (SF=100 at N=8, configs[4])",
         "sf_total": sf_per_gpu * n,
         "orders_replaced_per_batch": ORDERS_PER_BATCH_PER_GPU * n,
-        "parallelism": f"key-hash sharded x{n}, NCCL all-to-all per exchange point" if n > 1 else "1 GPU",
+        "parallelism": f"key-hash sharded x{n}; exchange rounds over NVLink peer memory (one scatter + one gather kernel,"
+        " no host wait), NCCL all-to-all for hydration chunks" if n > 1 else "1 GPU",
         "l2": "inputs_larger_than_l2 (arrangements >= 5 GB/GPU vs 126 MB L2)",
         "plan": "customer>>orders[custkey]>>lineitem[orderkey]; orders>>customer>>lineitem; lineitem>>orders[orderkey]>>customer",
     }
@@ -359,6 +361,32 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(w)
             torch.cuda.synchronize()
 
+    p2p = False
+    if world > 1:
+        import ctypes as C
+
+        import numpy as np
+
+        from materialize_b200 import _ffi as F
+
+        with stdout_to_stderr():
+            # NCCL connects peers lazily on first use: one small all-to-all now, so that connection
+            # setup is not counted as hydration
+            warm_in = mz.DeviceRows(ctx, 32).upload(np.zeros(4096, dtype=mz.R32))
+            warm_out = mz.DeviceRows(ctx, 32)
+            ctx.check(F.lib.mzgpu_exchange(ctx.h, warm_in.h, warm_out.h))
+            ctx.sync()
+        if os.environ.get("MZGPU_P2P", "1") != "0":
+            # update-batch exchange rounds over peer memory: every rank exports its landing zone
+            # (CUDA IPC handle), the handles are all-gathered on the host side, every rank maps all
+            hnd = mz.p2p_export(ctx, P2P_LANDING_ROWS, 32)
+            t = torch.tensor(list(hnd), dtype=torch.uint8, device="cuda")
+            ts = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(ts, t)
+            mz.p2p_import(ctx, [bytes(x.cpu().tolist()) for x in ts])
+            dist.barrier()
+            p2p = True
+
     def barrier():
         ctx.sync()
         torch.cuda.synchronize()
@@ -382,6 +410,9 @@ def run_ours(args, rank, world, local_rank):
     sf = sf_per_gpu(args, world) * world
     per_batch = ORDERS_PER_BATCH_PER_GPU * world
     q = harness.Q3Dataflow(ctx, SEED, per_batch=per_batch, worker=rank, peers=world, **scale(sf))
+    if p2p:
+        q.use_p2p(True)
+    barrier()
     t0 = time.time()
     hyd_rows = q.hydrate()
     ctx.sync()
@@ -399,12 +430,16 @@ def run_ours(args, rank, world, local_rank):
         staged_rows.append(rows)
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
-    def run_device_step(b, clear=True):
+    OUT_ROWS_MAX = 1 << 16  # output corrections of one timestamp (a few hundred) -- checked on the device
+    kept = mz.DeviceRows(ctx, 64)
+
+    def run_device_step(b, keep=False):
         for a, d in zip((1, 2, 3), staged[b]):
             q.stage_device(a, d)
         q.step()
-        if clear:
-            q.clear_out()
+        if keep:
+            q.keep_out(kept, OUT_ROWS_MAX)
+        q.clear_out()
 
     # ---- device-resident timing
     b = 0
@@ -421,9 +456,9 @@ def run_ours(args, rank, world, local_rank):
     e0.record(ext)
     rows_timed = 0
     for i in range(n_timed):
-        # the output corrections of the timed steps stay in the output buffer (appended, one
-        # timestamp after the other) and are compared with the CPU oracle's after the region
-        run_device_step(b, clear=False)
+        # the output corrections of every timed step are appended (device to device, no read-back)
+        # to `kept` and compared with the CPU oracle's after the region
+        run_device_step(b, keep=True)
         step_ev[i].record(ext)
         rows_timed += staged_rows[b]
         b += 1
@@ -438,8 +473,7 @@ def run_ours(args, rank, world, local_rank):
     # completion-to-completion interval of consecutive steps on this rank's stream
     step_ms = sorted(([e0.elapsed_time(step_ev[0])] + [step_ev[i - 1].elapsed_time(step_ev[i]) for i in range(1, n_timed)]))
     per_step = {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]}
-    timed_out = q.out_rows().copy()  # (outside the timed region)
-    q.clear_out()
+    timed_out = kept.download()  # (outside the timed region)
     launches = ctx.stats()["kernel_launches"] - launches0
     total_rows = allsum(rows_timed)
     value = total_rows / (ms / 1000.0)

@@ -296,6 +296,11 @@ int32_t mzgpu_buf_download(mzgpu_buf* buf, void* rows, uint64_t cap, int32_t mem
 int32_t mzgpu_buf_clear(mzgpu_buf* buf);
 /* Append the rows of `src` (same row width) without reading its length back. */
 int32_t mzgpu_buf_append_buf(mzgpu_buf* dst, mzgpu_buf* src);
+/* The same where the caller knows a tighter bound on src's row count than the library does
+ * (`dst` then grows by at most `max_rows`, not by src's internal upper bound): e.g. collecting a
+ * reduce's few output corrections timestamp after timestamp.  More rows than `max_rows` are
+ * detected on the device: MZGPU_E_CAPACITY at the next read-back, nothing out of bounds. */
+int32_t mzgpu_buf_append_buf_at_most(mzgpu_buf* dst, mzgpu_buf* src, uint64_t max_rows);
 
 /* ---------------------------------------------------- a1: consolidation */
 /* differential_dataflow::consolidation::consolidate on Vec<(u64,i64)>:
@@ -555,6 +560,34 @@ int32_t mzgpu_exchange(mzgpu_ctx* ctx, mzgpu_buf* in, mzgpu_buf* out);
  * payload all-to-all): the exchange points of operators that run side by side,
  * e.g. the arrangement inputs of one timestamp.  k <= 8; all peers pass the same k. */
 int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs);
+/* ---- the same pact over peer memory (NVLink / NVSwitch): no NCCL, no host wait.
+ * Every worker owns a landing zone with a fixed-capacity region per (buffer slot, source
+ * worker); an exchange round is ONE scatter kernel that partitions the rows and writes them
+ * straight into the destination workers' zones (peer stores), publishing counts and a round
+ * flag, and ONE gather kernel that waits for all sources' flags on the device and compacts
+ * the regions into the operator's input buffer, leaving the row count on the device.
+ * Setup (once, host bootstrap as for mzgpu_comm_init): every worker calls _export, the 64-byte
+ * handles are all-gathered by the host, every worker calls _import with all of them (index =
+ * worker).  `landing_rows` = capacity of one region: no worker may send more than that many
+ * rows of one buffer to one destination in one round (violations are detected on the device
+ * and reported as MZGPU_E_CAPACITY at the next read-back; nothing wrong is delivered);
+ * `region_row_bytes` = widest row exchanged (32 or 80).  Zone size = 4 KB + 2 x 8 x peers x
+ * landing_rows x region_row_bytes bytes. */
+#define MZGPU_P2P_HANDLE_BYTES 64
+int32_t mzgpu_comm_p2p_export(mzgpu_ctx* ctx, uint64_t landing_rows, uint32_t region_row_bytes,
+                              uint8_t handle[MZGPU_P2P_HANDLE_BYTES]);
+int32_t mzgpu_comm_p2p_import(mzgpu_ctx* ctx, const uint8_t* handles /* peers x 64 bytes */);
+/* Same-process variant (several workers of one process, e.g. one thread per GPU, or a test
+ * that runs every worker on one GPU): zones[w] = worker w's mzgpu_comm_p2p_zone(). */
+void* mzgpu_comm_p2p_zone(mzgpu_ctx* ctx);
+int32_t mzgpu_comm_p2p_import_local(mzgpu_ctx* ctx, void* const* zones);
+/* One round for k buffers (all workers call with the same k, in the same order).
+ * outs[e] is replaced; its capacity is recv_ub[e] rows if given (the caller's bound on what
+ * this worker can receive, e.g. the global batch size), else peers x landing_rows.
+ * mzgpu_exchange_p2p = _send (scatter) followed by _recv (gather). */
+int32_t mzgpu_exchange_p2p(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs, const uint64_t* recv_ub);
+int32_t mzgpu_exchange_p2p_send(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins);
+int32_t mzgpu_exchange_p2p_recv(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** outs, const uint64_t* recv_ub);
 /* The routing function itself (for tests and host-side pre-partitioning). */
 uint32_t mzgpu_route(uint64_t key, uint32_t peers);
 /* The device half of an exchange round on its own: the k buffers are bucketed by

@@ -42,6 +42,11 @@ from .api import (  # noqa: F401
     make_closure,
     map_rows,
     partition_many,
+    p2p_export,
+    p2p_import,
+    p2p_connect_local,
+    exchange_p2p_send,
+    exchange_p2p_recv,
     route,
     update_stream,
     update_stream_dev,

@@ -59,6 +59,7 @@ OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NCCL, E_FRONTIER = 0, -1, -2
 HALFJOIN_LE, HALFJOIN_LT = 0, 1
 AGG_COUNT_SUM_I64, AGG_COUNT_SUM_F64, AGG_DISTINCT, AGG_THRESHOLD, AGG_MIN, AGG_MAX, AGG_TOPK = 0, 1, 2, 3, 4, 5, 6
 COMM_ID_BYTES = 128
+P2P_HANDLE_BYTES = 64
 
 
 class Field(C.Structure):
@@ -123,6 +124,7 @@ SIGNATURES = {
     "mzgpu_buf_upload": (i32, [vp, vp, u64, i32]),
     "mzgpu_buf_append": (i32, [vp, vp, u64, i32]),
     "mzgpu_buf_append_buf": (i32, [vp, vp]),
+    "mzgpu_buf_append_buf_at_most": (i32, [vp, vp, u64]),
     "mzgpu_batcher_push_buf": (i32, [vp, vp]),
     "mzgpu_half_join_buf": (i32, [vp, vp, vp, i32, C.POINTER(Closure), i32, vp]),
     "mzgpu_half_join_many": (i32, [vp, u32, vp, vp, vp, vp, vp]),
@@ -179,6 +181,13 @@ SIGNATURES = {
     "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
     "mzgpu_partition_many": (i32, [vp, u32, PV, u32, PV, PU64]),
+    "mzgpu_comm_p2p_export": (i32, [vp, u64, u32, C.POINTER(C.c_uint8)]),
+    "mzgpu_comm_p2p_import": (i32, [vp, C.POINTER(C.c_uint8)]),
+    "mzgpu_comm_p2p_zone": (vp, [vp]),
+    "mzgpu_comm_p2p_import_local": (i32, [vp, PV]),
+    "mzgpu_exchange_p2p": (i32, [vp, u32, PV, PV, PU64]),
+    "mzgpu_exchange_p2p_send": (i32, [vp, u32, PV]),
+    "mzgpu_exchange_p2p_recv": (i32, [vp, u32, PV, PU64]),
     "mzgpu_batch_seek_keys": (i32, [vp, vp, u64, i32, vp]),
     "mzgpu_batch_key_page": (i32, [vp, u64, u64, i32, vp, PU64]),
     "mzgpu_batch_rows": (i32, [vp, u64, u64, vp, i32]),

@@ -170,6 +170,11 @@ class DeviceRows:
         self.ctx.check(F.lib.mzgpu_buf_append_buf(self.h, other.h))
         return self
 
+    def append_buf_at_most(self, other, max_rows):
+        """append_buf where the caller bounds other's row count (checked on the device)."""
+        self.ctx.check(F.lib.mzgpu_buf_append_buf_at_most(self.h, other.h, max_rows))
+        return self
+
     def device_ptr(self):
         return F.lib.mzgpu_buf_device_ptr(self.h)
 
@@ -566,3 +571,38 @@ def partition_many(ctx, bufs, peers):
     counts = (C.c_uint64 * (k * peers))()
     ctx.check(F.lib.mzgpu_partition_many(ctx.h, k, ins_a, peers, outs_a, counts))
     return [(outs[e].download(), [int(counts[e * peers + p]) for p in range(peers)]) for e in range(k)]
+
+
+# -- exchange over peer memory (a13): setup helpers and the round itself
+def p2p_export(ctx, landing_rows, region_row_bytes=32):
+    """Allocate this worker's landing zone; returns the 64-byte IPC handle to all-gather."""
+    h = (C.c_uint8 * F.P2P_HANDLE_BYTES)()
+    ctx.check(F.lib.mzgpu_comm_p2p_export(ctx.h, landing_rows, region_row_bytes, h))
+    return bytes(h)
+
+
+def p2p_import(ctx, handles):
+    """handles: list of every worker's handle (index = worker)."""
+    raw = b"".join(handles)
+    buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+    ctx.check(F.lib.mzgpu_comm_p2p_import(ctx.h, buf))
+
+
+def p2p_connect_local(ctxs, landing_rows, region_row_bytes=32):
+    """All workers live in this process (tests: every worker on one GPU): map the zones directly."""
+    for c in ctxs:
+        c.check(F.lib.mzgpu_comm_p2p_export(c.h, landing_rows, region_row_bytes, None))
+    zones = (C.c_void_p * len(ctxs))(*[F.lib.mzgpu_comm_p2p_zone(c.h) for c in ctxs])
+    for c in ctxs:
+        c.check(F.lib.mzgpu_comm_p2p_import_local(c.h, zones))
+
+
+def exchange_p2p_send(ctx, bufs):
+    a = (C.c_void_p * len(bufs))(*[b.h for b in bufs])
+    ctx.check(F.lib.mzgpu_exchange_p2p_send(ctx.h, len(bufs), a))
+
+
+def exchange_p2p_recv(ctx, outs, recv_ub=None):
+    a = (C.c_void_p * len(outs))(*[b.h for b in outs])
+    ub = (C.c_uint64 * len(outs))(*recv_ub) if recv_ub is not None else None
+    ctx.check(F.lib.mzgpu_exchange_p2p_recv(ctx.h, len(outs), a, ub))

@@ -86,6 +86,16 @@ struct mzgpu_ctx {
   // NCCL (resolved with dlopen at mzgpu_comm_init)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
+  // exchange over peer memory (exchange.cu): landing zones, one per worker
+  void* p2p_local = nullptr;        // this worker's zone (cudaMalloc: IPC-exportable)
+  void* p2p_peer[16] = {};          // every worker's zone as mapped here ([worker] == p2p_local)
+  bool p2p_peer_ipc[16] = {};       // mapped with cudaIpcOpenMemHandle (closed at destroy)
+  u64 p2p_rows = 0;                 // rows per region
+  u32 p2p_region_rb = 0;            // bytes per row reserved in a region
+  u64 p2p_round = 0;                // rounds issued so far
+  u64* p2p_cursors = nullptr;       // [MZ_MAX_EXCHANGE][16] scatter cursors (zero between rounds)
+  u32* p2p_done = nullptr;          // scatter CTAs finished (zero between rounds)
+  bool p2p_ready = false;
 };
 
 #define MZ_SET_ERR(ctx, ...)                              \
@@ -795,6 +805,13 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
 
 // exchange.cu
 #define MZ_MAX_EXCHANGE 8
+#define MZ_P2P_MAX_PEERS 16
+#define MZ_P2P_HEADER_BYTES 4096
+size_t mz_p2p_zone_bytes(u64 landing_rows, u32 region_rb, u32 peers);
+int32_t mz_p2p_send(mzgpu_ctx* ctx, u32 k, const int* row_bytes, const void* const* d_rows, const DLen* n,
+                    const u64* n_ub);
+int32_t mz_p2p_recv(mzgpu_ctx* ctx, u32 k, const int* row_bytes, void* const* d_out, const u64* out_cap,
+                    u64* const* d_out_len);
 int32_t mz_partition_many(mzgpu_ctx* ctx, u32 k, const int* row_bytes, const void* const* d_rows, const DLen* n,
                           const u64* n_ub, u32 peers, void* const* d_out, u64* d_counts, u64* d_cursors,
                           u64* d_send_by_peer /* [peer][k] */);

@@ -147,6 +147,7 @@ struct mzh_q3 {
   int fill_slot = 0, run_slot = 0;
   bool static_rel[4] = {true, false, false, false};  // relations the generator never updates after hydration
   bool stepping = false;                             // false while hydrating
+  bool use_p2p = false;                              // update-batch exchange rounds go over peer memory
   bool streams_prepared = false;                     // stage-0 streams already mapped + exchanged
 };
 
@@ -177,6 +178,14 @@ static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, in
   H_CUDA(cudaStreamSynchronize(q->stream));
   *n_li = h;
   return MZGPU_OK;
+}
+
+// One exchange round for k buffers.  Update batches go over peer memory when the landing zones are
+// connected (mzh_q3_use_p2p): no host wait, `recv_ub` = what this worker can receive at most, if
+// the dataflow knows (the global batch size); bulk hydration chunks take the NCCL round.
+static int32_t q3_exchange(mzh_q3* q, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs, const uint64_t* recv_ub) {
+  if (q->use_p2p && q->stepping) return mzgpu_exchange_p2p(q->ctx, k, ins, outs, recv_ub);
+  return mzgpu_exchange_many(q->ctx, k, ins, outs);
 }
 
 // Exchange(key) then Batcher::push_container for arrangement `a`
@@ -235,9 +244,14 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
           outs[k] = q->pxchg[path];
           ++k;
         }
-      st = mzgpu_exchange_many(q->ctx, k, ins, outs);
+      st = q3_exchange(q, k, ins, outs, nullptr);
       for (int path = 0; path < 3; ++path)
         if (active[path]) std::swap(q->pstream[path], q->pxchg[path]);
+      // The one host wait of a timestamp over peer memory: the received stream lengths become
+      // exact here (a worker cannot bound what the others send it), so the probes below run in
+      // their bounded single-pass form; everything queued so far overlaps with this wait.
+      if (st == MZGPU_OK && q->use_p2p && q->stepping)
+        for (uint32_t i = 0; i < k; ++i) (void)mzgpu_buf_len(outs[i]);
     }
     // the active paths' stage-s half joins are independent operators: one launch.  Last stage:
     // the paths' outputs are concatenated (delta_join.rs:302-308), so every path appends
@@ -280,7 +294,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
         if (active[path]) std::swap(q->pstream[path], q->pnext[path]);
   }
   if (st == MZGPU_OK && q->peers > 1) {
-    st = mzgpu_exchange(q->ctx, q->results, q->xchg);
+    st = q3_exchange(q, 1, &q->results, &q->xchg, nullptr);
     std::swap(q->results, q->xchg);
   }
   mzgpu_buf* out_buf = q->out;
@@ -419,15 +433,20 @@ int32_t mzh_q3_hydrate(mzh_q3* q, uint64_t* rows_in) {
     uint64_t n = first < hi ? (hi - first < CHUNK ? hi - first : CHUNK) : 0;
     uint64_t n_li = 0;
     H_TRY(q3_gen_orders(q, first, n, 0, 1, 0, &n_li));
-    H_TRY(mzgpu_buf_upload(tmp, q->gen_ok.p, n, MZGPU_MEM_DEVICE));
-    H_TRY(q3_arrange_push(q, 1, tmp));
-    H_TRY(mzgpu_buf_upload(tmp, q->gen_ck.p, n, MZGPU_MEM_DEVICE));
-    H_TRY(q3_arrange_push(q, 2, tmp));
-    H_TRY(mzgpu_buf_upload(tmp, q->gen_li.p, n_li, MZGPU_MEM_DEVICE));
-    H_TRY(q3_arrange_push(q, 3, tmp));
+    H_TRY(mzgpu_buf_upload(q->input[1], q->gen_ok.p, n, MZGPU_MEM_DEVICE));
+    H_TRY(mzgpu_buf_upload(q->input[2], q->gen_ck.p, n, MZGPU_MEM_DEVICE));
+    H_TRY(mzgpu_buf_upload(q->input[3], q->gen_li.p, n_li, MZGPU_MEM_DEVICE));
+    if (q->peers > 1) {
+      // the three relations of a chunk share one exchange round (one host wait, not three)
+      mzgpu_buf *ins[3] = {q->input[1], q->input[2], q->input[3]}, *outs[3] = {q->axchg[1], q->axchg[2], q->axchg[3]};
+      H_TRY(mzgpu_exchange_many(q->ctx, 3, ins, outs));
+      for (int a = 1; a < 4; ++a) H_TRY(mzgpu_batcher_push_buf(q->batcher[a], q->axchg[a]));
+    } else {
+      for (int a = 1; a < 4; ++a) H_TRY(mzgpu_batcher_push_buf(q->batcher[a], q->input[a]));
+    }
     total += n + n_li;
   }
-  H_TRY(mzgpu_buf_clear(tmp));
+  for (int a = 0; a < 4; ++a) H_TRY(mzgpu_buf_clear(q->input[a]));
   if (rows_in) *rows_in = total;
   H_TRY(q3_run_timestamp(q, 0));
   H_TRY(q3_maintenance(q));
@@ -533,11 +552,16 @@ int32_t mzh_q3_step(mzh_q3* q) {
   if (q->peers > 1) {
     // the arrangement inputs of one timestamp share one exchange round
     mzgpu_buf *ins[8], *outs[8];
+    uint64_t recv_ub[8];
+    // what one worker can receive of a relation's updates: all of the (global) batch -- two
+    // versions of every replaced order, at most seven lineitems each
+    const uint64_t ub_rel[4] = {0, 2 * q->per_batch, 2 * q->per_batch, 14 * q->per_batch};
     uint32_t k = 0;
     for (int a = 0; a < 4; ++a)
       if (!q->static_rel[a]) {
         ins[k] = q->input[a];
         outs[k] = q->axchg[a];
+        recv_ub[k] = ub_rel[a];
         ++k;
       }
     // ... and so do the delta paths' update streams: build_update_stream is a per-row map, so
@@ -552,9 +576,10 @@ int32_t mzh_q3_step(mzh_q3* q) {
                            MZGPU_MEM_DEVICE, &q->plan.initial[path], q->pstream[path]));
       ins[k] = q->pstream[path];
       outs[k] = q->pxchg[path];
+      recv_ub[k] = ub_rel[src];
       ++k;
     }
-    H_TRY(mzgpu_exchange_many(q->ctx, k, ins, outs));
+    H_TRY(q3_exchange(q, k, ins, outs, recv_ub));
     for (int a = 0; a < 4; ++a)
       if (!q->static_rel[a]) H_TRY(mzgpu_batcher_push_buf(q->batcher[a], q->axchg[a]));
     for (int path = 0; path < 3; ++path)
@@ -565,6 +590,13 @@ int32_t mzh_q3_step(mzh_q3* q) {
   }
   H_TRY(q3_run_timestamp(q, t));
   q->next_time = t + 1;
+  return MZGPU_OK;
+}
+// Update-batch exchange rounds over peer memory from now on (the caller has connected the landing
+// zones: mzgpu_comm_p2p_export / _import on q's context).
+int32_t mzh_q3_use_p2p(mzh_q3* q, int32_t on) {
+  if (q == nullptr) return MZGPU_E_INVALID;
+  q->use_p2p = on != 0;
   return MZGPU_OK;
 }
 // Run the maintenance that is due (tests call this before inspecting the spines).

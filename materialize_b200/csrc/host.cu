@@ -101,6 +101,10 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   for (int i = 0; i < 16; ++i)
     if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
   mz_fused_deferred_free(ctx);
+  for (int p = 0; p < 16; ++p)
+    if (ctx->p2p_peer_ipc[p] && ctx->p2p_peer[p]) cudaIpcCloseMemHandle(ctx->p2p_peer[p]);
+  if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+  if (ctx->p2p_cursors) cudaFree(ctx->p2p_cursors);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
@@ -492,6 +496,32 @@ static int32_t buf_append_dev(mzgpu_buf* b, const void* d_rows, DLen n, u64 n_ub
   MZ_TRY(buf_begin_append(b, &a));
   MZ_TRY(append_dev(b->ctx, d_rows, n, n_ub, b->rb, b->mem.p, a.base, b->cap, a.out_len));
   buf_end_append(b, a, n_ub);
+  return MZGPU_OK;
+}
+
+// append src's rows where the CALLER bounds their number (tighter than the library's own bound):
+// the destination grows by at most `max_rows`; more rows than that are detected on the device
+// (reported as MZGPU_E_CAPACITY at the next read-back, nothing is written past the capacity)
+extern "C" int32_t mzgpu_buf_append_buf_at_most(mzgpu_buf* dst, mzgpu_buf* src, uint64_t max_rows) {
+  if (dst == nullptr || src == nullptr || dst == src || dst->rb != src->rb) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(dst->ctx);
+  const u64 n_ub = std::min<u64>(src->ub, max_rows);
+  if (n_ub == 0) return MZGPU_OK;
+  mzgpu_ctx* ctx = dst->ctx;
+  MZ_TRY(buf_reserve(dst, dst->ub + n_ub, true));
+  if (dst->len.known && src->len.known) {
+    if (src->len.v[src->word] > max_rows) {
+      MZ_SET_ERR(ctx, "buf_append_buf_at_most: %llu rows exceed the caller's bound %llu",
+                 (unsigned long long)src->len.v[src->word], (unsigned long long)max_rows);
+      return MZGPU_E_CAPACITY;
+    }
+    return buf_append_dev(dst, src->mem.p, buf_dlen(src), n_ub);
+  }
+  Append a;
+  MZ_TRY(buf_begin_append(dst, &a));
+  // capacity as seen by the kernel = what this append may fill at most
+  MZ_TRY(append_dev(ctx, src->mem.p, buf_dlen(src), src->ub, dst->rb, dst->mem.p, a.base, dst->ub + n_ub, a.out_len));
+  buf_end_append(dst, a, n_ub);
   return MZGPU_OK;
 }
 
@@ -1931,7 +1961,10 @@ extern "C" int32_t mzgpu_join_core_work_until(mzgpu_join* j, uint64_t fuel_rows,
     return MZGPU_E_INVALID;
   }
   u64 produced = 0;
-  while (!j->todo.empty() && produced < fuel_rows && (deadline_ns == 0 || mono_ns() < deadline_ns)) {
+  // (at least one slice per call: a deadline that has already passed still makes progress)
+  bool first = true;
+  while (!j->todo.empty() && produced < fuel_rows && (first || deadline_ns == 0 || mono_ns() < deadline_ns)) {
+    first = false;
     // the item leaves the queue only once its output has been appended: a failure below (more
     // batches than a trace view holds, counter arena, ...) leaves it queued, so no join work is lost
     mzgpu_join::Work& w = j->todo.front();
@@ -2686,6 +2719,135 @@ extern "C" int32_t mzgpu_exchange_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** i
   return MZGPU_OK;
 #undef NCCL_TRY
 }
+// ---- exchange over peer memory (kernels in exchange.cu)
+extern "C" int32_t mzgpu_comm_p2p_export(mzgpu_ctx* ctx, uint64_t landing_rows, uint32_t region_row_bytes,
+                                         uint8_t handle[MZGPU_P2P_HANDLE_BYTES]) {
+  MZ_CHECK_CTX(ctx);
+  if (landing_rows == 0 || (region_row_bytes != 32 && region_row_bytes != 80) || ctx->peers > MZ_P2P_MAX_PEERS ||
+      ctx->p2p_local != nullptr)
+    return MZGPU_E_INVALID;
+  const size_t bytes = mz_p2p_zone_bytes(landing_rows, region_row_bytes, (u32)ctx->peers);
+  MZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  MZ_CUDA(ctx, cudaMalloc(&ctx->p2p_local, bytes));  // (not from the pool: the zone is exported)
+  MZ_CUDA(ctx, cudaMemset(ctx->p2p_local, 0, MZ_P2P_HEADER_BYTES));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->p2p_cursors, MZ_MAX_EXCHANGE * 16 * 8 + 16));
+  MZ_CUDA(ctx, cudaMemset(ctx->p2p_cursors, 0, MZ_MAX_EXCHANGE * 16 * 8 + 16));
+  ctx->p2p_done = (u32*)(ctx->p2p_cursors + MZ_MAX_EXCHANGE * 16);
+  ctx->p2p_rows = landing_rows;
+  ctx->p2p_region_rb = region_row_bytes;
+  ctx->stats.device_bytes_in_use += bytes;
+  if (ctx->stats.device_bytes_in_use > ctx->stats.device_bytes_peak) ctx->stats.device_bytes_peak = ctx->stats.device_bytes_in_use;
+  if (handle != nullptr) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == MZGPU_P2P_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    MZ_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    memcpy(handle, &h, MZGPU_P2P_HANDLE_BYTES);
+  }
+  return MZGPU_OK;
+}
+extern "C" void* mzgpu_comm_p2p_zone(mzgpu_ctx* ctx) { return ctx ? ctx->p2p_local : nullptr; }
+extern "C" int32_t mzgpu_comm_p2p_import(mzgpu_ctx* ctx, const uint8_t* handles) {
+  MZ_CHECK_CTX(ctx);
+  if (handles == nullptr || ctx->p2p_local == nullptr) return MZGPU_E_INVALID;
+  MZ_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int p = 0; p < ctx->peers; ++p) {
+    if (p == ctx->worker) {
+      ctx->p2p_peer[p] = ctx->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)p * MZGPU_P2P_HANDLE_BYTES, MZGPU_P2P_HANDLE_BYTES);
+    MZ_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->p2p_peer_ipc[p] = true;
+  }
+  ctx->p2p_ready = true;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_comm_p2p_import_local(mzgpu_ctx* ctx, void* const* zones) {
+  MZ_CHECK_CTX(ctx);
+  if (zones == nullptr || ctx->p2p_local == nullptr) return MZGPU_E_INVALID;
+  for (int p = 0; p < ctx->peers; ++p) {
+    if (zones[p] == nullptr) return MZGPU_E_INVALID;
+    ctx->p2p_peer[p] = zones[p];
+  }
+  if (ctx->p2p_peer[ctx->worker] != ctx->p2p_local) return MZGPU_E_INVALID;
+  ctx->p2p_ready = true;
+  return MZGPU_OK;
+}
+static int32_t p2p_check(mzgpu_ctx* ctx, uint32_t k) {
+  if (k > MZ_MAX_EXCHANGE) return MZGPU_E_INVALID;
+  if (!ctx->p2p_ready) {
+    MZ_SET_ERR(ctx, "exchange_p2p: the landing zones have not been exported / imported");
+    return MZGPU_E_INVALID;
+  }
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_exchange_p2p_send(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (ins == nullptr) return MZGPU_E_INVALID;
+  MZ_TRY(p2p_check(ctx, k));
+  int rbs[MZ_MAX_EXCHANGE];
+  const void* srcs[MZ_MAX_EXCHANGE];
+  DLen ns[MZ_MAX_EXCHANGE];
+  u64 ubs[MZ_MAX_EXCHANGE];
+  for (uint32_t e = 0; e < k; ++e) {
+    if (ins[e] == nullptr) return MZGPU_E_INVALID;
+    rbs[e] = (int)ins[e]->rb;
+    srcs[e] = ins[e]->mem.p;
+    ns[e] = buf_dlen(ins[e]);
+    ubs[e] = ins[e]->ub;
+  }
+  ctx->p2p_round++;
+  return mz_p2p_send(ctx, k, rbs, srcs, ns, ubs);
+}
+extern "C" int32_t mzgpu_exchange_p2p_recv(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** outs, const uint64_t* recv_ub) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (outs == nullptr) return MZGPU_E_INVALID;
+  MZ_TRY(p2p_check(ctx, k));
+  int rbs[MZ_MAX_EXCHANGE];
+  void* dsts[MZ_MAX_EXCHANGE];
+  u64 caps[MZ_MAX_EXCHANGE];
+  u64* lens[MZ_MAX_EXCHANGE];
+  const u64 most = (u64)ctx->peers * ctx->p2p_rows;
+  for (uint32_t e = 0; e < k; ++e) {
+    if (outs[e] == nullptr) return MZGPU_E_INVALID;
+    u64 cap = recv_ub != nullptr && recv_ub[e] < most ? recv_ub[e] : most;
+    if (cap == 0) cap = 1;
+    buf_set_len(outs[e], 0);
+    MZ_TRY(buf_reserve(outs[e], cap, false));
+    MZ_TRY(outs[e]->len.make_pending(ctx));
+    outs[e]->word = 0;
+    outs[e]->ub = cap;
+    rbs[e] = (int)outs[e]->rb;
+    dsts[e] = outs[e]->mem.p;
+    caps[e] = cap;
+    lens[e] = outs[e]->len.dptr();
+  }
+  MZ_TRY(mz_p2p_recv(ctx, k, rbs, dsts, caps, lens));
+  for (uint32_t e = 0; e < k; ++e) outs[e]->len.mark_written();
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_exchange_p2p(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, mzgpu_buf** outs,
+                                      const uint64_t* recv_ub) {
+  MZ_CHECK_CTX(ctx);
+  if (k == 0) return MZGPU_OK;
+  if (ins == nullptr || outs == nullptr || k > MZ_MAX_EXCHANGE) return MZGPU_E_INVALID;
+  for (uint32_t e = 0; e < k; ++e)
+    if (ins[e] == nullptr || outs[e] == nullptr || ins[e]->rb != outs[e]->rb || ins[e] == outs[e])
+      return MZGPU_E_INVALID;
+  if (ctx->peers == 1) {
+    for (uint32_t e = 0; e < k; ++e) {
+      buf_set_len(outs[e], 0);
+      MZ_TRY(buf_append_dev(outs[e], ins[e]->mem.p, buf_dlen(ins[e]), ins[e]->ub));
+    }
+    return MZGPU_OK;
+  }
+  MZ_TRY(mzgpu_exchange_p2p_send(ctx, k, ins));
+  return mzgpu_exchange_p2p_recv(ctx, k, outs, recv_ub);
+}
+
 extern "C" int32_t mzgpu_partition_many(mzgpu_ctx* ctx, uint32_t k, mzgpu_buf** ins, uint32_t peers,
                                         mzgpu_buf** outs, uint64_t* counts) {
   MZ_CHECK_CTX(ctx);

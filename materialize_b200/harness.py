@@ -24,6 +24,7 @@ _SIG = {
     "mzh_q3_pipeline_out": (i32, [vp]),
     "mzh_q3_fetch_out": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_maintain": (i32, [vp]),
+    "mzh_q3_use_p2p": (i32, [vp, i32]),
     "mzh_q3_input": (vp, [vp, i32]),
     "mzh_q3_staged": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_step": (i32, [vp]),
@@ -83,6 +84,10 @@ class Q3Dataflow:
     def h2d_bytes(self):
         return _lib.mzh_q3_h2d_bytes(self.h)
 
+    def use_p2p(self, on=True):
+        """Update-batch exchange rounds over peer memory (landing zones connected by the caller)."""
+        self.ctx.check(_lib.mzh_q3_use_p2p(self.h, 1 if on else 0))
+
     def maintain(self):
         self.ctx.check(_lib.mzh_q3_maintain(self.h))
 
@@ -118,6 +123,11 @@ class Q3Dataflow:
         got = u64(0)
         self.ctx.check(F.lib.mzgpu_buf_download(buf, out.ctypes.data_as(vp), n, F.MEM_HOST, C.byref(got)))
         return out
+
+    def keep_out(self, acc, max_rows):
+        """Append this timestamp's output corrections to the device buffer `acc` (at most `max_rows`
+        of them, checked on the device) without reading anything back."""
+        self.ctx.check(F.lib.mzgpu_buf_append_buf_at_most(acc.h, _lib.mzh_q3_out(self.h), max_rows))
 
     def clear_out(self):
         self.ctx.check(_lib.mzh_q3_clear_out(self.h))

@@ -199,7 +199,11 @@ def test_arrange_join_full_size_properties(mz, ctx):
     assert int(out["val1"].astype(np.int64).sum()) == int((va * cb).sum())
     assert int(out["val2"].astype(np.int64).sum()) == int((vb * ca).sum())
     assert np.all(out["diff"] == 1) and np.all(out["time"] == 0)
-    k, v1, v2 = out["key"], out["val1"], out["val2"]
+    # (a work item is joined in slices of 1M probe rows, each slice's results consolidated on its own:
+    # the whole result is sorted and duplicate-free once consolidated)
+    outc = ctx.consolidate(out)
+    assert len(outc) == len(out)
+    k, v1, v2 = outc["key"], outc["val1"], outc["val2"]
     lt = (k[:-1] < k[1:]) | ((k[:-1] == k[1:]) & ((v1[:-1] < v1[1:]) | ((v1[:-1] == v1[1:]) & (v2[:-1] < v2[1:]))))
     assert np.all(lt)
 
@@ -410,13 +414,13 @@ def test_join_core_yields_inside_a_work_item(mz, ctx, oracle):
     import time
 
     rng = np.random.default_rng(412)
-    n = (1 << 20) + 50000  # more than one slice
+    n = (1 << 20) + 50000  # more than one slice (every row distinct: nothing consolidates away)
     a = np.zeros(n, dtype=oracle.R32)
     a["key"] = rng.integers(0, 200000, size=n, dtype=np.uint64)
-    a["val"] = rng.integers(0, 3, size=n, dtype=np.uint64)
+    a["val"] = np.arange(n, dtype=np.uint64) * np.uint64(16)
     a["diff"] = 1
     b = a[:70000].copy()
-    b["val"] += 10
+    b["val"] += np.uint64(3)
     g1, g2 = mz.Spine(ctx, 32), mz.Spine(ctx, 32)
     o1, o2 = oracle.Spine(32, 1, True), oracle.Spine(32, 1, True)
     ga, gbb = mz.Batch.build(ctx, a, 0, 1), mz.Batch.build(ctx, b, 0, 1)
@@ -978,6 +982,48 @@ def test_exchange_partition_kernels_route_like_the_oracle(mz, ctx, oracle, peers
             want = x[dest == p]
             assert multiset(grp) == multiset(want)
             assert all(mz.route(int(k), peers) == p for k in grp["key"][:50])
+
+
+@pytest.mark.parametrize("peers", [2, 4])
+def test_exchange_over_peer_memory_on_one_gpu(mz, oracle, peers):
+    """The peer-memory exchange (k_p2p_scatter / k_p2p_gather: partition + delivery in one kernel,
+    flags and counts in the landing zones, compaction on the receiver) with every worker running
+    on ONE GPU (zones mapped in-process): several rounds, R32 and RACC buffers of uneven sizes,
+    an empty buffer, a worker that sends nothing -- every destination receives exactly the rows
+    the oracle's routing function sends it, grouped by source worker in worker order."""
+    rng = np.random.default_rng(500 + peers)
+    ctxs = [mz.Context(0, w, peers) for w in range(peers)]
+    mz.p2p_connect_local(ctxs, 40000, 80)
+    for rnd in range(5):
+        ins = []
+        for w in range(peers):
+            n1 = 0 if (w == 1 and rnd == 2) else int(rng.integers(1, 30000))
+            a = rand_r32(rng, n1, 1 << 40, 1 << 30, 4, dtype=mz.R32)
+            b = np.zeros(int(rng.integers(0, 9000)), dtype=mz.RACC)
+            b["key"] = rng.integers(0, 1 << 63, size=len(b), dtype=np.uint64)
+            b["total"] = rng.integers(-5, 5, size=len(b), dtype=np.int64)
+            e = np.zeros(0, dtype=mz.R32)
+            ins.append([a, b, e])
+        dev = [[mz.DeviceRows(c, x.dtype.itemsize).upload(x) for x in ins[w]] for w, c in enumerate(ctxs)]
+        outs = [[mz.DeviceRows(c, x.dtype.itemsize) for x in ins[w]] for w, c in enumerate(ctxs)]
+        for w, c in enumerate(ctxs):
+            mz.exchange_p2p_send(c, dev[w])
+        for w, c in enumerate(ctxs):
+            mz.exchange_p2p_recv(c, outs[w], None if rnd % 2 else [200000, 200000, 10])
+        for d in range(peers):
+            for e in range(3):
+                got = outs[d][e].download()
+                at = 0
+                for s_ in range(peers):
+                    x = ins[s_][e]
+                    dest = np.array([oracle.lib().mzo_route(int(k), peers) for k in x["key"]], dtype=np.int64)
+                    want = x[dest == d]
+                    assert multiset(got[at : at + len(want)]) == multiset(want), (rnd, d, e, s_)
+                    at += len(want)
+                assert at == len(got)
+    for c in ctxs:
+        c.sync()
+        c.close()
 
 
 def test_q3_dataflow_matches_oracle(mz, ctx, oracle):
