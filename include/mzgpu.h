@@ -544,6 +544,27 @@ int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows, uint64_t 
 /* The input arrangement (for sharing / inspection). Borrowed. */
 mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r);
 
+/* --------------------------------- f3: the MV sink's correction buffer */
+/* CorrectionV2 (src/compute/src/sink/correction_v2.rs:213-498): the difference between the
+ * desired and the persisted contents of a materialized view, as R32 updates
+ * ((key, val), time, diff).  insert / insert_negated add (negated) updates, with times
+ * advanced to `since`; updates_before(upper) appends to `out` every update whose advanced
+ * time is before `upper`, consolidated and ordered by (time, key, val) (nothing if
+ * !(since < upper)); advance_since moves `since` forward (MZGPU_FRONTIER_EMPTY discards
+ * everything); consolidate_at_since compacts the updates at `since`.  The reference's chains
+ * of chunks are an amortisation device of the CPU implementation: here inserts are stashed
+ * and a read consolidates everything buffered in one pass (same results). */
+typedef struct mzgpu_correction mzgpu_correction;
+int32_t mzgpu_correction_new(mzgpu_ctx* ctx, mzgpu_correction** out);
+void mzgpu_correction_free(mzgpu_correction* c);
+int32_t mzgpu_correction_insert(mzgpu_correction* c, const mzgpu_r32* rows, uint64_t n, int32_t mem, int32_t negate);
+int32_t mzgpu_correction_insert_buf(mzgpu_correction* c, mzgpu_buf* rows, int32_t negate);
+int32_t mzgpu_correction_updates_before(mzgpu_correction* c, uint64_t upper, mzgpu_buf* out);
+int32_t mzgpu_correction_advance_since(mzgpu_correction* c, uint64_t since);
+int32_t mzgpu_correction_consolidate_at_since(mzgpu_correction* c);
+/* Updates held (after consolidating what is buffered; waits for the device). */
+uint64_t mzgpu_correction_len(mzgpu_correction* c);
+
 /* ------------------------------------------------------- a13: exchange */
 /* Bytes of the NCCL unique id passed to mzgpu_comm_init. */
 #define MZGPU_COMM_ID_BYTES 128

@@ -28,6 +28,7 @@ from .api import (  # noqa: F401
     Builder,
     Closure,
     Context,
+    Correction,
     DeviceRows,
     JoinCore,
     MzGpuError,

@@ -181,6 +181,14 @@ SIGNATURES = {
     "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
     "mzgpu_partition_many": (i32, [vp, u32, PV, u32, PV, PU64]),
+    "mzgpu_correction_new": (i32, [vp, PV]),
+    "mzgpu_correction_free": (None, [vp]),
+    "mzgpu_correction_insert": (i32, [vp, vp, u64, i32, i32]),
+    "mzgpu_correction_insert_buf": (i32, [vp, vp, i32]),
+    "mzgpu_correction_updates_before": (i32, [vp, u64, vp]),
+    "mzgpu_correction_advance_since": (i32, [vp, u64]),
+    "mzgpu_correction_consolidate_at_since": (i32, [vp]),
+    "mzgpu_correction_len": (u64, [vp]),
     "mzgpu_comm_p2p_export": (i32, [vp, u64, u32, C.POINTER(C.c_uint8)]),
     "mzgpu_comm_p2p_import": (i32, [vp, C.POINTER(C.c_uint8)]),
     "mzgpu_comm_p2p_zone": (vp, [vp]),

@@ -606,3 +606,39 @@ def exchange_p2p_recv(ctx, outs, recv_ub=None):
     a = (C.c_void_p * len(outs))(*[b.h for b in outs])
     ub = (C.c_uint64 * len(outs))(*recv_ub) if recv_ub is not None else None
     ctx.check(F.lib.mzgpu_exchange_p2p_recv(ctx.h, len(outs), a, ub))
+
+
+class Correction:
+    """The MV sink's correction buffer on the device (CorrectionV2, src/compute/src/sink/correction_v2.rs)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_correction_new(ctx.h, C.byref(h)))
+        self.h = h
+
+    def insert(self, rows, negate=False):
+        rows = np.ascontiguousarray(rows)
+        self.ctx.check(F.lib.mzgpu_correction_insert(self.h, _ptr(rows), len(rows), F.MEM_HOST, 1 if negate else 0))
+
+    def insert_buf(self, dev_rows, negate=False):
+        self.ctx.check(F.lib.mzgpu_correction_insert_buf(self.h, dev_rows.h, 1 if negate else 0))
+
+    def updates_before(self, upper):
+        out = DeviceRows(self.ctx, 32)
+        self.ctx.check(F.lib.mzgpu_correction_updates_before(self.h, upper, out.h))
+        return out.download()
+
+    def advance_since(self, since):
+        self.ctx.check(F.lib.mzgpu_correction_advance_since(self.h, since))
+
+    def consolidate_at_since(self):
+        self.ctx.check(F.lib.mzgpu_correction_consolidate_at_since(self.h))
+
+    def __len__(self):
+        return F.lib.mzgpu_correction_len(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_correction_free(self.h)
+            self.h = None

@@ -764,11 +764,15 @@ struct ProbeJobHost {
 int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs);
 // tiles the single-pass probe cuts `n_ub` probe rows into (rows per tile shrink with the trace's
 // batch count so that a tile's hit list fits in shared memory)
-static inline u64 mz_probe_tile_rows(u32 n_batches) {
-  return n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
+static inline u64 mz_probe_tile_rows(u64 n_ub, u32 n_batches) {
+  const u64 by_hits = n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
+  // update-batch sized streams: 64-row tiles (a few hundred tiles that all run at once, each with
+  // a short candidate walk); bulk streams: as many rows as the hit list allows
+  const u64 by_size = n_ub <= (4ull << 20) ? 64u : 256u;
+  return by_hits < by_size ? by_hits : by_size;
 }
 static inline u64 mz_probe_tiles(u64 n_ub, u32 n_batches) {
-  const u64 tr = mz_probe_tile_rows(n_batches);
+  const u64 tr = mz_probe_tile_rows(n_ub, n_batches);
   return (n_ub + tr - 1) / tr;
 }
 // Probe `n` R32 stream rows against the trace; appends results to d_out
@@ -802,6 +806,14 @@ int32_t mz_reduce_corrections_async(mzgpu_ctx* ctx, const u64* d_batch_rows, DLe
                                     u64* d_out_len);
 int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, const TraceView& prior,
                               int agg_kind, DevMem* out, u64* n_out);
+
+// correction.cu (time-major rows: (time, key, val | diff))
+int32_t mz_corr_to_td(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, u64 since, bool negate, u64* d_td, DLen base,
+                      u64 cap_rows, u64* d_out_len);
+int32_t mz_corr_advance(mzgpu_ctx* ctx, u64* d_td, DLen n, u64 n_ub, u64 since);
+int32_t mz_corr_split(mzgpu_ctx* ctx, const u64* d_td, DLen n, u64 upper, u64* d_out);
+int32_t mz_corr_from_td(mzgpu_ctx* ctx, const u64* d_td, DLen n, u64 n_ub, u64* d_dst, DLen base, u64 cap_rows,
+                        u64* d_out_len);
 
 // exchange.cu
 #define MZ_MAX_EXCHANGE 8

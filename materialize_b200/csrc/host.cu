@@ -2557,6 +2557,129 @@ extern "C" int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows
   return reduce_dev(r, rows->mem.as<u64>(), buf_dlen(rows), rows->ub, upper, out);
 }
 
+// ============================================================ correction buffer (f3)
+struct mzgpu_correction {
+  mzgpu_ctx* ctx;
+  mzgpu_buf td;        // time-major rows (time, key, val | diff); sorted + consolidated iff !dirty
+  u64 since = 0;       // Timestamp::MIN
+  u64 applied = 0;     // the stored rows' times have been advanced to this
+  bool dirty = false;  // rows were appended since the last consolidation
+};
+extern "C" int32_t mzgpu_correction_new(mzgpu_ctx* ctx, mzgpu_correction** out) {
+  MZ_CHECK_CTX(ctx);
+  if (out == nullptr) return MZGPU_E_INVALID;
+  mzgpu_correction* c = new mzgpu_correction();
+  c->ctx = ctx;
+  c->td.ctx = ctx;
+  c->td.rb = 32;
+  buf_set_len(&c->td, 0);
+  *out = c;
+  return MZGPU_OK;
+}
+extern "C" void mzgpu_correction_free(mzgpu_correction* c) { delete c; }
+static int32_t correction_insert_dev(mzgpu_correction* c, const u64* d_rows, DLen n, u64 n_ub, bool negate) {
+  if (c->since == MZGPU_FRONTIER_EMPTY || n_ub == 0) return MZGPU_OK;  // the empty since discards everything
+  mzgpu_ctx* ctx = c->ctx;
+  MZ_TRY(buf_reserve(&c->td, c->td.ub + n_ub, true));
+  Append a;
+  MZ_TRY(buf_begin_append(&c->td, &a));
+  MZ_TRY(mz_corr_to_td(ctx, d_rows, n, n_ub, c->since, negate, c->td.mem.as<u64>(), a.base, c->td.cap, a.out_len));
+  buf_end_append(&c->td, a, n_ub);
+  c->dirty = true;
+  ctx->stats.rows_in += n_ub;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_correction_insert(mzgpu_correction* c, const mzgpu_r32* rows, uint64_t n, int32_t mem,
+                                           int32_t negate) {
+  if (c == nullptr || (rows == nullptr && n)) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(c->ctx);
+  if (n == 0) return MZGPU_OK;
+  DevMem in;
+  const u64* d_rows = (const u64*)rows;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(in.alloc(c->ctx, n * 32));
+    MZ_TRY(copy_in(c->ctx, in.p, rows, n * 32, mem));
+    d_rows = in.as<u64>();
+  }
+  return correction_insert_dev(c, d_rows, dlen_imm(n), n, negate != 0);
+}
+extern "C" int32_t mzgpu_correction_insert_buf(mzgpu_correction* c, mzgpu_buf* rows, int32_t negate) {
+  if (c == nullptr || rows == nullptr || rows->rb != 32) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(c->ctx);
+  return correction_insert_dev(c, rows->mem.as<u64>(), buf_dlen(rows), rows->ub, negate != 0);
+}
+// everything buffered: times advanced to `since`, sorted by (time, data), consolidated
+static int32_t correction_consolidate(mzgpu_correction* c) {
+  mzgpu_ctx* ctx = c->ctx;
+  if (c->since == MZGPU_FRONTIER_EMPTY) {
+    buf_set_len(&c->td, 0);
+    c->dirty = false;
+    return MZGPU_OK;
+  }
+  if (c->td.ub == 0 || (!c->dirty && c->applied == c->since)) return MZGPU_OK;
+  if (c->applied != c->since) MZ_TRY(mz_corr_advance(ctx, c->td.mem.as<u64>(), buf_dlen(&c->td), c->td.ub, c->since));
+  DevMem cons;
+  u64 cap = 0;
+  Lazy4 len;
+  MZ_TRY(consolidate_dev(ctx, 32, c->td.mem.p, buf_dlen(&c->td), c->td.ub, &cons, &cap, &len));
+  const u64 ub = len.known ? len.v[0] : c->td.ub;
+  c->td.mem = std::move(cons);
+  c->td.cap = cap;
+  c->td.len = std::move(len);
+  c->td.word = 0;
+  c->td.ub = ub;
+  c->applied = c->since;
+  c->dirty = false;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_correction_updates_before(mzgpu_correction* c, uint64_t upper, mzgpu_buf* out) {
+  if (c == nullptr || out == nullptr || out->rb != 32) return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = c->ctx;
+  MZ_CHECK_CTX(ctx);
+  // PartialOrder::less_than(since, upper) on one-element antichains (correction_v2.rs:285)
+  const bool since_lt_upper = c->since != MZGPU_FRONTIER_EMPTY && (upper == MZGPU_FRONTIER_EMPTY || c->since < upper);
+  if (!since_lt_upper) return MZGPU_OK;
+  MZ_TRY(correction_consolidate(c));
+  if (c->td.ub == 0) return MZGPU_OK;
+  Lazy4 cut;
+  MZ_TRY(cut.make_pending(ctx));
+  MZ_TRY(mz_corr_split(ctx, c->td.mem.as<u64>(), buf_dlen(&c->td), upper, cut.dptr()));
+  cut.mark_written();
+  MZ_TRY(buf_reserve(out, out->ub + c->td.ub, true));
+  Append a;
+  MZ_TRY(buf_begin_append(out, &a));
+  MZ_TRY(mz_corr_from_td(ctx, c->td.mem.as<u64>(), dlen_of(cut, 0), c->td.ub, out->mem.as<u64>(), a.base, out->cap,
+                         a.out_len));
+  buf_end_append(out, a, c->td.ub);
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_correction_advance_since(mzgpu_correction* c, uint64_t since) {
+  if (c == nullptr) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(c->ctx);
+  if (c->since != MZGPU_FRONTIER_EMPTY && since != MZGPU_FRONTIER_EMPTY && since < c->since) {
+    MZ_SET_ERR(c->ctx, "correction: since regresses from %llu to %llu", (unsigned long long)c->since,
+               (unsigned long long)since);
+    return MZGPU_E_FRONTIER;
+  }
+  c->since = since;
+  if (since == MZGPU_FRONTIER_EMPTY) {
+    buf_set_len(&c->td, 0);
+    c->dirty = false;
+  }
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_correction_consolidate_at_since(mzgpu_correction* c) {
+  if (c == nullptr) return MZGPU_E_INVALID;
+  MZ_CHECK_CTX(c->ctx);
+  return correction_consolidate(c);
+}
+extern "C" uint64_t mzgpu_correction_len(mzgpu_correction* c) {
+  if (c == nullptr || c->ctx->sticky) return 0;
+  if (correction_consolidate(c) != MZGPU_OK) return 0;
+  if (buf_resolve(&c->td) != MZGPU_OK) return 0;
+  return c->td.len.v[c->td.word];
+}
+
 // ================================================================= exchange
 struct NcclId {
   char internal[128];

@@ -115,9 +115,9 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 // Rows per tile shrink with the number of batches so that the hit list always fits
 // (hits <= rows x batches <= PROBE_HCAP).
 constexpr int PROBE_HCAP = 2048;
-__host__ __device__ __forceinline__ u32 probe_tile_rows(u32 n_batches) {
-  return n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
-}
+// (the host picks the rows per tile -- mz_probe_tile_rows, common.cuh -- and passes it down: at
+// most what the hit list allows, and 64 for update-batch sized streams, whose few hundred tiles
+// then all run at once and each has a short candidate walk)
 struct ProbeSmem {
   u32 scan[34];
   u32 tile;
@@ -205,10 +205,26 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
   const u64 h0 = mix64(key);
   // ---- 2. hits: count, scan, record (the second walk of the slots hits L1)
   u32 my_hits = 0, my_cand = 0, hit_off = 0, cand_off = 0;
+  const bool one_group = tv.n_batches <= (u32)GROUP;  // hits stay in registers: one walk of the slots
+  u64 reg_first[GROUP];
+  u32 reg_len[GROUP];
+#pragma unroll
+  for (int j = 0; j < GROUP; ++j) reg_len[j] = 0;
 #pragma unroll 1
   for (int phase = 0; phase < 2; ++phase) {
     u32 k_hit = 0, k_cand = 0;
-    if (live) {
+    if (phase == 1 && one_group) {
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j)
+        if (reg_len[j] != 0) {
+          const u32 h = hit_off + k_hit;
+          S.hit_first[h] = reg_first[j] | ((u64)j << 48);
+          S.hit_row[h] = (uint16_t)tid;
+          S.hit_pref[h] = cand_off + k_cand;
+          k_hit++;
+          k_cand += reg_len[j];
+        }
+    } else if (live) {
 #pragma unroll 1
       for (u32 b0 = 0; b0 < tv.n_batches; b0 += GROUP) {
         ulonglong2 slot[GROUP];
@@ -222,12 +238,16 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
             slot[j] = *reinterpret_cast<const ulonglong2*>(&bv.table[hh[j]]);
           }
         }
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < GROUP; ++j) {
           if (b0 + j >= tv.n_batches) break;
           u64 first;
           u32 len;
           if (!probe_slot_resolve(tv.b[b0 + j], key, slot[j], hh[j], msk[j], &first, &len)) continue;
+          if (phase == 0 && one_group) {
+            reg_first[j] = first;
+            reg_len[j] = len;
+          }
           if (phase == 1) {
             const u32 h = hit_off + k_hit;
             S.hit_first[h] = first | ((u64)(b0 + j) << 48);
@@ -262,69 +282,82 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
   u64 excl = 0;
   u32 total = 0;
   u64 wbase = 0;
+  constexpr int U = 4;  // candidates per lane and step: their searches and row loads overlap
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     u32 run = 0;
 #pragma unroll 1
-    for (u32 c0 = c_lo; c0 < c_hi; c0 += 32) {
-      const u32 c = c0 + lane;
-      bool keep = false;
-      u64 row[OUT_NW];
-      if (c < c_hi) {
-        // the hit this candidate belongs to: last h with hit_pref[h] <= c
-        u32 lo = 0, hi = n_hits;
-        while (hi - lo > 1) {
-          const u32 mid = (lo + hi) >> 1;
-          if (S.hit_pref[mid] <= c)
-            lo = mid;
-          else
-            hi = mid;
-        }
-        const u64 hf = S.hit_first[lo];
-        const BatchView& bv = tv.b[(u32)(hf >> 48)];
-        const u64 r = (hf & MZ_SLOT_ROW_MASK) + (u64)(c - S.hit_pref[lo]);
-        const u32 pr = S.hit_row[lo];
-        const ulonglong2 rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
-        const ulonglong2 rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
-        const u64 pk = S.key[pr], pv = S.v1[pr], pt = S.t1[pr];
-        const u64 t2 = rtd.x;
-        keep = pp.mode == MZ_PROBE_HALF_LE ? t2 <= pt : (pp.mode == MZ_PROBE_HALF_LT ? t2 < pt : true);
-        if (keep) {
-          u64 t = pt;
-          if (pp.mode == MZ_PROBE_JOIN) {
-            t = pt > t2 ? pt : t2;
-            t = t > pp.meet ? t : pp.meet;
-          }
-          const u64 d = S.d1[pr] * rtd.y;
-          const u64 va = pp.swap_vals ? rkv.y : pv, vb = pp.swap_vals ? pv : rkv.y;
-          if (OUT_NW == 4) {
-            u64 k, v;
-            keep = closure_eval(pp.closure, pk, va, vb, &k, &v);
-            row[0] = k;
-            row[1] = v;
-            row[2] = t;
-            row[3] = d;
-          } else {
-            row[0] = pk;
-            row[1] = va;
-            row[2] = vb;
-            row[3] = t;
-            row[OUT_NW - 1] = d;
-          }
-        }
-      }
-      const u32 m = __ballot_sync(0xffffffffu, keep);
-      if (pass == 1 && keep) {
-        const u64 pos = wbase + run + __popc(m & ((1u << lane) - 1));
-        if (pos >= out_cap) {
-          atomicMax((unsigned long long*)status, (unsigned long long)(pos + 1));
-        } else {
-          u64* o = out + pos * OUT_NW;
+    for (u32 c0 = c_lo; c0 < c_hi; c0 += 32 * U) {
+      bool keep[U];
+      u64 row[U][OUT_NW];
+      ulonglong2 rkv[U], rtd[U];
+      u32 pr[U];
 #pragma unroll
-          for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
+      for (int u = 0; u < U; ++u) {
+        const u32 c = c0 + u * 32 + lane;
+        keep[u] = c < c_hi;
+        pr[u] = 0;
+        if (keep[u]) {
+          // the hit this candidate belongs to: last h with hit_pref[h] <= c
+          u32 lo = 0, hi = n_hits;
+          while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if (S.hit_pref[mid] <= c)
+              lo = mid;
+            else
+              hi = mid;
+          }
+          const u64 hf = S.hit_first[lo];
+          const BatchView& bv = tv.b[(u32)(hf >> 48)];
+          const u64 r = (hf & MZ_SLOT_ROW_MASK) + (u64)(c - S.hit_pref[lo]);
+          pr[u] = S.hit_row[lo];
+          rkv[u] = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+          rtd[u] = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
         }
       }
-      run += __popc(m);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (keep[u]) {
+          const u64 pk = S.key[pr[u]], pv = S.v1[pr[u]], pt = S.t1[pr[u]];
+          const u64 t2 = rtd[u].x;
+          keep[u] = pp.mode == MZ_PROBE_HALF_LE ? t2 <= pt : (pp.mode == MZ_PROBE_HALF_LT ? t2 < pt : true);
+          if (keep[u]) {
+            u64 t = pt;
+            if (pp.mode == MZ_PROBE_JOIN) {
+              t = pt > t2 ? pt : t2;
+              t = t > pp.meet ? t : pp.meet;
+            }
+            const u64 d = S.d1[pr[u]] * rtd[u].y;
+            const u64 va = pp.swap_vals ? rkv[u].y : pv, vb = pp.swap_vals ? pv : rkv[u].y;
+            if (OUT_NW == 4) {
+              u64 k, v;
+              keep[u] = closure_eval(pp.closure, pk, va, vb, &k, &v);
+              row[u][0] = k;
+              row[u][1] = v;
+              row[u][2] = t;
+              row[u][3] = d;
+            } else {
+              row[u][0] = pk;
+              row[u][1] = va;
+              row[u][2] = vb;
+              row[u][3] = t;
+              row[u][OUT_NW - 1] = d;
+            }
+          }
+        }
+        const u32 m = __ballot_sync(0xffffffffu, keep[u]);
+        if (pass == 1 && keep[u]) {
+          const u64 pos = wbase + run + __popc(m & ((1u << lane) - 1));
+          if (pos >= out_cap) {
+            atomicMax((unsigned long long*)status, (unsigned long long)(pos + 1));
+          } else {
+            u64* o = out + pos * OUT_NW;
+#pragma unroll
+            for (int w = 0; w < OUT_NW; ++w) o[w] = row[u][w];
+          }
+        }
+        run += __popc(m);
+      }
     }
     if (pass == 0) {
       if (lane == 0) S.warp_keep[warp] = run;
@@ -350,10 +383,10 @@ __global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stre
                                                  const __grid_constant__ TraceView tv,
                                                  const __grid_constant__ ProbeParams pp, const LookBack lb,
                                                  u64* __restrict__ out, const DLen out_base, u64 out_cap,
-                                                 u64* __restrict__ out_len, u64* __restrict__ status) {
+                                                 u64* __restrict__ out_len, u64* __restrict__ status, u32 tile_rows) {
   __shared__ ProbeSmem S;
   const u64 n = dlen_get(dn);
-  const u32 TR = probe_tile_rows(tv.n_batches);
+  const u32 TR = tile_rows;
   const u64 n_tiles = (n + TR - 1) / TR;
   const u64 base0 = dlen_get(out_base);
   ProbePre pre;
@@ -392,6 +425,7 @@ struct ProbeJobDev {
   int has_pre, pre_has_closure;
   u64 skip_time;
   mzgpu_closure pre;
+  u32 tile_rows;  // probe rows per tile (mz_probe_tile_rows)
 };
 struct ProbeChain {
   u32 first, count;  // jobs [first, first + count)
@@ -419,7 +453,7 @@ __global__ void __launch_bounds__(PT, 3) k_probe_chains(const __grid_constant__ 
 #pragma unroll
   for (int q = 0; q < PROBE_MANY_MAX; ++q) {
     nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
-    trj[q] = (u32)q < ch.count ? probe_tile_rows(m.job[ch.first + q].tv.n_batches) : 256u;
+    trj[q] = (u32)q < ch.count ? m.job[ch.first + q].tile_rows : 256u;
     tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
   }
   const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
@@ -690,15 +724,16 @@ int32_t mz_probe_async(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_ub, co
                        const ProbeParams& pp, u64* d_out, DLen out_base, u64 out_cap, u64* d_out_len) {
   LookBack lb;
   const u64 tiles = mz_probe_tiles(n_ub, trace.n_batches);
+  const u32 tr = (u32)mz_probe_tile_rows(n_ub, trace.n_batches);
   MZ_TRY(mz_lookback_begin(ctx, tiles, &lb));
   const int out_rb = pp.has_closure ? 32 : 40;
   MZ_BYTES(ctx, n.p == nullptr ? n.imm * (32 + 16 * trace.n_batches + 32 + out_rb) : 0);  // exact counts only
   if (pp.has_closure) {
     MZ_LAUNCH(ctx, (k_probe_lb<4>), probe_grid(ctx, tiles), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base, out_cap,
-              d_out_len, ctx->d_status);
+              d_out_len, ctx->d_status, tr);
   } else {
     MZ_LAUNCH(ctx, (k_probe_lb<5>), probe_grid(ctx, tiles), PT, 0, d_stream, n, trace, pp, lb, d_out, out_base, out_cap,
-              d_out_len, ctx->d_status);
+              d_out_len, ctx->d_status, tr);
   }
   return MZGPU_OK;
 }
@@ -729,6 +764,7 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     m.job[j].pre_has_closure = (jobs[j].has_pre && jobs[j].pre != nullptr) ? 1 : 0;
     m.job[j].skip_time = jobs[j].skip_time;
     if (m.job[j].pre_has_closure) m.job[j].pre = *jobs[j].pre;
+    m.job[j].tile_rows = (u32)mz_probe_tile_rows(jobs[j].n_ub, jobs[j].trace->n_batches);
     if (j == 0 || jobs[j].chain != jobs[j - 1].chain) {
       ProbeChain& c = m.chain[nc++];
       c.first = (u32)j;

@@ -1026,6 +1026,52 @@ def test_exchange_over_peer_memory_on_one_gpu(mz, oracle, peers):
         c.close()
 
 
+def test_device_correction_buffer_matches_oracle(mz, ctx, oracle):
+    """CorrectionV2 on the device (f3): the same random sequence of insert / insert_negated /
+    advance_since / consolidate_at_since / updates_before drives the oracle's chain-of-chunks
+    restatement and the GPU buffer; every read returns the same rows in the same (time, data)
+    order, at update-batch sizes as well as in the small."""
+    EMPTY = mz.FRONTIER_EMPTY
+    for seed, scale in ((1, 1), (2, 1), (3, 400)):
+        rng = np.random.default_rng(600 + seed)
+        g, o = mz.Correction(ctx), oracle.Correction(3.0, 64)
+        since = 0
+        for step in range(50):
+            op = rng.integers(0, 10)
+            if op < 5:
+                n = int(rng.integers(0, 90)) * scale
+                a = np.zeros(n, dtype=oracle.R32)
+                a["key"] = rng.integers(0, 40 * scale, size=n, dtype=np.uint64)
+                a["val"] = rng.integers(0, 3, size=n, dtype=np.uint64)
+                a["time"] = rng.integers(max(0, since - 3), since + 12, size=n, dtype=np.uint64)
+                a["diff"] = rng.integers(-2, 3, size=n)
+                neg = bool(rng.integers(0, 2))
+                if rng.integers(0, 2):
+                    g.insert(a, neg)
+                else:
+                    g.insert_buf(mz.DeviceRows(ctx, 32).upload(a), neg)
+                o.insert(a, neg)
+            elif op < 7:
+                since += int(rng.integers(0, 4))
+                g.advance_since(since)
+                o.advance_since(since)
+            elif op < 8:
+                g.consolidate_at_since()
+                o.consolidate_at_since()
+            else:
+                upper = max(since + int(rng.integers(-1, 8)), 0)
+                same(g.updates_before(upper), o.updates_before(upper))
+        same(g.updates_before(EMPTY), o.updates_before(EMPTY))
+        assert len(g) == len(o.updates_before(EMPTY))
+        # what was written comes back negated: the buffer empties; the empty since discards
+        rest = o.updates_before(EMPTY)
+        g.insert(rest, negate=True)
+        assert len(g.updates_before(EMPTY)) == 0 and len(g) == 0
+        g.advance_since(EMPTY)
+        g.insert(rest)
+        assert len(g.updates_before(EMPTY)) == 0
+
+
 def test_q3_dataflow_matches_oracle(mz, ctx, oracle):
     """Hydration + update batches through the C++ harness (delta join, 3 paths x 2
     half_joins, reduce) vs the CPU oracle dataflow on the same seeded inputs."""
