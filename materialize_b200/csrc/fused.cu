@@ -406,50 +406,54 @@ __device__ __forceinline__ void msd_warp_buckets2(const FusedArgs& a, FusedCtl* 
       }
     }
     // bitonic network over positions p = r*32 + lane, ordered by (hi, lo, idx): idx makes real
-    // elements distinct (and puts the padding last among equal keys)
-#pragma unroll
+    // elements distinct (and puts the padding last among equal keys).  The (k, j) stages are
+    // LOOPS: fully unrolled the network is ~2K instructions that every warp runs through once,
+    // and the kernel stalled on instruction fetch (profiles/r02b: 22-55 % "no_instructions").
+    // Stages with j >= 32 exchange whole register rows (static pairs), the others shuffle.
+    auto greater = [&](u64 h1, u64 l1, u32 i1, u64 h2, u64 l2, u32 i2) -> bool {
+      if (KW == 2) return h1 > h2 || (h1 == h2 && (l1 > l2 || (l1 == l2 && i1 > i2)));
+      return l1 > l2 || (l1 == l2 && i1 > i2);
+    };
+    auto local_exchange = [&](int r, int r2, int k) {
+      const bool up = (((r * 32 + (int)lane) & k) == 0);
+      if (greater(hi[r], lo[r], ix[r], hi[r2], lo[r2], ix[r2]) == up) {
+        u64 t0 = lo[r];
+        lo[r] = lo[r2];
+        lo[r2] = t0;
+        if (KW == 2) {
+          t0 = hi[r];
+          hi[r] = hi[r2];
+          hi[r2] = t0;
+        }
+        const u32 t1 = ix[r];
+        ix[r] = ix[r2];
+        ix[r2] = t1;
+      }
+    };
+#pragma unroll 1
     for (int k = 2; k <= 32 * R; k <<= 1) {
-#pragma unroll
+#pragma unroll 1
       for (int j = k >> 1; j > 0; j >>= 1) {
         if (j >= 32) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int r2 = r ^ (j >> 5);
-            if (r2 > r) {
-              const bool up = (((r * 32 + (int)lane) & k) == 0);
-              bool gt;
-              if (KW == 2)
-                gt = hi[r] > hi[r2] || (hi[r] == hi[r2] && (lo[r] > lo[r2] || (lo[r] == lo[r2] && ix[r] > ix[r2])));
-              else
-                gt = lo[r] > lo[r2] || (lo[r] == lo[r2] && ix[r] > ix[r2]);
-              if (gt == up) {
-                u64 t0 = lo[r];
-                lo[r] = lo[r2];
-                lo[r2] = t0;
-                if (KW == 2) {
-                  t0 = hi[r];
-                  hi[r] = hi[r2];
-                  hi[r2] = t0;
-                }
-                u32 t1 = ix[r];
-                ix[r] = ix[r2];
-                ix[r2] = t1;
-              }
+          // R <= 4: j == 64 pairs rows (0,2),(1,3); j == 32 pairs (0,1),(2,3)
+          if (j == 64) {
+            if (R >= 4) {
+              local_exchange(0, 2 < R ? 2 : 0, k);
+              local_exchange(1 < R ? 1 : 0, 3 < R ? 3 : 0, k);
             }
+          } else {
+            if (R >= 2) local_exchange(0, 1 < R ? 1 : 0, k);
+            if (R >= 4) local_exchange(2 < R ? 2 : 0, 3 < R ? 3 : 0, k);
           }
         } else {
+          const bool lower = ((lane & j) == 0);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const u64 olo = __shfl_xor_sync(0xffffffffu, lo[r], j);
             const u64 ohi = KW == 2 ? __shfl_xor_sync(0xffffffffu, hi[r], j) : 0ull;
             const u32 oix = __shfl_xor_sync(0xffffffffu, ix[r], j);
             const bool up = (((r * 32 + (int)lane) & k) == 0);
-            const bool lower = ((lane & j) == 0);
-            bool gt;
-            if (KW == 2)
-              gt = hi[r] > ohi || (hi[r] == ohi && (lo[r] > olo || (lo[r] == olo && ix[r] > oix)));
-            else
-              gt = lo[r] > olo || (lo[r] == olo && ix[r] > oix);
+            const bool gt = greater(hi[r], lo[r], ix[r], ohi, olo, oix);
             const bool take = (lower == up) ? gt : !gt;
             if (take) {
               lo[r] = olo;

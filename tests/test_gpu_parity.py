@@ -510,6 +510,98 @@ def test_join_core_with_closure(mz, ctx, oracle):
     same(oracle.consolidate(gj.results()), oracle.consolidate(oj.results()))
 
 
+def test_linear_join_two_stages_matches_oracle_and_bruteforce(mz, ctx, oracle):
+    """Row L: a linear join plan (src/compute/src/render/join/linear_join.rs:327-527) of three
+    inputs -- stage 1 joins A and B by k1, its result is re-arranged by the next stage's key k2
+    (the "JoinStage" arrangement: Batcher -> seal -> Spine) and stage 2 joins it with C by k2 --
+    run incrementally over several timestamps with retractions.  The GPU operators and the
+    oracle's produce the same stage-1 and final collections, and the accumulated final collection
+    equals the brute-force three-way join of the accumulated inputs."""
+    rng = np.random.default_rng(33)
+    # A: (k1, a)   B: (k1, k2 << 20 | b)   C: (k2, c)
+    cl1 = dict(key_fields=[(2, 20, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 0, 20, 20)])  # key' = k2, val' = a | b << 20
+    cl2 = dict(key_fields=[(0, 0, 10, 0)], val_fields=[(1, 0, 40, 0), (2, 0, 20, 40)])  # val'' = a | b << 20 | c << 40
+    g = dict(A=mz.Spine(ctx, 32), B=mz.Spine(ctx, 32), S=mz.Spine(ctx, 32), C=mz.Spine(ctx, 32))
+    o = dict(A=oracle.Spine(32, 1, True), B=oracle.Spine(32, 1, True), S=oracle.Spine(32, 1, True), C=oracle.Spine(32, 1, True))
+    gj1, oj1 = mz.JoinCore(ctx, g["A"], g["B"], mz.make_closure(**cl1)), oracle.Join(o["A"], o["B"], oracle.make_closure(**cl1))
+    gj2, oj2 = mz.JoinCore(ctx, g["S"], g["C"], mz.make_closure(**cl2)), oracle.Join(o["S"], o["C"], oracle.make_closure(**cl2))
+    gstage, ostage = mz.Batcher(ctx, 32), oracle.Batcher(32)
+    acc = dict(A=[], B=[], C=[])
+    g1_seen = o1_seen = g2_seen = o2_seen = 0
+    for t in range(6):
+        ins = {}
+        for name, (kh, n) in dict(A=(60, 500), B=(60, 400), C=(40, 300)).items():
+            x = np.zeros(n, dtype=oracle.R32)
+            x["key"] = rng.integers(0, kh, size=n, dtype=np.uint64)
+            x["val"] = rng.integers(0, 50, size=n, dtype=np.uint64)
+            if name == "B":
+                x["val"] |= rng.integers(0, 40, size=n, dtype=np.uint64) << np.uint64(20)
+            x["time"] = t
+            x["diff"] = rng.integers(-1, 3, size=n)
+            if t >= 2 and acc[name]:  # retract some of what an earlier timestamp added
+                old = acc[name][t - 2][:100].copy()
+                old["time"] = t
+                old["diff"] = -old["diff"]
+                x = np.concatenate([x, old])
+            ins[name] = x
+            acc[name].append(x)
+        # stage 1
+        for side, name in enumerate(("A", "B")):
+            gb, ob = mz.Batch.build(ctx, ins[name], t, t + 1), oracle.Batch.build(ins[name], t, t + 1)
+            g[name].insert(gb)
+            o[name].insert(ob)
+            gj1.push(side, gb, t)
+            oj1.push(side, ob, t)
+        gj1.work()
+        oj1.work()
+        gr, orr = gj1.results(), oj1.results()
+        g_new, o_new = gr[g1_seen:], orr[o1_seen:]
+        g1_seen, o1_seen = len(gr), len(orr)
+        same(oracle.consolidate(g_new), oracle.consolidate(o_new))
+        # the stage arrangement ("JoinStage"): re-arrange the running result by k2
+        gstage.push_container(g_new)
+        ostage.push(o_new)
+        gsb, osb = gstage.seal(t + 1), ostage.seal(t + 1)
+        same(gsb.rows(), osb.rows())
+        g["S"].insert(gsb)
+        o["S"].insert(osb)
+        gj2.push(0, gsb, t)
+        oj2.push(0, osb, t)
+        gc, oc = mz.Batch.build(ctx, ins["C"], t, t + 1), oracle.Batch.build(ins["C"], t, t + 1)
+        g["C"].insert(gc)
+        o["C"].insert(oc)
+        gj2.push(1, gc, t)
+        oj2.push(1, oc, t)
+        gj2.work()
+        oj2.work()
+        gr2, or2 = gj2.results(), oj2.results()
+        same(oracle.consolidate(gr2[g2_seen:]), oracle.consolidate(or2[o2_seen:]))
+        g2_seen, o2_seen = len(gr2), len(or2)
+        for sp in list(g.values()) + list(o.values()):
+            sp.set_physical_compaction(t + 1)
+    # accumulated final collection (times collapsed) == brute-force three-way join
+    final = gj2.results().copy()
+    final["time"] = 0
+    final = oracle.consolidate(final)
+    A, B, Cc = (np.concatenate(acc[n]) for n in ("A", "B", "C"))
+    for x in (A, B, Cc):
+        x["time"] = 0
+    A, B, Cc = oracle.consolidate(A), oracle.consolidate(B), oracle.consolidate(Cc)
+    by_b, by_c = {}, {}
+    for k, v, _, d in B.tolist():
+        by_b.setdefault(k, []).append((v >> 20, v & 0xFFFFF, d))
+    for k, v, _, d in Cc.tolist():
+        by_c.setdefault(k, []).append((v, d))
+    want = {}
+    for k1, a, _, da in A.tolist():
+        for k2, b, db in by_b.get(k1, ()):
+            for c, dc in by_c.get(k2, ()):
+                key = (k2, a | (b << 20) | (c << 40))
+                want[key] = want.get(key, 0) + da * db * dc
+    want = sorted((k, v, 0, d) for (k, v), d in want.items() if d != 0)
+    assert [tuple(r) for r in final.tolist()] == want
+
+
 # ---------------------------------------------------------------- a10
 @pytest.mark.parametrize("cmp_mode", [0, 1])
 def test_half_join_matches_oracle(mz, ctx, oracle, cmp_mode):
