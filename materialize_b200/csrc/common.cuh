@@ -765,11 +765,10 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs);
 // tiles the single-pass probe cuts `n_ub` probe rows into (rows per tile shrink with the trace's
 // batch count so that a tile's hit list fits in shared memory)
 static inline u64 mz_probe_tile_rows(u64 n_ub, u32 n_batches) {
-  const u64 by_hits = n_batches <= 8 ? 256u : (n_batches <= 16 ? 128u : (n_batches <= 32 ? 64u : 32u));
-  // update-batch sized streams: 64-row tiles (a few hundred tiles that all run at once, each with
-  // a short candidate walk); bulk streams: as many rows as the hit list allows
-  const u64 by_size = n_ub <= (4ull << 20) ? 64u : 256u;
-  return by_hits < by_size ? by_hits : by_size;
+  // 8 warps per tile, each with a private hit list of 256 entries: rows per warp x batches <= 256
+  (void)n_ub;
+  const u64 per_warp = n_batches <= 8 ? 32u : (n_batches <= 16 ? 16u : (n_batches <= 32 ? 8u : 4u));
+  return 8 * per_warp;
 }
 static inline u64 mz_probe_tiles(u64 n_ub, u32 n_batches) {
   const u64 tr = mz_probe_tile_rows(n_ub, n_batches);

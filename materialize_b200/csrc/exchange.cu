@@ -402,8 +402,10 @@ int32_t mz_p2p_send(mzgpu_ctx* ctx, u32 k, const int* row_bytes, const void* con
   }
   P2PView v;
   p2p_view(ctx, k, &v);
-  u64 blocks = (max_ub + XT - 1) / XT;
-  const u64 maxb = (u64)ctx->num_sms * 2;
+  // few, fat CTAs: every CTA ends with a system-wide fence (its peer stores must have landed
+  // before it counts itself done), and the last one waits for all of them
+  u64 blocks = (max_ub + 4 * XT - 1) / (4 * XT);
+  const u64 maxb = std::max<u64>(1, (u64)ctx->num_sms / k);
   if (blocks > maxb) blocks = maxb;
   if (blocks == 0) blocks = 1;
   MZ_LAUNCH(ctx, k_p2p_scatter, dim3((unsigned)blocks, k), XT, 0, jobs, v, (unsigned long long*)ctx->p2p_cursors,

@@ -114,19 +114,17 @@ __device__ __forceinline__ void for_each_match(const TraceView& tv, u64 key, u64
 //      inside either walk.
 // Rows per tile shrink with the number of batches so that the hit list always fits
 // (hits <= rows x batches <= PROBE_HCAP).
-constexpr int PROBE_HCAP = 2048;
-// (the host picks the rows per tile -- mz_probe_tile_rows, common.cuh -- and passes it down: at
-// most what the hit list allows, and 64 for update-batch sized streams, whose few hundred tiles
-// then all run at once and each has a short candidate walk)
+constexpr int PROBE_WHCAP = 256;  // hits one WARP's share of a tile can hold (rows x batches)
+struct ProbeWarpSmem {
+  u32 hit_pref[PROBE_WHCAP + 1];  // candidates before hit h (exclusive); [n_hits] = all candidates
+  u64 hit_first[PROBE_WHCAP];     // first row of the run | batch index << 48
+  uint8_t hit_lane[PROBE_WHCAP];  // lane that owns the probe row
+};
 struct ProbeSmem {
-  u32 scan[34];
   u32 tile;
   u64 bcast;
   u32 warp_keep[PT / 32];
-  u32 hit_pref[PROBE_HCAP + 1];  // candidates before hit h (exclusive); [n_hits] = all candidates
-  u64 hit_first[PROBE_HCAP];     // first row of the run | batch index << 48
-  uint16_t hit_row[PROBE_HCAP];       // probe row (thread) the hit belongs to
-  u64 key[PT], v1[PT], t1[PT], d1[PT];  // the tile's probe rows (after the optional pre-map)
+  ProbeWarpSmem w[PT / 32];
 };
 
 struct ProbePre {  // optional map in front of the probe (build_update_stream fused in)
@@ -164,19 +162,35 @@ __device__ __forceinline__ bool probe_slot_resolve(const BatchView& bv, u64 key,
   return true;
 }
 
-// One tile: probe rows [row0, row0 + TR) of `stream` (n rows) against `tv`.  Returns through
-// *tile_total the rows the tile appended; `excl_out` the look-back prefix it was given.
+__device__ __forceinline__ u32 warp_exclusive_scan(u32 v, u32* total) {
+  const u32 lane = threadIdx.x & 31;
+  u32 incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const u32 o = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= (u32)off) incl += o;
+  }
+  *total = __shfl_sync(0xffffffffu, incl, 31);
+  return incl - v;
+}
+
+// One tile: probe rows [row0, row0 + 8 * TRW) of `stream` (n rows) against `tv`: warp w takes rows
+// [row0 + w * TRW, + TRW), one per lane.  The warps of the CTA run on their own -- private hit
+// lists, warp scans, no block barrier -- up to the point where the tile's total is needed for the
+// look-back (one barrier), so one warp's memory latency never stalls the other seven.
 template <int OUT_NW>
-__device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__ stream, u64 n, u64 row0, u32 TR,
+__device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__ stream, u64 n, u64 row0, u32 TRW,
                                            const TraceView& tv, const ProbeParams& pp, const ProbePre& pre,
                                            const LookBack& lb, u32 tile, u64* __restrict__ out, u64 base0,
                                            u64 out_cap, u64* __restrict__ status, u64* excl_out, u32* total_out) {
   constexpr int GROUP = 8;
+  constexpr int U = 4;  // candidates per lane and step: their searches and row loads overlap
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- 1. this thread's probe row
-  const u64 i = row0 + tid;
+  ProbeWarpSmem& W = S.w[warp];
+  // ---- 1. this lane's probe row
+  const u64 i = row0 + (u64)warp * TRW + lane;
   u64 key = 0, v1 = 0, t1 = 0, d1 = 0;
-  bool live = tid < TR && i < n;
+  bool live = lane < TRW && i < n;
   if (live) {
     const ulonglong2 kv = *reinterpret_cast<const ulonglong2*>(stream + i * 4);
     const ulonglong2 td = *reinterpret_cast<const ulonglong2*>(stream + i * 4 + 2);
@@ -198,14 +212,12 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
       }
     }
   }
-  S.key[tid] = key;
-  S.v1[tid] = v1;
-  S.t1[tid] = t1;
-  S.d1[tid] = d1;
   const u64 h0 = mix64(key);
-  // ---- 2. hits: count, scan, record (the second walk of the slots hits L1)
-  u32 my_hits = 0, my_cand = 0, hit_off = 0, cand_off = 0;
-  const bool one_group = tv.n_batches <= (u32)GROUP;  // hits stay in registers: one walk of the slots
+  // ---- 2. hits: first slot of every batch (independent loads), warp scans, private hit list.
+  // A trace of at most GROUP batches keeps its hits in registers (one walk of the slots); a
+  // longer one walks the slots twice (the second time from L1).
+  u32 hit_off = 0, cand_off = 0, n_hits = 0, n_cand = 0;
+  const bool one_group = tv.n_batches <= (u32)GROUP;
   u64 reg_first[GROUP];
   u32 reg_len[GROUP];
 #pragma unroll
@@ -218,9 +230,9 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
       for (int j = 0; j < GROUP; ++j)
         if (reg_len[j] != 0) {
           const u32 h = hit_off + k_hit;
-          S.hit_first[h] = reg_first[j] | ((u64)j << 48);
-          S.hit_row[h] = (uint16_t)tid;
-          S.hit_pref[h] = cand_off + k_cand;
+          W.hit_first[h] = reg_first[j] | ((u64)j << 48);
+          W.hit_lane[h] = (uint8_t)lane;
+          W.hit_pref[h] = cand_off + k_cand;
           k_hit++;
           k_cand += reg_len[j];
         }
@@ -250,9 +262,9 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
           }
           if (phase == 1) {
             const u32 h = hit_off + k_hit;
-            S.hit_first[h] = first | ((u64)(b0 + j) << 48);
-            S.hit_row[h] = (uint16_t)tid;
-            S.hit_pref[h] = cand_off + k_cand;
+            W.hit_first[h] = first | ((u64)(b0 + j) << 48);
+            W.hit_lane[h] = (uint8_t)lane;
+            W.hit_pref[h] = cand_off + k_cand;
           }
           k_hit++;
           k_cand += len;
@@ -260,119 +272,113 @@ __device__ __forceinline__ void probe_tile(ProbeSmem& S, const u64* __restrict__
       }
     }
     if (phase == 0) {
-      my_hits = k_hit;
-      my_cand = k_cand;
-      u32 tot_h, tot_c;
-      hit_off = block_exclusive_scan(my_hits, S.scan, &tot_h);
-      cand_off = block_exclusive_scan(my_cand, S.scan, &tot_c);
-      if (tid == 0) {
-        S.hit_pref[tot_h] = tot_c;
-        S.warp_keep[0] = tot_h;  // (borrowed: read back below, before the walks use it)
-      }
+      hit_off = warp_exclusive_scan(k_hit, &n_hits);
+      cand_off = warp_exclusive_scan(k_cand, &n_cand);
     }
   }
-  __syncthreads();
-  const u32 n_hits = S.warp_keep[0];
-  const u32 n_cand = S.hit_pref[n_hits];
-  __syncthreads();
-  // ---- 3. the candidate walks: warp w owns candidates [w * per, (w + 1) * per)
-  const u32 per = (n_cand + PT / 32 - 1) / (PT / 32);
-  const u32 c_lo = warp * per < n_cand ? warp * per : n_cand;
-  const u32 c_hi = c_lo + per < n_cand ? c_lo + per : n_cand;
-  u64 excl = 0;
-  u32 total = 0;
-  u64 wbase = 0;
-  constexpr int U = 4;  // candidates per lane and step: their searches and row loads overlap
+  if (lane == 0) W.hit_pref[n_hits] = n_cand;
+  __syncwarp();
+  // ---- 3. the candidate walk (pass 0 counts, pass 1 writes).  The first 32 * U candidates --
+  // all of them for most warps -- are evaluated once and kept in registers across the look-back.
+  auto eval = [&](u32 c, bool valid, u64* row) -> bool {
+    // the hit this candidate belongs to: last h with hit_pref[h] <= c
+    u32 lo = 0, hi = n_hits;
+    while (hi - lo > 1) {
+      const u32 mid = (lo + hi) >> 1;
+      if (W.hit_pref[mid] <= c)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    u32 owner = 0;
+    ulonglong2 rkv = make_ulonglong2(0, 0), rtd = make_ulonglong2(0, 0);
+    if (valid) {
+      const u64 hf = W.hit_first[lo];
+      const BatchView& bv = tv.b[(u32)(hf >> 48)];
+      const u64 r = (hf & MZ_SLOT_ROW_MASK) + (u64)(c - W.hit_pref[lo]);
+      owner = W.hit_lane[lo];
+      rkv = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
+      rtd = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
+    }
+    // the probe row lives in its owner lane's registers
+    const u64 pk = __shfl_sync(0xffffffffu, key, owner), pv = __shfl_sync(0xffffffffu, v1, owner);
+    const u64 pt = __shfl_sync(0xffffffffu, t1, owner), pd = __shfl_sync(0xffffffffu, d1, owner);
+    if (!valid) return false;
+    const u64 t2 = rtd.x;
+    bool keep = pp.mode == MZ_PROBE_HALF_LE ? t2 <= pt : (pp.mode == MZ_PROBE_HALF_LT ? t2 < pt : true);
+    if (!keep) return false;
+    u64 t = pt;
+    if (pp.mode == MZ_PROBE_JOIN) {
+      t = pt > t2 ? pt : t2;
+      t = t > pp.meet ? t : pp.meet;
+    }
+    const u64 d = pd * rtd.y;
+    const u64 va = pp.swap_vals ? rkv.y : pv, vb = pp.swap_vals ? pv : rkv.y;
+    if (OUT_NW == 4) {
+      u64 k, v;
+      keep = closure_eval(pp.closure, pk, va, vb, &k, &v);
+      row[0] = k;
+      row[1] = v;
+      row[2] = t;
+      row[3] = d;
+    } else {
+      row[0] = pk;
+      row[1] = va;
+      row[2] = vb;
+      row[3] = t;
+      row[OUT_NW - 1] = d;
+    }
+    return keep;
+  };
+  bool keep0[U];
+  u64 row0r[U][OUT_NW];
+  u32 run = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const u32 c = (u32)u * 32 + lane;
+    keep0[u] = eval(c, c < n_cand, row0r[u]);
+    run += __popc(__ballot_sync(0xffffffffu, keep0[u]));
+  }
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    u32 run = 0;
-#pragma unroll 1
-    for (u32 c0 = c_lo; c0 < c_hi; c0 += 32 * U) {
-      bool keep[U];
-      u64 row[U][OUT_NW];
-      ulonglong2 rkv[U], rtd[U];
-      u32 pr[U];
+  for (u32 c0 = 32 * U; c0 < n_cand; c0 += 32) {  // (rare: more than 128 candidates in one warp)
+    u64 row[OUT_NW];
+    const bool k = eval(c0 + lane, c0 + lane < n_cand, row);
+    run += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  // ---- 4. the tile's total, the look-back
+  if (lane == 0) S.warp_keep[warp] = run;
+  __syncthreads();
+  u32 mine = 0, total = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const u32 c = c0 + u * 32 + lane;
-        keep[u] = c < c_hi;
-        pr[u] = 0;
-        if (keep[u]) {
-          // the hit this candidate belongs to: last h with hit_pref[h] <= c
-          u32 lo = 0, hi = n_hits;
-          while (hi - lo > 1) {
-            const u32 mid = (lo + hi) >> 1;
-            if (S.hit_pref[mid] <= c)
-              lo = mid;
-            else
-              hi = mid;
-          }
-          const u64 hf = S.hit_first[lo];
-          const BatchView& bv = tv.b[(u32)(hf >> 48)];
-          const u64 r = (hf & MZ_SLOT_ROW_MASK) + (u64)(c - S.hit_pref[lo]);
-          pr[u] = S.hit_row[lo];
-          rkv[u] = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4);
-          rtd[u] = *reinterpret_cast<const ulonglong2*>(bv.rows + r * 4 + 2);
-        }
-      }
+  for (int w = 0; w < PT / 32; ++w) {
+    const u32 v = S.warp_keep[w];
+    if ((u32)w < warp) mine += v;
+    total += v;
+  }
+  const u64 excl = lb_exclusive_prefix(lb, tile, (u64)total, &S.bcast);
+  u64 pos = base0 + excl + mine;
+  // ---- 5. write
+  auto put = [&](bool keep, const u64* row) {
+    const u32 m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const u64 p = pos + __popc(m & ((1u << lane) - 1));
+      if (p >= out_cap) {
+        atomicMax((unsigned long long*)status, (unsigned long long)(p + 1));
+      } else {
+        u64* o = out + p * OUT_NW;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (keep[u]) {
-          const u64 pk = S.key[pr[u]], pv = S.v1[pr[u]], pt = S.t1[pr[u]];
-          const u64 t2 = rtd[u].x;
-          keep[u] = pp.mode == MZ_PROBE_HALF_LE ? t2 <= pt : (pp.mode == MZ_PROBE_HALF_LT ? t2 < pt : true);
-          if (keep[u]) {
-            u64 t = pt;
-            if (pp.mode == MZ_PROBE_JOIN) {
-              t = pt > t2 ? pt : t2;
-              t = t > pp.meet ? t : pp.meet;
-            }
-            const u64 d = S.d1[pr[u]] * rtd[u].y;
-            const u64 va = pp.swap_vals ? rkv[u].y : pv, vb = pp.swap_vals ? pv : rkv[u].y;
-            if (OUT_NW == 4) {
-              u64 k, v;
-              keep[u] = closure_eval(pp.closure, pk, va, vb, &k, &v);
-              row[u][0] = k;
-              row[u][1] = v;
-              row[u][2] = t;
-              row[u][3] = d;
-            } else {
-              row[u][0] = pk;
-              row[u][1] = va;
-              row[u][2] = vb;
-              row[u][3] = t;
-              row[u][OUT_NW - 1] = d;
-            }
-          }
-        }
-        const u32 m = __ballot_sync(0xffffffffu, keep[u]);
-        if (pass == 1 && keep[u]) {
-          const u64 pos = wbase + run + __popc(m & ((1u << lane) - 1));
-          if (pos >= out_cap) {
-            atomicMax((unsigned long long*)status, (unsigned long long)(pos + 1));
-          } else {
-            u64* o = out + pos * OUT_NW;
-#pragma unroll
-            for (int w = 0; w < OUT_NW; ++w) o[w] = row[u][w];
-          }
-        }
-        run += __popc(m);
+        for (int w = 0; w < OUT_NW; ++w) o[w] = row[w];
       }
     }
-    if (pass == 0) {
-      if (lane == 0) S.warp_keep[warp] = run;
-      __syncthreads();
-      u32 mine = 0;
-      total = 0;
+    pos += __popc(m);
+  };
 #pragma unroll
-      for (int w = 0; w < PT / 32; ++w) {
-        const u32 v = S.warp_keep[w];
-        if ((u32)w < warp) mine += v;
-        total += v;
-      }
-      excl = lb_exclusive_prefix(lb, tile, (u64)total, &S.bcast);
-      wbase = base0 + excl + mine;
-    }
+  for (int u = 0; u < U; ++u) put(keep0[u], row0r[u]);
+#pragma unroll 1
+  for (u32 c0 = 32 * U; c0 < n_cand; c0 += 32) {
+    u64 row[OUT_NW];
+    const bool k = eval(c0 + lane, c0 + lane < n_cand, row);
+    put(k, row);
   }
   *excl_out = excl;
   *total_out = total;
@@ -402,8 +408,8 @@ __global__ void __launch_bounds__(PT, 3) k_probe_lb(const u64* __restrict__ stre
     }
     u64 excl;
     u32 total;
-    probe_tile<OUT_NW>(S, stream, n, (u64)tile * TR, TR, tv, pp, pre, lb, tile, out, base0, out_cap, status, &excl,
-                       &total);
+    probe_tile<OUT_NW>(S, stream, n, (u64)tile * TR, TR / (PT / 32), tv, pp, pre, lb, tile, out, base0, out_cap, status,
+                       &excl, &total);
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *out_len = base0 + excl + total;
   }
 }
@@ -474,8 +480,8 @@ __global__ void __launch_bounds__(PT, 3) k_probe_chains(const __grid_constant__ 
     pre.pre = &J.pre;
     u64 excl;
     u32 total;
-    probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q], J.tv, J.pp, pre, ch.lb, tile,
-                       ch.out, base0, ch.out_cap, status, &excl, &total);
+    probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q] / (PT / 32), J.tv, J.pp, pre,
+                       ch.lb, tile, ch.out, base0, ch.out_cap, status, &excl, &total);
     if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
   }
 }
@@ -787,7 +793,10 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     }
     MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
     lb_at += tiles;
-    const u64 g = probe_grid(ctx, tiles);
+    // (all chains of a launch run side by side: each gets an equal share of the resident CTAs)
+    u64 g = probe_grid(ctx, tiles);
+    const u64 share = ((u64)ctx->num_sms * 3 + nc - 1) / (u64)nc;
+    if (g > share) g = share;
     if (g > max_grid) max_grid = g;
   }
   MZ_BYTES(ctx, bytes);

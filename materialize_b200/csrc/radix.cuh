@@ -12,8 +12,9 @@ constexpr u32 RS_VALUE_MASK = (1u << 30) - 1;
 
 template <int ITEMS, int THREADS = RS_THREADS>
 struct RsSmemT {
-  u64 keys[THREADS * ITEMS];
-  u32 vals[THREADS * ITEMS];
+  alignas(16) u64 keys[THREADS * ITEMS];
+  alignas(16) u32 vals[THREADS * ITEMS];
+  alignas(8) u64 mbar;  // TMA tile load: transaction barrier
   u32 whist[THREADS / 32][256];
   u32 digit_start[256];
   u32 gofs[256];
@@ -55,7 +56,37 @@ __device__ __forceinline__ u32 match_digit(u32 d) {
   return m;
 }
 
-template <int ITEMS, int THREADS = RS_THREADS, bool BALLOT = true>
+// ---- TMA (bulk async copy) helpers: one thread arms a transaction barrier with the tile's byte
+// count and issues cp.async.bulk global -> shared; everybody waits on the barrier's phase.
+__device__ __forceinline__ u32 rs_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rs_smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(rs_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(rs_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int ITEMS, int THREADS = RS_THREADS, bool BALLOT = true, bool TMA_LOAD = false>
 __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 tile, const u64* kin,
                                              const u32* vin, u64* kout,
                                              u32* vout, u64 n, int shift,
@@ -63,22 +94,45 @@ __device__ __forceinline__ void rs_tile_pass(RsSmemT<ITEMS, THREADS>& s, u32 til
   constexpr u32 TILE = THREADS * ITEMS;
   constexpr int WARPS = THREADS / 32;
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < WARPS * 256; i += THREADS) (&s.whist[0][0])[i] = 0;
-  __syncthreads();
   const u64 base = (u64)tile * TILE;
   const u32 n_valid = (u32)((n - base) < (u64)TILE ? (n - base) : (u64)TILE);
+  // TMA-staged tile load (full tiles): ONE thread issues two bulk copies (keys, values) into the
+  // staging arrays and the whole tile arrives through the async proxy while the CTA clears its
+  // histograms; the partial last tile takes ordinary loads.
+  const bool tma = TMA_LOAD && n_valid == TILE;
+  if (TMA_LOAD) {
+    if (tid == 0) rs_mbar_init(&s.mbar, 1);
+    __syncthreads();
+    if (tma && tid == 0) {
+      rs_mbar_expect_tx(&s.mbar, TILE * 12u);
+      rs_bulk_g2s(s.keys, kin + base, TILE * 8u, &s.mbar);
+      rs_bulk_g2s(s.vals, vin + base, TILE * 4u, &s.mbar);
+    }
+  }
+  for (int i = tid; i < WARPS * 256; i += THREADS) (&s.whist[0][0])[i] = 0;
+  __syncthreads();
 
   // warp-striped load: element index inside the tile = warp*(ITEMS*32) + j*32 + lane
   u64 key[ITEMS];
   u32 val[ITEMS];
   u32 rank[ITEMS];
   const u32 wb = warp * (ITEMS * 32);
+  if (tma) {
+    rs_mbar_wait(&s.mbar, 0);
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    u32 idx = wb + j * 32 + lane;
-    bool ok = idx < n_valid;
-    key[j] = ok ? kin[base + idx] : ~0ull;
-    val[j] = ok ? vin[base + idx] : 0u;
+    for (int j = 0; j < ITEMS; ++j) {
+      const u32 idx = wb + j * 32 + lane;
+      key[j] = s.keys[idx];
+      val[j] = s.vals[idx];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      u32 idx = wb + j * 32 + lane;
+      bool ok = idx < n_valid;
+      key[j] = ok ? kin[base + idx] : ~0ull;
+      val[j] = ok ? vin[base + idx] : 0u;
+    }
   }
   // stable in-warp ranking with match_any / popc (warp-shuffle histograms)
   const u32 lt_mask = (1u << lane) - 1;

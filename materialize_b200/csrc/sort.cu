@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_rs_onesweep(
   // which is what makes the look-back deadlock-free
   if (threadIdx.x == 0) s.tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
-  rs_tile_pass<ITEMS, THREADS, BALLOT>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
+  // (MZGPU_RS_TMA=0 at build time of the variant table would select plain loads; the bulk path is
+  // the default: see rs_tile_pass)
+  rs_tile_pass<ITEMS, THREADS, BALLOT, true>(s, s.tile, kin, vin, kout, vout, n, shift, gbase, tile_state);
 }
 
 template <int ITEMS, int THREADS, bool BALLOT = true, int MINB = (THREADS >= 512 ? 1 : (ITEMS > 16 ? 2 : 3))>

@@ -33,6 +33,17 @@ def main():
 
     args = dict(seed=7, n_customer=3000, n_orders=30000, n_part=4000, per_batch=500)
     g = harness.Q3Dataflow(ctx, worker=rank, peers=world, **args)
+    if os.environ.get("MZGPU_P2P", "1") != "0":
+        # update-batch exchange rounds over peer memory (CUDA IPC handles all-gathered on the host side)
+        hnd = mz.p2p_export(ctx, 1 << 16, 32)
+        ht = torch.tensor(list(hnd), dtype=torch.uint8, device="cuda")
+        hs = [torch.zeros_like(ht) for _ in range(world)]
+        dist.all_gather(hs, ht)
+        mz.p2p_import(ctx, [bytes(x.cpu().tolist()) for x in hs])
+        dist.barrier()
+        g.use_p2p(True)
+        if rank == 0:
+            print("exchange rounds over peer memory", flush=True)
 
     def gather_rows(rows):
         """all ranks' ROUT rows on rank 0"""
@@ -61,7 +72,7 @@ def main():
         want = o.drain()
         ok = ok and oracle.consolidate(got).tobytes() == want.tobytes()
         print("hydrate", len(got), len(want), ok, flush=True)
-    for b in range(5):
+    for b in range(8):
         g.stage_batch(b, g.time())
         g.step()
         got = gather_rows(g.out_rows())
