@@ -544,6 +544,24 @@ int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows, uint64_t 
 /* The input arrangement (for sharing / inspection). Borrowed. */
 mzgpu_spine* mzgpu_reduce_input_trace(mzgpu_reduce* r);
 
+/* ------------------------------ f1 (first step): Row keys as fixed-width words */
+/* A `Row` orders by byte length first, then by its bytes (RowRef::cmp,
+ * src/repr/src/row.rs:704-722; the arrangement key order of RowRowSpine,
+ * src/compute/src/row_spine.rs:116-290).  A Row of at most 7 bytes maps to one u64 that
+ * orders the same way and maps back: key = len << 56 | bytes, big-endian, zero padded.
+ * (Materialize encodes small integers in 2-5 bytes, src/repr/src/row.rs: the tag byte plus a
+ * minimal-width payload, so single-column integer keys usually fit.)  Pure host functions:
+ * no context, no device.  MZGPU_E_UNSUPPORTED for longer rows: such an arrangement stays on
+ * the Rust path until variable-width keys are built. */
+int32_t mzgpu_rowkey_pack(const uint8_t* row_bytes, uint64_t len, uint64_t* key_out);
+/* n rows stored back to back, row i = data[offsets[i] .. offsets[i + 1]) (the layout of a
+ * columnar Row container).  Stops at the first row that does not fit: returns
+ * MZGPU_E_UNSUPPORTED and *n_done = rows packed. */
+int32_t mzgpu_rowkeys_pack(const uint8_t* data, const uint64_t* offsets, uint64_t n, uint64_t* keys_out,
+                           uint64_t* n_done);
+/* Inverse: writes `len` bytes (at most 7) to row_bytes_out. */
+int32_t mzgpu_rowkey_unpack(uint64_t key, uint8_t row_bytes_out[7], uint64_t* len_out);
+
 /* --------------------------------- f3: the MV sink's correction buffer */
 /* CorrectionV2 (src/compute/src/sink/correction_v2.rs:213-498): the difference between the
  * desired and the persisted contents of a materialized view, as R32 updates

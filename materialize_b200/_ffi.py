@@ -181,6 +181,9 @@ SIGNATURES = {
     "mzgpu_exchange_many": (i32, [vp, u32, PV, PV]),
     "mzgpu_route": (u32, [u64, u32]),
     "mzgpu_partition_many": (i32, [vp, u32, PV, u32, PV, PU64]),
+    "mzgpu_rowkey_pack": (i32, [C.POINTER(C.c_uint8), u64, PU64]),
+    "mzgpu_rowkeys_pack": (i32, [C.POINTER(C.c_uint8), PU64, u64, PU64, PU64]),
+    "mzgpu_rowkey_unpack": (i32, [u64, C.POINTER(C.c_uint8), PU64]),
     "mzgpu_correction_new": (i32, [vp, PV]),
     "mzgpu_correction_free": (None, [vp]),
     "mzgpu_correction_insert": (i32, [vp, vp, u64, i32, i32]),

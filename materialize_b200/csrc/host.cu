@@ -2557,6 +2557,40 @@ extern "C" int32_t mzgpu_reduce_accumulable_buf(mzgpu_reduce* r, mzgpu_buf* rows
   return reduce_dev(r, rows->mem.as<u64>(), buf_dlen(rows), rows->ub, upper, out);
 }
 
+// ============================================================ Row keys as words (f1, first step)
+extern "C" int32_t mzgpu_rowkey_pack(const uint8_t* row_bytes, uint64_t len, uint64_t* key_out) {
+  if (key_out == nullptr || (row_bytes == nullptr && len)) return MZGPU_E_INVALID;
+  if (len > 7) return MZGPU_E_UNSUPPORTED;
+  u64 k = len << 56;
+  for (u64 i = 0; i < len; ++i) k |= (u64)row_bytes[i] << (8 * (6 - i));
+  *key_out = k;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_rowkeys_pack(const uint8_t* data, const uint64_t* offsets, uint64_t n, uint64_t* keys_out,
+                                      uint64_t* n_done) {
+  if ((n && (data == nullptr || offsets == nullptr || keys_out == nullptr))) return MZGPU_E_INVALID;
+  for (u64 i = 0; i < n; ++i) {
+    if (offsets[i + 1] < offsets[i]) return MZGPU_E_INVALID;
+    const int32_t st = mzgpu_rowkey_pack(data + offsets[i], offsets[i + 1] - offsets[i], &keys_out[i]);
+    if (st != MZGPU_OK) {
+      if (n_done) *n_done = i;
+      return st;
+    }
+  }
+  if (n_done) *n_done = n;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_rowkey_unpack(uint64_t key, uint8_t row_bytes_out[7], uint64_t* len_out) {
+  if (row_bytes_out == nullptr || len_out == nullptr) return MZGPU_E_INVALID;
+  const u64 len = key >> 56;
+  if (len > 7) return MZGPU_E_INVALID;
+  for (u64 i = 0; i < len; ++i) row_bytes_out[i] = (uint8_t)(key >> (8 * (6 - i)));
+  // canonical form: the padding below the row's bytes is zero
+  if (len < 7 && (key & ((1ull << (8 * (7 - len))) - 1)) != 0) return MZGPU_E_INVALID;
+  *len_out = len;
+  return MZGPU_OK;
+}
+
 // ============================================================ correction buffer (f3)
 struct mzgpu_correction {
   mzgpu_ctx* ctx;

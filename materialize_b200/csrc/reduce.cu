@@ -473,6 +473,123 @@ __device__ __forceinline__ void mm_prior(const TraceView& tv, u64 key, MinMaxAcc
     }
   }
 }
+// ---- groups wider than the local table (more than MM_CAP distinct live values of one key).
+// The reference bounds the work per update with a tree of hashed buckets (build_bucketed,
+// reduce.rs:796-900; top_k.rs:251-380); what the tree COMPUTES is the same per-key function of
+// the key's (value, count) pairs.  Every batch holds a key's updates as a run sorted by (value,
+// time), so that function is a k-way merge of the runs in value order, one value at a time --
+// any group width, no table.  Only a key that overflowed the table takes this path.
+struct RunCur {
+  const u64* rows;
+  u64 lo, hi;  // rows [lo, hi) of the key, sorted by (val, time)
+};
+constexpr int MM_MAX_RUNS = MZ_MAX_TRACE_BATCHES + 1;
+__device__ __noinline__ int mm_runs(const TraceView& tv, u64 key, RunCur* cur) {
+  int nc = 0;
+  const u64 h0 = mix64(key);
+  for (u32 b = 0; b < tv.n_batches; ++b) {
+    const BatchView& bv = tv.b[b];
+    const u64 mask = bv_mask(bv);
+    u64 h = h0 & mask;
+    while (true) {
+      const ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+      if (sl.y == 0) break;
+      if (sl.x == key) {
+        const u64 first = (sl.y & MZ_SLOT_ROW_MASK) - 1;
+        const u32 len = (u32)(sl.y >> 44);
+        u64 end = first + len;
+        if (len == 0) {  // run length not recorded: upper bound search (rows are sorted by key)
+          u64 lo = first + 1, hi = bv_n(bv);
+          while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if (bv.rows[mid * 4] == key)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          end = lo;
+        }
+        cur[nc].rows = bv.rows;
+        cur[nc].lo = first;
+        cur[nc].hi = end;
+        ++nc;
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+  return nc;
+}
+// Visit the key's distinct values in ascending (or descending) order with their total count:
+// all rows of the prior runs, and the rows of the new batch's run [nlo, nhi) whose time is
+// <= t_limit (use_new).  f(value, count) returns false to stop early.  The cursors are copied:
+// `cur` is left untouched.
+template <class F>
+__device__ __forceinline__ void mm_stream(const RunCur* cur, int nc, const u64* nrows, u64 nlo, u64 nhi, bool use_new,
+                                          u64 t_limit, bool desc, F f) {
+  u64 lo[MM_MAX_RUNS], hi[MM_MAX_RUNS];
+  for (int c = 0; c < nc; ++c) {
+    lo[c] = cur[c].lo;
+    hi[c] = cur[c].hi;
+  }
+  const int nn = use_new ? nc + 1 : nc;
+  if (use_new) {
+    lo[nc] = nlo;
+    hi[nc] = nhi;
+  }
+  while (true) {
+    bool have = false;
+    u64 v = 0;
+    for (int c = 0; c < nn; ++c) {
+      if (lo[c] >= hi[c]) continue;
+      const u64* rows = c < nc ? cur[c].rows : nrows;
+      const u64 hv = rows[(desc ? hi[c] - 1 : lo[c]) * 4 + 1];
+      if (!have || (desc ? hv > v : hv < v)) {
+        v = hv;
+        have = true;
+      }
+    }
+    if (!have) break;
+    i64 cnt = 0;
+    for (int c = 0; c < nn; ++c) {
+      const u64* rows = c < nc ? cur[c].rows : nrows;
+      while (lo[c] < hi[c]) {
+        const u64 r = desc ? hi[c] - 1 : lo[c];
+        if (rows[r * 4 + 1] != v) break;
+        if (c < nc || rows[r * 4 + 2] <= t_limit) cnt += (i64)rows[r * 4 + 3];
+        if (desc)
+          --hi[c];
+        else
+          ++lo[c];
+      }
+    }
+    if (!f(v, cnt)) break;
+  }
+}
+// MIN / MAX of a wide group: one ascending pass (every value is looked at: the error row needs
+// to know about any negative count)
+__device__ __noinline__ bool mm_eval_stream(const RunCur* cur, int nc, const u64* nrows, u64 nlo, u64 nhi, bool use_new,
+                                            u64 t_limit, int agg_kind, u64* o) {
+  bool any = false, bad = false, have = false;
+  u64 best = 0;
+  mm_stream(cur, nc, nrows, nlo, nhi, use_new, t_limit, false, [&](u64 v, i64 c) -> bool {
+    if (c == 0) return true;
+    any = true;
+    if (c < 0) {
+      bad = true;
+      return true;
+    }
+    if (!have || agg_kind == MZGPU_AGG_MAX) best = v;  // ascending: first positive = MIN, last = MAX
+    have = true;
+    return true;
+  });
+  o[0] = 0;
+  o[1] = bad ? 0 : best;
+  o[2] = 0;
+  o[3] = bad ? 2 : 0;
+  return any;
+}
+
 // rows [i, ...) of the new batch share `key` (sorted by (val, time)): replay them in
 // time order on top of the prior pairs and emit (-old, +new) whenever the result changes.
 __device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64 i, u64 key,
@@ -482,8 +599,18 @@ __device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64
   a.m = 0;
   a.overflow = false;
   mm_prior(prior, key, a);
+  // the key's run in the new batch, and (only if the table overflows) its runs in the prior batches
+  u64 i_end = i;
+  while (i_end < n && rows[i_end * 4] == key) ++i_end;
+  RunCur runs[MM_MAX_RUNS];
+  int n_runs = -1;
+  auto eval_at = [&](bool use_new, u64 t_limit, u64* o) -> bool {
+    if (!a.overflow) return mm_eval(a, agg_kind, o);
+    if (n_runs < 0) n_runs = mm_runs(prior, key, runs);
+    return mm_eval_stream(runs, n_runs, rows, i, i_end, use_new, t_limit, agg_kind, o);
+  };
   u64 oldv[4];
-  bool had = mm_eval(a, agg_kind, oldv);
+  bool had = eval_at(false, 0, oldv);
   u32 c = 0;
   bool first = true;
   u64 t_prev = 0;
@@ -507,7 +634,7 @@ __device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64
       if (row[2] == t_cur) mm_add(a, row[1], (i64)row[3]);
     }
     u64 newv[4];
-    const bool has = mm_eval(a, agg_kind, newv);
+    const bool has = eval_at(true, t_cur, newv);
     const bool same = (had == has) && (!has || (oldv[1] == newv[1] && oldv[3] == newv[3]));
     if (!same) {
       if (had) {
@@ -531,7 +658,7 @@ __device__ __noinline__ u32 walk_minmax(const u64* __restrict__ rows, u64 n, u64
     first = false;
     t_prev = t_cur;
   }
-  if (a.overflow) status[1] = 1;
+  (void)status;
   return c;
 }
 
@@ -585,6 +712,47 @@ __device__ __noinline__ void tk_eval(const MinMaxAcc& a, const TopKParams& tp, T
     }
   }
 }
+// the same window for a group wider than the table: a first pass looks for a negative count (the
+// error row), a second walks the values in the plan's order until the limit is spent.  Returns
+// false if the WINDOW itself has more than MM_CAP distinct values (limit > MM_CAP or none).
+__device__ __noinline__ bool tk_eval_stream(const RunCur* cur, int nc, const u64* nrows, u64 nlo, u64 nhi, bool use_new,
+                                            u64 t_limit, const TopKParams& tp, TopKWin& w) {
+  w.n = 0;
+  w.err = false;
+  mm_stream(cur, nc, nrows, nlo, nhi, use_new, t_limit, false, [&](u64, i64 c) -> bool {
+    if (c < 0) w.err = true;
+    return !w.err;
+  });
+  if (w.err) return true;
+  u64 skip = tp.offset;
+  i64 left = tp.limit;
+  bool fits = true;
+  if (tp.limit == 0) return true;
+  mm_stream(cur, nc, nrows, nlo, nhi, use_new, t_limit, tp.descending != 0, [&](u64 v, i64 c) -> bool {
+    if (c <= 0) return true;
+    i64 cnt = c;
+    if (skip > 0) {
+      const u64 s_ = skip < (u64)cnt ? skip : (u64)cnt;
+      skip -= s_;
+      cnt -= (i64)s_;
+    }
+    if (tp.limit >= 0) {
+      cnt = cnt < left ? cnt : left;
+      left -= cnt;
+    }
+    if (cnt > 0) {
+      if (w.n == MM_CAP) {
+        fits = false;
+        return false;
+      }
+      w.v[w.n] = v;
+      w.m[w.n] = cnt;
+      ++w.n;
+    }
+    return !(tp.limit >= 0 && left == 0);
+  });
+  return fits;
+}
 // changes old -> fresh at time t; returns the number of rows (written at out[pos...] if do_write)
 __device__ __forceinline__ u32 tk_emit(u64 key, const TopKWin& old, const TopKWin& fresh, u64 t, bool do_write,
                                        u64* __restrict__ out, u64 pos) {
@@ -617,8 +785,21 @@ __device__ __noinline__ u32 walk_topk(const u64* __restrict__ rows, u64 n, u64 i
   a.m = 0;
   a.overflow = false;
   mm_prior(prior, key, a);
+  u64 i_end = i;
+  while (i_end < n && rows[i_end * 4] == key) ++i_end;
+  RunCur runs[MM_MAX_RUNS];
+  int n_runs = -1;
+  bool window_fits = true;
+  auto eval_at = [&](bool use_new, u64 t_limit, TopKWin& w) {
+    if (!a.overflow) {
+      tk_eval(a, tp, w);
+      return;
+    }
+    if (n_runs < 0) n_runs = mm_runs(prior, key, runs);
+    if (!tk_eval_stream(runs, n_runs, rows, i, i_end, use_new, t_limit, tp, w)) window_fits = false;
+  };
   TopKWin old, fresh;
-  tk_eval(a, tp, old);
+  eval_at(false, 0, old);
   u32 c = 0;
   bool first = true;
   u64 t_prev = 0;
@@ -640,13 +821,15 @@ __device__ __noinline__ u32 walk_topk(const u64* __restrict__ rows, u64 n, u64 i
       if (row[0] != key) break;
       if (row[2] == t_cur) mm_add(a, row[1], (i64)row[3]);
     }
-    tk_eval(a, tp, fresh);
+    eval_at(true, t_cur, fresh);
     c += tk_emit(key, old, fresh, t_cur, do_write, out, pos + c);
     old = fresh;
     first = false;
     t_prev = t_cur;
   }
-  if (a.overflow) status[1] = 1;
+  // (a window of more than MM_CAP distinct values -- LIMIT beyond 32 on a wide group -- is the one
+  // shape still outside the subset: reported, never wrong)
+  if (!window_fits) status[1] = 1;
   return c;
 }
 

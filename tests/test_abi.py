@@ -66,3 +66,42 @@ def test_product_does_not_touch_oracle():
                 assert "libmzoracle" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert not re.search(r'#include\s+"[^"]*oracle/', text), f
+
+
+def test_row_keys_pack_order_preserving_and_invertible():
+    """f1, first step: Rows of at most 7 bytes as one u64 that orders exactly like RowRef::cmp
+    (length first, then bytes: src/repr/src/row.rs:704-722) and maps back.  Host-only functions of
+    the C ABI: no GPU needed."""
+    import ctypes as C
+    import random
+
+    from materialize_b200 import _ffi as F
+
+    rng = random.Random(5)
+    rows = [bytes(rng.randrange(256) for _ in range(rng.randrange(0, 8))) for _ in range(4000)]
+    rows += [b"", b"\x00", b"\x00\x00", b"\xff", b"\xff" * 7, b"\x01\x00", b"\x00\x01"]
+    data = b"".join(rows)
+    offs = [0]
+    for r in rows:
+        offs.append(offs[-1] + len(r))
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\x00")
+    offsets = (C.c_uint64 * len(offs))(*offs)
+    keys = (C.c_uint64 * len(rows))()
+    done = C.c_uint64(0)
+    assert F.lib.mzgpu_rowkeys_pack(buf, offsets, len(rows), keys, C.byref(done)) == F.OK and done.value == len(rows)
+    keys = list(keys)
+    # same order as the reference's Row comparison
+    by_row = sorted(range(len(rows)), key=lambda i: (len(rows[i]), rows[i]))
+    by_key = sorted(range(len(rows)), key=lambda i: keys[i])
+    assert [rows[i] for i in by_row] == [rows[i] for i in by_key]
+    assert len(set(keys)) == len(set(rows))  # injective
+    out, n = (C.c_uint8 * 7)(), C.c_uint64(0)
+    for r, k in zip(rows[:500] + rows[-7:], keys[:500] + keys[-7:]):
+        assert F.lib.mzgpu_rowkey_unpack(k, out, C.byref(n)) == F.OK and bytes(out[: n.value]) == r
+    # longer rows are outside the subset, reported at the first one
+    two = b"\x01\x02" + b"\x09" * 8
+    buf2 = (C.c_uint8 * len(two)).from_buffer_copy(two)
+    offs2 = (C.c_uint64 * 3)(0, 2, 10)
+    keys2 = (C.c_uint64 * 2)()
+    assert F.lib.mzgpu_rowkeys_pack(buf2, offs2, 2, keys2, C.byref(done)) == F.E_UNSUPPORTED and done.value == 1
+    assert F.lib.mzgpu_rowkey_unpack((8 << 56), out, C.byref(n)) == F.E_INVALID

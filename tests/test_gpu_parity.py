@@ -235,6 +235,62 @@ def test_reduce_full_size_properties(mz, ctx):
     assert np.all(out["diff"] == 1) and np.all(out["flags"] == 0)
 
 
+@pytest.mark.parametrize("agg_kind", [0, 1])
+def test_reduce_incremental_full_size(mz, ctx, agg_kind):
+    """BASELINE configs[3] in its incremental regime at full size (100 batches of 1 M
+    rows, 1 M Zipf(0.9) keys, half of every batch retracting rows of the batch before): the CPU
+    oracle cannot run 100 M rows in seconds, so the operator is pinned by the property that
+    defines it -- at every timestamp, the accumulated output corrections are exactly GROUP BY
+    (COUNT, SUM) of the accumulated input -- checked with numpy on host copies of the batches.
+    i64 sums are compared exactly; f64 sums (kind 1) are compared exactly in the operator's 2^24
+    fixed point (the reference accumulates floats as (x * 2^24) as i128), i.e. with tolerance 0,
+    inside the 1e-6 relative tolerance north_star allows."""
+    from materialize_b200 import harness
+
+    nb, per, nk = 100, 1_000_000, 1_000_000
+    w = 1.0 / np.power(np.arange(1, nk + 1, dtype=np.float64), 0.9)
+    cdf = np.cumsum(w / w.sum())
+    cdf[-1] = 1.0
+    r = mz.ReduceAccumulable(ctx, agg_kind)
+    cnt = np.zeros(nk + 1, dtype=np.int64)
+    tot = np.zeros(nk + 1, dtype=np.float64)  # sums of small integers: exact in float64
+    o_cnt = np.zeros(nk + 1, dtype=np.int64)
+    o_sum = np.zeros(nk + 1, dtype=np.float64)
+    prev = None
+    for b in range(nb):
+        fresh = harness.gen_cfg4(ctx, 5, per // 2, cdf, as_f64=(agg_kind == 1), first=b * (per // 2), t=b, diff=1)
+        batch = mz.DeviceRows(ctx, 32)
+        batch.append_buf(fresh)
+        if prev is not None:  # retract the rows the previous batch added
+            batch.append_buf(harness.gen_cfg4(ctx, 5, per // 2, cdf, as_f64=(agg_kind == 1), first=(b - 1) * (per // 2), t=b, diff=-1))
+        h = batch.download()
+        out = r.step_dev(batch, b + 1).download()
+        prev = fresh
+        keys = h["key"].astype(np.int64)
+        d = h["diff"].astype(np.int64)
+        if agg_kind == 1:  # the operator's fixed point: (x * 2^24) as i128, truncating (reduce.rs:1528)
+            vals = np.trunc(h["val"].view(np.float64) * 2.0**24)
+        else:
+            vals = h["val"].astype(np.int64).astype(np.float64)
+        cnt += np.bincount(keys, weights=d.astype(np.float64), minlength=nk + 1).astype(np.int64)
+        tot += np.bincount(keys, weights=d * vals, minlength=nk + 1)
+        # fold the corrections in: output row (key, count, sum) with diff +-1
+        ok = out["key"].astype(np.int64)
+        od = out["diff"].astype(np.int64)
+        assert np.all(out["flags"] == 0) and np.all(out["time"] == b)
+        if agg_kind == 1:  # finalized f64 sums: back to fixed-point units (exact: multiples of 2^-24 below 2^29)
+            osum = out["sum_lo"].view(np.float64) * 2.0**24
+        else:
+            osum = out["sum_lo"].astype(np.int64).astype(np.float64) + out["sum_hi"].astype(np.float64) * 2.0**64
+        o_cnt += np.bincount(ok, weights=(od * out["count"].astype(np.int64)).astype(np.float64), minlength=nk + 1).astype(np.int64)
+        o_sum += np.bincount(ok, weights=od * osum, minlength=nk + 1)
+        if b % 10 == 9 or b == nb - 1:
+            assert np.array_equal(o_cnt, cnt), b
+            assert np.array_equal(o_sum, tot), b
+    assert np.abs(tot).max() < 2.0**52
+    assert int(cnt.sum()) == per // 2  # everything but the last half batch has been retracted
+
+
 # ------------------------------------------------------------- a2 - a5
 def test_batcher_seal_matches_oracle(mz, ctx, oracle):
     rng = np.random.default_rng(21)
@@ -868,17 +924,82 @@ def test_topk_matches_oracle(mz, ctx, oracle, limit, offset, desc):
         same(gr.step(a, t), orr.step(a, t))
 
 
-def test_reduce_min_max_group_too_wide_is_reported(mz, oracle):
-    """A key with more than 32 distinct live values needs the bucketed tree: reported, not wrong.
-    (The report is deferred and poisons the context, hence a private one.)"""
-    ctx = mz.Context(0)
-    a = np.zeros(40, dtype=oracle.R32)
-    a["key"] = 7
-    a["val"] = np.arange(40)
-    a["diff"] = 1
-    gr = mz.ReduceAccumulable(ctx, 4)
+@pytest.mark.parametrize("agg_kind", [4, 5])
+def test_reduce_min_max_wide_groups_match_oracle(mz, ctx, oracle, agg_kind):
+    """Groups with 10^3 .. 10^5 distinct live values (the reference's bucketed reduction tree,
+    reduce.rs:796-1135, exists for these): values arrive over several batches and timestamps, the
+    extremum is retracted and comes back, whole prefixes of the value range cancel, a negative
+    count appears and is repaired.  Narrow keys in the same batches keep the table path."""
+    rng = np.random.default_rng(700 + agg_kind)
+    gr, orr = mz.ReduceAccumulable(ctx, agg_kind), oracle.Reduce(agg_kind)
+    widths = {11: 1000, 12: 20000, 13: 100000}
+    t = 0
+    live = {k: np.zeros(0, dtype=np.uint64) for k in widths}
+    broken = {}
+    for step in range(7):
+        parts = []
+        for k, wdt in widths.items():
+            n = wdt // 4 if step < 4 else wdt // 50
+            v = rng.integers(0, 1 << 40, size=n, dtype=np.uint64)
+            x = np.zeros(n, dtype=oracle.R32)
+            x["key"], x["val"], x["diff"] = k, v, 1
+            x["time"] = rng.integers(t, t + 2, size=n, dtype=np.uint64)
+            parts.append(x)
+            live[k] = np.concatenate([live[k], v])
+            if step in (2, 4, 5) and len(live[k]):
+                # retract the current extremum's neighbourhood (the smallest / largest 5 %) ...
+                srt = np.sort(live[k])
+                cut = srt[: len(srt) // 20] if agg_kind == 4 else srt[-(len(srt) // 20) :]
+                y = np.zeros(len(cut), dtype=oracle.R32)
+                y["key"], y["val"], y["diff"], y["time"] = k, cut, -1, t + 1
+                parts.append(y)
+                live[k] = np.setdiff1d(live[k], cut)
+            if step == 3:
+                # ... and one value (far from the extremum) more often than it was inserted: the
+                # error row, repaired at step 4
+                broken[k] = live[k].max() if agg_kind == 4 else live[k].min()
+                z = np.zeros(1, dtype=oracle.R32)
+                z["key"], z["val"], z["diff"], z["time"] = k, broken[k], -2, t
+                parts.append(z)
+            if step == 4:
+                z = np.zeros(1, dtype=oracle.R32)
+                z["key"], z["val"], z["diff"], z["time"] = k, broken[k], 2, t
+                parts.append(z)
+        nar = rand_r32(rng, 3000, 300, 9, 1, dtype=oracle.R32)
+        nar["key"] += np.uint64(1000)
+        nar["time"] = t
+        nar["diff"] = rng.integers(-1, 3, size=len(nar))
+        parts.append(nar)
+        a = np.concatenate(parts)
+        t += 2
+        got, want = gr.step(a, t), orr.step(a, t)
+        same(got, want)
+        if step == 3:
+            assert (want["flags"][np.isin(want["key"], list(widths))] == 2).any()
+
+
+def test_topk_wide_groups_match_oracle(mz, ctx, oracle):
+    """TopK on groups of thousands of distinct values: limits up to 32 take any group width (the
+    window is found by the value-ordered merge of the key's runs); a window wider than 32
+    distinct values on a wide group is reported as unsupported, never wrong."""
+    rng = np.random.default_rng(720)
+    for limit, offset, desc in ((1, 0, False), (5, 3, True), (32, 100, False)):
+        gr, orr = mz.TopK(ctx, limit, offset, desc), oracle.TopK(limit, offset, desc)
+        t = 0
+        for step in range(4):
+            n = 6000
+            a = np.zeros(n, dtype=oracle.R32)
+            a["key"] = rng.integers(0, 3, size=n, dtype=np.uint64)
+            a["val"] = rng.integers(0, 4000, size=n, dtype=np.uint64)
+            a["time"] = rng.integers(t, t + 2, size=n, dtype=np.uint64)
+            a["diff"] = rng.integers(0, 3, size=n) if step != 2 else -rng.integers(0, 2, size=n)
+            t += 2
+            same(gr.step(a, t), orr.step(a, t))
+    priv = mz.Context(0)  # (the report is deferred and poisons the context, hence a private one)
+    a = np.zeros(100, dtype=oracle.R32)
+    a["key"], a["val"], a["diff"] = 7, np.arange(100), 1
     with pytest.raises(mz.MzGpuError) as e:
-        gr.step(a, 1)
+        mz.TopK(priv, 40, 0, False).step(a, 1)
     assert e.value.status == -4  # MZGPU_E_UNSUPPORTED
 
 
