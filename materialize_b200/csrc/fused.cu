@@ -42,7 +42,10 @@ constexpr u32 MAX_RUN_SAT = 1024;  // key runs longer than this report as 1024
 // MSD path: rows are partitioned into buckets by the leading bits of their
 // composite key and every bucket is sorted AND consolidated inside one CTA's
 // shared memory (rows with equal keys always share a bucket).
-constexpr u32 MSD_MAX_BUCKETS = 4096;
+constexpr u32 MSD_MAX_BUCKETS = 4096;        // exact (count -> scan -> scatter) MSD path: bucket bases live in shared memory
+constexpr u32 MSD_FAST_MAX_BUCKETS = 32768;  // fast MSD path (fixed-capacity regions): up to 2^20 rows at 32-48 rows per bucket
+constexpr u64 MSD_FAST_MAX_ROWS = 1ull << 20;
+constexpr u64 MSD_EXACT_MAX_ROWS = 1ull << 18;
 constexpr u32 MSD_LOCAL_MAX = 1024;  // largest bucket the in-CTA sort takes
 
 struct FusedCtl {
@@ -53,7 +56,7 @@ struct FusedCtl {
   u64 n_seg;
   u64 n_out;
   u32 hist[MAX_ROUNDS * 8 * 256];
-  u32 bcnt[4096];  // MSD path: rows per bucket
+  u32 bcnt[MSD_FAST_MAX_BUCKETS];  // MSD paths: rows per bucket
 };
 constexpr size_t CTL_HEADER = offsetof(FusedCtl, hist);
 
@@ -648,7 +651,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   const u64 T = (n + FTILE - 1) / FTILE;
   // A merge of update-batch size runs as a sort of A ++ B: the fast MSD path below has two grid
   // barriers, the merge path five; sortedness only pays beyond the bucket phase's reach.
-  const bool merge = a.merge != 0 && !(a.fast != 0 && n <= (1ull << 18));
+  const bool merge = a.merge != 0 && !(a.fast != 0 && n <= MSD_FAST_MAX_ROWS);
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
   // MSD bucket count from the row count alone: at most 48 (12 for the 80-byte
   // accumulable rows, whose warp capacity is 64 and whose keys arrive in clumps:
@@ -656,7 +659,9 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   constexpr int WR = 4;                     // register rows per lane in the warp-bucket phase
   constexpr u32 WCAP = 32u * WR;            // largest bucket a warp takes
   u32 bb = 0;  // log2(buckets)
-  while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n) ++bb;
+  // (the fast path takes up to 32768 buckets -- a million rows; without it the exact path's 4096)
+  const u32 bb_max = a.fast != 0 ? 15u : 12u;
+  while (bb < bb_max && ((u64)(ND == 8 ? 12 : 48) << bb) < n) ++bb;
   const u32 NB = 1u << bb;
   u32 G = gdim;
   {
@@ -714,8 +719,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
       }
     }
     for (u64 i = gtid; i < (u64)MAX_ROUNDS * 8 * 256; i += gstride) ctl->hist[i] = 0;
-    for (u64 i = gtid; i < (u64)NB; i += gstride) {
-      ctl->bcnt[i] = 0;
+    for (u64 i = gtid; i < (u64)NB; i += gstride) ctl->bcnt[i] = 0;
+    for (u64 i = gtid; i < (u64)(NB + 7) / 8; i += gstride) {  // look-back state: one word per chunk of eight buckets
       a.lb_ship[i] = 0;
       a.lb_keep[i] = 0;
     }
@@ -811,7 +816,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   // =================================================================== MSD path
   bool msd_done = false;
   // (beyond ~256K rows the bucket phase stops paying: the look-back radix passes win)
-  if (!merge && s_w128 <= 128 && n <= (1ull << 18)) {
+  if (!merge && s_w128 <= 128 && n <= (a.fast != 0 ? MSD_FAST_MAX_ROWS : MSD_EXACT_MAX_ROWS)) {
     const int W = s_w128;
     auto composite = [&](const u64* row, u64* clo, u64* chi) {
       unsigned __int128 comp = 0;
@@ -887,7 +892,9 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
         grid_barrier(&ctl->barrier, G, epoch);
       }
     }
-    if (!fast_done) {
+    // the exact path keeps its bucket bases in shared memory: at most MSD_MAX_BUCKETS of them
+    // (a bigger job whose fast path overflowed takes the radix path below)
+    if (!fast_done && NB <= MSD_MAX_BUCKETS && n <= MSD_EXACT_MAX_ROWS) {
     // ---- pack composites, count rows per bucket (the atomic's return value is
     // the row's slot inside its bucket; the order inside a bucket is irrelevant)
     for (u64 i = gtid; i < n; i += gstride) {
@@ -1592,9 +1599,9 @@ int32_t fused_prepare(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res, int sl
   // hold (buckets for the largest row count this launch can see) x 128 entries
   u64 mcap = cap;
   {
-    const u64 n_max = cap < (1ull << 18) ? cap : (1ull << 18);
+    const u64 n_max = cap < MSD_FAST_MAX_ROWS ? cap : MSD_FAST_MAX_ROWS;
     u32 bb = 0;
-    while (bb < 12 && ((u64)(ND == 8 ? 12 : 48) << bb) < n_max) ++bb;
+    while (bb < 15 && ((u64)(ND == 8 ? 12 : 48) << bb) < n_max) ++bb;
     const u64 regions = ((u64)1 << bb) * 128;
     if (regions > mcap) mcap = regions;
   }
