@@ -136,9 +136,23 @@ struct ProbePre {  // optional map in front of the probe (build_update_stream fu
 // first matching slot of `key` in batch `bv`: {first row, run length} or len = 0 when absent
 __device__ __forceinline__ bool probe_slot_resolve(const BatchView& bv, u64 key, ulonglong2 sl, u64 h, u64 mask,
                                                    u64* first, u32* len) {
+  // linear probing: after the first slot, FOUR slots per round trip (independent loads, mostly one
+  // 64-byte sector).  A tile resolves a couple of thousand slots and waits for the longest chain
+  // among them (~10 steps at load factor 0.5): one memory latency per step was the tile's tail.
   while (sl.y != 0 && sl.x != key) {
-    h = (h + 1) & mask;
-    sl = *reinterpret_cast<const ulonglong2*>(&bv.table[h]);
+    ulonglong2 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const ulonglong2*>(&bv.table[(h + 1 + i) & mask]);
+    bool settled = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (!settled && (q[i].y == 0 || q[i].x == key)) {
+        sl = q[i];
+        settled = true;
+      }
+    if (settled) break;
+    h = (h + 4) & mask;
+    sl = q[3];  // occupied by another key: the loop goes on from the slot after it
   }
   if (sl.y == 0) return false;
   const u64 f = (sl.y & MZ_SLOT_ROW_MASK) - 1;

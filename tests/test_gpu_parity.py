@@ -281,7 +281,10 @@ def test_reduce_incremental_full_size(mz, ctx, agg_kind):
         if agg_kind == 1:  # finalized f64 sums: back to fixed-point units (exact: multiples of 2^-24 below 2^29)
             osum = out["sum_lo"].view(np.float64) * 2.0**24
         else:
-            osum = out["sum_lo"].astype(np.int64).astype(np.float64) + out["sum_hi"].astype(np.float64) * 2.0**64
+            # i128 sums that fit i64 here: the low word read as two's complement, the high word its sign
+            lo64 = out["sum_lo"].astype(np.int64)
+            assert np.array_equal(out["sum_hi"].astype(np.int64), np.where(lo64 < 0, -1, 0))
+            osum = lo64.astype(np.float64)
         o_cnt += np.bincount(ok, weights=(od * out["count"].astype(np.int64)).astype(np.float64), minlength=nk + 1).astype(np.int64)
         o_sum += np.bincount(ok, weights=od * osum, minlength=nk + 1)
         if b % 10 == 9 or b == nb - 1:

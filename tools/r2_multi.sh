@@ -7,7 +7,10 @@ TAG=${2:-r02m}
 O=gpurun_out
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-echo "== parity, peer-memory exchange" | tee $O/${TAG}_multi.log
+echo "== one-GPU smoke of what changed last" | tee $O/${TAG}_multi.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "half_join or first_stage or join_core or q3_dataflow or peer_memory or incremental_full_size" 2>&1 | tail -4 | tee -a $O/${TAG}_multi.log
+if [ "${PIPESTATUS[0]}" -ne 0 ]; then echo "smoke failed: stopping"; exit 1; fi
+echo "== parity, peer-memory exchange" | tee -a $O/${TAG}_multi.log
 timeout 300 $TR tools/q3_multi_gpu_check.py 2>&1 | grep -E "PARITY|batch|hydrate|exchange|Error|error" | tail -14 | tee -a $O/${TAG}_multi.log
 echo "== parity, NCCL exchange" | tee -a $O/${TAG}_multi.log
 MZGPU_P2P=0 timeout 300 $TR tools/q3_multi_gpu_check.py 2>&1 | grep -E "PARITY|Error|error" | tail -4 | tee -a $O/${TAG}_multi.log
