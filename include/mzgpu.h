@@ -562,6 +562,67 @@ int32_t mzgpu_rowkeys_pack(const uint8_t* data, const uint64_t* offsets, uint64_
 /* Inverse: writes `len` bytes (at most 7) to row_bytes_out. */
 int32_t mzgpu_rowkey_unpack(uint64_t key, uint8_t row_bytes_out[7], uint64_t* len_out);
 
+/* ------------------------------------ f4: the columnar wire format */
+/* `Column<C>` (src/timely-util/src/columnar.rs:54-222) is the container the reference moves
+ * update batches in: between workers (`ContainerBytes::{from_bytes, into_bytes}`, :177-222), out
+ * of `ColumnBuilder` (src/timely-util/src/columnar/builder.rs:28-111) and into the merge batcher
+ * (`Col2ValBatcher`, columnar.rs:41-45).  Serialized (`Column::Bytes` / `Column::Align`) it is
+ * `columnar::bytes::indexed` (crate columnar 0.12.1, not vendored; layout pinned by the
+ * reference's `raw_columnar_bytes`, columnar.rs:247-258): word 0 = 8 * (k + 1), words 1..k = the
+ * byte offset where each of the k slices ends (a slice starts at the previous end rounded up to 8),
+ * then the slices, zero padded to whole words.  These entry points move between that format and
+ * the row buffers of this library ON THE DEVICE (one transposing kernel each way), so that a
+ * worker can hand over the bytes it received or ship the bytes it must send without a host-side
+ * row loop:
+ *   MZGPU_COLUMN_U64X4   Column<((u64, u64), u64, i64)>: 4 slices key, val, time, diff <-> R32
+ *   MZGPU_COLUMN_U64X2   Column<(u64, i64)>: 2 slices key, diff                       <-> R16
+ *   MZGPU_COLUMN_ROWROW  Column<((Row, Row), Timestamp, Diff)>: 6 slices key bounds (the END
+ *                        offset of every row, src/repr/src/row.rs:447-452,606-611), key bytes,
+ *                        val bounds, val bytes, times, diffs <-> R32 whose key and val are Rows
+ *                        of at most 7 bytes packed as by mzgpu_rowkey_pack (a longer Row:
+ *                        MZGPU_E_UNSUPPORTED, nothing appended) */
+#define MZGPU_COLUMN_U64X4 0
+#define MZGPU_COLUMN_U64X2 1
+#define MZGPU_COLUMN_ROWROW 2
+/* indexed::length_in_words of a container of `rows` updates; key_bytes / val_bytes = total Row
+ * bytes (ROWROW only, else ignored).  Pure host function. */
+uint64_t mzgpu_column_length_in_words(int32_t layout, uint64_t rows, uint64_t key_bytes, uint64_t val_bytes);
+/* The ship signal shared by ColumnBuilder::push_into (builder.rs:48-52) and
+ * `at_serialized_capacity` (columnar.rs:164-175): 1 when `words` is within 10 % of the next
+ * multiple of 2 MiB (2^18 words).  Pure host function. */
+int32_t mzgpu_column_at_capacity(uint64_t words);
+/* Rows of the container ColumnBuilder mints for a fixed-width layout (the smallest row count at
+ * which the ship signal fires); 0 for ROWROW, where it depends on the data. */
+uint64_t mzgpu_column_ship_rows(int32_t layout);
+/* `Column::borrow()` + drain: APPEND the updates of one serialized container (`n_words` words in
+ * host or device memory, 8-byte aligned as `Column::Align` guarantees) to `out` (R32, or R16 for
+ * U64X2).  The index is validated on the host (MZGPU_E_INVALID: not a container of this layout;
+ * for device memory the k + 1 index words are read back first).  ROWROW waits for the device once
+ * (bounds are validated and over-long Rows detected there). */
+int32_t mzgpu_column_decode(mzgpu_ctx* ctx, int32_t layout, const uint64_t* words, uint64_t n_words, int32_t mem,
+                            mzgpu_buf* out);
+/* `indexed::encode` of rows [first, first + n) of `rows` (clamped to its length) into `words`
+ * (host or device memory, capacity cap_words); *n_words = words written.  MZGPU_E_CAPACITY with
+ * *n_words = the size needed if cap_words is too small.  Waits for the device (the caller needs
+ * the size to ship the bytes). */
+int32_t mzgpu_column_encode(mzgpu_buf* rows, int32_t layout, uint64_t first, uint64_t n, uint64_t* words,
+                            uint64_t cap_words, int32_t mem, uint64_t* n_words);
+/* ColumnBuilder over a whole buffer: the containers push_into would mint for these rows in order,
+ * then the remainder (`finish`), written back to back into `words`; chunk_words[i] = size of
+ * container i, *n_chunks = their number.  MZGPU_E_CAPACITY (with the totals needed in *n_words
+ * and *n_chunks) if either capacity is too small. */
+int32_t mzgpu_column_build(mzgpu_buf* rows, int32_t layout, uint64_t* words, uint64_t cap_words, int32_t mem,
+                           uint64_t* n_words, uint64_t* chunk_words, uint32_t cap_chunks, uint32_t* n_chunks);
+/* walk_cursor over one batch into a container (src/compute/src/render/context.rs:1299-1355; the
+ * read side of an arrangement import / peek): rows [first, first + fuel) of the batch in cursor
+ * order -- a sealed batch is consolidated, so the per-(key, val) consolidation of the walk is the
+ * identity -- encoded as by mzgpu_column_encode.  With `key` non-NULL only that key's rows are
+ * walked (seek_key); *n_rows = rows emitted (the caller resumes at first + *n_rows while it equals
+ * fuel). */
+int32_t mzgpu_batch_walk_column(mzgpu_batch* batch, const uint64_t* key, uint64_t first, uint64_t fuel,
+                                int32_t layout, uint64_t* words, uint64_t cap_words, int32_t mem,
+                                uint64_t* n_words, uint64_t* n_rows);
+
 /* --------------------------------- f3: the MV sink's correction buffer */
 /* CorrectionV2 (src/compute/src/sink/correction_v2.rs:213-498): the difference between the
  * desired and the persisted contents of a materialized view, as R32 updates

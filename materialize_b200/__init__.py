@@ -51,4 +51,9 @@ from .api import (  # noqa: F401
     route,
     update_stream,
     update_stream_dev,
+    column_decode,
+    column_encode,
+    column_build,
+    batch_walk_column,
 )
+from ._ffi import COLUMN_ROWROW, COLUMN_U64X2, COLUMN_U64X4  # noqa: F401

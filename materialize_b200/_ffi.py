@@ -209,7 +209,15 @@ SIGNATURES = {
     "mzgpu_builder_done": (i32, [vp, Desc, PV]),
     "mzgpu_spine_size": (i32, [vp, vp]),
     "mzgpu_join_core_work_until": (i32, [vp, u64, u64, vp, PI32]),
+    "mzgpu_column_length_in_words": (u64, [i32, u64, u64, u64]),
+    "mzgpu_column_at_capacity": (i32, [u64]),
+    "mzgpu_column_ship_rows": (u64, [i32]),
+    "mzgpu_column_decode": (i32, [vp, i32, vp, u64, i32, vp]),
+    "mzgpu_column_encode": (i32, [vp, i32, u64, u64, vp, u64, i32, PU64]),
+    "mzgpu_column_build": (i32, [vp, i32, vp, u64, i32, PU64, PU64, u32, PU32]),
+    "mzgpu_batch_walk_column": (i32, [vp, PU64, u64, u64, i32, vp, u64, i32, PU64, PU64]),
 }
+COLUMN_U64X4, COLUMN_U64X2, COLUMN_ROWROW = 0, 1, 2
 
 KEY_RUN = np.dtype([("key", "<u8"), ("first", "<u8"), ("len", "<u8")])
 ARRANGEMENT_SIZE = np.dtype([("size_bytes", "<u8"), ("capacity_bytes", "<u8"), ("allocations", "<u8"), ("batches", "<u8"), ("updates", "<u8")])

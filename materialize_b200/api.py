@@ -642,3 +642,64 @@ class Correction:
         if getattr(self, "h", None) and self.ctx.h:
             F.lib.mzgpu_correction_free(self.h)
             self.h = None
+
+
+# ---- f4: the columnar wire format (Column<C>, src/timely-util/src/columnar.rs:54-222)
+def column_decode(ctx, layout, words, out=None):
+    """Column::borrow() + drain on the device: append the updates of one serialized container
+    (numpy u64 words) to `out` (a DeviceRows; created if None) and return it."""
+    words = np.ascontiguousarray(words, dtype="<u8")
+    if out is None:
+        out = DeviceRows(ctx, 16 if layout == F.COLUMN_U64X2 else 32)
+    ctx.check(F.lib.mzgpu_column_decode(ctx.h, layout, _ptr(words), len(words), F.MEM_HOST, out.h))
+    return out
+
+
+def column_encode(dev_rows, layout, first=0, n=(1 << 64) - 1):
+    """indexed::encode of rows [first, first + n) of a DeviceRows -> numpy u64 words."""
+    ctx = dev_rows.ctx
+    need = C.c_uint64(0)
+    st = F.lib.mzgpu_column_encode(dev_rows.h, layout, first, n, None, 0, F.MEM_HOST, C.byref(need))
+    if st not in (F.OK, F.E_CAPACITY):
+        ctx.check(st)
+    words = np.zeros(need.value, dtype="<u8")
+    ctx.check(F.lib.mzgpu_column_encode(dev_rows.h, layout, first, n, _ptr(words), len(words), F.MEM_HOST, C.byref(need)))
+    return words
+
+
+def column_build(dev_rows, layout):
+    """ColumnBuilder over a DeviceRows: the serialized containers it mints, in order."""
+    ctx = dev_rows.ctx
+    need, nch = C.c_uint64(0), C.c_uint32(0)
+    st = F.lib.mzgpu_column_build(dev_rows.h, layout, None, 0, F.MEM_HOST, C.byref(need), None, 0, C.byref(nch))
+    if st not in (F.OK, F.E_CAPACITY):
+        ctx.check(st)
+    words = np.zeros(need.value, dtype="<u8")
+    sizes = np.zeros(max(1, nch.value), dtype="<u8")
+    ctx.check(
+        F.lib.mzgpu_column_build(
+            dev_rows.h, layout, _ptr(words), len(words), F.MEM_HOST, C.byref(need),
+            sizes.ctypes.data_as(C.POINTER(C.c_uint64)), len(sizes), C.byref(nch),
+        )
+    )
+    out, at = [], 0
+    for i in range(nch.value):
+        out.append(words[at : at + int(sizes[i])])
+        at += int(sizes[i])
+    return out
+
+
+def batch_walk_column(batch, layout, key=None, first=0, fuel=(1 << 64) - 1):
+    """walk_cursor over one batch into a serialized container (src/compute/src/render/context.rs:1299-1355);
+    returns (words, rows emitted)."""
+    ctx = batch.ctx
+    kp = C.byref(C.c_uint64(key)) if key is not None else None
+    need, nrows = C.c_uint64(0), C.c_uint64(0)
+    st = F.lib.mzgpu_batch_walk_column(batch.h, kp, first, fuel, layout, None, 0, F.MEM_HOST, C.byref(need), C.byref(nrows))
+    if st not in (F.OK, F.E_CAPACITY):
+        ctx.check(st)
+    words = np.zeros(need.value, dtype="<u8")
+    ctx.check(
+        F.lib.mzgpu_batch_walk_column(batch.h, kp, first, fuel, layout, _ptr(words), len(words), F.MEM_HOST, C.byref(need), C.byref(nrows))
+    )
+    return words, nrows.value

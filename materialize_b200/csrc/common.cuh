@@ -807,6 +807,18 @@ int32_t mz_reduce_corrections(mzgpu_ctx* ctx, const u64* d_batch_rows, u64 n, co
                               int agg_kind, DevMem* out, u64* n_out);
 
 // correction.cu (time-major rows: (time, key, val | diff))
+// column.cu (columnar wire format, f4)
+int32_t mz_col_decode_fixed(mzgpu_ctx* ctx, int nw, const u64* d_words, u64 n, const u64* off_words, u64* d_dst,
+                            u64 base);
+int32_t mz_col_encode_fixed(mzgpu_ctx* ctx, int nw, const u64* d_rows, u64 first, u64 n, const u64* off_words,
+                            u64* d_words);
+int32_t mz_col_decode_rows(mzgpu_ctx* ctx, const u64* d_words, u64 n, const u64* off_words, u64 key_bytes,
+                           u64 val_bytes, u64* d_dst, u64 base, u64* d_flag);
+int32_t mz_col_row_prefix(mzgpu_ctx* ctx, const u64* d_rows, u64 first, u64 n, u64* d_bsum, u64* d_pk, u64* d_pv,
+                          u64* d_tot);
+int32_t mz_col_encode_rows(mzgpu_ctx* ctx, const u64* d_rows, u64 first, u64 s, u64 n, const u64* d_pk,
+                           const u64* d_pv, const u64* off_words, u64* d_words);
+int32_t mz_col_cuts(mzgpu_ctx* ctx, const u64* d_pk, const u64* d_pv, u64 n, u64* d_cuts, u64 cap, u64* d_n_cuts);
 int32_t mz_corr_to_td(mzgpu_ctx* ctx, const u64* d_rows, DLen n, u64 n_ub, u64 since, bool negate, u64* d_td, DLen base,
                       u64 cap_rows, u64* d_out_len);
 int32_t mz_corr_advance(mzgpu_ctx* ctx, u64* d_td, DLen n, u64 n_ub, u64 since);

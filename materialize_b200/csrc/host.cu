@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstring>
 #include <deque>
 #include <memory>
 #include <new>
@@ -2712,6 +2713,285 @@ extern "C" uint64_t mzgpu_correction_len(mzgpu_correction* c) {
   if (correction_consolidate(c) != MZGPU_OK) return 0;
   if (buf_resolve(&c->td) != MZGPU_OK) return 0;
   return c->td.len.v[c->td.word];
+}
+
+// ================================================ f4: columnar wire format
+// Host side of column.cu: index arithmetic of `columnar::bytes::indexed`, the ship heuristic, and the
+// entry points that move serialized containers in and out of row buffers.
+static int col_slices(int32_t layout) {
+  return layout == MZGPU_COLUMN_U64X2 ? 2 : layout == MZGPU_COLUMN_U64X4 ? 4 : layout == MZGPU_COLUMN_ROWROW ? 6 : 0;
+}
+static uint32_t col_row_bytes(int32_t layout) { return layout == MZGPU_COLUMN_U64X2 ? 16 : 32; }
+static u64 col_words(int32_t layout, u64 rows, u64 kbytes, u64 vbytes) {
+  switch (layout) {
+    case MZGPU_COLUMN_U64X2: return 3 + 2 * rows;
+    case MZGPU_COLUMN_U64X4: return 5 + 4 * rows;
+    case MZGPU_COLUMN_ROWROW: return 7 + 4 * rows + (kbytes + 7) / 8 + (vbytes + 7) / 8;
+  }
+  return 0;
+}
+static bool col_at_capacity(u64 words) {
+  const u64 ship = 1ull << 18;
+  const u64 round = (words + (ship - 1)) & ~(ship - 1);
+  return round - words < round / 10;
+}
+// word offsets of the slices of one container
+static void col_offsets(int32_t layout, u64 rows, u64 kbytes, u64 vbytes, u64 off[6]) {
+  const int k = col_slices(layout);
+  u64 at = (u64)k + 1;
+  for (int i = 0; i < 6; ++i) off[i] = 0;
+  for (int i = 0; i < k; ++i) {
+    off[i] = at;
+    if (layout == MZGPU_COLUMN_ROWROW && i == 1)
+      at += (kbytes + 7) / 8;
+    else if (layout == MZGPU_COLUMN_ROWROW && i == 3)
+      at += (vbytes + 7) / 8;
+    else
+      at += rows;
+  }
+}
+extern "C" uint64_t mzgpu_column_length_in_words(int32_t layout, uint64_t rows, uint64_t key_bytes,
+                                                 uint64_t val_bytes) {
+  return col_words(layout, rows, key_bytes, val_bytes);
+}
+extern "C" int32_t mzgpu_column_at_capacity(uint64_t words) { return col_at_capacity(words) ? 1 : 0; }
+extern "C" uint64_t mzgpu_column_ship_rows(int32_t layout) {
+  if (layout != MZGPU_COLUMN_U64X2 && layout != MZGPU_COLUMN_U64X4) return 0;
+  // the ship signal first fires at 2^18 - 2^18 / 10 + 1 words (the size grows by 2 or 4 words a push)
+  const u64 ship = (1ull << 18) - (1ull << 18) / 10 + 1, per = layout == MZGPU_COLUMN_U64X2 ? 2 : 4;
+  const u64 fixed = layout == MZGPU_COLUMN_U64X2 ? 3 : 5;
+  return (ship - fixed + per - 1) / per;
+}
+
+extern "C" int32_t mzgpu_column_decode(mzgpu_ctx* ctx, int32_t layout, const uint64_t* words, uint64_t n_words,
+                                       int32_t mem, mzgpu_buf* out) {
+  MZ_CHECK_CTX(ctx);
+  const int k = col_slices(layout);
+  if (k == 0 || out == nullptr || words == nullptr || out->ctx != ctx || out->rb != col_row_bytes(layout) ||
+      ((uintptr_t)words & 7))
+    return MZGPU_E_INVALID;
+  if (n_words < (u64)k + 1) {
+    MZ_SET_ERR(ctx, "column_decode: %llu words cannot hold an index of %d offsets", (unsigned long long)n_words, k + 1);
+    return MZGPU_E_INVALID;
+  }
+  u64 idx[7];
+  if (mem == MZGPU_MEM_HOST) {
+    std::memcpy(idx, words, 8 * (size_t)(k + 1));
+  } else {
+    MZ_CUDA(ctx, cudaMemcpyAsync(idx, words, 8 * (size_t)(k + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    MZ_SYNC(ctx);
+  }
+  // indexed::decode: slice i = [round_up(idx[i], 8), idx[i + 1]); a container of this layout has
+  // k slices whose row-count-sized members agree
+  bool ok = idx[0] == 8 * (u64)(k + 1) && idx[k] <= 8 * n_words;
+  u64 off[6] = {0, 0, 0, 0, 0, 0}, len[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; ok && i < k; ++i) {
+    const u64 lo = (idx[i] + 7) & ~7ull;
+    if (idx[i + 1] < lo && !(idx[i + 1] == idx[i])) ok = false;
+    off[i] = lo / 8;
+    len[i] = idx[i + 1] >= lo ? idx[i + 1] - lo : 0;
+  }
+  const u64 n = ok ? len[k - 1] / 8 : 0;
+  for (int i = 0; ok && i < k; ++i) {
+    const bool bytes_slice = layout == MZGPU_COLUMN_ROWROW && (i == 1 || i == 3);
+    if (!bytes_slice && len[i] != 8 * n) ok = false;
+  }
+  if (!ok) {
+    MZ_SET_ERR(ctx, "column_decode: the index is not that of a layout-%d container", layout);
+    return MZGPU_E_INVALID;
+  }
+  if (n == 0) return MZGPU_OK;
+  DevMem in;
+  const u64* d_words = words;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(in.alloc(ctx, n_words * 8));
+    MZ_TRY(copy_in(ctx, in.p, words, n_words * 8, mem));
+    d_words = in.as<u64>();
+  }
+  MZ_TRY(buf_resolve(out));  // the rows land at a base the host knows
+  const u64 base = out->ub;
+  MZ_TRY(buf_reserve(out, base + n, true));
+  if (layout != MZGPU_COLUMN_ROWROW) {
+    MZ_TRY(mz_col_decode_fixed(ctx, k, d_words, n, off, out->mem.as<u64>(), base));
+    buf_set_len(out, base + n);
+    ctx->stats.rows_in += n;
+    return MZGPU_OK;
+  }
+  Lazy4 flag;
+  MZ_TRY(flag.make_pending(ctx));
+  MZ_CUDA(ctx, cudaMemsetAsync(flag.dptr(), 0, 32, ctx->stream));
+  MZ_TRY(mz_col_decode_rows(ctx, d_words, n, off, len[1], len[3], out->mem.as<u64>(), base, flag.dptr()));
+  flag.mark_written();
+  MZ_TRY(flag.resolve());
+  if (flag.v[0] == 2) {
+    MZ_SET_ERR(ctx, "column_decode: Row bounds are not monotone or point outside the bytes slice");
+    return MZGPU_E_INVALID;
+  }
+  if (flag.v[0] == 1) {
+    MZ_SET_ERR(ctx, "column_decode: a Row is longer than 7 bytes (variable-width keys: SURVEY 8f-1)");
+    return MZGPU_E_UNSUPPORTED;
+  }
+  buf_set_len(out, base + n);  // committed only now: a rejected container appends nothing
+  ctx->stats.rows_in += n;
+  return MZGPU_OK;
+}
+
+// prefix sums of the Row byte lengths of rows [first, first + n) (ROWROW)
+struct RowPrefix {
+  DevMem bsum, pk, pv;
+  Lazy4 tot;
+};
+static int32_t row_prefix(mzgpu_ctx* ctx, const u64* d_rows, u64 first, u64 n, RowPrefix* rp) {
+  const u64 nb = (n + 2047) / 2048;
+  MZ_TRY(rp->bsum.alloc(ctx, 16 * (nb + 1)));
+  MZ_TRY(rp->pk.alloc(ctx, 8 * (n + 1)));
+  MZ_TRY(rp->pv.alloc(ctx, 8 * (n + 1)));
+  MZ_TRY(rp->tot.make_pending(ctx));
+  MZ_TRY(mz_col_row_prefix(ctx, d_rows, first, n, rp->bsum.as<u64>(), rp->pk.as<u64>(), rp->pv.as<u64>(),
+                           rp->tot.dptr()));
+  rp->tot.mark_written();
+  return MZGPU_OK;
+}
+// one container of rows [s, s + n) of the range into d_words (capacity checked by the caller)
+static int32_t col_encode_into(mzgpu_ctx* ctx, int32_t layout, const u64* d_rows, u64 first, u64 s, u64 n,
+                               const RowPrefix* rp, u64 kbytes, u64 vbytes, u64* d_words) {
+  u64 off[6];
+  col_offsets(layout, n, kbytes, vbytes, off);
+  if (layout != MZGPU_COLUMN_ROWROW) return mz_col_encode_fixed(ctx, col_slices(layout), d_rows, first + s, n, off, d_words);
+  // zero padding of the two byte slices' last words
+  if (kbytes % 8) MZ_CUDA(ctx, cudaMemsetAsync(d_words + off[1] + kbytes / 8, 0, 8, ctx->stream));
+  if (vbytes % 8) MZ_CUDA(ctx, cudaMemsetAsync(d_words + off[3] + vbytes / 8, 0, 8, ctx->stream));
+  return mz_col_encode_rows(ctx, d_rows, first, s, n, rp->pk.as<u64>(), rp->pv.as<u64>(), off, d_words);
+}
+// rows [first, first + n) of a device row array as ONE container in caller memory
+static int32_t col_encode_range(mzgpu_ctx* ctx, int32_t layout, const u64* d_rows, u64 first, u64 n, u64* words,
+                                u64 cap_words, int32_t mem, u64* n_words) {
+  RowPrefix rp;
+  u64 kb = 0, vb = 0;
+  if (layout == MZGPU_COLUMN_ROWROW) {
+    MZ_TRY(row_prefix(ctx, d_rows, first, n, &rp));
+    MZ_TRY(rp.tot.resolve());
+    kb = rp.tot.v[0], vb = rp.tot.v[1];
+  }
+  const u64 need = col_words(layout, n, kb, vb);
+  if (n_words) *n_words = need;
+  if (need > cap_words || words == nullptr) {
+    MZ_SET_ERR(ctx, "column_encode: %llu words needed, capacity %llu", (unsigned long long)need,
+               (unsigned long long)cap_words);
+    return MZGPU_E_CAPACITY;
+  }
+  DevMem stage;
+  u64* d_words = words;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(stage.alloc(ctx, need * 8));
+    d_words = stage.as<u64>();
+  }
+  MZ_TRY(col_encode_into(ctx, layout, d_rows, first, 0, n, &rp, kb, vb, d_words));
+  if (mem == MZGPU_MEM_HOST) MZ_TRY(copy_out(ctx, words, d_words, need * 8, mem));
+  else MZ_SYNC(ctx);
+  ctx->stats.rows_out += n;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_column_encode(mzgpu_buf* rows, int32_t layout, uint64_t first, uint64_t n, uint64_t* words,
+                                       uint64_t cap_words, int32_t mem, uint64_t* n_words) {
+  if (rows == nullptr || col_slices(layout) == 0 || rows->rb != col_row_bytes(layout) || ((uintptr_t)words & 7))
+    return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = rows->ctx;
+  MZ_CHECK_CTX(ctx);
+  MZ_TRY(buf_resolve(rows));
+  if (first > rows->ub) first = rows->ub;
+  if (n > rows->ub - first) n = rows->ub - first;
+  return col_encode_range(ctx, layout, rows->mem.as<u64>(), first, n, words, cap_words, mem, n_words);
+}
+extern "C" int32_t mzgpu_column_build(mzgpu_buf* rows, int32_t layout, uint64_t* words, uint64_t cap_words,
+                                      int32_t mem, uint64_t* n_words, uint64_t* chunk_words, uint32_t cap_chunks,
+                                      uint32_t* n_chunks) {
+  if (rows == nullptr || col_slices(layout) == 0 || rows->rb != col_row_bytes(layout) || ((uintptr_t)words & 7))
+    return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = rows->ctx;
+  MZ_CHECK_CTX(ctx);
+  MZ_TRY(buf_resolve(rows));
+  const u64 n = rows->ub;
+  // container j = rows [start[j], start[j + 1]) with kb[j] / vb[j] Row bytes
+  std::vector<u64> ends, kbs, vbs;
+  RowPrefix rp;
+  if (layout != MZGPU_COLUMN_ROWROW) {
+    const u64 ship = mzgpu_column_ship_rows(layout);
+    for (u64 s = 0; s < n; s += ship) ends.push_back(std::min<u64>(n, s + ship));
+    kbs.assign(ends.size(), 0), vbs.assign(ends.size(), 0);
+  } else if (n) {
+    MZ_TRY(row_prefix(ctx, rows->mem.as<u64>(), 0, n, &rp));
+    const u64 cap = n / 39000 + 2;  // a container holds at least (235931 - 7) / 6 rows
+    DevMem d_cuts;
+    MZ_TRY(d_cuts.alloc(ctx, 8 * (3 * cap + 1)));
+    MZ_TRY(mz_col_cuts(ctx, rp.pk.as<u64>(), rp.pv.as<u64>(), n, d_cuts.as<u64>() + 1, cap, d_cuts.as<u64>()));
+    std::vector<u64> h(3 * cap + 1);
+    MZ_TRY(copy_out(ctx, h.data(), d_cuts.p, 8 * h.size(), MZGPU_MEM_HOST));
+    if (h[0] > cap) {
+      MZ_SET_ERR(ctx, "column_build: %llu containers exceed the bound %llu", (unsigned long long)h[0], (unsigned long long)cap);
+      return MZGPU_E_CAPACITY;
+    }
+    u64 pk = 0, pv = 0;
+    for (u64 j = 0; j < h[0]; ++j) {
+      ends.push_back(h[1 + 3 * j]);
+      kbs.push_back(h[2 + 3 * j] - pk), vbs.push_back(h[3 + 3 * j] - pv);
+      pk = h[2 + 3 * j], pv = h[3 + 3 * j];
+    }
+  }
+  u64 total = 0;
+  for (size_t j = 0; j < ends.size(); ++j) total += col_words(layout, ends[j] - (j ? ends[j - 1] : 0), kbs[j], vbs[j]);
+  if (n_words) *n_words = total;
+  if (n_chunks) *n_chunks = (uint32_t)ends.size();
+  if (total > cap_words || ends.size() > cap_chunks || (total && words == nullptr) ||
+      (!ends.empty() && chunk_words == nullptr)) {
+    MZ_SET_ERR(ctx, "column_build: %llu words in %zu containers needed, capacity %llu / %u",
+               (unsigned long long)total, ends.size(), (unsigned long long)cap_words, cap_chunks);
+    return MZGPU_E_CAPACITY;
+  }
+  if (ends.empty()) return MZGPU_OK;
+  DevMem stage;
+  u64* d_words = words;
+  if (mem == MZGPU_MEM_HOST) {
+    MZ_TRY(stage.alloc(ctx, total * 8));
+    d_words = stage.as<u64>();
+  }
+  u64 at = 0;
+  for (size_t j = 0; j < ends.size(); ++j) {
+    const u64 s = j ? ends[j - 1] : 0, cnt = ends[j] - s;
+    MZ_TRY(col_encode_into(ctx, layout, rows->mem.as<u64>(), 0, s, cnt, &rp, kbs[j], vbs[j], d_words + at));
+    chunk_words[j] = col_words(layout, cnt, kbs[j], vbs[j]);
+    at += chunk_words[j];
+  }
+  if (mem == MZGPU_MEM_HOST) MZ_TRY(copy_out(ctx, words, d_words, total * 8, mem));
+  else MZ_SYNC(ctx);
+  ctx->stats.rows_out += n;
+  return MZGPU_OK;
+}
+extern "C" int32_t mzgpu_batch_walk_column(mzgpu_batch* b, const uint64_t* key, uint64_t first, uint64_t fuel,
+                                           int32_t layout, uint64_t* words, uint64_t cap_words, int32_t mem,
+                                           uint64_t* n_words, uint64_t* n_rows) {
+  if (b == nullptr || col_slices(layout) == 0 || b->rb != col_row_bytes(layout) || ((uintptr_t)words & 7))
+    return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = b->ctx;
+  MZ_CHECK_CTX(ctx);
+  MZ_TRY(batch_ready(b));
+  MZ_TRY(batch_resolve(b));
+  u64 lo = 0, len = b->st.v[0];
+  if (key != nullptr) {
+    // seek_key: only this key's rows are walked (context.rs:1314-1333)
+    mzgpu_key_run run;
+    MZ_TRY(mzgpu_batch_seek_keys(b, key, 1, MZGPU_MEM_HOST, &run));
+    if (run.len == 0 || run.key != *key) {
+      lo = 0, len = 0;
+    } else {
+      lo = run.first, len = run.len;
+    }
+  }
+  if (first > len) first = len;
+  u64 cnt = len - first;
+  if (cnt > fuel) cnt = fuel;
+  if (n_rows) *n_rows = cnt;
+  return col_encode_range(ctx, layout, b->rows.as<u64>(), lo + first, cnt, words, cap_words, mem, n_words);
 }
 
 // ================================================================= exchange

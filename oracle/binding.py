@@ -178,6 +178,13 @@ def lib():
             "mzo_explode": (None, [vp, u64, i32, vp]),
             "mzo_finalize": (None, [vp, u64, i32, vp]),
             "mzo_route": (u32, [u64, u32]),
+            "mzo_col_encode_slices": (None, [vp, vp, u32, vp]),
+            "mzo_col_decode_slices": (i32, [vp, u64, vp, u32]),
+            "mzo_col_length_in_words": (u64, [vp, u32]),
+            "mzo_col_at_capacity": (i32, [u64]),
+            "mzo_column_encode": (None, [i32, vp, u64, vp]),
+            "mzo_column_rows": (i32, [i32, vp, u64, vp]),
+            "mzo_column_builder": (u32, [i32, vp, u64, vp, vp, u32]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -525,3 +532,89 @@ def gen_cfg4(seed, first, n, cdf, as_f64=False):
     out = np.zeros(n, dtype=R32)
     _q3_sigs().mzo_gen_cfg4(seed, first, n, _ptr(cdf), len(cdf), 1 if as_f64 else 0, _ptr(out))
     return out
+
+
+# ---- f4: columnar wire format (oracle/mzo_column.hpp)
+COLUMN_U64X4, COLUMN_U64X2, COLUMN_ROWROW = 0, 1, 2
+
+
+def _words(vec_h):
+    n = lib().mzo_vec_len(vec_h)
+    if n == 0:
+        return np.zeros(0, dtype="<u8")
+    buf = (C.c_char * (n * 8)).from_address(lib().mzo_vec_data(vec_h))
+    return np.frombuffer(buf, dtype="<u8").copy()
+
+
+def col_encode_slices(slices):
+    """indexed::encode over raw byte slices -> words."""
+    keep = [np.frombuffer(bytes(s), dtype=np.uint8) if len(s) else np.zeros(0, np.uint8) for s in slices]
+    ptrs = (C.c_void_p * len(keep))(*[a.ctypes.data if len(a) else None for a in keep])
+    lens = np.array([len(a) for a in keep], dtype="<u8")
+    h = lib().mzo_vec_new(8)
+    try:
+        lib().mzo_col_encode_slices(ptrs, _ptr(lens), len(keep), h)
+        return _words(h)
+    finally:
+        lib().mzo_vec_free(h)
+
+
+def col_decode_slices(words):
+    """indexed::decode -> list of bytes (None if malformed)."""
+    words = np.ascontiguousarray(words, dtype="<u8")
+    off_len = np.zeros(2 * 64, dtype="<u8")
+    k = lib().mzo_col_decode_slices(_ptr(words), len(words), _ptr(off_len), 64)
+    if k < 0:
+        return None
+    raw = words.tobytes()
+    return [raw[int(off_len[2 * i]) : int(off_len[2 * i] + off_len[2 * i + 1])] for i in range(k)]
+
+
+def col_length_in_words(lens):
+    lens = np.array(list(lens), dtype="<u8")
+    return lib().mzo_col_length_in_words(_ptr(lens), len(lens))
+
+
+def col_at_capacity(words):
+    return bool(lib().mzo_col_at_capacity(words))
+
+
+def column_encode(layout, a):
+    """One serialized container holding the R32 rows `a` (U64X2 uses key and diff only)."""
+    a = np.ascontiguousarray(a, dtype=R32)
+    h = lib().mzo_vec_new(8)
+    try:
+        lib().mzo_column_encode(layout, _ptr(a), len(a), h)
+        return _words(h)
+    finally:
+        lib().mzo_vec_free(h)
+
+
+def column_rows(layout, words):
+    """The updates of a serialized container as R32 rows; raises ValueError (malformed) or
+    NotImplementedError (a Row longer than 7 bytes)."""
+    words = np.ascontiguousarray(words, dtype="<u8")
+    v = Vec(32)
+    rc = lib().mzo_column_rows(layout, _ptr(words), len(words), v.h)
+    if rc == -1:
+        raise ValueError("malformed container")
+    if rc == -2:
+        raise NotImplementedError("Row longer than 7 bytes")
+    return v.array()
+
+
+def column_builder(layout, a):
+    """ColumnBuilder over the rows: list of serialized containers in order."""
+    a = np.ascontiguousarray(a, dtype=R32)
+    h = lib().mzo_vec_new(8)
+    try:
+        sizes = np.zeros(4096, dtype="<u8")
+        k = lib().mzo_column_builder(layout, _ptr(a), len(a), h, _ptr(sizes), len(sizes))
+        w = _words(h)
+        out, at = [], 0
+        for i in range(k):
+            out.append(w[at : at + int(sizes[i])])
+            at += int(sizes[i])
+        return out
+    finally:
+        lib().mzo_vec_free(h)

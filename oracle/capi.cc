@@ -8,6 +8,7 @@
 #include <sstream>
 #include <string>
 
+#include "mzo_column.hpp"
 #include "mzo_correction.hpp"
 #include "mzo_ops.hpp"
 #include "mzo_vec.hpp"
@@ -530,6 +531,59 @@ uint64_t mzo_correction_chains(void* cv, uint64_t* lens, uint64_t cap, uint64_t*
   for (size_t i = 0; i < c->chains.size() && i < cap; ++i) lens[i] = c->chains[i].size();
   if (staged) *staged = c->stage.size();
   return c->chains.size();
+}
+
+// ---- f4: columnar wire format (mzo_column.hpp)
+// generic indexed::encode over caller slices (the reference's Column<i32> golden bytes)
+void mzo_col_encode_slices(const void* const* ptrs, const uint64_t* lens, uint32_t k, void* vec) {
+  std::vector<ColSlice> s;
+  for (uint32_t i = 0; i < k; i++) s.push_back(ColSlice{(const uint8_t*)ptrs[i], (size_t)lens[i]});
+  std::vector<uint64_t> store;
+  col_encode(store, s);
+  vec_append((Vec*)vec, store);
+}
+// indexed::decode: (byte offset, byte length) of every slice; -1 if malformed
+int32_t mzo_col_decode_slices(const uint64_t* words, uint64_t n_words, uint64_t* off_len, uint32_t cap) {
+  std::vector<ColSlice> s;
+  if (!col_decode(words, n_words, &s)) return -1;
+  for (size_t i = 0; i < s.size() && i < cap; i++) {
+    off_len[2 * i] = (uint64_t)(s[i].p - (const uint8_t*)words);
+    off_len[2 * i + 1] = s[i].len;
+  }
+  return (int32_t)s.size();
+}
+uint64_t mzo_col_length_in_words(const uint64_t* lens, uint32_t k) {
+  std::vector<ColSlice> s;
+  for (uint32_t i = 0; i < k; i++) s.push_back(ColSlice{nullptr, (size_t)lens[i]});
+  return col_length_in_words(s);
+}
+int32_t mzo_col_at_capacity(uint64_t words) { return col_at_capacity(words) ? 1 : 0; }
+// one container holding all the rows
+void mzo_column_encode(int32_t layout, const mzgpu_r32* rows, uint64_t n, void* vec) {
+  ColumnTyped c;
+  c.layout = layout;
+  for (uint64_t i = 0; i < n; i++) column_push(c, rows[i]);
+  std::vector<uint64_t> store;
+  col_encode(store, c.as_bytes());
+  vec_append((Vec*)vec, store);
+}
+int32_t mzo_column_rows(int32_t layout, const uint64_t* words, uint64_t n_words, void* vec) {
+  std::vector<mzgpu_r32> out;
+  int rc = column_rows(layout, words, n_words, &out);
+  if (rc == 0) vec_append((Vec*)vec, out);
+  return rc;
+}
+// ColumnBuilder: push every row, finish; containers back to back in `vec`, sizes in chunk_words
+uint32_t mzo_column_builder(int32_t layout, const mzgpu_r32* rows, uint64_t n, void* vec, uint64_t* chunk_words,
+                            uint32_t cap) {
+  ColumnBuilder b(layout);
+  for (uint64_t i = 0; i < n; i++) b.push(rows[i]);
+  b.finish();
+  for (size_t i = 0; i < b.pending.size(); i++) {
+    if (i < cap) chunk_words[i] = b.pending[i].size();
+    vec_append((Vec*)vec, b.pending[i]);
+  }
+  return (uint32_t)b.pending.size();
 }
 
 }  // extern "C"

@@ -105,3 +105,24 @@ def test_row_keys_pack_order_preserving_and_invertible():
     keys2 = (C.c_uint64 * 2)()
     assert F.lib.mzgpu_rowkeys_pack(buf2, offs2, 2, keys2, C.byref(done)) == F.E_UNSUPPORTED and done.value == 1
     assert F.lib.mzgpu_rowkey_unpack((8 << 56), out, C.byref(n)) == F.E_INVALID
+
+
+def test_column_size_arithmetic_matches_oracle(oracle):
+    """f4: the pure host functions of the columnar wire format (indexed::length_in_words, the ship signal of
+    columnar.rs:164-175 / builder.rs:48-52, rows per minted container) agree with the oracle restatement."""
+    import numpy as np
+
+    import materialize_b200._ffi as F
+
+    rng = np.random.default_rng(1)
+    for words in [0, 1, 235930, 235931, 262143, 262144, 262145, 471860, 471861, 524288] + rng.integers(0, 1 << 24, size=200).tolist():
+        assert bool(F.lib.mzgpu_column_at_capacity(int(words))) == oracle.col_at_capacity(int(words))
+    for n, kb, vb in [(0, 0, 0), (1, 0, 7), (1000, 3001, 12), (58982, 1, 1)]:
+        assert F.lib.mzgpu_column_length_in_words(F.COLUMN_U64X4, n, kb, vb) == oracle.col_length_in_words([8 * n] * 4)
+        assert F.lib.mzgpu_column_length_in_words(F.COLUMN_U64X2, n, kb, vb) == oracle.col_length_in_words([8 * n] * 2)
+        assert F.lib.mzgpu_column_length_in_words(F.COLUMN_ROWROW, n, kb, vb) == oracle.col_length_in_words([8 * n, kb, 8 * n, vb, 8 * n, 8 * n])
+    a = np.zeros(120_000, dtype=oracle.R32)
+    for layout in (F.COLUMN_U64X4, F.COLUMN_U64X2):
+        first = oracle.column_builder(layout, a)[0]
+        assert F.lib.mzgpu_column_ship_rows(layout) == len(oracle.column_rows(layout, first))
+    assert F.lib.mzgpu_column_ship_rows(F.COLUMN_ROWROW) == 0

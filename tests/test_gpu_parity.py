@@ -1288,6 +1288,133 @@ def test_device_correction_buffer_matches_oracle(mz, ctx, oracle):
         assert len(g.updates_before(EMPTY)) == 0
 
 
+def _column_rows(oracle, rng, n, row_keys):
+    a = np.zeros(n, dtype=oracle.R32)
+    if row_keys:
+        for f in ("key", "val"):
+            lens = rng.integers(0, 8, size=n, dtype=np.uint64)
+            body = rng.integers(0, 1 << 56, size=n, dtype=np.uint64)
+            keep = np.where(lens == 0, np.uint64(0), ~((np.uint64(1) << (np.uint64(56) - np.uint64(8) * lens)) - np.uint64(1)) & np.uint64((1 << 56) - 1))
+            a[f] = (lens << np.uint64(56)) | (body & keep)
+    else:
+        a["key"] = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * 2 + 1
+        a["val"] = rng.integers(0, 1 << 40, size=n, dtype=np.uint64)
+    a["time"] = rng.integers(0, 50, size=n, dtype=np.uint64)
+    a["diff"] = rng.integers(-3, 4, size=n)
+    return a
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("n", [0, 1, 255, 4097, 200_000])
+def test_column_wire_format_matches_oracle(mz, ctx, oracle, layout, n):
+    """f4: a serialized `Column` (columnar.rs:54-222) decoded on the device gives the oracle's rows, and rows
+    encoded on the device give the oracle's bytes, word for word -- ((u64, u64), u64, i64), (u64, i64) and
+    ((Row, Row), Timestamp, Diff) with Rows of 0..7 bytes."""
+    rng = np.random.default_rng(900 + 10 * layout + n % 97)
+    a = _column_rows(oracle, rng, n, layout == 2)
+    words = oracle.column_encode(layout, a)
+    dev = mz.column_decode(ctx, layout, words)
+    got = dev.download()
+    if layout == 1:
+        assert got.dtype.itemsize == 16
+        assert got["key"].tobytes() == a["key"].tobytes() and got["diff"].tobytes() == a["diff"].tobytes()
+    else:
+        assert got.tobytes() == oracle.column_rows(layout, words).tobytes() == a.tobytes()
+    # decode appends: a second container lands behind the first
+    mz.column_decode(ctx, layout, words, out=dev)
+    assert len(dev) == 2 * n
+    assert dev.download()[n:].tobytes() == got.tobytes()
+    # encode: the same bytes back (a sub-range too)
+    assert mz.column_encode(dev, layout, 0, n).tobytes() == words.tobytes()
+    if n > 10:
+        sub = mz.column_encode(dev, layout, 3, n - 7)
+        assert sub.tobytes() == oracle.column_encode(layout, a[3 : n - 4]).tobytes()
+    assert mz._ffi.lib.mzgpu_column_length_in_words(layout, n, int((a["key"] >> np.uint64(56)).sum()) if layout == 2 else 0,
+                                                     int((a["val"] >> np.uint64(56)).sum()) if layout == 2 else 0) == len(words)
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+def test_column_builder_matches_oracle(mz, ctx, oracle, layout):
+    """ColumnBuilder (builder.rs:28-111) over a device buffer: the same containers, cut at the same rows, as
+    pushing the rows one at a time through the oracle's builder; decoding them all restores the rows."""
+    rng = np.random.default_rng(950 + layout)
+    n = 400_000
+    a = _column_rows(oracle, rng, n, layout == 2)
+    want = oracle.column_builder(layout, a)
+    dev = mz.DeviceRows(ctx, 16 if layout == 1 else 32)
+    if layout == 1:
+        r16 = np.zeros(n, dtype=mz.R16)
+        r16["key"], r16["diff"] = a["key"], a["diff"]
+        dev.upload(r16)
+    else:
+        dev.upload(a)
+    got = mz.column_build(dev, layout)
+    assert len(got) == len(want) >= 3
+    for g, w in zip(got, want):
+        assert g.tobytes() == w.tobytes()
+    back = mz.DeviceRows(ctx, dev.row_bytes)
+    for g in got:
+        mz.column_decode(ctx, layout, g, out=back)
+    assert back.download().tobytes() == dev.download().tobytes()
+    if layout != 2:
+        assert mz._ffi.lib.mzgpu_column_ship_rows(layout) == len(oracle.column_rows(layout, want[0]))
+
+
+def test_column_rejects_what_it_cannot_hold(mz, ctx, oracle):
+    """Malformed indexes are MZGPU_E_INVALID, a Row longer than 7 bytes is MZGPU_E_UNSUPPORTED, and neither
+    appends anything."""
+    F = mz._ffi
+    rng = np.random.default_rng(970)
+    a = _column_rows(oracle, rng, 1000, True)
+    words = oracle.column_encode(2, a)
+    out = mz.DeviceRows(ctx, 32).upload(a[:5])
+    for mutate in (lambda w: w.__setitem__(0, 48), lambda w: w.__setitem__(6, 8 * len(w) + 8), lambda w: w.__setitem__(3, w[3] + 8)):
+        bad = words.copy()
+        mutate(bad)
+        with pytest.raises(mz.MzGpuError) as e:
+            mz.column_decode(ctx, 2, bad, out=out)
+        assert e.value.status == F.E_INVALID
+    # bounds that run backwards are found on the device
+    bad = words.copy()
+    bad[7 + 10] = bad[7 + 9] - 1 if bad[7 + 9] else 999999
+    with pytest.raises(mz.MzGpuError) as e:
+        mz.column_decode(ctx, 2, bad, out=out)
+    assert e.value.status == F.E_INVALID
+    # an eight-byte Row
+    one = np.array([5], dtype="<u8").tobytes()
+    long_row = oracle.col_encode_slices([np.array([8], dtype="<u8").tobytes(), b"12345678", np.array([0], dtype="<u8").tobytes(), b"", one, one])
+    with pytest.raises(mz.MzGpuError) as e:
+        mz.column_decode(ctx, 2, long_row, out=out)
+    assert e.value.status == F.E_UNSUPPORTED
+    with pytest.raises(mz.MzGpuError):
+        mz.column_decode(ctx, 0, words, out=out)  # six slices are not a four-slice container
+    assert out.download().tobytes() == a[:5].tobytes()
+
+
+def test_batch_walk_into_columns(mz, ctx, oracle):
+    """walk_cursor (context.rs:1299-1355) over a sealed batch into containers: the whole batch in fuel-sized
+    pieces, and one key's rows after seek_key."""
+    rng = np.random.default_rng(980)
+    a = rand_r32(rng, 30_000, 2000, 50, 3, 1, 3, dtype=mz.R32)
+    gb = mz.Batcher(ctx, 32)
+    gb.push_container(a)
+    batch = gb.seal(3)
+    rows = batch.rows()
+    pieces, first = [], 0
+    while True:
+        words, n = mz.batch_walk_column(batch, 0, first=first, fuel=7001)
+        pieces.append(oracle.column_rows(0, words))
+        first += n
+        if n < 7001:
+            break
+    assert np.concatenate(pieces).tobytes() == rows.tobytes()
+    key = int(rows["key"][len(rows) // 2])
+    words, n = mz.batch_walk_column(batch, 0, key=key)
+    assert oracle.column_rows(0, words).tobytes() == rows[rows["key"] == key].tobytes() and n == (rows["key"] == key).sum()
+    words, n = mz.batch_walk_column(batch, 0, key=(1 << 63) + 12345)
+    assert n == 0 and len(oracle.column_rows(0, words)) == 0
+
+
 def test_q3_dataflow_matches_oracle(mz, ctx, oracle):
     """Hydration + update batches through the C++ harness (delta join, 3 paths x 2
     half_joins, reduce) vs the CPU oracle dataflow on the same seeded inputs."""
