@@ -96,7 +96,24 @@ struct mzgpu_ctx {
   u64* p2p_cursors = nullptr;       // [MZ_MAX_EXCHANGE][16] scatter cursors (zero between rounds)
   u32* p2p_done = nullptr;          // scatter CTAs finished (zero between rounds)
   bool p2p_ready = false;
+  // large blocks (>= MZ_BIG_BLOCK bytes) freed by this ctx, kept for reuse (DevMem): the bulk regimes
+  // (hydration, BASELINE configs 1/2/4) cycle through a handful of multi-GB arrays per call
+  struct BigBlock {
+    void* p;
+    size_t bytes;
+    cudaStream_t freed_on;  // the ctx stream at the time of the free
+  };
+  std::vector<BigBlock> big_cache;
+  size_t big_cached_bytes = 0;
+  u64 big_hits = 0, big_misses = 0;
 };
+// Blocks of at least this size bypass the driver's stream-ordered pool on reuse: measured on B200
+// (tools/diag_bulk.py cfg4, profiles/r02_diag_cfg4_before.log), cudaMallocAsync of 3-8 GB blocks cost
+// 0.2 s -> 1.9 s -> 4.3 s of HOST time per 100M-row reduce call although every block had been freed in
+// stream order before (20 ms of kernels per call).  The update-batch path (blocks of a few hundred MB
+// at most) allocates in microseconds and stays on the pool.
+#define MZ_BIG_BLOCK ((size_t)512 << 20)
+#define MZ_BIG_CACHE_MAX ((size_t)96 << 30)
 
 #define MZ_SET_ERR(ctx, ...)                              \
   do {                                                    \
@@ -211,8 +228,45 @@ struct DevMem {
     release();
     ctx = c;
     if (n == 0) n = 16;
+    if (n >= MZ_BIG_BLOCK) {
+      // best fit among the cached big blocks, wasting at most half of the block
+      int best = -1;
+      for (int i = 0; i < (int)c->big_cache.size(); ++i) {
+        const size_t b = c->big_cache[i].bytes;
+        if (b >= n && b / 2 <= n && (best < 0 || b < c->big_cache[best].bytes)) best = i;
+      }
+      if (best >= 0) {
+        const mzgpu_ctx::BigBlock blk = c->big_cache[best];
+        c->big_cache.erase(c->big_cache.begin() + best);
+        c->big_cached_bytes -= blk.bytes;
+        if (blk.freed_on != c->stream) {
+          // freed in another stream's order: everything enqueued there so far happens first
+          if (cudaEventRecord(c->ev, blk.freed_on) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->ev, 0) != cudaSuccess) {
+            MZ_SET_ERR(c, "big-block reuse: cross-stream ordering failed");
+            c->sticky = true;
+            return MZGPU_E_CUDA;
+          }
+        }
+        p = blk.p;
+        bytes = blk.bytes;
+        c->big_hits++;
+        c->stats.device_bytes_in_use += bytes;
+        if (c->stats.device_bytes_in_use > c->stats.device_bytes_peak)
+          c->stats.device_bytes_peak = c->stats.device_bytes_in_use;
+        return MZGPU_OK;
+      }
+      c->big_misses++;
+    }
     auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMallocAsync(&p, n, c->stream);
+    if (e != cudaSuccess && !c->big_cache.empty()) {
+      // out of memory with blocks parked in the cache: hand them back and try once more
+      (void)cudaGetLastError();
+      for (auto& b : c->big_cache) cudaFreeAsync(b.p, c->stream);
+      c->big_cache.clear();
+      c->big_cached_bytes = 0;
+      e = cudaMallocAsync(&p, n, c->stream);
+    }
     c->ns_alloc += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     c->n_alloc++;
     c->bytes_alloc += n;
@@ -230,8 +284,13 @@ struct DevMem {
   }
   void release() {
     if (p != nullptr) {
-      cudaFreeAsync(p, ctx->stream);
       ctx->stats.device_bytes_in_use -= bytes;
+      if (bytes >= MZ_BIG_BLOCK && ctx->big_cached_bytes + bytes <= MZ_BIG_CACHE_MAX) {
+        ctx->big_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream});
+        ctx->big_cached_bytes += bytes;
+      } else {
+        cudaFreeAsync(p, ctx->stream);
+      }
       p = nullptr;
       bytes = 0;
     }

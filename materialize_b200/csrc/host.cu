@@ -102,6 +102,8 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   for (int i = 0; i < 16; ++i)
     if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
   mz_fused_deferred_free(ctx);
+  for (auto& b : ctx->big_cache) cudaFree(b.p);
+  ctx->big_cache.clear();
   for (int p = 0; p < 16; ++p)
     if (ctx->p2p_peer_ipc[p] && ctx->p2p_peer[p]) cudaIpcCloseMemHandle(ctx->p2p_peer[p]);
   if (ctx->p2p_local) cudaFree(ctx->p2p_local);
@@ -237,10 +239,11 @@ extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   if (getenv("MZGPU_DEBUG"))
     fprintf(stderr,
             "[mzgpu] allocs %llu (%.1f MB, %.3f ms host)  syncs %llu (%.3f ms waiting)  launches %llu  counter blocks %d"
-            " in use (high water %d)\n",
+            " in use (high water %d)  big blocks: %llu reused, %llu new, %.1f MB parked\n",
             (unsigned long long)ctx->n_alloc, ctx->bytes_alloc / 1e6, ctx->ns_alloc / 1e6,
             (unsigned long long)ctx->stats.host_syncs, ctx->ns_sync / 1e6,
-            (unsigned long long)ctx->stats.kernel_launches, ctx->cnt_high - (int)ctx->cnt_free.size(), ctx->cnt_high);
+            (unsigned long long)ctx->stats.kernel_launches, ctx->cnt_high - (int)ctx->cnt_free.size(), ctx->cnt_high,
+            (unsigned long long)ctx->big_hits, (unsigned long long)ctx->big_misses, ctx->big_cached_bytes / 1e6);
   *out = ctx->stats;
   return MZGPU_OK;
 }

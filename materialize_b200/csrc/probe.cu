@@ -457,6 +457,7 @@ struct ProbeChain {
 };
 struct ProbeMany {
   u32 n_chains;
+  u32 steal;  // a CTA whose chain is exhausted moves on to the next chain (MZGPU_PROBE_STEAL=0: A/B, bisecting)
   ProbeChain chain[PROBE_MANY_MAX];
   ProbeJobDev job[PROBE_MANY_MAX];
 };
@@ -466,37 +467,49 @@ template <int OUT_NW>
 __global__ void __launch_bounds__(PT, 3) k_probe_chains(const __grid_constant__ ProbeMany m,
                                                      u64* __restrict__ status) {
   __shared__ ProbeSmem S;
-  const ProbeChain& ch = m.chain[blockIdx.y];
-  u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
-  u32 trj[PROBE_MANY_MAX];
-  tiles_before[0] = 0;
+  // A CTA starts on chain blockIdx.y and, when that chain's tickets run out, moves on to the next
+  // one: the chains of a launch differ in size by an order of magnitude (the lineitem path of a Q3
+  // step carries four times the rows of the orders path, the customer path none), and an equal split
+  // of the resident CTAs left the longest chain running four tiles deep on a third of the machine
+  // (profiles/r02: 44-55 us per launch at 20 % of the warp slots).  Tiles of a chain are still handed
+  // out in ticket order to CTAs that are all resident, so the look-back cannot deadlock.
+  const u32 rounds = m.steal ? m.n_chains : 1u;
+#pragma unroll 1
+  for (u32 r = 0; r < rounds; ++r) {
+    u32 ci = blockIdx.y + r;
+    if (ci >= m.n_chains) ci -= m.n_chains;
+    const ProbeChain& ch = m.chain[ci];
+    u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
+    u32 trj[PROBE_MANY_MAX];
+    tiles_before[0] = 0;
 #pragma unroll
-  for (int q = 0; q < PROBE_MANY_MAX; ++q) {
-    nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
-    trj[q] = (u32)q < ch.count ? m.job[ch.first + q].tile_rows : 256u;
-    tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
-  }
-  const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
-  const u64 base0 = dlen_get(ch.out_base);
-  while (true) {
-    const u32 tile = lb_next_tile(ch.lb, &S.tile);
-    if ((u64)tile >= n_tiles) {
-      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
-      break;
+    for (int q = 0; q < PROBE_MANY_MAX; ++q) {
+      nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
+      trj[q] = (u32)q < ch.count ? m.job[ch.first + q].tile_rows : 256u;
+      tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
     }
-    u32 q = 0;
-    while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
-    const ProbeJobDev& J = m.job[ch.first + q];
-    ProbePre pre;
-    pre.has_pre = J.has_pre;
-    pre.pre_has_closure = J.pre_has_closure;
-    pre.skip_time = J.skip_time;
-    pre.pre = &J.pre;
-    u64 excl;
-    u32 total;
-    probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q] / (PT / 32), J.tv, J.pp, pre,
-                       ch.lb, tile, ch.out, base0, ch.out_cap, status, &excl, &total);
-    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
+    const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
+    const u64 base0 = dlen_get(ch.out_base);
+    while (true) {
+      const u32 tile = lb_next_tile(ch.lb, &S.tile);
+      if ((u64)tile >= n_tiles) {
+        if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
+        break;
+      }
+      u32 q = 0;
+      while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
+      const ProbeJobDev& J = m.job[ch.first + q];
+      ProbePre pre;
+      pre.has_pre = J.has_pre;
+      pre.pre_has_closure = J.pre_has_closure;
+      pre.skip_time = J.skip_time;
+      pre.pre = &J.pre;
+      u64 excl;
+      u32 total;
+      probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q] / (PT / 32), J.tv, J.pp,
+                         pre, ch.lb, tile, ch.out, base0, ch.out_cap, status, &excl, &total);
+      if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
+    }
   }
 }
 
@@ -769,7 +782,7 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
   static thread_local ProbeMany m;  // large: kept off the stack
   memset(&m, 0, sizeof(m));
   const bool closure = jobs[0].pp->has_closure != 0;
-  u64 lb_at = 0, max_grid = 1, bytes = 0;
+  u64 lb_at = 0, max_grid = 1, bytes = 0, total_tiles = 0, max_chain_tiles = 0;
   int nc = 0;
   for (int j = 0; j < k; ++j) {
     if ((jobs[j].pp->has_closure != 0) != closure) {
@@ -807,12 +820,20 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     }
     MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
     lb_at += tiles;
-    // (all chains of a launch run side by side: each gets an equal share of the resident CTAs)
-    u64 g = probe_grid(ctx, tiles);
-    const u64 share = ((u64)ctx->num_sms * 3 + nc - 1) / (u64)nc;
-    if (g > share) g = share;
-    if (g > max_grid) max_grid = g;
+    total_tiles += tiles;
+    if (tiles > max_chain_tiles) max_chain_tiles = tiles;
   }
+  // all chains of a launch run side by side; a CTA whose chain is exhausted moves on to the next
+  // one, so the grid only has to cover the machine (or the work, if that is less)
+  static const bool steal = getenv("MZGPU_PROBE_STEAL") == nullptr || atoi(getenv("MZGPU_PROBE_STEAL")) != 0;
+  m.steal = steal ? 1u : 0u;
+  max_grid = ((u64)ctx->num_sms * 3) / (u64)nc;
+  if (steal) {
+    if (max_grid * (u64)nc > total_tiles) max_grid = (total_tiles + nc - 1) / (u64)nc;
+  } else if (max_grid > max_chain_tiles) {
+    max_grid = max_chain_tiles;  // chains keep to their own CTAs: the grid covers the longest chain
+  }
+  if (max_grid == 0) max_grid = 1;
   MZ_BYTES(ctx, bytes);
   if (closure) {
     MZ_LAUNCH(ctx, (k_probe_chains<4>), dim3((unsigned)max_grid, (unsigned)nc), PT, 0, m, ctx->d_status);

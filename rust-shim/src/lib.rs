@@ -7,6 +7,7 @@
 pub mod batch;
 pub mod batcher;
 pub mod builder;
+pub mod column;
 pub mod sys;
 pub mod trace;
 

@@ -84,7 +84,22 @@ extern "C" {
     pub fn mzgpu_buf_len(b: *mut Buf) -> u64;
     pub fn mzgpu_buf_download(b: *mut Buf, rows: *mut c_void, cap: u64, mem: i32, n_out: *mut u64) -> i32;
     pub fn mzgpu_buf_clear(b: *mut Buf) -> i32;
+    // f4: the columnar wire format (Column<C>)
+    pub fn mzgpu_column_length_in_words(layout: i32, rows: u64, key_bytes: u64, val_bytes: u64) -> u64;
+    pub fn mzgpu_column_at_capacity(words: u64) -> i32;
+    pub fn mzgpu_column_ship_rows(layout: i32) -> u64;
+    pub fn mzgpu_column_decode(ctx: *mut Ctx, layout: i32, words: *const u64, n_words: u64, mem: i32, out: *mut Buf) -> i32;
+    pub fn mzgpu_column_encode(rows: *mut Buf, layout: i32, first: u64, n: u64, words: *mut u64, cap_words: u64, mem: i32,
+                               n_words: *mut u64) -> i32;
+    pub fn mzgpu_column_build(rows: *mut Buf, layout: i32, words: *mut u64, cap_words: u64, mem: i32, n_words: *mut u64,
+                              chunk_words: *mut u64, cap_chunks: u32, n_chunks: *mut u32) -> i32;
+    pub fn mzgpu_batch_walk_column(batch: *mut Batch, key: *const u64, first: u64, fuel: u64, layout: i32, words: *mut u64,
+                                   cap_words: u64, mem: i32, n_words: *mut u64, n_rows: *mut u64) -> i32;
+    pub fn mzgpu_batcher_push_buf(b: *mut Batcher, rows: *mut Buf) -> i32;
 }
+pub const COLUMN_U64X4: i32 = 0;
+pub const COLUMN_U64X2: i32 = 1;
+pub const COLUMN_ROWROW: i32 = 2;
 
 /// Status -> Result; CUDA / NCCL failures are sticky: the caller panics the worker (compute state
 /// is soft, the replica rehydrates: src/cluster/src/communication.rs:18-27).
