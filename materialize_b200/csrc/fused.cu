@@ -93,6 +93,7 @@ struct FusedArgs {
   u32 max_g;     // CTAs that take part at most
   u32 merge;     // both inputs are sorted and consolidated: merge path instead of a sort
   u32 fast;      // fast MSD path allowed (MZGPU_FUSED_FAST=0 turns it off: bisecting, A/B timing)
+  u32 merge_sort_max;  // a merge of at most this many rows runs as a sort of A ++ B (MZGPU_MERGE_SORT_MAX)
 };
 
 __device__ __forceinline__ u64 gtimer() {
@@ -651,7 +652,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& a, const u32 c, cons
   const u64 T = (n + FTILE - 1) / FTILE;
   // A merge of update-batch size runs as a sort of A ++ B: the fast MSD path below has two grid
   // barriers, the merge path five; sortedness only pays beyond the bucket phase's reach.
-  const bool merge = a.merge != 0 && !(a.fast != 0 && n <= MSD_FAST_MAX_ROWS);
+  const bool merge = a.merge != 0 && !(a.fast != 0 && n <= (u64)a.merge_sort_max);
   // CTAs the actual input needs; the rest leave (they hold no barrier slot)
   // MSD bucket count from the row count alone: at most 48 (12 for the 80-byte
   // accumulable rows, whose warp capacity is 64 and whose keys arrive in clumps:
@@ -1563,6 +1564,17 @@ static int fused_fast_mode() {
   return fast;
 }
 
+static u32 fused_merge_sort_max() {
+  static long long v = -1;
+  if (v < 0) {
+    const char* ev = getenv("MZGPU_MERGE_SORT_MAX");
+    v = ev ? atoll(ev) : (long long)MSD_FAST_MAX_ROWS;
+    if (v > (long long)MSD_FAST_MAX_ROWS) v = (long long)MSD_FAST_MAX_ROWS;
+    if (v < 0) v = 0;
+  }
+  return (u32)v;
+}
+
 // Everything of a launch but the launch: buffers, control block, kernel arguments.
 // `slot` < 0: the context's single-job control blocks; otherwise job slot `slot` of a
 // multi-job launch (each slot flips between its own pair of control blocks).
@@ -1651,6 +1663,7 @@ int32_t fused_prepare(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res, int sl
   a.res = res->st.dptr();
   a.kres = res->kst.dptr();
   a.fast = fused_fast_mode() ? 1u : 0u;
+  a.merge_sort_max = fused_merge_sort_max();
   a.dbg = nullptr;
   if (ctx->profile && ctx->d_dbg != nullptr && ctx->dbg_next < MZ_DBG_RECORDS) {
     a.dbg = ctx->d_dbg + 32 * (size_t)ctx->dbg_next++;

@@ -1984,7 +1984,12 @@ extern "C" int32_t mzgpu_join_core_work_until(mzgpu_join* j, uint64_t fuel_rows,
     Lazy4 clen;
     // this slice: rows [w.pos, w.pos + n_probe) of the work item's batch
     const u64 n_total = st == MZGPU_OK ? w.batch->st.v[0] : 0;
-    const u64 n_probe = std::min<u64>(n_total - std::min(n_total, w.pos), MZ_JOIN_SLICE_ROWS);
+    // a caller that gave no deadline and has fuel left for more than one slice is not asking to be
+    // yielded to: it gets slices as large as its fuel allows (up to 16M rows), which take the bulk
+    // sort for the slice's output instead of ten 1M-row fused launches (BASELINE config 2)
+    u64 slice = MZ_JOIN_SLICE_ROWS;
+    if (deadline_ns == 0) slice = std::max<u64>(slice, std::min<u64>(fuel_rows - produced, 16ull << 20));
+    const u64 n_probe = std::min<u64>(n_total - std::min(n_total, w.pos), slice);
     const u64* d_probe = w.batch->rows.as<u64>() + w.pos * 4;
     if (st == MZGPU_OK && n_probe > 0) {
       ProbeParams pp;
