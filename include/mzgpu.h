@@ -562,6 +562,52 @@ int32_t mzgpu_rowkeys_pack(const uint8_t* data, const uint64_t* offsets, uint64_
 /* Inverse: writes `len` bytes (at most 7) to row_bytes_out. */
 int32_t mzgpu_rowkey_unpack(uint64_t key, uint8_t row_bytes_out[7], uint64_t* len_out);
 
+/* --------------------------------------- row L: linear join plans */
+/* LinearJoinPlan (src/compute-types/src/plan/join/linear_join.rs:26-62) as rendered by
+ * LinearJoinSpec::render / differential_join (src/compute/src/render/join/linear_join.rs:230-527):
+ * the running result starts as the source relation, and every stage (a) re-keys it by the stage's
+ * stream_key, keeping the thinned columns as the value ("LinearJoinKeyPreparation", :343-383),
+ * (b) arranges it ("JoinStage": Batcher -> seal -> Spine, :387-398) and (c) joins the arrangement
+ * with the stage's lookup arrangement through mz_join_core with the stage's JoinClosure
+ * (differential_join_inner, :462-527); initial / final closures are per-row maps in front of the
+ * first stage and behind the last one (:243-266, :296-316).  Closures are POD descriptors as
+ * everywhere on this boundary; the key preparation of a stage is one too (key fields = stream_key,
+ * val fields = stream_thinning, evaluated on the running (key, val) row with val2 = 0). */
+#define MZGPU_LINEAR_MAX_STAGES 6
+typedef struct mzgpu_linear_stage_plan {
+  mzgpu_closure stream_key; /* (key, val) of the running result -> (stage key, thinned val) */
+  mzgpu_closure closure;    /* JoinClosure on (key, stream val, lookup val) -> next running row */
+} mzgpu_linear_stage_plan;
+typedef struct mzgpu_linear_join_plan {
+  int32_t has_initial_closure; /* 0: identity */
+  int32_t has_final_closure;   /* 0: identity */
+  uint32_t n_stages;           /* 1 .. MZGPU_LINEAR_MAX_STAGES */
+  uint32_t _pad;
+  mzgpu_closure initial_closure;
+  mzgpu_closure final_closure;
+  mzgpu_linear_stage_plan stages[MZGPU_LINEAR_MAX_STAGES];
+} mzgpu_linear_join_plan;
+typedef struct mzgpu_linear_join mzgpu_linear_join;
+/* lookup_traces[s] = the arrangement of stage s's lookup relation by its lookup_key (owned by the
+ * caller, who inserts the relation's batches and advances its compaction); the operator owns the
+ * "JoinStage" arrangements of the running result.  A plan the descriptors cannot express is
+ * MZGPU_E_UNSUPPORTED / MZGPU_E_INVALID here, at render time. */
+int32_t mzgpu_linear_join_new(mzgpu_ctx* ctx, const mzgpu_linear_join_plan* plan, mzgpu_spine* const* lookup_traces,
+                              mzgpu_linear_join** out);
+void mzgpu_linear_join_free(mzgpu_linear_join* lj);
+/* One activation: the frontier advances to `upper` (every update of this activation is at a time
+ * in [previous upper, upper)).  `source` = the source relation's new updates (R32, may be empty or
+ * NULL), lookup_batches[s] = the batch the caller has just inserted into lookup_traces[s] (NULL: that
+ * relation did not change).  The final collection's new updates are APPENDED to `out` (R32).  Stage
+ * by stage: key preparation, seal of the stage arrangement at `upper`, join_core over the new batches
+ * of both sides (fuel: to completion), result handed to the next stage -- no row count returns to
+ * the host in between beyond what join_core itself reads. */
+int32_t mzgpu_linear_join_step(mzgpu_linear_join* lj, mzgpu_buf* source, mzgpu_batch* const* lookup_batches,
+                               uint64_t upper, mzgpu_buf* out);
+/* The "JoinStage" arrangement of stage s (logical compaction is the caller's call, as for any
+ * arrangement; physical compaction follows the acknowledged frontiers inside the operator). */
+mzgpu_spine* mzgpu_linear_join_stage_trace(mzgpu_linear_join* lj, uint32_t stage);
+
 /* ------------------------------------ f4: the columnar wire format */
 /* `Column<C>` (src/timely-util/src/columnar.rs:54-222) is the container the reference moves
  * update batches in: between workers (`ContainerBytes::{from_bytes, into_bytes}`, :177-222), out

@@ -31,6 +31,7 @@ from .api import (  # noqa: F401
     Correction,
     DeviceRows,
     JoinCore,
+    LinearJoin,
     MzGpuError,
     ReduceAccumulable,
     Spine,

@@ -85,6 +85,25 @@ class Closure(C.Structure):
     ]
 
 
+LINEAR_MAX_STAGES = 6
+
+
+class LinearStagePlan(C.Structure):
+    _fields_ = [("stream_key", Closure), ("closure", Closure)]
+
+
+class LinearJoinPlan(C.Structure):
+    _fields_ = [
+        ("has_initial_closure", C.c_int32),
+        ("has_final_closure", C.c_int32),
+        ("n_stages", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("initial_closure", Closure),
+        ("final_closure", Closure),
+        ("stages", LinearStagePlan * LINEAR_MAX_STAGES),
+    ]
+
+
 class Desc(C.Structure):
     _fields_ = [("lower", C.c_uint64), ("upper", C.c_uint64), ("since", C.c_uint64)]
 
@@ -209,6 +228,10 @@ SIGNATURES = {
     "mzgpu_builder_done": (i32, [vp, Desc, PV]),
     "mzgpu_spine_size": (i32, [vp, vp]),
     "mzgpu_join_core_work_until": (i32, [vp, u64, u64, vp, PI32]),
+    "mzgpu_linear_join_new": (i32, [vp, C.POINTER(LinearJoinPlan), PV, PV]),
+    "mzgpu_linear_join_free": (None, [vp]),
+    "mzgpu_linear_join_step": (i32, [vp, vp, PV, u64, vp]),
+    "mzgpu_linear_join_stage_trace": (vp, [vp, u32]),
     "mzgpu_column_length_in_words": (u64, [i32, u64, u64, u64]),
     "mzgpu_column_at_capacity": (i32, [u64]),
     "mzgpu_column_ship_rows": (u64, [i32]),

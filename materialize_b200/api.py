@@ -444,6 +444,48 @@ class JoinCore:
             self.h = None
 
 
+class LinearJoin:
+    """A LinearJoinPlan (src/compute-types/src/plan/join/linear_join.rs:26-62) rendered over the operators as
+    src/compute/src/render/join/linear_join.rs:230-527 renders it.  stages: [(lookup Spine, stream_key closure,
+    join closure)]; the source relation arrives as update rows, each lookup relation as the batch the caller has
+    just inserted into its arrangement."""
+
+    def __init__(self, ctx, stages, initial_closure=None, final_closure=None):
+        self.ctx = ctx
+        self._keep = [st[0] for st in stages]
+        plan = F.LinearJoinPlan()
+        plan.n_stages = len(stages)
+        if initial_closure is not None:
+            plan.has_initial_closure, plan.initial_closure = 1, initial_closure
+        if final_closure is not None:
+            plan.has_final_closure, plan.final_closure = 1, final_closure
+        for i, (_, stream_key, closure) in enumerate(stages[: F.LINEAR_MAX_STAGES]):
+            plan.stages[i].stream_key = stream_key
+            plan.stages[i].closure = closure
+        traces = (C.c_void_p * max(1, len(stages)))(*[st[0].h for st in stages])
+        h = C.c_void_p()
+        ctx.check(F.lib.mzgpu_linear_join_new(ctx.h, C.byref(plan), traces, C.byref(h)))
+        self.h, self.n = h, len(stages)
+        self.out = DeviceRows(ctx, 32)
+
+    def step(self, source_rows, lookup_batches, upper):
+        """One activation; returns the final collection's new updates (downloaded)."""
+        src = DeviceRows(self.ctx, 32).upload(source_rows) if source_rows is not None and len(source_rows) else None
+        lb = (C.c_void_p * self.n)(*[b.h if b is not None else None for b in lookup_batches])
+        self.out.clear()
+        self.ctx.check(F.lib.mzgpu_linear_join_step(self.h, src.h if src is not None else None, lb, upper, self.out.h))
+        return self.out.download()
+
+    def stage_trace_layers(self, stage):
+        """Raw handle of the stage's "JoinStage" arrangement (owned by the operator)."""
+        return F.lib.mzgpu_linear_join_stage_trace(self.h, stage)
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            F.lib.mzgpu_linear_join_free(self.h)
+            self.h = None
+
+
 def half_join(ctx, stream, trace, cmp_mode, closure=None, consolidate_output=True):
     stream = np.ascontiguousarray(stream)
     out = DeviceRows(ctx, 32)

@@ -2723,6 +2723,121 @@ extern "C" uint64_t mzgpu_correction_len(mzgpu_correction* c) {
   return c->td.len.v[c->td.word];
 }
 
+// ====================================================== row L: linear join
+// LinearJoinPlan rendered as linear_join.rs:230-527 does (see include/mzgpu.h): per stage a key
+// preparation map, the "JoinStage" arrangement of the running result, and mz_join_core against
+// the lookup arrangement.
+struct mzgpu_linear_join {
+  mzgpu_ctx* ctx = nullptr;
+  mzgpu_linear_join_plan plan;
+  uint32_t n = 0;
+  mzgpu_spine* lookup[MZGPU_LINEAR_MAX_STAGES] = {};
+  mzgpu_batcher* batcher[MZGPU_LINEAR_MAX_STAGES] = {};  // "JoinStage" arrange operators
+  mzgpu_spine* stage[MZGPU_LINEAR_MAX_STAGES] = {};
+  mzgpu_join* join[MZGPU_LINEAR_MAX_STAGES] = {};
+  mzgpu_buf* keyed = nullptr;    // key-prepared rows of the stage being fed
+  mzgpu_buf* running = nullptr;  // a stage's join output = the next stage's input
+  mzgpu_buf* tmp = nullptr;
+  u64 upper = 0;
+  ~mzgpu_linear_join() {
+    for (uint32_t s = 0; s < MZGPU_LINEAR_MAX_STAGES; ++s) {
+      delete join[s];
+      delete stage[s];
+      delete batcher[s];
+    }
+    delete keyed;
+    delete running;
+    delete tmp;
+  }
+};
+extern "C" int32_t mzgpu_linear_join_new(mzgpu_ctx* ctx, const mzgpu_linear_join_plan* plan,
+                                         mzgpu_spine* const* lookup_traces, mzgpu_linear_join** out) {
+  MZ_CHECK_CTX(ctx);
+  if (plan == nullptr || lookup_traces == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  if (plan->n_stages == 0 || plan->n_stages > MZGPU_LINEAR_MAX_STAGES) {
+    MZ_SET_ERR(ctx, "linear join: %u stages (1..%d supported)", plan->n_stages, MZGPU_LINEAR_MAX_STAGES);
+    return MZGPU_E_UNSUPPORTED;
+  }
+  if (plan->has_initial_closure) MZ_TRY(validate_closure(ctx, &plan->initial_closure));
+  if (plan->has_final_closure) MZ_TRY(validate_closure(ctx, &plan->final_closure));
+  for (uint32_t s = 0; s < plan->n_stages; ++s) {
+    if (lookup_traces[s] == nullptr || lookup_traces[s]->rb != 32 || lookup_traces[s]->ctx != ctx) return MZGPU_E_INVALID;
+    MZ_TRY(validate_closure(ctx, &plan->stages[s].stream_key));
+    MZ_TRY(validate_closure(ctx, &plan->stages[s].closure));
+  }
+  std::unique_ptr<mzgpu_linear_join> lj(new mzgpu_linear_join());
+  lj->ctx = ctx;
+  lj->plan = *plan;
+  lj->n = plan->n_stages;
+  for (mzgpu_buf** b : {&lj->keyed, &lj->running, &lj->tmp}) MZ_TRY(mzgpu_buf_new(ctx, 32, b));
+  for (uint32_t s = 0; s < lj->n; ++s) {
+    lj->lookup[s] = lookup_traces[s];
+    MZ_TRY(mzgpu_batcher_new(ctx, 32, &lj->batcher[s]));
+    MZ_TRY(mzgpu_spine_new(ctx, 32, 1, &lj->stage[s]));
+    // join_core(stage arrangement, lookup arrangement): what the lookup trace already holds is
+    // queued against the (empty) stage arrangement by the operator's pre-load (mz_join_core.rs:109-190)
+    MZ_TRY(mzgpu_join_new(ctx, lj->stage[s], lj->lookup[s], &plan->stages[s].closure, &lj->join[s]));
+  }
+  *out = lj.release();
+  return MZGPU_OK;
+}
+extern "C" void mzgpu_linear_join_free(mzgpu_linear_join* lj) { delete lj; }
+extern "C" mzgpu_spine* mzgpu_linear_join_stage_trace(mzgpu_linear_join* lj, uint32_t stage) {
+  return lj != nullptr && stage < lj->n ? lj->stage[stage] : nullptr;
+}
+extern "C" int32_t mzgpu_linear_join_step(mzgpu_linear_join* lj, mzgpu_buf* source,
+                                          mzgpu_batch* const* lookup_batches, uint64_t upper, mzgpu_buf* out) {
+  if (lj == nullptr || out == nullptr || out->rb != 32 || (source != nullptr && source->rb != 32) || source == out)
+    return MZGPU_E_INVALID;
+  mzgpu_ctx* ctx = lj->ctx;
+  MZ_CHECK_CTX(ctx);
+  if (upper <= lj->upper) {
+    MZ_SET_ERR(ctx, "linear join: frontier %llu does not advance past %llu", (unsigned long long)upper,
+               (unsigned long long)lj->upper);
+    return MZGPU_E_FRONTIER;
+  }
+  const u64 cap_time = lj->upper;  // the capability the join's outputs are produced under
+  // the running result entering stage 0: the source updates behind the initial closure
+  MZ_TRY(mzgpu_buf_clear(lj->running));
+  if (source != nullptr && source->ub) {
+    if (lj->plan.has_initial_closure)
+      MZ_TRY(map_rows_into(ctx, source->mem.as<u64>(), buf_dlen(source), source->ub, &lj->plan.initial_closure,
+                           MZGPU_FRONTIER_EMPTY, lj->running));
+    else
+      MZ_TRY(buf_append_dev(lj->running, source->mem.p, buf_dlen(source), source->ub));
+  }
+  for (uint32_t s = 0; s < lj->n; ++s) {
+    // (a) LinearJoinKeyPreparation, (b) the JoinStage arrangement sealed at the new frontier
+    MZ_TRY(mzgpu_buf_clear(lj->keyed));
+    if (lj->running->ub)
+      MZ_TRY(map_rows_into(ctx, lj->running->mem.as<u64>(), buf_dlen(lj->running), lj->running->ub,
+                           &lj->plan.stages[s].stream_key, MZGPU_FRONTIER_EMPTY, lj->keyed));
+    MZ_TRY(mzgpu_batcher_push_buf(lj->batcher[s], lj->keyed));
+    mzgpu_batch* sb = nullptr;
+    MZ_TRY(mzgpu_batcher_seal(lj->batcher[s], upper, &sb, nullptr));
+    int32_t st = mzgpu_spine_insert(lj->stage[s], sb);
+    // (c) mz_join_core over what is new on either side
+    if (st == MZGPU_OK) st = mzgpu_join_core_push(lj->join[s], 0, sb, cap_time);
+    mzgpu_batch_release(sb);
+    MZ_TRY(st);
+    if (lookup_batches != nullptr && lookup_batches[s] != nullptr)
+      MZ_TRY(mzgpu_join_core_push(lj->join[s], 1, lookup_batches[s], cap_time));
+    MZ_TRY(mzgpu_buf_clear(lj->tmp));
+    int32_t done = 0;
+    while (!done) MZ_TRY(mzgpu_join_core_work(lj->join[s], ~0ull, lj->tmp, &done));
+    std::swap(lj->running, lj->tmp);
+  }
+  if (lj->running->ub) {
+    if (lj->plan.has_final_closure)
+      MZ_TRY(map_rows_into(ctx, lj->running->mem.as<u64>(), buf_dlen(lj->running), lj->running->ub,
+                           &lj->plan.final_closure, MZGPU_FRONTIER_EMPTY, out));
+    else
+      MZ_TRY(buf_append_dev(out, lj->running->mem.p, buf_dlen(lj->running), lj->running->ub));
+  }
+  lj->upper = upper;
+  return MZGPU_OK;
+}
+
 // ================================================ f4: columnar wire format
 // Host side of column.cu: index arithmetic of `columnar::bytes::indexed`, the ship heuristic, and the
 // entry points that move serialized containers in and out of row buffers.

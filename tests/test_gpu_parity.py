@@ -661,6 +661,102 @@ def test_linear_join_two_stages_matches_oracle_and_bruteforce(mz, ctx, oracle):
     assert [tuple(r) for r in final.tolist()] == want
 
 
+def test_linear_join_plan_operator_matches_oracle_composition(mz, ctx, oracle):
+    """Row L through the boundary's plan descriptor: `mzgpu_linear_join_{new, step}` renders a two-stage
+    LinearJoinPlan (source A; stage 0: lookup B by k1, closure re-keys by k2; stage 1: lookup C by k2; a final
+    closure that filters and projects) itself -- key preparation, the "JoinStage" arrangements, mz_join_core per
+    stage (src/compute/src/render/join/linear_join.rs:230-527) -- and produces, activation by activation, the
+    collection the same plan composed by hand from the oracle's operators produces; accumulated, that is the
+    brute-force three-way join behind the final closure."""
+    rng = np.random.default_rng(34)
+    ident = dict(key_fields=[(0, 0, 64, 0)], val_fields=[(1, 0, 64, 0)])
+    cl1 = dict(key_fields=[(2, 20, 10, 0)], val_fields=[(1, 0, 20, 0), (2, 0, 20, 20)])  # key' = k2, val' = a | b << 20
+    cl2 = dict(key_fields=[(0, 0, 10, 0)], val_fields=[(1, 0, 40, 0), (2, 0, 20, 40)])  # val'' = a | b << 20 | c << 40
+    fin = dict(key_fields=[(0, 0, 10, 0)], val_fields=[(1, 20, 40, 0)], filters=[(1, 0, 20, "lt", 40)])  # a < 40; keep b, c
+    gB, gC = mz.Spine(ctx, 32), mz.Spine(ctx, 32)
+    lj = mz.LinearJoin(ctx, [(gB, mz.make_closure(**ident), mz.make_closure(**cl1)), (gC, mz.make_closure(**ident), mz.make_closure(**cl2))],
+                       final_closure=mz.make_closure(**fin))
+    o = dict(A=oracle.Spine(32, 1, True), B=oracle.Spine(32, 1, True), S=oracle.Spine(32, 1, True), C=oracle.Spine(32, 1, True))
+    oj1 = oracle.Join(o["A"], o["B"], oracle.make_closure(**cl1))
+    oj2 = oracle.Join(o["S"], o["C"], oracle.make_closure(**cl2))
+    ostage = oracle.Batcher(32)
+    acc = dict(A=[], B=[], C=[])
+    o1_seen = o2_seen = 0
+    got_all = []
+    for t in range(7):
+        ins = {}
+        for name, (kh, n) in dict(A=(60, 500), B=(60, 400), C=(40, 300)).items():
+            x = np.zeros(n if not (name == "C" and t == 3) else 0, dtype=oracle.R32)  # C is silent at t = 3
+            x["key"] = rng.integers(0, kh, size=len(x), dtype=np.uint64)
+            x["val"] = rng.integers(0, 50, size=len(x), dtype=np.uint64)
+            if name == "B":
+                x["val"] |= rng.integers(0, 40, size=len(x), dtype=np.uint64) << np.uint64(20)
+            x["time"] = t
+            x["diff"] = rng.integers(-1, 3, size=len(x))
+            if t >= 2 and len(acc[name][t - 2]):
+                old = acc[name][t - 2][:100].copy()
+                old["time"] = t
+                old["diff"] = -old["diff"]
+                x = np.concatenate([x, old])
+            ins[name] = x
+            acc[name].append(x)
+        # the oracle's composition of the same plan
+        for side, name in enumerate(("A", "B")):
+            ob = oracle.Batch.build(ins[name], t, t + 1)
+            o[name].insert(ob)
+            oj1.push(side, ob, t)
+        oj1.work()
+        orr = oj1.results()
+        o_new, o1_seen = orr[o1_seen:], len(orr)
+        ostage.push(o_new)
+        osb = ostage.seal(t + 1)
+        o["S"].insert(osb)
+        oj2.push(0, osb, t)
+        oc = oracle.Batch.build(ins["C"], t, t + 1)
+        o["C"].insert(oc)
+        oj2.push(1, oc, t)
+        oj2.work()
+        or2 = oj2.results()
+        want = oracle.consolidate(oracle.map_rows(or2[o2_seen:], oracle.make_closure(**fin)))
+        o2_seen = len(or2)
+        # the operator: the lookup batches go into the caller's arrangements, then one activation
+        gb, gc = mz.Batch.build(ctx, ins["B"], t, t + 1), mz.Batch.build(ctx, ins["C"], t, t + 1)
+        gB.insert(gb)
+        gC.insert(gc)
+        got = lj.step(ins["A"], [gb, gc], t + 1)
+        same(oracle.consolidate(got), want)
+        got_all.append(got)
+        for sp in o.values():
+            sp.set_physical_compaction(t + 1)
+    final = np.concatenate(got_all)
+    final["time"] = 0
+    final = oracle.consolidate(final)
+    A, B, Cc = (np.concatenate(acc[n]) for n in ("A", "B", "C"))
+    for x in (A, B, Cc):
+        x["time"] = 0
+    A, B, Cc = oracle.consolidate(A), oracle.consolidate(B), oracle.consolidate(Cc)
+    by_b, by_c = {}, {}
+    for k, v, _, d in B.tolist():
+        by_b.setdefault(k, []).append((v >> 20, v & 0xFFFFF, d))
+    for k, v, _, d in Cc.tolist():
+        by_c.setdefault(k, []).append((v, d))
+    want = {}
+    for k1, a, _, da in A.tolist():
+        if a >= 40:
+            continue
+        for k2, b, db in by_b.get(k1, ()):
+            for c, dc in by_c.get(k2, ()):
+                key = (k2, b | (c << 20))
+                want[key] = want.get(key, 0) + da * db * dc
+    want = sorted((k, v, 0, d) for (k, v), d in want.items() if d != 0)
+    assert [tuple(r) for r in final.tolist()] == want
+    # plans the descriptor cannot hold are refused at render time
+    with pytest.raises(mz.MzGpuError):
+        mz.LinearJoin(ctx, [])
+    with pytest.raises(mz.MzGpuError):
+        mz.LinearJoin(ctx, [(gB, mz.make_closure(**ident), mz.make_closure(**cl1))] * 7)
+
+
 # ---------------------------------------------------------------- a10
 @pytest.mark.parametrize("cmp_mode", [0, 1])
 def test_half_join_matches_oracle(mz, ctx, oracle, cmp_mode):
