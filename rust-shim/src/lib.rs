@@ -8,6 +8,7 @@ pub mod batch;
 pub mod batcher;
 pub mod builder;
 pub mod column;
+pub mod linear_join;
 pub mod sys;
 pub mod trace;
 

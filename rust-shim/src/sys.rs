@@ -96,6 +96,21 @@ extern "C" {
     pub fn mzgpu_batch_walk_column(batch: *mut Batch, key: *const u64, first: u64, fuel: u64, layout: i32, words: *mut u64,
                                    cap_words: u64, mem: i32, n_words: *mut u64, n_rows: *mut u64) -> i32;
     pub fn mzgpu_batcher_push_buf(b: *mut Batcher, rows: *mut Buf) -> i32;
+    pub fn mzgpu_buf_upload(b: *mut Buf, rows: *const c_void, n: u64, mem: i32) -> i32;
+    // row L: linear join plans
+    pub fn mzgpu_linear_join_new(ctx: *mut Ctx, plan: *const LinearJoinPlan, lookup_traces: *const *mut Spine,
+                                 out: *mut *mut LinearJoin) -> i32;
+    pub fn mzgpu_linear_join_free(lj: *mut LinearJoin);
+    pub fn mzgpu_linear_join_step(lj: *mut LinearJoin, source: *mut Buf, lookup_batches: *const *mut Batch, upper: u64,
+                                  out: *mut Buf) -> i32;
+    pub fn mzgpu_linear_join_stage_trace(lj: *mut LinearJoin, stage: u32) -> *mut Spine;
+}
+pub enum LinearJoin {}
+pub const LINEAR_MAX_STAGES: usize = 6;
+#[repr(C)] pub struct LinearStagePlan { pub stream_key: Closure, pub closure: Closure }
+#[repr(C)] pub struct LinearJoinPlan {
+    pub has_initial_closure: i32, pub has_final_closure: i32, pub n_stages: u32, pub _pad: u32,
+    pub initial_closure: Closure, pub final_closure: Closure, pub stages: [LinearStagePlan; LINEAR_MAX_STAGES],
 }
 pub const COLUMN_U64X4: i32 = 0;
 pub const COLUMN_U64X2: i32 = 1;

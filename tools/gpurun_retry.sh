@@ -1,6 +1,6 @@
 #!/bin/bash
 # gpurun with retries while the pod answers "transient" (busy); usage: gpurun_retry.sh [gpurun args] -- 'cmd'
-for attempt in $(seq 1 30); do
+for attempt in $(seq 1 80); do
   out=$(/usr/local/graft/bin/gpurun "$@" 2>&1)
   if echo "$out" | grep -q "status=transient"; then
     wait=$(echo "$out" | grep -o "retry in [0-9]*s" | grep -o "[0-9]*")
