@@ -456,6 +456,7 @@ def run_ours(args, rank, world, local_rank):
     e0.record(ext)
     rows_timed = 0
     host_t0 = time.perf_counter()
+    ht0 = ctx.host_times()
     for i in range(n_timed):
         # the output corrections of every timed step are appended (device to device, no read-back)
         # to `kept` and compared with the CPU oracle's after the region
@@ -463,7 +464,9 @@ def run_ours(args, rank, world, local_rank):
         step_ev[i].record(ext)
         rows_timed += staged_rows[b]
         b += 1
-    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / n_timed  # host time to ENQUEUE a step (no wait inside)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / n_timed  # host time per step inside the loop ...
+    ht1 = ctx.host_times()
+    host_wait_ms = (ht1["wait_ns"] - ht0["wait_ns"]) / 1e6 / n_timed  # ... of which: waiting for the device
     e1.record(ext)
     try:
         clocks.sample_now()  # the GPU is still working through the queued steps
@@ -604,7 +607,8 @@ def run_ours(args, rank, world, local_rank):
         "warmup": n_warm,
         "ms_per_step": ms / n_timed,
         "per_step_ms": per_step,
-        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "host_ms_per_step": {"loop": host_enqueue_ms, "waiting_for_device": host_wait_ms, "work": host_enqueue_ms - host_wait_ms,
+                             "allocations": (ht1["allocs"] - ht0["allocs"]) / n_timed},
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,

@@ -259,6 +259,10 @@ typedef struct mzgpu_stats {
   uint64_t host_syncs; /* times the host waited for the device */
 } mzgpu_stats;
 int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out);
+/* Host-side time accounting since the ctx was created: out[0] = ns spent WAITING for the device
+ * (the host_syncs above), out[1] = ns spent inside the allocator, out[2] = allocations, out[3] =
+ * bytes allocated.  The measurement harness uses it to tell host work from host waiting. */
+int32_t mzgpu_ctx_host_times(mzgpu_ctx* ctx, uint64_t out[4]);
 /* Per-kernel device timing (CUDA events on the ctx stream around every launch).
  * Off by default; the measurement harness switches it on for a profiling pass
  * (it adds two event records per launch).  mzgpu_profile_report writes one line

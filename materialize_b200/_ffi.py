@@ -228,6 +228,7 @@ SIGNATURES = {
     "mzgpu_builder_done": (i32, [vp, Desc, PV]),
     "mzgpu_spine_size": (i32, [vp, vp]),
     "mzgpu_join_core_work_until": (i32, [vp, u64, u64, vp, PI32]),
+    "mzgpu_ctx_host_times": (i32, [vp, PU64]),
     "mzgpu_linear_join_new": (i32, [vp, C.POINTER(LinearJoinPlan), PV, PV]),
     "mzgpu_linear_join_free": (None, [vp]),
     "mzgpu_linear_join_step": (i32, [vp, vp, PV, u64, vp]),

@@ -101,6 +101,12 @@ class Context:
         """Bracket every kernel launch with CUDA events on the ctx stream."""
         self.check(F.lib.mzgpu_profile_enable(self.h, 1 if on else 0))
 
+    def host_times(self):
+        """{wait_ns, alloc_ns, allocs, alloc_bytes}: host time spent waiting for the device / in the allocator."""
+        out = (C.c_uint64 * 4)()
+        self.check(F.lib.mzgpu_ctx_host_times(self.h, out))
+        return {"wait_ns": out[0], "alloc_ns": out[1], "allocs": out[2], "alloc_bytes": out[3]}
+
     def profile_report(self):
         """{kernel: {launches, ms, bytes}} since the last report."""
         buf = C.create_string_buffer(1 << 20)

@@ -1564,11 +1564,15 @@ static int fused_fast_mode() {
   return fast;
 }
 
+// Measured (tools/merge_bench.py, profiles/r02_merge_bench_*.log): two sorted 20K / 80K-row batches merge
+// faster as a sort of A ++ B on the fast MSD path (44 / 59 us vs 52 / 65 us), from 2 x 160K rows on the
+// merge-path form wins (79 vs 93 us; 161 vs 245 us at 2 x 500K).
+constexpr long long MERGE_SORT_MAX_DEFAULT = 1ll << 18;
 static u32 fused_merge_sort_max() {
   static long long v = -1;
   if (v < 0) {
     const char* ev = getenv("MZGPU_MERGE_SORT_MAX");
-    v = ev ? atoll(ev) : (long long)MSD_FAST_MAX_ROWS;
+    v = ev ? atoll(ev) : (long long)MERGE_SORT_MAX_DEFAULT;
     if (v > (long long)MSD_FAST_MAX_ROWS) v = (long long)MSD_FAST_MAX_ROWS;
     if (v < 0) v = 0;
   }

@@ -248,6 +248,15 @@ extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   return MZGPU_OK;
 }
 
+extern "C" int32_t mzgpu_ctx_host_times(mzgpu_ctx* ctx, uint64_t out[4]) {
+  if (ctx == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  out[0] = ctx->ns_sync;
+  out[1] = ctx->ns_alloc;
+  out[2] = ctx->n_alloc;
+  out[3] = ctx->bytes_alloc;
+  return MZGPU_OK;
+}
+
 extern "C" int32_t mzgpu_profile_enable(mzgpu_ctx* ctx, int32_t on) {
   MZ_CHECK_CTX(ctx);
   ctx->profile = on != 0;

@@ -457,7 +457,7 @@ struct ProbeChain {
 };
 struct ProbeMany {
   u32 n_chains;
-  u32 steal;  // a CTA whose chain is exhausted moves on to the next chain (MZGPU_PROBE_STEAL=0: A/B, bisecting)
+  u32 ctas[PROBE_MANY_MAX];  // CTAs of the launch that work on chain c (blockIdx.y = c, blockIdx.x < ctas[c])
   ProbeChain chain[PROBE_MANY_MAX];
   ProbeJobDev job[PROBE_MANY_MAX];
 };
@@ -467,49 +467,44 @@ template <int OUT_NW>
 __global__ void __launch_bounds__(PT, 3) k_probe_chains(const __grid_constant__ ProbeMany m,
                                                      u64* __restrict__ status) {
   __shared__ ProbeSmem S;
-  // A CTA starts on chain blockIdx.y and, when that chain's tickets run out, moves on to the next
-  // one: the chains of a launch differ in size by an order of magnitude (the lineitem path of a Q3
-  // step carries four times the rows of the orders path, the customer path none), and an equal split
-  // of the resident CTAs left the longest chain running four tiles deep on a third of the machine
-  // (profiles/r02: 44-55 us per launch at 20 % of the warp slots).  Tiles of a chain are still handed
-  // out in ticket order to CTAs that are all resident, so the look-back cannot deadlock.
-  const u32 rounds = m.steal ? m.n_chains : 1u;
-#pragma unroll 1
-  for (u32 r = 0; r < rounds; ++r) {
-    u32 ci = blockIdx.y + r;
-    if (ci >= m.n_chains) ci -= m.n_chains;
-    const ProbeChain& ch = m.chain[ci];
-    u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
-    u32 trj[PROBE_MANY_MAX];
-    tiles_before[0] = 0;
+  // The chains of a launch differ in size by an order of magnitude (the lineitem path of a Q3 step
+  // carries four times the rows of the orders path, the customer path none): the resident CTAs are
+  // shared out in proportion to the chains' tile counts (host bounds), not equally -- an equal split
+  // left the longest chain running four tiles deep on a third of the machine (profiles/r02: 44-55 us
+  // per launch at 20 % of the warp slots).  A chain's tiles are handed out by ticket to whichever of
+  // its CTAs is free, so the look-back never waits for a CTA that has not started.
+  if (blockIdx.x >= m.ctas[blockIdx.y]) return;
+  const ProbeChain& ch = m.chain[blockIdx.y];
+  u64 nj[PROBE_MANY_MAX], tiles_before[PROBE_MANY_MAX + 1];
+  u32 trj[PROBE_MANY_MAX];
+  tiles_before[0] = 0;
 #pragma unroll
-    for (int q = 0; q < PROBE_MANY_MAX; ++q) {
-      nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
-      trj[q] = (u32)q < ch.count ? m.job[ch.first + q].tile_rows : 256u;
-      tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
+  for (int q = 0; q < PROBE_MANY_MAX; ++q) {
+    nj[q] = (u32)q < ch.count ? dlen_get(m.job[ch.first + q].dn) : 0;
+    trj[q] = (u32)q < ch.count ? m.job[ch.first + q].tile_rows : 256u;
+    tiles_before[q + 1] = tiles_before[q] + (nj[q] + trj[q] - 1) / trj[q];
+  }
+  const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
+  const u64 base0 = dlen_get(ch.out_base);
+  while (true) {
+    const u32 tile = lb_next_tile(ch.lb, &S.tile);
+    if ((u64)tile >= n_tiles) {
+      if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
+      break;
     }
-    const u64 n_tiles = tiles_before[PROBE_MANY_MAX];
-    const u64 base0 = dlen_get(ch.out_base);
-    while (true) {
-      const u32 tile = lb_next_tile(ch.lb, &S.tile);
-      if ((u64)tile >= n_tiles) {
-        if (n_tiles == 0 && tile == 0 && threadIdx.x == 0) *ch.out_len = base0;
-        break;
-      }
-      u32 q = 0;
-      while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
-      const ProbeJobDev& J = m.job[ch.first + q];
-      ProbePre pre;
-      pre.has_pre = J.has_pre;
-      pre.pre_has_closure = J.pre_has_closure;
-      pre.skip_time = J.skip_time;
-      pre.pre = &J.pre;
-      u64 excl;
-      u32 total;
-      probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q] / (PT / 32), J.tv, J.pp,
-                         pre, ch.lb, tile, ch.out, base0, ch.out_cap, status, &excl, &total);
-      if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
-    }
+    u32 q = 0;
+    while (q + 1 < ch.count && (u64)tile >= tiles_before[q + 1]) ++q;
+    const ProbeJobDev& J = m.job[ch.first + q];
+    ProbePre pre;
+    pre.has_pre = J.has_pre;
+    pre.pre_has_closure = J.pre_has_closure;
+    pre.skip_time = J.skip_time;
+    pre.pre = &J.pre;
+    u64 excl;
+    u32 total;
+    probe_tile<OUT_NW>(S, J.stream, nj[q], (u64)(tile - tiles_before[q]) * trj[q], trj[q] / (PT / 32), J.tv, J.pp, pre,
+                       ch.lb, tile, ch.out, base0, ch.out_cap, status, &excl, &total);
+    if ((u64)tile == n_tiles - 1 && threadIdx.x == 0) *ch.out_len = base0 + excl + total;
   }
 }
 
@@ -782,7 +777,7 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
   static thread_local ProbeMany m;  // large: kept off the stack
   memset(&m, 0, sizeof(m));
   const bool closure = jobs[0].pp->has_closure != 0;
-  u64 lb_at = 0, max_grid = 1, bytes = 0, total_tiles = 0, max_chain_tiles = 0;
+  u64 lb_at = 0, max_grid = 1, bytes = 0, total_tiles = 0, chain_tiles[PROBE_MANY_MAX] = {};
   int nc = 0;
   for (int j = 0; j < k; ++j) {
     if ((jobs[j].pp->has_closure != 0) != closure) {
@@ -821,19 +816,20 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
     MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
     lb_at += tiles;
     total_tiles += tiles;
-    if (tiles > max_chain_tiles) max_chain_tiles = tiles;
+    chain_tiles[c] = tiles;
   }
-  // all chains of a launch run side by side; a CTA whose chain is exhausted moves on to the next
-  // one, so the grid only has to cover the machine (or the work, if that is less)
-  static const bool steal = getenv("MZGPU_PROBE_STEAL") == nullptr || atoi(getenv("MZGPU_PROBE_STEAL")) != 0;
-  m.steal = steal ? 1u : 0u;
-  max_grid = ((u64)ctx->num_sms * 3) / (u64)nc;
-  if (steal) {
-    if (max_grid * (u64)nc > total_tiles) max_grid = (total_tiles + nc - 1) / (u64)nc;
-  } else if (max_grid > max_chain_tiles) {
-    max_grid = max_chain_tiles;  // chains keep to their own CTAs: the grid covers the longest chain
+  // all chains of a launch run side by side: the resident CTAs (3 per SM) are shared out in proportion
+  // to the chains' tiles (MZGPU_PROBE_SHARE=0: equally, the round-1 split, for A/B runs)
+  static const bool prop = getenv("MZGPU_PROBE_SHARE") == nullptr || atoi(getenv("MZGPU_PROBE_SHARE")) != 0;
+  const u64 resident = (u64)ctx->num_sms * 3;
+  max_grid = 1;
+  for (int c = 0; c < nc; ++c) {
+    u64 g = prop && total_tiles > 0 ? (resident * chain_tiles[c] + total_tiles - 1) / total_tiles : (resident + nc - 1) / (u64)nc;
+    if (g > chain_tiles[c]) g = chain_tiles[c];  // one CTA per tile at most
+    if (g == 0) g = 1;                            // (an empty chain still has its length word to write)
+    m.ctas[c] = (u32)g;
+    if (g > max_grid) max_grid = g;
   }
-  if (max_grid == 0) max_grid = 1;
   MZ_BYTES(ctx, bytes);
   if (closure) {
     MZ_LAUNCH(ctx, (k_probe_chains<4>), dim3((unsigned)max_grid, (unsigned)nc), PT, 0, m, ctx->d_status);

@@ -12,7 +12,7 @@ line() {
 import sys, json
 try:
     d = json.loads(sys.stdin.read().strip().split('\n')[-1])
-    print('$1', round(d['value'] / 1e6, 1), 'M rows/s', round(d['ms_per_step'], 4), 'ms/step', d.get('per_step_ms'), 'host_enqueue', d.get('host_enqueue_ms_per_step'),
+    print('$1', round(d['value'] / 1e6, 1), 'M rows/s', round(d['ms_per_step'], 4), 'ms/step', d.get('per_step_ms'), 'host_enqueue', d.get('host_ms_per_step'),
           'e2e', round(d['e2e']['value'] / 1e6, 1), 'launches', d.get('gpu_launches'))
     for t in d['roofline']['top_kernels'][:4]: print('    ', t)
 except Exception as e:
@@ -20,14 +20,10 @@ except Exception as e:
 }
 echo "== bench (default switches)"
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> $O/${TAG}_bench.err | tee $O/${TAG}_bench.json | line "default      "
-echo "== bench, chains keep to their own CTAs"
-MZGPU_PROBE_STEAL=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> /dev/null | line "steal=0      "
-echo "== merges: where a merge stops being run as a sort"
-for v in 1048576 262144 0; do
-  MZGPU_MERGE_SORT_MAX=$v timeout 120 python tools/merge_bench.py 2>&1 | tail -9 | tee $O/${TAG}_merge_bench_$v.log
-done
-echo "== bench with merges on the merge path from 256K rows"
-MZGPU_MERGE_SORT_MAX=262144 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> /dev/null | line "merge>=256K  "
+echo "== bench, equal CTA shares per chain"
+MZGPU_PROBE_SHARE=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> /dev/null | line "share=0      "
+echo "== bench with every merge up to 1M rows run as a sort"
+MZGPU_MERGE_SORT_MAX=1048576 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2> /dev/null | line "sort<=1M     "
 echo "== bulk regimes"
 timeout 200 python tools/diag_bulk.py cfg4 > $O/${TAG}_diag_cfg4.log 2>&1; grep -E "rep|groups|big blocks" $O/${TAG}_diag_cfg4.log | tail -12
 timeout 200 python tools/diag_bulk.py cfg2 10000000 > $O/${TAG}_diag_cfg2.log 2>&1; grep -E "rep . (seals|work)|out rows" $O/${TAG}_diag_cfg2.log | tail -9

@@ -11,7 +11,7 @@ python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench.json 2
 python - <<PY
 import json
 d = json.loads(open("$O/${TAG}_bench.json").read().strip().split("\n")[-1])
-print("value", round(d["value"] / 1e6, 1), "M rows/s", round(d["ms_per_step"], 4), "ms/step", d.get("per_step_ms"), "host_enqueue", d.get("host_enqueue_ms_per_step"), "e2e", round(d["e2e"]["value"] / 1e6, 1), "parity", (d.get("parity") or {}).get("ok"))
+print("value", round(d["value"] / 1e6, 1), "M rows/s", round(d["ms_per_step"], 4), "ms/step", d.get("per_step_ms"), "host_enqueue", d.get("host_ms_per_step"), "e2e", round(d["e2e"]["value"] / 1e6, 1), "parity", (d.get("parity") or {}).get("ok"))
 for t in d["roofline"]["top_kernels"][:6]:
     print("  ", t)
 PY
