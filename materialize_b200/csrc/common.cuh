@@ -736,6 +736,10 @@ int32_t mz_fused_consolidate(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out)
 // k independent jobs of one row width in one cooperative launch (k <= MZ_FUSED_MANY_MAX)
 #define MZ_FUSED_MANY_MAX 4
 int32_t mz_fused_consolidate_many(mzgpu_ctx* ctx, int k, const FusedJob* jobs, FusedOut* outs);
+// mergepath.cu: two sorted, consolidated R32 arrays merged (times advanced to `since`), consolidated and
+// indexed by three ordinary stream-ordered launches; results as the fused kernel's merge leaves them
+int32_t mz_merge_r32_async(mzgpu_ctx* ctx, const void* d_a, DLen na, const void* d_b, DLen nb, u64 cap, u64 since,
+                           FusedOut* res);
 // prepare now, launch with the other deferred jobs at mz_fused_flush (host.cu: mz_flush_deferred)
 int32_t mz_fused_defer(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* out);
 int32_t mz_fused_flush(mzgpu_ctx* ctx);

@@ -988,6 +988,15 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
   // advance_by of an empty antichain leaves every time alone; the kernels compute
   // max(time, since), for which 0 is the no-op
   const u64 adv = since == MZGPU_FRONTIER_EMPTY ? 0 : since;
+  // R32 arrangements: the merge-path kernels (mergepath.cu) -- three ordinary launches, any size, no
+  // host wait, no cooperative launch (opt-in with MZGPU_MERGE_KERNELS=1 until validated on the GPU suite)
+  static const bool merge_kernels = getenv("MZGPU_MERGE_KERNELS") != nullptr && atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
+  if (merge_kernels && b1->rb == 32 && (b1->len_ub + b2->len_ub + 1023) / 1024 <= MZ_LB_TILES) {
+    const u64 cap = b1->len_ub + b2->len_ub;
+    FusedOut fo;
+    MZ_TRY(mz_merge_r32_async(ctx, b1->rows.p, batch_dlen(b1), b2->rows.p, batch_dlen(b2), cap, adv, &fo));
+    return batch_from_fused(ctx, 32, std::move(fo), cap, d, out);
+  }
   if (!mz_use_fused(false, b1->len_ub + b2->len_ub)) {
     MZ_TRY(batch_resolve(b1));
     MZ_TRY(batch_resolve(b2));
