@@ -52,6 +52,13 @@ struct mzgpu_ctx {
   u32 lb_epoch = 0;            // tag of the next launch (20 bits)
   u32* d_tickets = nullptr;    // MZ_TICKETS zeroed tile counters, handed out round-robin
   u32 ticket_next = 0;
+  // the same for single-pass kernels launched on the side stream (they run concurrently with the main
+  // stream's: shared state words or a shared ticket reset would corrupt each other)
+  u64* d_lb_side = nullptr;
+  u32* d_tickets_side = nullptr;
+  u32 ticket_next_side = 0;
+  // merges in flight on the side stream whose inputs readers still use (host.cu: mz_join_side)
+  std::vector<struct mzgpu_batch*> side_outputs;
   u64* d_status = nullptr;     // [0] != 0: a bounded output overflowed (rows required), [1] != 0: a MIN/MAX key outgrew its table
   u64* d_dbg = nullptr;  // per-launch phase stamps of the fused kernel while profiling (32 words each)
   u32 dbg_next = 0;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 // ====================================================================== ctx
+static void side_outputs_joined(mzgpu_ctx* ctx);  // (defined with the batch type)
 extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_t peers,
                                     mzgpu_ctx** out) {
   if (out == nullptr || peers < 1 || worker_index < 0 || worker_index >= peers) return MZGPU_E_INVALID;
@@ -41,6 +42,10 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   MZ_CUDA(ctx, cudaMemset(ctx->d_lb, 0, (size_t)MZ_LB_TILES * 8));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_tickets, (size_t)MZ_TICKETS * 4));
   MZ_CUDA(ctx, cudaMemset(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_lb_side, (size_t)MZ_LB_TILES * 8));
+  MZ_CUDA(ctx, cudaMemset(ctx->d_lb_side, 0, (size_t)MZ_LB_TILES * 8));
+  MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_tickets_side, (size_t)MZ_TICKETS * 4));
+  MZ_CUDA(ctx, cudaMemset(ctx->d_tickets_side, 0, (size_t)MZ_TICKETS * 4));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_status, 16));
   MZ_CUDA(ctx, cudaMemset(ctx->d_status, 0, 16));
   for (int i = 0; i < 4; ++i) {
@@ -84,6 +89,10 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
 extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx == nullptr) return;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+  ctx->stream = ctx->main_stream ? ctx->main_stream : ctx->stream;
+  ctx->joined_seq = ctx->side_seq;
+  side_outputs_joined(ctx);  // merges that were never joined: let go of their inputs
   if (ctx->nccl_comm && ctx->nccl_lib) {
     typedef int (*destroy_t)(void*);
     destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
@@ -95,6 +104,8 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   if (ctx->d_cnt) cudaFree(ctx->d_cnt);
   if (ctx->d_lb) cudaFree(ctx->d_lb);
   if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+  if (ctx->d_lb_side) cudaFree(ctx->d_lb_side);
+  if (ctx->d_tickets_side) cudaFree(ctx->d_tickets_side);
   if (ctx->d_status) cudaFree(ctx->d_status);
   if (ctx->d_dbg) cudaFree(ctx->d_dbg);
   for (int i = 0; i < 4; ++i)
@@ -162,11 +173,14 @@ void mz_cnt_unpark(mzgpu_ctx* ctx) {
 // One copy of the whole arena (a few KB) + one wait: every count produced by a
 // kernel enqueued before this call becomes readable on the host.
 // the main stream waits for every merge issued on the side stream so far
+static void batch_release_internal(struct mzgpu_batch* b);
+static void side_outputs_joined(mzgpu_ctx* ctx);  // (after the batch type is complete)
 static int32_t mz_join_side(mzgpu_ctx* ctx) {
   if (ctx->joined_seq == ctx->side_seq) return MZGPU_OK;
   if (ctx->stream == ctx->main_stream) {
     MZ_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side, 0));
     ctx->joined_seq = ctx->side_seq;
+    side_outputs_joined(ctx);
     mz_cnt_unpark(ctx);
   }
   return MZGPU_OK;
@@ -176,12 +190,10 @@ int32_t mz_resolve_counters(mzgpu_ctx* ctx) {
   MZ_CHECK_CTX(ctx);
   // counters of deferred jobs count as written: their launch must precede the copy
   MZ_TRY(mz_flush_deferred(ctx));
-  // counts may have been written on either stream
-  if (ctx->stream == ctx->main_stream) {
-    MZ_TRY(mz_join_side(ctx));
-  } else {
-    MZ_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
-  }
+  // Counts written on the side stream are NOT waited for: the counter blocks of a merge in flight
+  // there carry seq = ~0 until the main stream joins it (mz_join_side), so this copy never passes
+  // for their value, and the operators of a timestamp keep running beside the merges it triggered.
+  if (ctx->stream != ctx->main_stream) MZ_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
   const size_t bytes = (size_t)ctx->cnt_high * 32;
   if (bytes) MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   MZ_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 40, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -214,17 +226,23 @@ int32_t mz_lookback_begin_at(mzgpu_ctx* ctx, u64 at, u64 max_tiles, LookBack* lb
                (unsigned long long)(at + max_tiles));
     return MZGPU_E_UNSUPPORTED;
   }
+  const bool side = ctx->side_stream != nullptr && ctx->stream == ctx->side_stream;
   ctx->lb_epoch = (ctx->lb_epoch + 1) & 0xfffffu;
-  if (ctx->lb_epoch == 0) {  // tag space wrapped: clear the state once
+  if (ctx->lb_epoch == 0) {  // tag space wrapped (once per million launches): clear both state arrays
+    if (ctx->side_stream != nullptr) MZ_CUDA(ctx, cudaStreamSynchronize(side ? ctx->main_stream : ctx->side_stream));
     MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_lb, 0, (size_t)MZ_LB_TILES * 8, ctx->stream));
+    MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_lb_side, 0, (size_t)MZ_LB_TILES * 8, ctx->stream));
+    MZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->lb_epoch = 1;
   }
-  if (ctx->ticket_next == MZ_TICKETS) {
-    MZ_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t)MZ_TICKETS * 4, ctx->stream));
-    ctx->ticket_next = 0;
+  u32& next = side ? ctx->ticket_next_side : ctx->ticket_next;
+  u32* tickets = side ? ctx->d_tickets_side : ctx->d_tickets;
+  if (next == MZ_TICKETS) {
+    MZ_CUDA(ctx, cudaMemsetAsync(tickets, 0, (size_t)MZ_TICKETS * 4, ctx->stream));
+    next = 0;
   }
-  lb->state = ctx->d_lb + at;
-  lb->ticket = ctx->d_tickets + ctx->ticket_next++;
+  lb->state = (side ? ctx->d_lb_side : ctx->d_lb) + at;
+  lb->ticket = tickets + next++;
   lb->epoch = ctx->lb_epoch;
   return MZGPU_OK;
 }
@@ -695,8 +713,12 @@ struct mzgpu_batch {
   int refs = 1;
   u64 side_seq = 0;  // != 0: produced by merge #side_seq on the side stream
   u64 deferred_seq = 0;  // != 0: produced by deferred job #deferred_seq (launched at the next flush)
+  // a merge running on the side stream keeps its inputs: until the main stream has joined that merge,
+  // readers (probes) use the inputs in place of this batch -- the reference's readers likewise see a
+  // merge's source batches until the merge completes (Spine: in-progress merges keep both batches)
+  mzgpu_batch* src1 = nullptr;
+  mzgpu_batch* src2 = nullptr;
 };
-static void batch_release_internal(mzgpu_batch* b);
 // Launch the deferred merges (one multi-job launch) and let go of their inputs.
 static int32_t mz_flush_deferred(mzgpu_ctx* ctx) {
   if (ctx->flushed_seq == ctx->defer_seq) return MZGPU_OK;
@@ -714,8 +736,39 @@ static int32_t batch_ready(mzgpu_batch* b) {
   return MZGPU_OK;
 }
 
+// the main stream has joined every side-stream merge issued so far: their result counters become
+// ordinary pending counters (covered by the next read-back), their inputs are let go
+static void side_outputs_joined(mzgpu_ctx* ctx) {
+  std::vector<mzgpu_batch*> outs;
+  outs.swap(ctx->side_outputs);
+  for (auto* o : outs) {
+    if (!o->st.known) o->st.seq = ++ctx->op_seq;
+    mzgpu_batch *a = o->src1, *b = o->src2;
+    o->src1 = o->src2 = nullptr;
+    if (a) batch_release_internal(a);
+    if (b) batch_release_internal(b);
+    batch_release_internal(o);  // the list's reference
+  }
+}
+// what a reader uses in place of `b`: the batch itself, or -- while its merge is still in flight on the
+// side stream -- the merge's inputs (recursively)
+static void expand_readable(mzgpu_batch* b, std::vector<mzgpu_batch*>& out) {
+  if (b->side_seq > b->ctx->joined_seq && b->src1 != nullptr && b->src2 != nullptr) {
+    expand_readable(b->src1, out);
+    expand_readable(b->src2, out);
+  } else {
+    out.push_back(b);
+  }
+}
 static int32_t batch_resolve(mzgpu_batch* b) {
   if (b->st.known) return MZGPU_OK;
+  if (b->side_seq > b->ctx->joined_seq) {
+    // its counters are written by a merge on the side stream
+    if (b->ctx->stream == b->ctx->main_stream)
+      MZ_TRY(mz_join_side(b->ctx));
+    else if (b->st.seq == ~0ull)
+      b->st.seq = ++b->ctx->op_seq;  // asked from the side stream itself: ordered behind that merge
+  }
   MZ_TRY(b->st.resolve());
   b->len_ub = b->st.v[0];
   return MZGPU_OK;
@@ -977,6 +1030,10 @@ extern "C" int32_t mzgpu_builder_done(mzgpu_builder* b, mzgpu_desc desc, mzgpu_b
   return st;
 }
 
+static bool mz_merge_kernels_on() {
+  static const bool on = getenv("MZGPU_MERGE_KERNELS") != nullptr && atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
+  return on;
+}
 // Batch::Merger in one step: union, advance_by(since), consolidate, index.
 static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_batch** out) {
   mzgpu_ctx* ctx = b1->ctx;
@@ -990,8 +1047,7 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
   const u64 adv = since == MZGPU_FRONTIER_EMPTY ? 0 : since;
   // R32 arrangements: the merge-path kernels (mergepath.cu) -- three ordinary launches, any size, no
   // host wait, no cooperative launch (opt-in with MZGPU_MERGE_KERNELS=1 until validated on the GPU suite)
-  static const bool merge_kernels = getenv("MZGPU_MERGE_KERNELS") != nullptr && atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
-  if (merge_kernels && b1->rb == 32 && (b1->len_ub + b2->len_ub + 1023) / 1024 <= MZ_LB_TILES) {
+  if (mz_merge_kernels_on() && b1->rb == 32 && (b1->len_ub + b2->len_ub + 1023) / 1024 <= MZ_LB_TILES) {
     const u64 cap = b1->len_ub + b2->len_ub;
     FusedOut fo;
     MZ_TRY(mz_merge_r32_async(ctx, b1->rows.p, batch_dlen(b1), b2->rows.p, batch_dlen(b2), cap, adv, &fo));
@@ -1531,22 +1587,28 @@ struct mzgpu_spine {
     if (b1->st.known && b2->st.known && b1->st.v[0] == 0 && b2->st.v[0] == 0) {
       mzgpu_desc d = {b1->desc.lower, b2->desc.upper, m.merge_since};
       st = make_empty_batch(ctx, rb, d, &out);
-    } else if (ctx->use_side && ctx->stream == ctx->main_stream && !ctx->profile &&
-               b1->len_ub + b2->len_ub <= MZ_FUSED_MAX_ROWS) {  // (bulk merges read sizes back: main stream)
-      // Spine maintenance runs on the side stream, concurrently with the operators on the
-      // main stream.  The side stream first catches up with the main stream (the inputs,
-      // and every earlier reader of the batches about to be freed, are ordered before it).
+    } else if (ctx->use_side && ctx->stream == ctx->main_stream && !ctx->profile && mz_merge_kernels_on() && rb == 32) {
+      // Spine maintenance runs on the side stream, concurrently with the operators on the main
+      // stream (the merge-path kernels are ordinary launches: they share the machine with the probes
+      // and the reduce of the timestamp that triggered them).  The side stream first catches up with
+      // the main stream (the inputs are ordered before it).  The inputs stay alive, and VISIBLE TO
+      // READERS in place of the output, until the main stream joins the merge (expand_readable).
       cudaEventRecord(ctx->ev_fork, ctx->main_stream);
       cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
       ctx->stream = ctx->side_stream;
       st = merge_batches(b1, b2, m.merge_since, &out);
-      mzgpu_batch_release(b1);  // freed in side-stream order, after the merge has read them
-      mzgpu_batch_release(b2);
-      b1 = b2 = nullptr;
       cudaEventRecord(ctx->ev_side, ctx->side_stream);
       ctx->stream = ctx->main_stream;
       ctx->side_seq++;
-      if (out != nullptr) out->side_seq = ctx->side_seq;
+      if (out != nullptr) {
+        out->side_seq = ctx->side_seq;
+        if (!out->st.known) out->st.seq = ~0ull;  // not covered by a read-back before the join
+        out->src1 = b1;  // (the references this function holds move to the output)
+        out->src2 = b2;
+        b1 = b2 = nullptr;
+        out->refs++;
+        ctx->side_outputs.push_back(out);
+      }
     } else {
       st = merge_batches(b1, b2, m.merge_since, &out);
     }
@@ -1778,6 +1840,13 @@ static void spine_through(mzgpu_spine* s, u64 through, std::vector<mzgpu_batch*>
       out.push_back(b);
   }
 }
+// the batches a reader of the arrangement probes: every batch, a merge still in flight on the side
+// stream represented by its inputs
+static void spine_readable(const mzgpu_spine* s, std::vector<mzgpu_batch*>& out) {
+  std::vector<mzgpu_batch*> all;
+  s->all_batches(all);
+  for (auto* b : all) expand_readable(b, out);
+}
 extern "C" int32_t mzgpu_spine_batches_through(mzgpu_spine* s, uint64_t upper, mzgpu_batch** batches,
                                                uint32_t cap, uint32_t* n_out) {
   if (s == nullptr || n_out == nullptr) return MZGPU_E_INVALID;
@@ -1915,7 +1984,11 @@ static void join_enqueue(mzgpu_join* j, int side, mzgpu_batch* batch, u64 cap) {
   w.side = side;
   w.batch = batch;
   mzgpu_batch_retain(batch);
-  spine_through(side == 0 ? j->t2 : j->t1, side == 0 ? j->ack2 : j->ack1, w.others);
+  {
+    std::vector<mzgpu_batch*> through;
+    spine_through(side == 0 ? j->t2 : j->t1, side == 0 ? j->ack2 : j->ack1, through);
+    for (auto* b : through) expand_readable(b, w.others);
+  }
   for (auto* b : w.others) mzgpu_batch_retain(b);
   w.cap = cap;
   j->todo.push_back(std::move(w));
@@ -2075,7 +2148,7 @@ static int32_t half_join_dev(mzgpu_ctx* ctx, const u64* d_stream, DLen n, u64 n_
                              mzgpu_buf* out) {
   if (n_ub == 0) return MZGPU_OK;
   std::vector<mzgpu_batch*> all;
-  trace->all_batches(all);
+  spine_readable(trace, all);
   u64 fan = 0;
   bool exact = true;
   MZ_TRY(trace_fanout(all, &fan, &exact));
@@ -2216,7 +2289,7 @@ static int32_t half_join_many_dev(mzgpu_ctx* ctx, int k, const HalfJoinReq* reqs
       if (reqs[i].stream != nullptr && reqs[i].stream == r.out) return one_by_one();
     if (req_ub(r) == 0) return one_by_one();
     std::vector<mzgpu_batch*> all;
-    r.trace->all_batches(all);
+    spine_readable(r.trace, all);
     u64 fan = 0;
     bool exact = true;
     MZ_TRY(trace_fanout(all, &fan, &exact));

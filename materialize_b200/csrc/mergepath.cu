@@ -11,7 +11,7 @@
 // 44-60 us whatever the size (two to five grid-wide barriers at ~5 us each, phases that re-read the
 // rows four times), and cooperative launches cannot overlap with one another.  Both inputs are
 // sorted, so the work is one pass:
-//   k_mrg_partition  one thread per 1024-row output tile: merge-path split of (A, B) on the tile's
+//   k_mrg_partition  one warp per 1024-row output tile: merge-path split of (A, B) on the tile's
 //                    diagonal, moved forward to the end of the run of equal (key, val, time') rows
 //                    that straddles it -- a tile never shares a run with its neighbour, so the
 //                    consolidation below needs no carry between tiles; also zeroes the hash table
@@ -77,48 +77,64 @@ __global__ void __launch_bounds__(MT) k_mrg_partition(const MergeArgs m) {
     m.st[2] = 0;
     m.st[3] = 0;
   }
-  for (u64 t = gtid; t <= T; t += gstride) {
+  // one WARP per diagonal: a 32-ary search (every lane probes one candidate split per round, the ballot
+  // narrows the range 32-fold) -- four or five dependent memory round trips instead of the twenty of a
+  // binary search, which were the whole cost of this kernel for update-batch merges
+  const u32 lane = threadIdx.x & 31;
+  const u64 gwarp = gtid >> 5, nwarps = gstride >> 5;
+  for (u64 t = gwarp; t <= T; t += nwarps) {
     const u64 d = t * M_TILE < n ? t * M_TILE : n;
-    // merge path on diagonal d, ties taken from A first: ia = rows of A among the first d merged
+    // merge path on diagonal d, ties taken from A first: ia = rows of A among the first d merged =
+    // the first mid in [lo, hi] for which "A[mid] <= B[d - 1 - mid]" fails
     u64 lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
     while (lo < hi) {
-      const u64 mid = (lo + hi) >> 1;
-      u64 ka[3], kb[3];
-      key_of(m.a, mid, m.since, ka);
-      key_of(m.b, d - 1 - mid, m.since, kb);
-      if (!key_lt(kb, ka))
-        lo = mid + 1;  // A[mid] <= B[d-1-mid]: A[mid] is among the first d
-      else
-        hi = mid;
+      const u64 width = hi - lo, step = (width + 31) / 32;
+      const u64 mid = lo + (u64)lane * step;
+      bool ok = false;  // predicate holds at mid (lanes past the range: treated as failing)
+      if (mid < hi) {
+        u64 ka[3], kb[3];
+        key_of(m.a, mid, m.since, ka);
+        key_of(m.b, d - 1 - mid, m.since, kb);
+        ok = !key_lt(kb, ka);
+      }
+      const u32 okm = __ballot_sync(0xffffffffu, ok);
+      const u32 f = okm == 0xffffffffu ? 32u : (u32)__ffs(~okm) - 1;  // first lane whose probe fails (monotone)
+      // the answer lies after the last holding probe and at or before the first failing one
+      const u64 new_hi = f < 32 && lo + (u64)f * step < hi ? lo + (u64)f * step : hi;
+      const u64 new_lo = f == 0 ? lo : lo + (u64)(f - 1) * step + 1;
+      lo = new_lo;
+      hi = new_hi;
     }
     u64 ia = lo, ib = d - lo;
-    if (d > 0 && d < n) {
-      // the last merged row before the split; rows equal to it on either side belong to its tile
-      u64 prev[3], x[3];
-      bool have = false;
-      if (ia > 0) {
-        key_of(m.a, ia - 1, m.since, prev);
-        have = true;
-      }
-      if (ib > 0) {
-        key_of(m.b, ib - 1, m.since, x);
-        if (!have || key_lt(prev, x)) {
-          prev[0] = x[0], prev[1] = x[1], prev[2] = x[2];
+    if (lane == 0) {
+      if (d > 0 && d < n) {
+        // the last merged row before the split; rows equal to it on either side belong to its tile
+        u64 prev[3], x[3];
+        bool have = false;
+        if (ia > 0) {
+          key_of(m.a, ia - 1, m.since, prev);
+          have = true;
+        }
+        if (ib > 0) {
+          key_of(m.b, ib - 1, m.since, x);
+          if (!have || key_lt(prev, x)) {
+            prev[0] = x[0], prev[1] = x[1], prev[2] = x[2];
+          }
+        }
+        while (ia < na) {
+          key_of(m.a, ia, m.since, x);
+          if (!key_eq(x, prev)) break;
+          ++ia;
+        }
+        while (ib < nb) {
+          key_of(m.b, ib, m.since, x);
+          if (!key_eq(x, prev)) break;
+          ++ib;
         }
       }
-      while (ia < na) {
-        key_of(m.a, ia, m.since, x);
-        if (!key_eq(x, prev)) break;
-        ++ia;
-      }
-      while (ib < nb) {
-        key_of(m.b, ib, m.since, x);
-        if (!key_eq(x, prev)) break;
-        ++ib;
-      }
+      m.splits[2 * t] = ia;
+      m.splits[2 * t + 1] = ib;
     }
-    m.splits[2 * t] = ia;
-    m.splits[2 * t + 1] = ib;
   }
 }
 
@@ -378,7 +394,7 @@ int32_t mz_merge_r32_async(mzgpu_ctx* ctx, const void* d_a, DLen na, const void*
   MZ_TRY(mz_lookback_begin(ctx, Tcap, &m.lb));
   // partition + table clear: enough CTAs to zero the table at bandwidth, at least one thread per tile
   u64 g1 = (slots * 2 + MT * 8 - 1) / (MT * 8);
-  const u64 g1_min = (Tcap + 1 + MT - 1) / MT, g_max = (u64)ctx->num_sms * 8;
+  const u64 g1_min = (Tcap + 1 + MT / 32 - 1) / (MT / 32), g_max = (u64)ctx->num_sms * 8;  // a warp per diagonal
   if (g1 < g1_min) g1 = g1_min;
   if (g1 > g_max) g1 = g_max;
   const bool exact = na.p == nullptr && nb.p == nullptr;
