@@ -77,7 +77,8 @@ struct mzgpu_ctx {
   // stream waits for the side stream the first time it touches such a batch
   cudaStream_t main_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
-  bool use_side = false;  // off by default: measured no gain on the Q3 step (MZGPU_SIDE_STREAM=1 enables)
+  bool use_side = true;   // spine merges of R32 arrangements run beside the operators (MZGPU_SIDE_STREAM=0: main stream);
+                          // measured on the Q3 step: 212 -> 267 M rows/s (profiles/r03_*)
   u64 side_seq = 0;    // merges issued on the side stream so far
   u64 joined_seq = 0;  // the main stream has waited for merges <= this
   // per-kernel profiling (mzgpu_profile_enable)

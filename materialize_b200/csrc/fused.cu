@@ -1705,12 +1705,14 @@ int32_t fused_t(mzgpu_ctx* ctx, const FusedJob& job, FusedOut* res) {
   u64 want = 0;
   DevMem scratch;
   MZ_TRY(fused_prepare<RB>(ctx, job, res, -1, &a, &want, &scratch));
-  // With the side stream in use a launch takes at most one CTA slot per SM, so that a merge on
-  // the side stream and a seal on the main stream can be co-resident (cooperative launches
-  // only start when the whole grid fits).
+  // A launch ON the side stream (a merge too large for the merge-path kernels' look-back state; the
+  // ordinary spine merges there are plain launches, mergepath.cu) takes at most one CTA slot per SM, so
+  // that it can be co-resident with the operators' launches on the main stream (a cooperative launch
+  // starts when its whole grid fits).  Main-stream launches use the whole resident capacity:
   // (64 registers per thread: four CTAs per SM are resident, 592 on a B200; the bucket phase
   // wants one warp per bucket, and a 160K-row merge has 4096 of them)
-  a.max_g = ctx->use_side ? (u32)ctx->num_sms : (u32)max_ctas;
+  const bool on_side = ctx->side_stream != nullptr && ctx->stream == ctx->side_stream;
+  a.max_g = on_side ? (u32)ctx->num_sms : (u32)max_ctas;
   if (a.max_g > (u32)max_ctas) a.max_g = (u32)max_ctas;
   const unsigned a_max_g_host = a.max_g;
   unsigned grid = (unsigned)(want < (u64)max_ctas ? want : (u64)max_ctas);

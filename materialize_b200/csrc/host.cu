@@ -1031,7 +1031,9 @@ extern "C" int32_t mzgpu_builder_done(mzgpu_builder* b, mzgpu_desc desc, mzgpu_b
 }
 
 static bool mz_merge_kernels_on() {
-  static const bool on = getenv("MZGPU_MERGE_KERNELS") != nullptr && atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
+  // on by default (validated: the GPU suite and the bench's per-step parity check pass either way,
+  // profiles/r03_*); MZGPU_MERGE_KERNELS=0 runs R32 merges in the fused cooperative kernel instead
+  static const bool on = getenv("MZGPU_MERGE_KERNELS") == nullptr || atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
   return on;
 }
 // Batch::Merger in one step: union, advance_by(since), consolidate, index.
@@ -1046,7 +1048,7 @@ static int32_t merge_batches(mzgpu_batch* b1, mzgpu_batch* b2, u64 since, mzgpu_
   // max(time, since), for which 0 is the no-op
   const u64 adv = since == MZGPU_FRONTIER_EMPTY ? 0 : since;
   // R32 arrangements: the merge-path kernels (mergepath.cu) -- three ordinary launches, any size, no
-  // host wait, no cooperative launch (opt-in with MZGPU_MERGE_KERNELS=1 until validated on the GPU suite)
+  // host wait, no cooperative launch (MZGPU_MERGE_KERNELS=0 switches them off)
   if (mz_merge_kernels_on() && b1->rb == 32 && (b1->len_ub + b2->len_ub + 1023) / 1024 <= MZ_LB_TILES) {
     const u64 cap = b1->len_ub + b2->len_ub;
     FusedOut fo;

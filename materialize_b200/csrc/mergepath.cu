@@ -404,8 +404,10 @@ int32_t mz_merge_r32_async(mzgpu_ctx* ctx, const void* d_a, DLen na, const void*
   if (g2 == 0) g2 = 1;
   MZ_BYTES(ctx, exact ? (na.imm + nb.imm) * 64 : 0);
   MZ_LAUNCH(ctx, k_mrg_tiles, (unsigned)g2, MT, 0, m);
-  u64 g3 = (cap + MT * 4 - 1) / (MT * 4);
-  if (g3 > g_max) g3 = g_max;
+  // one row per thread where the machine can hold it: a head walks its key's run with dependent loads,
+  // and four rows per thread made that chain four times as long for update-batch merges
+  u64 g3 = (cap + MT - 1) / MT;
+  if (g3 > g_max * 4) g3 = g_max * 4;
   if (g3 == 0) g3 = 1;
   MZ_BYTES(ctx, exact ? (na.imm + nb.imm) * 8 : 0);
   MZ_LAUNCH(ctx, k_mrg_index, (unsigned)g3, MT, 0, res->rows.as<u64>(), res->st.dptr(), res->table.as<HashSlot>());
