@@ -105,8 +105,9 @@ class ClockSampler:
         try:
             self._nvml_open()
             self.samples = []  # the probe sample was taken before the timed region
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
+            if os.environ.get("MZ_CLOCK_SAMPLER", "1") != "0":  # (0: only the sample the timing loop takes itself)
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
             return
         except Exception:
             self.nvml, self.thread = None, None
@@ -457,6 +458,7 @@ def run_ours(args, rank, world, local_rank):
     rows_timed = 0
     host_t0 = time.perf_counter()
     ht0 = ctx.host_times()
+    hp0 = q.host_ns()
     for i in range(n_timed):
         # the output corrections of every timed step are appended (device to device, no read-back)
         # to `kept` and compared with the CPU oracle's after the region
@@ -466,6 +468,9 @@ def run_ours(args, rank, world, local_rank):
         b += 1
     host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / n_timed  # host time per step inside the loop ...
     ht1 = ctx.host_times()
+    hp1 = q.host_ns()
+    host_phase_ms = {k: round((hp1[k] - hp0[k]) / 1e6 / n_timed, 4) for k in hp1}  # host time inside the harness's step, by phase
+    host_alloc_ms = (ht1["alloc_ns"] - ht0["alloc_ns"]) / 1e6 / n_timed if "alloc_ns" in ht1 else None
     host_wait_ms = (ht1["wait_ns"] - ht0["wait_ns"]) / 1e6 / n_timed  # ... of which: waiting for the device
     e1.record(ext)
     try:
@@ -608,7 +613,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / n_timed,
         "per_step_ms": per_step,
         "host_ms_per_step": {"loop": host_enqueue_ms, "waiting_for_device": host_wait_ms, "work": host_enqueue_ms - host_wait_ms,
-                             "allocations": (ht1["allocs"] - ht0["allocs"]) / n_timed},
+                             "allocations": (ht1["allocs"] - ht0["allocs"]) / n_timed, "in_allocator": host_alloc_ms,
+                             "harness_phases": host_phase_ms},
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,

@@ -23,6 +23,7 @@ struct mzgpu_ctx {
   int peers = 1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;
+  cudaEvent_t ev_block = nullptr;  // MZGPU_BLOCKING_SYNC=1: host waits block on this event (no spinning)
   int num_sms = 148;
   bool sticky = false;  // a CUDA/NCCL failure (or a deferred device-side report) happened: every later call fails
   int32_t sticky_code = MZGPU_E_CUDA;  // ... with this status
@@ -114,6 +115,12 @@ struct mzgpu_ctx {
   std::vector<BigBlock> big_cache;
   size_t big_cached_bytes = 0;
   u64 big_hits = 0, big_misses = 0;
+  // mid-size blocks ([MZ_MID_BLOCK, MZ_BIG_BLOCK)): kept too, but handed out again only on the stream they were
+  // freed on (no cross-stream wait: the side stream's merges and the main stream's operators stay decoupled)
+  std::vector<BigBlock> mid_cache;
+  size_t mid_cached_bytes = 0;
+  u64 mid_hits = 0, mid_misses = 0;
+  size_t mid_block = (size_t)8 << 20;  // MZGPU_MID_BLOCK_MB (0: off)
 };
 // Blocks of at least this size bypass the driver's stream-ordered pool on reuse: measured on B200
 // (tools/diag_bulk.py cfg4, profiles/r02_diag_cfg4_before.log), cudaMallocAsync of 3-8 GB blocks cost
@@ -122,6 +129,11 @@ struct mzgpu_ctx {
 // at most) allocates in microseconds and stays on the pool.
 #define MZ_BIG_BLOCK ((size_t)512 << 20)
 #define MZ_BIG_CACHE_MAX ((size_t)96 << 30)
+// Mid-size blocks: with several workers an operator's scratch is sized by what the worker COULD receive
+// (a reduce activation at 2 GPUs allocates and frees ~600 MB in blocks of 30-200 MB for ~10 K actual rows),
+// and the driver's pool took 0.4-10 ms of host time per timestamp for them (profiles/r03_diag_n2.log: all
+// of it inside the reduce activation's cudaMallocAsync / cudaFreeAsync calls, worse while NVML is polled).
+#define MZ_MID_CACHE_MAX ((size_t)24 << 30)
 
 #define MZ_SET_ERR(ctx, ...)                              \
   do {                                                    \
@@ -145,7 +157,13 @@ struct mzgpu_ctx {
 #define MZ_SYNC(ctx)                                            \
   do {                                                          \
     auto _t0 = std::chrono::steady_clock::now();                \
-    MZ_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));         \
+    if ((ctx)->ev_block != nullptr) {                           \
+      /* MZGPU_BLOCKING_SYNC=1: sleep in the driver instead of spinning on a core */ \
+      MZ_CUDA(ctx, cudaEventRecord((ctx)->ev_block, (ctx)->stream)); \
+      MZ_CUDA(ctx, cudaEventSynchronize((ctx)->ev_block));      \
+    } else {                                                    \
+      MZ_CUDA(ctx, cudaStreamSynchronize((ctx)->stream));       \
+    }                                                           \
     (ctx)->ns_sync += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - _t0).count(); \
     (ctx)->stats.host_syncs++;                                  \
   } while (0)
@@ -232,11 +250,12 @@ struct DevMem {
     return *this;
   }
   ~DevMem() { release(); }
-  int32_t alloc(mzgpu_ctx* c, size_t n) {
+  // `exact`: long-lived storage sized to its contents (a shrunk batch) -- never a larger parked block
+  int32_t alloc(mzgpu_ctx* c, size_t n, bool exact = false) {
     release();
     ctx = c;
     if (n == 0) n = 16;
-    if (n >= MZ_BIG_BLOCK) {
+    if (n >= MZ_BIG_BLOCK && !exact) {
       // best fit among the cached big blocks, wasting at most half of the block
       int best = -1;
       for (int i = 0; i < (int)c->big_cache.size(); ++i) {
@@ -265,14 +284,41 @@ struct DevMem {
       }
       c->big_misses++;
     }
+    if (c->mid_block != 0 && n >= c->mid_block && n < MZ_BIG_BLOCK && !exact) {
+      // best fit among the blocks freed on THIS stream (stream order makes the reuse safe without an event)
+      int best = -1;
+      for (int i = 0; i < (int)c->mid_cache.size(); ++i) {
+        const size_t b = c->mid_cache[i].bytes;
+        if (c->mid_cache[i].freed_on == c->stream && b >= n && b / 2 <= n && (best < 0 || b < c->mid_cache[best].bytes))
+          best = i;
+      }
+      if (best >= 0) {
+        const mzgpu_ctx::BigBlock blk = c->mid_cache[best];
+        c->mid_cache.erase(c->mid_cache.begin() + best);
+        c->mid_cached_bytes -= blk.bytes;
+        p = blk.p;
+        bytes = blk.bytes;
+        c->mid_hits++;
+        c->stats.device_bytes_in_use += bytes;
+        if (c->stats.device_bytes_in_use > c->stats.device_bytes_peak)
+          c->stats.device_bytes_peak = c->stats.device_bytes_in_use;
+        return MZGPU_OK;
+      }
+      c->mid_misses++;
+    }
     auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMallocAsync(&p, n, c->stream);
-    if (e != cudaSuccess && !c->big_cache.empty()) {
-      // out of memory with blocks parked in the cache: hand them back and try once more
+    if (e != cudaSuccess && (!c->big_cache.empty() || !c->mid_cache.empty())) {
+      // out of memory with blocks parked in the caches: hand them back (each in the order of the stream
+      // it was freed on), let those frees happen, and try once more
       (void)cudaGetLastError();
-      for (auto& b : c->big_cache) cudaFreeAsync(b.p, c->stream);
+      for (auto& b : c->big_cache) cudaFreeAsync(b.p, b.freed_on);
+      for (auto& b : c->mid_cache) cudaFreeAsync(b.p, b.freed_on);
       c->big_cache.clear();
       c->big_cached_bytes = 0;
+      c->mid_cache.clear();
+      c->mid_cached_bytes = 0;
+      cudaDeviceSynchronize();
       e = cudaMallocAsync(&p, n, c->stream);
     }
     c->ns_alloc += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
@@ -296,8 +342,20 @@ struct DevMem {
       if (bytes >= MZ_BIG_BLOCK && ctx->big_cached_bytes + bytes <= MZ_BIG_CACHE_MAX) {
         ctx->big_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream});
         ctx->big_cached_bytes += bytes;
+      } else if (ctx->mid_block != 0 && bytes >= ctx->mid_block && bytes < MZ_BIG_BLOCK) {
+        ctx->mid_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream});
+        ctx->mid_cached_bytes += bytes;
+        // over the budget: the oldest parked blocks go back to the driver's pool, in the order of their stream
+        while (ctx->mid_cached_bytes > MZ_MID_CACHE_MAX && ctx->mid_cache.size() > 1) {
+          const mzgpu_ctx::BigBlock old = ctx->mid_cache.front();
+          ctx->mid_cache.erase(ctx->mid_cache.begin());
+          ctx->mid_cached_bytes -= old.bytes;
+          cudaFreeAsync(old.p, old.freed_on);
+        }
       } else {
+        auto t0 = std::chrono::steady_clock::now();
         cudaFreeAsync(p, ctx->stream);
+        ctx->ns_alloc += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
       }
       p = nullptr;
       bytes = 0;

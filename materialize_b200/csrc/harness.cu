@@ -18,6 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <chrono>
+#include <memory>
+
 #include <utility>
 #include <vector>
 
@@ -149,7 +152,21 @@ struct mzh_q3 {
   bool stepping = false;                             // false while hydrating
   bool use_p2p = false;                              // update-batch exchange rounds go over peer memory
   bool streams_prepared = false;                     // stage-0 streams already mapped + exchanged
+  // host time spent inside the phases of a step (steady_clock; mzh_q3_host_ns): 0 inputs (staging hand-over,
+  // arrangement-input exchange, pushes), 1 seals + spine inserts, 2 maintenance, 3 / 4 the delta paths' two
+  // stages (exchange round, read-back, half joins), 5 result exchange, 6 reduce, 7 the whole step
+  uint64_t host_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+namespace {
+struct PhaseTimer {
+  uint64_t* acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(uint64_t* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() {
+    *acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+}  // namespace
 
 static int32_t q3_gen_orders(mzh_q3* q, uint64_t first, uint64_t n, int tick, int n_versions, uint64_t t,
                              uint64_t* n_li) {
@@ -213,12 +230,18 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
   mzgpu_batch* batch[4] = {nullptr, nullptr, nullptr, nullptr};
   int32_t st = MZGPU_OK;
   // the four arrange operators are activated by the same frontier advance: one batched seal
-  st = mzgpu_batcher_seal_many(4, q->batcher, upper, batch);
-  for (int a = 0; a < 4 && st == MZGPU_OK; ++a) st = mzgpu_spine_insert(q->spine[a], batch[a]);
+  {
+    PhaseTimer pt(&q->host_ns[1]);
+    st = mzgpu_batcher_seal_many(4, q->batcher, upper, batch);
+    for (int a = 0; a < 4 && st == MZGPU_OK; ++a) st = mzgpu_spine_insert(q->spine[a], batch[a]);
+  }
   // The previous timestamp's maintenance runs here: the seals above are already queued on
   // the device, so the merges it schedules (side stream) and the few lengths it has to read
   // back overlap with them instead of delaying them.
-  if (st == MZGPU_OK) st = q3_maintenance(q);
+  if (st == MZGPU_OK) {
+    PhaseTimer pt(&q->host_ns[2]);
+    st = q3_maintenance(q);
+  }
   if (st == MZGPU_OK) st = mzgpu_buf_clear(q->results);
   // the three delta paths run side by side, stage by stage, so that the exchange
   // points of one stage share a round (mzgpu_exchange_many).  A path whose source
@@ -235,6 +258,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
                                path == 0 ? MZGPU_FRONTIER_EMPTY : 0, q->pstream[path]);
   }
   for (int s = 0; s < 2 && st == MZGPU_OK; ++s) {
+    PhaseTimer pt(&q->host_ns[3 + s]);
     if (q->peers > 1 && !(s == 0 && q->streams_prepared)) {  // half_join exchanges its stream by key
       mzgpu_buf *ins[3], *outs[3];
       uint32_t k = 0;
@@ -294,6 +318,7 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
         if (active[path]) std::swap(q->pstream[path], q->pnext[path]);
   }
   if (st == MZGPU_OK && q->peers > 1) {
+    PhaseTimer pt(&q->host_ns[5]);
     st = q3_exchange(q, 1, &q->results, &q->xchg, nullptr);
     std::swap(q->results, q->xchg);
   }
@@ -306,7 +331,10 @@ static int32_t q3_run_timestamp(mzh_q3* q, uint64_t t) {
       q->out_pending[q->out_parity] = false;
     }
   }
-  if (st == MZGPU_OK) st = mzgpu_reduce_accumulable_buf(q->reduce, q->results, upper, out_buf);
+  if (st == MZGPU_OK) {
+    PhaseTimer pt(&q->host_ns[6]);
+    st = mzgpu_reduce_accumulable_buf(q->reduce, q->results, upper, out_buf);
+  }
   if (st == MZGPU_OK && q->pipelined_out) {
     H_CUDA(cudaEventRecord(q->ev_out[q->out_parity], q->stream));
     q->out_pending[q->out_parity] = true;
@@ -536,6 +564,8 @@ int32_t mzh_q3_staged(mzh_q3* q, int32_t a, mzgpu_r32* rows, uint64_t cap, uint6
 // maintenance runs first (its counts have reached the host by now).
 int32_t mzh_q3_step(mzh_q3* q) {
   if (q == nullptr) return MZGPU_E_INVALID;
+  PhaseTimer pt_all(&q->host_ns[7]);
+  std::unique_ptr<PhaseTimer> pt_in(new PhaseTimer(&q->host_ns[0]));
   q->stepping = true;
   if (q->slot_full[q->run_slot]) {
     // a committed host batch: the ctx stream waits for its H2D copies, takes the
@@ -588,8 +618,15 @@ int32_t mzh_q3_step(mzh_q3* q) {
   } else {
     for (int a = 0; a < 4; ++a) H_TRY(q3_arrange_push(q, a, q->input[a]));
   }
+  pt_in.reset();
   H_TRY(q3_run_timestamp(q, t));
   q->next_time = t + 1;
+  return MZGPU_OK;
+}
+// Host nanoseconds spent in the phases of mzh_q3_step so far (see mzh_q3::host_ns).
+int32_t mzh_q3_host_ns(mzh_q3* q, uint64_t out[8]) {
+  if (q == nullptr || out == nullptr) return MZGPU_E_INVALID;
+  for (int i = 0; i < 8; ++i) out[i] = q->host_ns[i];
   return MZGPU_OK;
 }
 // Update-batch exchange rounds over peer memory from now on (the caller has connected the landing

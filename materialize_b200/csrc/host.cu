@@ -32,6 +32,8 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   ctx->num_sms = prop.multiProcessorCount;
   MZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+  if (const char* e = getenv("MZGPU_BLOCKING_SYNC"))
+    if (atoi(e) != 0) MZ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 128 * 8));
   MZ_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 128 * 8));
   MZ_CUDA(ctx, cudaMallocHost((void**)&ctx->h_big, 4096));
@@ -53,6 +55,7 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl[i], 0, mz_fused_ctl_bytes()));
   }
   if (const char* e = getenv("MZGPU_DEFER_MERGES")) ctx->defer_merges = atoi(e) != 0;
+  if (const char* e = getenv("MZGPU_MID_BLOCK_MB")) ctx->mid_block = (size_t)strtoull(e, nullptr, 10) << 20;
   for (int i = 0; i < 16; ++i) {
     MZ_CUDA(ctx, cudaMalloc(&ctx->d_fused_ctl_many[i], mz_fused_ctl_bytes()));
     MZ_CUDA(ctx, cudaMemset(ctx->d_fused_ctl_many[i], 0, mz_fused_ctl_bytes()));
@@ -114,6 +117,7 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
     if (ctx->d_fused_ctl_many[i]) cudaFree(ctx->d_fused_ctl_many[i]);
   mz_fused_deferred_free(ctx);
   for (auto& b : ctx->big_cache) cudaFree(b.p);
+  for (auto& b : ctx->mid_cache) cudaFree(b.p);
   ctx->big_cache.clear();
   for (int p = 0; p < 16; ++p)
     if (ctx->p2p_peer_ipc[p] && ctx->p2p_peer[p]) cudaIpcCloseMemHandle(ctx->p2p_peer[p]);
@@ -128,6 +132,7 @@ extern "C" void mzgpu_ctx_destroy(mzgpu_ctx* ctx) {
   ctx->stream = ctx->main_stream;
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev) cudaEventDestroy(ctx->ev);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   for (auto& r : ctx->prof) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -257,11 +262,13 @@ extern "C" int32_t mzgpu_ctx_stats(mzgpu_ctx* ctx, mzgpu_stats* out) {
   if (getenv("MZGPU_DEBUG"))
     fprintf(stderr,
             "[mzgpu] allocs %llu (%.1f MB, %.3f ms host)  syncs %llu (%.3f ms waiting)  launches %llu  counter blocks %d"
-            " in use (high water %d)  big blocks: %llu reused, %llu new, %.1f MB parked\n",
+            " in use (high water %d)  big blocks: %llu reused, %llu new, %.1f MB parked  mid blocks: %llu reused, %llu new,"
+            " %.1f MB parked\n",
             (unsigned long long)ctx->n_alloc, ctx->bytes_alloc / 1e6, ctx->ns_alloc / 1e6,
             (unsigned long long)ctx->stats.host_syncs, ctx->ns_sync / 1e6,
             (unsigned long long)ctx->stats.kernel_launches, ctx->cnt_high - (int)ctx->cnt_free.size(), ctx->cnt_high,
-            (unsigned long long)ctx->big_hits, (unsigned long long)ctx->big_misses, ctx->big_cached_bytes / 1e6);
+            (unsigned long long)ctx->big_hits, (unsigned long long)ctx->big_misses, ctx->big_cached_bytes / 1e6,
+            (unsigned long long)ctx->mid_hits, (unsigned long long)ctx->mid_misses, ctx->mid_cached_bytes / 1e6);
   *out = ctx->stats;
   return MZGPU_OK;
 }
@@ -825,7 +832,7 @@ static int32_t batch_shrink(mzgpu_batch* b) {
   if ((realloc_rows || realloc_table) && ctx->deferred_unlaunched > 0) MZ_TRY(mz_flush_deferred(ctx));
   if (realloc_rows) {
     DevMem m;
-    MZ_TRY(m.alloc(ctx, std::max<u64>(len, 1) * b->rb));
+    MZ_TRY(m.alloc(ctx, std::max<u64>(len, 1) * b->rb, true));
     MZ_TRY(copy_in(ctx, m.p, b->rows.p, len * b->rb, MZGPU_MEM_DEVICE));
     b->rows = std::move(m);
     b->rows_cap = std::max<u64>(len, 1);
@@ -833,7 +840,7 @@ static int32_t batch_shrink(mzgpu_batch* b) {
   const u64 slots = b->st.v[1] + 1;
   if (b->table.p != nullptr && b->table.bytes > 2 * slots * sizeof(HashSlot) + 65536) {
     DevMem t;
-    MZ_TRY(t.alloc(ctx, slots * sizeof(HashSlot)));
+    MZ_TRY(t.alloc(ctx, slots * sizeof(HashSlot), true));
     MZ_TRY(copy_in(ctx, t.p, b->table.p, slots * sizeof(HashSlot), MZGPU_MEM_DEVICE));
     b->table = std::move(t);
   }

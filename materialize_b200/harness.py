@@ -25,6 +25,7 @@ _SIG = {
     "mzh_q3_fetch_out": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_maintain": (i32, [vp]),
     "mzh_q3_use_p2p": (i32, [vp, i32]),
+    "mzh_q3_host_ns": (i32, [vp, C.POINTER(u64)]),
     "mzh_q3_input": (vp, [vp, i32]),
     "mzh_q3_staged": (i32, [vp, i32, vp, u64, C.POINTER(u64)]),
     "mzh_q3_step": (i32, [vp]),
@@ -83,6 +84,13 @@ class Q3Dataflow:
 
     def h2d_bytes(self):
         return _lib.mzh_q3_h2d_bytes(self.h)
+
+    def host_ns(self):
+        """Host nanoseconds spent so far in the phases of step(): inputs, seals, maintenance, the delta
+        paths' two stages, result exchange, reduce, the whole step."""
+        out = (C.c_uint64 * 8)()
+        self.ctx.check(_lib.mzh_q3_host_ns(self.h, out))
+        return dict(zip(("inputs", "seals", "maintenance", "stage1", "stage2", "result_exchange", "reduce", "step"), [int(x) for x in out]))
 
     def use_p2p(self, on=True):
         """Update-batch exchange rounds over peer memory (landing zones connected by the caller)."""
