@@ -79,7 +79,7 @@ struct mzgpu_ctx {
   cudaStream_t main_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
   bool use_side = true;   // spine merges of R32 arrangements run beside the operators (MZGPU_SIDE_STREAM=0: main stream);
-                          // measured on the Q3 step: 212 -> 267 M rows/s (profiles/r03_*)
+                          // measured on the Q3 step: 212 -> 267 M rows/s (profiles/r02b_*)
   u64 side_seq = 0;    // merges issued on the side stream so far
   u64 joined_seq = 0;  // the main stream has waited for merges <= this
   // per-kernel profiling (mzgpu_profile_enable)
@@ -111,12 +111,15 @@ struct mzgpu_ctx {
     void* p;
     size_t bytes;
     cudaStream_t freed_on;  // the ctx stream at the time of the free
+    unsigned ok;            // mid-size blocks: streams whose order already covers the free (1 main, 2 side)
   };
   std::vector<BigBlock> big_cache;
   size_t big_cached_bytes = 0;
   u64 big_hits = 0, big_misses = 0;
-  // mid-size blocks ([MZ_MID_BLOCK, MZ_BIG_BLOCK)): kept too, but handed out again only on the stream they were
-  // freed on (no cross-stream wait: the side stream's merges and the main stream's operators stay decoupled)
+  // mid-size blocks ([mid_block, MZ_BIG_BLOCK)): kept too, and handed out again only to a stream whose order
+  // already covers the free -- the stream it was freed on, the side stream once it has forked from the main
+  // stream after the free, the main stream once it has joined the side stream after the free (mz_mid_forked /
+  // mz_mid_joined) -- so no event wait is ever added: merges and operators stay decoupled
   std::vector<BigBlock> mid_cache;
   size_t mid_cached_bytes = 0;
   u64 mid_hits = 0, mid_misses = 0;
@@ -131,9 +134,20 @@ struct mzgpu_ctx {
 #define MZ_BIG_CACHE_MAX ((size_t)96 << 30)
 // Mid-size blocks: with several workers an operator's scratch is sized by what the worker COULD receive
 // (a reduce activation at 2 GPUs allocates and frees ~600 MB in blocks of 30-200 MB for ~10 K actual rows),
-// and the driver's pool took 0.4-10 ms of host time per timestamp for them (profiles/r03_diag_n2.log: all
+// and the driver's pool took 0.4-10 ms of host time per timestamp for them (profiles/r02b_diag_n2.log: all
 // of it inside the reduce activation's cudaMallocAsync / cudaFreeAsync calls, worse while NVML is polled).
 #define MZ_MID_CACHE_MAX ((size_t)24 << 30)
+// the side stream has just been made to wait for the main stream: what the main stream's order covers, the
+// side stream's order covers now
+static inline void mz_mid_forked(mzgpu_ctx* ctx) {
+  for (auto& b : ctx->mid_cache)
+    if (b.ok & 1u) b.ok |= 2u;
+}
+// the main stream has just been made to wait for everything issued on the side stream
+static inline void mz_mid_joined(mzgpu_ctx* ctx) {
+  for (auto& b : ctx->mid_cache)
+    if (b.ok & 2u) b.ok |= 1u;
+}
 
 #define MZ_SET_ERR(ctx, ...)                              \
   do {                                                    \
@@ -285,11 +299,12 @@ struct DevMem {
       c->big_misses++;
     }
     if (c->mid_block != 0 && n >= c->mid_block && n < MZ_BIG_BLOCK && !exact) {
-      // best fit among the blocks freed on THIS stream (stream order makes the reuse safe without an event)
+      // best fit among the blocks whose free this stream's order already covers (no event needed)
+      const unsigned me = (c->side_stream != nullptr && c->stream == c->side_stream) ? 2u : 1u;
       int best = -1;
       for (int i = 0; i < (int)c->mid_cache.size(); ++i) {
         const size_t b = c->mid_cache[i].bytes;
-        if (c->mid_cache[i].freed_on == c->stream && b >= n && b / 2 <= n && (best < 0 || b < c->mid_cache[best].bytes))
+        if ((c->mid_cache[i].ok & me) != 0 && b >= n && b / 2 <= n && (best < 0 || b < c->mid_cache[best].bytes))
           best = i;
       }
       if (best >= 0) {
@@ -340,10 +355,11 @@ struct DevMem {
     if (p != nullptr) {
       ctx->stats.device_bytes_in_use -= bytes;
       if (bytes >= MZ_BIG_BLOCK && ctx->big_cached_bytes + bytes <= MZ_BIG_CACHE_MAX) {
-        ctx->big_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream});
+        ctx->big_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream, 0u});
         ctx->big_cached_bytes += bytes;
       } else if (ctx->mid_block != 0 && bytes >= ctx->mid_block && bytes < MZ_BIG_BLOCK) {
-        ctx->mid_cache.push_back(mzgpu_ctx::BigBlock{p, bytes, ctx->stream});
+        ctx->mid_cache.push_back(mzgpu_ctx::BigBlock{
+            p, bytes, ctx->stream, (ctx->side_stream != nullptr && ctx->stream == ctx->side_stream) ? 2u : 1u});
         ctx->mid_cached_bytes += bytes;
         // over the budget: the oldest parked blocks go back to the driver's pool, in the order of their stream
         while (ctx->mid_cached_bytes > MZ_MID_CACHE_MAX && ctx->mid_cache.size() > 1) {

@@ -76,7 +76,7 @@ extern "C" int32_t mzgpu_ctx_create(int32_t device, int32_t worker_index, int32_
   {
     size_t free_b = 0, total_b = 0;
     MZ_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    size_t want = (size_t)24 << 30;
+    size_t want = (size_t)40 << 30;  // (blocks parked in the library's own caches, DevMem, are not free memory of the pool)
     if (const char* e = getenv("MZGPU_POOL_MB")) want = (size_t)strtoull(e, nullptr, 10) << 20;
     if (want > free_b / 2) want = free_b / 2;
     if (want >= ((size_t)1 << 20)) {
@@ -184,6 +184,7 @@ static int32_t mz_join_side(mzgpu_ctx* ctx) {
   if (ctx->joined_seq == ctx->side_seq) return MZGPU_OK;
   if (ctx->stream == ctx->main_stream) {
     MZ_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side, 0));
+    mz_mid_joined(ctx);
     ctx->joined_seq = ctx->side_seq;
     side_outputs_joined(ctx);
     mz_cnt_unpark(ctx);
@@ -1039,7 +1040,7 @@ extern "C" int32_t mzgpu_builder_done(mzgpu_builder* b, mzgpu_desc desc, mzgpu_b
 
 static bool mz_merge_kernels_on() {
   // on by default (validated: the GPU suite and the bench's per-step parity check pass either way,
-  // profiles/r03_*); MZGPU_MERGE_KERNELS=0 runs R32 merges in the fused cooperative kernel instead
+  // profiles/r02b_*); MZGPU_MERGE_KERNELS=0 runs R32 merges in the fused cooperative kernel instead
   static const bool on = getenv("MZGPU_MERGE_KERNELS") == nullptr || atoi(getenv("MZGPU_MERGE_KERNELS")) != 0;
   return on;
 }
@@ -1604,6 +1605,7 @@ struct mzgpu_spine {
       // READERS in place of the output, until the main stream joins the merge (expand_readable).
       cudaEventRecord(ctx->ev_fork, ctx->main_stream);
       cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0);
+      mz_mid_forked(ctx);
       ctx->stream = ctx->side_stream;
       st = merge_batches(b1, b2, m.merge_since, &out);
       cudaEventRecord(ctx->ev_side, ctx->side_stream);
