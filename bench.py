@@ -555,10 +555,10 @@ def run_ours(args, rank, world, local_rank):
     ranked = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     top_name, top = ranked[0]
     # the roofline record is for the kernel with the largest share of the step among those whose algorithmic
-    # bytes are exact: launches whose row counts live on the device report bytes only where the kernel leaves
-    # a debug record (the fused seal / merge kernel; the merge-path tiles with host-known sizes); the probe
-    # chains' counts are device resident, so their bytes cover a fraction of the launches (see top_kernels)
-    exact = [kv for kv in ranked if kv[1]["bytes"] > 0 and "probe" not in kv[0] and "map_rows" not in kv[0]]
+    # bytes are exact under profiling: the fused seal / merge kernel leaves a debug record with its row count,
+    # the probe chains read their stream lengths back ahead of the launch (probe.cu), the merge-path tiles have
+    # host-known sizes; the stream maps of the multi-GPU path report bytes only for host-known counts
+    exact = [kv for kv in ranked if kv[1]["bytes"] > 0 and "map_rows" not in kv[0]]
     with_bytes = exact or [kv for kv in ranked if kv[1]["bytes"] > 0]
     dom_name, dom = with_bytes[0] if with_bytes else ranked[0]
     peak, peak_kind = measured_peak()

@@ -200,25 +200,44 @@ __global__ void __launch_bounds__(XT) k_p2p_scatter(const __grid_constant__ P2PJ
   __shared__ u32 sh_count[MZ_P2P_MAX_PEERS];
   __shared__ u64 sh_base[MZ_P2P_MAX_PEERS];
   __shared__ u32 s_last;
-  for (u64 i0 = (u64)blockIdx.x * XT; i0 < n; i0 += (u64)gridDim.x * XT) {
+  // P2P_IT rows per thread and round: the keys of a round are loaded together, one range per destination is
+  // reserved for all of them with a single global atomic, then the rows go out -- the per-round chain (key
+  // load, reservation, stores) is paid once per 1024 rows instead of once per 256 (25 us per launch for an
+  // 80 K-row buffer on 29 CTAs before: profiles/r02b_check_n1_n2_block_cache.log)
+  constexpr int P2P_IT = 4;
+  for (u64 i0 = (u64)blockIdx.x * XT * P2P_IT; i0 < n; i0 += (u64)gridDim.x * XT * P2P_IT) {
     __syncthreads();
     if (threadIdx.x < MZ_P2P_MAX_PEERS) sh_count[threadIdx.x] = 0;
     __syncthreads();
-    const u64 i = i0 + threadIdx.x;
-    u32 dest = 0, rank = 0;
-    if (i < n) {
-      dest = (u32)(fnv1a64(rows[i * nw]) % v.P);
-      rank = atomicAdd(&sh_count[dest], 1u);
+    u64 key[P2P_IT];
+    u32 dest[P2P_IT], rank[P2P_IT];
+#pragma unroll
+    for (int u = 0; u < P2P_IT; ++u) {
+      const u64 i = i0 + (u64)u * XT + threadIdx.x;
+      key[u] = i < n ? rows[i * nw] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < P2P_IT; ++u) {
+      const u64 i = i0 + (u64)u * XT + threadIdx.x;
+      dest[u] = 0;
+      rank[u] = 0;
+      if (i < n) {
+        dest[u] = (u32)(fnv1a64(key[u]) % v.P);
+        rank[u] = atomicAdd(&sh_count[dest[u]], 1u);
+      }
     }
     __syncthreads();
     if (threadIdx.x < v.P && sh_count[threadIdx.x])
       sh_base[threadIdx.x] = atomicAdd(&cursors[j * 16 + threadIdx.x], (unsigned long long)sh_count[threadIdx.x]);
     __syncthreads();
-    if (i < n) {
-      const u64 at = sh_base[dest] + rank;
+#pragma unroll
+    for (int u = 0; u < P2P_IT; ++u) {
+      const u64 i = i0 + (u64)u * XT + threadIdx.x;
+      if (i >= n) continue;
+      const u64 at = sh_base[dest[u]] + rank[u];
       if (at < v.L) {
         const u64* src = rows + i * nw;
-        u64* dst = (u64*)(v.peer[dest] + p2p_region_off(v, par, (u32)j, v.me)) + at * nw;
+        u64* dst = (u64*)(v.peer[dest[u]] + p2p_region_off(v, par, (u32)j, v.me)) + at * nw;
         for (int w = 0; w < nw; w += 2) {  // rows are 16-byte multiples
           const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(src + w);
           *reinterpret_cast<ulonglong2*>(dst + w) = x;

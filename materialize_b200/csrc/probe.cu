@@ -777,6 +777,13 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
   static thread_local ProbeMany m;  // large: kept off the stack
   memset(&m, 0, sizeof(m));
   const bool closure = jobs[0].pp->has_closure != 0;
+  if (ctx->profile) {
+    // per-kernel profiling: the algorithmic bytes of this launch need the actual stream lengths, which
+    // live on the device -- one read-back ahead of the launch (outside its event bracket)
+    bool pending = false;
+    for (int j = 0; j < k; ++j) pending = pending || jobs[j].n.p != nullptr;
+    if (pending) MZ_TRY(mz_resolve_counters(ctx));
+  }
   u64 lb_at = 0, max_grid = 1, bytes = 0, total_tiles = 0, chain_tiles[PROBE_MANY_MAX] = {};
   int nc = 0;
   for (int j = 0; j < k; ++j) {
@@ -811,7 +818,10 @@ int32_t mz_probe_async_many(mzgpu_ctx* ctx, int k, const ProbeJobHost* jobs) {
       const ProbeJobHost& J = jobs[m.chain[c].first + q];
       tiles += mz_probe_tiles(J.n_ub, J.trace->n_batches);
       rows_ub += J.n_ub;
-      if (J.n.p == nullptr) bytes += J.n.imm * (32 + 16 * J.trace->n_batches + 32 + (closure ? 32 : 40));
+      u64 rows_now = J.n.imm;
+      if (J.n.p != nullptr)  // (profiling only: the arena was just read back)
+        rows_now = (ctx->profile && J.n.p >= ctx->d_cnt && J.n.p < ctx->d_cnt + (size_t)MZ_CNT_BLOCKS * 4) ? ctx->h_cnt[J.n.p - ctx->d_cnt] : 0;
+      bytes += rows_now * (32 + 16 * J.trace->n_batches + 32 + (closure ? 32 : 40));
     }
     MZ_TRY(mz_lookback_begin_at(ctx, lb_at, tiles, &m.chain[c].lb));
     lb_at += tiles;
