@@ -8,7 +8,11 @@ pub mod batch;
 pub mod batcher;
 pub mod builder;
 pub mod column;
+pub mod correction;
+pub mod delta_join;
+pub mod exchange;
 pub mod linear_join;
+pub mod reduce;
 pub mod sys;
 pub mod trace;
 

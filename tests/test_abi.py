@@ -25,6 +25,26 @@ def test_every_declared_symbol_is_exported():
     assert set(names) == set(_ffi.SIGNATURES), set(names) ^ set(_ffi.SIGNATURES)
 
 
+def test_rust_shim_declares_every_entry_point():
+    """rust-shim/src/sys.rs (uncompiled: no Rust toolchain here) stays one to one with the header:
+    the same functions, each with the same number of arguments."""
+    src = open(os.path.join(ROOT, "include", "mzgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    c_args = {}
+    for name, args in re.findall(r"\b(mzgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        args = " ".join(args.split())
+        c_args[name] = 0 if args in ("", "void") else len(args.split(","))
+    rs = open(os.path.join(ROOT, "rust-shim", "src", "sys.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+    r_args = {}
+    for name, args in re.findall(r"pub fn (mzgpu_[a-z0-9_]+)\s*\(([^)]*)\)", rs):
+        args = " ".join(args.split())
+        r_args[name] = 0 if args == "" else len([a for a in args.split(",") if a.strip()])
+    assert set(c_args) == set(declared_functions())
+    assert set(r_args) == set(c_args), set(r_args) ^ set(c_args)
+    assert {n: r_args[n] for n in c_args} == c_args
+
+
 def test_row_layouts_match_header():
     from materialize_b200 import _ffi
 
