@@ -363,3 +363,43 @@ def test_oracle_sum_of_nulls_is_null(oracle):
     assert int(out["flags"][0]) & 1
     acc["non_nulls"] = 2
     assert int(oracle.finalize(acc, 0)["flags"][0]) & 1 == 0
+
+
+def test_oracle_topk_reproduces_sqllogictest_answers(oracle):
+    """Pins the oracle's TopK operator to reference-held known answers: the integer-encodable cases of
+    test/sqllogictest/topk.slt (tests/golden/sqllogictest_topk.json cites the lines).  A city is one
+    (key = state, val = pop << 8 | city) row: the operator orders a key's values, so the population leads the
+    word and the city rides in its low bits; NULL sorts above every population (DESC NULLS FIRST) or below
+    (DESC NULLS LAST), as `order_by=[#2{pop} desc nulls_first]` / `nulls_last` ask."""
+    import json
+    import os
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sqllogictest_topk.json")))
+    rows = fx["cities"]["rows"]
+    states = sorted({r[1] for r in rows})
+    names = [r[0] for r in rows]
+    for case in fx["per_group"]:
+        a = np.zeros(len(rows), dtype=oracle.R32)
+        for i, (name, state, pop) in enumerate(rows):
+            if pop is None:
+                pop = (1 << 40) - 1 if case["nulls_first"] else 0
+            a[i] = (states.index(state), (pop << 8) | names.index(name), 0, 1)
+        out = oracle.TopK(case["limit"], 0, case["descending"]).step(a, 1)
+        got = set()
+        for row in out.tolist():
+            assert row[4] == 0 and row[6] == 1, row  # no error row, every city once
+            got.add((states[row[0]], names[row[2] & 0xFF]))
+        assert got == {tuple(x) for x in case["answer"]}, case["name"]
+        assert len(out) == len(case["answer"])
+    for case in fx["global"]:
+        cur = np.zeros(len(case["t"]), dtype=oracle.R32)
+        cur["val"] = np.array(case["t"], dtype=np.uint64)
+        cur["diff"] = 1
+        for st in case["stages"]:
+            out = oracle.TopK(st["limit"], st["offset"], False).step(cur, 1)
+            cur = np.zeros(len(out), dtype=oracle.R32)
+            cur["val"] = np.array([row[2] for row in out.tolist()], dtype=np.uint64)
+            cur["diff"] = np.array([row[6] for row in out.tolist()], dtype=np.int64)
+        assert sorted(cur["val"].tolist()) == case["answer"], case["name"]
+        assert (cur["diff"] == 1).all()
+
