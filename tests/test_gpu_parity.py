@@ -359,6 +359,20 @@ def test_batch_merge_matches_oracle(mz, ctx, oracle):
         same(g.rows(), oracle.rows(oracle.R32, [tuple(r) for r in case["expected"]]))
 
 
+def test_batch_merge_long_collapsed_runs(mz, ctx, oracle):
+    """advance_by(since) collapsing hundreds / thousands of times of one (key, val): runs longer than a merge
+    tile's slack take k_mrg_tiles' single-thread walk and move tile boundaries across whole tiles; cancelling
+    runs drop out.  The cases live in tools/merge_long_runs_check.py (also a stand-alone GPU check)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "merge_long_runs_check", os.path.join(os.path.dirname(HERE), "tools", "merge_long_runs_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lines = []
+    assert mod.run(mz, ctx, oracle, log=lines.append), "\n".join(lines)
+
+
 # ----------------------------------------------------------- a6, a14
 def test_spine_structure_and_contents_match_oracle(mz, ctx, oracle):
     rng = np.random.default_rng(23)
